@@ -1,0 +1,19 @@
+#!/bin/bash
+# Builds libfunasr_b200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr"
+mkdir -p ../_build
+objs=""
+pids=""
+for f in fbank layernorm gemm_f32 gemm_tc attention_f32 fsmn cif decode_ops model; do
+  if [ ! -f ../_build/$f.o ] || [ $f.cu -nt ../_build/$f.o ] || [ common.cuh -nt ../_build/$f.o ] || [ kernels.h -nt ../_build/$f.o ] || [ ../../include/funasr_b200.h -nt ../_build/$f.o ]; then
+    ( $NVCC $FLAGS -c $f.cu -o ../_build/$f.o 2> ../_build/$f.ptxas.log || { cat ../_build/$f.ptxas.log; rm -f ../_build/$f.o; exit 1; } ) &
+    pids="$pids $!"
+  fi
+  objs="$objs ../_build/$f.o"
+done
+for p in $pids; do wait $p || exit 1; done
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libfunasr_b200.so $objs -lcudart
+echo "built $(cd ..; pwd)/libfunasr_b200.so"

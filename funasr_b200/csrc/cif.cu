@@ -1,0 +1,143 @@
+// CIF predictor tail: im2col for the k=3 conv, alpha head, tail threshold, fp64 prefix scan, fire detection and
+// the weight-integrate ("continuous integrate-and-fire") segment sums — CifPredictorV2.forward inference branch
+// (funasr/models/paraformer/cif_predictor.py:253-314), tail_process_fn (:414-446), cif_wo_hidden_v1 (:818-850)
+// and cif_v1 (:853-908).  No host synchronisation: fires are compacted on the device, the token count per
+// utterance is written to token_num and read by the host once per batch.
+//
+// Arithmetic follows the reference's rounding order where it decides integer outcomes: alpha prefix sums in
+// fp64 then cast to fp32 (:835), fires = (fire + ps) - floor(ps) (:846-847), per-channel fp32 running sum of
+// alpha*h with separate multiply and add (:878), frame = ((PH[t_k] - PH[t_{k-1}]) + rem_{k-1} h_{k-1}) - rem_k h_k (:896).
+#include "common.cuh"
+#include <math.h>
+
+namespace fa {
+
+// Xc[(b,t), k*D + c] = enc[b, t+k-1, c], zero outside [0, T)  (ConstantPad1d((1,1)) + Conv1d(k=3), :275-276)
+__global__ void __launch_bounds__(256)
+cif_im2col_kernel(const float* __restrict__ enc, int t_max, int d, float* __restrict__ xc, int64_t total4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int d4 = d >> 2;
+  const int c4 = (int)(i % d4);
+  const int64_t rk = i / d4;
+  const int k = (int)(rk % 3);
+  const int64_t row = rk / 3;
+  const int t = (int)(row % t_max) + k - 1;
+  float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t >= 0 && t < t_max) val = __ldg(reinterpret_cast<const float4*>(enc + (row + k - 1) * d) + c4);
+  reinterpret_cast<float4*>(xc)[i] = val;
+}
+
+// alpha[b,t] = relu(sigmoid(c . w + b0) * smooth - noise) * mask     (:280-285); one warp per row
+__global__ void __launch_bounds__(256)
+cif_alpha_kernel(const float* __restrict__ c, int d, const float* __restrict__ w, const float* __restrict__ b0,
+                 const int32_t* __restrict__ lens, int t_max, int64_t rows, float smooth, float noise,
+                 float* __restrict__ alpha_rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* cr = reinterpret_cast<const float4*>(c + row * d);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  float acc = 0.f;
+  for (int i = lane; i < (d >> 2); i += 32) {
+    const float4 a = __ldg(cr + i), ww = __ldg(w4 + i);
+    acc += (a.x * ww.x + a.y * ww.y) + (a.z * ww.z + a.w * ww.w);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const int b = (int)(row / t_max), t = (int)(row % t_max);
+    const float z = acc + __ldg(b0);
+    float a = 1.0f / (1.0f + expf(-z));
+    a = fmaxf(__fsub_rn(__fmul_rn(a, smooth), noise), 0.f);
+    alpha_rows[row] = t < lens[b] ? a : 0.f;
+  }
+}
+
+// One CTA per utterance, one thread per channel.
+//   phase 1 (thread 0): alpha' = [alpha, 0], alpha'[len] += tail; token_num = floor(sum alpha'); fp64 prefix
+//                       sums -> fires / remainders / fire ordinals into shared memory.
+//   phase 2 (all threads): channel-wise running sum of alpha'*h' over time, emitting one acoustic frame per fire.
+__global__ void __launch_bounds__(512)
+cif_fire_kernel(const float* __restrict__ enc, const float* __restrict__ alpha_rows, const int32_t* __restrict__ lens,
+                int t_max, int d, float tail, float* __restrict__ acoustic, int n_cap, int32_t* __restrict__ token_num,
+                float* __restrict__ alphas_out, float* __restrict__ peaks_out) {
+  extern __shared__ float sm[];
+  float* s_alpha = sm;                    // [T+1]
+  float* s_rem = sm + (t_max + 1);        // [T+1]
+  int* s_ord = reinterpret_cast<int*>(sm + 2 * (t_max + 1));  // [T+1] fire ordinal or -1
+  const int b = blockIdx.x;
+  const int T1 = t_max + 1;
+  const int len = min(lens[b], t_max);
+  for (int t = threadIdx.x; t < T1; t += blockDim.x) {
+    float a = t < t_max ? alpha_rows[(int64_t)b * t_max + t] : 0.f;
+    if (t == len) a = __fadd_rn(a, tail);           // mask_2 - mask_1 is 1 exactly at index len (:426-433)
+    s_alpha[t] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ps = 0.0;
+    float prev_floor = 0.f;
+    int ord = 0;
+    for (int t = 0; t < T1; ++t) {
+      ps += (double)s_alpha[t];                     // cumsum(dtype=float64) :835
+      const float psf = (float)ps;
+      const float fl = floorf(psf);
+      const bool fire = (fl - prev_floor) > 0.f;    // :838-845 (prefix_sum_floor - shifted floor, [:,0] := 0)
+      prev_floor = fl;
+      const float fires = __fsub_rn(__fadd_rn(fire ? 1.f : 0.f, psf), fl);   // :846-847
+      s_rem[t] = __fsub_rn(fires, floorf(fires));   // :889
+      s_ord[t] = fire ? ord++ : -1;
+      peaks_out[(int64_t)b * T1 + t] = fires;
+      alphas_out[(int64_t)b * T1 + t] = s_alpha[t];
+    }
+    // token_num = floor(alphas.sum(-1)) in fp32 (:443-444).  torch's vectorised fp32 sum is reproduced to within
+    // an ulp by rounding the exact (fp64) sum once.
+    token_num[b] = (int32_t)floorf((float)ps);
+  }
+  __syncthreads();
+  const float* hb = enc + (int64_t)b * t_max * d;
+  float* ob = acoustic + (int64_t)b * n_cap * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float acc = 0.f, prev_acc = 0.f, prev_rh = 0.f;
+    for (int t = 0; t < T1; ++t) {
+      const float h = t < t_max ? __ldg(hb + (int64_t)t * d + c) : 0.f;   // hidden gets one zero frame appended (:441-442)
+      acc = __fadd_rn(acc, __fmul_rn(s_alpha[t], h));                     // cumsum(alphas * hidden) :878
+      const int k = s_ord[t];
+      if (k >= 0) {
+        const float rh = __fmul_rn(s_rem[t], h);
+        if (k < n_cap) ob[(int64_t)k * d + c] = __fsub_rn(__fadd_rn(__fsub_rn(acc, prev_acc), prev_rh), rh);   // :896
+        prev_acc = acc;
+        prev_rh = rh;
+      }
+    }
+  }
+}
+
+int cif_im2col_launch(const float* enc, int64_t rows, int t_max, int d, float* xc, cudaStream_t st) {
+  const int64_t total4 = rows * 3 * (d / 4);
+  if (total4 <= 0) return FA_OK;
+  cif_im2col_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(enc, t_max, d, xc, total4);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+int cif_alpha_launch(const float* c, int d, const float* w, const float* b0, const int32_t* lens, int t_max,
+                     int64_t rows, float smooth, float noise, float* alpha_rows, cudaStream_t st) {
+  if (rows <= 0) return FA_OK;
+  cif_alpha_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(c, d, w, b0, lens, t_max, rows, smooth, noise, alpha_rows);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+int cif_fire_launch(const float* enc, const float* alpha_rows, const int32_t* lens, int batch, int t_max, int d,
+                    float tail, float* acoustic, int n_cap, int32_t* token_num, float* alphas, float* peaks,
+                    cudaStream_t st) {
+  const size_t smem = (size_t)3 * (t_max + 1) * sizeof(float);
+  if (smem > 200 * 1024) return FA_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) FA_CUDA_OK(cudaFuncSetAttribute(cif_fire_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cif_fire_kernel<<<batch, 512, smem, st>>>(enc, alpha_rows, lens, t_max, d, tail, acoustic, n_cap, token_num, alphas, peaks);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+}  // namespace fa

@@ -1,0 +1,68 @@
+// Shared helpers for the funasr_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include "../../include/funasr_b200.h"
+
+namespace fa {
+
+extern std::atomic<unsigned long long> g_launch_count;
+
+inline void count_launch(unsigned n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+// Returns FA_ERR_CUDA from the enclosing function when the launch that just happened failed.
+#define FA_CHECK_LAUNCH()                                        \
+  do {                                                           \
+    ::fa::count_launch();                                        \
+    cudaError_t _e = cudaGetLastError();                         \
+    if (_e != cudaSuccess) return FA_ERR_CUDA;                   \
+  } while (0)
+
+#define FA_CUDA_OK(expr)                                         \
+  do {                                                           \
+    cudaError_t _e = (expr);                                     \
+    if (_e != cudaSuccess) return FA_ERR_CUDA;                   \
+  } while (0)
+
+#define FA_RETURN_IF_ERR(expr)                                   \
+  do {                                                           \
+    int _s = (expr);                                             \
+    if (_s != FA_OK) return _s;                                  \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+  char* base;
+  size_t cap, off;
+  Arena(void* p, size_t bytes) : base(static_cast<char*>(p)), cap(bytes), off(0) {}
+  template <typename T>
+  T* take(size_t n) {
+    size_t o = align_up(off, 256);
+    size_t need = n * sizeof(T);
+    if (base == nullptr || o + need > cap) { off = cap + 1; return nullptr; }
+    off = o + need;
+    return reinterpret_cast<T*>(base + o);
+  }
+  bool ok() const { return off <= cap; }
+};
+// Same arithmetic as Arena::take, for the *_workspace_bytes queries.
+struct ArenaSizer {
+  size_t off = 0;
+  void take(size_t bytes) { off = align_up(off, 256) + bytes; }
+};
+
+}  // namespace fa

@@ -1,0 +1,136 @@
+// Output-side kernels of the greedy decode: row arg-max with log-sum-exp (log_softmax value of the arg-max,
+// paraformer/model.py:345,642-644), optional in-place log_softmax of the full logits for parity checks, the
+// {blank,sos,eos} filter (:655-666), and the fp32 -> bf16 plane split used by the tcgen05 GEMM weights.
+#include "common.cuh"
+#include <cuda_bf16.h>
+#include <math.h>
+
+namespace fa {
+
+// One CTA (256 threads) per row of logits [rows, vocab].  Ties resolve to the lowest index (torch.argmax).
+__global__ void __launch_bounds__(256)
+argmax_lse_kernel(float* __restrict__ logits, int vocab, int64_t ld, int32_t* __restrict__ ids,
+                  float* __restrict__ best_logp, int write_log_softmax) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ float s_sum[8];
+  const int64_t row = blockIdx.x;
+  float* x = logits + row * ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+    const float v = x[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+  __syncthreads();
+  best = s_val[0]; bi = s_idx[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) {
+    if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+  }
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < vocab; i += blockDim.x) sum += expf(x[i] - best);
+  sum = warp_sum(sum);
+  if (lane == 0) s_sum[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += s_sum[w];
+  // torch log_softmax: (x - max) - log(sum exp(x - max)); arg-max is taken over those rounded values (model.py:642),
+  // so an element whose log-prob rounds to the same float as the maximum's wins if its index is lower.
+  const float lsum = logf(sum);
+  const float best_lp = __fsub_rn(0.f, lsum);
+  int tie = bi;
+  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+    const float lp = __fsub_rn(__fsub_rn(x[i], best), lsum);
+    if (lp == best_lp && i < tie) tie = i;
+    if (write_log_softmax) x[i] = lp;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tie = min(tie, __shfl_xor_sync(0xffffffffu, tie, o));
+  __syncthreads();
+  if (lane == 0) s_idx[warp] = tie;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = s_idx[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t = min(t, s_idx[w]);
+    ids[row] = t;
+    best_logp[row] = best_lp;
+  }
+}
+
+// One warp per utterance: ordered compaction of ids not in {blank, sos, eos}.
+__global__ void greedy_filter_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ tok_lens, int n_max,
+                                     int sos, int eos, int blank, int32_t* __restrict__ out_ids,
+                                     int32_t* __restrict__ out_lens) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int len = min(tok_lens[b], n_max);
+  int count = 0;
+  for (int base = 0; base < n_max; base += 32) {
+    const int k = base + lane;
+    const int id = k < len ? ids[(int64_t)b * n_max + k] : -1;
+    const bool keep = k < len && id != sos && id != eos && id != blank;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) out_ids[(int64_t)b * n_max + count + __popc(m & ((1u << lane) - 1))] = id;
+    count += __popc(m);
+  }
+  for (int k = count + lane; k < n_max; k += 32) out_ids[(int64_t)b * n_max + k] = -1;
+  if (lane == 0) out_lens[b] = count;
+}
+
+// x = hi + mid + lo with hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid); planes [3][rows][cols_pad].
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, int cols_pad,
+                  __nv_bfloat16* __restrict__ planes) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = rows * cols_pad;
+  if (i >= total) return;
+  const int64_t r = i / cols_pad;
+  const int c = (int)(i - r * cols_pad);
+  const float x = c < cols ? src[r * ld + c] : 0.f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h);
+  const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(m);
+  planes[i] = h;
+  planes[total + i] = m;
+  planes[2 * total + i] = __float2bfloat16_rn(r2);
+}
+
+int argmax_lse_launch(float* logits, int64_t rows, int vocab, int64_t ld, int32_t* ids, float* best_logp,
+                      int write_log_softmax, cudaStream_t st) {
+  if (rows <= 0) return FA_OK;
+  argmax_lse_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, vocab, ld, ids, best_logp, write_log_softmax);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+}  // namespace fa
+
+extern "C" int fa_greedy_filter(const int32_t* argmax_ids, const int32_t* tok_lens, int32_t batch, int32_t n_max,
+                                int32_t sos, int32_t eos, int32_t blank, int32_t* out_ids, int32_t* out_lens,
+                                fa_stream_t stream) {
+  if (!argmax_ids || !tok_lens || !out_ids || !out_lens || batch <= 0 || n_max <= 0) return FA_ERR_ARG;
+  fa::greedy_filter_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(argmax_ids, tok_lens, n_max, sos, eos, blank, out_ids, out_lens);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+extern "C" int fa_split_bf16(const float* src, int64_t ld_src, int64_t rows, int32_t cols, int32_t cols_pad,
+                             void* planes, fa_stream_t stream) {
+  if (!src || !planes || rows <= 0 || cols <= 0 || cols_pad < cols) return FA_ERR_ARG;
+  const int64_t total = rows * cols_pad;
+  fa::split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      src, ld_src, rows, cols, cols_pad, reinterpret_cast<__nv_bfloat16*>(planes));
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}

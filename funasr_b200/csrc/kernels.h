@@ -1,0 +1,31 @@
+// Internal launch helpers shared between translation units (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace fa {
+
+int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, const float* pe_inv, float xscale,
+                     int rows_per_batch, cudaStream_t st);
+int gemm_f32_launch(const float* A, int64_t lda, int64_t M, const float* W, int N, int K, const float* bias, int relu,
+                    const float* r1, int64_t ldr1, const float* r2, int64_t ldr2, float* C, int64_t ldc,
+                    cudaStream_t st);
+// tcgen05 bf16-split GEMM (gemm_tc.cu)
+size_t gemm_tc_scratch_bytes(int64_t max_rows, int max_k, int mode);
+int gemm_tc_launch(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, const float* r1,
+                   int64_t ld1, const float* r2, int64_t ld2, float* y, int64_t ldy, int mode, Arena* scratch,
+                   cudaStream_t st);
+int attention_f32_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                         const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
+                         cudaStream_t st);
+int fsmn_launch(const float* v, int64_t ldv, const int32_t* lens, int batch, int t_max, int channels, const float* w,
+                int ksize, const float* res, int64_t ldr, float* out, int64_t ldo, cudaStream_t st);
+int cif_im2col_launch(const float* enc, int64_t rows, int t_max, int d, float* xc, cudaStream_t st);
+int cif_alpha_launch(const float* c, int d, const float* w, const float* b0, const int32_t* lens, int t_max,
+                     int64_t rows, float smooth, float noise, float* alpha_rows, cudaStream_t st);
+int cif_fire_launch(const float* enc, const float* alpha_rows, const int32_t* lens, int batch, int t_max, int d,
+                    float tail, float* acoustic, int n_cap, int32_t* token_num, float* alphas, float* peaks,
+                    cudaStream_t st);
+int argmax_lse_launch(float* logits, int64_t rows, int vocab, int64_t ld, int32_t* ids, float* best_logp,
+                      int write_log_softmax, cudaStream_t st);
+
+}  // namespace fa

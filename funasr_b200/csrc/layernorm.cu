@@ -1,0 +1,101 @@
+// Row LayerNorm (funasr/models/transformer/layer_norm.py:13-39, eps = 1e-12), one warp per row, the row
+// held in registers (two-pass mean / variance in fp32), float4 loads and stores.
+// Optional fused prologue for the first encoder layer: x*sqrt(d_model) + sinusoidal position encoding
+// (SANMEncoder.forward encoder.py:409,428; SinusoidalPositionEncoder embedding.py:396-432).
+// HBM-bound: algorithmic bytes = 8 B per element (read + write).
+#include "common.cuh"
+
+namespace fa {
+
+template <int NV>  // float4 per lane (row length <= 128*NV)
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ g,
+                 const float* __restrict__ bta, float eps, float* y,   // x may alias y (in-place)
+                 const float* __restrict__ pe_inv, float xscale, int rows_per_batch) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = n >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * n);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    v[i] = c4 < nvec ? xr[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (pe_inv != nullptr) {
+    const float pos = (float)((int)(row % rows_per_batch) + 1);
+    const int half = n >> 1;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = lane + 32 * i;
+      if (c4 < nvec) {
+        float* e = reinterpret_cast<float*>(&v[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * c4 + k;
+          const float pe = c < half ? sinf(__fmul_rn(pos, __ldg(pe_inv + c))) : cosf(__fmul_rn(pos, __ldg(pe_inv + c - half)));
+          e[k] = __fadd_rn(__fmul_rn(e[k], xscale), pe);
+        }
+      }
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(sum) / (float)n;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    if (c4 < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)n + eps);
+  float4* yr = reinterpret_cast<float4*>(y + row * n);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* b4 = reinterpret_cast<const float4*>(bta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    if (c4 < nvec) {
+      const float4 gg = __ldg(g4 + c4), bb = __ldg(b4 + c4);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * gg.x + bb.x;
+      o.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+      o.z = (v[i].z - mean) * rstd * gg.z + bb.z;
+      o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+      yr[c4] = o;
+    }
+  }
+}
+
+int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, const float* pe_inv, float xscale,
+                     int rows_per_batch, cudaStream_t st) {
+  if (rows <= 0) return FA_OK;
+  if (!x || !y || !nm.g || !nm.b) return FA_ERR_ARG;
+  const int n = nm.n;
+  if (n <= 0 || (n & 3) || n > 2048) return FA_ERR_UNSUPPORTED;
+  const int need = (n / 4 + 31) / 32;
+  const unsigned blocks = (unsigned)((rows + 7) / 8);
+#define FA_LN_CASE(NV)                                                                                       \
+  layernorm_kernel<NV><<<blocks, 256, 0, st>>>(x, rows, n, nm.g, nm.b, nm.eps, y, pe_inv, xscale,           \
+                                               rows_per_batch > 0 ? rows_per_batch : 1)
+  if (need <= 4) FA_LN_CASE(4);
+  else if (need <= 5) FA_LN_CASE(5);
+  else if (need <= 8) FA_LN_CASE(8);
+  else FA_LN_CASE(16);
+#undef FA_LN_CASE
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+}  // namespace fa
+
+extern "C" int fa_layernorm(const float* x, int64_t rows, const FaNorm* norm, float* y, const float* pe_inv,
+                            float xscale, int32_t rows_per_batch, fa_stream_t stream) {
+  if (!norm) return FA_ERR_ARG;
+  return fa::layernorm_launch(x, rows, *norm, y, pe_inv, xscale, rows_per_batch, (cudaStream_t)stream);
+}

@@ -1,0 +1,241 @@
+// Model-level C-ABI entry points: the kernel sequences of SANMEncoder.forward, CifPredictorV2.forward and
+// ParaformerSANMDecoder.forward (+ greedy arg-max), stream-ordered over a caller-provided workspace.
+#include "common.cuh"
+#include "kernels.h"
+#include <string.h>
+
+namespace fa {
+
+std::atomic<unsigned long long> g_launch_count{0};
+
+static int linear(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
+                  const float* r2, int64_t ld2, float* y, int64_t ldy, int mode, Arena* scratch, cudaStream_t st) {
+  if (!lin.w) return FA_ERR_ARG;
+  if (mode == FA_GEMM_F32_SIMT)
+    return gemm_f32_launch(x, ldx, rows, lin.w, lin.out_f, lin.in_f, lin.b, relu, r1, ld1, r2, ld2, y, ldy, st);
+  return gemm_tc_launch(x, ldx, rows, lin, relu, r1, ld1, r2, ld2, y, ldy, mode, scratch, st);
+}
+
+// ------------------------------------------------------------------------------------------------ encoder
+struct EncPlan {
+  size_t u, qkv, mem, ctx, xa, xb, h, scratch;
+};
+static size_t enc_plan(int64_t M, int din, int mode, EncPlan* p) {
+  ArenaSizer s;
+  s.take(M * (size_t)din * 4);   // u
+  s.take(M * 1536ull * 4);       // qkv
+  s.take(M * 512ull * 4);        // mem
+  s.take(M * 512ull * 4);        // ctx
+  s.take(M * 512ull * 4);        // xa
+  s.take(M * 512ull * 4);        // xb
+  s.take(M * 2048ull * 4);       // h
+  s.take(gemm_tc_scratch_bytes(M, 2048, mode));
+  (void)p;
+  return s.off + 256;
+}
+
+}  // namespace fa
+
+using namespace fa;
+
+extern "C" size_t fa_sanm_encoder_workspace_bytes(int32_t batch, int32_t t_max, int32_t gemm_mode) {
+  return enc_plan((int64_t)batch * t_max, 560, gemm_mode, nullptr);
+}
+
+extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats, const int32_t* lens, int32_t batch,
+                                       int32_t t_max, float* out, int32_t gemm_mode, void* workspace, size_t ws_bytes,
+                                       fa_stream_t stream) {
+  if (!enc || !enc->layers || !feats || !lens || !out || batch <= 0 || t_max <= 0 || enc->n_layers < 1) return FA_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = (int64_t)batch * t_max;
+  const int D = enc->after_norm.n;
+  const int din = enc->layers[0].norm1.n;
+  if (D != 512 || enc->heads * 128 != D || din > 560) return FA_ERR_UNSUPPORTED;
+  Arena a(workspace, ws_bytes);
+  float* u = a.take<float>(M * (size_t)560);
+  float* qkv = a.take<float>(M * 1536ull);
+  float* mem = a.take<float>(M * 512ull);
+  float* ctx = a.take<float>(M * 512ull);
+  float* xa = a.take<float>(M * 512ull);
+  float* xb = a.take<float>(M * 512ull);
+  float* h = a.take<float>(M * 2048ull);
+  const size_t sb = gemm_tc_scratch_bytes(M, 2048, gemm_mode);
+  char* sp = a.take<char>(sb);
+  if (!a.ok()) return FA_ERR_WORKSPACE;
+  Arena scratch(sp, sb);
+
+  const float* x = nullptr;  // residual stream (undefined before layer 0: in_size != size -> no residual)
+  for (int l = 0; l < enc->n_layers; ++l) {
+    const FaEncLayer& L = enc->layers[l];
+    const int in = L.norm1.n;
+    if (L.qkv.in_f != in || L.qkv.out_f != 3 * D || L.w1.in_f != D || L.w2.out_f != D) return FA_ERR_ARG;
+    // x = x*sqrt(D) + PE is folded into the first LayerNorm (encoder.py:409,428)
+    if (l == 0) {
+      FA_RETURN_IF_ERR(layernorm_launch(feats, M, L.norm1, u, enc->pe_inv_timescales, sqrtf((float)D), t_max, st));
+    } else {
+      if (in != D) return FA_ERR_UNSUPPORTED;
+      FA_RETURN_IF_ERR(layernorm_launch(x, M, L.norm1, u, nullptr, 1.f, t_max, st));
+    }
+    FA_RETURN_IF_ERR(linear(u, in, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, gemm_mode, &scratch, st));
+    FA_RETURN_IF_ERR(fsmn_launch(qkv + 2 * D, 3 * D, lens, batch, t_max, D, L.fsmn_w, enc->fsmn_k, nullptr, 0, mem, D, st));
+    FA_RETURN_IF_ERR(attention_f32_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, t_max,
+                                          t_max, ctx, D, st));
+    // x2 = (residual if in_size == size) + (linear_out(ctx) + fsmn_memory)     encoder.py:120-137, attention.py:327
+    float* x2 = (x == xa) ? xb : xa;
+    FA_RETURN_IF_ERR(linear(ctx, D, M, L.out, 0, mem, D, (in == D) ? x : nullptr, D, x2, D, gemm_mode, &scratch, st));
+    FA_RETURN_IF_ERR(layernorm_launch(x2, M, L.norm2, u, nullptr, 1.f, t_max, st));
+    FA_RETURN_IF_ERR(linear(u, D, M, L.w1, 1, nullptr, 0, nullptr, 0, h, L.w1.out_f, gemm_mode, &scratch, st));
+    float* x3 = (x2 == xa) ? xb : xa;
+    FA_RETURN_IF_ERR(linear(h, L.w1.out_f, M, L.w2, 0, x2, D, nullptr, 0, x3, D, gemm_mode, &scratch, st));
+    x = x3;
+  }
+  return layernorm_launch(x, M, enc->after_norm, out, nullptr, 1.f, t_max, st);
+}
+
+// ---------------------------------------------------------------------------------------------- predictor
+extern "C" size_t fa_cif_predictor_workspace_bytes(int32_t batch, int32_t t_max, int32_t gemm_mode) {
+  const int64_t M = (int64_t)batch * t_max;
+  ArenaSizer s;
+  s.take(M * 1536ull * 4);
+  s.take(M * 512ull * 4);
+  s.take(M * 4ull);
+  s.take(gemm_tc_scratch_bytes(M, 1536, gemm_mode));
+  return s.off + 256;
+}
+
+extern "C" int fa_cif_predictor_forward(const FaPredictor* pred, const float* enc, const int32_t* lens, int32_t batch,
+                                        int32_t t_max, float* acoustic, int32_t n_cap, int32_t* token_num,
+                                        float* alphas, float* peaks, int32_t gemm_mode, void* workspace, size_t ws_bytes,
+                                        fa_stream_t stream) {
+  if (!pred || !enc || !lens || !acoustic || !token_num || !alphas || !peaks || batch <= 0 || t_max <= 0 || n_cap <= 0)
+    return FA_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = 512;
+  if (pred->conv.out_f != D || pred->conv.in_f != 3 * D) return FA_ERR_UNSUPPORTED;
+  const int64_t M = (int64_t)batch * t_max;
+  Arena a(workspace, ws_bytes);
+  float* xc = a.take<float>(M * 1536ull);
+  float* c = a.take<float>(M * 512ull);
+  float* alpha_rows = a.take<float>(M);
+  const size_t sb = gemm_tc_scratch_bytes(M, 1536, gemm_mode);
+  char* sp = a.take<char>(sb);
+  if (!a.ok()) return FA_ERR_WORKSPACE;
+  Arena scratch(sp, sb);
+  FA_RETURN_IF_ERR(cif_im2col_launch(enc, M, t_max, D, xc, st));
+  FA_RETURN_IF_ERR(linear(xc, 3 * D, M, pred->conv, 1, nullptr, 0, nullptr, 0, c, D, gemm_mode, &scratch, st));
+  FA_RETURN_IF_ERR(cif_alpha_launch(c, D, pred->out_w, pred->out_b, lens, t_max, M, pred->smooth_factor,
+                                    pred->noise_threshold, alpha_rows, st));
+  FA_CUDA_OK(cudaMemsetAsync(acoustic, 0, (size_t)batch * n_cap * D * sizeof(float), st));
+  return cif_fire_launch(enc, alpha_rows, lens, batch, t_max, D, pred->tail_threshold, acoustic, n_cap, token_num, alphas,
+                         peaks, st);
+}
+
+// ------------------------------------------------------------------------------------------------ decoder
+static size_t dec_plan(int64_t Mq, int64_t Mk, int vocab, int mode) {
+  ArenaSizer s;
+  s.take(Mq * 512ull * 4);   // ya
+  s.take(Mq * 512ull * 4);   // yb
+  s.take(Mq * 512ull * 4);   // t1
+  s.take(Mq * 2048ull * 4);  // hq
+  s.take(Mq * 512ull * 4);   // f
+  s.take(Mq * 512ull * 4);   // qd
+  s.take(Mq * 512ull * 4);   // ctx
+  s.take(Mk * 1024ull * 4);  // kv
+  s.take(Mq * (size_t)vocab * 4);  // logits (used when the caller passes none)
+  s.take(gemm_tc_scratch_bytes(Mq > Mk ? Mq : Mk, 2048, mode));
+  return s.off + 256;
+}
+
+extern "C" size_t fa_paraformer_decoder_workspace_bytes(int32_t batch, int32_t t_max, int32_t n_max, int32_t vocab,
+                                                        int32_t gemm_mode) {
+  return dec_plan((int64_t)batch * n_max, (int64_t)batch * t_max, vocab, gemm_mode);
+}
+
+static int dec_ffn(const FaDecLayer& L, const float* y, int64_t Mq, float* t1, float* hq, float* f, int mode,
+                   Arena* scratch, cudaStream_t st) {
+  // f = w_2( LN_2048( relu( w_1( LN1(y) ) ) ) )   decoder.py:97-100, sanm/positionwise_feed_forward.py:33
+  FA_RETURN_IF_ERR(layernorm_launch(y, Mq, L.norm1, t1, nullptr, 1.f, 1, st));
+  FA_RETURN_IF_ERR(linear(t1, 512, Mq, L.ffn_w1, 1, nullptr, 0, nullptr, 0, hq, L.ffn_w1.out_f, mode, scratch, st));
+  FA_RETURN_IF_ERR(layernorm_launch(hq, Mq, L.ffn_norm, hq, nullptr, 1.f, 1, st));
+  return linear(hq, L.ffn_w1.out_f, Mq, L.ffn_w2, 0, nullptr, 0, nullptr, 0, f, 512, mode, scratch, st);
+}
+
+extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* enc, const int32_t* enc_lens,
+                                             int32_t batch, int32_t t_max, const float* acoustic,
+                                             int64_t ld_acoustic_rows, const int32_t* tok_lens, int32_t n_max,
+                                             int32_t* argmax_ids, float* argmax_logp, float* logits, int32_t log_softmax,
+                                             int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream) {
+  if (!dec || !enc || !enc_lens || !acoustic || !tok_lens || !argmax_ids || !argmax_logp || batch <= 0 || t_max <= 0 ||
+      n_max <= 0 || ld_acoustic_rows < n_max)
+    return FA_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = 512;
+  if (dec->after_norm.n != D || dec->heads * 128 != D) return FA_ERR_UNSUPPORTED;
+  const int64_t Mq = (int64_t)batch * n_max, Mk = (int64_t)batch * t_max;
+  const int V = dec->vocab;
+  Arena a(workspace, ws_bytes);
+  float* ya = a.take<float>(Mq * 512ull);
+  float* yb = a.take<float>(Mq * 512ull);
+  float* t1 = a.take<float>(Mq * 512ull);
+  float* hq = a.take<float>(Mq * 2048ull);
+  float* f = a.take<float>(Mq * 512ull);
+  float* qd = a.take<float>(Mq * 512ull);
+  float* ctx = a.take<float>(Mq * 512ull);
+  float* kv = a.take<float>(Mk * 1024ull);
+  float* lg = a.take<float>(Mq * (size_t)V);
+  const size_t sb = gemm_tc_scratch_bytes(Mq > Mk ? Mq : Mk, 2048, gemm_mode);
+  char* sp = a.take<char>(sb);
+  if (!a.ok()) return FA_ERR_WORKSPACE;
+  Arena scratch(sp, sb);
+  if (logits) lg = logits;
+
+  // tgt = acoustic[:, :n_max]  (decoder.py:424)
+  FA_CUDA_OK(cudaMemcpy2DAsync(ya, (size_t)n_max * D * 4, acoustic, (size_t)ld_acoustic_rows * D * 4, (size_t)n_max * D * 4,
+                               batch, cudaMemcpyDeviceToDevice, st));
+  fa::count_launch();
+  float* y = ya;
+  for (int l = 0; l < dec->n_layers; ++l) {
+    const FaDecLayer& L = dec->layers[l];
+    FA_RETURN_IF_ERR(dec_ffn(L, y, Mq, t1, hq, f, gemm_mode, &scratch, st));
+    // x = residual + fsmn(LN2(f), tgt_mask)     decoder.py:103-107
+    FA_RETURN_IF_ERR(layernorm_launch(f, Mq, L.norm2, t1, nullptr, 1.f, 1, st));
+    float* x2 = (y == ya) ? yb : ya;
+    FA_RETURN_IF_ERR(fsmn_launch(t1, D, tok_lens, batch, n_max, D, L.fsmn_w, dec->fsmn_k, y, D, x2, D, st));
+    // x = residual + src_attn(LN3(x), memory)    decoder.py:109-118, attention.py:796-813
+    FA_RETURN_IF_ERR(layernorm_launch(x2, Mq, L.norm3, t1, nullptr, 1.f, 1, st));
+    FA_RETURN_IF_ERR(linear(t1, D, Mq, L.q, 0, nullptr, 0, nullptr, 0, qd, D, gemm_mode, &scratch, st));
+    FA_RETURN_IF_ERR(linear(enc, D, Mk, L.kv, 0, nullptr, 0, nullptr, 0, kv, 2 * D, gemm_mode, &scratch, st));
+    FA_RETURN_IF_ERR(attention_f32_launch(qd, D, kv, 2 * D, kv + D, 2 * D, enc_lens, batch, dec->heads, n_max, t_max, ctx,
+                                          D, st));
+    float* y2 = (x2 == ya) ? yb : ya;
+    FA_RETURN_IF_ERR(linear(ctx, D, Mq, L.out, 0, x2, D, nullptr, 0, y2, D, gemm_mode, &scratch, st));
+    y = y2;
+  }
+  // decoders3: FFN only, no residual (decoder.py:97-102,121); after_norm; output_layer
+  FA_RETURN_IF_ERR(dec_ffn(dec->last, y, Mq, t1, hq, f, gemm_mode, &scratch, st));
+  FA_RETURN_IF_ERR(layernorm_launch(f, Mq, dec->after_norm, t1, nullptr, 1.f, 1, st));
+  FA_RETURN_IF_ERR(linear(t1, D, Mq, dec->output, 0, nullptr, 0, nullptr, 0, lg, V, gemm_mode, &scratch, st));
+  return argmax_lse_launch(lg, Mq, V, V, argmax_ids, argmax_logp, (logits && log_softmax) ? 1 : 0, st);
+}
+
+// ------------------------------------------------------------------------------------------ op-level + info
+extern "C" int fa_linear(const float* x, int64_t ldx, int64_t rows, const FaLinear* lin, int32_t relu, const float* res1,
+                         int64_t ld_res1, const float* res2, int64_t ld_res2, float* y, int64_t ldy, int32_t gemm_mode,
+                         void* workspace, size_t ws_bytes, fa_stream_t stream) {
+  if (!lin || !x || !y) return FA_ERR_ARG;
+  Arena scratch(workspace, ws_bytes);
+  return linear(x, ldx, rows, *lin, relu, res1, ld_res1, res2, ld_res2, y, ldy, gemm_mode, &scratch, (cudaStream_t)stream);
+}
+
+extern "C" const char* fa_version(void) { return "funasr_b200 0.1.0 (sm_100a)"; }
+extern "C" uint64_t fa_launch_count(void) { return (uint64_t)fa::g_launch_count.load(); }
+extern "C" const char* fa_status_string(int status) {
+  switch (status) {
+    case FA_OK: return "ok";
+    case FA_ERR_ARG: return "bad argument";
+    case FA_ERR_CUDA: return "CUDA error";
+    case FA_ERR_WORKSPACE: return "workspace too small";
+    case FA_ERR_UNSUPPORTED: return "unsupported shape";
+    default: return "unknown";
+  }
+}

@@ -1,0 +1,167 @@
+"""Seeded synthetic Paraformer weights, waveforms and configs.
+
+No pretrained Paraformer weights exist offline, so parity and the
+benchmark run on a deterministic, well-conditioned synthetic ``state_dict`` whose
+key names and shapes are exactly the reference's (SURVEY.md §8 row a21:
+``encoder.encoders0.0.self_attn.linear_q_k_v.weight`` ...), so the very same dict
+loads into the reference ``Paraformer`` through ``load_pretrained_model`` and into
+this backend.  Everything is generated on the CPU with ``torch.Generator`` so it
+is identical on every machine with this torch version.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from dataclasses import dataclass, asdict
+
+import torch
+
+
+@dataclass(frozen=True)
+class ParaformerConfig:
+    """Architecture constants of Paraformer-large (funasr/models/paraformer/template.yaml:9-66)."""
+    n_mels: int = 80
+    lfr_m: int = 7
+    lfr_n: int = 6
+    d_model: int = 512
+    heads: int = 4
+    ffn: int = 2048
+    enc_layers: int = 50      # encoder_conf.num_blocks (1 x encoders0 + 49 x encoders)
+    dec_layers: int = 16      # decoder_conf.num_blocks == att_layer_num
+    kernel: int = 11          # FSMN kernel_size, sanm_shfit = 0
+    vocab: int = 8404
+    cif_threshold: float = 1.0
+    tail_threshold: float = 0.45
+    ln_eps: float = 1e-12     # funasr/models/transformer/layer_norm.py:24
+
+    @property
+    def feat_dim(self) -> int:
+        return self.n_mels * self.lfr_m
+
+    def to_dict(self):
+        return asdict(self)
+
+
+PARAFORMER_LARGE = ParaformerConfig()
+# Same operator shapes, fewer layers: the oracle finishes in well under a second.
+PARAFORMER_TINY = ParaformerConfig(enc_layers=3, dec_layers=2, vocab=1000)
+
+
+def _randn(g, *shape, std=1.0):
+    return torch.randn(*shape, generator=g, dtype=torch.float32) * std
+
+
+def make_state_dict(cfg: ParaformerConfig = PARAFORMER_LARGE, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Well-conditioned synthetic weights under the reference's parameter names."""
+    g = torch.Generator().manual_seed(1000003 * seed + 17)
+    D, F, V, K, Din = cfg.d_model, cfg.ffn, cfg.vocab, cfg.kernel, cfg.feat_dim
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+
+    def linear(prefix, out_f, in_f, bias=True, gain=1.0):
+        sd[prefix + ".weight"] = _randn(g, out_f, in_f, std=gain / math.sqrt(in_f))
+        if bias:
+            sd[prefix + ".bias"] = _randn(g, out_f, std=0.02)
+
+    def norm(prefix, n):
+        sd[prefix + ".weight"] = 1.0 + _randn(g, n, std=0.1)
+        sd[prefix + ".bias"] = _randn(g, n, std=0.05)
+
+    # Gains chosen so that (a) frames/tokens stay distinct through 50+16 layers (diverse greedy ids) and (b) the
+    # network is well conditioned: 1e-6 relative input noise moves log-probs by ~5e-4 while the smallest top-1/top-2
+    # margin is ~1e-2, so greedy ids are a meaningful bit-exact parity target.
+    def enc_layer(prefix, in_size):
+        res = 0.7 if in_size != D else 0.3
+        linear(prefix + ".self_attn.linear_out", D, D, gain=res)
+        linear(prefix + ".self_attn.linear_q_k_v", 3 * D, in_size, gain=1.5)
+        sd[prefix + ".self_attn.linear_q_k_v.weight"][: 2 * D] *= 1.5   # sharper q.k scores -> frame-specific context
+        sd[prefix + ".self_attn.fsmn_block.weight"] = _randn(g, D, 1, K, std=0.15)
+        linear(prefix + ".feed_forward.w_1", F, D)
+        linear(prefix + ".feed_forward.w_2", D, F, gain=res)
+        norm(prefix + ".norm1", in_size)
+        norm(prefix + ".norm2", D)
+
+    enc_layer("encoder.encoders0.0", Din)
+    for i in range(cfg.enc_layers - 1):
+        enc_layer("encoder.encoders.%d" % i, D)
+    norm("encoder.after_norm", D)
+
+    # CIF predictor (paraformer/cif_predictor.py:241-242)
+    sd["predictor.cif_conv1d.weight"] = _randn(g, D, D, 3, std=1.0 / math.sqrt(3 * D))
+    sd["predictor.cif_conv1d.bias"] = _randn(g, D, std=0.02)
+    sd["predictor.cif_output.weight"] = _randn(g, 1, D, std=1.2 / math.sqrt(D))
+    # sigmoid(-1.6) ~ 0.17 per 60 ms LFR frame -> a few tokens per second
+    sd["predictor.cif_output.bias"] = torch.full((1,), -1.6)
+
+    sd["decoder.embed.0.weight"] = _randn(g, V, D, std=0.1)  # unused at inference
+    norm("decoder.after_norm", D)
+    linear("decoder.output_layer", V, D, gain=3.0)
+
+    def dec_ffn(prefix, res=0.3):
+        linear(prefix + ".feed_forward.w_1", F, D)
+        sd[prefix + ".feed_forward.w_2.weight"] = _randn(g, D, F, std=res / math.sqrt(F))
+        norm(prefix + ".feed_forward.norm", F)
+
+    for i in range(cfg.dec_layers):
+        p = "decoder.decoders.%d" % i
+        dec_ffn(p)
+        sd[p + ".self_attn.fsmn_block.weight"] = _randn(g, D, 1, K, std=0.15)
+        linear(p + ".src_attn.linear_q", D, D, gain=1.5)
+        linear(p + ".src_attn.linear_k_v", 2 * D, D, gain=1.5)
+        linear(p + ".src_attn.linear_out", D, D, gain=0.3)
+        norm(p + ".norm1", D)
+        norm(p + ".norm2", D)
+        norm(p + ".norm3", D)
+    dec_ffn("decoder.decoders3.0", res=0.7)
+    norm("decoder.decoders3.0.norm1", D)
+    return sd
+
+
+def make_cmvn(cfg: ParaformerConfig = PARAFORMER_LARGE, seed: int = 0) -> torch.Tensor:
+    """A plausible [2, 560] (shift, scale) pair.  Log-mel energies of 16-bit-scaled synthetic audio sit
+    near 13 (low bins) .. 21 (high bins) with unit-ish spread, so shift ~ -(that), scale ~ 1."""
+    g = torch.Generator().manual_seed(7919 * seed + 5)
+    mel = torch.arange(cfg.n_mels, dtype=torch.float32) / (cfg.n_mels - 1)
+    mean = (14.0 + 5.0 * mel).repeat(cfg.lfr_m)
+    shift = -(mean + _randn(g, cfg.feat_dim, std=0.3))
+    scale = 0.8 + 0.4 * torch.rand(cfg.feat_dim, generator=g)
+    return torch.stack([shift, scale]).float()
+
+
+def make_wav(n_samples: int, seed: int = 0, kind: str = "speechlike") -> torch.Tensor:
+    """float32 waveform in [-1, 1], 16 kHz (SURVEY.md §8d synthetic input recipe).
+
+    ``noise``: 0.1*N(0,1).  ``speechlike``: band-limited noise bursts with independent slowly varying
+    envelopes per band ("formants") plus an amplitude-modulated harmonic stack ("voicing"), so spectra
+    change from frame to frame and CIF weights vary over time.
+    """
+    g = torch.Generator().manual_seed(104729 * seed + 11)
+    noise = torch.randn(n_samples, generator=g, dtype=torch.float32)
+    if kind == "noise":
+        return (0.1 * noise).clamp_(-1, 1)
+    spec = torch.fft.rfft(noise.double())
+    freqs = torch.arange(spec.numel(), dtype=torch.float64) * (16000.0 / n_samples)
+    edges = [60.0, 300.0, 600.0, 1000.0, 1500.0, 2200.0, 3000.0, 4200.0, 6000.0, 8000.0]
+    n_ctrl = max(4, int(n_samples / 16000.0 * 7.0) + 2)        # ~7 envelope control points per second
+    x = torch.zeros(n_samples, dtype=torch.float64)
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        band = torch.fft.irfft(spec * ((freqs >= lo) & (freqs < hi)), n=n_samples)
+        band = band / (band.std() + 1e-9)
+        ctrl = torch.rand(n_ctrl, generator=g, dtype=torch.float32).double() ** 3
+        env = torch.nn.functional.interpolate(ctrl[None, None, :], size=n_samples, mode="linear", align_corners=True)[0, 0]
+        x += (0.02 + 0.3 * float(torch.rand(1, generator=g))) * env * band
+    t = torch.arange(n_samples, dtype=torch.float64) / 16000.0
+    f0 = 100.0 + 120.0 * float(torch.rand(1, generator=g))
+    vib = 1.0 + 0.08 * torch.sin(2 * math.pi * 0.7 * t)
+    ctrl = torch.rand(n_ctrl, generator=g, dtype=torch.float32).double() ** 2
+    env = torch.nn.functional.interpolate(ctrl[None, None, :], size=n_samples, mode="linear", align_corners=True)[0, 0]
+    phase = 2 * math.pi * torch.cumsum(f0 * vib / 16000.0, dim=0)
+    for h in range(1, 9):
+        x += (0.25 / h) * env * torch.sin(h * phase)
+    x = x + 0.003 * noise.double()
+    return (0.6 * x / x.abs().max()).float()
+
+
+def sinusoid_inv_timescales(depth: int) -> torch.Tensor:
+    """inv_timescales of SinusoidalPositionEncoder.encode (transformer/embedding.py:409-414), fp32 ops in the same order."""
+    inc = torch.log(torch.tensor([10000], dtype=torch.float32)) / (depth / 2 - 1)
+    return torch.exp(torch.arange(depth / 2).type(torch.float32) * (-inc))

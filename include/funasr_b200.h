@@ -1,0 +1,216 @@
+/*
+ * funasr_b200 — C ABI of the B200-native (sm_100a) backend for FunASR's offline Paraformer hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (as void*); no torch / C++
+ * types cross the boundary.  All functions are stream-ordered, re-entrant, hold no global state, never
+ * synchronise the device, and return FA_OK (0) or a negative FaStatus.  The caller owns every buffer
+ * (inputs, outputs, workspace); weights are borrowed pointers.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the FunASR tree,
+ * commit 3c58cb5 / funasr 1.4.3).  The tensor-level operator boundary mirrors the reference's own
+ * export signature  export_forward(speech[B,T,560], speech_lengths[B]) -> (logits[B,N,V], token_num[B])
+ * (funasr/models/paraformer/export_meta.py) extended upward by the frontend and downward by greedy ids.
+ *
+ * Layout conventions: row-major, innermost dimension contiguous; a "row" is one (utterance, frame) or
+ * (utterance, token) pair; nn.Linear weights keep their [out_features, in_features] layout.
+ */
+#ifndef FUNASR_B200_H_
+#define FUNASR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fa_stream_t; /* cudaStream_t */
+
+typedef enum {
+  FA_OK = 0,
+  FA_ERR_ARG = -1,         /* null pointer / bad size */
+  FA_ERR_CUDA = -2,        /* a CUDA runtime call or launch failed */
+  FA_ERR_WORKSPACE = -3,   /* workspace too small */
+  FA_ERR_UNSUPPORTED = -4  /* shape outside what the kernels are built for */
+} FaStatus;
+
+/* GEMM arithmetic modes (FaLinear contractions). fp32 accumulate everywhere. */
+typedef enum {
+  FA_GEMM_F32_SIMT = 0, /* fp32 FFMA tiles: the parity reference path */
+  FA_GEMM_BF16X1 = 1,   /* tcgen05 kind::f16, one bf16 pass (fast mode) */
+  FA_GEMM_BF16X3 = 3,   /* tcgen05, hi*hi + hi*lo + lo*hi (~2^-17 relative) */
+  FA_GEMM_BF16X6 = 6    /* tcgen05, three bf16 planes, six products (~fp32) */
+} FaGemmMode;
+
+/* nn.Linear: y = x W^T + b.  w_planes (optional) holds the bf16 planes made by fa_split_bf16 for the
+ * tcgen05 path: [3][out_f][in_pad] bf16 (hi, mid, lo), in_pad = in_f rounded up to 64. */
+typedef struct {
+  const float* w;        /* [out_f, in_f] */
+  const float* b;        /* [out_f] or NULL */
+  const void* w_planes;  /* or NULL */
+  int32_t out_f, in_f, in_pad, _pad;
+} FaLinear;
+
+typedef struct {
+  const float* g; /* weight [n] */
+  const float* b; /* bias   [n] */
+  int32_t n;
+  float eps;
+} FaNorm;
+
+/* EncoderLayerSANM (funasr/models/sanm/encoder.py:44-148) */
+typedef struct {
+  FaNorm norm1;          /* over in_size (560 for encoders0, 512 otherwise) */
+  FaLinear qkv;          /* self_attn.linear_q_k_v  [1536, in_size] */
+  const float* fsmn_w;   /* self_attn.fsmn_block.weight [512, 11] (depthwise) */
+  FaLinear out;          /* self_attn.linear_out    [512, 512] */
+  FaNorm norm2;
+  FaLinear w1;           /* feed_forward.w_1 [2048, 512] */
+  FaLinear w2;           /* feed_forward.w_2 [512, 2048] */
+} FaEncLayer;
+
+/* SANMEncoder (funasr/models/sanm/encoder.py:188-461), input_layer == "pe" */
+typedef struct {
+  const FaEncLayer* layers;  /* host array, n_layers entries; [0] is encoders0.0 */
+  int32_t n_layers;
+  int32_t heads;
+  int32_t fsmn_k;            /* 11 */
+  int32_t _pad;
+  FaNorm after_norm;
+  const float* pe_inv_timescales; /* [in_size/2] device, transformer/embedding.py:409-414 */
+} FaEncoder;
+
+/* CifPredictorV2 (funasr/models/paraformer/cif_predictor.py:209-314) */
+typedef struct {
+  FaLinear conv;      /* cif_conv1d as a GEMM: weight repacked to [512, 3*512], W[n, k*512+c] = w[n,c,k] */
+  const float* out_w; /* cif_output.weight [512] */
+  const float* out_b; /* cif_output.bias   [1]   */
+  float threshold;      /* 1.0 */
+  float tail_threshold; /* 0.45 */
+  float smooth_factor;  /* 1.0 */
+  float noise_threshold;/* 0.0 */
+} FaPredictor;
+
+/* DecoderLayerSANM (funasr/models/paraformer/decoder.py:26-121) */
+typedef struct {
+  FaNorm norm1;
+  FaLinear ffn_w1;       /* feed_forward.w_1 [2048, 512] */
+  FaNorm ffn_norm;       /* feed_forward.norm over 2048 */
+  FaLinear ffn_w2;       /* feed_forward.w_2 [512, 2048], no bias */
+  FaNorm norm2;
+  const float* fsmn_w;   /* self_attn.fsmn_block.weight [512, 11]; NULL for decoders3 */
+  FaNorm norm3;
+  FaLinear q;            /* src_attn.linear_q   [512, 512] */
+  FaLinear kv;           /* src_attn.linear_k_v [1024, 512] */
+  FaLinear out;          /* src_attn.linear_out [512, 512] */
+} FaDecLayer;
+
+/* ParaformerSANMDecoder (funasr/models/paraformer/decoder.py:234-449) */
+typedef struct {
+  const FaDecLayer* layers; /* host array, n_layers entries (decoders) */
+  int32_t n_layers;
+  int32_t heads;
+  int32_t fsmn_k;
+  int32_t vocab;
+  FaDecLayer last;          /* decoders3.0: norm1 + ffn only */
+  FaNorm after_norm;
+  FaLinear output;          /* output_layer [vocab, 512] */
+} FaDecoder;
+
+/* ---------------------------------------------------------------------------------------------
+ * Library info
+ * ------------------------------------------------------------------------------------------- */
+const char* fa_version(void);
+/* Monotone count of kernel launches issued by this library in this process (bench "gpu_launches"). */
+uint64_t fa_launch_count(void);
+const char* fa_status_string(int status);
+
+/* ---------------------------------------------------------------------------------------------
+ * Frontend — replaces WavFrontend.forward (funasr/frontends/wav_frontend.py:149-196), i.e.
+ * torchaudio.compliance.kaldi.fbank (dither=0, hamming, 25 ms / 10 ms, 80 mel, snip_edges) + apply_lfr
+ * (:63-86, m=7 n=6) + apply_cmvn (:46-60), fused.  wav is float32 in [-1,1] (x32768 applied inside,
+ * :169).  Rows t >= feat_lens[b] of feats are zero-filled (pad_sequence(..., 0.0), :195).
+ *   wav [B, wav_stride], wav_lens[B] (samples, >= 400), cmvn [2,560] or NULL,
+ *   mel_banks [80,257] (kaldi.py get_mel_banks + zero column), window [400] (hamming),
+ *   feats [B, t_max, 560], feat_lens [B].
+ * ------------------------------------------------------------------------------------------- */
+int fa_fbank_lfr_cmvn(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride,
+                      const float* cmvn, const float* mel_banks, const float* window,
+                      float* feats, int32_t* feat_lens, int32_t t_max, fa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Operator-level entry points (each is used by the model-level calls below and exposed for parity tests)
+ * ------------------------------------------------------------------------------------------- */
+/* LayerNorm over the last dim (funasr/models/transformer/layer_norm.py:13-39).  If pe_inv != NULL the
+ * input row (b,t) is first mapped x*xscale + PE(t+1) (SANMEncoder.forward encoder.py:409,428 with
+ * SinusoidalPositionEncoder embedding.py:396-432); rows_per_batch gives t = row % rows_per_batch. */
+int fa_layernorm(const float* x, int64_t rows, const FaNorm* norm, float* y,
+                 const float* pe_inv, float xscale, int32_t rows_per_batch, fa_stream_t stream);
+
+/* y[rows, out_f] = act(x[rows, in_f(ldx)] W^T + b) (+ res1) (+ res2); replaces torch.nn.Linear calls
+ * (attention.py:256,306; positionwise_feed_forward.py:34).  relu != 0 applies ReLU before residuals. */
+int fa_linear(const float* x, int64_t ldx, int64_t rows, const FaLinear* lin, int32_t relu,
+              const float* res1, int64_t ld_res1, const float* res2, int64_t ld_res2,
+              float* y, int64_t ldy, int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream);
+
+/* FSMN memory block: out = m * (v*m + dwconv_k(v*m)) (+ res); m[t] = t < lens[b]
+ * (MultiHeadedAttentionSANM.forward_fsmn attention.py:216-239; decoder variant :583-631). */
+int fa_fsmn(const float* v, int64_t ldv, const int32_t* lens, int32_t batch, int32_t t_max, int32_t channels,
+            const float* w, int32_t ksize, const float* res, int64_t ld_res, float* out, int64_t ld_out,
+            fa_stream_t stream);
+
+/* Multi-head scaled-dot attention with key-padding mask: masked_fill(-inf) -> softmax -> masked_fill(0)
+ * -> @V, heads merged (attention.py:288-304 self, :760-794 cross).  head_dim is 128.
+ *   q [B, tq, ldq], k/v [B, tk, ldk/ldv] (head h at column h*128), ctx [B, tq, ld_ctx]. */
+int fa_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                 const int32_t* key_lens, int32_t batch, int32_t heads, int32_t tq, int32_t tk,
+                 float* ctx, int64_t ld_ctx, fa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Model-level entry points
+ * ------------------------------------------------------------------------------------------- */
+/* SANMEncoder.forward (encoder.py:392-461): feats [B,T,560], lens[B] -> enc [B,T,512]. */
+size_t fa_sanm_encoder_workspace_bytes(int32_t batch, int32_t t_max, int32_t gemm_mode);
+int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats, const int32_t* lens, int32_t batch,
+                            int32_t t_max, float* out, int32_t gemm_mode, void* workspace, size_t ws_bytes,
+                            fa_stream_t stream);
+
+/* CifPredictorV2.forward, inference branch (cif_predictor.py:253-314 + tail_process_fn :414-446 + cif_v1
+ * :853-908).  enc [B,T,512], lens[B] ->
+ *   acoustic [B, n_cap, 512] (rows >= fires zero-filled; n_cap >= 1, tokens beyond n_cap are dropped),
+ *   token_num [B] int32 (= floor(sum alpha'), the reference's pre_token_length),
+ *   alphas [B, T+1], peaks [B, T+1] (cif_peak / "fires"). */
+size_t fa_cif_predictor_workspace_bytes(int32_t batch, int32_t t_max, int32_t gemm_mode);
+int fa_cif_predictor_forward(const FaPredictor* pred, const float* enc, const int32_t* lens, int32_t batch,
+                             int32_t t_max, float* acoustic, int32_t n_cap, int32_t* token_num, float* alphas,
+                             float* peaks, int32_t gemm_mode, void* workspace, size_t ws_bytes,
+                             fa_stream_t stream);
+
+/* ParaformerSANMDecoder.forward (decoder.py:397-449) + greedy argmax (paraformer/model.py:642-644).
+ *   enc [B,T,512], enc_lens[B]; acoustic [B, ld_acoustic_rows, 512] of which the first n_max rows are used;
+ *   tok_lens[B].  Outputs: argmax_ids [B, n_max] int32, argmax_logp [B, n_max] (log-softmax value of the
+ *   arg-max, :643), and — if logits != NULL — the full pre-softmax logits [B, n_max, vocab].
+ *   If log_softmax != 0 the logits buffer is converted in place to log_softmax (model.py:345). */
+size_t fa_paraformer_decoder_workspace_bytes(int32_t batch, int32_t t_max, int32_t n_max, int32_t vocab,
+                                             int32_t gemm_mode);
+int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* enc, const int32_t* enc_lens, int32_t batch,
+                                  int32_t t_max, const float* acoustic, int64_t ld_acoustic_rows,
+                                  const int32_t* tok_lens, int32_t n_max, int32_t* argmax_ids, float* argmax_logp,
+                                  float* logits, int32_t log_softmax, int32_t gemm_mode, void* workspace,
+                                  size_t ws_bytes, fa_stream_t stream);
+
+/* Greedy post-filter (paraformer/model.py:655-666): keep argmax_ids[b, k] for k < tok_lens[b] that are not
+ * in {blank=0, sos=1, eos=2}; out_ids [B, n_max] (padded with -1), out_lens [B]. */
+int fa_greedy_filter(const int32_t* argmax_ids, const int32_t* tok_lens, int32_t batch, int32_t n_max,
+                     int32_t sos, int32_t eos, int32_t blank, int32_t* out_ids, int32_t* out_lens,
+                     fa_stream_t stream);
+
+/* Split fp32 [rows, cols] into three bf16 planes [3][rows][cols_pad] (hi, mid, lo; zero padded columns):
+ * weight repack for the tcgen05 GEMM path (called once per weight after load_pretrained_model). */
+int fa_split_bf16(const float* src, int64_t ld_src, int64_t rows, int32_t cols, int32_t cols_pad,
+                  void* planes, fa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUNASR_B200_H_ */

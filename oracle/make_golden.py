@@ -1,0 +1,128 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference, funasr 1.4.3) on CPU.
+
+Run here (the build container), never on the GPU box:   python oracle/make_golden.py
+The reference is driven through its own plugin surface: AutoModel(model="Paraformer", model_conf=...,
+init_param=<synthetic model.pt>) -> model.inference(..., tokenizer=None) for the greedy ids
+(paraformer/model.py:694) and model.encode / calc_predictor / cal_decoder_with_predictor for stage taps
+(SURVEY.md App. B).  Weights/waveforms come from funasr_b200/synth.py (seeded), so only outputs are stored.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import ref_shim  # noqa: E402
+from funasr_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (cfg, weight seed, [(n_samples, wav seed, kind)], use_cmvn)
+    "tiny_ragged3": (synth.PARAFORMER_TINY, 3, [(48000, 1, "speechlike"), (27200, 2, "noise"), (38437, 3, "speechlike")], True),
+    "tiny_single": (synth.PARAFORMER_TINY, 3, [(16000, 4, "speechlike")], False),
+    "large_ragged2": (synth.PARAFORMER_LARGE, 0, [(480000, 0, "speechlike"), (196800, 5, "speechlike")], True),
+}
+
+
+def write_cmvn_file(path, cmvn):
+    """Kaldi-nnet text layout parsed by load_cmvn (wav_frontend.py:15-43)."""
+    d = cmvn.shape[1]
+    with open(path, "w") as f:
+        f.write("<Nnet>\n<Splice> %d %d\n[ 0 ]\n<AddShift> %d %d\n" % (d, d, d, d))
+        f.write("<LearnRateCoef> 0 [ " + " ".join("%.9g" % v for v in cmvn[0].tolist()) + " ]\n")
+        f.write("<Rescale> %d %d\n" % (d, d))
+        f.write("<LearnRateCoef> 0 [ " + " ".join("%.9g" % v for v in cmvn[1].tolist()) + " ]\n</Nnet>\n")
+
+
+def build_reference_model(cfg, seed, cmvn_file, tmp):
+    from funasr import AutoModel
+    sd = synth.make_state_dict(cfg, seed)
+    pt = os.path.join(tmp, "model_%d_%d.pt" % (cfg.enc_layers, seed))
+    torch.save(sd, pt)
+    tokens = ["<blank>", "<s>", "</s>"] + ["t%d" % i for i in range(cfg.vocab - 4)] + ["<unk>"]
+    am = AutoModel(
+        model="Paraformer",
+        model_conf=dict(ctc_weight=0.0, lsm_weight=0.1, length_normalized_loss=True, predictor_weight=1.0,
+                        predictor_bias=1, sampling_ratio=0.75),
+        encoder="SANMEncoder",
+        encoder_conf=dict(output_size=cfg.d_model, attention_heads=cfg.heads, linear_units=cfg.ffn,
+                          num_blocks=cfg.enc_layers, dropout_rate=0.1, positional_dropout_rate=0.1,
+                          attention_dropout_rate=0.1, input_layer="pe", pos_enc_class="SinusoidalPositionEncoder",
+                          normalize_before=True, kernel_size=cfg.kernel, sanm_shfit=0, selfattention_layer_type="sanm"),
+        decoder="ParaformerSANMDecoder",
+        decoder_conf=dict(attention_heads=cfg.heads, linear_units=cfg.ffn, num_blocks=cfg.dec_layers, dropout_rate=0.1,
+                          positional_dropout_rate=0.1, self_attention_dropout_rate=0.1, src_attention_dropout_rate=0.1,
+                          att_layer_num=cfg.dec_layers, kernel_size=cfg.kernel, sanm_shfit=0),
+        predictor="CifPredictorV2",
+        predictor_conf=dict(idim=cfg.d_model, threshold=1.0, l_order=1, r_order=1, tail_threshold=cfg.tail_threshold),
+        frontend="WavFrontend",
+        frontend_conf=dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6,
+                           dither=0.0, cmvn_file=cmvn_file),
+        tokenizer="CharTokenizer",
+        tokenizer_conf=dict(token_list=tokens, unk_symbol="<unk>", split_with_space=True),
+        device="cpu", ncpu=os.cpu_count(), disable_update=True, disable_pbar=True, init_param=pt,
+    )
+    return am
+
+
+def run_case(name, cfg, wseed, wav_specs, use_cmvn, tmp):
+    cmvn_file = None
+    if use_cmvn:
+        cmvn_file = os.path.join(tmp, "am_%s.mvn" % name)
+        write_cmvn_file(cmvn_file, synth.make_cmvn(cfg, seed=1))
+    am = build_reference_model(cfg, wseed, cmvn_file, tmp)
+    model, frontend = am.model, am.kwargs["frontend"]
+    wavs = [synth.make_wav(n, s, k) for (n, s, k) in wav_specs]
+    with torch.no_grad():
+        res, meta = model.inference(data_in=[w.numpy() for w in wavs], key=["u%d" % i for i in range(len(wavs))],
+                                    tokenizer=None, frontend=frontend, device="cpu")
+        from funasr.utils.load_utils import extract_fbank
+        feats, flens = extract_fbank([w for w in wavs], frontend=frontend)
+        enc, elens = model.encode(feats, flens)
+        emb, tok, alphas, peaks = model.calc_predictor(enc, elens)
+        tokl = tok.round().long()
+        logp, _ = model.cal_decoder_with_predictor(enc, elens, emb, tokl)
+    ids = [r["token_int"] for r in res]
+    top2 = torch.topk(logp, 2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1])
+    N = logp.shape[1]
+    keep = sorted(set(list(range(min(4, N))) + [N // 2, N - 1]))
+    out = dict(
+        feats=feats.numpy(), feat_lens=flens.numpy().astype(np.int32),
+        enc=enc.numpy().astype(np.float32), alphas=alphas.numpy(), token_num=tokl.numpy().astype(np.int32),
+        acoustic=emb.numpy(), logp_rows=np.array(keep, dtype=np.int32), logp_sel=logp[:, keep, :].numpy(),
+        logp_max=logp.max(-1).values.numpy(), argmax=logp.argmax(-1).numpy().astype(np.int32), margin=margin.numpy(),
+        ids_flat=np.array([t for r in ids for t in r], dtype=np.int32), ids_len=np.array([len(r) for r in ids], dtype=np.int32),
+        batch_data_time=np.float64(meta["batch_data_time"]),
+    )
+    if cfg.enc_layers > 10:   # keep the large fixture small: drop the big dense taps, keep strided samples
+        out["feats"] = out["feats"][:, ::7, :]
+        out["enc"] = out["enc"][:, ::7, :]
+        out["acoustic"] = out["acoustic"][:, ::5, :]
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    valid = torch.arange(N)[None, :] < tokl[:, None]
+    print("%s: B=%d T=%d tokens=%s min_margin(valid)=%.3e  ids[0][:8]=%s" % (
+        name, len(wavs), feats.shape[1], tokl.tolist(), float(margin[valid].min()), ids[0][:8]))
+
+
+def main():
+    ref_shim.import_reference()
+    os.makedirs(GOLD, exist_ok=True)
+    only = sys.argv[1:] or list(CASES)
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in only:
+            cfg, wseed, specs, use_cmvn = CASES[name]
+            run_case(name, cfg, wseed, specs, use_cmvn, tmp)
+    # a cmvn file fixture in the Kaldi-nnet text layout for the parser test
+    write_cmvn_file(os.path.join(GOLD, "am_synth.mvn"), synth.make_cmvn(synth.PARAFORMER_LARGE, seed=1))
+
+
+if __name__ == "__main__":
+    main()

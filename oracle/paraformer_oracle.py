@@ -1,0 +1,327 @@
+"""ORACLE — CPU fp32 restatement of FunASR's offline Paraformer hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this file; the product (funasr_b200/) never does and fails loudly without its CUDA library.
+
+Parity status: PINNED against the live reference.  oracle/make_golden.py runs the unmodified
+reference classes from /root/reference (funasr 1.4.3) on CPU with the seeded synthetic weights of
+funasr_b200/synth.py and stores their outputs under tests/golden/; tests/test_oracle_golden.py checks
+this restatement against those files, and (when /root/reference is present) against the live
+reference directly.  The Fbank arithmetic lives in a third-party dependency that is NOT under
+/root/reference: torchaudio.compliance.kaldi.fbank — pinned here to torchaudio 2.11.0+cu128
+(site-packages/torchaudio/compliance/kaldi.py); the reference ships no test that pins Fbank values,
+so that boundary is pinned by our own golden vectors generated from that torchaudio version.
+
+Each function cites the reference lines it restates (paths relative to /root/reference).
+Plain torch CPU ops are used in the same order as the reference so that on the same machine the
+restatement is (near) bit-identical to it.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+EPS_F32 = torch.finfo(torch.float32).eps  # kaldi.py:_get_epsilon -> 1.1920929e-07
+
+
+# --------------------------------------------------------------------------------------
+# Frontend: torchaudio.compliance.kaldi.fbank (kaldi.py:514-647) as called by
+# funasr/frontends/wav_frontend.py:165-189, then apply_lfr (:63-86) and apply_cmvn (:46-60)
+# --------------------------------------------------------------------------------------
+def mel_scale(f):
+    return 1127.0 * (1.0 + f / 700.0).log()          # kaldi.py:mel_scale
+
+
+def mel_scale_scalar(f: float) -> float:
+    return 1127.0 * math.log(1.0 + f / 700.0)        # kaldi.py:mel_scale_scalar
+
+
+def get_mel_banks(num_bins=80, padded=512, fs=16000.0, low=20.0, high=0.0) -> Tensor:
+    """kaldi.py:436-511 (vtln_warp == 1.0 branch). Returns [num_bins, padded/2]."""
+    num_fft_bins = padded / 2
+    nyquist = 0.5 * fs
+    if high <= 0.0:
+        high += nyquist
+    fft_bin_width = fs / padded
+    mel_low, mel_high = mel_scale_scalar(low), mel_scale_scalar(high)
+    delta = (mel_high - mel_low) / (num_bins + 1)
+    b = torch.arange(num_bins).unsqueeze(1)
+    left = mel_low + b * delta
+    center = mel_low + (b + 1.0) * delta
+    right = mel_low + (b + 2.0) * delta
+    mel = mel_scale(fft_bin_width * torch.arange(num_fft_bins)).unsqueeze(0)
+    up = (mel - left) / (center - left)
+    down = (right - mel) / (right - center)
+    return torch.max(torch.zeros(1), torch.min(up, down))
+
+
+def kaldi_fbank(waveform_scaled: Tensor, n_mels=80, fs=16000, frame_length_ms=25.0, frame_shift_ms=10.0) -> Tensor:
+    """kaldi.fbank with the arguments WavFrontend passes (wav_frontend.py:171-181): dither=0 (parity
+    config), energy_floor=0, hamming, snip_edges=True, remove_dc_offset, preemph 0.97, power, log.
+    waveform_scaled: 1-D float32 already multiplied by 32768 (wav_frontend.py:169)."""
+    n = waveform_scaled.numel()
+    shift = int(fs * frame_shift_ms * 0.001)
+    win = int(fs * frame_length_ms * 0.001)
+    padded = 1 if win == 0 else 2 ** (win - 1).bit_length()
+    if n < win:
+        return torch.empty(0, n_mels)
+    m = 1 + (n - win) // shift                                     # kaldi.py:_get_strided snip_edges
+    x = waveform_scaled.as_strided((m, win), (shift, 1))
+    x = x - torch.mean(x, dim=1).unsqueeze(1)                      # remove_dc_offset :183-186
+    off = F.pad(x.unsqueeze(0), (1, 0), mode="replicate").squeeze(0)
+    x = x - 0.97 * off[:, :-1]                                     # pre-emphasis :193-198
+    x = x * torch.hamming_window(win, periodic=False, alpha=0.54, beta=0.46).unsqueeze(0)
+    if padded != win:
+        x = F.pad(x.unsqueeze(0), (0, padded - win), mode="constant", value=0).squeeze(0)
+    spec = torch.fft.rfft(x).abs().pow(2.0)                        # :616-618
+    banks = F.pad(get_mel_banks(n_mels, padded, float(fs)), (0, 1), mode="constant", value=0)
+    mel = torch.mm(spec, banks.T)                                  # :630
+    return torch.max(mel, torch.tensor(EPS_F32)).log()             # :632-633
+
+
+def apply_lfr(x: Tensor, m: int = 7, n: int = 6) -> Tensor:
+    """wav_frontend.py:63-86 restated as the clamped gather it equals (probed):
+    out[i] = concat_j x[clamp(n*i - (m-1)//2 + j, 0, T-1)], i < ceil(T/n)."""
+    T = x.shape[0]
+    T_lfr = (T + n - 1) // n
+    idx = (torch.arange(T_lfr).unsqueeze(1) * n - (m - 1) // 2 + torch.arange(m).unsqueeze(0)).clamp_(0, T - 1)
+    return x[idx].reshape(T_lfr, m * x.shape[1]).contiguous()
+
+
+def frontend(wavs: List[Tensor], cmvn: Optional[Tensor], lfr_m=7, lfr_n=6) -> Tuple[Tensor, Tensor]:
+    """WavFrontend.forward (wav_frontend.py:149-196). wavs: list of 1-D float32 in [-1,1]."""
+    feats, lens = [], []
+    for w in wavs:
+        n = w.numel()
+        mat = kaldi_fbank(w * (1 << 15), frame_length_ms=min(25, n / 16000 * 1000))
+        mat = apply_lfr(mat, lfr_m, lfr_n)
+        if cmvn is not None:
+            mat = (mat + cmvn[0:1]) * cmvn[1:2]
+        feats.append(mat)
+        lens.append(mat.shape[0])
+    pad = torch.nn.utils.rnn.pad_sequence(feats, batch_first=True, padding_value=0.0)
+    return pad, torch.tensor(lens, dtype=torch.int32)
+
+
+# --------------------------------------------------------------------------------------
+# Encoder: funasr/models/sanm/encoder.py:392-461, attention.py:216-327
+# --------------------------------------------------------------------------------------
+def layer_norm(x, w, b, eps=1e-12):
+    return F.layer_norm(x, (x.shape[-1],), w, b, eps)               # transformer/layer_norm.py:13-39
+
+
+def sinusoid_pe(T: int, depth: int) -> Tensor:
+    """transformer/embedding.py:396-432: positions 1..T, concat(sin, cos) halves."""
+    pos = torch.arange(1, T + 1)[None, :].type(torch.float32)
+    inc = torch.log(torch.tensor([10000], dtype=torch.float32)) / (depth / 2 - 1)
+    inv = torch.exp(torch.arange(depth / 2).type(torch.float32) * (-inc))
+    st = pos.reshape(1, -1, 1) * inv.reshape(1, 1, -1)
+    return torch.cat([torch.sin(st), torch.cos(st)], dim=2)
+
+
+def fsmn(v: Tensor, w: Tensor, mask_bt1: Tensor) -> Tensor:
+    """forward_fsmn attention.py:216-239 / decoder variant :583-631: depthwise conv (k, zero pad (k-1)//2 both sides)."""
+    k = w.shape[-1]
+    left = (k - 1) // 2
+    inp = v * mask_bt1
+    x = F.pad(inp.transpose(1, 2), (left, k - 1 - left), value=0.0)
+    x = F.conv1d(x, w, None, groups=w.shape[0]).transpose(1, 2)
+    return (x + inp) * mask_bt1
+
+
+def mh_attention(q, k, v, key_mask_b1t, heads: int) -> Tensor:
+    """attention.py:288-304 / :760-794: scores, masked_fill(-inf) -> softmax -> masked_fill(0) -> @v, merge heads."""
+    B, Tq, D = q.shape
+    dk = D // heads
+    qh = q.reshape(B, Tq, heads, dk).transpose(1, 2) * dk ** (-0.5)
+    kh = k.reshape(B, -1, heads, dk).transpose(1, 2)
+    vh = v.reshape(B, -1, heads, dk).transpose(1, 2)
+    scores = torch.matmul(qh, kh.transpose(-2, -1))
+    m = key_mask_b1t.unsqueeze(1).eq(0)
+    attn = torch.softmax(scores.masked_fill(m, -float("inf")), dim=-1).masked_fill(m, 0.0)
+    return torch.matmul(attn, vh).transpose(1, 2).contiguous().view(B, Tq, D)
+
+
+def sanm_attention(u, p: Dict[str, Tensor], pre: str, mask_b1t, heads: int) -> Tensor:
+    """MultiHeadedAttentionSANM.forward attention.py:308-327."""
+    B, T, _ = u.shape
+    qkv = F.linear(u, p[pre + "linear_q_k_v.weight"], p[pre + "linear_q_k_v.bias"])
+    D = qkv.shape[-1] // 3
+    q, k, v = torch.split(qkv, D, dim=-1)
+    mem = fsmn(v, p[pre + "fsmn_block.weight"], mask_b1t.reshape(B, -1, 1).float())
+    ctx = mh_attention(q, k, v, mask_b1t, heads)
+    return F.linear(ctx, p[pre + "linear_out.weight"], p[pre + "linear_out.bias"]) + mem
+
+
+def encoder_layer(x, p, pre, mask_b1t, heads, eps, taps=None) -> Tensor:
+    """EncoderLayerSANM.forward encoder.py:72-148 (eval, normalize_before, no concat_after)."""
+    in_size = p[pre + "norm1.weight"].numel()
+    size = p[pre + "norm2.weight"].numel()
+    a = sanm_attention(layer_norm(x, p[pre + "norm1.weight"], p[pre + "norm1.bias"], eps), p, pre + "self_attn.", mask_b1t, heads)
+    x = x + a if in_size == size else a
+    h = F.linear(layer_norm(x, p[pre + "norm2.weight"], p[pre + "norm2.bias"], eps),
+                 p[pre + "feed_forward.w_1.weight"], p[pre + "feed_forward.w_1.bias"])
+    return x + F.linear(torch.relu(h), p[pre + "feed_forward.w_2.weight"], p[pre + "feed_forward.w_2.bias"])
+
+
+def encoder(feats: Tensor, lens: Tensor, p: Dict[str, Tensor], enc_layers: int, heads=4, eps=1e-12,
+            taps: Optional[dict] = None) -> Tuple[Tensor, Tensor]:
+    """SANMEncoder.forward encoder.py:392-461 (input_layer='pe')."""
+    B, T, Din = feats.shape
+    mask = (torch.arange(T)[None, :] < lens[:, None].long())[:, None, :]   # ~make_pad_mask
+    D = p["encoder.after_norm.weight"].numel()
+    x = feats * D ** 0.5
+    x = x + sinusoid_pe(T, Din)
+    x = encoder_layer(x, p, "encoder.encoders0.0.", mask, heads, eps)
+    if taps is not None:
+        taps["enc_l0"] = x
+    for i in range(enc_layers - 1):
+        x = encoder_layer(x, p, "encoder.encoders.%d." % i, mask, heads, eps)
+    x = layer_norm(x, p["encoder.after_norm.weight"], p["encoder.after_norm.bias"], eps)
+    return x, mask.squeeze(1).sum(1).to(torch.int32)
+
+
+# --------------------------------------------------------------------------------------
+# CIF predictor: funasr/models/paraformer/cif_predictor.py:253-314, 414-446, 818-908
+# --------------------------------------------------------------------------------------
+def cif_alphas(enc: Tensor, mask_b1t: Tensor, p, smooth=1.0, noise=0.0) -> Tensor:
+    """cif_predictor.py:273-287."""
+    q = F.pad(enc.transpose(1, 2), (1, 1), value=0.0)
+    out = torch.relu(F.conv1d(q, p["predictor.cif_conv1d.weight"], p["predictor.cif_conv1d.bias"])).transpose(1, 2)
+    out = F.linear(out, p["predictor.cif_output.weight"], p["predictor.cif_output.bias"])
+    al = torch.relu(torch.sigmoid(out) * smooth - noise)
+    return (al * mask_b1t.transpose(-1, -2).float()).squeeze(-1)
+
+
+def cif_tail(hidden: Tensor, alphas: Tensor, mask_bt: Tensor, tail_threshold: float):
+    """tail_process_fn cif_predictor.py:414-446 (mask given)."""
+    b, t, d = hidden.shape
+    z = torch.zeros((b, 1), dtype=torch.float32)
+    m = torch.cat([torch.ones_like(z), mask_bt], dim=1) - torch.cat([mask_bt, z], dim=1)
+    alphas = torch.add(torch.cat([alphas, z], dim=1), m * tail_threshold)
+    hidden = torch.cat([hidden, torch.zeros((b, 1, d), dtype=hidden.dtype)], dim=1)
+    return hidden, alphas, torch.floor(alphas.sum(dim=-1))
+
+
+def cif_fires(alphas: Tensor):
+    """cif_wo_hidden_v1 cif_predictor.py:818-850."""
+    ps = torch.cumsum(alphas, dim=1, dtype=torch.float64).to(torch.float32)
+    psf = torch.floor(ps)
+    dis = torch.floor(torch.roll(ps, 1, dims=1))
+    dis[:, 0] = 0
+    fire_idxs = (psf - dis) > 0
+    fires = torch.zeros_like(alphas)
+    fires[fire_idxs] = 1
+    return fires + ps - psf, fire_idxs
+
+
+def cif_v1(hidden: Tensor, alphas: Tensor):
+    """cif_v1 cif_predictor.py:853-908, restated per row (identical arithmetic order for every emitted
+    frame: ((PH[t_k] - PH[t_{k-1}]) + rem_{k-1} h_{k-1}) - rem_k h_k), with the reference's
+    undefined case (a row with zero fires inside a batch that has fires) defined as 'zero tokens'."""
+    fires, fire_idxs = cif_fires(alphas)
+    B, T, D = hidden.shape
+    max_label_len = int(torch.round(alphas.sum(-1)).int().max())
+    out = torch.zeros(B, max_label_len, D, dtype=hidden.dtype)
+    if fire_idxs.sum() == 0:
+        return out, fires
+    PH = torch.cumsum(alphas.unsqueeze(-1).repeat((1, 1, D)) * hidden, dim=1)
+    rem = fires - torch.floor(fires)
+    for b in range(B):
+        idx = torch.nonzero(fire_idxs[b]).flatten()
+        if idx.numel() == 0:
+            continue
+        fr = PH[b, idx]
+        rf = rem[b, idx].unsqueeze(-1).repeat((1, D)) * hidden[b, idx]
+        sfr = torch.roll(fr, 1, dims=0)
+        srf = torch.roll(rf, 1, dims=0)
+        sfr[0] = 0
+        srf[0] = 0
+        e = fr - sfr + srf - rf
+        n = min(e.shape[0], max_label_len)
+        out[b, :n] = e[:n]
+    return out, fires
+
+
+def predictor(enc: Tensor, enc_lens: Tensor, p, tail_threshold=0.45):
+    """Paraformer.calc_predictor model.py:315-329 -> CifPredictorV2.forward (inference branch)."""
+    B, T, _ = enc.shape
+    mask = (torch.arange(T)[None, :] < enc_lens[:, None].long())[:, None, :]
+    al = cif_alphas(enc, mask, p)
+    hidden, al2, token_num = cif_tail(enc, al, mask.squeeze(1).float(), tail_threshold)
+    emb, peaks = cif_v1(hidden, al2)
+    n_int = int(torch.max(token_num).type(torch.int32).item())
+    return emb[:, :n_int, :], token_num, al2, peaks
+
+
+# --------------------------------------------------------------------------------------
+# Decoder: funasr/models/paraformer/decoder.py:78-121, 397-449
+# --------------------------------------------------------------------------------------
+def dec_ffn(x, p, pre, eps):
+    """PositionwiseFeedForwardDecoderSANM sanm/positionwise_feed_forward.py:12-33."""
+    h = torch.relu(F.linear(x, p[pre + "w_1.weight"], p[pre + "w_1.bias"]))
+    return F.linear(layer_norm(h, p[pre + "norm.weight"], p[pre + "norm.bias"], eps), p[pre + "w_2.weight"])
+
+
+def decoder(enc, enc_lens, emb, tok_lens, p, dec_layers: int, heads=4, eps=1e-12, taps=None):
+    """ParaformerSANMDecoder.forward decoder.py:397-449 -> logits [B, N, V]."""
+    B, N, D = emb.shape
+    T = enc.shape[1]
+    tgt_mask = (torch.arange(N)[None, :] < tok_lens[:, None].long()).float()[:, :, None]
+    mem_mask = (torch.arange(T)[None, :] < enc_lens[:, None].long()).float()[:, None, :]
+    x = emb
+    for i in range(dec_layers):
+        pre = "decoder.decoders.%d." % i
+        r = x
+        t = dec_ffn(layer_norm(x, p[pre + "norm1.weight"], p[pre + "norm1.bias"], eps), p, pre + "feed_forward.", eps)
+        t = layer_norm(t, p[pre + "norm2.weight"], p[pre + "norm2.bias"], eps)
+        x = r + fsmn(t, p[pre + "self_attn.fsmn_block.weight"], tgt_mask)
+        r = x
+        y = layer_norm(x, p[pre + "norm3.weight"], p[pre + "norm3.bias"], eps)
+        q = F.linear(y, p[pre + "src_attn.linear_q.weight"], p[pre + "src_attn.linear_q.bias"])
+        kv = F.linear(enc, p[pre + "src_attn.linear_k_v.weight"], p[pre + "src_attn.linear_k_v.bias"])
+        k, v = torch.split(kv, D, dim=-1)
+        ctx = mh_attention(q, k, v, mem_mask, heads)
+        x = r + F.linear(ctx, p[pre + "src_attn.linear_out.weight"], p[pre + "src_attn.linear_out.bias"])
+        if taps is not None and i == 0:
+            taps["dec_l0"] = x
+    pre = "decoder.decoders3.0."
+    x = dec_ffn(layer_norm(x, p[pre + "norm1.weight"], p[pre + "norm1.bias"], eps), p, pre + "feed_forward.", eps)
+    h = layer_norm(x, p["decoder.after_norm.weight"], p["decoder.after_norm.bias"], eps)
+    return F.linear(h, p["decoder.output_layer.weight"], p["decoder.output_layer.bias"])
+
+
+def greedy_ids(logp: Tensor, tok_lens: Tensor, sos=1, eos=2, blank=0) -> List[List[int]]:
+    """paraformer/model.py:628-666 greedy branch with tokenizer=None -> token_int lists."""
+    res = []
+    for i in range(logp.shape[0]):
+        ys = logp[i, : int(tok_lens[i])].argmax(dim=-1).tolist()
+        res.append([t for t in ys if t not in (eos, sos, blank)])
+    return res
+
+
+def paraformer_forward(wavs: List[Tensor], p: Dict[str, Tensor], cmvn: Optional[Tensor], enc_layers: int,
+                       dec_layers: int, heads: int = 4, eps: float = 1e-12, tail_threshold: float = 0.45,
+                       want_taps: bool = False):
+    """Paraformer.inference model.py:534-697 from waveforms to greedy ids (plus stage taps)."""
+    taps = {} if want_taps else None
+    with torch.no_grad():
+        feats, flens = frontend(wavs, cmvn)
+        enc, elens = encoder(feats, flens, p, enc_layers, heads, eps, taps)
+        emb, token_num, alphas, peaks = predictor(enc, elens, p, tail_threshold)
+        tok = token_num.round().long()
+        out = {"feats": feats, "feat_lens": flens, "enc": enc, "alphas": alphas, "token_num": tok.to(torch.int32),
+               "acoustic": emb}
+        if int(tok.max()) < 1:
+            out.update(ids=[[] for _ in wavs], logp=None)
+            return out
+        logits = decoder(enc, elens, emb, tok, p, dec_layers, heads, eps, taps)
+        logp = torch.log_softmax(logits, dim=-1)
+        out.update(logp=logp, ids=greedy_ids(logp, tok))
+        if taps:
+            out.update(taps)
+    return out
