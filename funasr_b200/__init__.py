@@ -1,0 +1,16 @@
+"""funasr_b200 — B200-native (sm_100a) backend for FunASR's offline Paraformer hot path.
+
+Importing this package registers the drop-in plugin classes (ParaformerB200, WavFrontendB200, SANMEncoderB200,
+CifPredictorV2B200, ParaformerSANMDecoderB200) — into ``funasr.register.tables`` when FunASR is imported, else into
+a local table with the same API.  ``funasr_b200.install(override_reference_keys=True)`` additionally re-points the
+reference's own keys at these classes so an unmodified FunASR config runs on this backend.
+"""
+from .registry import get_tables, install, register  # noqa: F401
+from .synth import PARAFORMER_LARGE, PARAFORMER_TINY, ParaformerConfig  # noqa: F401
+from . import modules  # noqa: F401  (registers the classes)
+from .modules import (CifPredictorV2B200, ParaformerB200, ParaformerSANMDecoderB200, SANMEncoderB200,  # noqa: F401
+                      WavFrontendB200, load_cmvn)
+from .engine import FrontendEngine, ParaformerEngine  # noqa: F401
+from .sharding import shard_utterances, gather_token_ids  # noqa: F401
+
+__version__ = "0.1.0"

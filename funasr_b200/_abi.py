@@ -1,0 +1,107 @@
+"""ctypes mirror of include/funasr_b200.h and loader of the in-tree CUDA library.
+
+The product path has NO fallback: if ``libfunasr_b200.so`` is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfunasr_b200.so")
+
+FA_OK = 0
+GEMM_F32_SIMT, GEMM_BF16X1, GEMM_BF16X3, GEMM_BF16X6 = 0, 1, 3, 6
+GEMM_MODES = {"fp32": GEMM_F32_SIMT, "bf16": GEMM_BF16X1, "bf16x3": GEMM_BF16X3, "bf16x6": GEMM_BF16X6}
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+
+
+class FaLinear(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("w_planes", C.c_void_p),
+                ("out_f", C.c_int32), ("in_f", C.c_int32), ("in_pad", C.c_int32), ("_pad", C.c_int32)]
+
+
+class FaNorm(C.Structure):
+    _fields_ = [("g", C.c_void_p), ("b", C.c_void_p), ("n", C.c_int32), ("eps", C.c_float)]
+
+
+class FaEncLayer(C.Structure):
+    _fields_ = [("norm1", FaNorm), ("qkv", FaLinear), ("fsmn_w", C.c_void_p), ("out", FaLinear),
+                ("norm2", FaNorm), ("w1", FaLinear), ("w2", FaLinear)]
+
+
+class FaEncoder(C.Structure):
+    _fields_ = [("layers", C.POINTER(FaEncLayer)), ("n_layers", C.c_int32), ("heads", C.c_int32),
+                ("fsmn_k", C.c_int32), ("_pad", C.c_int32), ("after_norm", FaNorm),
+                ("pe_inv_timescales", C.c_void_p)]
+
+
+class FaPredictor(C.Structure):
+    _fields_ = [("conv", FaLinear), ("out_w", C.c_void_p), ("out_b", C.c_void_p), ("threshold", C.c_float),
+                ("tail_threshold", C.c_float), ("smooth_factor", C.c_float), ("noise_threshold", C.c_float)]
+
+
+class FaDecLayer(C.Structure):
+    _fields_ = [("norm1", FaNorm), ("ffn_w1", FaLinear), ("ffn_norm", FaNorm), ("ffn_w2", FaLinear),
+                ("norm2", FaNorm), ("fsmn_w", C.c_void_p), ("norm3", FaNorm), ("q", FaLinear), ("kv", FaLinear),
+                ("out", FaLinear)]
+
+
+class FaDecoder(C.Structure):
+    _fields_ = [("layers", C.POINTER(FaDecLayer)), ("n_layers", C.c_int32), ("heads", C.c_int32),
+                ("fsmn_k", C.c_int32), ("vocab", C.c_int32), ("last", FaDecLayer), ("after_norm", FaNorm),
+                ("output", FaLinear)]
+
+
+_vp, _i32, _i64, _sz, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float
+
+# name -> (restype, argtypes); every symbol include/funasr_b200.h declares
+SIGNATURES = {
+    "fa_version": (C.c_char_p, []),
+    "fa_launch_count": (C.c_uint64, []),
+    "fa_status_string": (C.c_char_p, [C.c_int]),
+    "fa_fbank_lfr_cmvn": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fa_layernorm": (C.c_int, [_vp, _i64, C.POINTER(FaNorm), _vp, _vp, _f, _i32, _vp]),
+    "fa_linear": (C.c_int, [_vp, _i64, _i64, C.POINTER(FaLinear), _i32, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _sz, _vp]),
+    "fa_fsmn": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp, _i64, _vp]),
+    "fa_attention": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "fa_sanm_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "fa_sanm_encoder_forward": (C.c_int, [C.POINTER(FaEncoder), _vp, _vp, _i32, _i32, _vp, _i32, _vp, _sz, _vp]),
+    "fa_cif_predictor_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "fa_cif_predictor_forward": (C.c_int, [C.POINTER(FaPredictor), _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "fa_paraformer_decoder_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "fa_paraformer_decoder_forward": (C.c_int, [C.POINTER(FaDecoder), _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
+    "fa_greedy_filter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fa_split_bf16": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+}
+
+_lib = None
+
+
+class FunasrB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the CUDA library; raises loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FunasrB200Error(
+            "funasr_b200: %s not found — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or funasr_b200/csrc/build.sh). There is no CPU/PyTorch fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str):
+    if status != FA_OK:
+        raise FunasrB200Error("%s failed: %s (%d)" % (what, load().fa_status_string(status).decode(), status))

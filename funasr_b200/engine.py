@@ -1,0 +1,219 @@
+"""Host-side driver of the C ABI: packs weights into the FaEncoder/FaPredictor/FaDecoder structs, owns the
+device workspace, and sequences frontend -> encoder -> CIF predictor -> decoder -> greedy ids on the current
+CUDA stream.  PyTorch is used for device memory, streams and H2D/D2H copies only; every arithmetic op on the hot
+path is a kernel in libfunasr_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _abi
+from .synth import ParaformerConfig, sinusoid_inv_timescales
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def kaldi_mel_banks(n_mels=80, n_fft=512, fs=16000.0, low=20.0, high=0.0) -> torch.Tensor:
+    """Triangular mel filters exactly as torchaudio.compliance.kaldi.get_mel_banks (kaldi.py:436-511, vtln 1.0)
+    builds them, right-padded with one zero column (kaldi.py:621-627): [n_mels, n_fft/2 + 1] fp32.
+    Host-side table construction (a constant of the configuration), same torch ops in the same order."""
+    nyq = 0.5 * fs
+    if high <= 0.0:
+        high += nyq
+    bw = fs / n_fft
+    ml = 1127.0 * math.log(1.0 + low / 700.0)
+    mh = 1127.0 * math.log(1.0 + high / 700.0)
+    delta = (mh - ml) / (n_mels + 1)
+    b = torch.arange(n_mels).unsqueeze(1)
+    left, center, right = ml + b * delta, ml + (b + 1.0) * delta, ml + (b + 2.0) * delta
+    mel = (1127.0 * (1.0 + (bw * torch.arange(n_fft / 2)) / 700.0).log()).unsqueeze(0)
+    up = (mel - left) / (center - left)
+    down = (right - mel) / (right - center)
+    banks = torch.max(torch.zeros(1), torch.min(up, down))
+    return torch.nn.functional.pad(banks, (0, 1), value=0.0).float().contiguous()
+
+
+def num_lfr_frames(n_samples: int, win=400, shift=160, lfr_n=6) -> int:
+    m = 1 + (n_samples - win) // shift if n_samples >= win else 0
+    return (m + lfr_n - 1) // lfr_n
+
+
+class FrontendEngine:
+    """Fused Fbank+LFR+CMVN (fa_fbank_lfr_cmvn)."""
+
+    def __init__(self, cmvn: Optional[torch.Tensor], device):
+        self.lib = _abi.load()
+        self.device = torch.device(device)
+        self.cmvn = None if cmvn is None else cmvn.to(self.device, torch.float32).contiguous()
+        self.mel = kaldi_mel_banks().to(self.device)
+        self.window = torch.hamming_window(400, periodic=False, alpha=0.54, beta=0.46, dtype=torch.float32).to(self.device)
+
+    def __call__(self, wav: torch.Tensor, wav_lens: torch.Tensor, t_max: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """wav [B, Nmax] fp32 on device, wav_lens [B] int32 on device -> feats [B, t_max, 560], feat_lens [B] int32."""
+        assert wav.is_cuda and wav.dtype == torch.float32 and wav.stride(1) == 1
+        B = wav.shape[0]
+        feats = torch.empty((B, t_max, 560), dtype=torch.float32, device=self.device)
+        flens = torch.empty((B,), dtype=torch.int32, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _abi.check(self.lib.fa_fbank_lfr_cmvn(wav.data_ptr(), wav_lens.data_ptr(), B, wav.stride(0), _ptr(self.cmvn),
+                                              self.mel.data_ptr(), self.window.data_ptr(), feats.data_ptr(),
+                                              flens.data_ptr(), t_max, st), "fa_fbank_lfr_cmvn")
+        return feats, flens
+
+
+class ParaformerEngine:
+    """Packed weights + workspace + the encoder/predictor/decoder ABI calls."""
+
+    def __init__(self, state: Dict[str, torch.Tensor], cfg: ParaformerConfig, device, gemm_mode: str = "fp32",
+                 prefix_enc="encoder.", prefix_pred="predictor.", prefix_dec="decoder."):
+        self.lib = _abi.load()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.mode = _abi.GEMM_MODES[gemm_mode] if isinstance(gemm_mode, str) else int(gemm_mode)
+        self._keep: List[torch.Tensor] = []   # keeps every packed tensor alive
+        self._ws: Optional[torch.Tensor] = None
+        g = lambda k: self._dev(state[k])
+        D, K = cfg.d_model, cfg.kernel
+
+        def lin(prefix, bias=True, weight=None) -> _abi.FaLinear:
+            w = self._dev(state[prefix + ".weight"]) if weight is None else weight
+            b = self._dev(state[prefix + ".bias"]) if bias else None
+            out_f, in_f = w.shape
+            in_pad = (in_f + 63) // 64 * 64
+            planes = None
+            if self.mode != _abi.GEMM_F32_SIMT:
+                planes = torch.empty((3, out_f, in_pad), dtype=torch.bfloat16, device=self.device)
+                st = torch.cuda.current_stream(self.device).cuda_stream
+                _abi.check(self.lib.fa_split_bf16(w.data_ptr(), in_f, out_f, in_f, in_pad, planes.data_ptr(), st), "fa_split_bf16")
+                self._keep.append(planes)
+            return _abi.FaLinear(w.data_ptr(), _ptr(b), _ptr(planes), out_f, in_f, in_pad, 0)
+
+        def norm(prefix) -> _abi.FaNorm:
+            w, b = g(prefix + ".weight"), g(prefix + ".bias")
+            return _abi.FaNorm(w.data_ptr(), b.data_ptr(), w.numel(), cfg.ln_eps)
+
+        # ---- encoder
+        self.enc_layers = (_abi.FaEncLayer * cfg.enc_layers)()
+        for i in range(cfg.enc_layers):
+            p = prefix_enc + ("encoders0.0" if i == 0 else "encoders.%d" % (i - 1))
+            L = self.enc_layers[i]
+            L.norm1, L.norm2 = norm(p + ".norm1"), norm(p + ".norm2")
+            L.qkv, L.out = lin(p + ".self_attn.linear_q_k_v"), lin(p + ".self_attn.linear_out")
+            L.fsmn_w = g(p + ".self_attn.fsmn_block.weight").data_ptr()     # [512,1,11] contiguous == [512,11]
+            L.w1, L.w2 = lin(p + ".feed_forward.w_1"), lin(p + ".feed_forward.w_2")
+        self.pe_inv = self._dev(sinusoid_inv_timescales(cfg.feat_dim))
+        self.enc = _abi.FaEncoder(self.enc_layers, cfg.enc_layers, cfg.heads, K, 0, norm(prefix_enc + "after_norm"),
+                                  self.pe_inv.data_ptr())
+        # ---- predictor: Conv1d(512,512,3) weight [out, in, k] -> GEMM weight [out, k*512 + in]
+        cw = state[prefix_pred + "cif_conv1d.weight"]
+        cw = self._dev(cw.permute(0, 2, 1).reshape(cw.shape[0], -1))
+        conv = lin(prefix_pred + "cif_conv1d", weight=cw)
+        self.pred = _abi.FaPredictor(conv, g(prefix_pred + "cif_output.weight").data_ptr(),
+                                     g(prefix_pred + "cif_output.bias").data_ptr(), cfg.cif_threshold,
+                                     cfg.tail_threshold, 1.0, 0.0)
+        # ---- decoder
+        def dec_layer(L, p, full=True):
+            L.norm1 = norm(p + ".norm1")
+            L.ffn_w1, L.ffn_norm = lin(p + ".feed_forward.w_1"), norm(p + ".feed_forward.norm")
+            L.ffn_w2 = lin(p + ".feed_forward.w_2", bias=False)
+            if full:
+                L.norm2, L.norm3 = norm(p + ".norm2"), norm(p + ".norm3")
+                L.fsmn_w = g(p + ".self_attn.fsmn_block.weight").data_ptr()
+                L.q, L.kv, L.out = lin(p + ".src_attn.linear_q"), lin(p + ".src_attn.linear_k_v"), lin(p + ".src_attn.linear_out")
+
+        self.dec_layers = (_abi.FaDecLayer * cfg.dec_layers)()
+        for i in range(cfg.dec_layers):
+            dec_layer(self.dec_layers[i], prefix_dec + "decoders.%d" % i)
+        self.dec = _abi.FaDecoder()
+        self.dec.layers = self.dec_layers
+        self.dec.n_layers, self.dec.heads, self.dec.fsmn_k, self.dec.vocab = cfg.dec_layers, cfg.heads, K, cfg.vocab
+        dec_layer(self.dec.last, prefix_dec + "decoders3.0", full=False)
+        self.dec.after_norm = norm(prefix_dec + "after_norm")
+        self.dec.output = lin(prefix_dec + "output_layer")
+        torch.cuda.current_stream(self.device).synchronize()
+
+    # ------------------------------------------------------------------------------------------
+    def _dev(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.detach().to(self.device, torch.float32).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty((int(nbytes * 1.1) + 4096,), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def encode(self, feats: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+        """SANMEncoder.forward: feats [B,T,560], lens [B] int32 -> [B,T,512]."""
+        B, T, _ = feats.shape
+        out = torch.empty((B, T, self.cfg.d_model), dtype=torch.float32, device=self.device)
+        ws = self._workspace(self.lib.fa_sanm_encoder_workspace_bytes(B, T, self.mode))
+        _abi.check(self.lib.fa_sanm_encoder_forward(C.byref(self.enc), feats.data_ptr(), lens.data_ptr(), B, T, out.data_ptr(),
+                                                    self.mode, ws.data_ptr(), ws.numel(), self._stream()), "fa_sanm_encoder_forward")
+        return out
+
+    def predict(self, enc: torch.Tensor, lens: torch.Tensor):
+        """CifPredictorV2.forward -> (acoustic [B,T+1,512] zero padded, token_num [B] i32, alphas [B,T+1], peaks [B,T+1])."""
+        B, T, D = enc.shape
+        n_cap = T + 1
+        acoustic = torch.empty((B, n_cap, D), dtype=torch.float32, device=self.device)
+        tok = torch.empty((B,), dtype=torch.int32, device=self.device)
+        alphas = torch.empty((B, T + 1), dtype=torch.float32, device=self.device)
+        peaks = torch.empty((B, T + 1), dtype=torch.float32, device=self.device)
+        ws = self._workspace(self.lib.fa_cif_predictor_workspace_bytes(B, T, self.mode))
+        _abi.check(self.lib.fa_cif_predictor_forward(C.byref(self.pred), enc.data_ptr(), lens.data_ptr(), B, T, acoustic.data_ptr(),
+                                                     n_cap, tok.data_ptr(), alphas.data_ptr(), peaks.data_ptr(), self.mode,
+                                                     ws.data_ptr(), ws.numel(), self._stream()), "fa_cif_predictor_forward")
+        return acoustic, tok, alphas, peaks
+
+    def decode(self, enc: torch.Tensor, enc_lens: torch.Tensor, acoustic: torch.Tensor, tok_lens: torch.Tensor, n_max: int,
+               want_logp: bool = False):
+        """ParaformerSANMDecoder.forward + arg-max -> (argmax ids [B,n_max] i32, best logp [B,n_max], logp or None)."""
+        B, T, D = enc.shape
+        ids = torch.empty((B, n_max), dtype=torch.int32, device=self.device)
+        best = torch.empty((B, n_max), dtype=torch.float32, device=self.device)
+        logp = torch.empty((B, n_max, self.cfg.vocab), dtype=torch.float32, device=self.device) if want_logp else None
+        ws = self._workspace(self.lib.fa_paraformer_decoder_workspace_bytes(B, T, n_max, self.cfg.vocab, self.mode))
+        _abi.check(self.lib.fa_paraformer_decoder_forward(
+            C.byref(self.dec), enc.data_ptr(), enc_lens.data_ptr(), B, T, acoustic.data_ptr(), acoustic.shape[1],
+            tok_lens.data_ptr(), n_max, ids.data_ptr(), best.data_ptr(), _ptr(logp), 1, self.mode, ws.data_ptr(), ws.numel(),
+            self._stream()), "fa_paraformer_decoder_forward")
+        return ids, best, logp
+
+    def greedy_filter(self, ids: torch.Tensor, tok_lens: torch.Tensor, sos=1, eos=2, blank=0):
+        B, n_max = ids.shape
+        out = torch.empty_like(ids)
+        out_lens = torch.empty((B,), dtype=torch.int32, device=self.device)
+        _abi.check(self.lib.fa_greedy_filter(ids.data_ptr(), tok_lens.data_ptr(), B, n_max, sos, eos, blank, out.data_ptr(),
+                                             out_lens.data_ptr(), self._stream()), "fa_greedy_filter")
+        return out, out_lens
+
+    def forward_feats(self, feats: torch.Tensor, lens: torch.Tensor, want_taps: bool = False, sos=1, eos=2, blank=0):
+        """feats -> greedy ids.  One host synchronisation (the token counts), like the reference's `.item()`
+        (cif_predictor.py:311) — every other reference sync is gone."""
+        enc = self.encode(feats, lens)
+        acoustic, tok, alphas, peaks = self.predict(enc, lens)
+        tok_host = tok.cpu()                       # D2H + sync: B int32
+        n_max = int(tok_host.max()) if tok_host.numel() else 0
+        out = {"enc": enc, "alphas": alphas, "peaks": peaks, "token_num": tok_host, "acoustic": acoustic} if want_taps else {"token_num": tok_host}
+        if n_max < 1:                              # paraformer/model.py:615-616
+            out["ids"] = [[] for _ in range(feats.shape[0])]
+            return out
+        ids, best, logp = self.decode(enc, lens, acoustic, tok, n_max, want_logp=want_taps)
+        fids, flens = self.greedy_filter(ids, tok, sos, eos, blank)
+        fids_h, flens_h = fids.cpu(), flens.cpu()  # D2H of the result
+        out["ids"] = [fids_h[b, : int(flens_h[b])].tolist() for b in range(fids_h.shape[0])]
+        out["ids_padded"], out["ids_lens"] = fids_h, flens_h
+        if want_taps:
+            out.update(argmax=ids, best_logp=best, logp=logp)
+        return out

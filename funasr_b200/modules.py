@@ -1,0 +1,365 @@
+"""Reference-shaped plugin classes backed by the CUDA library.
+
+Each class mirrors the constructor arguments, the parameter names (state_dict keys) and the call contract of the
+reference class it replaces, so FunASR's own AutoModel.build_model / load_pretrained_model drive it unchanged:
+
+  WavFrontendB200             <- funasr/frontends/wav_frontend.py:91-196        (WavFrontend)
+  SANMEncoderB200             <- funasr/models/sanm/encoder.py:188-461          (SANMEncoder)
+  CifPredictorV2B200          <- funasr/models/paraformer/cif_predictor.py:209-314
+  ParaformerSANMDecoderB200   <- funasr/models/paraformer/decoder.py:234-449
+  ParaformerB200              <- funasr/models/paraformer/model.py:30-697       (Paraformer, inference path)
+
+The modules are torch.nn.Module only as *parameter containers* (so load_state_dict(strict=True), .to(device) and
+.eval() work as the reference expects); no torch.nn op runs on the hot path, and there is no CPU fallback —
+calling them without CUDA or without the built library raises.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _abi
+from .engine import FrontendEngine, ParaformerEngine, num_lfr_frames
+from .registry import get_tables, register
+from .synth import ParaformerConfig
+
+
+class _Container(nn.Module):
+    """Plain container so dotted parameter names reproduce the reference's state_dict keys."""
+
+
+def _add_param(root: nn.Module, dotted: str, shape) -> None:
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Container())
+        mod = getattr(mod, p)
+    mod.register_parameter(parts[-1], nn.Parameter(torch.zeros(*shape), requires_grad=False))
+
+
+class _ParamHolder(nn.Module):
+    def _specs(self) -> Dict[str, tuple]:
+        raise NotImplementedError
+
+    def _build(self):
+        for name, shape in self._specs().items():
+            _add_param(self, name, shape)
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise _abi.FunasrB200Error("%s runs only inside ParaformerB200 on a CUDA device" % type(self).__name__)
+
+
+def load_cmvn(cmvn_file: str) -> torch.Tensor:
+    """Kaldi-nnet text `am.mvn` -> [2, dim] (shift, scale); same parse as load_cmvn (wav_frontend.py:15-43):
+    the row after <AddShift>/<Rescale> starting with <LearnRateCoef>, tokens [3:-1]."""
+    with open(cmvn_file, "r", encoding="utf-8") as f:
+        lines = f.readlines()
+    means, scales = [], []
+    for i, line in enumerate(lines):
+        item = line.split()
+        if not item:
+            continue
+        if item[0] in ("<AddShift>", "<Rescale>") and i + 1 < len(lines):
+            nxt = lines[i + 1].split()
+            if nxt and nxt[0] == "<LearnRateCoef>":
+                vals = nxt[3:len(nxt) - 1]
+                if item[0] == "<AddShift>":
+                    means = vals
+                else:
+                    scales = vals
+    return torch.as_tensor(np.array([np.array(means).astype(np.float32), np.array(scales).astype(np.float32)]), dtype=torch.float32)
+
+
+@register("frontend_classes", "WavFrontendB200")
+class WavFrontendB200(nn.Module):
+    """Drop-in for WavFrontend: forward(input [B,Nmax] fp32, input_lengths) -> (feats [B,Tmax,560], lens int64)."""
+
+    def __init__(self, cmvn_file: str = None, fs: int = 16000, window: str = "hamming", n_mels: int = 80,
+                 frame_length: int = 25, frame_shift: int = 10, filter_length_min: int = -1, filter_length_max: int = -1,
+                 lfr_m: int = 1, lfr_n: int = 1, dither: float = 1.0, snip_edges: bool = True, upsacle_samples: bool = True,
+                 device: str = "cuda", cmvn: Optional[torch.Tensor] = None, **kwargs):
+        super().__init__()
+        self.fs, self.window, self.n_mels = fs, window, n_mels
+        self.frame_length, self.frame_shift = frame_length, frame_shift
+        self.lfr_m, self.lfr_n, self.dither = lfr_m, lfr_n, dither
+        self.snip_edges, self.upsacle_samples, self.cmvn_file = snip_edges, upsacle_samples, cmvn_file
+        self.cmvn = cmvn if cmvn is not None else (None if cmvn_file is None else load_cmvn(cmvn_file))
+        if (fs, window, n_mels, frame_length, frame_shift, lfr_m, lfr_n, snip_edges, upsacle_samples) != \
+                (16000, "hamming", 80, 25, 10, 7, 6, True, True):
+            raise _abi.FunasrB200Error("WavFrontendB200 is built for the Paraformer/SenseVoice frontend config "
+                                       "(16 kHz, hamming 25/10 ms, 80 mel, LFR 7/6, snip_edges)")
+        # dither: the reference default 1.0 adds torch.randn noise per frame (kaldi.py:179-181), which cannot be
+        # reproduced bit-for-bit by construction; this backend is deterministic (== dither 0.0).
+        self._device = device
+        self._engine: Optional[FrontendEngine] = None
+
+    def output_size(self) -> int:
+        return self.n_mels * self.lfr_m
+
+    def engine(self, device=None) -> FrontendEngine:
+        dev = torch.device(device or self._device)
+        if self._engine is None or self._engine.device != dev:
+            self._engine = FrontendEngine(self.cmvn, dev)
+        return self._engine
+
+    def forward(self, input: torch.Tensor, input_lengths, device=None, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        eng = self.engine(device if device is not None else (input.device if input.is_cuda else None))
+        lens = [int(x) for x in (input_lengths.tolist() if torch.is_tensor(input_lengths) else input_lengths)]
+        if min(lens) < 400:
+            raise _abi.FunasrB200Error("utterances shorter than one 25 ms frame (400 samples) are not supported")
+        t_max = max(num_lfr_frames(n) for n in lens)
+        wav = input.to(eng.device, torch.float32, non_blocking=True).contiguous()
+        wl = torch.tensor(lens, dtype=torch.int32).to(eng.device, non_blocking=True)
+        feats, flens = eng(wav, wl, t_max)
+        return feats, flens.to(torch.int64)
+
+
+@register("encoder_classes", "SANMEncoderB200")
+class SANMEncoderB200(_ParamHolder):
+    def __init__(self, input_size: int, output_size: int = 256, attention_heads: int = 4, linear_units: int = 2048,
+                 num_blocks: int = 6, kernel_size: int = 11, sanm_shfit: int = 0, input_layer: str = "pe",
+                 normalize_before: bool = True, selfattention_layer_type: str = "sanm", **kwargs):
+        super().__init__()
+        if (output_size, attention_heads, input_layer, normalize_before, selfattention_layer_type, sanm_shfit) != \
+                (512, 4, "pe", True, "sanm", 0) or input_size > 560:
+            raise _abi.FunasrB200Error("SANMEncoderB200 supports the Paraformer-large / SenseVoiceSmall encoder shape "
+                                       "(d=512, 4 heads, input_layer='pe', sanm, normalize_before)")
+        self.input_size, self._output_size = input_size, output_size
+        self.heads, self.ffn, self.num_blocks, self.kernel_size = attention_heads, linear_units, num_blocks, kernel_size
+        self._build()
+
+    def output_size(self) -> int:
+        return self._output_size
+
+    def _specs(self):
+        D, F, K = self._output_size, self.ffn, self.kernel_size
+        s = {}
+
+        def layer(p, in_size):
+            s[p + ".self_attn.linear_out.weight"] = (D, D)
+            s[p + ".self_attn.linear_out.bias"] = (D,)
+            s[p + ".self_attn.linear_q_k_v.weight"] = (3 * D, in_size)
+            s[p + ".self_attn.linear_q_k_v.bias"] = (3 * D,)
+            s[p + ".self_attn.fsmn_block.weight"] = (D, 1, K)
+            s[p + ".feed_forward.w_1.weight"] = (F, D)
+            s[p + ".feed_forward.w_1.bias"] = (F,)
+            s[p + ".feed_forward.w_2.weight"] = (D, F)
+            s[p + ".feed_forward.w_2.bias"] = (D,)
+            s[p + ".norm1.weight"] = (in_size,)
+            s[p + ".norm1.bias"] = (in_size,)
+            s[p + ".norm2.weight"] = (D,)
+            s[p + ".norm2.bias"] = (D,)
+
+        layer("encoders0.0", self.input_size)
+        for i in range(self.num_blocks - 1):
+            layer("encoders.%d" % i, D)
+        s["after_norm.weight"] = (D,)
+        s["after_norm.bias"] = (D,)
+        return s
+
+
+@register("predictor_classes", "CifPredictorV2B200")
+class CifPredictorV2B200(_ParamHolder):
+    def __init__(self, idim, l_order, r_order, threshold=1.0, dropout=0.1, smooth_factor=1.0, noise_threshold=0,
+                 tail_threshold=0.0, tail_mask=True, **kwargs):
+        super().__init__()
+        if (idim, l_order, r_order, smooth_factor, noise_threshold, tail_mask) != (512, 1, 1, 1.0, 0, True) or tail_threshold <= 0:
+            raise _abi.FunasrB200Error("CifPredictorV2B200 supports idim=512, l_order=r_order=1, tail_threshold>0, tail_mask")
+        self.idim, self.threshold, self.tail_threshold = idim, threshold, tail_threshold
+        self._build()
+
+    def _specs(self):
+        D = self.idim
+        return {"cif_conv1d.weight": (D, D, 3), "cif_conv1d.bias": (D,), "cif_output.weight": (1, D), "cif_output.bias": (1,)}
+
+
+@register("decoder_classes", "ParaformerSANMDecoderB200")
+class ParaformerSANMDecoderB200(_ParamHolder):
+    def __init__(self, vocab_size: int, encoder_output_size: int, attention_heads: int = 4, linear_units: int = 2048,
+                 num_blocks: int = 6, att_layer_num: int = 6, kernel_size: int = 21, sanm_shfit: int = 0, **kwargs):
+        super().__init__()
+        if encoder_output_size != 512 or attention_heads != 4 or att_layer_num != num_blocks or sanm_shfit != 0:
+            raise _abi.FunasrB200Error("ParaformerSANMDecoderB200 supports d=512, 4 heads, att_layer_num == num_blocks, sanm_shfit=0")
+        self.vocab_size, self.D, self.ffn = vocab_size, encoder_output_size, linear_units
+        self.num_blocks, self.kernel_size = num_blocks, kernel_size
+        self._build()
+
+    def _specs(self):
+        D, F, K, V = self.D, self.ffn, self.kernel_size, self.vocab_size
+        s = {"embed.0.weight": (V, D), "after_norm.weight": (D,), "after_norm.bias": (D,),
+             "output_layer.weight": (V, D), "output_layer.bias": (V,)}
+
+        def ffn(p):
+            s[p + ".feed_forward.w_1.weight"] = (F, D)
+            s[p + ".feed_forward.w_1.bias"] = (F,)
+            s[p + ".feed_forward.w_2.weight"] = (D, F)
+            s[p + ".feed_forward.norm.weight"] = (F,)
+            s[p + ".feed_forward.norm.bias"] = (F,)
+
+        for i in range(self.num_blocks):
+            p = "decoders.%d" % i
+            ffn(p)
+            s[p + ".self_attn.fsmn_block.weight"] = (D, 1, K)
+            for nme, shp in (("linear_q", (D, D)), ("linear_k_v", (2 * D, D)), ("linear_out", (D, D))):
+                s[p + ".src_attn.%s.weight" % nme] = shp
+                s[p + ".src_attn.%s.bias" % nme] = (shp[0],)
+            for n in ("norm1", "norm2", "norm3"):
+                s[p + ".%s.weight" % n] = (D,)
+                s[p + ".%s.bias" % n] = (D,)
+        ffn("decoders3.0")
+        s["decoders3.0.norm1.weight"] = (D,)
+        s["decoders3.0.norm1.bias"] = (D,)
+        return s
+
+
+def _as_wave_list(data_in, fs: int, frontend=None, **kwargs) -> List[torch.Tensor]:
+    """ndarray / tensor / list thereof -> list of 1-D fp32 tensors.  Paths, bytes and urls are delegated to the
+    reference's own loader (funasr.utils.load_utils.load_audio_text_image_video, model.py:578) when FunASR is
+    installed; that part of the pipeline (audio decode / resample) is outside this backend's scope."""
+    items = data_in if isinstance(data_in, (list, tuple)) else [data_in]
+    out = []
+    for x in items:
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(x)
+        if not torch.is_tensor(x):
+            try:
+                from funasr.utils.load_utils import load_audio_text_image_video
+            except Exception as e:  # pragma: no cover
+                raise _abi.FunasrB200Error("only ndarray / tensor waveforms are accepted without FunASR installed") from e
+            x = load_audio_text_image_video(x, fs=fs, audio_fs=kwargs.get("fs", 16000), data_type=kwargs.get("data_type", "sound"))
+        x = x.to(torch.float32)
+        if x.dim() > 1:
+            x = x.mean(dim=0) if x.shape[0] > 1 else x[0]     # mono (load_utils.py:extract_fbank)
+        out.append(x.contiguous())
+    return out
+
+
+@register("model_classes", "ParaformerB200")
+class ParaformerB200(nn.Module):
+    """Drop-in for funasr.models.paraformer.model.Paraformer on the offline greedy inference path."""
+
+    def __init__(self, specaug=None, specaug_conf=None, normalize=None, normalize_conf=None, encoder: str = None,
+                 encoder_conf: dict = None, decoder: str = None, decoder_conf: dict = None, ctc=None, ctc_conf=None,
+                 predictor: str = None, predictor_conf: dict = None, ctc_weight: float = 0.0, input_size: int = 80,
+                 vocab_size: int = -1, ignore_id: int = -1, blank_id: int = 0, sos: int = 1, eos: int = 2,
+                 gemm_mode: str = "fp32", **kwargs):
+        super().__init__()
+        tables = get_tables()
+        enc_cls = tables.encoder_classes.get(encoder) if isinstance(encoder, str) else encoder
+        dec_cls = tables.decoder_classes.get(decoder) if isinstance(decoder, str) else decoder
+        pred_cls = tables.predictor_classes.get(predictor) if isinstance(predictor, str) else predictor
+        # an unmodified reference config names the reference classes; they map onto the B200 components
+        enc_cls = enc_cls if (enc_cls is not None and issubclass(enc_cls, _ParamHolder)) else SANMEncoderB200
+        dec_cls = dec_cls if (dec_cls is not None and issubclass(dec_cls, _ParamHolder)) else ParaformerSANMDecoderB200
+        pred_cls = pred_cls if (pred_cls is not None and issubclass(pred_cls, _ParamHolder)) else CifPredictorV2B200
+        self.encoder = enc_cls(input_size=input_size, **(encoder_conf or {}))                       # model.py:131-132
+        self.decoder = dec_cls(vocab_size=vocab_size, encoder_output_size=self.encoder.output_size(), **(decoder_conf or {}))
+        self.predictor = pred_cls(**(predictor_conf or {}))                                         # model.py:149-150
+        self.vocab_size, self.ignore_id = vocab_size, ignore_id
+        self.blank_id, self.sos, self.eos = blank_id, sos, eos
+        self.gemm_mode = gemm_mode
+        self.cfg = ParaformerConfig(enc_layers=self.encoder.num_blocks, dec_layers=self.decoder.num_blocks, vocab=vocab_size,
+                                    kernel=self.encoder.kernel_size, tail_threshold=self.predictor.tail_threshold,
+                                    cif_threshold=self.predictor.threshold)
+        self._engine: Optional[ParaformerEngine] = None
+        self._pin: Optional[torch.Tensor] = None
+
+    # -- weights enter through load_pretrained_model -> load_state_dict(strict=True) -> this hook
+    #    (funasr/train_utils/load_pretrained_model.py:104-113)
+    def on_pretrained_model_loaded(self, loaded_keys=None):
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def engine(self, device=None) -> ParaformerEngine:
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _abi.FunasrB200Error("ParaformerB200 needs a CUDA device (got %s); there is no CPU path" % dev)
+        if self._engine is None or self._engine.device != dev:
+            self._engine = ParaformerEngine(self.state_dict(), self.cfg, dev, gemm_mode=self.gemm_mode)
+        return self._engine
+
+    # -- stage methods with the reference's names (model.py:286-346), tensors in / tensors out
+    def encode(self, speech: torch.Tensor, speech_lengths: torch.Tensor, **kwargs):
+        eng = self.engine(speech.device)
+        lens = speech_lengths.to(speech.device, torch.int32)
+        return eng.encode(speech.contiguous(), lens), lens
+
+    def calc_predictor(self, encoder_out, encoder_out_lens):
+        eng = self.engine(encoder_out.device)
+        acoustic, tok, alphas, peaks = eng.predict(encoder_out, encoder_out_lens.to(torch.int32))
+        n = int(tok.max().item())
+        return acoustic[:, :n, :], tok.to(torch.float32), alphas, peaks
+
+    def cal_decoder_with_predictor(self, encoder_out, encoder_out_lens, sematic_embeds, ys_pad_lens):
+        eng = self.engine(encoder_out.device)
+        n_max = sematic_embeds.shape[1]
+        tok = ys_pad_lens.to(torch.int32)
+        _, _, logp = eng.decode(encoder_out, encoder_out_lens.to(torch.int32), sematic_embeds.contiguous(), tok, n_max, want_logp=True)
+        return logp, ys_pad_lens
+
+    def inference(self, data_in, data_lengths=None, key: list = None, tokenizer=None, frontend=None, **kwargs):
+        """Same contract as Paraformer.inference (model.py:534-697): returns (results, meta_data)."""
+        device = torch.device(kwargs.get("device", "cuda"))
+        if device.type != "cuda":
+            raise _abi.FunasrB200Error("ParaformerB200.inference needs device='cuda' (no CPU fallback)")
+        meta_data = {}
+        eng = self.engine(device)
+        if isinstance(data_in, torch.Tensor) and kwargs.get("data_type", "sound") == "fbank":
+            speech = data_in if data_in.dim() == 3 else data_in[None]
+            speech_lengths = data_lengths.reshape(-1) if data_lengths is not None else torch.tensor([speech.shape[1]])
+            speech = speech.to(device, torch.float32).contiguous()
+            lens = speech_lengths.to(device, torch.int32)
+        else:
+            t1 = time.perf_counter()
+            wavs = _as_wave_list(data_in, fs=getattr(frontend, "fs", 16000), **kwargs)
+            t2 = time.perf_counter()
+            meta_data["load_data"] = f"{t2 - t1:0.3f}"
+            if not isinstance(frontend, WavFrontendB200):
+                raise _abi.FunasrB200Error("ParaformerB200 needs frontend='WavFrontendB200' (the fused CUDA frontend)")
+            wl = [int(w.numel()) for w in wavs]
+            nmax = max(wl)
+            if self._pin is None or self._pin.shape[0] < len(wavs) or self._pin.shape[1] < nmax:
+                self._pin = torch.zeros((len(wavs), nmax), dtype=torch.float32).pin_memory()
+            pin = self._pin[: len(wavs), :nmax]
+            for i, w in enumerate(wavs):                      # pad_sequence (load_utils.py:412)
+                pin[i, : wl[i]].copy_(w)
+                pin[i, wl[i]:].zero_()
+            speech, flens = frontend.forward(pin, wl, device=device)
+            lens = flens.to(torch.int32)
+            meta_data["extract_feat"] = f"{time.perf_counter() - t2:0.3f}"
+            meta_data["batch_data_time"] = sum(num_lfr_frames(n) for n in wl) * frontend.frame_shift * frontend.lfr_n / 1000
+        out = eng.forward_feats(speech, lens, sos=self.sos, eos=self.eos, blank=self.blank_id)
+        ids = out["ids"]
+        if max((int(t) for t in out["token_num"].tolist()), default=0) < 1:
+            return [], meta_data                              # model.py:615-616
+        b = len(ids)
+        if key is None:
+            key = ["utt%d" % i for i in range(b)]
+        if isinstance(key[0], (list, tuple)):
+            key = key[0]
+        if len(key) < b:
+            key = key * b
+        results = []
+        for i in range(b):
+            token_int = ids[i]
+            if tokenizer is not None:                         # CPU string work stays the reference's (model.py:668-687)
+                token = tokenizer.ids2tokens(token_int)
+                text = tokenizer.tokens2text(token)
+                if not hasattr(tokenizer, "bpemodel"):
+                    try:
+                        from funasr.utils import postprocess_utils
+                        text, _ = postprocess_utils.sentence_postprocess(token)
+                    except ImportError:
+                        pass
+                results.append({"key": key[i], "text": text})
+            else:
+                results.append({"key": key[i], "token_int": token_int})
+        return results, meta_data

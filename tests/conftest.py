@@ -1,0 +1,64 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# name: (config name, weight seed, [(n_samples, wav seed, kind)], use_cmvn) — must match oracle/make_golden.py:CASES
+GOLDEN_CASES = {
+    "tiny_ragged3": ("tiny", 3, [(48000, 1, "speechlike"), (27200, 2, "noise"), (38437, 3, "speechlike")], True),
+    "tiny_single": ("tiny", 3, [(16000, 4, "speechlike")], False),
+    "large_ragged2": ("large", 0, [(480000, 0, "speechlike"), (196800, 5, "speechlike")], True),
+}
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_case(name):
+    from funasr_b200 import synth
+    cfg_name, wseed, specs, use_cmvn = GOLDEN_CASES[name]
+    cfg = synth.PARAFORMER_TINY if cfg_name == "tiny" else synth.PARAFORMER_LARGE
+    gold = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    wavs = [synth.make_wav(n, s, k) for (n, s, k) in specs]
+    cmvn = synth.make_cmvn(cfg, seed=1) if use_cmvn else None
+    if cmvn is not None:
+        # the golden run passed CMVN through an am.mvn text file written with %.9g (lossless for fp32)
+        cmvn = torch.tensor(np.array([[float("%.9g" % v) for v in row] for row in cmvn.tolist()], dtype=np.float32))
+    return cfg, wseed, wavs, cmvn, gold
+
+
+_STATE_CACHE = {}
+
+
+def state_dict_for(cfg, seed):
+    from funasr_b200 import synth
+    key = (cfg.enc_layers, cfg.dec_layers, cfg.vocab, seed)
+    if key not in _STATE_CACHE:
+        _STATE_CACHE.clear()            # at most one (large ~880 MB) dict alive
+        _STATE_CACHE[key] = synth.make_state_dict(cfg, seed)
+    return _STATE_CACHE[key]
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))

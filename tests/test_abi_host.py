@@ -1,0 +1,177 @@
+"""CPU: the C-ABI library loads and exports every symbol include/funasr_b200.h declares; host-side logic
+(registry drop-in surface, parameter names, cmvn parsing, sharding + all-gather over gloo with 2 ranks)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+import funasr_b200
+from funasr_b200 import _abi, synth
+from funasr_b200.engine import kaldi_mel_banks, num_lfr_frames
+from funasr_b200.sharding import shard_utterances
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "funasr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_abi.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_abi.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), "library does not export %s" % s
+        assert s in _abi.SIGNATURES, "ctypes mirror lacks %s" % s
+    assert set(_abi.SIGNATURES) == set(syms)
+    lib.fa_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.fa_version()
+
+
+def test_no_cpu_fallback():
+    m = _tiny_model()
+    with pytest.raises(_abi.FunasrB200Error):
+        m.inference([np.zeros(16000, dtype=np.float32)], key=["a"], frontend=None, device="cpu")
+    with pytest.raises(_abi.FunasrB200Error):
+        m.encoder(torch.zeros(1, 4, 560), torch.tensor([4]))
+
+
+def _tiny_conf():
+    cfg = synth.PARAFORMER_TINY
+    return dict(
+        encoder="SANMEncoderB200",
+        encoder_conf=dict(output_size=512, attention_heads=4, linear_units=2048, num_blocks=cfg.enc_layers, dropout_rate=0.1,
+                          input_layer="pe", pos_enc_class="SinusoidalPositionEncoder", normalize_before=True, kernel_size=11,
+                          sanm_shfit=0, selfattention_layer_type="sanm"),
+        decoder="ParaformerSANMDecoderB200",
+        decoder_conf=dict(attention_heads=4, linear_units=2048, num_blocks=cfg.dec_layers, att_layer_num=cfg.dec_layers,
+                          kernel_size=11, sanm_shfit=0),
+        predictor="CifPredictorV2B200",
+        predictor_conf=dict(idim=512, threshold=1.0, l_order=1, r_order=1, tail_threshold=0.45),
+        input_size=560, vocab_size=cfg.vocab)
+
+
+def _tiny_model():
+    return funasr_b200.ParaformerB200(**_tiny_conf())
+
+
+def test_state_dict_names_match_reference_layout():
+    """the synthetic dict uses the reference's names; strict load must accept it unchanged."""
+    m = _tiny_model()
+    sd = synth.make_state_dict(synth.PARAFORMER_TINY, 3)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=True)
+    full = synth.ParaformerConfig()
+    assert full.feat_dim == 560
+
+
+def test_registry_surface():
+    t = funasr_b200.get_tables()
+    for table, key in [("model_classes", "ParaformerB200"), ("frontend_classes", "WavFrontendB200"),
+                       ("encoder_classes", "SANMEncoderB200"), ("predictor_classes", "CifPredictorV2B200"),
+                       ("decoder_classes", "ParaformerSANMDecoderB200")]:
+        assert key in getattr(t, table)
+
+
+def test_cmvn_file_parse():
+    cm = funasr_b200.load_cmvn(os.path.join(GOLDEN, "am_synth.mvn"))
+    ref = synth.make_cmvn(synth.PARAFORMER_LARGE, seed=1)
+    assert cm.shape == (2, 560) and torch.allclose(cm, ref, rtol=0, atol=0)
+
+
+def test_frame_count_and_mel_banks():
+    assert num_lfr_frames(480000) == 500 and num_lfr_frames(80000) == 83 and num_lfr_frames(400) == 1 and num_lfr_frames(399) == 0
+    import paraformer_oracle as O
+    banks = torch.nn.functional.pad(O.get_mel_banks(), (0, 1))
+    assert torch.equal(kaldi_mel_banks(), banks.float())
+    assert torch.equal(synth.sinusoid_inv_timescales(560), torch.exp(torch.arange(280.0) * -(torch.log(torch.tensor([10000.0])) / 279)))
+
+
+def test_shard_utterances_partition():
+    g = torch.Generator().manual_seed(1234)
+    dur = (5 + 25 * torch.rand(512, generator=g)).tolist()
+    for w in (1, 2, 4, 8):
+        sh = shard_utterances(dur, w)
+        assert sorted(i for s in sh for i in s) == list(range(512))
+        assert max(len(s) for s in sh) - min(len(s) for s in sh) <= 1
+        loads = [sum(dur[i] for i in s) for s in sh]
+        assert max(loads) / min(loads) < 1.02
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from funasr_b200.sharding import shard_utterances, gather_token_ids
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+n = 11
+dur = [float((7 * i) % 13 + 1) for i in range(n)]
+shards = shard_utterances(dur, 2)
+mine = shards[dist.get_rank()]
+fake = lambda i: [100 * i + k for k in range(i % 5)]       # utterance i "decodes" to a known id list
+res = gather_token_ids([fake(i) for i in mine], mine, n, width=16)
+assert res == [fake(i) for i in range(n)], res
+dist.barrier(); dist.destroy_process_group(); print("ok")
+'''
+
+
+def test_gather_token_ids_two_ranks_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("ok" in o for o in outs)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/funasr"), reason="live reference not present")
+def test_plugs_into_reference_tables_and_automodel_build():
+    """Drop-in surface against the real FunASR: classes land in funasr.register.tables and AutoModel.build_model
+    constructs ParaformerB200 + WavFrontendB200 and strict-loads a checkpoint via load_pretrained_model (CPU build
+    only — running it needs a GPU)."""
+    import ref_shim
+    ref_shim.import_reference()
+    from funasr.register import tables
+    funasr_b200.install()
+    assert tables.model_classes["ParaformerB200"] is funasr_b200.ParaformerB200
+    assert tables.frontend_classes["WavFrontendB200"] is funasr_b200.WavFrontendB200
+    from funasr import AutoModel
+    import tempfile
+    cfg = synth.PARAFORMER_TINY
+    conf = _tiny_conf()
+    tokens = ["<blank>", "<s>", "</s>"] + ["t%d" % i for i in range(cfg.vocab - 4)] + ["<unk>"]
+    with tempfile.TemporaryDirectory() as tmp:
+        pt = os.path.join(tmp, "model.pt")
+        torch.save(synth.make_state_dict(cfg, 3), pt)
+        am = AutoModel(model="ParaformerB200", model_conf={}, encoder=conf["encoder"], encoder_conf=conf["encoder_conf"],
+                       decoder=conf["decoder"], decoder_conf=conf["decoder_conf"], predictor=conf["predictor"],
+                       predictor_conf=conf["predictor_conf"], frontend="WavFrontendB200",
+                       frontend_conf=dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6,
+                                          dither=0.0, cmvn_file=os.path.join(GOLDEN, "am_synth.mvn")),
+                       tokenizer="CharTokenizer", tokenizer_conf=dict(token_list=tokens, unk_symbol="<unk>", split_with_space=True),
+                       device="cpu", disable_update=True, disable_pbar=True, init_param=pt)
+    assert isinstance(am.model, funasr_b200.ParaformerB200)
+    assert isinstance(am.kwargs["frontend"], funasr_b200.WavFrontendB200)
+    sd = synth.make_state_dict(cfg, 3)
+    assert torch.equal(am.model.state_dict()["encoder.encoders.0.feed_forward.w_1.weight"], sd["encoder.encoders.0.feed_forward.w_1.weight"])
+    # override mode: the reference's own keys now resolve to this backend
+    saved = {k: getattr(tables, k[0]).get(k[1]) for k in funasr_b200.registry.DROP_IN_KEYS}
+    try:
+        funasr_b200.install(override_reference_keys=True)
+        assert tables.model_classes["Paraformer"] is funasr_b200.ParaformerB200
+    finally:
+        for (tb, key), cls in saved.items():
+            if cls is not None:
+                getattr(tables, tb)[key] = cls

@@ -1,0 +1,249 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle on the same seeded inputs, against the
+committed golden vectors of the reference, and — at BASELINE sizes — through size-independent properties.
+
+Bars: integer outcomes (frame counts, token counts, greedy ids) bit-exact; floating point within 1e-3 relative of the
+fp32 reference (rel = max|a-b| / max|b|), the tolerance the north star states for logits; the frontend within 2e-4
+absolute on log-mel features (fp32 FFT vs torch's pocketfft).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_case, rel_err, state_dict_for
+
+import paraformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _lib():
+    from funasr_b200 import _abi
+    return _abi, _abi.load()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ----------------------------------------------------------------------------------------------- frontend
+def _run_frontend(wavs, cmvn):
+    from funasr_b200.engine import FrontendEngine, num_lfr_frames
+    eng = FrontendEngine(cmvn, DEV)
+    lens = [w.numel() for w in wavs]
+    pad = torch.nn.utils.rnn.pad_sequence(wavs, batch_first=True).to(DEV)
+    t_max = max(num_lfr_frames(n) for n in lens)
+    feats, fl = eng(pad, torch.tensor(lens, dtype=torch.int32, device=DEV), t_max)
+    torch.cuda.synchronize()
+    return feats.cpu(), fl.cpu()
+
+
+@pytest.mark.parametrize("lens,use_cmvn", [([16000, 400, 8123, 559, 560, 1359, 1360], True), ([48000, 27200], False), ([480000], True)])
+def test_fbank_lfr_cmvn_vs_oracle(lens, use_cmvn):
+    from funasr_b200 import synth
+    wavs = [synth.make_wav(n, 20 + i, "speechlike" if i % 2 == 0 else "noise") for i, n in enumerate(lens)]
+    cmvn = synth.make_cmvn(synth.PARAFORMER_LARGE, 2) if use_cmvn else None
+    ref, ref_len = O.frontend(wavs, cmvn)
+    got, got_len = _run_frontend(wavs, cmvn)
+    assert got_len.tolist() == ref_len.tolist()                    # integer: exact
+    assert got.shape == ref.shape
+    for b, n in enumerate(ref_len.tolist()):
+        assert np.abs(got[b, :n].numpy() - ref[b, :n].numpy()).max() <= 2e-4
+        assert float(got[b, n:].abs().max()) == 0.0 if n < got.shape[1] else True   # pad_sequence(0.0)
+
+
+def test_fbank_silence_and_clipping_edges():
+    """All-zero audio hits the log floor (log eps); full-scale square wave exercises large magnitudes."""
+    z = torch.zeros(3200)
+    sq = torch.sign(torch.sin(torch.arange(4000.0) * 0.3)).float()
+    ref, _ = O.frontend([z, sq], None)
+    got, _ = _run_frontend([z, sq], None)
+    assert np.abs(got[0, :4].numpy() - ref[0, :4].numpy()).max() <= 2e-4
+    assert np.abs(got[1].numpy() - ref[1].numpy()).max() <= 5e-4
+
+
+# ------------------------------------------------------------------------------------------- operator level
+def test_layernorm_vs_oracle():
+    abi, lib = _lib()
+    g = torch.Generator().manual_seed(0)
+    for n, rows in [(512, 1000), (560, 333), (2048, 77)]:
+        x = torch.randn(rows, n, generator=g) * 3 + 0.5
+        w, b = 1 + 0.1 * torch.randn(n, generator=g), 0.1 * torch.randn(n, generator=g)
+        xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+        y = torch.empty_like(xd)
+        nm = abi.FaNorm(wd.data_ptr(), bd.data_ptr(), n, 1e-12)
+        abi.check(lib.fa_layernorm(xd.data_ptr(), rows, C.byref(nm), y.data_ptr(), None, 1.0, 1, _st()), "ln")
+        assert rel_err(y.cpu().numpy(), O.layer_norm(x, w, b).numpy()) <= 1e-5
+    # fused x*sqrt(512)+PE prologue (encoder.py:409,428)
+    from funasr_b200 import synth
+    B, T, n = 2, 97, 560
+    x = torch.randn(B, T, n, generator=g)
+    w, b = 1 + 0.1 * torch.randn(n, generator=g), 0.1 * torch.randn(n, generator=g)
+    inv = synth.sinusoid_inv_timescales(n).to(DEV)
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    y = torch.empty_like(xd)
+    nm = abi.FaNorm(wd.data_ptr(), bd.data_ptr(), n, 1e-12)
+    abi.check(lib.fa_layernorm(xd.data_ptr(), B * T, C.byref(nm), y.data_ptr(), inv.data_ptr(), 512 ** 0.5, T, _st()), "ln+pe")
+    ref = O.layer_norm(x * 512 ** 0.5 + O.sinusoid_pe(T, n), w, b)
+    assert rel_err(y.cpu().numpy(), ref.numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("rows,out_f,in_f", [(1000, 1536, 560), (777, 512, 2048), (130, 8404, 512), (64, 1000, 512)])
+def test_linear_fp32_vs_oracle(rows, out_f, in_f):
+    abi, lib = _lib()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(rows, in_f, generator=g)
+    w = torch.randn(out_f, in_f, generator=g) / in_f ** 0.5
+    b = torch.randn(out_f, generator=g) * 0.1
+    r1 = torch.randn(rows, out_f, generator=g)
+    xd, wd, bd, r1d = x.to(DEV), w.to(DEV), b.to(DEV), r1.to(DEV)
+    y = torch.empty(rows, out_f, device=DEV)
+    lin = abi.FaLinear(wd.data_ptr(), bd.data_ptr(), None, out_f, in_f, (in_f + 63) // 64 * 64, 0)
+    abi.check(lib.fa_linear(xd.data_ptr(), in_f, rows, C.byref(lin), 1, r1d.data_ptr(), out_f, None, 0, y.data_ptr(), out_f,
+                            abi.GEMM_F32_SIMT, None, 0, _st()), "linear")
+    ref = torch.relu(torch.nn.functional.linear(x, w, b)) + r1
+    assert rel_err(y.cpu().numpy(), ref.numpy()) <= 2e-6
+
+
+def test_fsmn_vs_oracle():
+    abi, lib = _lib()
+    g = torch.Generator().manual_seed(2)
+    B, T, Cn = 3, 150, 512
+    lens = torch.tensor([150, 1, 77], dtype=torch.int32)
+    qkv = torch.randn(B, T, 1536, generator=g)
+    w = torch.randn(Cn, 1, 11, generator=g) * 0.2
+    res = torch.randn(B, T, Cn, generator=g)
+    mask = (torch.arange(T)[None, :] < lens[:, None]).float()[:, :, None]
+    ref = O.fsmn(qkv[:, :, 1024:], w, mask)
+    qd, wd, ld, rd = qkv.to(DEV), w.to(DEV), lens.to(DEV), res.to(DEV)
+    out = torch.empty(B, T, Cn, device=DEV)
+    abi.check(lib.fa_fsmn(qd.data_ptr() + 1024 * 4, 1536, ld.data_ptr(), B, T, Cn, wd.data_ptr(), 11, None, 0, out.data_ptr(), Cn, _st()), "fsmn")
+    assert rel_err(out.cpu().numpy(), ref.numpy()) <= 1e-6
+    abi.check(lib.fa_fsmn(qd.data_ptr() + 1024 * 4, 1536, ld.data_ptr(), B, T, Cn, wd.data_ptr(), 11, rd.data_ptr(), Cn, out.data_ptr(), Cn, _st()), "fsmn+res")
+    assert rel_err(out.cpu().numpy(), (res + ref).numpy()) <= 1e-6
+
+
+@pytest.mark.parametrize("tq,tk,lens", [(130, 130, [130, 1, 65]), (37, 211, [211, 64, 129])])
+def test_attention_vs_oracle(tq, tk, lens):
+    abi, lib = _lib()
+    g = torch.Generator().manual_seed(3)
+    B, H, D = 3, 4, 512
+    q = torch.randn(B, tq, D, generator=g) * 1.5
+    k = torch.randn(B, tk, D, generator=g) * 1.5
+    v = torch.randn(B, tk, D, generator=g)
+    kl = torch.tensor(lens, dtype=torch.int32)
+    mask = (torch.arange(tk)[None, :] < kl[:, None])[:, None, :]
+    ref = O.mh_attention(q, k, v, mask, H)
+    qd, kd, vd, ld = q.to(DEV), k.to(DEV), v.to(DEV), kl.to(DEV)
+    ctx = torch.empty(B, tq, D, device=DEV)
+    abi.check(lib.fa_attention(qd.data_ptr(), D, kd.data_ptr(), D, vd.data_ptr(), D, ld.data_ptr(), B, H, tq, tk, ctx.data_ptr(), D, _st()), "attn")
+    assert rel_err(ctx.cpu().numpy(), ref.numpy()) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ model level
+def _engine(cfg, wseed, mode="fp32"):
+    from funasr_b200.engine import ParaformerEngine
+    return ParaformerEngine(state_dict_for(cfg, wseed), cfg, DEV, gemm_mode=mode)
+
+
+def _run_model(cfg, wseed, wavs, cmvn, mode="fp32"):
+    from funasr_b200.engine import FrontendEngine, num_lfr_frames
+    fe = FrontendEngine(cmvn, DEV)
+    lens = [w.numel() for w in wavs]
+    pad = torch.nn.utils.rnn.pad_sequence(wavs, batch_first=True).to(DEV)
+    feats, fl = fe(pad, torch.tensor(lens, dtype=torch.int32, device=DEV), max(num_lfr_frames(n) for n in lens))
+    eng = _engine(cfg, wseed, mode)
+    out = eng.forward_feats(feats, fl, want_taps=True)
+    torch.cuda.synchronize()
+    out["feats"], out["feat_lens"] = feats, fl
+    return out
+
+
+def _sub(cfg, t, step):
+    return t[:, ::step] if cfg.enc_layers > 10 else t
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_paraformer_vs_reference_golden(name):
+    """End-to-end against the UNMODIFIED reference's outputs (tests/golden, made by oracle/make_golden.py)."""
+    cfg, wseed, wavs, cmvn, g = load_case(name)
+    o = _run_model(cfg, wseed, wavs, cmvn)
+    assert o["feat_lens"].cpu().tolist() == g["feat_lens"].tolist()
+    assert np.abs(_sub(cfg, o["feats"].cpu(), 7).numpy() - g["feats"]).max() <= 2e-4
+    assert rel_err(_sub(cfg, o["enc"].cpu(), 7).numpy(), g["enc"]) <= 1e-3
+    assert np.abs(o["alphas"].cpu().numpy() - g["alphas"]).max() <= 1e-4
+    assert o["token_num"].tolist() == g["token_num"].tolist()                      # integer: exact
+    n = int(g["token_num"].max())
+    assert rel_err(_sub(cfg, o["acoustic"][:, :n].cpu(), 5).numpy(), g["acoustic"]) <= 1e-3
+    lp = o["logp"][:, g["logp_rows"].tolist(), :].cpu().numpy()
+    assert rel_err(lp, g["logp_sel"]) <= 1e-3                                      # contract tolerance
+    valid = np.arange(n)[None, :] < g["token_num"][:, None]
+    assert (o["argmax"].cpu().numpy()[valid] == g["argmax"][valid]).all()
+    ids_flat = [t for r in o["ids"] for t in r]
+    assert ids_flat == g["ids_flat"].tolist()                                      # greedy ids: bit-exact
+    assert [len(r) for r in o["ids"]] == g["ids_len"].tolist()
+
+
+def test_paraformer_vs_oracle_fresh_inputs():
+    """Same seeded inputs through the oracle and the CUDA path (inputs not in the golden set, ragged batch of 5)."""
+    from funasr_b200 import synth
+    cfg = synth.PARAFORMER_TINY
+    wavs = [synth.make_wav(n, 40 + i, "speechlike") for i, n in enumerate([64000, 9000, 33333, 400, 20480])]
+    cmvn = synth.make_cmvn(cfg, 3)
+    p = state_dict_for(cfg, 9)
+    ref = O.paraformer_forward(wavs, p, cmvn, cfg.enc_layers, cfg.dec_layers)
+    o = _run_model(cfg, 9, wavs, cmvn)
+    assert o["token_num"].tolist() == ref["token_num"].tolist()
+    assert rel_err(o["enc"].cpu().numpy(), ref["enc"].numpy()) <= 1e-3
+    assert rel_err(o["logp"].cpu().numpy(), ref["logp"].numpy()) <= 1e-3
+    assert o["ids"] == ref["ids"]
+
+
+def test_properties_at_baseline_size():
+    """BASELINE config 2 shape (B=64 x 30 s, T=500) with a 3+2-layer stack: size-independent properties —
+    determinism (bit-identical reruns), permutation equivariance over utterances (bit-exact: utterances are
+    independent), zero-filled feature padding, token counts within the CIF bound T+1."""
+    from funasr_b200 import synth
+    from funasr_b200.engine import FrontendEngine
+    cfg = synth.PARAFORMER_TINY
+    B, N = 64, 480000
+    g = torch.Generator().manual_seed(77)
+    base = [synth.make_wav(N, 60 + i, "speechlike") for i in range(4)]
+    gains = 0.3 + 0.7 * torch.rand(B, generator=g)
+    wav = torch.stack([base[i % 4].roll(137 * i) * gains[i] for i in range(B)])
+    lens = torch.full((B,), N, dtype=torch.int32)
+    lens[5], lens[17] = 80000, 400 + 160 * 6 * 100
+    fe = FrontendEngine(synth.make_cmvn(cfg, 1), DEV)
+    eng = _engine(cfg, 5)
+    feats, fl = fe(wav.to(DEV), lens.to(DEV), 500)
+    assert fl.cpu().tolist() == [500 if i not in (5, 17) else (83 if i == 5 else 101) for i in range(B)]
+    assert float(feats[5, 83:].abs().max()) == 0.0
+    a = eng.forward_feats(feats, fl, want_taps=True)
+    b = eng.forward_feats(feats, fl, want_taps=True)
+    assert a["ids"] == b["ids"] and torch.equal(a["enc"], b["enc"]) and torch.equal(a["logp"], b["logp"])
+    assert all(0 <= int(t) <= 501 for t in a["token_num"].tolist())
+    perm = torch.randperm(B, generator=g)
+    c = eng.forward_feats(feats[perm.to(DEV)].contiguous(), fl[perm.to(DEV)].contiguous(), want_taps=True)
+    assert [a["ids"][int(i)] for i in perm] == c["ids"]
+    assert torch.equal(a["enc"][perm.to(DEV)], c["enc"])
+
+
+def test_plugin_inference_contract():
+    """ParaformerB200.inference keeps Paraformer.inference's contract (model.py:534-697): results with key/token_int,
+    meta_data['batch_data_time'] in audio seconds; ids identical to the golden reference ids."""
+    import funasr_b200
+    cfg, wseed, wavs, cmvn, g = load_case("tiny_ragged3")
+    from test_abi_host import _tiny_conf
+    m = funasr_b200.ParaformerB200(**_tiny_conf())
+    m.load_state_dict(state_dict_for(cfg, wseed), strict=True)
+    m.to(DEV).eval()
+    fe = funasr_b200.WavFrontendB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6,
+                                     dither=0.0, cmvn=cmvn)
+    res, meta = m.inference([w.numpy() for w in wavs], key=["a", "b", "c"], tokenizer=None, frontend=fe, device=DEV)
+    assert [r["key"] for r in res] == ["a", "b", "c"]
+    assert [t for r in res for t in r["token_int"]] == g["ids_flat"].tolist()
+    assert abs(meta["batch_data_time"] - float(g["batch_data_time"])) < 1e-6

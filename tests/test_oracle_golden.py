@@ -1,0 +1,98 @@
+"""CPU: the oracle restatement against the golden vectors produced by the UNMODIFIED reference
+(oracle/make_golden.py), and — when /root/reference is present — against the live reference itself."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_case, rel_err, state_dict_for
+
+import paraformer_oracle as O
+import ref_shim
+
+
+def _sub(cfg, t, step):
+    return t[:, ::step] if cfg.enc_layers > 10 else t
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_oracle_matches_reference_golden(name):
+    cfg, wseed, wavs, cmvn, g = load_case(name)
+    p = state_dict_for(cfg, wseed)
+    o = O.paraformer_forward(wavs, p, cmvn, cfg.enc_layers, cfg.dec_layers, tail_threshold=cfg.tail_threshold)
+    assert o["feat_lens"].tolist() == g["feat_lens"].tolist()
+    # same machine class + same torch ops: frontend and encoder are (near) bit-identical to the reference
+    assert np.abs(_sub(cfg, o["feats"], 7).numpy() - g["feats"]).max() <= 1e-5
+    assert rel_err(_sub(cfg, o["enc"], 7).numpy(), g["enc"]) <= 1e-5
+    assert np.abs(o["alphas"].numpy() - g["alphas"]).max() <= 1e-5
+    assert o["token_num"].tolist() == g["token_num"].tolist()            # integer outcome: exact
+    assert rel_err(_sub(cfg, o["acoustic"], 5).numpy(), g["acoustic"]) <= 1e-4
+    lp = o["logp"][:, g["logp_rows"].tolist(), :].numpy()
+    assert rel_err(lp, g["logp_sel"]) <= 1e-3                            # contract: logits within 1e-3 rel fp32
+    valid = np.arange(g["argmax"].shape[1])[None, :] < g["token_num"][:, None]
+    assert (o["logp"].argmax(-1).numpy()[valid] == g["argmax"][valid]).all()
+    ids_flat = [t for r in o["ids"] for t in r]
+    assert ids_flat == g["ids_flat"].tolist() and [len(r) for r in o["ids"]] == g["ids_len"].tolist()   # bit-exact ids
+    assert abs(float(g["batch_data_time"]) - sum(int(x) for x in o["feat_lens"]) * 0.06) < 1e-6
+
+
+def test_fbank_matches_pinned_torchaudio():
+    """Third-party pin: torchaudio.compliance.kaldi.fbank (2.11.0) as WavFrontend calls it (wav_frontend.py:171-181)."""
+    ta = pytest.importorskip("torchaudio")
+    import torchaudio.compliance.kaldi as kaldi
+    from funasr_b200 import synth
+    for n, seed, kind in [(16000, 7, "speechlike"), (400, 8, "noise"), (8123, 9, "noise")]:
+        w = synth.make_wav(n, seed, kind) * (1 << 15)
+        ref = kaldi.fbank(w.unsqueeze(0), num_mel_bins=80, frame_length=25, frame_shift=10, dither=0.0, energy_floor=0.0,
+                          window_type="hamming", sample_frequency=16000, snip_edges=True)
+        assert torch.equal(ref, O.kaldi_fbank(w))
+
+
+def test_lfr_equals_reference_formula():
+    """apply_lfr restated as a clamped gather == the reference's pad+as_strided construction (wav_frontend.py:63-86)."""
+    def ref_lfr(inputs, m, n):
+        T = inputs.shape[0]
+        T_lfr = int(np.ceil(T / n))
+        inputs = torch.vstack((inputs[0].repeat((m - 1) // 2, 1), inputs))
+        T = T + (m - 1) // 2
+        d = inputs.shape[-1]
+        last_idx = (T - m) // n + 1
+        num_padding = m - (T - last_idx * n)
+        if num_padding > 0:
+            num_padding = (2 * m - 2 * T + (T_lfr - 1 + last_idx) * n) / 2 * (T_lfr - last_idx)
+            inputs = torch.vstack([inputs] + [inputs[-1:]] * int(num_padding))
+        return inputs.as_strided((T_lfr, m * d), (n * d, 1)).clone()
+    g = torch.Generator().manual_seed(0)
+    for T in list(range(1, 40)) + [499, 2998, 3000]:
+        x = torch.randn(T, 5, generator=g)
+        assert torch.equal(ref_lfr(x, 7, 6), O.apply_lfr(x, 7, 6)), T
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="live reference tree not present")
+def test_oracle_matches_live_reference_components():
+    """Run the reference's own classes (from /root/reference) on fresh random inputs and compare stage by stage."""
+    ref_shim.import_reference()
+    from funasr.register import tables
+    from funasr_b200 import synth
+    cfg = synth.PARAFORMER_TINY
+    p = synth.make_state_dict(cfg, 11)
+    enc = tables.encoder_classes["SANMEncoder"](input_size=560, output_size=512, attention_heads=4, linear_units=2048,
+                                                num_blocks=cfg.enc_layers, input_layer="pe", kernel_size=11, sanm_shfit=0,
+                                                selfattention_layer_type="sanm").eval()
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in p.items() if k.startswith("encoder.")}, strict=True)
+    pred = tables.predictor_classes["CifPredictorV2"](idim=512, threshold=1.0, l_order=1, r_order=1, tail_threshold=0.45).eval()
+    pred.load_state_dict({k[len("predictor."):]: v for k, v in p.items() if k.startswith("predictor.")}, strict=True)
+    g = torch.Generator().manual_seed(5)
+    feats = torch.randn(3, 41, 560, generator=g)
+    lens = torch.tensor([41, 17, 30], dtype=torch.int32)
+    for b in range(3):
+        feats[b, lens[b]:] = 0
+    with torch.no_grad():
+        r_enc, r_len, _ = enc(feats, lens)
+        o_enc, o_len = O.encoder(feats, lens, p, cfg.enc_layers)
+        assert torch.allclose(r_enc, o_enc, rtol=0, atol=1e-5) and r_len.tolist() == o_len.tolist()
+        mask = (torch.arange(41)[None, :] < lens[:, None])[:, None, :]
+        r_emb, r_tok, r_al, r_pk = pred(r_enc, None, mask, ignore_id=-1)
+        o_emb, o_tok, o_al, o_pk = O.predictor(r_enc, lens, p)
+        assert r_tok.tolist() == o_tok.tolist()
+        assert torch.allclose(r_al, o_al, atol=1e-6) and torch.allclose(r_pk, o_pk, atol=1e-5)
+        assert torch.allclose(r_emb, o_emb, atol=1e-4)
