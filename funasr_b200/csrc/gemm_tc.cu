@@ -1,15 +1,446 @@
-// tcgen05 / TMEM / TMA bf16-split GEMM path (FA_GEMM_BF16X1 / X3 / X6).  Placeholder until the kernel lands:
-// every call reports FA_ERR_UNSUPPORTED so that nothing silently falls back to another path.
+// tcgen05 / TMEM / TMA GEMM with bf16 operand splitting and a fused nn.Linear epilogue (sm_100a only).
+//
+//   Y[M,N] = act( sum_{(p,q) in terms} A_p[M,K] * W_q[N,K]^T + b ) (+ res1) (+ res2)
+//
+// A_p / W_q are the bf16 planes of the fp32 operands (x = hi + mid + lo, made by split kernels), accumulation is
+// fp32 in TMEM.  Modes: BF16X1 = {(0,0)} (fast), BF16X3 = {(0,0),(0,1),(1,0)} (~2^-17 relative, the default
+// parity mode on tensor cores), BF16X6 = X3 + {(1,1),(0,2),(2,0)} (~fp32).  This replaces the torch.nn.Linear calls
+// of the hot path (sanm/attention.py:256,306, transformer/positionwise_feed_forward.py:34,
+// sanm/positionwise_feed_forward.py:33, paraformer/decoder.py:444, cif conv as GEMM).
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0 : TMA producer  — cp.async.bulk.tensor.2d (SWIZZLE_128B) of the A/W plane tiles into a smem ring
+//   warp 1 : MMA issuer    — one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (128xBNx16) per K=16
+//                            slice and per split term; tcgen05.commit releases ring slots / publishes accumulators
+//   warp 2 : TMEM allocator (2 accumulators x BN columns, double buffered so the epilogue of tile i overlaps
+//            the MMAs of tile i+1)
+//   warps 4-7 : epilogue   — tcgen05.ld (32 lanes x 32 columns per warp and step) -> bias/ReLU/residuals ->
+//            fp32 rows to HBM, or bf16 planes for a following GEMM.
+// Tensor-pipe bound when operand tiles are reused from L2; roofline notes in DESIGN.md.
 #include "common.cuh"
 #include "kernels.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
 
 namespace fa {
 
-size_t gemm_tc_scratch_bytes(int64_t, int, int) { return 0; }
+constexpr int TC_BM = 128;      // UMMA M (cta_group::1)
+constexpr int TC_BK = 64;       // one 128-byte swizzle span of bf16
+constexpr int TC_UK = 16;       // UMMA K for 16-bit inputs
+constexpr uint32_t TC_TILE_BYTES_A = TC_BM * TC_BK * 2;   // 16 KB per plane tile
 
-int gemm_tc_launch(const float*, int64_t, int64_t, const FaLinear&, int, const float*, int64_t, const float*, int64_t,
-                   float*, int64_t, int, Arena*, cudaStream_t) {
-  return FA_ERR_UNSUPPORTED;
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread i <-> TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (tile rows at 128-byte pitch, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, 16-byte units      bits [0,14)
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: 8 rows x 128 B [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)     [46,48)
+  d |= (uint64_t)2 << 61;                             // layout: SWIZZLE_128B               [61,64)
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, shape M x N.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct TcParams {
+  int64_t M;
+  int N, Kp;            // Kp: K padded to a multiple of 64 (planes are zero padded)
+  int64_t a_plane_rows; // rows between consecutive A planes in the 2D tensor map (= M)
+  int w_plane_rows;     // = N
+  int n_terms;          // 1, 3 or 6
+  int relu;
+  const float* bias;
+  const float* r1; int64_t ldr1;
+  const float* r2; int64_t ldr2;
+  float* C; int64_t ldc;                 // fp32 output (or null)
+  __nv_bfloat16* out_planes;             // bf16 plane output [3][M][ldo] (or null)
+  int64_t ldo; int out_nplanes;
+  int tiles_m, tiles_n;
+};
+
+__constant__ int c_term_a[6] = {0, 0, 1, 1, 0, 2};
+__constant__ int c_term_w[6] = {0, 1, 0, 1, 2, 0};
+
+template <int BN, int STAGES, int APL, int WPL>  // APL / WPL: A / W planes resident per stage
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr uint32_t TILE_W_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t STAGE_BYTES = APL * TC_TILE_BYTES_A + WPL * TILE_W_BYTES;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.tiles_m * p.tiles_n;
+  const int k_blocks = p.Kp / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          unsigned char* st = smem + stage * STAGE_BYTES;
+#pragma unroll
+          for (int pl = 0; pl < APL; ++pl)
+            tma_load_2d(st + pl * TC_TILE_BYTES_A, &map_a, &full_bar[stage], kb * TC_BK, (int)(pl * p.a_plane_rows + (int64_t)tm * TC_BM));
+#pragma unroll
+          for (int pl = 0; pl < WPL; ++pl)
+            tma_load_2d(st + APL * TC_TILE_BYTES_A + pl * TILE_W_BYTES, &map_w, &full_bar[stage], kb * TC_BK, pl * p.w_plane_rows + tn * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+          for (int t = 0; t < p.n_terms; ++t) {
+            const uint64_t da = make_sw128_desc(st + c_term_a[t] * TC_TILE_BYTES_A);
+            const uint64_t dw = make_sw128_desc(st + APL * TC_TILE_BYTES_A + c_term_w[t] * TILE_W_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UK; ++k) {
+              // advance 32 bytes (16 bf16) inside the 128-byte swizzle span: +2 in 16-byte units
+              umma_bf16(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | t | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);                  // ring slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);                      // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (warps 4..7 <-> TMEM lanes 32*(warp-4) ..) =====================
+    const int q = warp - 4;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int64_t row = (int64_t)tm * TC_BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
+        const int col0 = tn * BN + c0;
+        if (row_ok && col0 < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const bool full = col0 + 32 <= p.N;
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.r1) {
+            const float* rr = p.r1 + row * p.ldr1 + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (full) { const float4 t = __ldg(reinterpret_cast<const float4*>(rr + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+              else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) v[j + e] += __ldg(rr + j + e); }
+            }
+          }
+          if (p.r2) {
+            const float* rr = p.r2 + row * p.ldr2 + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (full) { const float4 t = __ldg(reinterpret_cast<const float4*>(rr + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+              else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) v[j + e] += __ldg(rr + j + e); }
+            }
+          }
+          if (p.C) {
+            float* cr = p.C + row * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (full) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) cr[j + e] = v[j + e]; }
+            }
+          }
+          if (p.out_planes && full) {
+            // x = hi + mid + lo split for a following GEMM (planes [3][M][ldo])
+            __nv_bfloat16* o0 = p.out_planes + row * p.ldo + col0;
+            const int64_t plane = p.M * p.ldo;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float a = v[j], b = v[j + 1];
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+              *reinterpret_cast<__nv_bfloat162*>(o0 + j) = __halves2bfloat162(h0, h1);
+              if (p.out_nplanes > 1) {
+                a -= __bfloat162float(h0); b -= __bfloat162float(h1);
+                const __nv_bfloat16 m0 = __float2bfloat16_rn(a), m1 = __float2bfloat16_rn(b);
+                *reinterpret_cast<__nv_bfloat162*>(o0 + plane + j) = __halves2bfloat162(m0, m1);
+                if (p.out_nplanes > 2) {
+                  a -= __bfloat162float(m0); b -= __bfloat162float(m1);
+                  *reinterpret_cast<__nv_bfloat162*>(o0 + 2 * plane + j) = __halves2bfloat162(__float2bfloat16_rn(a), __float2bfloat16_rn(b));
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);        // 4 arrivals (one per epilogue warp) free the accumulator
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// fp32 rows [rows, cols] (ld) -> bf16 planes [nplanes][rows][cols_pad]; 4 elements per thread.
+__global__ void __launch_bounds__(256)
+split_rows_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, int cols_pad, int nplanes,
+                  __nv_bfloat16* __restrict__ planes) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = cols_pad >> 2;
+  const int64_t total = rows * c4n;
+  if (i >= total) return;
+  const int64_t r = i / c4n;
+  const int c = (int)(i - r * c4n) * 4;
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c + 3 < cols) x = __ldg(reinterpret_cast<const float4*>(src + r * ld + c));
+  else {
+    float* e = reinterpret_cast<float*>(&x);
+    for (int k = 0; k < 4; ++k) if (c + k < cols) e[k] = __ldg(src + r * ld + c + k);
+  }
+  float v[4] = {x.x, x.y, x.z, x.w};
+  const int64_t plane = rows * cols_pad;
+  for (int pl = 0; pl < nplanes; ++pl) {
+    __nv_bfloat16 h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { h[k] = __float2bfloat16_rn(v[k]); v[k] -= __bfloat162float(h[k]); }
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(planes + pl * plane + r * cols_pad + c);
+    dst[0] = __halves2bfloat162(h[0], h[1]);
+    dst[1] = __halves2bfloat162(h[2], h[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 tensor [rows, cols] (row pitch ld elements), box {64 cols, box_rows}, 128B swizzle
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return FA_ERR_CUDA;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FA_OK : FA_ERR_CUDA;
+}
+
+static int planes_for_mode(int mode) { return mode == FA_GEMM_BF16X1 ? 1 : (mode == FA_GEMM_BF16X3 ? 2 : 3); }
+
+size_t gemm_tc_scratch_bytes(int64_t max_rows, int max_k, int mode) {
+  if (mode == FA_GEMM_F32_SIMT) return 0;
+  const int kp = (max_k + 63) / 64 * 64;
+  return (size_t)planes_for_mode(mode) * (size_t)max_rows * kp * 2 + 1024;
+}
+
+template <int BN, int STAGES, int APL, int WPL>
+static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (APL * TC_TILE_BYTES_A + WPL * BN * TC_BK * 2) + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, APL, WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    FA_CUDA_OK(cudaGetDevice(&dev));
+    FA_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < n_sm ? tiles : n_sm;
+  gemm_tc_kernel<BN, STAGES, APL, WPL><<<grid, 256, smem, st>>>(ma, mw, p);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+// A planes already split: a_planes [npl][M][Kp]
+int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
+                          const float* r2, int64_t ld2, float* y, int64_t ldy, __nv_bfloat16* out_planes, int64_t ldo,
+                          int mode, cudaStream_t st) {
+  if (M <= 0) return FA_OK;
+  if (!lin.w_planes || !a_planes) return FA_ERR_ARG;
+  const int N = lin.out_f, Kp = lin.in_pad;
+  if (Kp % TC_BK != 0 || M * 3 > 0x7fffffffLL) return FA_ERR_UNSUPPORTED;
+  if (y && ((ldy & 3) || (((uintptr_t)y) & 15))) return FA_ERR_UNSUPPORTED;
+  if ((r1 && (ld1 & 3)) || (r2 && (ld2 & 3))) return FA_ERR_UNSUPPORTED;
+  const int npl = planes_for_mode(mode);
+  constexpr int BN = 128;
+  CUtensorMap ma, mw;
+  FA_RETURN_IF_ERR(make_map(&ma, a_planes, (uint64_t)M * npl, (uint64_t)Kp, (uint64_t)Kp, TC_BM));
+  FA_RETURN_IF_ERR(make_map(&mw, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, BN));
+  TcParams p;
+  p.M = M; p.N = N; p.Kp = Kp; p.a_plane_rows = M; p.w_plane_rows = N;
+  p.n_terms = mode == FA_GEMM_BF16X1 ? 1 : (mode == FA_GEMM_BF16X3 ? 3 : 6);
+  p.relu = relu; p.bias = lin.b; p.r1 = r1; p.ldr1 = ld1; p.r2 = r2; p.ldr2 = ld2; p.C = y; p.ldc = ldy;
+  p.out_planes = out_planes; p.ldo = ldo; p.out_nplanes = npl;
+  p.tiles_m = (int)((M + TC_BM - 1) / TC_BM); p.tiles_n = (N + BN - 1) / BN;
+  if (out_planes && (N % 32 != 0)) return FA_ERR_UNSUPPORTED;
+  switch (npl) {
+    case 1: return launch_cfg<BN, 6, 1, 1>(ma, mw, p, st);
+    case 2: return launch_cfg<BN, 3, 2, 2>(ma, mw, p, st);
+    default: return launch_cfg<BN, 2, 3, 3>(ma, mw, p, st);
+  }
+}
+
+int split_rows_launch(const float* x, int64_t ldx, int64_t rows, int cols, int cols_pad, int nplanes, __nv_bfloat16* planes,
+                      cudaStream_t st) {
+  if (rows <= 0) return FA_OK;
+  if ((ldx & 3) || (((uintptr_t)x) & 15) || (cols_pad & 3)) return FA_ERR_UNSUPPORTED;
+  const int64_t total = rows * (cols_pad / 4);
+  split_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, ldx, rows, cols, cols_pad, nplanes, planes);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+int gemm_tc_launch(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
+                   const float* r2, int64_t ld2, float* y, int64_t ldy, int mode, Arena* scratch, cudaStream_t st) {
+  if (rows <= 0) return FA_OK;
+  if (mode != FA_GEMM_BF16X1 && mode != FA_GEMM_BF16X3 && mode != FA_GEMM_BF16X6) return FA_ERR_ARG;
+  if (!scratch) return FA_ERR_WORKSPACE;
+  const int npl = planes_for_mode(mode);
+  Arena local(scratch->base, scratch->cap);   // scratch is reused by every call (stream ordered)
+  __nv_bfloat16* planes = local.take<__nv_bfloat16>((size_t)npl * rows * lin.in_pad);
+  if (!local.ok()) return FA_ERR_WORKSPACE;
+  FA_RETURN_IF_ERR(split_rows_launch(x, ldx, rows, lin.in_f, lin.in_pad, npl, planes, st));
+  return gemm_tc_planes_launch(planes, rows, lin, relu, r1, ld1, r2, ld2, y, ldy, nullptr, 0, mode, st);
 }
 
 }  // namespace fa
