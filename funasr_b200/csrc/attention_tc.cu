@@ -1,0 +1,394 @@
+// tcgen05 / TMEM / TMA fused multi-head attention with bf16 operand splitting (sm_100a).
+//
+// Same contract as attention_f32.cu (sanm/attention.py:288-304 with scores from :324-325; cross-attention :760-794,
+// :811-812): ctx = softmax(mask(q d_k^-0.5 . k^T)) v per head, key-padding mask, heads merged.  Score and context
+// contractions run on the 5th-gen tensor cores with fp32 accumulation in TMEM; operands are bf16 planes (hi, lo) of the
+// fp32 tensors so that S = Qh.Kh + Qh.Kl + Ql.Kh and O = Ph.Vh + Ph.Vl + Pl.Vh carry ~2^-17 relative error (x3 mode),
+// or one plane (x1 mode).  The [B,H,Tq,Tk] score tensor never leaves the SM.
+//
+// One CTA = 128 queries of one (utterance, head), keys in chunks of 64, two passes over the keys:
+//   pass A: S~ = Qh.Kh (one MMA term) -> per-row max m   (softmax is invariant to the choice of m; an approximate
+//           maximum only has to keep exp(s - m) in range, so one bf16 term suffices)
+//   pass B: S (all terms) -> p = exp(s - m), l += sum p, P planes -> smem, O += P.V accumulated in TMEM with no
+//           rescaling traffic; finally O / l -> bf16 planes (A operand of the out-projection GEMM) and/or fp32.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 softmax + epilogue (one query
+// row per thread, TMEM lane == row).  S is double buffered in TMEM so the MMAs of chunk j+1 overlap softmax of chunk j.
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+#include <math.h>
+
+namespace fa {
+
+constexpr int AT_BQ = 128, AT_BKEY = 64, AT_D = 128;
+constexpr uint32_t AT_Q_KBLK = AT_BQ * 128;      // 16 KB: 128 rows x 64 bf16
+constexpr uint32_t AT_K_KBLK = AT_BKEY * 128;    // 8 KB : 64 keys x 64 bf16
+constexpr uint32_t AT_V_TILE = AT_D * 128;       // 16 KB: 128 d-rows x 64 keys
+constexpr uint32_t AT_P_TILE = AT_BQ * 128;      // 16 KB: 128 queries x 64 keys
+
+struct AttTcParams {
+  int tq, tk, heads, batch;
+  const int32_t* key_lens;
+  int64_t q_plane_rows, k_plane_rows, v_plane_rows;   // rows between planes in the respective 2D maps
+  float* ctx; int64_t ldc;                             // fp32 output (or null)
+  __nv_bfloat16* ctx_planes; int64_t ldp; int out_nplanes;   // bf16 planes [npl][B*tq][ldp] (or null)
+};
+
+template <int NPL>
+__global__ void __launch_bounds__(256, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const AttTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr uint32_t Q_BYTES = NPL * 2 * AT_Q_KBLK;
+  constexpr uint32_t K_BYTES = NPL * 2 * AT_K_KBLK;
+  constexpr uint32_t V_BYTES = NPL * AT_V_TILE;
+  constexpr uint32_t STAGE_BYTES = K_BYTES + V_BYTES;
+  constexpr uint32_t P_BYTES = NPL * AT_P_TILE;
+  constexpr int NT = NPL == 1 ? 1 : 3;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sKV = sQ + Q_BYTES;
+  unsigned char* sP = sKV + 2 * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* kv_full = bars + 1;       // [2]
+  uint64_t* kv_empty = bars + 3;      // [2]
+  uint64_t* s_full = bars + 5;        // [2]
+  uint64_t* s_empty = bars + 7;       // [2]
+  uint64_t* p_full = bars + 9;        // [1]
+  uint64_t* p_empty = bars + 10;      // [1]
+  uint64_t* o_full = bars + 11;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+  const int klen = min(p.key_lens[b], p.tk);
+  const int nc = (klen + AT_BKEY - 1) / AT_BKEY;     // key chunks with at least one valid key
+  const int njobs = 2 * nc;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
+    mbar_init(p_full, 4); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && nc > 0) {
+      mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+      for (int pl = 0; pl < NPL; ++pl)
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_2d(sQ + (pl * 2 + kb) * AT_Q_KBLK, &map_q, q_full, h * AT_D + kb * 64,
+                      (int)(pl * p.q_plane_rows + (int64_t)b * p.tq + q0));
+      for (int i = 0; i < njobs; ++i) {
+        const int st = i & 1, j = i < nc ? i : i - nc;
+        const bool passB = i >= nc;
+        mbar_wait(&kv_empty[st], (((uint32_t)i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], passB ? STAGE_BYTES : K_BYTES);
+        unsigned char* sk = sKV + st * STAGE_BYTES;
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl)
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+            tma_load_2d(sk + (pl * 2 + kb) * AT_K_KBLK, &map_k, &kv_full[st], h * AT_D + kb * 64,
+                        (int)(pl * p.k_plane_rows + (int64_t)b * p.tk + j * AT_BKEY));
+        if (passB) {
+#pragma unroll
+          for (int pl = 0; pl < NPL; ++pl)
+            tma_load_2d(sk + K_BYTES + pl * AT_V_TILE, &map_v, &kv_full[st], j * AT_BKEY,
+                        (int)(pl * p.v_plane_rows + ((int64_t)b * p.heads + h) * AT_D));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && nc > 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(AT_BQ, AT_BKEY);
+      constexpr uint32_t idesc_o = make_idesc_bf16(AT_BQ, AT_D);
+      const int ta[3] = {0, 0, 1}, tb[3] = {0, 1, 0};
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      auto issue_pv = [&](int t) {   // t-th PV of pass B, uses kv stage of job nc + t
+        const int i = nc + t, st = i & 1;
+        mbar_wait(p_full, (uint32_t)t & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sKV + st * STAGE_BYTES + K_BYTES);
+        for (int term = 0; term < NT; ++term) {
+          const uint64_t da = make_sw128_desc(p_addr + ta[term] * AT_P_TILE);
+          const uint64_t db = make_sw128_desc(v_addr + tb[term] * AT_V_TILE);
+#pragma unroll
+          for (int k = 0; k < AT_BKEY / 16; ++k) umma_bf16(tmem_o, da + 2 * k, db + 2 * k, idesc_o, (t | term | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(p_empty);
+      };
+      for (int i = 0; i < njobs; ++i) {
+        const int st = i & 1;
+        const bool passB = i >= nc;
+        const uint32_t ph = ((uint32_t)i >> 1) & 1;
+        mbar_wait(&kv_full[st], ph);
+        mbar_wait(&s_empty[st], ph ^ 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sKV + st * STAGE_BYTES);
+        const uint32_t d_s = tmem_base + st * AT_BKEY;
+        const int nterm = passB ? NT : 1;
+        for (int term = 0; term < nterm; ++term) {
+#pragma unroll
+          for (int k = 0; k < AT_D / 16; ++k) {
+            const uint64_t da = make_sw128_desc(q_addr + (ta[term] * 2 + (k >> 2)) * AT_Q_KBLK) + 2 * (k & 3);
+            const uint64_t db = make_sw128_desc(k_addr + (tb[term] * 2 + (k >> 2)) * AT_K_KBLK) + 2 * (k & 3);
+            umma_bf16(d_s, da, db, idesc_s, (term | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&s_full[st]);
+        if (!passB) umma_commit(&kv_empty[st]);
+        else if (i > nc) issue_pv(i - nc - 1);
+      }
+      issue_pv(nc - 1);
+      umma_commit(o_full);
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax + epilogue: thread <-> query row =====================
+    const int qw = warp - 4;
+    const int r = qw * 32 + lane;              // row in tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(qw * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    if (nc > 0) {
+      // ---- pass A: approximate row max
+      for (int i = 0; i < nc; ++i) {
+        const int st = i & 1;
+        mbar_wait(&s_full[st], ((uint32_t)i >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < AT_BKEY; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + c0, v);
+          const int kbase = i * AT_BKEY + c0;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) if (kbase + jj < klen) m = fmaxf(m, __uint_as_float(v[jj]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);
+      }
+      // ---- pass B: probabilities
+      uint32_t* prow = reinterpret_cast<uint32_t*>(sP + (size_t)r * 128);
+      for (int t = 0; t < nc; ++t) {
+        const int i = nc + t, st = i & 1;
+        mbar_wait(&s_full[st], ((uint32_t)i >> 1) & 1);
+        tc_fence_after();
+        float pr[AT_BKEY];
+#pragma unroll
+        for (int c0 = 0; c0 < AT_BKEY; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + c0, v);
+          const int kbase = t * AT_BKEY + c0;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const float pv = (kbase + jj < klen) ? expf(__uint_as_float(v[jj]) - m) : 0.f;
+            pr[c0 + jj] = pv;
+            l += pv;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);
+        // P planes -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
+        mbar_wait(p_empty, ((uint32_t)t & 1) ^ 1);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = pr[c * 8 + 2 * e], bb = pr[c * 8 + 2 * e + 1];
+            const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(bb);
+            hi[e] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+            if (NPL > 1) {
+              const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(bb - __bfloat162float(hb));
+              lo[e] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+            }
+          }
+          const int pc = (c ^ (r & 7)) * 4;
+          *reinterpret_cast<uint4*>(prow + pc) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (NPL > 1) *reinterpret_cast<uint4*>(prow + AT_P_TILE / 4 + pc) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+    }
+    // ---- epilogue: O / l
+    const int qrow = q0 + r;
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    const int64_t grow = (int64_t)b * p.tq + qrow;
+#pragma unroll 1
+    for (int c0 = 0; c0 < AT_D; c0 += 32) {
+      uint32_t v[32];
+      if (nc > 0) tmem_ld_32x32(tmem_o + lane_addr + c0, v);
+      if (qrow < p.tq) {
+        float o[32];
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) o[jj] = nc > 0 ? __uint_as_float(v[jj]) * inv : 0.f;
+        if (p.ctx) {
+          float* dst = p.ctx + grow * p.ldc + h * AT_D + c0;
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 4) *reinterpret_cast<float4*>(dst + jj) = make_float4(o[jj], o[jj + 1], o[jj + 2], o[jj + 3]);
+        }
+        if (p.ctx_planes) {
+          __nv_bfloat16* d0 = p.ctx_planes + grow * p.ldp + h * AT_D + c0;
+          const int64_t plane = (int64_t)p.batch * p.tq * p.ldp;
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 2) {
+            float a = o[jj], bb = o[jj + 1];
+            for (int pl = 0; pl < p.out_nplanes; ++pl) {
+              const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(bb);
+              *reinterpret_cast<__nv_bfloat162*>(d0 + pl * plane + jj) = __halves2bfloat162(ha, hb);
+              a -= __bfloat162float(ha); bb -= __bfloat162float(hb);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// V [B, tk, ldv] (head h at column h*128) -> Vt planes [npl][B*H*128][tkp] (keys contiguous), via a 64x64 smem transpose.
+__global__ void __launch_bounds__(256)
+vt_planes_kernel(const float* __restrict__ v, int64_t ldv, int tk, int tkp, int heads, int nplanes, int64_t plane_elems,
+                 __nv_bfloat16* __restrict__ vt) {
+  __shared__ float tile[64][65];
+  const int t0 = blockIdx.x * 64, dblk = blockIdx.y, b = blockIdx.z;   // dblk over heads*2 (64-wide d blocks)
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < 64 * 16; idx += 256) {
+    const int tr = idx >> 4, c4 = idx & 15;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t0 + tr < tk) x = __ldg(reinterpret_cast<const float4*>(v + ((int64_t)b * tk + t0 + tr) * ldv + dblk * 64 + 4 * c4));
+    tile[tr][4 * c4 + 0] = x.x; tile[tr][4 * c4 + 1] = x.y; tile[tr][4 * c4 + 2] = x.z; tile[tr][4 * c4 + 3] = x.w;
+  }
+  __syncthreads();
+  // each thread writes 2 consecutive keys for one d: 64 d x 32 key-pairs = 2048 items / 256 threads
+  for (int idx = tid; idx < 64 * 32; idx += 256) {
+    const int d = idx >> 5, kp = (idx & 31) * 2;
+    if (t0 + kp >= tkp) continue;
+    float a = tile[kp][d], bb = tile[kp + 1][d];
+    __nv_bfloat16* dst = vt + ((int64_t)b * heads * AT_D + dblk * 64 + d) * tkp + t0 + kp;
+    for (int pl = 0; pl < nplanes; ++pl) {
+      const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(bb);
+      *reinterpret_cast<__nv_bfloat162*>(dst + pl * plane_elems) = __halves2bfloat162(ha, hb);
+      a -= __bfloat162float(ha); bb -= __bfloat162float(hb);
+    }
+  }
+}
+
+// fp32 [rows, cols] (ld) * scale -> bf16 planes [nplanes][rows][cols]
+__global__ void __launch_bounds__(256)
+scale_split_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, float scale, int nplanes,
+                   __nv_bfloat16* __restrict__ planes) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = cols >> 2;
+  if (i >= rows * c4n) return;
+  const int64_t r = i / c4n;
+  const int c = (int)(i - r * c4n) * 4;
+  const float4 x = __ldg(reinterpret_cast<const float4*>(src + r * ld + c));
+  float v[4] = {__fmul_rn(x.x, scale), __fmul_rn(x.y, scale), __fmul_rn(x.z, scale), __fmul_rn(x.w, scale)};
+  const int64_t plane = rows * cols;
+  for (int pl = 0; pl < nplanes; ++pl) {
+    __nv_bfloat16 hh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { hh[k] = __float2bfloat16_rn(v[k]); v[k] -= __bfloat162float(hh[k]); }
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(planes + pl * plane + r * cols + c);
+    dst[0] = __halves2bfloat162(hh[0], hh[1]);
+    dst[1] = __halves2bfloat162(hh[2], hh[3]);
+  }
+}
+
+size_t attention_tc_scratch_bytes(int batch, int heads, int tq, int tk, int mode) {
+  if (mode == FA_GEMM_F32_SIMT) return 0;
+  const int npl = mode == FA_GEMM_BF16X1 ? 1 : 2;
+  const int tkp = (tk + 63) / 64 * 64;
+  const int d = heads * AT_D;
+  return (size_t)npl * 2 * ((size_t)batch * tq * d + (size_t)batch * tk * d + (size_t)batch * d * tkp) + 4096;
+}
+
+int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                        const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
+                        __nv_bfloat16* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st) {
+  if (batch <= 0 || tq <= 0) return FA_OK;
+  if (!q || !k || !v || !key_lens || tk <= 0 || !scratch) return FA_ERR_ARG;
+  if ((ldq | ldk | ldv) & 3) return FA_ERR_UNSUPPORTED;
+  const int npl = mode == FA_GEMM_BF16X1 ? 1 : 2;
+  const int d = heads * AT_D;
+  const int tkp = (tk + 63) / 64 * 64;
+  const int64_t mq = (int64_t)batch * tq, mk = (int64_t)batch * tk, mv = (int64_t)batch * d;
+  Arena local(scratch->base, scratch->cap);
+  __nv_bfloat16* qp = local.take<__nv_bfloat16>((size_t)npl * mq * d);
+  __nv_bfloat16* kp = local.take<__nv_bfloat16>((size_t)npl * mk * d);
+  __nv_bfloat16* vt = local.take<__nv_bfloat16>((size_t)npl * mv * tkp);
+  if (!local.ok()) return FA_ERR_WORKSPACE;
+  const float qscale = (float)(1.0 / sqrt((double)AT_D));
+  {
+    const int64_t tot = mq * (d / 4);
+    scale_split_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q, ldq, mq, d, qscale, npl, qp);
+    FA_CHECK_LAUNCH();
+    const int64_t totk = mk * (d / 4);
+    scale_split_kernel<<<(unsigned)((totk + 255) / 256), 256, 0, st>>>(k, ldk, mk, d, 1.0f, npl, kp);
+    FA_CHECK_LAUNCH();
+    dim3 g((tkp + 63) / 64, heads * 2, batch);
+    vt_planes_kernel<<<g, 256, 0, st>>>(v, ldv, tk, tkp, heads, npl, mv * tkp, vt);
+    FA_CHECK_LAUNCH();
+  }
+  CUtensorMap mq_map, mk_map, mv_map;
+  FA_RETURN_IF_ERR(make_bf16_map(&mq_map, qp, (uint64_t)mq * npl, (uint64_t)d, (uint64_t)d, AT_BQ));
+  FA_RETURN_IF_ERR(make_bf16_map(&mk_map, kp, (uint64_t)mk * npl, (uint64_t)d, (uint64_t)d, AT_BKEY));
+  FA_RETURN_IF_ERR(make_bf16_map(&mv_map, vt, (uint64_t)mv * npl, (uint64_t)tk, (uint64_t)tkp, AT_D));
+  AttTcParams p;
+  p.tq = tq; p.tk = tk; p.heads = heads; p.batch = batch; p.key_lens = key_lens;
+  p.q_plane_rows = mq; p.k_plane_rows = mk; p.v_plane_rows = mv;
+  p.ctx = ctx; p.ldc = ldc; p.ctx_planes = ctx_planes; p.ldp = ldp; p.out_nplanes = out_nplanes;
+  dim3 grid((tq + AT_BQ - 1) / AT_BQ, heads, batch);
+  if (npl == 1) {
+    constexpr size_t smem = 2 * AT_Q_KBLK + 2 * (2 * AT_K_KBLK + AT_V_TILE) + AT_P_TILE + 1024 + 256;
+    static bool done = false;
+    if (!done) { FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
+    attention_tc_kernel<1><<<grid, 256, smem, st>>>(mq_map, mk_map, mv_map, p);
+  } else {
+    constexpr size_t smem = 2 * (2 * AT_Q_KBLK + 2 * (2 * AT_K_KBLK + AT_V_TILE) + AT_P_TILE) + 1024 + 256;
+    static bool done = false;
+    if (!done) { FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
+    attention_tc_kernel<2><<<grid, 256, smem, st>>>(mq_map, mk_map, mv_map, p);
+  }
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+}  // namespace fa
+
+extern "C" size_t fa_attention_tc_workspace_bytes(int32_t batch, int32_t heads, int32_t tq, int32_t tk, int32_t gemm_mode) {
+  return fa::attention_tc_scratch_bytes(batch, heads, tq, tk, gemm_mode);
+}
+
+extern "C" int fa_attention_tc(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                               const int32_t* key_lens, int32_t batch, int32_t heads, int32_t tq, int32_t tk, float* ctx,
+                               int64_t ld_ctx, int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream) {
+  if (!ctx || heads * fa::AT_D > 4096 || (ld_ctx & 3)) return FA_ERR_ARG;
+  if (gemm_mode == FA_GEMM_F32_SIMT) return FA_ERR_ARG;
+  fa::Arena scratch(workspace, ws_bytes);
+  return fa::attention_tc_launch(q, ldq, k, ldk, v, ldv, key_lens, batch, heads, tq, tk, ctx, ld_ctx, nullptr, 0, 0, gemm_mode,
+                                 &scratch, (cudaStream_t)stream);
+}

@@ -1,6 +1,7 @@
 // Internal launch helpers shared between translation units (not part of the C ABI).
 #pragma once
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace fa {
 
@@ -14,6 +15,16 @@ size_t gemm_tc_scratch_bytes(int64_t max_rows, int max_k, int mode);
 int gemm_tc_launch(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, const float* r1,
                    int64_t ld1, const float* r2, int64_t ld2, float* y, int64_t ldy, int mode, Arena* scratch,
                    cudaStream_t st);
+// tcgen05 attention (attention_tc.cu); ctx fp32 and/or bf16 planes [npl][B*tq][ldp]
+size_t attention_tc_scratch_bytes(int batch, int heads, int tq, int tk, int mode);
+int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                        const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
+                        __nv_bfloat16* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st);
+int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
+                          const float* r2, int64_t ld2, float* y, int64_t ldy, __nv_bfloat16* out_planes, int64_t ldo,
+                          int mode, cudaStream_t st);
+int split_rows_launch(const float* x, int64_t ldx, int64_t rows, int cols, int cols_pad, int nplanes, __nv_bfloat16* planes,
+                      cudaStream_t st);
 int attention_f32_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                          const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
                          cudaStream_t st);

@@ -16,11 +16,27 @@ static int linear(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin
   return gemm_tc_launch(x, ldx, rows, lin, relu, r1, ld1, r2, ld2, y, ldy, mode, scratch, st);
 }
 
+static inline int npl_for(int mode) { return mode == FA_GEMM_BF16X1 ? 1 : (mode == FA_GEMM_BF16X3 ? 2 : 3); }
+static inline size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
+
+// tensor-core modes only: fp32 rows in -> bf16 planes out (input of a following GEMM), fused in the GEMM epilogue
+static int linear_to_planes(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, __nv_bfloat16* out_planes,
+                            int mode, Arena* scratch, cudaStream_t st) {
+  const int npl = npl_for(mode);
+  Arena local(scratch->base, scratch->cap);
+  __nv_bfloat16* planes = local.take<__nv_bfloat16>((size_t)npl * rows * lin.in_pad);
+  if (!local.ok()) return FA_ERR_WORKSPACE;
+  FA_RETURN_IF_ERR(split_rows_launch(x, ldx, rows, lin.in_f, lin.in_pad, npl, planes, st));
+  return gemm_tc_planes_launch(planes, rows, lin, relu, nullptr, 0, nullptr, 0, nullptr, 0, out_planes, lin.out_f, mode, st);
+}
+
 // ------------------------------------------------------------------------------------------------ encoder
-struct EncPlan {
-  size_t u, qkv, mem, ctx, xa, xb, h, scratch;
-};
-static size_t enc_plan(int64_t M, int din, int mode, EncPlan* p) {
+static size_t enc_scratch_bytes(int batch, int t_max, int heads, int mode) {
+  const int64_t M = (int64_t)batch * t_max;
+  return max_sz(gemm_tc_scratch_bytes(M, 2048, mode), attention_tc_scratch_bytes(batch, heads, t_max, t_max, mode));
+}
+static size_t enc_plan(int batch, int t_max, int din, int mode) {
+  const int64_t M = (int64_t)batch * t_max;
   ArenaSizer s;
   s.take(M * (size_t)din * 4);   // u
   s.take(M * 1536ull * 4);       // qkv
@@ -29,8 +45,11 @@ static size_t enc_plan(int64_t M, int din, int mode, EncPlan* p) {
   s.take(M * 512ull * 4);        // xa
   s.take(M * 512ull * 4);        // xb
   s.take(M * 2048ull * 4);       // h
-  s.take(gemm_tc_scratch_bytes(M, 2048, mode));
-  (void)p;
+  if (mode != FA_GEMM_F32_SIMT) {
+    s.take(3ull * M * 512 * 2);    // ctx planes
+    s.take(3ull * M * 2048 * 2);   // h planes
+  }
+  s.take(enc_scratch_bytes(batch, t_max, 4, mode));
   return s.off + 256;
 }
 
@@ -39,7 +58,7 @@ static size_t enc_plan(int64_t M, int din, int mode, EncPlan* p) {
 using namespace fa;
 
 extern "C" size_t fa_sanm_encoder_workspace_bytes(int32_t batch, int32_t t_max, int32_t gemm_mode) {
-  return enc_plan((int64_t)batch * t_max, 560, gemm_mode, nullptr);
+  return enc_plan(batch, t_max, 560, gemm_mode);
 }
 
 extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats, const int32_t* lens, int32_t batch,
@@ -59,7 +78,11 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
   float* xa = a.take<float>(M * 512ull);
   float* xb = a.take<float>(M * 512ull);
   float* h = a.take<float>(M * 2048ull);
-  const size_t sb = gemm_tc_scratch_bytes(M, 2048, gemm_mode);
+  const bool tc = gemm_mode != FA_GEMM_F32_SIMT;
+  const int npl = npl_for(gemm_mode);
+  __nv_bfloat16* ctx_planes = tc ? a.take<__nv_bfloat16>(3ull * M * 512) : nullptr;
+  __nv_bfloat16* h_planes = tc ? a.take<__nv_bfloat16>(3ull * M * 2048) : nullptr;
+  const size_t sb = enc_scratch_bytes(batch, t_max, enc->heads, gemm_mode);
   char* sp = a.take<char>(sb);
   if (!a.ok()) return FA_ERR_WORKSPACE;
   Arena scratch(sp, sb);
@@ -78,15 +101,28 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
     }
     FA_RETURN_IF_ERR(linear(u, in, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, gemm_mode, &scratch, st));
     FA_RETURN_IF_ERR(fsmn_launch(qkv + 2 * D, 3 * D, lens, batch, t_max, D, L.fsmn_w, enc->fsmn_k, nullptr, 0, mem, D, st));
-    FA_RETURN_IF_ERR(attention_f32_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, t_max,
-                                          t_max, ctx, D, st));
     // x2 = (residual if in_size == size) + (linear_out(ctx) + fsmn_memory)     encoder.py:120-137, attention.py:327
     float* x2 = (x == xa) ? xb : xa;
-    FA_RETURN_IF_ERR(linear(ctx, D, M, L.out, 0, mem, D, (in == D) ? x : nullptr, D, x2, D, gemm_mode, &scratch, st));
-    FA_RETURN_IF_ERR(layernorm_launch(x2, M, L.norm2, u, nullptr, 1.f, t_max, st));
-    FA_RETURN_IF_ERR(linear(u, D, M, L.w1, 1, nullptr, 0, nullptr, 0, h, L.w1.out_f, gemm_mode, &scratch, st));
+    const float* res = (in == D) ? x : nullptr;
     float* x3 = (x2 == xa) ? xb : xa;
-    FA_RETURN_IF_ERR(linear(h, L.w1.out_f, M, L.w2, 0, x2, D, nullptr, 0, x3, D, gemm_mode, &scratch, st));
+    if (!tc) {
+      FA_RETURN_IF_ERR(attention_f32_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, t_max,
+                                            t_max, ctx, D, st));
+      FA_RETURN_IF_ERR(linear(ctx, D, M, L.out, 0, mem, D, res, D, x2, D, gemm_mode, &scratch, st));
+      FA_RETURN_IF_ERR(layernorm_launch(x2, M, L.norm2, u, nullptr, 1.f, t_max, st));
+      FA_RETURN_IF_ERR(linear(u, D, M, L.w1, 1, nullptr, 0, nullptr, 0, h, L.w1.out_f, gemm_mode, &scratch, st));
+      FA_RETURN_IF_ERR(linear(h, L.w1.out_f, M, L.w2, 0, x2, D, nullptr, 0, x3, D, gemm_mode, &scratch, st));
+    } else {
+      // tensor-core path: attention emits the context as bf16 planes (A operand of linear_out); FFN w_1 emits its
+      // ReLU output as planes for w_2 — neither intermediate makes an fp32 round trip through HBM
+      FA_RETURN_IF_ERR(attention_tc_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, t_max, t_max,
+                                           nullptr, 0, ctx_planes, D, npl, gemm_mode, &scratch, st));
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(ctx_planes, M, L.out, 0, mem, D, res, D, x2, D, nullptr, 0, gemm_mode, st));
+      FA_RETURN_IF_ERR(layernorm_launch(x2, M, L.norm2, u, nullptr, 1.f, t_max, st));
+      if (L.w1.out_f != L.w2.in_pad) return FA_ERR_UNSUPPORTED;
+      FA_RETURN_IF_ERR(linear_to_planes(u, D, M, L.w1, 1, h_planes, gemm_mode, &scratch, st));
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(h_planes, M, L.w2, 0, x2, D, nullptr, 0, x3, D, nullptr, 0, gemm_mode, st));
+    }
     x = x3;
   }
   return layernorm_launch(x, M, enc->after_norm, out, nullptr, 1.f, t_max, st);
@@ -131,7 +167,11 @@ extern "C" int fa_cif_predictor_forward(const FaPredictor* pred, const float* en
 }
 
 // ------------------------------------------------------------------------------------------------ decoder
-static size_t dec_plan(int64_t Mq, int64_t Mk, int vocab, int mode) {
+static size_t dec_scratch_bytes(int batch, int t_max, int n_max, int mode) {
+  const int64_t Mq = (int64_t)batch * n_max, Mk = (int64_t)batch * t_max;
+  return max_sz(gemm_tc_scratch_bytes(Mq > Mk ? Mq : Mk, 2048, mode), attention_tc_scratch_bytes(batch, 4, n_max, t_max, mode));
+}
+static size_t dec_plan(int64_t Mq, int64_t Mk, int vocab, int mode, size_t dec_scratch) {
   ArenaSizer s;
   s.take(Mq * 512ull * 4);   // ya
   s.take(Mq * 512ull * 4);   // yb
@@ -142,13 +182,17 @@ static size_t dec_plan(int64_t Mq, int64_t Mk, int vocab, int mode) {
   s.take(Mq * 512ull * 4);   // ctx
   s.take(Mk * 1024ull * 4);  // kv
   s.take(Mq * (size_t)vocab * 4);  // logits (used when the caller passes none)
-  s.take(gemm_tc_scratch_bytes(Mq > Mk ? Mq : Mk, 2048, mode));
+  if (mode != FA_GEMM_F32_SIMT) {
+    s.take(3ull * Mq * 512 * 2);   // ctx planes
+    s.take(3ull * Mk * 512 * 2);   // enc planes (split once, reused by the 16 kv GEMMs)
+  }
+  s.take(dec_scratch);
   return s.off + 256;
 }
 
 extern "C" size_t fa_paraformer_decoder_workspace_bytes(int32_t batch, int32_t t_max, int32_t n_max, int32_t vocab,
                                                         int32_t gemm_mode) {
-  return dec_plan((int64_t)batch * n_max, (int64_t)batch * t_max, vocab, gemm_mode);
+  return dec_plan((int64_t)batch * n_max, (int64_t)batch * t_max, vocab, gemm_mode, dec_scratch_bytes(batch, t_max, n_max, gemm_mode));
 }
 
 static int dec_ffn(const FaDecLayer& L, const float* y, int64_t Mq, float* t1, float* hq, float* f, int mode,
@@ -183,11 +227,16 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
   float* ctx = a.take<float>(Mq * 512ull);
   float* kv = a.take<float>(Mk * 1024ull);
   float* lg = a.take<float>(Mq * (size_t)V);
-  const size_t sb = gemm_tc_scratch_bytes(Mq > Mk ? Mq : Mk, 2048, gemm_mode);
+  const bool tc = gemm_mode != FA_GEMM_F32_SIMT;
+  const int npl = npl_for(gemm_mode);
+  __nv_bfloat16* ctx_planes = tc ? a.take<__nv_bfloat16>(3ull * Mq * 512) : nullptr;
+  __nv_bfloat16* enc_planes = tc ? a.take<__nv_bfloat16>(3ull * Mk * 512) : nullptr;
+  const size_t sb = dec_scratch_bytes(batch, t_max, n_max, gemm_mode);
   char* sp = a.take<char>(sb);
   if (!a.ok()) return FA_ERR_WORKSPACE;
   Arena scratch(sp, sb);
   if (logits) lg = logits;
+  if (tc) FA_RETURN_IF_ERR(split_rows_launch(enc, D, Mk, D, D, npl, enc_planes, st));   // memory is layer-invariant
 
   // tgt = acoustic[:, :n_max]  (decoder.py:424)
   FA_CUDA_OK(cudaMemcpy2DAsync(ya, (size_t)n_max * D * 4, acoustic, (size_t)ld_acoustic_rows * D * 4, (size_t)n_max * D * 4,
@@ -204,11 +253,18 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
     // x = residual + src_attn(LN3(x), memory)    decoder.py:109-118, attention.py:796-813
     FA_RETURN_IF_ERR(layernorm_launch(x2, Mq, L.norm3, t1, nullptr, 1.f, 1, st));
     FA_RETURN_IF_ERR(linear(t1, D, Mq, L.q, 0, nullptr, 0, nullptr, 0, qd, D, gemm_mode, &scratch, st));
-    FA_RETURN_IF_ERR(linear(enc, D, Mk, L.kv, 0, nullptr, 0, nullptr, 0, kv, 2 * D, gemm_mode, &scratch, st));
-    FA_RETURN_IF_ERR(attention_f32_launch(qd, D, kv, 2 * D, kv + D, 2 * D, enc_lens, batch, dec->heads, n_max, t_max, ctx,
-                                          D, st));
     float* y2 = (x2 == ya) ? yb : ya;
-    FA_RETURN_IF_ERR(linear(ctx, D, Mq, L.out, 0, x2, D, nullptr, 0, y2, D, gemm_mode, &scratch, st));
+    if (!tc) {
+      FA_RETURN_IF_ERR(linear(enc, D, Mk, L.kv, 0, nullptr, 0, nullptr, 0, kv, 2 * D, gemm_mode, &scratch, st));
+      FA_RETURN_IF_ERR(attention_f32_launch(qd, D, kv, 2 * D, kv + D, 2 * D, enc_lens, batch, dec->heads, n_max, t_max, ctx,
+                                            D, st));
+      FA_RETURN_IF_ERR(linear(ctx, D, Mq, L.out, 0, x2, D, nullptr, 0, y2, D, gemm_mode, &scratch, st));
+    } else {
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(enc_planes, Mk, L.kv, 0, nullptr, 0, nullptr, 0, kv, 2 * D, nullptr, 0, gemm_mode, st));
+      FA_RETURN_IF_ERR(attention_tc_launch(qd, D, kv, 2 * D, kv + D, 2 * D, enc_lens, batch, dec->heads, n_max, t_max, nullptr, 0,
+                                           ctx_planes, D, npl, gemm_mode, &scratch, st));
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(ctx_planes, Mq, L.out, 0, x2, D, nullptr, 0, y2, D, nullptr, 0, gemm_mode, st));
+    }
     y = y2;
   }
   // decoders3: FFN only, no residual (decoder.py:97-102,121); after_norm; output_layer

@@ -267,7 +267,6 @@ class ParaformerB200(nn.Module):
                                     kernel=self.encoder.kernel_size, tail_threshold=self.predictor.tail_threshold,
                                     cif_threshold=self.predictor.threshold)
         self._engine: Optional[ParaformerEngine] = None
-        self._pin: Optional[torch.Tensor] = None
 
     # -- weights enter through load_pretrained_model -> load_state_dict(strict=True) -> this hook
     #    (funasr/train_utils/load_pretrained_model.py:104-113)
@@ -325,15 +324,17 @@ class ParaformerB200(nn.Module):
             if not isinstance(frontend, WavFrontendB200):
                 raise _abi.FunasrB200Error("ParaformerB200 needs frontend='WavFrontendB200' (the fused CUDA frontend)")
             wl = [int(w.numel()) for w in wavs]
+            if min(wl) < 400:
+                raise _abi.FunasrB200Error("utterances shorter than one 25 ms frame (400 samples) are not supported")
             nmax = max(wl)
-            if self._pin is None or self._pin.shape[0] < len(wavs) or self._pin.shape[1] < nmax:
-                self._pin = torch.zeros((len(wavs), nmax), dtype=torch.float32).pin_memory()
-            pin = self._pin[: len(wavs), :nmax]
-            for i, w in enumerate(wavs):                      # pad_sequence (load_utils.py:412)
-                pin[i, : wl[i]].copy_(w)
-                pin[i, wl[i]:].zero_()
-            speech, flens = frontend.forward(pin, wl, device=device)
-            lens = flens.to(torch.int32)
+            # pad_sequence (load_utils.py:412) done on the device: each utterance is copied host->device straight into its
+            # row (truly asynchronous when the caller's buffers are pinned), no host-side staging copy
+            ragged = min(wl) != nmax
+            wav_dev = (torch.zeros if ragged else torch.empty)((len(wavs), nmax), dtype=torch.float32, device=device)
+            for i, w in enumerate(wavs):
+                wav_dev[i, : wl[i]].copy_(w, non_blocking=True)
+            wl_dev = torch.tensor(wl, dtype=torch.int32).to(device, non_blocking=True)
+            speech, lens = frontend.engine(device)(wav_dev, wl_dev, max(num_lfr_frames(n) for n in wl))
             meta_data["extract_feat"] = f"{time.perf_counter() - t2:0.3f}"
             meta_data["batch_data_time"] = sum(num_lfr_frames(n) for n in wl) * frontend.frame_shift * frontend.lfr_n / 1000
         out = eng.forward_feats(speech, lens, sos=self.sos, eos=self.eos, blank=self.blank_id)

@@ -166,6 +166,14 @@ int fa_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const
                  const int32_t* key_lens, int32_t batch, int32_t heads, int32_t tq, int32_t tk,
                  float* ctx, int64_t ld_ctx, fa_stream_t stream);
 
+/* Same contract on the tcgen05 tensor cores (bf16 operand planes, fp32 accumulation in TMEM):
+ * gemm_mode FA_GEMM_BF16X1 (one plane) or FA_GEMM_BF16X3/X6 (hi+lo planes, three MMA terms).  workspace holds the
+ * operand planes (size from fa_attention_tc_workspace_bytes). */
+size_t fa_attention_tc_workspace_bytes(int32_t batch, int32_t heads, int32_t tq, int32_t tk, int32_t gemm_mode);
+int fa_attention_tc(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                    const int32_t* key_lens, int32_t batch, int32_t heads, int32_t tq, int32_t tk,
+                    float* ctx, int64_t ld_ctx, int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Model-level entry points
  * ------------------------------------------------------------------------------------------- */
