@@ -63,6 +63,10 @@ SIGNATURES = {
     "fa_launch_count": (C.c_uint64, []),
     "fa_status_string": (C.c_char_p, [C.c_int]),
     "fa_fbank_lfr_cmvn": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "fa_fbank_lfr_cmvn_strided": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp]),
+    "fa_broadcast_rows": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _i32, _vp]),
+    "fa_ctc_greedy_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "fa_ctc_greedy_forward": (C.c_int, [C.POINTER(FaLinear), _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
     "fa_layernorm": (C.c_int, [_vp, _i64, C.POINTER(FaNorm), _vp, _vp, _f, _i32, _vp]),
     "fa_linear": (C.c_int, [_vp, _i64, _i64, C.POINTER(FaLinear), _i32, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _sz, _vp]),
     "fa_fsmn": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp, _i64, _vp]),

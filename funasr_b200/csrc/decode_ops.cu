@@ -87,6 +87,41 @@ __global__ void greedy_filter_kernel(const int32_t* __restrict__ ids, const int3
   if (lane == 0) out_lens[b] = count;
 }
 
+// One warp per utterance: torch.unique_consecutive over the frame arg-max ids, then drop blank
+// (sense_voice/model.py:1015-1025).  Ordered compaction with ballots.
+__global__ void ctc_filter_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ lens, int t_max, int blank,
+                                  int32_t* __restrict__ out_ids, int32_t* __restrict__ out_lens) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int len = min(lens[b], t_max);
+  const int32_t* row = ids + (int64_t)b * t_max;
+  int count = 0;
+  for (int base = 0; base < t_max; base += 32) {
+    const int t = base + lane;
+    const int id = t < len ? row[t] : -1;
+    const int prev = (t > 0 && t < len) ? row[t - 1] : -2;
+    const bool keep = t < len && id != prev && id != blank;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) out_ids[(int64_t)b * t_max + count + __popc(m & ((1u << lane) - 1))] = id;
+    count += __popc(m);
+  }
+  for (int k = count + lane; k < t_max; k += 32) out_ids[(int64_t)b * t_max + k] = -1;
+  if (lane == 0) out_lens[b] = count;
+}
+
+__global__ void broadcast_rows_kernel(const float* __restrict__ rows, int n_rows, int cols, float* __restrict__ dst,
+                                      int64_t batch_stride_rows) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_rows * cols) dst[(int64_t)b * batch_stride_rows * cols + i] = rows[i];
+}
+
+int ctc_filter_launch(const int32_t* ids, const int32_t* lens, int batch, int t_max, int blank, int32_t* out_ids,
+                      int32_t* out_lens, cudaStream_t st) {
+  ctc_filter_kernel<<<batch, 32, 0, st>>>(ids, lens, t_max, blank, out_ids, out_lens);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
 // x = hi + mid + lo with hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid); planes [3][rows][cols_pad].
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, int cols_pad,
@@ -121,6 +156,15 @@ extern "C" int fa_greedy_filter(const int32_t* argmax_ids, const int32_t* tok_le
                                 fa_stream_t stream) {
   if (!argmax_ids || !tok_lens || !out_ids || !out_lens || batch <= 0 || n_max <= 0) return FA_ERR_ARG;
   fa::greedy_filter_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(argmax_ids, tok_lens, n_max, sos, eos, blank, out_ids, out_lens);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+extern "C" int fa_broadcast_rows(const float* rows, int32_t n_rows, int32_t cols, float* dst, int64_t dst_batch_stride_rows,
+                                 int32_t batch, fa_stream_t stream) {
+  if (!rows || !dst || n_rows <= 0 || cols <= 0 || batch <= 0 || dst_batch_stride_rows < n_rows) return FA_ERR_ARG;
+  dim3 grid((n_rows * cols + 255) / 256, batch);
+  fa::broadcast_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rows, n_rows, cols, dst, dst_batch_stride_rows);
   FA_CHECK_LAUNCH();
   return FA_OK;
 }

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 fbank_lfr_cmvn_kernel(const float* __restrict__ wav, const int32_t* __restrict__ wav_lens, int64_t wav_stride,
                       const float* __restrict__ cmvn, const float* __restrict__ mel_banks,
                       const float* __restrict__ window, float* __restrict__ feats, int32_t* __restrict__ feat_lens,
-                      int t_max) {
+                      int t_max, int64_t batch_stride_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FbankSmem& s = *reinterpret_cast<FbankSmem*>(smem_raw);
   const int b = blockIdx.y, i0 = blockIdx.x * kRows;
@@ -47,7 +47,7 @@ fbank_lfr_cmvn_kernel(const float* __restrict__ wav, const int32_t* __restrict__
   const int t_b = (m + kLfrN - 1) / kLfrN;                    // wav_frontend.py:73
   if (blockIdx.x == 0 && tid == 0) feat_lens[b] = t_b;
 
-  float* out = feats + ((int64_t)b * t_max + i0) * kFeat;
+  float* out = feats + ((int64_t)b * batch_stride_rows + i0) * kFeat;
   if (i0 >= t_b) {  // pure padding rows
     const int rows = min(kRows, t_max - i0);
     for (int idx = tid; idx < rows * kFeat; idx += blockDim.x) out[idx] = 0.f;
@@ -182,10 +182,12 @@ fbank_lfr_cmvn_kernel(const float* __restrict__ wav, const int32_t* __restrict__
 
 }  // namespace fa
 
-extern "C" int fa_fbank_lfr_cmvn(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride,
-                                 const float* cmvn, const float* mel_banks, const float* window, float* feats,
-                                 int32_t* feat_lens, int32_t t_max, fa_stream_t stream) {
-  if (!wav || !wav_lens || !mel_banks || !window || !feats || !feat_lens || batch <= 0 || t_max <= 0)
+extern "C" int fa_fbank_lfr_cmvn_strided(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride,
+                                         const float* cmvn, const float* mel_banks, const float* window, float* feats,
+                                         int64_t feats_batch_stride_rows, int32_t* feat_lens, int32_t t_max,
+                                         fa_stream_t stream) {
+  if (!wav || !wav_lens || !mel_banks || !window || !feats || !feat_lens || batch <= 0 || t_max <= 0 ||
+      feats_batch_stride_rows < t_max)
     return FA_ERR_ARG;
   const size_t smem = sizeof(fa::FbankSmem);
   static bool attr_done = false;
@@ -195,7 +197,13 @@ extern "C" int fa_fbank_lfr_cmvn(const float* wav, const int32_t* wav_lens, int3
   }
   dim3 grid((t_max + fa::kRows - 1) / fa::kRows, batch);
   fa::fbank_lfr_cmvn_kernel<<<grid, fa::kWarps * 32, smem, (cudaStream_t)stream>>>(
-      wav, wav_lens, wav_stride, cmvn, mel_banks, window, feats, feat_lens, t_max);
+      wav, wav_lens, wav_stride, cmvn, mel_banks, window, feats, feat_lens, t_max, feats_batch_stride_rows);
   FA_CHECK_LAUNCH();
   return FA_OK;
+}
+
+extern "C" int fa_fbank_lfr_cmvn(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride,
+                                 const float* cmvn, const float* mel_banks, const float* window, float* feats,
+                                 int32_t* feat_lens, int32_t t_max, fa_stream_t stream) {
+  return fa_fbank_lfr_cmvn_strided(wav, wav_lens, batch, wav_stride, cmvn, mel_banks, window, feats, t_max, feat_lens, t_max, stream);
 }

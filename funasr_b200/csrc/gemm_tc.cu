@@ -95,7 +95,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tma_load_2d(st + pl * TC_TILE_BYTES_A, &map_a, &full_bar[stage], kb * TC_BK, (int)(pl * p.a_plane_rows + (int64_t)tm * TC_BM));
 #pragma unroll
           for (int pl = 0; pl < WPL; ++pl)
-            tma_load_2d(st + APL * TC_TILE_BYTES_A + pl * TILE_W_BYTES, &map_w, &full_bar[stage], kb * TC_BK, pl * p.w_plane_rows + tn * BN);
+#pragma unroll
+            for (int hb = 0; hb < BN / 128; ++hb)   // W box = 128 rows; a 256-wide tile is two boxes, contiguous in smem
+              tma_load_2d(st + APL * TC_TILE_BYTES_A + pl * TILE_W_BYTES + hb * (128 * TC_BK * 2), &map_w, &full_bar[stage], kb * TC_BK,
+                          pl * p.w_plane_rows + tn * BN + hb * 128);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -317,10 +320,13 @@ int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLine
   if (y && ((ldy & 3) || (((uintptr_t)y) & 15))) return FA_ERR_UNSUPPORTED;
   if ((r1 && (ld1 & 3)) || (r2 && (ld2 & 3))) return FA_ERR_UNSUPPORTED;
   const int npl = planes_for_mode(mode);
-  constexpr int BN = 128;
+  // 128x256 tiles halve the operand bytes per MMA cycle (the 128x128 tile is L2-bandwidth bound); used when N splits
+  // evenly and there are enough tiles to fill the machine.  x6 keeps 128x128 (three planes per operand do not fit twice).
+  const bool wide = (npl <= 2) && (N % 256 == 0) && (N >= 1024);
+  const int BN = wide ? 256 : 128;
   CUtensorMap ma, mw;
   FA_RETURN_IF_ERR(make_bf16_map(&ma, a_planes, (uint64_t)M * npl, (uint64_t)Kp, (uint64_t)Kp, TC_BM));
-  FA_RETURN_IF_ERR(make_bf16_map(&mw, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, BN));
+  FA_RETURN_IF_ERR(make_bf16_map(&mw, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, wide ? 128 : BN));
   TcParams p;
   p.M = M; p.N = N; p.Kp = Kp; p.a_plane_rows = M; p.w_plane_rows = N;
   p.n_terms = mode == FA_GEMM_BF16X1 ? 1 : (mode == FA_GEMM_BF16X3 ? 3 : 6);
@@ -328,10 +334,11 @@ int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLine
   p.out_planes = out_planes; p.ldo = ldo; p.out_nplanes = npl;
   p.tiles_m = (int)((M + TC_BM - 1) / TC_BM); p.tiles_n = (N + BN - 1) / BN;
   if (out_planes && (N % 32 != 0)) return FA_ERR_UNSUPPORTED;
+  if (wide) return npl == 1 ? launch_cfg<256, 4, 1, 1>(ma, mw, p, st) : launch_cfg<256, 2, 2, 2>(ma, mw, p, st);
   switch (npl) {
-    case 1: return launch_cfg<BN, 6, 1, 1>(ma, mw, p, st);
-    case 2: return launch_cfg<BN, 3, 2, 2>(ma, mw, p, st);
-    default: return launch_cfg<BN, 2, 3, 3>(ma, mw, p, st);
+    case 1: return launch_cfg<128, 6, 1, 1>(ma, mw, p, st);
+    case 2: return launch_cfg<128, 3, 2, 2>(ma, mw, p, st);
+    default: return launch_cfg<128, 2, 3, 3>(ma, mw, p, st);
   }
 }
 

@@ -5,8 +5,9 @@
 
 namespace fa {
 
+// y (fp32) and/or planes (bf16 [nplanes][rows][cols_pad], the A operand of a following tcgen05 GEMM)
 int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, const float* pe_inv, float xscale,
-                     int rows_per_batch, cudaStream_t st);
+                     int rows_per_batch, cudaStream_t st, __nv_bfloat16* planes = nullptr, int nplanes = 0, int cols_pad = 0);
 int gemm_f32_launch(const float* A, int64_t lda, int64_t M, const float* W, int N, int K, const float* bias, int relu,
                     const float* r1, int64_t ldr1, const float* r2, int64_t ldr2, float* C, int64_t ldc,
                     cudaStream_t st);
@@ -36,6 +37,8 @@ int cif_alpha_launch(const float* c, int d, const float* w, const float* b0, con
 int cif_fire_launch(const float* enc, const float* alpha_rows, const int32_t* lens, int batch, int t_max, int d,
                     float tail, float* acoustic, int n_cap, int32_t* token_num, float* alphas, float* peaks,
                     cudaStream_t st);
+int ctc_filter_launch(const int32_t* ids, const int32_t* lens, int batch, int t_max, int blank, int32_t* out_ids,
+                      int32_t* out_lens, cudaStream_t st);
 int argmax_lse_launch(float* logits, int64_t rows, int vocab, int64_t ld, int32_t* ids, float* best_logp,
                       int write_log_softmax, cudaStream_t st);
 

@@ -2,8 +2,11 @@
 // held in registers (two-pass mean / variance in fp32), float4 loads and stores.
 // Optional fused prologue for the first encoder layer: x*sqrt(d_model) + sinusoidal position encoding
 // (SANMEncoder.forward encoder.py:409,428; SinusoidalPositionEncoder embedding.py:396-432).
+// Optional fused epilogue for the tensor-core path: the normalised row is written as bf16 planes (hi, mid, lo) — the A
+// operand of the following tcgen05 GEMM — instead of / in addition to fp32.
 // HBM-bound: algorithmic bytes = 8 B per element (read + write).
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace fa {
 
@@ -11,7 +14,8 @@ template <int NV>  // float4 per lane (row length <= 128*NV)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ g,
                  const float* __restrict__ bta, float eps, float* y,   // x may alias y (in-place)
-                 const float* __restrict__ pe_inv, float xscale, int rows_per_batch) {
+                 const float* __restrict__ pe_inv, float xscale, int rows_per_batch,
+                 __nv_bfloat16* __restrict__ planes, int nplanes, int cols_pad) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -54,7 +58,8 @@ layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ 
     }
   }
   const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)n + eps);
-  float4* yr = reinterpret_cast<float4*>(y + row * n);
+  float4* yr = y ? reinterpret_cast<float4*>(y + row * n) : nullptr;
+  const int64_t plane_elems = rows * cols_pad;
   const float4* g4 = reinterpret_cast<const float4*>(g);
   const float4* b4 = reinterpret_cast<const float4*>(bta);
 #pragma unroll
@@ -67,22 +72,41 @@ layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ 
       o.y = (v[i].y - mean) * rstd * gg.y + bb.y;
       o.z = (v[i].z - mean) * rstd * gg.z + bb.z;
       o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
-      yr[c4] = o;
+      if (yr) yr[c4] = o;
+      if (planes) {
+        float e[4] = {o.x, o.y, o.z, o.w};
+        __nv_bfloat16* dst = planes + row * cols_pad + 4 * c4;
+        for (int pl = 0; pl < nplanes; ++pl) {
+          __nv_bfloat16 hh[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { hh[k] = __float2bfloat16_rn(e[k]); e[k] -= __bfloat162float(hh[k]); }
+          __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(dst + pl * plane_elems);
+          d2[0] = __halves2bfloat162(hh[0], hh[1]);
+          d2[1] = __halves2bfloat162(hh[2], hh[3]);
+        }
+      }
+    } else if (planes && 4 * c4 < cols_pad) {          // zero the K padding (e.g. 560 -> 576)
+      for (int pl = 0; pl < nplanes; ++pl) {
+        __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(planes + pl * plane_elems + row * cols_pad + 4 * c4);
+        d2[0] = __halves2bfloat162(__float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f));
+        d2[1] = d2[0];
+      }
     }
   }
 }
 
 int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, const float* pe_inv, float xscale,
-                     int rows_per_batch, cudaStream_t st) {
+                     int rows_per_batch, cudaStream_t st, __nv_bfloat16* planes, int nplanes, int cols_pad) {
   if (rows <= 0) return FA_OK;
-  if (!x || !y || !nm.g || !nm.b) return FA_ERR_ARG;
+  if (!x || (!y && !planes) || !nm.g || !nm.b) return FA_ERR_ARG;
   const int n = nm.n;
   if (n <= 0 || (n & 3) || n > 2048) return FA_ERR_UNSUPPORTED;
-  const int need = (n / 4 + 31) / 32;
+  if (planes && (cols_pad < n || (cols_pad & 3) || cols_pad > 2048)) return FA_ERR_UNSUPPORTED;
+  const int need = ((planes ? cols_pad : n) / 4 + 31) / 32;
   const unsigned blocks = (unsigned)((rows + 7) / 8);
 #define FA_LN_CASE(NV)                                                                                       \
   layernorm_kernel<NV><<<blocks, 256, 0, st>>>(x, rows, n, nm.g, nm.b, nm.eps, y, pe_inv, xscale,           \
-                                               rows_per_batch > 0 ? rows_per_batch : 1)
+                                               rows_per_batch > 0 ? rows_per_batch : 1, planes, nplanes, cols_pad)
   if (need <= 4) FA_LN_CASE(4);
   else if (need <= 5) FA_LN_CASE(5);
   else if (need <= 8) FA_LN_CASE(8);
@@ -97,5 +121,5 @@ int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, c
 extern "C" int fa_layernorm(const float* x, int64_t rows, const FaNorm* norm, float* y, const float* pe_inv,
                             float xscale, int32_t rows_per_batch, fa_stream_t stream) {
   if (!norm) return FA_ERR_ARG;
-  return fa::layernorm_launch(x, rows, *norm, y, pe_inv, xscale, rows_per_batch, (cudaStream_t)stream);
+  return fa::layernorm_launch(x, rows, *norm, y, pe_inv, xscale, rows_per_batch, (cudaStream_t)stream, nullptr, 0, 0);
 }

@@ -19,17 +19,6 @@ static int linear(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin
 static inline int npl_for(int mode) { return mode == FA_GEMM_BF16X1 ? 1 : (mode == FA_GEMM_BF16X3 ? 2 : 3); }
 static inline size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 
-// tensor-core modes only: fp32 rows in -> bf16 planes out (input of a following GEMM), fused in the GEMM epilogue
-static int linear_to_planes(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, __nv_bfloat16* out_planes,
-                            int mode, Arena* scratch, cudaStream_t st) {
-  const int npl = npl_for(mode);
-  Arena local(scratch->base, scratch->cap);
-  __nv_bfloat16* planes = local.take<__nv_bfloat16>((size_t)npl * rows * lin.in_pad);
-  if (!local.ok()) return FA_ERR_WORKSPACE;
-  FA_RETURN_IF_ERR(split_rows_launch(x, ldx, rows, lin.in_f, lin.in_pad, npl, planes, st));
-  return gemm_tc_planes_launch(planes, rows, lin, relu, nullptr, 0, nullptr, 0, nullptr, 0, out_planes, lin.out_f, mode, st);
-}
-
 // ------------------------------------------------------------------------------------------------ encoder
 static size_t enc_scratch_bytes(int batch, int t_max, int heads, int mode) {
   const int64_t M = (int64_t)batch * t_max;
@@ -48,6 +37,7 @@ static size_t enc_plan(int batch, int t_max, int din, int mode) {
   if (mode != FA_GEMM_F32_SIMT) {
     s.take(3ull * M * 512 * 2);    // ctx planes
     s.take(3ull * M * 2048 * 2);   // h planes
+    s.take(3ull * M * 576 * 2);    // LN output planes
   }
   s.take(enc_scratch_bytes(batch, t_max, 4, mode));
   return s.off + 256;
@@ -69,7 +59,8 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
   const int64_t M = (int64_t)batch * t_max;
   const int D = enc->after_norm.n;
   const int din = enc->layers[0].norm1.n;
-  if (D != 512 || enc->heads * 128 != D || din > 560) return FA_ERR_UNSUPPORTED;
+  const bool embed = enc->pe_inv_timescales != nullptr;   // false: plain stack over an existing [B,T,512] stream
+  if (D != 512 || enc->heads * 128 != D || din > 560 || (!embed && din != D)) return FA_ERR_UNSUPPORTED;
   Arena a(workspace, ws_bytes);
   float* u = a.take<float>(M * (size_t)560);
   float* qkv = a.take<float>(M * 1536ull);
@@ -82,28 +73,29 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
   const int npl = npl_for(gemm_mode);
   __nv_bfloat16* ctx_planes = tc ? a.take<__nv_bfloat16>(3ull * M * 512) : nullptr;
   __nv_bfloat16* h_planes = tc ? a.take<__nv_bfloat16>(3ull * M * 2048) : nullptr;
+  __nv_bfloat16* u_planes = tc ? a.take<__nv_bfloat16>(3ull * M * 576) : nullptr;
   const size_t sb = enc_scratch_bytes(batch, t_max, enc->heads, gemm_mode);
   char* sp = a.take<char>(sb);
   if (!a.ok()) return FA_ERR_WORKSPACE;
   Arena scratch(sp, sb);
 
-  const float* x = nullptr;  // residual stream (undefined before layer 0: in_size != size -> no residual)
+  const float* x = embed ? nullptr : feats;  // residual stream (with PE input: undefined before layer 0, in_size != size)
   for (int l = 0; l < enc->n_layers; ++l) {
     const FaEncLayer& L = enc->layers[l];
     const int in = L.norm1.n;
     if (L.qkv.in_f != in || L.qkv.out_f != 3 * D || L.w1.in_f != D || L.w2.out_f != D) return FA_ERR_ARG;
     // x = x*sqrt(D) + PE is folded into the first LayerNorm (encoder.py:409,428)
-    if (l == 0) {
-      FA_RETURN_IF_ERR(layernorm_launch(feats, M, L.norm1, u, enc->pe_inv_timescales, sqrtf((float)D), t_max, st));
-    } else {
-      if (in != D) return FA_ERR_UNSUPPORTED;
-      FA_RETURN_IF_ERR(layernorm_launch(x, M, L.norm1, u, nullptr, 1.f, t_max, st));
-    }
-    FA_RETURN_IF_ERR(linear(u, in, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, gemm_mode, &scratch, st));
+    // tensor-core path: LayerNorm writes the bf16 planes the QKV GEMM consumes (no fp32 round trip, no split pass)
+    if (l > 0 && in != D) return FA_ERR_UNSUPPORTED;
+    const bool first = embed && l == 0;
+    FA_RETURN_IF_ERR(layernorm_launch(first ? feats : x, M, L.norm1, tc ? nullptr : u, first ? enc->pe_inv_timescales : nullptr,
+                                      first ? sqrtf((float)D) : 1.f, t_max, st, u_planes, npl, L.qkv.in_pad));
+    if (tc) FA_RETURN_IF_ERR(gemm_tc_planes_launch(u_planes, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, nullptr, 0, gemm_mode, st));
+    else FA_RETURN_IF_ERR(linear(u, in, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, gemm_mode, &scratch, st));
     FA_RETURN_IF_ERR(fsmn_launch(qkv + 2 * D, 3 * D, lens, batch, t_max, D, L.fsmn_w, enc->fsmn_k, nullptr, 0, mem, D, st));
     // x2 = (residual if in_size == size) + (linear_out(ctx) + fsmn_memory)     encoder.py:120-137, attention.py:327
     float* x2 = (x == xa) ? xb : xa;
-    const float* res = (in == D) ? x : nullptr;
+    const float* res = (in == D && x != nullptr) ? x : nullptr;
     float* x3 = (x2 == xa) ? xb : xa;
     if (!tc) {
       FA_RETURN_IF_ERR(attention_f32_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, t_max,
@@ -118,9 +110,9 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
       FA_RETURN_IF_ERR(attention_tc_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, t_max, t_max,
                                            nullptr, 0, ctx_planes, D, npl, gemm_mode, &scratch, st));
       FA_RETURN_IF_ERR(gemm_tc_planes_launch(ctx_planes, M, L.out, 0, mem, D, res, D, x2, D, nullptr, 0, gemm_mode, st));
-      FA_RETURN_IF_ERR(layernorm_launch(x2, M, L.norm2, u, nullptr, 1.f, t_max, st));
-      if (L.w1.out_f != L.w2.in_pad) return FA_ERR_UNSUPPORTED;
-      FA_RETURN_IF_ERR(linear_to_planes(u, D, M, L.w1, 1, h_planes, gemm_mode, &scratch, st));
+      if (L.w1.out_f != L.w2.in_pad || L.w1.in_pad != D) return FA_ERR_UNSUPPORTED;
+      FA_RETURN_IF_ERR(layernorm_launch(x2, M, L.norm2, nullptr, nullptr, 1.f, t_max, st, u_planes, npl, D));
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(u_planes, M, L.w1, 1, nullptr, 0, nullptr, 0, nullptr, 0, h_planes, L.w1.out_f, gemm_mode, st));
       FA_RETURN_IF_ERR(gemm_tc_planes_launch(h_planes, M, L.w2, 0, x2, D, nullptr, 0, x3, D, nullptr, 0, gemm_mode, st));
     }
     x = x3;
@@ -185,6 +177,8 @@ static size_t dec_plan(int64_t Mq, int64_t Mk, int vocab, int mode, size_t dec_s
   if (mode != FA_GEMM_F32_SIMT) {
     s.take(3ull * Mq * 512 * 2);   // ctx planes
     s.take(3ull * Mk * 512 * 2);   // enc planes (split once, reused by the 16 kv GEMMs)
+    s.take(3ull * Mq * 512 * 2);   // LN output planes
+    s.take(3ull * Mq * 2048 * 2);  // FFN hidden planes
   }
   s.take(dec_scratch);
   return s.off + 256;
@@ -196,8 +190,16 @@ extern "C" size_t fa_paraformer_decoder_workspace_bytes(int32_t batch, int32_t t
 }
 
 static int dec_ffn(const FaDecLayer& L, const float* y, int64_t Mq, float* t1, float* hq, float* f, int mode,
-                   Arena* scratch, cudaStream_t st) {
+                   Arena* scratch, cudaStream_t st, __nv_bfloat16* t1_planes, __nv_bfloat16* hq_planes) {
   // f = w_2( LN_2048( relu( w_1( LN1(y) ) ) ) )   decoder.py:97-100, sanm/positionwise_feed_forward.py:33
+  if (mode != FA_GEMM_F32_SIMT) {
+    const int npl = npl_for(mode);
+    if (L.ffn_w1.in_pad != 512 || L.ffn_w2.in_pad != L.ffn_w1.out_f) return FA_ERR_UNSUPPORTED;
+    FA_RETURN_IF_ERR(layernorm_launch(y, Mq, L.norm1, nullptr, nullptr, 1.f, 1, st, t1_planes, npl, 512));
+    FA_RETURN_IF_ERR(gemm_tc_planes_launch(t1_planes, Mq, L.ffn_w1, 1, nullptr, 0, nullptr, 0, hq, L.ffn_w1.out_f, nullptr, 0, mode, st));
+    FA_RETURN_IF_ERR(layernorm_launch(hq, Mq, L.ffn_norm, nullptr, nullptr, 1.f, 1, st, hq_planes, npl, L.ffn_w1.out_f));
+    return gemm_tc_planes_launch(hq_planes, Mq, L.ffn_w2, 0, nullptr, 0, nullptr, 0, f, 512, nullptr, 0, mode, st);
+  }
   FA_RETURN_IF_ERR(layernorm_launch(y, Mq, L.norm1, t1, nullptr, 1.f, 1, st));
   FA_RETURN_IF_ERR(linear(t1, 512, Mq, L.ffn_w1, 1, nullptr, 0, nullptr, 0, hq, L.ffn_w1.out_f, mode, scratch, st));
   FA_RETURN_IF_ERR(layernorm_launch(hq, Mq, L.ffn_norm, hq, nullptr, 1.f, 1, st));
@@ -231,6 +233,8 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
   const int npl = npl_for(gemm_mode);
   __nv_bfloat16* ctx_planes = tc ? a.take<__nv_bfloat16>(3ull * Mq * 512) : nullptr;
   __nv_bfloat16* enc_planes = tc ? a.take<__nv_bfloat16>(3ull * Mk * 512) : nullptr;
+  __nv_bfloat16* t1_planes = tc ? a.take<__nv_bfloat16>(3ull * Mq * 512) : nullptr;
+  __nv_bfloat16* hq_planes = tc ? a.take<__nv_bfloat16>(3ull * Mq * 2048) : nullptr;
   const size_t sb = dec_scratch_bytes(batch, t_max, n_max, gemm_mode);
   char* sp = a.take<char>(sb);
   if (!a.ok()) return FA_ERR_WORKSPACE;
@@ -245,14 +249,19 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
   float* y = ya;
   for (int l = 0; l < dec->n_layers; ++l) {
     const FaDecLayer& L = dec->layers[l];
-    FA_RETURN_IF_ERR(dec_ffn(L, y, Mq, t1, hq, f, gemm_mode, &scratch, st));
+    FA_RETURN_IF_ERR(dec_ffn(L, y, Mq, t1, hq, f, gemm_mode, &scratch, st, t1_planes, hq_planes));
     // x = residual + fsmn(LN2(f), tgt_mask)     decoder.py:103-107
     FA_RETURN_IF_ERR(layernorm_launch(f, Mq, L.norm2, t1, nullptr, 1.f, 1, st));
     float* x2 = (y == ya) ? yb : ya;
     FA_RETURN_IF_ERR(fsmn_launch(t1, D, tok_lens, batch, n_max, D, L.fsmn_w, dec->fsmn_k, y, D, x2, D, st));
     // x = residual + src_attn(LN3(x), memory)    decoder.py:109-118, attention.py:796-813
-    FA_RETURN_IF_ERR(layernorm_launch(x2, Mq, L.norm3, t1, nullptr, 1.f, 1, st));
-    FA_RETURN_IF_ERR(linear(t1, D, Mq, L.q, 0, nullptr, 0, nullptr, 0, qd, D, gemm_mode, &scratch, st));
+    if (tc) {
+      FA_RETURN_IF_ERR(layernorm_launch(x2, Mq, L.norm3, nullptr, nullptr, 1.f, 1, st, t1_planes, npl, D));
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(t1_planes, Mq, L.q, 0, nullptr, 0, nullptr, 0, qd, D, nullptr, 0, gemm_mode, st));
+    } else {
+      FA_RETURN_IF_ERR(layernorm_launch(x2, Mq, L.norm3, t1, nullptr, 1.f, 1, st));
+      FA_RETURN_IF_ERR(linear(t1, D, Mq, L.q, 0, nullptr, 0, nullptr, 0, qd, D, gemm_mode, &scratch, st));
+    }
     float* y2 = (x2 == ya) ? yb : ya;
     if (!tc) {
       FA_RETURN_IF_ERR(linear(enc, D, Mk, L.kv, 0, nullptr, 0, nullptr, 0, kv, 2 * D, gemm_mode, &scratch, st));
@@ -268,10 +277,45 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
     y = y2;
   }
   // decoders3: FFN only, no residual (decoder.py:97-102,121); after_norm; output_layer
-  FA_RETURN_IF_ERR(dec_ffn(dec->last, y, Mq, t1, hq, f, gemm_mode, &scratch, st));
-  FA_RETURN_IF_ERR(layernorm_launch(f, Mq, dec->after_norm, t1, nullptr, 1.f, 1, st));
-  FA_RETURN_IF_ERR(linear(t1, D, Mq, dec->output, 0, nullptr, 0, nullptr, 0, lg, V, gemm_mode, &scratch, st));
+  FA_RETURN_IF_ERR(dec_ffn(dec->last, y, Mq, t1, hq, f, gemm_mode, &scratch, st, t1_planes, hq_planes));
+  if (tc) {
+    FA_RETURN_IF_ERR(layernorm_launch(f, Mq, dec->after_norm, nullptr, nullptr, 1.f, 1, st, t1_planes, npl, D));
+    FA_RETURN_IF_ERR(gemm_tc_planes_launch(t1_planes, Mq, dec->output, 0, nullptr, 0, nullptr, 0, lg, V, nullptr, 0, gemm_mode, st));
+  } else {
+    FA_RETURN_IF_ERR(layernorm_launch(f, Mq, dec->after_norm, t1, nullptr, 1.f, 1, st));
+    FA_RETURN_IF_ERR(linear(t1, D, Mq, dec->output, 0, nullptr, 0, nullptr, 0, lg, V, gemm_mode, &scratch, st));
+  }
   return argmax_lse_launch(lg, Mq, V, V, argmax_ids, argmax_logp, (logits && log_softmax) ? 1 : 0, st);
+}
+
+// ------------------------------------------------------------------------------------------ CTC greedy head
+extern "C" size_t fa_ctc_greedy_workspace_bytes(int32_t batch, int32_t t_max, int32_t vocab, int32_t gemm_mode) {
+  const int64_t M = (int64_t)batch * t_max;
+  ArenaSizer s;
+  s.take(M * (size_t)vocab * 4);
+  s.take(M * 4ull);
+  s.take(gemm_tc_scratch_bytes(M, 512, gemm_mode));
+  return s.off + 256;
+}
+
+extern "C" int fa_ctc_greedy_forward(const FaLinear* ctc_lo, const float* enc, const int32_t* lens, int32_t batch,
+                                     int32_t t_max, int32_t blank, int32_t* argmax_ids, int32_t* out_ids, int32_t* out_lens,
+                                     float* logp, int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream) {
+  if (!ctc_lo || !enc || !lens || !argmax_ids || !out_ids || !out_lens || batch <= 0 || t_max <= 0) return FA_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = (int64_t)batch * t_max;
+  const int V = ctc_lo->out_f;
+  Arena a(workspace, ws_bytes);
+  float* lg = a.take<float>(M * (size_t)V);
+  float* best = a.take<float>(M);
+  const size_t sb = gemm_tc_scratch_bytes(M, 512, gemm_mode);
+  char* sp = a.take<char>(sb);
+  if (!a.ok()) return FA_ERR_WORKSPACE;
+  Arena scratch(sp, sb);
+  if (logp) lg = logp;
+  FA_RETURN_IF_ERR(linear(enc, ctc_lo->in_f, M, *ctc_lo, 0, nullptr, 0, nullptr, 0, lg, V, gemm_mode, &scratch, st));
+  FA_RETURN_IF_ERR(argmax_lse_launch(lg, M, V, V, argmax_ids, best, logp ? 1 : 0, st));
+  return ctc_filter_launch(argmax_ids, lens, batch, t_max, blank, out_ids, out_lens, st);
 }
 
 // ------------------------------------------------------------------------------------------ op-level + info

@@ -67,49 +67,87 @@ class FrontendEngine:
         return feats, flens
 
 
-class ParaformerEngine:
-    """Packed weights + workspace + the encoder/predictor/decoder ABI calls."""
+class _EngineBase:
+    """Weight packing (device copies, bf16 planes, ctypes structs), workspace and the encoder call."""
 
-    def __init__(self, state: Dict[str, torch.Tensor], cfg: ParaformerConfig, device, gemm_mode: str = "fp32",
-                 prefix_enc="encoder.", prefix_pred="predictor.", prefix_dec="decoder."):
+    def _init_base(self, state, device, gemm_mode, ln_eps):
         self.lib = _abi.load()
-        self.cfg = cfg
         self.device = torch.device(device)
         self.mode = _abi.GEMM_MODES[gemm_mode] if isinstance(gemm_mode, str) else int(gemm_mode)
         self._keep: List[torch.Tensor] = []   # keeps every packed tensor alive
         self._ws: Optional[torch.Tensor] = None
-        g = lambda k: self._dev(state[k])
+        self._state = state
+        self._eps = ln_eps
+
+    def _g(self, k):
+        return self._dev(self._state[k])
+
+    def _lin(self, prefix, bias=True, weight=None) -> _abi.FaLinear:
+        w = self._dev(self._state[prefix + ".weight"]) if weight is None else weight
+        b = self._dev(self._state[prefix + ".bias"]) if bias else None
+        out_f, in_f = w.shape
+        in_pad = (in_f + 63) // 64 * 64
+        planes = None
+        if self.mode != _abi.GEMM_F32_SIMT:
+            planes = torch.empty((3, out_f, in_pad), dtype=torch.bfloat16, device=self.device)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _abi.check(self.lib.fa_split_bf16(w.data_ptr(), in_f, out_f, in_f, in_pad, planes.data_ptr(), st), "fa_split_bf16")
+            self._keep.append(planes)
+        return _abi.FaLinear(w.data_ptr(), _ptr(b), _ptr(planes), out_f, in_f, in_pad, 0)
+
+    def _norm(self, prefix) -> _abi.FaNorm:
+        w, b = self._g(prefix + ".weight"), self._g(prefix + ".bias")
+        return _abi.FaNorm(w.data_ptr(), b.data_ptr(), w.numel(), self._eps)
+
+    def _enc_stack(self, layer_prefixes, after_norm_prefix, heads, fsmn_k, pe_depth):
+        """FaEncoder over the given layer name prefixes; pe_depth None -> plain 512->512 stack (no x*sqrt(d)+PE)."""
+        layers = (_abi.FaEncLayer * len(layer_prefixes))()
+        for L, p in zip(layers, layer_prefixes):
+            L.norm1, L.norm2 = self._norm(p + ".norm1"), self._norm(p + ".norm2")
+            L.qkv, L.out = self._lin(p + ".self_attn.linear_q_k_v"), self._lin(p + ".self_attn.linear_out")
+            L.fsmn_w = self._g(p + ".self_attn.fsmn_block.weight").data_ptr()     # [512,1,11] contiguous == [512,11]
+            L.w1, L.w2 = self._lin(p + ".feed_forward.w_1"), self._lin(p + ".feed_forward.w_2")
+        pe = self._dev(sinusoid_inv_timescales(pe_depth)) if pe_depth else None
+        enc = _abi.FaEncoder(layers, len(layer_prefixes), heads, fsmn_k, 0, self._norm(after_norm_prefix), _ptr(pe))
+        self._keep_structs = getattr(self, "_keep_structs", []) + [layers]
+        return enc
+
+    def _dev(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.detach().to(self.device, torch.float32).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty((int(nbytes * 1.1) + 4096,), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _encode(self, enc_struct, x: torch.Tensor, lens: torch.Tensor, d_model: int) -> torch.Tensor:
+        B, T, _ = x.shape
+        out = torch.empty((B, T, d_model), dtype=torch.float32, device=self.device)
+        ws = self._workspace(self.lib.fa_sanm_encoder_workspace_bytes(B, T, self.mode))
+        _abi.check(self.lib.fa_sanm_encoder_forward(C.byref(enc_struct), x.data_ptr(), lens.data_ptr(), B, T, out.data_ptr(),
+                                                    self.mode, ws.data_ptr(), ws.numel(), self._stream()), "fa_sanm_encoder_forward")
+        return out
+
+
+class ParaformerEngine(_EngineBase):
+    """Packed weights + workspace + the encoder/predictor/decoder ABI calls."""
+
+    def __init__(self, state: Dict[str, torch.Tensor], cfg: ParaformerConfig, device, gemm_mode: str = "fp32",
+                 prefix_enc="encoder.", prefix_pred="predictor.", prefix_dec="decoder."):
+        self._init_base(state, device, gemm_mode, cfg.ln_eps)
+        self.cfg = cfg
+        g, lin, norm = self._g, self._lin, self._norm
         D, K = cfg.d_model, cfg.kernel
-
-        def lin(prefix, bias=True, weight=None) -> _abi.FaLinear:
-            w = self._dev(state[prefix + ".weight"]) if weight is None else weight
-            b = self._dev(state[prefix + ".bias"]) if bias else None
-            out_f, in_f = w.shape
-            in_pad = (in_f + 63) // 64 * 64
-            planes = None
-            if self.mode != _abi.GEMM_F32_SIMT:
-                planes = torch.empty((3, out_f, in_pad), dtype=torch.bfloat16, device=self.device)
-                st = torch.cuda.current_stream(self.device).cuda_stream
-                _abi.check(self.lib.fa_split_bf16(w.data_ptr(), in_f, out_f, in_f, in_pad, planes.data_ptr(), st), "fa_split_bf16")
-                self._keep.append(planes)
-            return _abi.FaLinear(w.data_ptr(), _ptr(b), _ptr(planes), out_f, in_f, in_pad, 0)
-
-        def norm(prefix) -> _abi.FaNorm:
-            w, b = g(prefix + ".weight"), g(prefix + ".bias")
-            return _abi.FaNorm(w.data_ptr(), b.data_ptr(), w.numel(), cfg.ln_eps)
-
         # ---- encoder
-        self.enc_layers = (_abi.FaEncLayer * cfg.enc_layers)()
-        for i in range(cfg.enc_layers):
-            p = prefix_enc + ("encoders0.0" if i == 0 else "encoders.%d" % (i - 1))
-            L = self.enc_layers[i]
-            L.norm1, L.norm2 = norm(p + ".norm1"), norm(p + ".norm2")
-            L.qkv, L.out = lin(p + ".self_attn.linear_q_k_v"), lin(p + ".self_attn.linear_out")
-            L.fsmn_w = g(p + ".self_attn.fsmn_block.weight").data_ptr()     # [512,1,11] contiguous == [512,11]
-            L.w1, L.w2 = lin(p + ".feed_forward.w_1"), lin(p + ".feed_forward.w_2")
-        self.pe_inv = self._dev(sinusoid_inv_timescales(cfg.feat_dim))
-        self.enc = _abi.FaEncoder(self.enc_layers, cfg.enc_layers, cfg.heads, K, 0, norm(prefix_enc + "after_norm"),
-                                  self.pe_inv.data_ptr())
+        names = [prefix_enc + ("encoders0.0" if i == 0 else "encoders.%d" % (i - 1)) for i in range(cfg.enc_layers)]
+        self.enc = self._enc_stack(names, prefix_enc + "after_norm", cfg.heads, K, cfg.feat_dim)
+        self.enc_layers = self._keep_structs[-1]
         # ---- predictor: Conv1d(512,512,3) weight [out, in, k] -> GEMM weight [out, k*512 + in]
         cw = state[prefix_pred + "cif_conv1d.weight"]
         cw = self._dev(cw.permute(0, 2, 1).reshape(cw.shape[0], -1))
@@ -137,30 +175,12 @@ class ParaformerEngine:
         self.dec.after_norm = norm(prefix_dec + "after_norm")
         self.dec.output = lin(prefix_dec + "output_layer")
         torch.cuda.current_stream(self.device).synchronize()
+        self._state = None
 
     # ------------------------------------------------------------------------------------------
-    def _dev(self, t: torch.Tensor) -> torch.Tensor:
-        t = t.detach().to(self.device, torch.float32).contiguous()
-        self._keep.append(t)
-        return t
-
-    def _workspace(self, nbytes: int) -> torch.Tensor:
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
-            self._ws = torch.empty((int(nbytes * 1.1) + 4096,), dtype=torch.uint8, device=self.device)
-        return self._ws
-
-    def _stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
-
     def encode(self, feats: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
         """SANMEncoder.forward: feats [B,T,560], lens [B] int32 -> [B,T,512]."""
-        B, T, _ = feats.shape
-        out = torch.empty((B, T, self.cfg.d_model), dtype=torch.float32, device=self.device)
-        ws = self._workspace(self.lib.fa_sanm_encoder_workspace_bytes(B, T, self.mode))
-        _abi.check(self.lib.fa_sanm_encoder_forward(C.byref(self.enc), feats.data_ptr(), lens.data_ptr(), B, T, out.data_ptr(),
-                                                    self.mode, ws.data_ptr(), ws.numel(), self._stream()), "fa_sanm_encoder_forward")
-        return out
+        return self._encode(self.enc, feats, lens, self.cfg.d_model)
 
     def predict(self, enc: torch.Tensor, lens: torch.Tensor):
         """CifPredictorV2.forward -> (acoustic [B,T+1,512] zero padded, token_num [B] i32, alphas [B,T+1], peaks [B,T+1])."""
@@ -216,4 +236,64 @@ class ParaformerEngine:
         out["ids_padded"], out["ids_lens"] = fids_h, flens_h
         if want_taps:
             out.update(argmax=ids, best_logp=best, logp=logp)
+        return out
+
+
+class SenseVoiceEngine(_EngineBase):
+    """SenseVoiceSmall (BASELINE config 4): 4 query frames + fused frontend -> 50 SAN-M blocks -> after_norm -> 20 tp
+    blocks -> tp_norm -> CTC greedy (funasr/models/sense_voice/model.py:623-656, :918-1034)."""
+
+    def __init__(self, state: Dict[str, torch.Tensor], cfg, device, gemm_mode: str = "fp32", cmvn: Optional[torch.Tensor] = None):
+        self._init_base(state, device, gemm_mode, cfg.ln_eps)
+        self.cfg = cfg
+        names = ["encoder." + ("encoders0.0" if i == 0 else "encoders.%d" % (i - 1)) for i in range(cfg.enc_layers)]
+        self.enc = self._enc_stack(names, "encoder.after_norm", cfg.heads, cfg.kernel, cfg.feat_dim)
+        self.tp = self._enc_stack(["encoder.tp_encoders.%d" % i for i in range(cfg.tp_layers)], "encoder.tp_norm", cfg.heads,
+                                  cfg.kernel, None) if cfg.tp_layers > 0 else None
+        self.ctc = self._lin("ctc.ctc_lo")
+        self.embed = self._g("embed.weight")
+        self.frontend = FrontendEngine(cmvn, device)
+        self._queries = {}
+        torch.cuda.current_stream(self.device).synchronize()
+        self._state = None
+
+    def query_rows(self, language_id: int, textnorm_id: int) -> torch.Tensor:
+        """[language, event(1), emo(2), textnorm] embedding rows (model.py:971-995); built once per combination."""
+        key = (language_id, textnorm_id)
+        if key not in self._queries:
+            idx = torch.tensor([language_id, 1, 2, textnorm_id], device=self.device)
+            self._queries[key] = self.embed.index_select(0, idx).contiguous()
+        return self._queries[key]
+
+    def forward_wav(self, wav: torch.Tensor, wav_lens: torch.Tensor, host_lens: Sequence[int], language_id: int = 0,
+                    textnorm_id: int = 15, blank: int = 0, want_taps: bool = False):
+        """wav [B, Nmax] fp32 on device -> CTC greedy ids.  No host synchronisation before the final D2H."""
+        B = wav.shape[0]
+        t_feat = max(num_lfr_frames(int(n)) for n in host_lens)
+        T = t_feat + 4
+        x = torch.empty((B, T, self.cfg.feat_dim), dtype=torch.float32, device=self.device)
+        flens = torch.empty((B,), dtype=torch.int32, device=self.device)
+        fe = self.frontend
+        _abi.check(self.lib.fa_fbank_lfr_cmvn_strided(wav.data_ptr(), wav_lens.data_ptr(), B, wav.stride(0), _ptr(fe.cmvn), fe.mel.data_ptr(),
+                                                      fe.window.data_ptr(), x.data_ptr() + 4 * self.cfg.feat_dim * 4, T, flens.data_ptr(),
+                                                      t_feat, self._stream()), "fa_fbank_lfr_cmvn_strided")
+        q = self.query_rows(language_id, textnorm_id)
+        _abi.check(self.lib.fa_broadcast_rows(q.data_ptr(), 4, self.cfg.feat_dim, x.data_ptr(), T, B, self._stream()), "fa_broadcast_rows")
+        lens = torch.tensor([num_lfr_frames(int(n)) + 4 for n in host_lens], dtype=torch.int32).to(self.device, non_blocking=True)
+        enc = self._encode(self.enc, x, lens, self.cfg.d_model)
+        if self.tp is not None:
+            enc = self._encode(self.tp, enc, lens, self.cfg.d_model)
+        V = self.cfg.vocab
+        am = torch.empty((B, T), dtype=torch.int32, device=self.device)
+        ids = torch.empty((B, T), dtype=torch.int32, device=self.device)
+        olens = torch.empty((B,), dtype=torch.int32, device=self.device)
+        logp = torch.empty((B, T, V), dtype=torch.float32, device=self.device) if want_taps else None
+        ws = self._workspace(self.lib.fa_ctc_greedy_workspace_bytes(B, T, V, self.mode))
+        _abi.check(self.lib.fa_ctc_greedy_forward(C.byref(self.ctc), enc.data_ptr(), lens.data_ptr(), B, T, blank, am.data_ptr(), ids.data_ptr(),
+                                                  olens.data_ptr(), _ptr(logp), self.mode, ws.data_ptr(), ws.numel(), self._stream()),
+                   "fa_ctc_greedy_forward")
+        ids_h, olens_h = ids.cpu(), olens.cpu()
+        out = {"ids": [ids_h[b, : int(olens_h[b])].tolist() for b in range(B)], "enc_lens": lens}
+        if want_taps:
+            out.update(enc=enc, logp=logp, argmax=am)
         return out

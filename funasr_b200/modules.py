@@ -23,9 +23,9 @@ import torch
 import torch.nn as nn
 
 from . import _abi
-from .engine import FrontendEngine, ParaformerEngine, num_lfr_frames
+from .engine import FrontendEngine, ParaformerEngine, SenseVoiceEngine, num_lfr_frames
 from .registry import get_tables, register
-from .synth import ParaformerConfig
+from .synth import ParaformerConfig, SenseVoiceConfig
 
 
 class _Container(nn.Module):
@@ -363,4 +363,110 @@ class ParaformerB200(nn.Module):
                 results.append({"key": key[i], "text": text})
             else:
                 results.append({"key": key[i], "token_int": token_int})
+        return results, meta_data
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SenseVoiceSmall (BASELINE config 4)
+# ------------------------------------------------------------------------------------------------------------------
+@register("encoder_classes", "SenseVoiceEncoderSmallB200")
+class SenseVoiceEncoderSmallB200(SANMEncoderB200):
+    """Parameter container for SenseVoiceEncoderSmall (funasr/models/sense_voice/model.py:489-656): the SANMEncoder
+    layout plus `tp_encoders.{i}` and `tp_norm`."""
+
+    def __init__(self, input_size: int, tp_blocks: int = 0, **kwargs):
+        self.tp_blocks = tp_blocks
+        super().__init__(input_size=input_size, **kwargs)
+
+    def _specs(self):
+        s = super()._specs()
+        D = self._output_size
+        proto = {k[len("encoders.0"):]: v for k, v in s.items() if k.startswith("encoders.0.")} if self.num_blocks > 1 else None
+        if proto is None:
+            proto = {k[len("encoders0.0"):]: (v if "norm1" not in k and "linear_q_k_v.weight" not in k else
+                                               ((D,) if "norm1" in k else (3 * D, D))) for k, v in s.items() if k.startswith("encoders0.0.")}
+        for i in range(self.tp_blocks):
+            for suffix, shape in proto.items():
+                s["tp_encoders.%d%s" % (i, suffix)] = shape
+        s["tp_norm.weight"] = (D,)
+        s["tp_norm.bias"] = (D,)
+        return s
+
+
+class _CTCHolder(_ParamHolder):
+    def __init__(self, odim, eprojs):
+        super().__init__()
+        self.odim, self.eprojs = odim, eprojs
+        self._build()
+
+    def _specs(self):
+        return {"ctc_lo.weight": (self.odim, self.eprojs), "ctc_lo.bias": (self.odim,)}
+
+
+@register("model_classes", "SenseVoiceSmallB200")
+class SenseVoiceSmallB200(nn.Module):
+    """Drop-in for SenseVoiceSmall's greedy CTC inference (funasr/models/sense_voice/model.py:659-1034)."""
+
+    lid_dict = {"auto": 0, "zh": 3, "en": 4, "yue": 7, "ja": 11, "ko": 12, "nospeech": 13}
+    textnorm_dict = {"withitn": 14, "woitn": 15}
+
+    def __init__(self, encoder: str = None, encoder_conf: dict = None, ctc_conf: dict = None, input_size: int = 80,
+                 vocab_size: int = -1, blank_id: int = 0, gemm_mode: str = "fp32", **kwargs):
+        super().__init__()
+        tables = get_tables()
+        enc_cls = tables.encoder_classes.get(encoder) if isinstance(encoder, str) else encoder
+        if enc_cls is None or not issubclass(enc_cls, _ParamHolder):
+            enc_cls = SenseVoiceEncoderSmallB200
+        self.encoder = enc_cls(input_size=input_size, **(encoder_conf or {}))
+        self.ctc = _CTCHolder(vocab_size, self.encoder.output_size())
+        self.embed = nn.Embedding(7 + len(self.lid_dict) + len(self.textnorm_dict), input_size)   # parameter container only
+        self.embed.weight.requires_grad_(False)
+        self.vocab_size, self.blank_id, self.gemm_mode = vocab_size, blank_id, gemm_mode
+        self.cfg = SenseVoiceConfig(enc_layers=self.encoder.num_blocks, tp_layers=self.encoder.tp_blocks, vocab=vocab_size,
+                                    kernel=self.encoder.kernel_size)
+        self._engine = None
+
+    def on_pretrained_model_loaded(self, loaded_keys=None):
+        self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def engine(self, device, cmvn) -> SenseVoiceEngine:
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _abi.FunasrB200Error("SenseVoiceSmallB200 needs a CUDA device; there is no CPU path")
+        if self._engine is None or self._engine.device != dev:
+            self._engine = SenseVoiceEngine(self.state_dict(), self.cfg, dev, gemm_mode=self.gemm_mode, cmvn=cmvn)
+        return self._engine
+
+    def inference(self, data_in, data_lengths=None, key: list = ["wav_file_tmp_name"], tokenizer=None, frontend=None, **kwargs):
+        device = torch.device(kwargs.get("device", "cuda"))
+        if not isinstance(frontend, WavFrontendB200):
+            raise _abi.FunasrB200Error("SenseVoiceSmallB200 needs frontend='WavFrontendB200'")
+        eng = self.engine(device, frontend.cmvn)
+        meta_data = {}
+        wavs = _as_wave_list(data_in, fs=frontend.fs, **kwargs)
+        wl = [int(w.numel()) for w in wavs]
+        if min(wl) < 400:
+            raise _abi.FunasrB200Error("utterances shorter than one 25 ms frame (400 samples) are not supported")
+        nmax = max(wl)
+        wav_dev = (torch.zeros if min(wl) != nmax else torch.empty)((len(wavs), nmax), dtype=torch.float32, device=device)
+        for i, w in enumerate(wavs):
+            wav_dev[i, : wl[i]].copy_(w, non_blocking=True)
+        wl_dev = torch.tensor(wl, dtype=torch.int32).to(device, non_blocking=True)
+        meta_data["batch_data_time"] = sum(num_lfr_frames(n) for n in wl) * frontend.frame_shift * frontend.lfr_n / 1000
+        language = kwargs.get("language", "auto")
+        textnorm = kwargs.get("text_norm", None) or ("withitn" if kwargs.get("use_itn", False) else "woitn")
+        out = eng.forward_wav(wav_dev, wl_dev, wl, self.lid_dict.get(language, 0), self.textnorm_dict[textnorm], self.blank_id)
+        b = len(wavs)
+        if isinstance(key[0], (list, tuple)):
+            key = key[0]
+        if len(key) < b:
+            key = key * b
+        results = []
+        for i in range(b):
+            ids = out["ids"][i]
+            results.append({"key": key[i], "text": tokenizer.decode(ids)} if tokenizer is not None else {"key": key[i], "token_int": ids})
         return results, meta_data

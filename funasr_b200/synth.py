@@ -116,6 +116,70 @@ def make_state_dict(cfg: ParaformerConfig = PARAFORMER_LARGE, seed: int = 0) -> 
     return sd
 
 
+@dataclass(frozen=True)
+class SenseVoiceConfig:
+    """SenseVoiceSmall (funasr/models/sense_voice/model.py:489-1034; runtime/triton_gpu/.../config.yaml): the same SAN-M
+    encoder (50 blocks) + 20 "tp" blocks, LayerNorm eps 1e-5, CTC head over 25055 tokens, 4 prepended query frames."""
+    n_mels: int = 80
+    lfr_m: int = 7
+    lfr_n: int = 6
+    d_model: int = 512
+    heads: int = 4
+    ffn: int = 2048
+    enc_layers: int = 50
+    tp_layers: int = 20
+    kernel: int = 11
+    vocab: int = 25055
+    n_embed: int = 16          # 7 + len(lid_dict) + len(textnorm_dict), model.py:735
+    ln_eps: float = 1e-5       # torch.nn.LayerNorm default, model.py:300-322
+
+    @property
+    def feat_dim(self) -> int:
+        return self.n_mels * self.lfr_m
+
+
+SENSEVOICE_SMALL = SenseVoiceConfig()
+SENSEVOICE_TINY = SenseVoiceConfig(enc_layers=3, tp_layers=2, vocab=1200)
+
+
+def make_sensevoice_state_dict(cfg: SenseVoiceConfig = SENSEVOICE_SMALL, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Synthetic SenseVoiceSmall weights under the reference's names (encoder.*, ctc.ctc_lo.*, embed.weight)."""
+    g = torch.Generator().manual_seed(1000003 * seed + 29)
+    D, F, V, K, Din = cfg.d_model, cfg.ffn, cfg.vocab, cfg.kernel, cfg.feat_dim
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+
+    def linear(prefix, out_f, in_f, gain=1.0):
+        sd[prefix + ".weight"] = _randn(g, out_f, in_f, std=gain / math.sqrt(in_f))
+        sd[prefix + ".bias"] = _randn(g, out_f, std=0.02)
+
+    def norm(prefix, n):
+        sd[prefix + ".weight"] = 1.0 + _randn(g, n, std=0.1)
+        sd[prefix + ".bias"] = _randn(g, n, std=0.05)
+
+    def enc_layer(prefix, in_size):
+        res = 0.7 if in_size != D else 0.3
+        linear(prefix + ".self_attn.linear_out", D, D, gain=res)
+        linear(prefix + ".self_attn.linear_q_k_v", 3 * D, in_size, gain=1.5)
+        sd[prefix + ".self_attn.linear_q_k_v.weight"][: 2 * D] *= 1.5
+        sd[prefix + ".self_attn.fsmn_block.weight"] = _randn(g, D, 1, K, std=0.15)
+        linear(prefix + ".feed_forward.w_1", F, D)
+        linear(prefix + ".feed_forward.w_2", D, F, gain=res)
+        norm(prefix + ".norm1", in_size)
+        norm(prefix + ".norm2", D)
+
+    enc_layer("encoder.encoders0.0", Din)
+    for i in range(cfg.enc_layers - 1):
+        enc_layer("encoder.encoders.%d" % i, D)
+    for i in range(cfg.tp_layers):
+        enc_layer("encoder.tp_encoders.%d" % i, D)
+    norm("encoder.after_norm", D)
+    norm("encoder.tp_norm", D)
+    linear("ctc.ctc_lo", V, D, gain=3.0)
+    sd["ctc.ctc_lo.bias"][0] += 2.0       # CTC blank gets a head start so that blanks / repeats actually occur
+    sd["embed.weight"] = _randn(g, cfg.n_embed, Din, std=1.0)
+    return sd
+
+
 def make_cmvn(cfg: ParaformerConfig = PARAFORMER_LARGE, seed: int = 0) -> torch.Tensor:
     """A plausible [2, 560] (shift, scale) pair.  Log-mel energies of 16-bit-scaled synthetic audio sit
     near 13 (low bins) .. 21 (high bins) with unit-ish spread, so shift ~ -(that), scale ~ 1."""

@@ -137,6 +137,15 @@ const char* fa_status_string(int status);
 int fa_fbank_lfr_cmvn(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride,
                       const float* cmvn, const float* mel_banks, const float* window,
                       float* feats, int32_t* feat_lens, int32_t t_max, fa_stream_t stream);
+/* Same, writing utterance b at feats + b * feats_batch_stride_rows * 560 (t_max rows each): lets the caller leave room
+ * for prepended frames, e.g. SenseVoiceSmall's 4 query frames (funasr/models/sense_voice/model.py:971-995). */
+int fa_fbank_lfr_cmvn_strided(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride,
+                              const float* cmvn, const float* mel_banks, const float* window, float* feats,
+                              int64_t feats_batch_stride_rows, int32_t* feat_lens, int32_t t_max, fa_stream_t stream);
+/* dst[b, r, :] = rows[r, :] for r < n_rows (dst rows of `cols` floats, utterances dst_batch_stride_rows apart):
+ * the query-frame prepend `torch.cat((input_query, speech), dim=1)` of sense_voice/model.py:985-995. */
+int fa_broadcast_rows(const float* rows, int32_t n_rows, int32_t cols, float* dst, int64_t dst_batch_stride_rows,
+                      int32_t batch, fa_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Operator-level entry points (each is used by the model-level calls below and exposed for parity tests)
@@ -177,7 +186,10 @@ int fa_attention_tc(const float* q, int64_t ldq, const float* k, int64_t ldk, co
 /* ---------------------------------------------------------------------------------------------
  * Model-level entry points
  * ------------------------------------------------------------------------------------------- */
-/* SANMEncoder.forward (encoder.py:392-461): feats [B,T,560], lens[B] -> enc [B,T,512]. */
+/* SANMEncoder.forward (encoder.py:392-461): feats [B,T,560], lens[B] -> enc [B,T,512].
+ * If enc->pe_inv_timescales == NULL the struct describes a plain stack of 512->512 SAN-M layers applied to an
+ * existing [B,T,512] stream (no x*sqrt(d)+PE, every layer has its residual): SenseVoiceEncoderSmall's `tp_encoders`
+ * + `tp_norm` (sense_voice/model.py:650-655). */
 size_t fa_sanm_encoder_workspace_bytes(int32_t batch, int32_t t_max, int32_t gemm_mode);
 int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats, const int32_t* lens, int32_t batch,
                             int32_t t_max, float* out, int32_t gemm_mode, void* workspace, size_t ws_bytes,
@@ -212,6 +224,15 @@ int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* enc, const 
 int fa_greedy_filter(const int32_t* argmax_ids, const int32_t* tok_lens, int32_t batch, int32_t n_max,
                      int32_t sos, int32_t eos, int32_t blank, int32_t* out_ids, int32_t* out_lens,
                      fa_stream_t stream);
+
+/* CTC greedy head of SenseVoiceSmall (sense_voice/model.py:1003-1025, ctc/ctc.py:192-203): logits = enc W^T + b,
+ * log_softmax, arg-max per frame, torch.unique_consecutive, drop blank.
+ *   enc [B,T,512], lens[B] -> out_ids [B,T] (padded with -1), out_lens [B]; if logp != NULL it receives the
+ *   full log_softmax [B,T,vocab] (parity checks); argmax_ids [B,T] is scratch/diagnostic output. */
+size_t fa_ctc_greedy_workspace_bytes(int32_t batch, int32_t t_max, int32_t vocab, int32_t gemm_mode);
+int fa_ctc_greedy_forward(const FaLinear* ctc_lo, const float* enc, const int32_t* lens, int32_t batch, int32_t t_max,
+                          int32_t blank, int32_t* argmax_ids, int32_t* out_ids, int32_t* out_lens, float* logp,
+                          int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream);
 
 /* Split fp32 [rows, cols] into three bf16 planes [3][rows][cols_pad] (hi, mid, lo; zero padded columns):
  * weight repack for the tcgen05 GEMM path (called once per weight after load_pretrained_model). */

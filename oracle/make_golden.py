@@ -124,5 +124,71 @@ def main():
     write_cmvn_file(os.path.join(GOLD, "am_synth.mvn"), synth.make_cmvn(synth.PARAFORMER_LARGE, seed=1))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "sensevoice"):
     main()
+
+
+# ------------------------------------------------------------------------------------------------ SenseVoiceSmall
+SV_CASES = {
+    "sv_tiny_ragged3": (synth.SENSEVOICE_TINY, 4, [(48000, 11, "speechlike"), (27200, 12, "noise"), (38437, 13, "speechlike")], True),
+    "sv_large_single": (synth.SENSEVOICE_SMALL, 1, [(160000, 14, "speechlike")], True),
+}
+
+
+def run_sv_case(name, cfg, wseed, wav_specs, use_cmvn, tmp):
+    from funasr import AutoModel
+    cmvn_file = os.path.join(tmp, "am_%s.mvn" % name)
+    write_cmvn_file(cmvn_file, synth.make_cmvn(synth.PARAFORMER_LARGE, seed=1))
+    pt = os.path.join(tmp, "sv_%s.pt" % name)
+    torch.save(synth.make_sensevoice_state_dict(cfg, wseed), pt)
+    tokens = ["<blank>"] + ["t%d" % i for i in range(cfg.vocab - 2)] + ["<unk>"]
+    am = AutoModel(
+        model="SenseVoiceSmall", model_conf=dict(length_normalized_loss=True, sos=1, eos=2, ignore_id=-1),
+        encoder="SenseVoiceEncoderSmall",
+        encoder_conf=dict(output_size=cfg.d_model, attention_heads=cfg.heads, linear_units=cfg.ffn, num_blocks=cfg.enc_layers,
+                          tp_blocks=cfg.tp_layers, dropout_rate=0.1, positional_dropout_rate=0.1, attention_dropout_rate=0.1,
+                          input_layer="pe", pos_enc_class="SinusoidalPositionEncoder", normalize_before=True, kernel_size=cfg.kernel,
+                          sanm_shfit=0, selfattention_layer_type="sanm"),
+        frontend="WavFrontend",
+        frontend_conf=dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0,
+                           cmvn_file=cmvn_file),
+        tokenizer="CharTokenizer", tokenizer_conf=dict(token_list=tokens, unk_symbol="<unk>", split_with_space=True),
+        device="cpu", ncpu=os.cpu_count(), disable_update=True, disable_pbar=True, init_param=pt,
+    )
+    model, frontend = am.model, am.kwargs["frontend"]
+
+    class Tok:      # SenseVoiceSmall.inference needs tokenizer.decode(token_int) (model.py:1027); record the ids verbatim
+        def decode(self, ids):
+            return " ".join(str(int(i)) for i in ids)
+
+    wavs = [synth.make_wav(n, s, k) for (n, s, k) in wav_specs]
+    with torch.no_grad():
+        res, meta = model.inference(data_in=[w.numpy() for w in wavs], key=["u%d" % i for i in range(len(wavs))], tokenizer=Tok(),
+                                    frontend=frontend, device="cpu", language="auto", use_itn=False)
+        from funasr.utils.load_utils import extract_fbank
+        feats, flens = extract_fbank([w for w in wavs], frontend=frontend)
+        emb = model.embed.weight
+        q = torch.stack([emb[0], emb[1], emb[2], emb[15]])[None].repeat(feats.shape[0], 1, 1)
+        enc, elens = model.encoder(torch.cat([q, feats], dim=1), flens + 4)
+        logp = model.ctc.log_softmax(enc)
+    ids = [[int(t) for t in r["text"].split()] for r in res]
+    step = 7 if cfg.enc_layers > 10 else 1
+    top2 = torch.topk(logp, 2, dim=-1).values
+    rows = sorted(set([0, 1, 4, enc.shape[1] // 2, enc.shape[1] - 1]))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), enc=enc[:, ::step].numpy(), enc_lens=elens.numpy().astype(np.int32),
+                        logp_rows=np.array(rows, dtype=np.int32), logp_sel=logp[:, rows, :].numpy(),
+                        argmax=logp.argmax(-1).numpy().astype(np.int32), margin=(top2[..., 0] - top2[..., 1]).numpy(),
+                        ids_flat=np.array([t for r in ids for t in r], dtype=np.int32), ids_len=np.array([len(r) for r in ids], dtype=np.int32))
+    print("%s: B=%d T=%d ctc tokens=%s min margin %.3e ids[0][:8]=%s" % (name, len(wavs), enc.shape[1], [len(r) for r in ids],
+                                                                       float((top2[..., 0] - top2[..., 1]).min()), ids[0][:8]))
+
+
+def main_sv():
+    ref_shim.import_reference()
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (cfg, wseed, specs, use_cmvn) in SV_CASES.items():
+            run_sv_case(name, cfg, wseed, specs, use_cmvn, tmp)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sensevoice":
+    main_sv()

@@ -325,3 +325,42 @@ def paraformer_forward(wavs: List[Tensor], p: Dict[str, Tensor], cmvn: Optional[
         if taps:
             out.update(taps)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# SenseVoiceSmall (BASELINE config 4): funasr/models/sense_voice/model.py:623-656 (encoder), :918-1034 (inference)
+# --------------------------------------------------------------------------------------
+def sensevoice_encoder(x: Tensor, lens: Tensor, p: Dict[str, Tensor], enc_layers: int, tp_layers: int, heads=4, eps=1e-5):
+    """SenseVoiceEncoderSmall.forward model.py:623-656: x*sqrt(512)+PE, encoders0+encoders, after_norm, tp_encoders, tp_norm."""
+    B, T, Din = x.shape
+    mask = (torch.arange(T)[None, :] < lens[:, None].long())[:, None, :]
+    D = p["encoder.after_norm.weight"].numel()
+    x = x * D ** 0.5
+    x = x + sinusoid_pe(T, Din)
+    x = encoder_layer(x, p, "encoder.encoders0.0.", mask, heads, eps)
+    for i in range(enc_layers - 1):
+        x = encoder_layer(x, p, "encoder.encoders.%d." % i, mask, heads, eps)
+    x = layer_norm(x, p["encoder.after_norm.weight"], p["encoder.after_norm.bias"], eps)
+    for i in range(tp_layers):
+        x = encoder_layer(x, p, "encoder.tp_encoders.%d." % i, mask, heads, eps)
+    x = layer_norm(x, p["encoder.tp_norm.weight"], p["encoder.tp_norm.bias"], eps)
+    return x, mask.squeeze(1).sum(1).to(torch.int32)
+
+
+def sensevoice_forward(wavs: List[Tensor], p: Dict[str, Tensor], cmvn: Optional[Tensor], enc_layers: int, tp_layers: int,
+                       language_id: int = 0, textnorm_id: int = 15, heads: int = 4, eps: float = 1e-5, blank: int = 0):
+    """SenseVoiceSmall.inference model.py:918-1034: frontend -> prepend [language, event(1), emo(2), textnorm] query frames
+    (:971-995) -> encoder -> ctc.log_softmax (:1003) -> argmax -> unique_consecutive -> drop blank (:1015-1025)."""
+    with torch.no_grad():
+        feats, flens = frontend(wavs, cmvn)
+        emb = p["embed.weight"]
+        q = torch.stack([emb[language_id], emb[1], emb[2], emb[textnorm_id]])[None].repeat(feats.shape[0], 1, 1)
+        x = torch.cat([q, feats], dim=1)
+        lens = flens + 4
+        enc, elens = sensevoice_encoder(x, lens, p, enc_layers, tp_layers, heads, eps)
+        logp = torch.log_softmax(F.linear(enc, p["ctc.ctc_lo.weight"], p["ctc.ctc_lo.bias"]), dim=2)
+        ids = []
+        for i in range(enc.shape[0]):
+            y = torch.unique_consecutive(logp[i, : int(elens[i])].argmax(dim=-1), dim=-1)
+            ids.append(y[y != blank].tolist())
+    return {"feats": feats, "feat_lens": flens, "enc": enc, "enc_lens": elens, "logp": logp, "ids": ids}

@@ -62,3 +62,21 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+# SenseVoiceSmall golden cases — must match oracle/make_golden.py:SV_CASES
+SV_CASES = {
+    "sv_tiny_ragged3": ("tiny", 4, [(48000, 11, "speechlike"), (27200, 12, "noise"), (38437, 13, "speechlike")]),
+    "sv_large_single": ("large", 1, [(160000, 14, "speechlike")]),
+}
+
+
+def load_sv_case(name):
+    from funasr_b200 import synth
+    cfg_name, wseed, specs = SV_CASES[name]
+    cfg = synth.SENSEVOICE_TINY if cfg_name == "tiny" else synth.SENSEVOICE_SMALL
+    gold = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    wavs = [synth.make_wav(n, s, k) for (n, s, k) in specs]
+    cmvn = synth.make_cmvn(synth.PARAFORMER_LARGE, seed=1)
+    cmvn = torch.tensor(np.array([[float("%.9g" % v) for v in row] for row in cmvn.tolist()], dtype=np.float32))
+    return cfg, wseed, wavs, cmvn, gold

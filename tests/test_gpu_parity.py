@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, load_case, rel_err, state_dict_for
+from conftest import GOLDEN_CASES, SV_CASES, load_case, load_sv_case, rel_err, state_dict_for
 
 import paraformer_oracle as O
 
@@ -317,3 +317,41 @@ def test_plugin_inference_contract():
     assert [r["key"] for r in res] == ["a", "b", "c"]
     assert [t for r in res for t in r["token_int"]] == g["ids_flat"].tolist()
     assert abs(meta["batch_data_time"] - float(g["batch_data_time"])) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ SenseVoiceSmall
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("name", list(SV_CASES))
+def test_sensevoice_vs_reference_golden(name, mode):
+    """BASELINE config 4: query-frame prepend + 50+20 SAN-M blocks (eps 1e-5) + CTC greedy vs the reference's outputs."""
+    from funasr_b200 import synth
+    from funasr_b200.engine import SenseVoiceEngine
+    cfg, wseed, wavs, cmvn, g = load_sv_case(name)
+    eng = SenseVoiceEngine(synth.make_sensevoice_state_dict(cfg, wseed), cfg, DEV, gemm_mode=mode, cmvn=cmvn)
+    lens = [w.numel() for w in wavs]
+    pad = torch.nn.utils.rnn.pad_sequence(wavs, batch_first=True).to(DEV)
+    o = eng.forward_wav(pad, torch.tensor(lens, dtype=torch.int32, device=DEV), lens, language_id=0, textnorm_id=15, want_taps=True)
+    torch.cuda.synchronize()
+    step = 7 if cfg.enc_layers > 10 else 1
+    assert o["enc_lens"].cpu().tolist() == g["enc_lens"].tolist()
+    assert rel_err(o["enc"][:, ::step].cpu().numpy(), g["enc"]) <= 1e-3
+    assert rel_err(o["logp"][:, g["logp_rows"].tolist()].cpu().numpy(), g["logp_sel"]) <= 1e-3
+    valid = np.arange(g["argmax"].shape[1])[None, :] < g["enc_lens"][:, None]
+    assert (o["argmax"].cpu().numpy()[valid] == g["argmax"][valid]).all()
+    assert [t for r in o["ids"] for t in r] == g["ids_flat"].tolist()            # CTC greedy ids: bit-exact
+    assert [len(r) for r in o["ids"]] == g["ids_len"].tolist()
+
+
+def test_sensevoice_plugin_inference():
+    import funasr_b200
+    from funasr_b200 import synth
+    cfg, wseed, wavs, cmvn, g = load_sv_case("sv_tiny_ragged3")
+    m = funasr_b200.SenseVoiceSmallB200(encoder="SenseVoiceEncoderSmallB200",
+                                        encoder_conf=dict(output_size=512, attention_heads=4, linear_units=2048, num_blocks=cfg.enc_layers,
+                                                          tp_blocks=cfg.tp_layers, input_layer="pe", kernel_size=11, sanm_shfit=0,
+                                                          selfattention_layer_type="sanm"), input_size=560, vocab_size=cfg.vocab)
+    m.load_state_dict(synth.make_sensevoice_state_dict(cfg, wseed), strict=True)
+    m.to(DEV).eval()
+    fe = funasr_b200.WavFrontendB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0, cmvn=cmvn)
+    res, meta = m.inference([w.numpy() for w in wavs], key=["a", "b", "c"], tokenizer=None, frontend=fe, device=DEV, language="auto", use_itn=False)
+    assert [t for r in res for t in r["token_int"]] == g["ids_flat"].tolist()

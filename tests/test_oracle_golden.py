@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, load_case, rel_err, state_dict_for
+from conftest import GOLDEN_CASES, SV_CASES, load_case, load_sv_case, rel_err, state_dict_for
 
 import paraformer_oracle as O
 import ref_shim
@@ -96,3 +96,16 @@ def test_oracle_matches_live_reference_components():
         assert r_tok.tolist() == o_tok.tolist()
         assert torch.allclose(r_al, o_al, atol=1e-6) and torch.allclose(r_pk, o_pk, atol=1e-5)
         assert torch.allclose(r_emb, o_emb, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", list(SV_CASES))
+def test_sensevoice_oracle_matches_reference_golden(name):
+    """SenseVoiceSmall (BASELINE config 4): oracle vs outputs of the unmodified reference SenseVoiceSmall.inference."""
+    from funasr_b200 import synth
+    cfg, wseed, wavs, cmvn, g = load_sv_case(name)
+    o = O.sensevoice_forward(wavs, synth.make_sensevoice_state_dict(cfg, wseed), cmvn, cfg.enc_layers, cfg.tp_layers)
+    step = 7 if cfg.enc_layers > 10 else 1
+    assert o["enc_lens"].tolist() == g["enc_lens"].tolist()
+    assert rel_err(o["enc"][:, ::step].numpy(), g["enc"]) <= 1e-5
+    assert rel_err(o["logp"][:, g["logp_rows"].tolist()].numpy(), g["logp_sel"]) <= 1e-4
+    assert [t for r in o["ids"] for t in r] == g["ids_flat"].tolist() and [len(r) for r in o["ids"]] == g["ids_len"].tolist()
