@@ -9,7 +9,8 @@ from .registry import get_tables, install, register  # noqa: F401
 from .synth import PARAFORMER_LARGE, PARAFORMER_TINY, ParaformerConfig  # noqa: F401
 from . import modules  # noqa: F401  (registers the classes)
 from .modules import (CifPredictorV2B200, ParaformerB200, ParaformerSANMDecoderB200, SANMEncoderB200,  # noqa: F401
-                      SenseVoiceEncoderSmallB200, SenseVoiceSmallB200, WavFrontendB200, load_cmvn)
+                      SenseVoiceEncoderSmallB200, SenseVoiceSmallB200, WavFrontendB200, load_cmvn,
+                      ContextualParaformerB200, ContextualParaformerDecoderB200)
 from .engine import FrontendEngine, ParaformerEngine, SenseVoiceEngine  # noqa: F401
 from .synth import SENSEVOICE_SMALL, SENSEVOICE_TINY, SenseVoiceConfig  # noqa: F401
 from .sharding import shard_utterances, gather_token_ids  # noqa: F401

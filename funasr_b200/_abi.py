@@ -52,7 +52,10 @@ class FaDecLayer(C.Structure):
 class FaDecoder(C.Structure):
     _fields_ = [("layers", C.POINTER(FaDecLayer)), ("n_layers", C.c_int32), ("heads", C.c_int32),
                 ("fsmn_k", C.c_int32), ("vocab", C.c_int32), ("last", FaDecLayer), ("after_norm", FaNorm),
-                ("output", FaLinear)]
+                ("output", FaLinear), ("has_bias", C.c_int32), ("n_hotwords", C.c_int32), ("bias_last", FaDecLayer),
+                ("bias_norm3", FaNorm), ("bias_q", FaLinear), ("bias_kv", FaLinear), ("bias_out", FaLinear),
+                ("bias_output", FaLinear), ("hw_embed", C.c_void_p), ("hw_lens", C.c_void_p), ("clas_scale", C.c_float),
+                ("_pad2", C.c_int32)]
 
 
 _vp, _i32, _i64, _sz, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float

@@ -174,6 +174,8 @@ static size_t dec_plan(int64_t Mq, int64_t Mk, int vocab, int mode, size_t dec_s
   s.take(Mq * 512ull * 4);   // ctx
   s.take(Mk * 1024ull * 4);  // kv
   s.take(Mq * (size_t)vocab * 4);  // logits (used when the caller passes none)
+  s.take(Mq * 1024ull * 4);        // [x_src_attn ; cx] of the contextual decoder
+  s.take(Mk * 1024ull * 4);        // hotword k|v replicated per utterance (n_hotwords <= t_max)
   if (mode != FA_GEMM_F32_SIMT) {
     s.take(3ull * Mq * 512 * 2);   // ctx planes
     s.take(3ull * Mk * 512 * 2);   // enc planes (split once, reused by the 16 kv GEMMs)
@@ -229,6 +231,8 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
   float* ctx = a.take<float>(Mq * 512ull);
   float* kv = a.take<float>(Mk * 1024ull);
   float* lg = a.take<float>(Mq * (size_t)V);
+  float* cat = a.take<float>(Mq * 1024ull);
+  float* kvb_rep = a.take<float>(Mk * 1024ull);
   const bool tc = gemm_mode != FA_GEMM_F32_SIMT;
   const int npl = npl_for(gemm_mode);
   __nv_bfloat16* ctx_planes = tc ? a.take<__nv_bfloat16>(3ull * Mq * 512) : nullptr;
@@ -247,13 +251,15 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
                                batch, cudaMemcpyDeviceToDevice, st));
   fa::count_launch();
   float* y = ya;
-  for (int l = 0; l < dec->n_layers; ++l) {
-    const FaDecLayer& L = dec->layers[l];
-    FA_RETURN_IF_ERR(dec_ffn(L, y, Mq, t1, hq, f, gemm_mode, &scratch, st, t1_planes, hq_planes));
+  // One attention decoder layer.  x_self_out receives `residual + fsmn(...)` (x_self_attn); if src_out != nullptr the
+  // cross-attention output is written there WITHOUT the residual (x_src_attn, leading dim ld_src) and *y_next is not
+  // produced — the ContextualDecoderLayer contract (contextual_paraformer/decoder.py:60-100).
+  auto attention_layer = [&](const FaDecLayer& L, float* yin, float** x_self_out, float* src_out, int64_t ld_src, float** y_next) -> int {
+    FA_RETURN_IF_ERR(dec_ffn(L, yin, Mq, t1, hq, f, gemm_mode, &scratch, st, t1_planes, hq_planes));
     // x = residual + fsmn(LN2(f), tgt_mask)     decoder.py:103-107
     FA_RETURN_IF_ERR(layernorm_launch(f, Mq, L.norm2, t1, nullptr, 1.f, 1, st));
-    float* x2 = (y == ya) ? yb : ya;
-    FA_RETURN_IF_ERR(fsmn_launch(t1, D, tok_lens, batch, n_max, D, L.fsmn_w, dec->fsmn_k, y, D, x2, D, st));
+    float* x2 = (yin == ya) ? yb : ya;
+    FA_RETURN_IF_ERR(fsmn_launch(t1, D, tok_lens, batch, n_max, D, L.fsmn_w, dec->fsmn_k, yin, D, x2, D, st));
     // x = residual + src_attn(LN3(x), memory)    decoder.py:109-118, attention.py:796-813
     if (tc) {
       FA_RETURN_IF_ERR(layernorm_launch(x2, Mq, L.norm3, nullptr, nullptr, 1.f, 1, st, t1_planes, npl, D));
@@ -263,17 +269,48 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
       FA_RETURN_IF_ERR(linear(t1, D, Mq, L.q, 0, nullptr, 0, nullptr, 0, qd, D, gemm_mode, &scratch, st));
     }
     float* y2 = (x2 == ya) ? yb : ya;
+    float* dst = src_out ? src_out : y2;
+    const int64_t ldd = src_out ? ld_src : D;
+    const float* res = src_out ? nullptr : x2;
     if (!tc) {
       FA_RETURN_IF_ERR(linear(enc, D, Mk, L.kv, 0, nullptr, 0, nullptr, 0, kv, 2 * D, gemm_mode, &scratch, st));
       FA_RETURN_IF_ERR(attention_f32_launch(qd, D, kv, 2 * D, kv + D, 2 * D, enc_lens, batch, dec->heads, n_max, t_max, ctx,
                                             D, st));
-      FA_RETURN_IF_ERR(linear(ctx, D, Mq, L.out, 0, x2, D, nullptr, 0, y2, D, gemm_mode, &scratch, st));
+      FA_RETURN_IF_ERR(linear(ctx, D, Mq, L.out, 0, res, D, nullptr, 0, dst, ldd, gemm_mode, &scratch, st));
     } else {
       FA_RETURN_IF_ERR(gemm_tc_planes_launch(enc_planes, Mk, L.kv, 0, nullptr, 0, nullptr, 0, kv, 2 * D, nullptr, 0, gemm_mode, st));
       FA_RETURN_IF_ERR(attention_tc_launch(qd, D, kv, 2 * D, kv + D, 2 * D, enc_lens, batch, dec->heads, n_max, t_max, nullptr, 0,
                                            ctx_planes, D, npl, gemm_mode, &scratch, st));
-      FA_RETURN_IF_ERR(gemm_tc_planes_launch(ctx_planes, Mq, L.out, 0, x2, D, nullptr, 0, y2, D, nullptr, 0, gemm_mode, st));
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(ctx_planes, Mq, L.out, 0, res, D, nullptr, 0, dst, ldd, nullptr, 0, gemm_mode, st));
     }
+    *x_self_out = x2;
+    if (y_next) *y_next = y2;
+    return FA_OK;
+  };
+  for (int l = 0; l < dec->n_layers; ++l) {
+    float* xs = nullptr;
+    FA_RETURN_IF_ERR(attention_layer(dec->layers[l], y, &xs, nullptr, 0, &y));
+  }
+  if (dec->has_bias) {
+    // ContextualParaformerDecoder.forward decoder.py:325-340
+    const int nh = dec->n_hotwords;
+    if (!dec->hw_embed || !dec->hw_lens || nh <= 0 || nh > t_max || dec->clas_scale != 1.0f) return FA_ERR_UNSUPPORTED;
+    float* x_self = nullptr;
+    FA_RETURN_IF_ERR(attention_layer(dec->bias_last, y, &x_self, cat, 2 * D, nullptr));      // cat[:, :512] = x_src_attn
+    // bias decoder: cross attention of LN3(x_self_attn) over the hotword memory (identical for every utterance)
+    FA_RETURN_IF_ERR(layernorm_launch(x_self, Mq, dec->bias_norm3, t1, nullptr, 1.f, 1, st));
+    FA_RETURN_IF_ERR(linear(t1, D, Mq, dec->bias_q, 0, nullptr, 0, nullptr, 0, qd, D, gemm_mode, &scratch, st));
+    FA_RETURN_IF_ERR(linear(dec->hw_embed, D, nh, dec->bias_kv, 0, nullptr, 0, nullptr, 0, kv, 2 * D, gemm_mode, &scratch, st));
+    FA_RETURN_IF_ERR(fa_broadcast_rows(kv, 1, nh * 2 * D, kvb_rep, 1, batch, stream));
+    if (!tc) {
+      FA_RETURN_IF_ERR(attention_f32_launch(qd, D, kvb_rep, 2 * D, kvb_rep + D, 2 * D, dec->hw_lens, batch, dec->heads, n_max, nh, ctx, D, st));
+    } else {
+      FA_RETURN_IF_ERR(attention_tc_launch(qd, D, kvb_rep, 2 * D, kvb_rep + D, 2 * D, dec->hw_lens, batch, dec->heads, n_max, nh, ctx, D,
+                                           nullptr, 0, 0, gemm_mode, &scratch, st));
+    }
+    FA_RETURN_IF_ERR(linear(ctx, D, Mq, dec->bias_out, 0, nullptr, 0, nullptr, 0, cat + D, 2 * D, gemm_mode, &scratch, st));   // cat[:, 512:] = cx
+    float* y2 = (x_self == ya) ? yb : ya;
+    FA_RETURN_IF_ERR(linear(cat, 2 * D, Mq, dec->bias_output, 0, x_self, D, nullptr, 0, y2, D, gemm_mode, &scratch, st));
     y = y2;
   }
   // decoders3: FFN only, no residual (decoder.py:97-102,121); after_norm; output_layer

@@ -139,9 +139,10 @@ class ParaformerEngine(_EngineBase):
     """Packed weights + workspace + the encoder/predictor/decoder ABI calls."""
 
     def __init__(self, state: Dict[str, torch.Tensor], cfg: ParaformerConfig, device, gemm_mode: str = "fp32",
-                 prefix_enc="encoder.", prefix_pred="predictor.", prefix_dec="decoder."):
+                 prefix_enc="encoder.", prefix_pred="predictor.", prefix_dec="decoder.", contextual: bool = False):
         self._init_base(state, device, gemm_mode, cfg.ln_eps)
         self.cfg = cfg
+        self.contextual = contextual
         g, lin, norm = self._g, self._lin, self._norm
         D, K = cfg.d_model, cfg.kernel
         # ---- encoder
@@ -165,12 +166,24 @@ class ParaformerEngine(_EngineBase):
                 L.fsmn_w = g(p + ".self_attn.fsmn_block.weight").data_ptr()
                 L.q, L.kv, L.out = lin(p + ".src_attn.linear_q"), lin(p + ".src_attn.linear_k_v"), lin(p + ".src_attn.linear_out")
 
-        self.dec_layers = (_abi.FaDecLayer * cfg.dec_layers)()
-        for i in range(cfg.dec_layers):
+        n_plain = cfg.dec_layers - 1 if contextual else cfg.dec_layers
+        self.dec_layers = (_abi.FaDecLayer * max(n_plain, 1))()
+        for i in range(n_plain):
             dec_layer(self.dec_layers[i], prefix_dec + "decoders.%d" % i)
         self.dec = _abi.FaDecoder()
         self.dec.layers = self.dec_layers
-        self.dec.n_layers, self.dec.heads, self.dec.fsmn_k, self.dec.vocab = cfg.dec_layers, cfg.heads, K, cfg.vocab
+        self.dec.n_layers, self.dec.heads, self.dec.fsmn_k, self.dec.vocab = n_plain, cfg.heads, K, cfg.vocab
+        self.dec.has_bias = 0
+        if contextual:   # ContextualParaformerDecoder (contextual_paraformer/decoder.py:133-352)
+            dec_layer(self.dec.bias_last, prefix_dec + "last_decoder")
+            self.dec.bias_norm3 = norm(prefix_dec + "bias_decoder.norm3")
+            self.dec.bias_q = lin(prefix_dec + "bias_decoder.src_attn.linear_q")
+            self.dec.bias_kv = lin(prefix_dec + "bias_decoder.src_attn.linear_k_v")
+            self.dec.bias_out = lin(prefix_dec + "bias_decoder.src_attn.linear_out")
+            bw = state[prefix_dec + "bias_output.weight"]
+            self.dec.bias_output = lin(prefix_dec + "bias_output", bias=False, weight=self._dev(bw.reshape(bw.shape[0], -1)))
+            self.dec.clas_scale = 1.0
+            self._hw = None
         dec_layer(self.dec.last, prefix_dec + "decoders3.0", full=False)
         self.dec.after_norm = norm(prefix_dec + "after_norm")
         self.dec.output = lin(prefix_dec + "output_layer")
@@ -196,10 +209,24 @@ class ParaformerEngine(_EngineBase):
                                                      ws.data_ptr(), ws.numel(), self._stream()), "fa_cif_predictor_forward")
         return acoustic, tok, alphas, peaks
 
+    def set_hotwords(self, hw_embed: torch.Tensor):
+        """Hotword memory [Nhw, 512] (LSTM last hidden states) for the contextual bias decoder."""
+        if not self.contextual:
+            raise _abi.FunasrB200Error("engine was not built with contextual=True")
+        self._hw = hw_embed.detach().to(self.device, torch.float32).contiguous()
+        self._hw_lens = None
+
     def decode(self, enc: torch.Tensor, enc_lens: torch.Tensor, acoustic: torch.Tensor, tok_lens: torch.Tensor, n_max: int,
                want_logp: bool = False):
         """ParaformerSANMDecoder.forward + arg-max -> (argmax ids [B,n_max] i32, best logp [B,n_max], logp or None)."""
         B, T, D = enc.shape
+        if self.contextual:
+            if self._hw is None:
+                raise _abi.FunasrB200Error("call set_hotwords() first")
+            if self._hw_lens is None or self._hw_lens.numel() != B:
+                self._hw_lens = torch.full((B,), self._hw.shape[0], dtype=torch.int32, device=self.device)
+            self.dec.has_bias, self.dec.n_hotwords = 1, self._hw.shape[0]
+            self.dec.hw_embed, self.dec.hw_lens = self._hw.data_ptr(), self._hw_lens.data_ptr()
         ids = torch.empty((B, n_max), dtype=torch.int32, device=self.device)
         best = torch.empty((B, n_max), dtype=torch.float32, device=self.device)
         logp = torch.empty((B, n_max, self.cfg.vocab), dtype=torch.float32, device=self.device) if want_logp else None

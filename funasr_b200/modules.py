@@ -470,3 +470,72 @@ class SenseVoiceSmallB200(nn.Module):
             ids = out["ids"][i]
             results.append({"key": key[i], "text": tokenizer.decode(ids)} if tokenizer is not None else {"key": key[i], "token_int": ids})
         return results, meta_data
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ContextualParaformer (BASELINE config 5)
+# ------------------------------------------------------------------------------------------------------------------
+@register("decoder_classes", "ContextualParaformerDecoderB200")
+class ContextualParaformerDecoderB200(ParaformerSANMDecoderB200):
+    """Parameter container for ContextualParaformerDecoder (funasr/models/contextual_paraformer/decoder.py:133-290)."""
+
+    def _specs(self):
+        s = super()._specs()
+        D = self.D
+        last = "decoders.%d." % (self.num_blocks - 1)
+        for k in [k for k in s if k.startswith(last)]:
+            s["last_decoder." + k[len(last):]] = s.pop(k)
+        s["bias_decoder.norm3.weight"] = (D,)
+        s["bias_decoder.norm3.bias"] = (D,)
+        for nme, shp in (("linear_q", (D, D)), ("linear_k_v", (2 * D, D)), ("linear_out", (D, D))):
+            s["bias_decoder.src_attn.%s.weight" % nme] = shp
+            s["bias_decoder.src_attn.%s.bias" % nme] = (shp[0],)
+        s["bias_output.weight"] = (D, 2 * D, 1)
+        return s
+
+
+@register("model_classes", "ContextualParaformerB200")
+class ContextualParaformerB200(ParaformerB200):
+    """Drop-in for ContextualParaformer's greedy inference with hotwords (contextual_paraformer/model.py:46-520).
+    The hotword encoder (Embedding + 1-layer LSTM over a few short token sequences, O(#hotwords) and independent of the
+    audio) runs in torch as the scope contract allows; everything per audio frame/token is CUDA."""
+
+    def __init__(self, *args, inner_dim: int = 512, **kwargs):
+        if not isinstance(kwargs.get("decoder"), type) and kwargs.get("decoder") not in ("ContextualParaformerDecoderB200",):
+            kwargs["decoder"] = "ContextualParaformerDecoderB200"
+        super().__init__(*args, **kwargs)
+        if inner_dim != 512:
+            raise _abi.FunasrB200Error("ContextualParaformerB200 supports inner_dim=512")
+        self.bias_encoder = nn.LSTM(inner_dim, inner_dim, 1, batch_first=True)
+        self.bias_embed = nn.Embedding(self.vocab_size, inner_dim)
+        for p_ in list(self.bias_encoder.parameters()) + list(self.bias_embed.parameters()):
+            p_.requires_grad_(False)
+
+    def engine(self, device=None) -> ParaformerEngine:
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _abi.FunasrB200Error("ContextualParaformerB200 needs a CUDA device; there is no CPU path")
+        if self._engine is None or self._engine.device != dev:
+            self._engine = ParaformerEngine(self.state_dict(), self.cfg, dev, gemm_mode=self.gemm_mode, contextual=True)
+        return self._engine
+
+    @torch.no_grad()
+    def encode_hotwords(self, hw_list) -> torch.Tensor:
+        """bias_embed -> LSTM -> h_n: [Nhw, 512] (model.py:350-372); hw_list=None -> the single [sos] entry (:350-358)."""
+        dev = self.bias_embed.weight.device
+        if hw_list is None:
+            hw_list = [[1]]
+        lens = [len(h) for h in hw_list]
+        pad = torch.zeros((len(hw_list), max(lens)), dtype=torch.long, device=dev)
+        for i, h in enumerate(hw_list):
+            pad[i, : len(h)] = torch.tensor(h, device=dev)
+        packed = torch.nn.utils.rnn.pack_padded_sequence(self.bias_embed(pad), lens, batch_first=True, enforce_sorted=False)
+        _, (h_n, _) = self.bias_encoder(packed)
+        return h_n[0]
+
+    def inference(self, data_in, data_lengths=None, key: list = None, tokenizer=None, frontend=None, **kwargs):
+        hw = kwargs.get("hotword_ids")          # list of token-id lists (+ trailing [sos]); text hotwords need the tokenizer
+        if hw is None and kwargs.get("hotword") and tokenizer is not None:
+            hw = [tokenizer.tokens2ids(h.split()) for h in kwargs["hotword"].split()] + [[self.sos]]
+        self.engine(kwargs.get("device", "cuda")).set_hotwords(self.encode_hotwords(hw))
+        return super().inference(data_in, data_lengths, key, tokenizer, frontend, **kwargs)

@@ -116,6 +116,42 @@ def make_state_dict(cfg: ParaformerConfig = PARAFORMER_LARGE, seed: int = 0) -> 
     return sd
 
 
+def make_contextual_state_dict(cfg: ParaformerConfig = PARAFORMER_LARGE, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """ContextualParaformer (BASELINE config 5; funasr/models/contextual_paraformer): the Paraformer dict with the last
+    attention decoder layer renamed `decoder.last_decoder`, plus `decoder.bias_decoder.*`, `decoder.bias_output.weight`
+    (Conv1d 1024->512, k=1, no bias), the hotword LSTM `bias_encoder.*` and `bias_embed.weight` (inner_dim 512)."""
+    base = make_state_dict(cfg, seed)
+    g = torch.Generator().manual_seed(1000003 * seed + 41)
+    D, V = cfg.d_model, cfg.vocab
+    last = cfg.dec_layers - 1
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for k, v in base.items():
+        sd[k.replace("decoder.decoders.%d." % last, "decoder.last_decoder.")] = v
+    sd["decoder.bias_decoder.norm3.weight"] = 1.0 + _randn(g, D, std=0.1)
+    sd["decoder.bias_decoder.norm3.bias"] = _randn(g, D, std=0.05)
+    for name, shape, gain in (("linear_q", (D, D), 1.5), ("linear_k_v", (2 * D, D), 1.5), ("linear_out", (D, D), 0.3)):
+        sd["decoder.bias_decoder.src_attn.%s.weight" % name] = _randn(g, *shape, std=gain / math.sqrt(D))
+        sd["decoder.bias_decoder.src_attn.%s.bias" % name] = _randn(g, shape[0], std=0.02)
+    sd["decoder.bias_output.weight"] = _randn(g, D, 2 * D, 1, std=1.0 / math.sqrt(2 * D))
+    sd["bias_encoder.weight_ih_l0"] = _randn(g, 4 * D, D, std=1.0 / math.sqrt(D))
+    sd["bias_encoder.weight_hh_l0"] = _randn(g, 4 * D, D, std=1.0 / math.sqrt(D))
+    sd["bias_encoder.bias_ih_l0"] = _randn(g, 4 * D, std=0.05)
+    sd["bias_encoder.bias_hh_l0"] = _randn(g, 4 * D, std=0.05)
+    sd["bias_embed.weight"] = _randn(g, V, D, std=1.0)
+    return sd
+
+
+def make_hotwords(n: int, vocab: int, seed: int = 7, sos: int = 1):
+    """n random hotword token-id sequences (len 2..6) + the trailing [sos] entry generate_hotwords_list appends
+    (contextual_paraformer/model.py:606-607)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        ln = int(torch.randint(2, 7, (1,), generator=g))
+        out.append(torch.randint(3, vocab - 1, (ln,), generator=g).tolist())
+    return out + [[sos]]
+
+
 @dataclass(frozen=True)
 class SenseVoiceConfig:
     """SenseVoiceSmall (funasr/models/sense_voice/model.py:489-1034; runtime/triton_gpu/.../config.yaml): the same SAN-M

@@ -115,6 +115,19 @@ typedef struct {
   FaDecLayer last;          /* decoders3.0: norm1 + ffn only */
   FaNorm after_norm;
   FaLinear output;          /* output_layer [vocab, 512] */
+  /* ContextualParaformerDecoder (funasr/models/contextual_paraformer/decoder.py:133-352); has_bias == 0 for the plain
+   * Paraformer decoder.  With has_bias: `layers` are decoders.{0..att_layer_num-2}, `bias_last` is last_decoder, and
+   * x = x_self_attn + bias_output([x_src_attn ; clas_scale * bias_decoder(x_self_attn, hotword memory)]) (:330-340). */
+  int32_t has_bias;
+  int32_t n_hotwords;       /* rows of hw_embed, <= t_max */
+  FaDecLayer bias_last;     /* last_decoder (ContextualDecoderLayer :22-100) */
+  FaNorm bias_norm3;        /* bias_decoder.norm3 */
+  FaLinear bias_q, bias_kv, bias_out; /* bias_decoder.src_attn.linear_q / linear_k_v / linear_out */
+  FaLinear bias_output;     /* bias_output Conv1d(1024->512, k=1, no bias) as a [512, 1024] linear */
+  const float* hw_embed;    /* [n_hotwords, 512] hotword memory (LSTM last hidden states, model.py:350-372) */
+  const int32_t* hw_lens;   /* [batch] device, every entry == n_hotwords */
+  float clas_scale;         /* 1.0 */
+  int32_t _pad2;
 } FaDecoder;
 
 /* ---------------------------------------------------------------------------------------------

@@ -124,7 +124,7 @@ def main():
     write_cmvn_file(os.path.join(GOLD, "am_synth.mvn"), synth.make_cmvn(synth.PARAFORMER_LARGE, seed=1))
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "sensevoice"):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("sensevoice", "contextual")):
     main()
 
 
@@ -192,3 +192,76 @@ def main_sv():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sensevoice":
     main_sv()
+
+
+# ------------------------------------------------------------------------------------------------ ContextualParaformer
+CTX_CASES = {
+    "ctx_tiny_ragged3": (synth.PARAFORMER_TINY, 6, [(48000, 21, "speechlike"), (27200, 22, "noise"), (38437, 23, "speechlike")], 5),
+    "ctx_large_single": (synth.PARAFORMER_LARGE, 2, [(240000, 24, "speechlike")], 32),
+}
+
+
+def run_ctx_case(name, cfg, wseed, wav_specs, n_hot, tmp):
+    from funasr import AutoModel
+    cmvn_file = os.path.join(tmp, "am_%s.mvn" % name)
+    write_cmvn_file(cmvn_file, synth.make_cmvn(cfg, seed=1))
+    pt = os.path.join(tmp, "ctx_%s.pt" % name)
+    torch.save(synth.make_contextual_state_dict(cfg, wseed), pt)
+    tokens = ["<blank>", "<s>", "</s>"] + ["t%d" % i for i in range(cfg.vocab - 4)] + ["<unk>"]
+    am = AutoModel(
+        model="ContextualParaformer",
+        model_conf=dict(ctc_weight=0.0, lsm_weight=0.1, length_normalized_loss=True, predictor_weight=1.0, predictor_bias=1,
+                        sampling_ratio=0.75, inner_dim=512),
+        encoder="SANMEncoder",
+        encoder_conf=dict(output_size=cfg.d_model, attention_heads=cfg.heads, linear_units=cfg.ffn, num_blocks=cfg.enc_layers,
+                          dropout_rate=0.1, positional_dropout_rate=0.1, attention_dropout_rate=0.1, input_layer="pe",
+                          pos_enc_class="SinusoidalPositionEncoder", normalize_before=True, kernel_size=cfg.kernel, sanm_shfit=0,
+                          selfattention_layer_type="sanm"),
+        decoder="ContextualParaformerDecoder",
+        decoder_conf=dict(attention_heads=cfg.heads, linear_units=cfg.ffn, num_blocks=cfg.dec_layers, dropout_rate=0.1,
+                          positional_dropout_rate=0.1, self_attention_dropout_rate=0.1, src_attention_dropout_rate=0.1,
+                          att_layer_num=cfg.dec_layers, kernel_size=cfg.kernel, sanm_shfit=0),
+        predictor="CifPredictorV2",
+        predictor_conf=dict(idim=cfg.d_model, threshold=1.0, l_order=1, r_order=1, tail_threshold=cfg.tail_threshold),
+        frontend="WavFrontend",
+        frontend_conf=dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0,
+                           cmvn_file=cmvn_file),
+        tokenizer="CharTokenizer", tokenizer_conf=dict(token_list=tokens, unk_symbol="<unk>", split_with_space=True),
+        device="cpu", ncpu=os.cpu_count(), disable_update=True, disable_pbar=True, init_param=pt,
+    )
+    model, frontend = am.model, am.kwargs["frontend"]
+    hw_list = synth.make_hotwords(n_hot, cfg.vocab, seed=7)
+    wavs = [synth.make_wav(n, s, k) for (n, s, k) in wav_specs]
+    with torch.no_grad():
+        from funasr.utils.load_utils import extract_fbank
+        feats, flens = extract_fbank([w for w in wavs], frontend=frontend)
+        enc, elens = model.encode(feats, flens)
+        emb, tok, alphas, peaks = model.calc_predictor(enc, elens)
+        tokl = tok.round().long()
+        logp, _ = model.cal_decoder_with_predictor(enc, elens, emb, tokl, hw_list=hw_list, clas_scale=1.0)
+        # hotword embeddings exactly as cal_decoder_with_predictor builds them (model.py:360-372)
+        from funasr.models.transformer.utils.nets_utils import pad_list
+        pad = pad_list([torch.Tensor(i).long() for i in hw_list], 0)
+        packed = torch.nn.utils.rnn.pack_padded_sequence(model.bias_embed(pad), [len(i) for i in hw_list], batch_first=True, enforce_sorted=False)
+        _, (h_n, _) = model.bias_encoder(packed)
+    ids = []
+    for i in range(len(wavs)):
+        ys = logp[i, : int(tokl[i])].argmax(-1).tolist()
+        ids.append([t for t in ys if t not in (0, 1, 2)])
+    N = logp.shape[1]
+    keep = sorted(set(list(range(min(4, N))) + [N // 2, N - 1]))
+    top2 = torch.topk(logp, 2, dim=-1).values
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), token_num=tokl.numpy().astype(np.int32), hw_embed=h_n[0].numpy(),
+                        logp_rows=np.array(keep, dtype=np.int32), logp_sel=logp[:, keep, :].numpy(),
+                        argmax=logp.argmax(-1).numpy().astype(np.int32), margin=(top2[..., 0] - top2[..., 1]).numpy(),
+                        ids_flat=np.array([t for r in ids for t in r], dtype=np.int32), ids_len=np.array([len(r) for r in ids], dtype=np.int32))
+    valid = torch.arange(N)[None, :] < tokl[:, None]
+    print("%s: B=%d tokens=%s n_hot=%d min margin %.3e ids[0][:6]=%s" % (name, len(wavs), tokl.tolist(), len(hw_list),
+                                                                      float((top2[..., 0] - top2[..., 1])[valid].min()), ids[0][:6]))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "contextual":
+    ref_shim.import_reference()
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (cfg, wseed, specs, n_hot) in CTX_CASES.items():
+            run_ctx_case(name, cfg, wseed, specs, n_hot, tmp)

@@ -364,3 +364,85 @@ def sensevoice_forward(wavs: List[Tensor], p: Dict[str, Tensor], cmvn: Optional[
             y = torch.unique_consecutive(logp[i, : int(elens[i])].argmax(dim=-1), dim=-1)
             ids.append(y[y != blank].tolist())
     return {"feats": feats, "feat_lens": flens, "enc": enc, "enc_lens": elens, "logp": logp, "ids": ids}
+
+
+# --------------------------------------------------------------------------------------
+# ContextualParaformer (BASELINE config 5): funasr/models/contextual_paraformer/model.py:331-385, decoder.py:293-352
+# --------------------------------------------------------------------------------------
+def lstm_last_hidden(x: Tensor, lengths: List[int], p: Dict[str, Tensor], pre="bias_encoder.") -> Tensor:
+    """1-layer batch_first nn.LSTM over packed sequences -> h_n [N, H] (model.py:360-372). Gate order i,f,g,o."""
+    wih, whh = p[pre + "weight_ih_l0"], p[pre + "weight_hh_l0"]
+    bih, bhh = p[pre + "bias_ih_l0"], p[pre + "bias_hh_l0"]
+    N, _, H = x.shape[0], x.shape[1], whh.shape[1]
+    out = torch.zeros(N, H)
+    for n in range(N):
+        h, c = torch.zeros(H), torch.zeros(H)
+        for t in range(lengths[n]):
+            gates = F.linear(x[n, t], wih, bih) + F.linear(h, whh, bhh)
+            i, f, g, o = gates.chunk(4)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+        out[n] = h
+    return out
+
+
+def hotword_embeddings(hw_list: List[List[int]], p: Dict[str, Tensor]) -> Tensor:
+    """bias_embed -> LSTM -> last hidden state per hotword: [Nhw, 512] (model.py:350-372)."""
+    lens = [len(h) for h in hw_list]
+    pad = torch.zeros(len(hw_list), max(lens), dtype=torch.long)
+    for i, h in enumerate(hw_list):
+        pad[i, : len(h)] = torch.tensor(h)
+    return lstm_last_hidden(F.embedding(pad, p["bias_embed.weight"]), lens, p)
+
+
+def contextual_decoder(enc, enc_lens, emb, tok_lens, hw_embed, p, dec_layers: int, heads=4, eps=1e-12, clas_scale=1.0):
+    """ContextualParaformerDecoder.forward decoder.py:293-352 -> logits [B, N, V]."""
+    B, N, D = emb.shape
+    T = enc.shape[1]
+    tgt_mask = (torch.arange(N)[None, :] < tok_lens[:, None].long()).float()[:, :, None]
+    mem_mask = (torch.arange(T)[None, :] < enc_lens[:, None].long()).float()[:, None, :]
+
+    def layer(x, pre):
+        r = x
+        t = dec_ffn(layer_norm(x, p[pre + "norm1.weight"], p[pre + "norm1.bias"], eps), p, pre + "feed_forward.", eps)
+        t = layer_norm(t, p[pre + "norm2.weight"], p[pre + "norm2.bias"], eps)
+        x_self = r + fsmn(t, p[pre + "self_attn.fsmn_block.weight"], tgt_mask)
+        y = layer_norm(x_self, p[pre + "norm3.weight"], p[pre + "norm3.bias"], eps)
+        q = F.linear(y, p[pre + "src_attn.linear_q.weight"], p[pre + "src_attn.linear_q.bias"])
+        kv = F.linear(enc, p[pre + "src_attn.linear_k_v.weight"], p[pre + "src_attn.linear_k_v.bias"])
+        k, v = torch.split(kv, D, dim=-1)
+        x_src = F.linear(mh_attention(q, k, v, mem_mask, heads), p[pre + "src_attn.linear_out.weight"], p[pre + "src_attn.linear_out.bias"])
+        return x_self + x_src, x_self, x_src
+
+    x = emb
+    for i in range(dec_layers - 1):
+        x, _, _ = layer(x, "decoder.decoders.%d." % i)
+    _, x_self, x_src = layer(x, "decoder.last_decoder.")
+    # bias decoder: cross attention over the hotword embeddings (same list for every utterance)
+    mem = hw_embed[None].repeat(B, 1, 1)
+    pre = "decoder.bias_decoder."
+    y = layer_norm(x_self, p[pre + "norm3.weight"], p[pre + "norm3.bias"], eps)
+    q = F.linear(y, p[pre + "src_attn.linear_q.weight"], p[pre + "src_attn.linear_q.bias"])
+    kv = F.linear(mem, p[pre + "src_attn.linear_k_v.weight"], p[pre + "src_attn.linear_k_v.bias"])
+    k, v = torch.split(kv, D, dim=-1)
+    cmask = torch.ones(B, 1, mem.shape[1])
+    cx = F.linear(mh_attention(q, k, v, cmask, heads), p[pre + "src_attn.linear_out.weight"], p[pre + "src_attn.linear_out.bias"])
+    cat = torch.cat([x_src, cx * clas_scale], dim=2)
+    x = x_self + F.conv1d(cat.transpose(1, 2), p["decoder.bias_output.weight"]).transpose(1, 2)
+    pre = "decoder.decoders3.0."
+    x = dec_ffn(layer_norm(x, p[pre + "norm1.weight"], p[pre + "norm1.bias"], eps), p, pre + "feed_forward.", eps)
+    h = layer_norm(x, p["decoder.after_norm.weight"], p["decoder.after_norm.bias"], eps)
+    return F.linear(h, p["decoder.output_layer.weight"], p["decoder.output_layer.bias"])
+
+
+def contextual_forward(wavs, p, cmvn, enc_layers: int, dec_layers: int, hw_list, heads=4, eps=1e-12, tail_threshold=0.45):
+    """ContextualParaformer.inference greedy path (model.py:387-520) with a hotword list (token ids)."""
+    with torch.no_grad():
+        feats, flens = frontend(wavs, cmvn)
+        enc, elens = encoder(feats, flens, p, enc_layers, heads, eps)
+        emb, token_num, alphas, peaks = predictor(enc, elens, p, tail_threshold)
+        tok = token_num.round().long()
+        hw = hotword_embeddings(hw_list, p)
+        logits = contextual_decoder(enc, elens, emb, tok, hw, p, dec_layers, heads, eps)
+        logp = torch.log_softmax(logits, dim=-1)
+    return {"enc": enc, "token_num": tok.to(torch.int32), "acoustic": emb, "hw_embed": hw, "logp": logp, "ids": greedy_ids(logp, tok)}

@@ -80,3 +80,21 @@ def load_sv_case(name):
     cmvn = synth.make_cmvn(synth.PARAFORMER_LARGE, seed=1)
     cmvn = torch.tensor(np.array([[float("%.9g" % v) for v in row] for row in cmvn.tolist()], dtype=np.float32))
     return cfg, wseed, wavs, cmvn, gold
+
+
+# ContextualParaformer golden cases — must match oracle/make_golden.py:CTX_CASES
+CTX_CASES = {
+    "ctx_tiny_ragged3": ("tiny", 6, [(48000, 21, "speechlike"), (27200, 22, "noise"), (38437, 23, "speechlike")], 5),
+    "ctx_large_single": ("large", 2, [(240000, 24, "speechlike")], 32),
+}
+
+
+def load_ctx_case(name):
+    from funasr_b200 import synth
+    cfg_name, wseed, specs, n_hot = CTX_CASES[name]
+    cfg = synth.PARAFORMER_TINY if cfg_name == "tiny" else synth.PARAFORMER_LARGE
+    gold = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    wavs = [synth.make_wav(n, s, k) for (n, s, k) in specs]
+    cmvn = synth.make_cmvn(cfg, seed=1)
+    cmvn = torch.tensor(np.array([[float("%.9g" % v) for v in row] for row in cmvn.tolist()], dtype=np.float32))
+    return cfg, wseed, wavs, cmvn, synth.make_hotwords(n_hot, cfg.vocab, seed=7), gold

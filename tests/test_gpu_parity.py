@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, SV_CASES, load_case, load_sv_case, rel_err, state_dict_for
+from conftest import CTX_CASES, GOLDEN_CASES, SV_CASES, load_case, load_ctx_case, load_sv_case, rel_err, state_dict_for
 
 import paraformer_oracle as O
 
@@ -355,3 +355,36 @@ def test_sensevoice_plugin_inference():
     fe = funasr_b200.WavFrontendB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0, cmvn=cmvn)
     res, meta = m.inference([w.numpy() for w in wavs], key=["a", "b", "c"], tokenizer=None, frontend=fe, device=DEV, language="auto", use_itn=False)
     assert [t for r in res for t in r["token_int"]] == g["ids_flat"].tolist()
+
+
+# ------------------------------------------------------------------------------------------- ContextualParaformer
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("name", list(CTX_CASES))
+def test_contextual_vs_reference_golden(name, mode):
+    """BASELINE config 5 through the plugin class: hotword memory (torch LSTM, O(#hotwords)) + CUDA bias decoder."""
+    import funasr_b200
+    from funasr_b200 import synth
+    from test_abi_host import _tiny_conf
+    cfg, wseed, wavs, cmvn, hw, g = load_ctx_case(name)
+    conf = _tiny_conf()
+    conf["encoder_conf"]["num_blocks"] = cfg.enc_layers
+    conf["decoder_conf"].update(num_blocks=cfg.dec_layers, att_layer_num=cfg.dec_layers)
+    conf.update(decoder="ContextualParaformerDecoderB200", vocab_size=cfg.vocab, gemm_mode=mode)
+    m = funasr_b200.ContextualParaformerB200(**conf)
+    m.load_state_dict(synth.make_contextual_state_dict(cfg, wseed), strict=True)
+    m.to(DEV).eval()
+    hw_embed = m.encode_hotwords(hw)
+    assert rel_err(hw_embed.cpu().numpy(), g["hw_embed"]) <= 1e-4
+    fe = funasr_b200.WavFrontendB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0, cmvn=cmvn)
+    res, meta = m.inference([w.numpy() for w in wavs], key=["u%d" % i for i in range(len(wavs))], tokenizer=None, frontend=fe,
+                            device=DEV, hotword_ids=hw)
+    assert [t for r in res for t in r["token_int"]] == g["ids_flat"].tolist()       # bit-exact greedy ids
+    # log-probs through the stage API
+    eng = m.engine(DEV)
+    from funasr_b200.engine import num_lfr_frames
+    lens = [w.numel() for w in wavs]
+    pad = torch.nn.utils.rnn.pad_sequence(wavs, batch_first=True).to(DEV)
+    feats, fl = fe.engine(DEV)(pad, torch.tensor(lens, dtype=torch.int32, device=DEV), max(num_lfr_frames(n) for n in lens))
+    out = eng.forward_feats(feats, fl, want_taps=True)
+    assert out["token_num"].tolist() == g["token_num"].tolist()
+    assert rel_err(out["logp"][:, g["logp_rows"].tolist()].cpu().numpy(), g["logp_sel"]) <= 1e-3

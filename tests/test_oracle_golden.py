@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, SV_CASES, load_case, load_sv_case, rel_err, state_dict_for
+from conftest import CTX_CASES, GOLDEN_CASES, SV_CASES, load_case, load_ctx_case, load_sv_case, rel_err, state_dict_for
 
 import paraformer_oracle as O
 import ref_shim
@@ -107,5 +107,17 @@ def test_sensevoice_oracle_matches_reference_golden(name):
     step = 7 if cfg.enc_layers > 10 else 1
     assert o["enc_lens"].tolist() == g["enc_lens"].tolist()
     assert rel_err(o["enc"][:, ::step].numpy(), g["enc"]) <= 1e-5
+    assert rel_err(o["logp"][:, g["logp_rows"].tolist()].numpy(), g["logp_sel"]) <= 1e-4
+    assert [t for r in o["ids"] for t in r] == g["ids_flat"].tolist() and [len(r) for r in o["ids"]] == g["ids_len"].tolist()
+
+
+@pytest.mark.parametrize("name", list(CTX_CASES))
+def test_contextual_oracle_matches_reference_golden(name):
+    """ContextualParaformer (BASELINE config 5): hotword LSTM memory + bias decoder vs the unmodified reference."""
+    from funasr_b200 import synth
+    cfg, wseed, wavs, cmvn, hw, g = load_ctx_case(name)
+    o = O.contextual_forward(wavs, synth.make_contextual_state_dict(cfg, wseed), cmvn, cfg.enc_layers, cfg.dec_layers, hw)
+    assert o["token_num"].tolist() == g["token_num"].tolist()
+    assert rel_err(o["hw_embed"].numpy(), g["hw_embed"]) <= 1e-5
     assert rel_err(o["logp"][:, g["logp_rows"].tolist()].numpy(), g["logp_sel"]) <= 1e-4
     assert [t for r in o["ids"] for t in r] == g["ids_flat"].tolist() and [len(r) for r in o["ids"]] == g["ids_len"].tolist()
