@@ -11,8 +11,10 @@
 //           maximum only has to keep exp(s - m) in range, so one bf16 term suffices)
 //   pass B: S (all terms) -> p = exp(s - m), l += sum p, P planes -> smem, O += P.V accumulated in TMEM with no
 //           rescaling traffic; finally O / l -> bf16 planes (A operand of the out-projection GEMM) and/or fp32.
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 softmax + epilogue (one query
-// row per thread, TMEM lane == row).  S is double buffered in TMEM so the MMAs of chunk j+1 overlap softmax of chunk j.
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 softmax + epilogue:
+// TMEM lane == query row; two threads per row (warp w owns lane quarter w%4 and column half (w-4)/4) so that every SM
+// sub-partition has two softmax warps to interleave.  S is double buffered in TMEM so the MMAs of chunk j+1 overlap
+// the softmax of chunk j.
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -34,8 +36,10 @@ struct AttTcParams {
   __nv_bfloat16* ctx_planes; int64_t ldp; int out_nplanes;   // bf16 planes [npl][B*tq][ldp] (or null)
 };
 
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 softmax warps
+
 template <int NPL>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const AttTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -59,6 +63,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint64_t* p_empty = bars + 10;      // [1]
   uint64_t* o_full = bars + 11;       // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* s_red = reinterpret_cast<float*>(bars + 13);   // [2][128] row max / row sum exchange between column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
@@ -69,8 +74,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
-    mbar_init(p_full, 4); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8); }
+    mbar_init(p_full, 8); mbar_init(p_empty, 1); mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 256);
@@ -159,45 +164,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       umma_commit(o_full);
     }
   } else if (warp >= 4) {
-    // ===================== softmax + epilogue: thread <-> query row =====================
-    const int qw = warp - 4;
+    // ===================== softmax + epilogue: two threads per query row =====================
+    const int qw = warp & 3;                   // TMEM lane quarter this warp may access
+    const int hf = (warp - 4) >> 2;            // column half of a 64-key chunk / of the 128 output dims
     const int r = qw * 32 + lane;              // row in tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(qw * 32) << 16;
     float m = -INFINITY, l = 0.f;
     if (nc > 0) {
-      // ---- pass A: approximate row max
+      // ---- pass A: approximate row max over this thread's 32 columns of every chunk
       for (int i = 0; i < nc; ++i) {
         const int st = i & 1;
         mbar_wait(&s_full[st], ((uint32_t)i >> 1) & 1);
         tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + hf * 32, v);
+        const int kbase = i * AT_BKEY + hf * 32;
 #pragma unroll
-        for (int c0 = 0; c0 < AT_BKEY; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + c0, v);
-          const int kbase = i * AT_BKEY + c0;
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) if (kbase + jj < klen) m = fmaxf(m, __uint_as_float(v[jj]));
-        }
+        for (int jj = 0; jj < 32; ++jj) if (kbase + jj < klen) m = fmaxf(m, __uint_as_float(v[jj]));
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);
       }
+      s_red[hf * 128 + r] = m;
+      softmax_bar();
+      m = fmaxf(m, s_red[(hf ^ 1) * 128 + r]);     // finite: key 0 is always valid when nc > 0
       // ---- pass B: probabilities
       uint32_t* prow = reinterpret_cast<uint32_t*>(sP + (size_t)r * 128);
       for (int t = 0; t < nc; ++t) {
         const int i = nc + t, st = i & 1;
         mbar_wait(&s_full[st], ((uint32_t)i >> 1) & 1);
         tc_fence_after();
-        float pr[AT_BKEY];
-#pragma unroll
-        for (int c0 = 0; c0 < AT_BKEY; c0 += 32) {
+        float pr[32];
+        {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + c0, v);
-          const int kbase = t * AT_BKEY + c0;
+          tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + hf * 32, v);
+          const int kbase = t * AT_BKEY + hf * 32;
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
-            const float pv = (kbase + jj < klen) ? expf(__uint_as_float(v[jj]) - m) : 0.f;
-            pr[c0 + jj] = pv;
+            const float pv = (kbase + jj < klen) ? __expf(__uint_as_float(v[jj]) - m) : 0.f;
+            pr[jj] = pv;
             l += pv;
           }
         }
@@ -207,11 +212,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         // P planes -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
         mbar_wait(p_empty, ((uint32_t)t & 1) ^ 1);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int cc = 0; cc < 4; ++cc) {
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float a = pr[c * 8 + 2 * e], bb = pr[c * 8 + 2 * e + 1];
+            const float a = pr[cc * 8 + 2 * e], bb = pr[cc * 8 + 2 * e + 1];
             const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(bb);
             hi[e] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
             if (NPL > 1) {
@@ -219,7 +224,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
               lo[e] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
             }
           }
-          const int pc = (c ^ (r & 7)) * 4;
+          const int pc = ((hf * 4 + cc) ^ (r & 7)) * 4;
           *reinterpret_cast<uint4*>(prow + pc) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           if (NPL > 1) *reinterpret_cast<uint4*>(prow + AT_P_TILE / 4 + pc) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
@@ -227,15 +232,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
       }
+      softmax_bar();                   // everyone has read the exchanged maxima before the slots are reused
+      s_red[hf * 128 + r] = l;
+      softmax_bar();
+      l += s_red[(hf ^ 1) * 128 + r];
       mbar_wait(o_full, 0);
       tc_fence_after();
     }
-    // ---- epilogue: O / l
+    // ---- epilogue: O / l, this thread's 64 of the 128 head dims
     const int qrow = q0 + r;
     const float inv = l > 0.f ? 1.0f / l : 0.f;
     const int64_t grow = (int64_t)b * p.tq + qrow;
 #pragma unroll 1
-    for (int c0 = 0; c0 < AT_D; c0 += 32) {
+    for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
       uint32_t v[32];
       if (nc > 0) tmem_ld_32x32(tmem_o + lane_addr + c0, v);
       if (qrow < p.tq) {
@@ -353,6 +362,20 @@ int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk
     vt_planes_kernel<<<g, 256, 0, st>>>(v, ldv, tk, tkp, heads, npl, mv * tkp, vt);
     FA_CHECK_LAUNCH();
   }
+  return attention_tc_planes_launch(qp, kp, vt, key_lens, batch, heads, tq, tk, ctx, ldc, ctx_planes, ldp, out_nplanes, mode, st);
+}
+
+// Operand planes already in place (written by the producing GEMMs' epilogues, gemm_tc.cu AttnSinks):
+// qp [npl][B*tq][H*128] (scaled), kp [npl][B*tk][H*128], vt [npl][B*H*128][round_up(tk,64)].
+int attention_tc_planes_launch(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfloat16* vt, const int32_t* key_lens,
+                               int batch, int heads, int tq, int tk, float* ctx, int64_t ldc, __nv_bfloat16* ctx_planes,
+                               int64_t ldp, int out_nplanes, int mode, cudaStream_t st) {
+  if (batch <= 0 || tq <= 0) return FA_OK;
+  if (!qp || !kp || !vt || !key_lens || tk <= 0) return FA_ERR_ARG;
+  const int npl = mode == FA_GEMM_BF16X1 ? 1 : 2;
+  const int d = heads * AT_D;
+  const int tkp = (tk + 63) / 64 * 64;
+  const int64_t mq = (int64_t)batch * tq, mk = (int64_t)batch * tk, mv = (int64_t)batch * d;
   CUtensorMap mq_map, mk_map, mv_map;
   FA_RETURN_IF_ERR(make_bf16_map(&mq_map, qp, (uint64_t)mq * npl, (uint64_t)d, (uint64_t)d, AT_BQ));
   FA_RETURN_IF_ERR(make_bf16_map(&mk_map, kp, (uint64_t)mk * npl, (uint64_t)d, (uint64_t)d, AT_BKEY));
@@ -363,15 +386,15 @@ int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk
   p.ctx = ctx; p.ldc = ldc; p.ctx_planes = ctx_planes; p.ldp = ldp; p.out_nplanes = out_nplanes;
   dim3 grid((tq + AT_BQ - 1) / AT_BQ, heads, batch);
   if (npl == 1) {
-    constexpr size_t smem = 2 * AT_Q_KBLK + 2 * (2 * AT_K_KBLK + AT_V_TILE) + AT_P_TILE + 1024 + 256;
+    constexpr size_t smem = 2 * AT_Q_KBLK + 2 * (2 * AT_K_KBLK + AT_V_TILE) + AT_P_TILE + 1024 + 256 + 1024;
     static bool done = false;
     if (!done) { FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
-    attention_tc_kernel<1><<<grid, 256, smem, st>>>(mq_map, mk_map, mv_map, p);
+    attention_tc_kernel<1><<<grid, 384, smem, st>>>(mq_map, mk_map, mv_map, p);
   } else {
-    constexpr size_t smem = 2 * (2 * AT_Q_KBLK + 2 * (2 * AT_K_KBLK + AT_V_TILE) + AT_P_TILE) + 1024 + 256;
+    constexpr size_t smem = 2 * (2 * AT_Q_KBLK + 2 * (2 * AT_K_KBLK + AT_V_TILE) + AT_P_TILE) + 1024 + 256 + 1024;
     static bool done = false;
     if (!done) { FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
-    attention_tc_kernel<2><<<grid, 256, smem, st>>>(mq_map, mk_map, mv_map, p);
+    attention_tc_kernel<2><<<grid, 384, smem, st>>>(mq_map, mk_map, mv_map, p);
   }
   FA_CHECK_LAUNCH();
   return FA_OK;

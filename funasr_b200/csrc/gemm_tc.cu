@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace fa {
 
@@ -43,10 +44,130 @@ struct TcParams {
   __nv_bfloat16* out_planes;             // bf16 plane output [3][M][ldo] (or null)
   int64_t ldo; int out_nplanes;
   int tiles_m, tiles_n;
+  AttnSinks att;                          // optional: route column ranges to attention operand planes
 };
 
 __constant__ int c_term_a[6] = {0, 0, 1, 1, 0, 2};
 __constant__ int c_term_w[6] = {0, 1, 0, 1, 2, 0};
+
+// Epilogue of one accumulator tile for one thread (= one output row): TMEM -> registers -> bias / ReLU / residuals ->
+// fp32 rows, bf16 planes, or attention-operand planes.  tmem_acc = accumulator base + (lane quarter << 16).
+template <int BN>
+__device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t tmem_acc, int64_t row, int tile_col0) {
+  const bool row_ok = row < p.M;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_acc + c0, r);
+    const int col0 = tile_col0 + c0;
+    if (row_ok && col0 < p.N) {
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const bool full = col0 + 32 <= p.N;
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.r1) {
+        const float* rr = p.r1 + row * p.ldr1 + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (full) { const float4 t = __ldg(reinterpret_cast<const float4*>(rr + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+          else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) v[j + e] += __ldg(rr + j + e); }
+        }
+      }
+      if (p.r2) {
+        const float* rr = p.r2 + row * p.ldr2 + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (full) { const float4 t = __ldg(reinterpret_cast<const float4*>(rr + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+          else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) v[j + e] += __ldg(rr + j + e); }
+        }
+      }
+      if (p.att.enabled) {
+        // Attention-operand epilogue: this 32-column chunk belongs to exactly one of q / k / v (ranges are multiples
+        // of 512).  q (pre-scaled by d_k^-0.5, attention.py:324) and k go out as bf16 planes [npl][M][512]; v goes out
+        // transposed per head as bf16 planes [npl][B*H*128][t_pad] (keys contiguous: K-major B operand of P.V) and, when
+        // requested, as fp32 for the FSMN branch.  The fp32 q/k never touch HBM.
+        const AttnSinks& a = p.att;
+        if (col0 >= a.q0 && col0 < a.q0 + a.width) {
+          __nv_bfloat16* d0 = a.q_planes + row * a.width + (col0 - a.q0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float x0 = __fmul_rn(v[j], a.qscale), x1 = __fmul_rn(v[j + 1], a.qscale);
+            for (int pl = 0; pl < a.npl; ++pl) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+              *reinterpret_cast<__nv_bfloat162*>(d0 + pl * (p.M * a.width) + j) = __halves2bfloat162(h0, h1);
+              x0 -= __bfloat162float(h0); x1 -= __bfloat162float(h1);
+            }
+          }
+        } else if (col0 >= a.k0 && col0 < a.k0 + a.width) {
+          __nv_bfloat16* d0 = a.k_planes + row * a.width + (col0 - a.k0);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float x0 = v[j], x1 = v[j + 1];
+            for (int pl = 0; pl < a.npl; ++pl) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+              *reinterpret_cast<__nv_bfloat162*>(d0 + pl * (p.M * a.width) + j) = __halves2bfloat162(h0, h1);
+              x0 -= __bfloat162float(h0); x1 -= __bfloat162float(h1);
+            }
+          }
+        } else if (col0 >= a.v0 && col0 < a.v0 + a.width) {
+          const int bb = (int)(row / a.t_rows), tt = (int)(row - (int64_t)bb * a.t_rows);
+          const int cv = col0 - a.v0;                       // h*128 + d
+          __nv_bfloat16* d0 = a.vt_planes + ((int64_t)bb * a.width + cv) * a.t_pad + tt;
+          const int64_t plane = (int64_t)(p.M / a.t_rows) * a.width * a.t_pad;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x0 = v[j];
+            for (int pl = 0; pl < a.npl; ++pl) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0);
+              d0[pl * plane + (int64_t)j * a.t_pad] = h0;   // lanes = consecutive t: 64-byte coalesced segments
+              x0 -= __bfloat162float(h0);
+            }
+          }
+          if (p.C) {
+            float* cr = p.C + row * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      } else if (p.C) {
+        float* cr = p.C + row * p.ldc + col0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (full) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) cr[j + e] = v[j + e]; }
+        }
+      }
+      if (p.out_planes && full) {
+        // x = hi + mid + lo split for a following GEMM (planes [3][M][ldo])
+        __nv_bfloat16* o0 = p.out_planes + row * p.ldo + col0;
+        const int64_t plane = p.M * p.ldo;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float a = v[j], b = v[j + 1];
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
+          *reinterpret_cast<__nv_bfloat162*>(o0 + j) = __halves2bfloat162(h0, h1);
+          if (p.out_nplanes > 1) {
+            a -= __bfloat162float(h0); b -= __bfloat162float(h1);
+            const __nv_bfloat16 m0 = __float2bfloat16_rn(a), m1 = __float2bfloat16_rn(b);
+            *reinterpret_cast<__nv_bfloat162*>(o0 + plane + j) = __halves2bfloat162(m0, m1);
+            if (p.out_nplanes > 2) {
+              a -= __bfloat162float(m0); b -= __bfloat162float(m1);
+              *reinterpret_cast<__nv_bfloat162*>(o0 + 2 * plane + j) = __halves2bfloat162(__float2bfloat16_rn(a), __float2bfloat16_rn(b));
+            }
+          }
+        }
+      }
+    }
+  }
+}
 
 template <int BN, int STAGES, int APL, int WPL>  // APL / WPL: A / W planes resident per stage
 __global__ void __launch_bounds__(256, 1)
@@ -141,72 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int64_t row = (int64_t)tm * TC_BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c0, r);
-        const int col0 = tn * BN + c0;
-        if (row_ok && col0 < p.N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const bool full = col0 + 32 <= p.N;
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.r1) {
-            const float* rr = p.r1 + row * p.ldr1 + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (full) { const float4 t = __ldg(reinterpret_cast<const float4*>(rr + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
-              else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) v[j + e] += __ldg(rr + j + e); }
-            }
-          }
-          if (p.r2) {
-            const float* rr = p.r2 + row * p.ldr2 + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (full) { const float4 t = __ldg(reinterpret_cast<const float4*>(rr + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
-              else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) v[j + e] += __ldg(rr + j + e); }
-            }
-          }
-          if (p.C) {
-            float* cr = p.C + row * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (full) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) cr[j + e] = v[j + e]; }
-            }
-          }
-          if (p.out_planes && full) {
-            // x = hi + mid + lo split for a following GEMM (planes [3][M][ldo])
-            __nv_bfloat16* o0 = p.out_planes + row * p.ldo + col0;
-            const int64_t plane = p.M * p.ldo;
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float a = v[j], b = v[j + 1];
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-              *reinterpret_cast<__nv_bfloat162*>(o0 + j) = __halves2bfloat162(h0, h1);
-              if (p.out_nplanes > 1) {
-                a -= __bfloat162float(h0); b -= __bfloat162float(h1);
-                const __nv_bfloat16 m0 = __float2bfloat16_rn(a), m1 = __float2bfloat16_rn(b);
-                *reinterpret_cast<__nv_bfloat162*>(o0 + plane + j) = __halves2bfloat162(m0, m1);
-                if (p.out_nplanes > 2) {
-                  a -= __bfloat162float(m0); b -= __bfloat162float(m1);
-                  *reinterpret_cast<__nv_bfloat162*>(o0 + 2 * plane + j) = __halves2bfloat162(__float2bfloat16_rn(a), __float2bfloat16_rn(b));
-                }
-              }
-            }
-          }
-        }
-      }
+      epilogue_row<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32 + lane, tn * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);        // 4 arrivals (one per epilogue warp) free the accumulator
@@ -219,6 +275,120 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ cta_group::2 variant
+// CTA pair (cluster 2x1x1) computes a 256 x 256 output tile: each CTA stages ITS 128 rows of A and ITS 128 rows of W
+// (half of the N tile) per k-block, so operand bytes per MMA cycle are half those of the single-CTA 128x256 tile
+// (64 KB per k-block per SM for the three x3 terms) and three stages fit.  The leader issues
+// tcgen05.mma.cta_group::2 (M=256); each CTA drains its own 128 TMEM lanes in the epilogue.
+template <int STAGES, int PL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int BN = 256;
+  constexpr uint32_t TILE_BYTES = 128 * TC_BK * 2;                 // 16 KB: 128 rows x 64 bf16
+  constexpr uint32_t STAGE_BYTES = 2 * PL * TILE_BYTES;            // A planes + W-half planes of this CTA
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2] (used in the leader only: 8 arrivals = 4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_tiles = p.tiles_m * p.tiles_n;          // 256 x 256 pair tiles
+  const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int k_blocks = p.Kp / TC_BK;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_base_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // barriers of both CTAs are initialised before any remote use
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);       // bytes of BOTH CTAs land on the leader's barrier
+          unsigned char* st = smem + stage * STAGE_BYTES;
+#pragma unroll
+          for (int pl = 0; pl < PL; ++pl)
+            tma_load_2d_2sm(st + pl * TILE_BYTES, &map_a, &full_bar[stage], kb * TC_BK,
+                            (int)(pl * p.a_plane_rows + (int64_t)tm * 256 + rank * 128));
+#pragma unroll
+          for (int pl = 0; pl < PL; ++pl)
+            tma_load_2d_2sm(st + (PL + pl) * TILE_BYTES, &map_w, &full_bar[stage], kb * TC_BK,
+                            pl * p.w_plane_rows + tn * BN + (int)rank * 128);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+          for (int t = 0; t < p.n_terms; ++t) {
+            const uint64_t da = make_sw128_desc(st + c_term_a[t] * TILE_BYTES);
+            const uint64_t dw = make_sw128_desc(st + (PL + c_term_w[t]) * TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / TC_UK; ++k) umma_bf16_2sm(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | t | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);              // frees the slot in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);                  // accumulators complete in both CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (each CTA: its 128 rows) =====================
+    const int q = warp - 4;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_row<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * 256 + rank * 128 + q * 32 + lane, tn * BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // the peer may still arrive on / read this CTA's shared memory
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BN);
   }
 }
 
@@ -309,10 +479,37 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcPara
   return FA_OK;
 }
 
+template <int STAGES, int PL>
+static int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (2 * PL * 128 * TC_BK * 2) + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    FA_CUDA_OK(cudaGetDevice(&dev));
+    FA_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int pairs = tiles < n_sm / 2 ? tiles : n_sm / 2;
+  gemm_tc2_kernel<STAGES, PL><<<2 * pairs, 256, smem, st>>>(ma, mw, p);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+static bool use_2cta() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FA_GEMM_2CTA"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 // A planes already split: a_planes [npl][M][Kp]
 int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
                           const float* r2, int64_t ld2, float* y, int64_t ldy, __nv_bfloat16* out_planes, int64_t ldo,
-                          int mode, cudaStream_t st) {
+                          int mode, cudaStream_t st, const AttnSinks* att) {
   if (M <= 0) return FA_OK;
   if (!lin.w_planes || !a_planes) return FA_ERR_ARG;
   const int N = lin.out_f, Kp = lin.in_pad;
@@ -322,6 +519,21 @@ int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLine
   const int npl = planes_for_mode(mode);
   // 128x256 tiles halve the operand bytes per MMA cycle (the 128x128 tile is L2-bandwidth bound); used when N splits
   // evenly and there are enough tiles to fill the machine.  x6 keeps 128x128 (three planes per operand do not fit twice).
+  if (use_2cta() && npl <= 2 && N % 256 == 0 && M >= 256) {
+    // cta_group::2: 256 x 256 pair tiles (see gemm_tc2_kernel)
+    CUtensorMap ma2, mw2;
+    FA_RETURN_IF_ERR(make_bf16_map(&ma2, a_planes, (uint64_t)M * npl, (uint64_t)Kp, (uint64_t)Kp, 128));
+    FA_RETURN_IF_ERR(make_bf16_map(&mw2, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, 128));
+    TcParams p2;
+    p2.M = M; p2.N = N; p2.Kp = Kp; p2.a_plane_rows = M; p2.w_plane_rows = N;
+    p2.n_terms = mode == FA_GEMM_BF16X1 ? 1 : 3;
+    p2.relu = relu; p2.bias = lin.b; p2.r1 = r1; p2.ldr1 = ld1; p2.r2 = r2; p2.ldr2 = ld2; p2.C = y; p2.ldc = ldy;
+    p2.out_planes = out_planes; p2.ldo = ldo; p2.out_nplanes = npl;
+    p2.tiles_m = (int)((M + 255) / 256); p2.tiles_n = N / 256;
+    if (att) { p2.att = *att; p2.att.enabled = 1; } else { p2.att = AttnSinks{}; }
+    if (att && (att->width % 32 != 0 || att->t_rows <= 0 || M % att->t_rows != 0)) return FA_ERR_UNSUPPORTED;
+    return npl == 1 ? launch_cfg2<6, 1>(ma2, mw2, p2, st) : launch_cfg2<3, 2>(ma2, mw2, p2, st);
+  }
   const bool wide = (npl <= 2) && (N % 256 == 0) && (N >= 1024);
   const int BN = wide ? 256 : 128;
   CUtensorMap ma, mw;
@@ -333,6 +545,8 @@ int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLine
   p.relu = relu; p.bias = lin.b; p.r1 = r1; p.ldr1 = ld1; p.r2 = r2; p.ldr2 = ld2; p.C = y; p.ldc = ldy;
   p.out_planes = out_planes; p.ldo = ldo; p.out_nplanes = npl;
   p.tiles_m = (int)((M + TC_BM - 1) / TC_BM); p.tiles_n = (N + BN - 1) / BN;
+  if (att) { p.att = *att; p.att.enabled = 1; } else { p.att = AttnSinks{}; }
+  if (att && (N % 32 != 0 || att->width % 32 != 0 || att->t_rows <= 0 || M % att->t_rows != 0)) return FA_ERR_UNSUPPORTED;
   if (out_planes && (N % 32 != 0)) return FA_ERR_UNSUPPORTED;
   if (wide) return npl == 1 ? launch_cfg<256, 4, 1, 1>(ma, mw, p, st) : launch_cfg<256, 2, 2, 2>(ma, mw, p, st);
   switch (npl) {
@@ -362,7 +576,7 @@ int gemm_tc_launch(const float* x, int64_t ldx, int64_t rows, const FaLinear& li
   __nv_bfloat16* planes = local.take<__nv_bfloat16>((size_t)npl * rows * lin.in_pad);
   if (!local.ok()) return FA_ERR_WORKSPACE;
   FA_RETURN_IF_ERR(split_rows_launch(x, ldx, rows, lin.in_f, lin.in_pad, npl, planes, st));
-  return gemm_tc_planes_launch(planes, rows, lin, relu, r1, ld1, r2, ld2, y, ldy, nullptr, 0, mode, st);
+  return gemm_tc_planes_launch(planes, rows, lin, relu, r1, ld1, r2, ld2, y, ldy, nullptr, 0, mode, st, nullptr);
 }
 
 }  // namespace fa

@@ -16,14 +16,31 @@ size_t gemm_tc_scratch_bytes(int64_t max_rows, int max_k, int mode);
 int gemm_tc_launch(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, const float* r1,
                    int64_t ld1, const float* r2, int64_t ld2, float* y, int64_t ldy, int mode, Arena* scratch,
                    cudaStream_t st);
+// Column-range sinks of a GEMM epilogue feeding the tensor-core attention (gemm_tc.cu): columns [q0, q0+width) -> q planes
+// (scaled), [k0, k0+width) -> k planes, [v0, v0+width) -> transposed v planes (+ fp32 into the GEMM's C when C != null).
+// A range is disabled by placing it outside [0, N) (e.g. -1000000).
+struct AttnSinks {
+  int enabled = 0;
+  int q0 = -1000000, k0 = -1000000, v0 = -1000000;
+  int width = 512;             // heads * 128
+  int npl = 2;                 // planes written
+  int t_rows = 1, t_pad = 64;  // rows per utterance (v rows = keys), padded key pitch of the transposed planes
+  float qscale = 1.f;
+  __nv_bfloat16* q_planes = nullptr;   // [npl][M][width]
+  __nv_bfloat16* k_planes = nullptr;   // [npl][M][width]
+  __nv_bfloat16* vt_planes = nullptr;  // [npl][B*width][t_pad]
+};
 // tcgen05 attention (attention_tc.cu); ctx fp32 and/or bf16 planes [npl][B*tq][ldp]
+int attention_tc_planes_launch(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfloat16* vt, const int32_t* key_lens,
+                               int batch, int heads, int tq, int tk, float* ctx, int64_t ldc, __nv_bfloat16* ctx_planes,
+                               int64_t ldp, int out_nplanes, int mode, cudaStream_t st);
 size_t attention_tc_scratch_bytes(int batch, int heads, int tq, int tk, int mode);
 int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                         const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
                         __nv_bfloat16* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st);
 int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
                           const float* r2, int64_t ld2, float* y, int64_t ldy, __nv_bfloat16* out_planes, int64_t ldo,
-                          int mode, cudaStream_t st);
+                          int mode, cudaStream_t st, const AttnSinks* att = nullptr);
 int split_rows_launch(const float* x, int64_t ldx, int64_t rows, int cols, int cols_pad, int nplanes, __nv_bfloat16* planes,
                       cudaStream_t st);
 int attention_f32_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <string.h>
+#include <math.h>
 
 namespace fa {
 
@@ -38,6 +39,9 @@ static size_t enc_plan(int batch, int t_max, int din, int mode) {
     s.take(3ull * M * 512 * 2);    // ctx planes
     s.take(3ull * M * 2048 * 2);   // h planes
     s.take(3ull * M * 576 * 2);    // LN output planes
+    s.take(2ull * M * 512 * 2);    // q planes (scaled)
+    s.take(2ull * M * 512 * 2);    // k planes
+    s.take(2ull * batch * 512 * (size_t)((t_max + 63) / 64 * 64) * 2);   // v planes, transposed per head
   }
   s.take(enc_scratch_bytes(batch, t_max, 4, mode));
   return s.off + 256;
@@ -74,6 +78,10 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
   __nv_bfloat16* ctx_planes = tc ? a.take<__nv_bfloat16>(3ull * M * 512) : nullptr;
   __nv_bfloat16* h_planes = tc ? a.take<__nv_bfloat16>(3ull * M * 2048) : nullptr;
   __nv_bfloat16* u_planes = tc ? a.take<__nv_bfloat16>(3ull * M * 576) : nullptr;
+  const int t_pad = (t_max + 63) / 64 * 64;
+  __nv_bfloat16* q_planes = tc ? a.take<__nv_bfloat16>(2ull * M * 512) : nullptr;
+  __nv_bfloat16* k_planes = tc ? a.take<__nv_bfloat16>(2ull * M * 512) : nullptr;
+  __nv_bfloat16* vt_planes = tc ? a.take<__nv_bfloat16>(2ull * batch * 512 * (size_t)t_pad) : nullptr;
   const size_t sb = enc_scratch_bytes(batch, t_max, enc->heads, gemm_mode);
   char* sp = a.take<char>(sb);
   if (!a.ok()) return FA_ERR_WORKSPACE;
@@ -90,8 +98,16 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
     const bool first = embed && l == 0;
     FA_RETURN_IF_ERR(layernorm_launch(first ? feats : x, M, L.norm1, tc ? nullptr : u, first ? enc->pe_inv_timescales : nullptr,
                                       first ? sqrtf((float)D) : 1.f, t_max, st, u_planes, npl, L.qkv.in_pad));
-    if (tc) FA_RETURN_IF_ERR(gemm_tc_planes_launch(u_planes, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, nullptr, 0, gemm_mode, st));
-    else FA_RETURN_IF_ERR(linear(u, in, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, gemm_mode, &scratch, st));
+    if (tc) {
+      // QKV GEMM epilogue emits the attention operands directly: q (x d_k^-0.5) / k as bf16 planes, v transposed per head
+      // as bf16 planes plus fp32 v (the only fp32 columns written) for the FSMN branch
+      AttnSinks sk;
+      sk.q0 = 0; sk.k0 = D; sk.v0 = 2 * D; sk.width = D; sk.npl = npl < 2 ? npl : 2; sk.t_rows = t_max; sk.t_pad = t_pad;
+      sk.qscale = (float)(1.0 / sqrt(128.0)); sk.q_planes = q_planes; sk.k_planes = k_planes; sk.vt_planes = vt_planes;
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(u_planes, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, nullptr, 0, gemm_mode, st, &sk));
+    } else {
+      FA_RETURN_IF_ERR(linear(u, in, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, gemm_mode, &scratch, st));
+    }
     FA_RETURN_IF_ERR(fsmn_launch(qkv + 2 * D, 3 * D, lens, batch, t_max, D, L.fsmn_w, enc->fsmn_k, nullptr, 0, mem, D, st));
     // x2 = (residual if in_size == size) + (linear_out(ctx) + fsmn_memory)     encoder.py:120-137, attention.py:327
     float* x2 = (x == xa) ? xb : xa;
@@ -107,8 +123,8 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
     } else {
       // tensor-core path: attention emits the context as bf16 planes (A operand of linear_out); FFN w_1 emits its
       // ReLU output as planes for w_2 — neither intermediate makes an fp32 round trip through HBM
-      FA_RETURN_IF_ERR(attention_tc_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, t_max, t_max,
-                                           nullptr, 0, ctx_planes, D, npl, gemm_mode, &scratch, st));
+      FA_RETURN_IF_ERR(attention_tc_planes_launch(q_planes, k_planes, vt_planes, lens, batch, enc->heads, t_max, t_max, nullptr, 0,
+                                                  ctx_planes, D, npl, gemm_mode, st));
       FA_RETURN_IF_ERR(gemm_tc_planes_launch(ctx_planes, M, L.out, 0, mem, D, res, D, x2, D, nullptr, 0, gemm_mode, st));
       if (L.w1.out_f != L.w2.in_pad || L.w1.in_pad != D) return FA_ERR_UNSUPPORTED;
       FA_RETURN_IF_ERR(layernorm_launch(x2, M, L.norm2, nullptr, nullptr, 1.f, t_max, st, u_planes, npl, D));
@@ -163,7 +179,8 @@ static size_t dec_scratch_bytes(int batch, int t_max, int n_max, int mode) {
   const int64_t Mq = (int64_t)batch * n_max, Mk = (int64_t)batch * t_max;
   return max_sz(gemm_tc_scratch_bytes(Mq > Mk ? Mq : Mk, 2048, mode), attention_tc_scratch_bytes(batch, 4, n_max, t_max, mode));
 }
-static size_t dec_plan(int64_t Mq, int64_t Mk, int vocab, int mode, size_t dec_scratch) {
+static size_t dec_plan(int batch, int t_max, int n_max, int vocab, int mode, size_t dec_scratch) {
+  const int64_t Mq = (int64_t)batch * n_max, Mk = (int64_t)batch * t_max;
   ArenaSizer s;
   s.take(Mq * 512ull * 4);   // ya
   s.take(Mq * 512ull * 4);   // yb
@@ -181,6 +198,9 @@ static size_t dec_plan(int64_t Mq, int64_t Mk, int vocab, int mode, size_t dec_s
     s.take(3ull * Mk * 512 * 2);   // enc planes (split once, reused by the 16 kv GEMMs)
     s.take(3ull * Mq * 512 * 2);   // LN output planes
     s.take(3ull * Mq * 2048 * 2);  // FFN hidden planes
+    s.take(2ull * Mq * 512 * 2);   // q planes
+    s.take(2ull * Mk * 512 * 2);   // k planes
+    s.take(2ull * batch * 512 * (size_t)((t_max + 63) / 64 * 64) * 2);   // v planes, transposed per head
   }
   s.take(dec_scratch);
   return s.off + 256;
@@ -188,7 +208,7 @@ static size_t dec_plan(int64_t Mq, int64_t Mk, int vocab, int mode, size_t dec_s
 
 extern "C" size_t fa_paraformer_decoder_workspace_bytes(int32_t batch, int32_t t_max, int32_t n_max, int32_t vocab,
                                                         int32_t gemm_mode) {
-  return dec_plan((int64_t)batch * n_max, (int64_t)batch * t_max, vocab, gemm_mode, dec_scratch_bytes(batch, t_max, n_max, gemm_mode));
+  return dec_plan(batch, t_max, n_max, vocab, gemm_mode, dec_scratch_bytes(batch, t_max, n_max, gemm_mode));
 }
 
 static int dec_ffn(const FaDecLayer& L, const float* y, int64_t Mq, float* t1, float* hq, float* f, int mode,
@@ -239,6 +259,10 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
   __nv_bfloat16* enc_planes = tc ? a.take<__nv_bfloat16>(3ull * Mk * 512) : nullptr;
   __nv_bfloat16* t1_planes = tc ? a.take<__nv_bfloat16>(3ull * Mq * 512) : nullptr;
   __nv_bfloat16* hq_planes = tc ? a.take<__nv_bfloat16>(3ull * Mq * 2048) : nullptr;
+  const int t_pad = (t_max + 63) / 64 * 64;
+  __nv_bfloat16* q_planes = tc ? a.take<__nv_bfloat16>(2ull * Mq * 512) : nullptr;
+  __nv_bfloat16* k_planes = tc ? a.take<__nv_bfloat16>(2ull * Mk * 512) : nullptr;
+  __nv_bfloat16* vt_planes = tc ? a.take<__nv_bfloat16>(2ull * batch * 512 * (size_t)t_pad) : nullptr;
   const size_t sb = dec_scratch_bytes(batch, t_max, n_max, gemm_mode);
   char* sp = a.take<char>(sb);
   if (!a.ok()) return FA_ERR_WORKSPACE;
@@ -263,7 +287,9 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
     // x = residual + src_attn(LN3(x), memory)    decoder.py:109-118, attention.py:796-813
     if (tc) {
       FA_RETURN_IF_ERR(layernorm_launch(x2, Mq, L.norm3, nullptr, nullptr, 1.f, 1, st, t1_planes, npl, D));
-      FA_RETURN_IF_ERR(gemm_tc_planes_launch(t1_planes, Mq, L.q, 0, nullptr, 0, nullptr, 0, qd, D, nullptr, 0, gemm_mode, st));
+      AttnSinks sq;                       // q -> scaled bf16 planes only (no fp32 round trip)
+      sq.q0 = 0; sq.width = D; sq.npl = npl < 2 ? npl : 2; sq.t_rows = n_max; sq.qscale = (float)(1.0 / sqrt(128.0)); sq.q_planes = q_planes;
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(t1_planes, Mq, L.q, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, gemm_mode, st, &sq));
     } else {
       FA_RETURN_IF_ERR(layernorm_launch(x2, Mq, L.norm3, t1, nullptr, 1.f, 1, st));
       FA_RETURN_IF_ERR(linear(t1, D, Mq, L.q, 0, nullptr, 0, nullptr, 0, qd, D, gemm_mode, &scratch, st));
@@ -278,9 +304,12 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
                                             D, st));
       FA_RETURN_IF_ERR(linear(ctx, D, Mq, L.out, 0, res, D, nullptr, 0, dst, ldd, gemm_mode, &scratch, st));
     } else {
-      FA_RETURN_IF_ERR(gemm_tc_planes_launch(enc_planes, Mk, L.kv, 0, nullptr, 0, nullptr, 0, kv, 2 * D, nullptr, 0, gemm_mode, st));
-      FA_RETURN_IF_ERR(attention_tc_launch(qd, D, kv, 2 * D, kv + D, 2 * D, enc_lens, batch, dec->heads, n_max, t_max, nullptr, 0,
-                                           ctx_planes, D, npl, gemm_mode, &scratch, st));
+      AttnSinks skv;                      // k -> planes, v -> transposed planes; nothing in fp32
+      skv.k0 = 0; skv.v0 = D; skv.width = D; skv.npl = npl < 2 ? npl : 2; skv.t_rows = t_max; skv.t_pad = t_pad;
+      skv.k_planes = k_planes; skv.vt_planes = vt_planes;
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(enc_planes, Mk, L.kv, 0, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, gemm_mode, st, &skv));
+      FA_RETURN_IF_ERR(attention_tc_planes_launch(q_planes, k_planes, vt_planes, enc_lens, batch, dec->heads, n_max, t_max, nullptr, 0,
+                                                  ctx_planes, D, npl, gemm_mode, st));
       FA_RETURN_IF_ERR(gemm_tc_planes_launch(ctx_planes, Mq, L.out, 0, res, D, nullptr, 0, dst, ldd, nullptr, 0, gemm_mode, st));
     }
     *x_self_out = x2;

@@ -530,7 +530,8 @@ class ContextualParaformerB200(ParaformerB200):
         for i, h in enumerate(hw_list):
             pad[i, : len(h)] = torch.tensor(h, device=dev)
         packed = torch.nn.utils.rnn.pack_padded_sequence(self.bias_embed(pad), lens, batch_first=True, enforce_sorted=False)
-        _, (h_n, _) = self.bias_encoder(packed)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # cuDNN RNNs default to TF32: keep fp32
+            _, (h_n, _) = self.bias_encoder(packed)
         return h_n[0]
 
     def inference(self, data_in, data_lengths=None, key: list = None, tokenizer=None, frontend=None, **kwargs):
