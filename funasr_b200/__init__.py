@@ -14,5 +14,6 @@ from .modules import (CifPredictorV2B200, ParaformerB200, ParaformerSANMDecoderB
 from .engine import FrontendEngine, ParaformerEngine, SenseVoiceEngine  # noqa: F401
 from .synth import SENSEVOICE_SMALL, SENSEVOICE_TINY, SenseVoiceConfig  # noqa: F401
 from .sharding import shard_utterances, gather_token_ids  # noqa: F401
+from .batching import bucket_by_length, padding_efficiency, run_bucketed  # noqa: F401
 
 __version__ = "0.1.0"

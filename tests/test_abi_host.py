@@ -175,3 +175,21 @@ def test_plugs_into_reference_tables_and_automodel_build():
         for (tb, key), cls in saved.items():
             if cls is not None:
                 getattr(tables, tb)[key] = cls
+
+
+def test_bucket_by_length_config3():
+    """BASELINE config 3: 512 utterances, durations ~U[5,30] s (seed 1234): buckets are a partition, respect the caps,
+    and waste little padding; run_bucketed restores the input order."""
+    from funasr_b200.batching import bucket_by_length, padding_efficiency, run_bucketed
+    g = torch.Generator().manual_seed(1234)
+    n = [int(x) for x in ((5 + 25 * torch.rand(512, generator=g)) * 16000).tolist()]
+    for shard, mb, eff in ((n, 64, 0.9), (n[::8], 16, 0.85)):      # whole job / one GPU's shard of 64
+        bk = bucket_by_length(shard, max_batch=mb, max_frames=mb * 500)
+        assert sorted(i for b in bk for i in b) == list(range(len(shard)))
+        for b in bk:
+            t = [num_lfr_frames(shard[i]) for i in b]
+            assert len(b) <= mb and len(b) * max(t) <= mb * 500
+        assert padding_efficiency(shard, bk) > eff
+    fake = lambda batch: [[int(w.shape[-1]) % 97] for w in batch]
+    wavs = [torch.zeros(k) for k in n[:50]]
+    assert run_bucketed(wavs, fake, max_batch=8) == [[k % 97] for k in n[:50]]
