@@ -239,37 +239,51 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_wait(o_full, 0);
       tc_fence_after();
     }
-    // ---- epilogue: O / l, this thread's 64 of the 128 head dims
-    const int qrow = q0 + r;
+    // ---- epilogue: O / l for this warp's 32 rows x 64 head dims, staged through shared memory (the K/V ring is dead once
+    //      o_full has fired) so that the context rows leave as coalesced 8-byte (bf16 planes) / 16-byte (fp32) stores
     const float inv = l > 0.f ? 1.0f / l : 0.f;
-    const int64_t grow = (int64_t)b * p.tq + qrow;
+    float* stage = reinterpret_cast<float*>(sKV) + (warp - 4) * (32 * 36);
+    const int64_t grow0 = (int64_t)b * p.tq + q0 + qw * 32;
 #pragma unroll 1
     for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
-      uint32_t v[32];
-      if (nc > 0) tmem_ld_32x32(tmem_o + lane_addr + c0, v);
-      if (qrow < p.tq) {
-        float o[32];
+      {
+        uint32_t v[32];
+        if (nc > 0) tmem_ld_32x32(tmem_o + lane_addr + c0, v);
+        float* srow = stage + lane * 36;
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) o[jj] = nc > 0 ? __uint_as_float(v[jj]) * inv : 0.f;
-        if (p.ctx) {
-          float* dst = p.ctx + grow * p.ldc + h * AT_D + c0;
-#pragma unroll
-          for (int jj = 0; jj < 32; jj += 4) *reinterpret_cast<float4*>(dst + jj) = make_float4(o[jj], o[jj + 1], o[jj + 2], o[jj + 3]);
+        for (int jj = 0; jj < 32; jj += 4) {
+          float4 o4;
+          o4.x = nc > 0 ? __uint_as_float(v[jj]) * inv : 0.f;
+          o4.y = nc > 0 ? __uint_as_float(v[jj + 1]) * inv : 0.f;
+          o4.z = nc > 0 ? __uint_as_float(v[jj + 2]) * inv : 0.f;
+          o4.w = nc > 0 ? __uint_as_float(v[jj + 3]) * inv : 0.f;
+          *reinterpret_cast<float4*>(srow + jj) = o4;
         }
+      }
+      __syncwarp();
+      const int rr0 = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rr0;
+        if (q0 + qw * 32 + rr >= p.tq) break;
+        const float4 o4 = *reinterpret_cast<const float4*>(stage + rr * 36 + c4);
+        const int64_t grow = grow0 + rr;
+        const int col = h * AT_D + c0 + c4;
+        if (p.ctx) *reinterpret_cast<float4*>(p.ctx + grow * p.ldc + col) = o4;
         if (p.ctx_planes) {
-          __nv_bfloat16* d0 = p.ctx_planes + grow * p.ldp + h * AT_D + c0;
+          float x0 = o4.x, x1 = o4.y, x2 = o4.z, x3 = o4.w;
           const int64_t plane = (int64_t)p.batch * p.tq * p.ldp;
-#pragma unroll
-          for (int jj = 0; jj < 32; jj += 2) {
-            float a = o[jj], bb = o[jj + 1];
-            for (int pl = 0; pl < p.out_nplanes; ++pl) {
-              const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(bb);
-              *reinterpret_cast<__nv_bfloat162*>(d0 + pl * plane + jj) = __halves2bfloat162(ha, hb);
-              a -= __bfloat162float(ha); bb -= __bfloat162float(hb);
-            }
+          for (int pl = 0; pl < p.out_nplanes; ++pl) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1), h2 = __float2bfloat16_rn(x2), h3 = __float2bfloat16_rn(x3);
+            uint2 pk;
+            pk.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            pk.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+            *reinterpret_cast<uint2*>(p.ctx_planes + pl * plane + grow * p.ldp + col) = pk;
+            x0 -= __bfloat162float(h0); x1 -= __bfloat162float(h1); x2 -= __bfloat162float(h2); x3 -= __bfloat162float(h3);
           }
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();

@@ -50,122 +50,119 @@ struct TcParams {
 __constant__ int c_term_a[6] = {0, 0, 1, 1, 0, 2};
 __constant__ int c_term_w[6] = {0, 1, 0, 1, 2, 0};
 
-// Epilogue of one accumulator tile for one thread (= one output row): TMEM -> registers -> bias / ReLU / residuals ->
-// fp32 rows, bf16 planes, or attention-operand planes.  tmem_acc = accumulator base + (lane quarter << 16).
+// Epilogue of one accumulator tile for one warp (32 rows x BN columns), 32 columns at a time:
+//   phase 1  tcgen05.ld (thread = row) -> raw fp32 accumulators into a padded shared-memory tile [32][36]
+//   phase 2  re-read with the warp laid out as 4 rows x 8 float4 columns, so bias / residual loads and every store are
+//            fully coalesced 16-byte (fp32) or 8-byte (bf16 plane) accesses; V columns of the attention sink take a
+//            column-per-lane path that writes the per-head transposed planes as 4 consecutive keys (8 bytes) per store.
+// (The first version stored straight from the row-per-thread layout: 4-byte stores to 32 different lines per
+//  instruction made the GEMMs epilogue-bound — profiles/README.md.)
+constexpr int EPI_LD = 36;                       // padded row pitch (floats): 16-byte aligned, conflict-free float4 phases
+constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;     // 4.5 KB per epilogue warp
+
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_stride, int npl, float x0, float x1, float x2, float x3) {
+  for (int pl = 0; pl < npl; ++pl) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1), h2 = __float2bfloat16_rn(x2), h3 = __float2bfloat16_rn(x3);
+    uint2 pk;
+    pk.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    pk.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+    *reinterpret_cast<uint2*>(dst + pl * plane_stride) = pk;
+    x0 -= __bfloat162float(h0); x1 -= __bfloat162float(h1); x2 -= __bfloat162float(h2); x3 -= __bfloat162float(h3);
+  }
+}
+
 template <int BN>
-__device__ __forceinline__ void epilogue_row(const TcParams& p, uint32_t tmem_acc, int64_t row, int tile_col0) {
-  const bool row_ok = row < p.M;
+__device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane) {
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32(tmem_acc + c0, r);
+    {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + c0, r);
+      float* srow = stage + lane * EPI_LD;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    }
+    __syncwarp();
     const int col0 = tile_col0 + c0;
-    if (row_ok && col0 < p.N) {
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (col0 < p.N && row0 < p.M) {
       const bool full = col0 + 32 <= p.N;
-      if (p.bias) {
+      const AttnSinks& a = p.att;
+      const bool v_sink = a.enabled && col0 >= a.v0 && col0 < a.v0 + a.width;
+      if (v_sink) {
+        // transposed per-head V planes: lane = head dim, 4 consecutive keys per 8-byte store
+        const int cv = col0 - a.v0 + lane;                         // h*128 + d
+        const float bv = p.bias ? __ldg(p.bias + col0 + lane) : 0.f;
+        const int64_t plane = (int64_t)(p.M / a.t_rows) * a.width * a.t_pad;
+        const int bb0 = (int)(row0 / a.t_rows), tt0 = (int)(row0 - (int64_t)bb0 * a.t_rows);
+        const bool fast = ((tt0 & 3) == 0) && ((a.t_rows & 3) == 0) && (row0 + 32 <= p.M);
+#pragma unroll 1
+        for (int g = 0; g < 8; ++g) {
+          float x[4];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      }
-      if (p.r1) {
-        const float* rr = p.r1 + row * p.ldr1 + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (full) { const float4 t = __ldg(reinterpret_cast<const float4*>(rr + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
-          else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) v[j + e] += __ldg(rr + j + e); }
-        }
-      }
-      if (p.r2) {
-        const float* rr = p.r2 + row * p.ldr2 + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (full) { const float4 t = __ldg(reinterpret_cast<const float4*>(rr + j)); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
-          else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) v[j + e] += __ldg(rr + j + e); }
-        }
-      }
-      if (p.att.enabled) {
-        // Attention-operand epilogue: this 32-column chunk belongs to exactly one of q / k / v (ranges are multiples
-        // of 512).  q (pre-scaled by d_k^-0.5, attention.py:324) and k go out as bf16 planes [npl][M][512]; v goes out
-        // transposed per head as bf16 planes [npl][B*H*128][t_pad] (keys contiguous: K-major B operand of P.V) and, when
-        // requested, as fp32 for the FSMN branch.  The fp32 q/k never touch HBM.
-        const AttnSinks& a = p.att;
-        if (col0 >= a.q0 && col0 < a.q0 + a.width) {
-          __nv_bfloat16* d0 = a.q_planes + row * a.width + (col0 - a.q0);
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float x0 = __fmul_rn(v[j], a.qscale), x1 = __fmul_rn(v[j + 1], a.qscale);
-            for (int pl = 0; pl < a.npl; ++pl) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-              *reinterpret_cast<__nv_bfloat162*>(d0 + pl * (p.M * a.width) + j) = __halves2bfloat162(h0, h1);
-              x0 -= __bfloat162float(h0); x1 -= __bfloat162float(h1);
+          for (int i = 0; i < 4; ++i) { x[i] = stage[(4 * g + i) * EPI_LD + lane] + bv; if (p.relu) x[i] = fmaxf(x[i], 0.f); }
+          int tt = tt0 + 4 * g, bb = bb0;
+          if (tt >= a.t_rows) { bb += tt / a.t_rows; tt %= a.t_rows; }
+          if (fast) {                                              // 4 keys stay inside one utterance (t_rows % 4 == 0)
+            store_planes4(a.vt_planes + ((int64_t)bb * a.width + cv) * a.t_pad + tt, plane, a.npl, x[0], x[1], x[2], x[3]);
+          } else {
+            for (int i = 0; i < 4; ++i) {
+              const int64_t rw = row0 + 4 * g + i;
+              if (rw >= p.M) break;
+              const int b2 = (int)(rw / a.t_rows), t2 = (int)(rw - (int64_t)b2 * a.t_rows);
+              float xv = x[i];
+              for (int pl = 0; pl < a.npl; ++pl) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(xv);
+                a.vt_planes[pl * plane + ((int64_t)b2 * a.width + cv) * a.t_pad + t2] = h0;
+                xv -= __bfloat162float(h0);
+              }
             }
           }
-        } else if (col0 >= a.k0 && col0 < a.k0 + a.width) {
-          __nv_bfloat16* d0 = a.k_planes + row * a.width + (col0 - a.k0);
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float x0 = v[j], x1 = v[j + 1];
-            for (int pl = 0; pl < a.npl; ++pl) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-              *reinterpret_cast<__nv_bfloat162*>(d0 + pl * (p.M * a.width) + j) = __halves2bfloat162(h0, h1);
-              x0 -= __bfloat162float(h0); x1 -= __bfloat162float(h1);
-            }
-          }
-        } else if (col0 >= a.v0 && col0 < a.v0 + a.width) {
-          const int bb = (int)(row / a.t_rows), tt = (int)(row - (int64_t)bb * a.t_rows);
-          const int cv = col0 - a.v0;                       // h*128 + d
-          __nv_bfloat16* d0 = a.vt_planes + ((int64_t)bb * a.width + cv) * a.t_pad + tt;
-          const int64_t plane = (int64_t)(p.M / a.t_rows) * a.width * a.t_pad;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x0 = v[j];
-            for (int pl = 0; pl < a.npl; ++pl) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(x0);
-              d0[pl * plane + (int64_t)j * a.t_pad] = h0;   // lanes = consecutive t: 64-byte coalesced segments
-              x0 -= __bfloat162float(h0);
-            }
-          }
-          if (p.C) {
-            float* cr = p.C + row * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-        }
-      } else if (p.C) {
-        float* cr = p.C + row * p.ldc + col0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (full) *reinterpret_cast<float4*>(cr + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          else { for (int e = 0; e < 4; ++e) if (col0 + j + e < p.N) cr[j + e] = v[j + e]; }
         }
       }
-      if (p.out_planes && full) {
-        // x = hi + mid + lo split for a following GEMM (planes [3][M][ldo])
-        __nv_bfloat16* o0 = p.out_planes + row * p.ldo + col0;
-        const int64_t plane = p.M * p.ldo;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float a = v[j], b = v[j + 1];
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-          *reinterpret_cast<__nv_bfloat162*>(o0 + j) = __halves2bfloat162(h0, h1);
-          if (p.out_nplanes > 1) {
-            a -= __bfloat162float(h0); b -= __bfloat162float(h1);
-            const __nv_bfloat16 m0 = __float2bfloat16_rn(a), m1 = __float2bfloat16_rn(b);
-            *reinterpret_cast<__nv_bfloat162*>(o0 + plane + j) = __halves2bfloat162(m0, m1);
-            if (p.out_nplanes > 2) {
-              a -= __bfloat162float(m0); b -= __bfloat162float(m1);
-              *reinterpret_cast<__nv_bfloat162*>(o0 + 2 * plane + j) = __halves2bfloat162(__float2bfloat16_rn(a), __float2bfloat16_rn(b));
+      // coalesced row-major phase: 4 rows x 8 float4 per pass
+      const bool q_sink = a.enabled && col0 >= a.q0 && col0 < a.q0 + a.width;
+      const bool k_sink = a.enabled && col0 >= a.k0 && col0 < a.k0 + a.width;
+      const bool want_c = p.C != nullptr && (!a.enabled || v_sink);
+      if (want_c || p.out_planes || q_sink || k_sink) {
+        const int rr0 = lane >> 3, c4 = (lane & 7) * 4;
+        const int col = col0 + c4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) {
+          if (full) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          else { float* bp = reinterpret_cast<float*>(&bias4); for (int e = 0; e < 4; ++e) if (col + e < p.N) bp[e] = __ldg(p.bias + col + e); }
+        }
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + rr0;
+          const int64_t row = row0 + rr;
+          if (row >= p.M) break;
+          const float4 acc = *reinterpret_cast<const float4*>(stage + rr * EPI_LD + c4);
+          float v[4] = {acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w};
+          if (p.relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+          if (full) {
+            if (p.r1) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.r1 + row * p.ldr1 + col)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+            if (p.r2) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.r2 + row * p.ldr2 + col)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
+            if (want_c) {
+              if ((p.ldc & 3) == 0) *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = make_float4(v[0], v[1], v[2], v[3]);
+              else { float* cr = p.C + row * p.ldc + col; cr[0] = v[0]; cr[1] = v[1]; cr[2] = v[2]; cr[3] = v[3]; }
+            }
+            if (p.out_planes) store_planes4(p.out_planes + row * p.ldo + col, p.M * p.ldo, p.out_nplanes, v[0], v[1], v[2], v[3]);
+            if (q_sink) store_planes4(a.q_planes + row * a.width + (col - a.q0), p.M * a.width, a.npl, __fmul_rn(v[0], a.qscale),
+                                      __fmul_rn(v[1], a.qscale), __fmul_rn(v[2], a.qscale), __fmul_rn(v[3], a.qscale));
+            if (k_sink) store_planes4(a.k_planes + row * a.width + (col - a.k0), p.M * a.width, a.npl, v[0], v[1], v[2], v[3]);
+          } else {                                               // ragged N tail (e.g. vocab 8404 / 25055): scalar, bounds checked
+            for (int e = 0; e < 4; ++e) {
+              if (col + e >= p.N) break;
+              float x = v[e];
+              if (p.r1) x += __ldg(p.r1 + row * p.ldr1 + col + e);
+              if (p.r2) x += __ldg(p.r2 + row * p.ldr2 + col + e);
+              if (want_c) p.C[row * p.ldc + col + e] = x;
             }
           }
         }
       }
     }
+    __syncwarp();
   }
 }
 
@@ -181,6 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // 4 x [32][36] floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.tiles_m * p.tiles_n;
@@ -262,7 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_row<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32 + lane, tn * BN);
+      epilogue_warp<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32, tn * BN, epi_stage + q * EPI_WARP_FLOATS, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);        // 4 arrivals (one per epilogue warp) free the accumulator
@@ -297,6 +295,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2] (used in the leader only: 8 arrivals = 4 epilogue warps x 2 CTAs)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // 4 x [32][36] floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -375,7 +374,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_row<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * 256 + rank * 128 + q * 32 + lane, tn * BN);
+      epilogue_warp<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * 256 + rank * 128 + q * 32, tn * BN, epi_stage + q * EPI_WARP_FLOATS, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -460,7 +459,7 @@ size_t gemm_tc_scratch_bytes(int64_t max_rows, int max_k, int mode) {
 
 template <int BN, int STAGES, int APL, int WPL>
 static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (APL * TC_TILE_BYTES_A + WPL * BN * TC_BK * 2) + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (APL * TC_TILE_BYTES_A + WPL * BN * TC_BK * 2) + 1024 + 256 + 4 * EPI_WARP_FLOATS * 4;
   static bool attr_done = false;
   if (!attr_done) {
     FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, APL, WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -481,7 +480,7 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcPara
 
 template <int STAGES, int PL>
 static int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (2 * PL * 128 * TC_BK * 2) + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (2 * PL * 128 * TC_BK * 2) + 1024 + 256 + 4 * EPI_WARP_FLOATS * 4;
   static bool attr_done = false;
   if (!attr_done) {
     FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -514,7 +513,7 @@ int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLine
   if (!lin.w_planes || !a_planes) return FA_ERR_ARG;
   const int N = lin.out_f, Kp = lin.in_pad;
   if (Kp % TC_BK != 0 || M * 3 > 0x7fffffffLL) return FA_ERR_UNSUPPORTED;
-  if (y && ((ldy & 3) || (((uintptr_t)y) & 15))) return FA_ERR_UNSUPPORTED;
+  if (y && (ldy & 3) == 0 && (((uintptr_t)y) & 15)) return FA_ERR_UNSUPPORTED;
   if ((r1 && (ld1 & 3)) || (r2 && (ld2 & 3))) return FA_ERR_UNSUPPORTED;
   const int npl = planes_for_mode(mode);
   // 128x256 tiles halve the operand bytes per MMA cycle (the 128x128 tile is L2-bandwidth bound); used when N splits

@@ -388,3 +388,31 @@ def test_contextual_vs_reference_golden(name, mode):
     out = eng.forward_feats(feats, fl, want_taps=True)
     assert out["token_num"].tolist() == g["token_num"].tolist()
     assert rel_err(out["logp"][:, g["logp_rows"].tolist()].cpu().numpy(), g["logp_sel"]) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------- config 3: ragged buckets
+def test_config3_bucketed_ragged_vs_oracle():
+    """BASELINE config 3 in miniature: a ragged list is length-bucketed (funasr_b200.batching), every bucket runs as one
+    padded batch, results come back in input order and equal the oracle run on the same buckets (padded-batch semantics
+    of the reference, incl. what the CIF conv reads at the first padded frame)."""
+    from funasr_b200 import synth
+    from funasr_b200.batching import bucket_by_length, run_bucketed
+    from funasr_b200.engine import FrontendEngine, num_lfr_frames
+    cfg = synth.PARAFORMER_TINY
+    g = torch.Generator().manual_seed(99)
+    lens = [int(x) for x in (8000 + 56000 * torch.rand(12, generator=g)).tolist()]
+    wavs = [synth.make_wav(n, 70 + i, "speechlike") for i, n in enumerate(lens)]
+    cmvn = synth.make_cmvn(cfg, 1)
+    p = state_dict_for(cfg, 5)
+    fe, eng = FrontendEngine(cmvn, DEV), _engine(cfg, 5, "bf16x3")
+
+    def infer(batch):
+        ln = [w.numel() for w in batch]
+        pad = torch.nn.utils.rnn.pad_sequence(batch, batch_first=True).to(DEV)
+        feats, fl = fe(pad, torch.tensor(ln, dtype=torch.int32, device=DEV), max(num_lfr_frames(n) for n in ln))
+        return eng.forward_feats(feats, fl)["ids"]
+
+    got = run_bucketed(wavs, infer, max_batch=4, max_frames=4 * 100)
+    ref = run_bucketed(wavs, lambda b: O.paraformer_forward(b, p, cmvn, cfg.enc_layers, cfg.dec_layers)["ids"], max_batch=4, max_frames=4 * 100)
+    assert got == ref
+    assert len(bucket_by_length(lens, 4, 400)) >= 3
