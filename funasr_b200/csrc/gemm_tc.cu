@@ -50,56 +50,77 @@ struct TcParams {
 __constant__ int c_term_a[6] = {0, 0, 1, 1, 0, 2};
 __constant__ int c_term_w[6] = {0, 1, 0, 1, 2, 0};
 
-// Epilogue of one accumulator tile for one warp (32 rows x BN columns), 32 columns at a time:
-//   phase 1  tcgen05.ld (thread = row) -> raw fp32 accumulators into a padded shared-memory tile [32][36]
-//   phase 2  re-read with the warp laid out as 4 rows x 8 float4 columns, so bias / residual loads and every store are
-//            fully coalesced 16-byte (fp32) or 8-byte (bf16 plane) accesses; V columns of the attention sink take a
+// Epilogue of one accumulator tile.  Eight epilogue warps per CTA (two per SM sub-partition, so one warp's TMEM / shared /
+// global latencies are hidden by the other): warp w drains TMEM lane quarter w%4 and every second 16-column chunk.
+//   phase 1  tcgen05.ld 32x32b.x16 (thread = row) -> raw fp32 accumulators into a padded shared-memory tile [32][20]
+//   phase 2  re-read with the warp laid out as 8 rows x 4 float4 columns, so bias / residual loads and every store are
+//            coalesced 16-byte (fp32) or 8-byte (bf16 plane) accesses; V columns of the attention sink take a
 //            column-per-lane path that writes the per-head transposed planes as 4 consecutive keys (8 bytes) per store.
-// (The first version stored straight from the row-per-thread layout: 4-byte stores to 32 different lines per
-//  instruction made the GEMMs epilogue-bound — profiles/README.md.)
-constexpr int EPI_LD = 36;                       // padded row pitch (floats): 16-byte aligned, conflict-free float4 phases
-constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;     // 4.5 KB per epilogue warp
+// History (profiles/README.md): v1 stored straight from the row-per-thread layout (4-byte stores to 32 lines per
+// instruction); v2 staged through smem but kept 4 epilogue warps and measured SLOWER — ncu showed tensor pipe 17-25 %,
+// warps_active 12 %, 12-36 cycles per issued instruction: the epilogue was instruction-latency bound, not store bound.
+constexpr int EPI_CH = 16;                       // columns per chunk
+constexpr int EPI_LD = 20;                       // padded row pitch (floats): 16-byte aligned, conflict-free float4 phases
+constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;     // 2.5 KB per epilogue warp
+constexpr int EPI_WARPS = 8;
 
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// x = hi + mid + lo split of 4 values, packed converts (cvt.rn.bf16x2.f32), bf16 -> f32 by bit shifts
 __device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_stride, int npl, float x0, float x1, float x2, float x3) {
   for (int pl = 0; pl < npl; ++pl) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1), h2 = __float2bfloat16_rn(x2), h3 = __float2bfloat16_rn(x3);
+    const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
     uint2 pk;
-    pk.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    pk.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+    pk.x = *reinterpret_cast<const uint32_t*>(&p01);
+    pk.y = *reinterpret_cast<const uint32_t*>(&p23);
     *reinterpret_cast<uint2*>(dst + pl * plane_stride) = pk;
-    x0 -= __bfloat162float(h0); x1 -= __bfloat162float(h1); x2 -= __bfloat162float(h2); x3 -= __bfloat162float(h3);
+    if (pl + 1 < npl) {
+      x0 -= __uint_as_float(pk.x << 16); x1 -= __uint_as_float(pk.x & 0xFFFF0000u);
+      x2 -= __uint_as_float(pk.y << 16); x3 -= __uint_as_float(pk.y & 0xFFFF0000u);
+    }
   }
 }
 
 template <int BN>
-__device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane) {
+__device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
+                                              int half) {
+  const AttnSinks& a = p.att;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = half * EPI_CH; c0 < BN; c0 += 2 * EPI_CH) {
     {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_acc + c0, r);
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_acc + c0, r);
       float* srow = stage + lane * EPI_LD;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
     }
     __syncwarp();
     const int col0 = tile_col0 + c0;
     if (col0 < p.N && row0 < p.M) {
-      const bool full = col0 + 32 <= p.N;
-      const AttnSinks& a = p.att;
+      const bool full = col0 + EPI_CH <= p.N;
       const bool v_sink = a.enabled && col0 >= a.v0 && col0 < a.v0 + a.width;
       if (v_sink) {
-        // transposed per-head V planes: lane = head dim, 4 consecutive keys per 8-byte store
-        const int cv = col0 - a.v0 + lane;                         // h*128 + d
-        const float bv = p.bias ? __ldg(p.bias + col0 + lane) : 0.f;
+        // transposed per-head V planes: lane&15 = head dim, lane>>4 = which half of the eight 4-key groups
+        const int cl = lane & 15, gh = lane >> 4;
+        const int cv = col0 - a.v0 + cl;                           // h*128 + d
+        const float bv = p.bias ? __ldg(p.bias + col0 + cl) : 0.f;
         const int64_t plane = (int64_t)(p.M / a.t_rows) * a.width * a.t_pad;
         const int bb0 = (int)(row0 / a.t_rows), tt0 = (int)(row0 - (int64_t)bb0 * a.t_rows);
         const bool fast = ((tt0 & 3) == 0) && ((a.t_rows & 3) == 0) && (row0 + 32 <= p.M);
-#pragma unroll 1
-        for (int g = 0; g < 8; ++g) {
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          const int g = gh * 4 + gi;
           float x[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { x[i] = stage[(4 * g + i) * EPI_LD + lane] + bv; if (p.relu) x[i] = fmaxf(x[i], 0.f); }
+          for (int i = 0; i < 4; ++i) x[i] = stage[(4 * g + i) * EPI_LD + cl] + bv;
           int tt = tt0 + 4 * g, bb = bb0;
           if (tt >= a.t_rows) { bb += tt / a.t_rows; tt %= a.t_rows; }
           if (fast) {                                              // 4 keys stay inside one utterance (t_rows % 4 == 0)
@@ -119,44 +140,46 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
           }
         }
       }
-      // coalesced row-major phase: 4 rows x 8 float4 per pass
+      // coalesced row-major phase: 8 rows x 4 float4 per pass
       const bool q_sink = a.enabled && col0 >= a.q0 && col0 < a.q0 + a.width;
       const bool k_sink = a.enabled && col0 >= a.k0 && col0 < a.k0 + a.width;
       const bool want_c = p.C != nullptr && (!a.enabled || v_sink);
       if (want_c || p.out_planes || q_sink || k_sink) {
-        const int rr0 = lane >> 3, c4 = (lane & 7) * 4;
+        const int rr0 = lane >> 2, c4 = (lane & 3) * 4;
         const int col = col0 + c4;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) {
           if (full) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
           else { float* bp = reinterpret_cast<float*>(&bias4); for (int e = 0; e < 4; ++e) if (col + e < p.N) bp[e] = __ldg(p.bias + col + e); }
         }
-#pragma unroll 2
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + rr0;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + rr0;
           const int64_t row = row0 + rr;
-          if (row >= p.M) break;
-          const float4 acc = *reinterpret_cast<const float4*>(stage + rr * EPI_LD + c4);
-          float v[4] = {acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w};
-          if (p.relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
-          if (full) {
-            if (p.r1) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.r1 + row * p.ldr1 + col)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
-            if (p.r2) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.r2 + row * p.ldr2 + col)); v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w; }
-            if (want_c) {
-              if ((p.ldc & 3) == 0) *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = make_float4(v[0], v[1], v[2], v[3]);
-              else { float* cr = p.C + row * p.ldc + col; cr[0] = v[0]; cr[1] = v[1]; cr[2] = v[2]; cr[3] = v[3]; }
-            }
-            if (p.out_planes) store_planes4(p.out_planes + row * p.ldo + col, p.M * p.ldo, p.out_nplanes, v[0], v[1], v[2], v[3]);
-            if (q_sink) store_planes4(a.q_planes + row * a.width + (col - a.q0), p.M * a.width, a.npl, __fmul_rn(v[0], a.qscale),
-                                      __fmul_rn(v[1], a.qscale), __fmul_rn(v[2], a.qscale), __fmul_rn(v[3], a.qscale));
-            if (k_sink) store_planes4(a.k_planes + row * a.width + (col - a.k0), p.M * a.width, a.npl, v[0], v[1], v[2], v[3]);
-          } else {                                               // ragged N tail (e.g. vocab 8404 / 25055): scalar, bounds checked
-            for (int e = 0; e < 4; ++e) {
-              if (col + e >= p.N) break;
-              float x = v[e];
-              if (p.r1) x += __ldg(p.r1 + row * p.ldr1 + col + e);
-              if (p.r2) x += __ldg(p.r2 + row * p.ldr2 + col + e);
-              if (want_c) p.C[row * p.ldc + col + e] = x;
+          if (row < p.M) {
+            const float4 acc = *reinterpret_cast<const float4*>(stage + rr * EPI_LD + c4);
+            float v0 = acc.x + bias4.x, v1 = acc.y + bias4.y, v2 = acc.z + bias4.z, v3 = acc.w + bias4.w;
+            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+            if (full) {
+              if (p.r1) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.r1 + row * p.ldr1 + col)); v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w; }
+              if (p.r2) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.r2 + row * p.ldr2 + col)); v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w; }
+              if (want_c) {
+                if ((p.ldc & 3) == 0) *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = make_float4(v0, v1, v2, v3);
+                else { float* cr = p.C + row * p.ldc + col; cr[0] = v0; cr[1] = v1; cr[2] = v2; cr[3] = v3; }
+              }
+              if (p.out_planes) store_planes4(p.out_planes + row * p.ldo + col, p.M * p.ldo, p.out_nplanes, v0, v1, v2, v3);
+              if (q_sink) store_planes4(a.q_planes + row * a.width + (col - a.q0), p.M * a.width, a.npl, __fmul_rn(v0, a.qscale),
+                                        __fmul_rn(v1, a.qscale), __fmul_rn(v2, a.qscale), __fmul_rn(v3, a.qscale));
+              if (k_sink) store_planes4(a.k_planes + row * a.width + (col - a.k0), p.M * a.width, a.npl, v0, v1, v2, v3);
+            } else {                                             // ragged N tail (e.g. vocab 8404 / 25055): scalar, bounds checked
+              const float vv[4] = {v0, v1, v2, v3};
+              for (int e = 0; e < 4; ++e) {
+                if (col + e >= p.N) break;
+                float x = vv[e];
+                if (p.r1) x += __ldg(p.r1 + row * p.ldr1 + col + e);
+                if (p.r2) x += __ldg(p.r2 + row * p.ldr2 + col + e);
+                if (want_c) p.C[row * p.ldc + col + e] = x;
+              }
             }
           }
         }
@@ -167,7 +190,7 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
 }
 
 template <int BN, int STAGES, int APL, int WPL>  // APL / WPL: A / W planes resident per stage
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr uint32_t TILE_W_BYTES = BN * TC_BK * 2;
@@ -178,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // 4 x [32][36] floats
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // 8 x [32][20] floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.tiles_m * p.tiles_n;
@@ -190,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_base_slot, 2 * BN);
@@ -253,14 +276,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (warps 4..7 <-> TMEM lanes 32*(warp-4) ..) =====================
-    const int q = warp - 4;
+    // ===================== epilogue (warps 4..11: TMEM lane quarter warp%4, alternate 16-column chunks) =====================
+    const int q = warp & 3, half = (warp - 4) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_warp<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32, tn * BN, epi_stage + q * EPI_WARP_FLOATS, lane);
+      epilogue_warp<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32, tn * BN, epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);        // 4 arrivals (one per epilogue warp) free the accumulator
@@ -283,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // (64 KB per k-block per SM for the three x3 terms) and three stages fit.  The leader issues
 // tcgen05.mma.cta_group::2 (M=256); each CTA drains its own 128 TMEM lanes in the epilogue.
 template <int STAGES, int PL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int BN = 256;
@@ -295,7 +318,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2] (used in the leader only: 8 arrivals = 4 epilogue warps x 2 CTAs)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // 4 x [32][36] floats
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // 8 x [32][20] floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -307,7 +330,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm(tmem_base_slot, 2 * BN);
@@ -368,13 +391,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue (each CTA: its 128 rows) =====================
-    const int q = warp - 4;
+    const int q = warp & 3, half = (warp - 4) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = pair; tile < n_tiles; tile += n_pairs) {
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_warp<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * 256 + rank * 128 + q * 32, tn * BN, epi_stage + q * EPI_WARP_FLOATS, lane);
+      epilogue_warp<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * 256 + rank * 128 + q * 32, tn * BN, epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -459,7 +482,7 @@ size_t gemm_tc_scratch_bytes(int64_t max_rows, int max_k, int mode) {
 
 template <int BN, int STAGES, int APL, int WPL>
 static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (APL * TC_TILE_BYTES_A + WPL * BN * TC_BK * 2) + 1024 + 256 + 4 * EPI_WARP_FLOATS * 4;
+  constexpr size_t smem = (size_t)STAGES * (APL * TC_TILE_BYTES_A + WPL * BN * TC_BK * 2) + 1024 + 256 + EPI_WARPS * EPI_WARP_FLOATS * 4;
   static bool attr_done = false;
   if (!attr_done) {
     FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, APL, WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -473,14 +496,14 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcPara
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < n_sm ? tiles : n_sm;
-  gemm_tc_kernel<BN, STAGES, APL, WPL><<<grid, 256, smem, st>>>(ma, mw, p);
+  gemm_tc_kernel<BN, STAGES, APL, WPL><<<grid, 384, smem, st>>>(ma, mw, p);
   FA_CHECK_LAUNCH();
   return FA_OK;
 }
 
 template <int STAGES, int PL>
 static int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (2 * PL * 128 * TC_BK * 2) + 1024 + 256 + 4 * EPI_WARP_FLOATS * 4;
+  constexpr size_t smem = (size_t)STAGES * (2 * PL * 128 * TC_BK * 2) + 1024 + 256 + EPI_WARPS * EPI_WARP_FLOATS * 4;
   static bool attr_done = false;
   if (!attr_done) {
     FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -494,7 +517,7 @@ static int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mw, const TcPar
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int pairs = tiles < n_sm / 2 ? tiles : n_sm / 2;
-  gemm_tc2_kernel<STAGES, PL><<<2 * pairs, 256, smem, st>>>(ma, mw, p);
+  gemm_tc2_kernel<STAGES, PL><<<2 * pairs, 384, smem, st>>>(ma, mw, p);
   FA_CHECK_LAUNCH();
   return FA_OK;
 }
