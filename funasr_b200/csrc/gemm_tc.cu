@@ -89,7 +89,13 @@ __device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_
   }
 }
 
-template <int BN>
+// EPI selects the output kind at compile time so the inner loops carry no runtime branching on it:
+//   EPI_F32    fp32 rows (+ bias, ReLU, up to two residuals; ragged N tail supported)
+//   EPI_PLANES bf16 planes for a following GEMM (+ bias, ReLU)
+//   EPI_ATT    attention operands: scaled q planes / k planes / per-head transposed v planes (+ fp32 v for FSMN)
+constexpr int EPI_F32 = 0, EPI_PLANES = 1, EPI_ATT = 2;
+
+template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
                                               int half) {
   const AttnSinks& a = p.att;
@@ -106,8 +112,8 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
     const int col0 = tile_col0 + c0;
     if (col0 < p.N && row0 < p.M) {
       const bool full = col0 + EPI_CH <= p.N;
-      const bool v_sink = a.enabled && col0 >= a.v0 && col0 < a.v0 + a.width;
-      if (v_sink) {
+      const bool v_sink = EPI == EPI_ATT && col0 >= a.v0 && col0 < a.v0 + a.width;
+      if (EPI == EPI_ATT && v_sink) {
         // transposed per-head V planes: lane&15 = head dim, lane>>4 = which half of the eight 4-key groups
         const int cl = lane & 15, gh = lane >> 4;
         const int cv = col0 - a.v0 + cl;                           // h*128 + d
@@ -140,46 +146,61 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
           }
         }
       }
-      // coalesced row-major phase: 8 rows x 4 float4 per pass
-      const bool q_sink = a.enabled && col0 >= a.q0 && col0 < a.q0 + a.width;
-      const bool k_sink = a.enabled && col0 >= a.k0 && col0 < a.k0 + a.width;
-      const bool want_c = p.C != nullptr && (!a.enabled || v_sink);
-      if (want_c || p.out_planes || q_sink || k_sink) {
+      // coalesced row-major phase: 8 rows x 4 float4 per pass.  All row/column address arithmetic is hoisted: one 64-bit
+      // multiply per output stream per chunk, then constant strides (8 rows) across the four passes.
+      const bool q_sink = EPI == EPI_ATT && col0 >= a.q0 && col0 < a.q0 + a.width;
+      const bool k_sink = EPI == EPI_ATT && col0 >= a.k0 && col0 < a.k0 + a.width;
+      const bool want_c = EPI == EPI_F32 ? true : (EPI == EPI_ATT ? (p.C != nullptr && v_sink) : false);
+      if (EPI != EPI_ATT || want_c || q_sink || k_sink) {
         const int rr0 = lane >> 2, c4 = (lane & 3) * 4;
         const int col = col0 + c4;
+        const int64_t rfirst = row0 + rr0;
+        const int rows_left = (int)((p.M - rfirst + 7) >> 3);        // passes (of 8 rows) with a valid row for this lane
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) {
           if (full) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
           else { float* bp = reinterpret_cast<float*>(&bias4); for (int e = 0; e < 4; ++e) if (col + e < p.N) bp[e] = __ldg(p.bias + col + e); }
         }
+        const float* sp = stage + rr0 * EPI_LD + c4;
+        if (EPI != EPI_F32 || full) {
+          float* pc = want_c ? p.C + rfirst * p.ldc + col : nullptr;
+          const float* pr1 = (EPI == EPI_F32 && p.r1) ? p.r1 + rfirst * p.ldr1 + col : nullptr;
+          const float* pr2 = (EPI == EPI_F32 && p.r2) ? p.r2 + rfirst * p.ldr2 + col : nullptr;
+          __nv_bfloat16* po = EPI == EPI_PLANES ? p.out_planes + rfirst * p.ldo + col : nullptr;
+          __nv_bfloat16* pq = q_sink ? a.q_planes + rfirst * a.width + (col - a.q0) : (k_sink ? a.k_planes + rfirst * a.width + (col - a.k0) : nullptr);
+          const float qs = q_sink ? a.qscale : 1.0f;
+          const int64_t sc = 8 * p.ldc, s1 = 8 * p.ldr1, s2 = 8 * p.ldr2, so = 8 * p.ldo, sq = 8 * (int64_t)a.width;
+          const int64_t plane_o = p.M * p.ldo, plane_q = p.M * (int64_t)a.width;
+          const bool c_vec = (p.ldc & 3) == 0;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int rr = it * 8 + rr0;
-          const int64_t row = row0 + rr;
-          if (row < p.M) {
-            const float4 acc = *reinterpret_cast<const float4*>(stage + rr * EPI_LD + c4);
-            float v0 = acc.x + bias4.x, v1 = acc.y + bias4.y, v2 = acc.z + bias4.z, v3 = acc.w + bias4.w;
-            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-            if (full) {
-              if (p.r1) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.r1 + row * p.ldr1 + col)); v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w; }
-              if (p.r2) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.r2 + row * p.ldr2 + col)); v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w; }
-              if (want_c) {
-                if ((p.ldc & 3) == 0) *reinterpret_cast<float4*>(p.C + row * p.ldc + col) = make_float4(v0, v1, v2, v3);
-                else { float* cr = p.C + row * p.ldc + col; cr[0] = v0; cr[1] = v1; cr[2] = v2; cr[3] = v3; }
+          for (int it = 0; it < 4; ++it) {
+            if (it < rows_left) {
+              const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
+              float v0 = acc.x + bias4.x, v1 = acc.y + bias4.y, v2 = acc.z + bias4.z, v3 = acc.w + bias4.w;
+              if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+              if (EPI == EPI_F32) {
+                if (pr1) { const float4 t = __ldg(reinterpret_cast<const float4*>(pr1 + it * s1)); v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w; }
+                if (pr2) { const float4 t = __ldg(reinterpret_cast<const float4*>(pr2 + it * s2)); v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w; }
               }
-              if (p.out_planes) store_planes4(p.out_planes + row * p.ldo + col, p.M * p.ldo, p.out_nplanes, v0, v1, v2, v3);
-              if (q_sink) store_planes4(a.q_planes + row * a.width + (col - a.q0), p.M * a.width, a.npl, __fmul_rn(v0, a.qscale),
-                                        __fmul_rn(v1, a.qscale), __fmul_rn(v2, a.qscale), __fmul_rn(v3, a.qscale));
-              if (k_sink) store_planes4(a.k_planes + row * a.width + (col - a.k0), p.M * a.width, a.npl, v0, v1, v2, v3);
-            } else {                                             // ragged N tail (e.g. vocab 8404 / 25055): scalar, bounds checked
-              const float vv[4] = {v0, v1, v2, v3};
-              for (int e = 0; e < 4; ++e) {
-                if (col + e >= p.N) break;
-                float x = vv[e];
-                if (p.r1) x += __ldg(p.r1 + row * p.ldr1 + col + e);
-                if (p.r2) x += __ldg(p.r2 + row * p.ldr2 + col + e);
-                if (want_c) p.C[row * p.ldc + col + e] = x;
+              if (EPI != EPI_PLANES && pc) {
+                if (c_vec) *reinterpret_cast<float4*>(pc + it * sc) = make_float4(v0, v1, v2, v3);
+                else { float* cr = pc + it * sc; cr[0] = v0; cr[1] = v1; cr[2] = v2; cr[3] = v3; }
               }
+              if (EPI == EPI_PLANES) store_planes4(po + it * so, plane_o, p.out_nplanes, v0, v1, v2, v3);
+              if (EPI == EPI_ATT && pq) store_planes4(pq + it * sq, plane_q, a.npl, __fmul_rn(v0, qs), __fmul_rn(v1, qs), __fmul_rn(v2, qs), __fmul_rn(v3, qs));
+            }
+          }
+        } else {                                                   // ragged N tail (e.g. vocab 8404 / 25055): scalar, bounds checked
+          for (int it = 0; it < 4 && it < rows_left; ++it) {
+            const int64_t row = rfirst + 8 * it;
+            const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
+            const float vv[4] = {acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w};
+            for (int e = 0; e < 4; ++e) {
+              if (col + e >= p.N) break;
+              float x = p.relu ? fmaxf(vv[e], 0.f) : vv[e];
+              if (p.r1) x += __ldg(p.r1 + row * p.ldr1 + col + e);
+              if (p.r2) x += __ldg(p.r2 + row * p.ldr2 + col + e);
+              if (want_c) p.C[row * p.ldc + col + e] = x;
             }
           }
         }
@@ -189,7 +210,7 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
   }
 }
 
-template <int BN, int STAGES, int APL, int WPL>  // APL / WPL: A / W planes resident per stage
+template <int BN, int STAGES, int APL, int WPL, int EPI>  // APL / WPL: A / W planes resident per stage
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -283,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_warp<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32, tn * BN, epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half);
+      epilogue_warp<BN, EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32, tn * BN, epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);        // 4 arrivals (one per epilogue warp) free the accumulator
@@ -305,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // (half of the N tile) per k-block, so operand bytes per MMA cycle are half those of the single-CTA 128x256 tile
 // (64 KB per k-block per SM for the three x3 terms) and three stages fit.  The leader issues
 // tcgen05.mma.cta_group::2 (M=256); each CTA drains its own 128 TMEM lanes in the epilogue.
-template <int STAGES, int PL>
+template <int STAGES, int PL, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -397,7 +418,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_warp<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * 256 + rank * 128 + q * 32, tn * BN, epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half);
+      epilogue_warp<BN, EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * 256 + rank * 128 + q * 32, tn * BN, epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -480,12 +501,12 @@ size_t gemm_tc_scratch_bytes(int64_t max_rows, int max_k, int mode) {
   return (size_t)planes_for_mode(mode) * (size_t)max_rows * kp * 2 + 1024;
 }
 
-template <int BN, int STAGES, int APL, int WPL>
-static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+template <int BN, int STAGES, int APL, int WPL, int EPI>
+static int launch_cfg_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (APL * TC_TILE_BYTES_A + WPL * BN * TC_BK * 2) + 1024 + 256 + EPI_WARPS * EPI_WARP_FLOATS * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, APL, WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, APL, WPL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   static int n_sm = 0;
@@ -496,17 +517,28 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcPara
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < n_sm ? tiles : n_sm;
-  gemm_tc_kernel<BN, STAGES, APL, WPL><<<grid, 384, smem, st>>>(ma, mw, p);
+  gemm_tc_kernel<BN, STAGES, APL, WPL, EPI><<<grid, 384, smem, st>>>(ma, mw, p);
   FA_CHECK_LAUNCH();
   return FA_OK;
 }
 
-template <int STAGES, int PL>
-static int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+static inline int epi_kind(const TcParams& p) { return p.att.enabled ? EPI_ATT : (p.out_planes ? EPI_PLANES : EPI_F32); }
+
+template <int BN, int STAGES, int APL, int WPL>
+static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+  switch (epi_kind(p)) {
+    case EPI_ATT: return launch_cfg_e<BN, STAGES, APL, WPL, EPI_ATT>(ma, mw, p, st);
+    case EPI_PLANES: return launch_cfg_e<BN, STAGES, APL, WPL, EPI_PLANES>(ma, mw, p, st);
+    default: return launch_cfg_e<BN, STAGES, APL, WPL, EPI_F32>(ma, mw, p, st);
+  }
+}
+
+template <int STAGES, int PL, int EPI>
+static int launch_cfg2_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (2 * PL * 128 * TC_BK * 2) + 1024 + 256 + EPI_WARPS * EPI_WARP_FLOATS * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, PL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   static int n_sm = 0;
@@ -517,9 +549,18 @@ static int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mw, const TcPar
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int pairs = tiles < n_sm / 2 ? tiles : n_sm / 2;
-  gemm_tc2_kernel<STAGES, PL><<<2 * pairs, 384, smem, st>>>(ma, mw, p);
+  gemm_tc2_kernel<STAGES, PL, EPI><<<2 * pairs, 384, smem, st>>>(ma, mw, p);
   FA_CHECK_LAUNCH();
   return FA_OK;
+}
+
+template <int STAGES, int PL>
+static int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+  switch (epi_kind(p)) {
+    case EPI_ATT: return launch_cfg2_e<STAGES, PL, EPI_ATT>(ma, mw, p, st);
+    case EPI_PLANES: return launch_cfg2_e<STAGES, PL, EPI_PLANES>(ma, mw, p, st);
+    default: return launch_cfg2_e<STAGES, PL, EPI_F32>(ma, mw, p, st);
+  }
 }
 
 static bool use_2cta() {
