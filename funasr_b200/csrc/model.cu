@@ -393,6 +393,20 @@ extern "C" int fa_linear(const float* x, int64_t ldx, int64_t rows, const FaLine
   return linear(x, ldx, rows, *lin, relu, res1, ld_res1, res2, ld_res2, y, ldy, gemm_mode, &scratch, (cudaStream_t)stream);
 }
 
+extern "C" int fa_split_rows(const float* x, int64_t ldx, int64_t rows, int32_t cols, int32_t cols_pad, int32_t nplanes, void* planes,
+                             fa_stream_t stream) {
+  if (!x || !planes || nplanes < 1 || nplanes > 3) return FA_ERR_ARG;
+  return split_rows_launch(x, ldx, rows, cols, cols_pad, nplanes, reinterpret_cast<__nv_bfloat16*>(planes), (cudaStream_t)stream);
+}
+
+extern "C" int fa_linear_planes(const void* a_planes, int64_t rows, const FaLinear* lin, int32_t relu, const float* res1,
+                                int64_t ld_res1, const float* res2, int64_t ld_res2, float* y, int64_t ldy, int32_t gemm_mode,
+                                fa_stream_t stream) {
+  if (!a_planes || !lin || !y || gemm_mode == FA_GEMM_F32_SIMT) return FA_ERR_ARG;
+  return gemm_tc_planes_launch(reinterpret_cast<const __nv_bfloat16*>(a_planes), rows, *lin, relu, res1, ld_res1, res2, ld_res2, y, ldy,
+                               nullptr, 0, gemm_mode, (cudaStream_t)stream);
+}
+
 extern "C" const char* fa_version(void) { return "funasr_b200 0.1.0 (sm_100a)"; }
 extern "C" uint64_t fa_launch_count(void) { return (uint64_t)fa::g_launch_count.load(); }
 extern "C" const char* fa_status_string(int status) {

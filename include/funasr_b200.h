@@ -175,6 +175,13 @@ int fa_linear(const float* x, int64_t ldx, int64_t rows, const FaLinear* lin, in
               const float* res1, int64_t ld_res1, const float* res2, int64_t ld_res2,
               float* y, int64_t ldy, int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream);
 
+/* The tensor-core GEMM alone, A operand already split into bf16 planes [npl][rows][lin->in_pad] (npl = 1 / 2 / 3 for
+ * BF16X1 / X3 / X6) by fa_split_rows: what the model-level calls launch between fused producers and consumers. */
+int fa_split_rows(const float* x, int64_t ldx, int64_t rows, int32_t cols, int32_t cols_pad, int32_t nplanes, void* planes,
+                  fa_stream_t stream);
+int fa_linear_planes(const void* a_planes, int64_t rows, const FaLinear* lin, int32_t relu, const float* res1, int64_t ld_res1,
+                     const float* res2, int64_t ld_res2, float* y, int64_t ldy, int32_t gemm_mode, fa_stream_t stream);
+
 /* FSMN memory block: out = m * (v*m + dwconv_k(v*m)) (+ res); m[t] = t < lens[b]
  * (MultiHeadedAttentionSANM.forward_fsmn attention.py:216-239; decoder variant :583-631). */
 int fa_fsmn(const float* v, int64_t ldv, const int32_t* lens, int32_t batch, int32_t t_max, int32_t channels,
