@@ -46,24 +46,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   constexpr uint32_t Q_BYTES = NPL * 2 * AT_Q_KBLK;
   constexpr uint32_t K_BYTES = NPL * 2 * AT_K_KBLK;
   constexpr uint32_t V_BYTES = NPL * AT_V_TILE;
-  constexpr uint32_t STAGE_BYTES = K_BYTES + V_BYTES;
+  constexpr uint32_t K_HI_BYTES = 2 * AT_K_KBLK;          // pass A needs only the hi plane
   constexpr uint32_t P_BYTES = NPL * AT_P_TILE;
   constexpr int NT = NPL == 1 ? 1 : 3;
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sQ = smem;
-  unsigned char* sKV = sQ + Q_BYTES;
-  unsigned char* sP = sKV + 2 * STAGE_BYTES;
+  // K and V live in separate 2-deep rings: a K chunk is dead as soon as its score MMAs retire (long before P.V of the same
+  // chunk), so the next K load is issued early and its latency hides behind softmax + P.V; V is only needed at P.V time.
+  unsigned char* sKV = sQ + Q_BYTES;          // K ring [2][K_BYTES] followed by V ring [2][V_BYTES]
+  unsigned char* sV = sKV + 2 * K_BYTES;
+  unsigned char* sP = sV + 2 * V_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
   uint64_t* q_full = bars;            // [1]
-  uint64_t* kv_full = bars + 1;       // [2]
-  uint64_t* kv_empty = bars + 3;      // [2]
-  uint64_t* s_full = bars + 5;        // [2]
-  uint64_t* s_empty = bars + 7;       // [2]
-  uint64_t* p_full = bars + 9;        // [1]
-  uint64_t* p_empty = bars + 10;      // [1]
-  uint64_t* o_full = bars + 11;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  float* s_red = reinterpret_cast<float*>(bars + 13);   // [2][128] row max / row sum exchange between column halves
+  uint64_t* k_full = bars + 1;        // [2]
+  uint64_t* k_empty = bars + 3;       // [2]
+  uint64_t* v_full = bars + 5;        // [2]
+  uint64_t* v_empty = bars + 7;       // [2]
+  uint64_t* s_full = bars + 9;        // [2]
+  uint64_t* s_empty = bars + 11;      // [2]
+  uint64_t* p_full = bars + 13;       // [1]
+  uint64_t* p_empty = bars + 14;      // [1]
+  uint64_t* o_full = bars + 15;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* s_red = reinterpret_cast<float*>(bars + 17);   // [2][128] row max / row sum exchange between column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
@@ -74,7 +79,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8);
+    }
     mbar_init(p_full, 8); mbar_init(p_empty, 1); mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -95,24 +103,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int kb = 0; kb < 2; ++kb)
           tma_load_2d(sQ + (pl * 2 + kb) * AT_Q_KBLK, &map_q, q_full, h * AT_D + kb * 64,
                       (int)(pl * p.q_plane_rows + (int64_t)b * p.tq + q0));
-      for (int i = 0; i < njobs; ++i) {
+      for (int i = 0; i < njobs; ++i) {                       // K ring: every job (pass A: hi plane only)
         const int st = i & 1, j = i < nc ? i : i - nc;
         const bool passB = i >= nc;
-        mbar_wait(&kv_empty[st], (((uint32_t)i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], passB ? STAGE_BYTES : K_BYTES);
-        unsigned char* sk = sKV + st * STAGE_BYTES;
-#pragma unroll
-        for (int pl = 0; pl < NPL; ++pl)
+        mbar_wait(&k_empty[st], (((uint32_t)i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], passB ? K_BYTES : K_HI_BYTES);
+        unsigned char* sk = sKV + st * K_BYTES;
+        const int npl_load = passB ? NPL : 1;
+        for (int pl = 0; pl < npl_load; ++pl)
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb)
-            tma_load_2d(sk + (pl * 2 + kb) * AT_K_KBLK, &map_k, &kv_full[st], h * AT_D + kb * 64,
+            tma_load_2d(sk + (pl * 2 + kb) * AT_K_KBLK, &map_k, &k_full[st], h * AT_D + kb * 64,
                         (int)(pl * p.k_plane_rows + (int64_t)b * p.tk + j * AT_BKEY));
-        if (passB) {
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== V producer (pass B chunks) =====================
+    if (lane == 0 && nc > 0) {
+      for (int t = 0; t < nc; ++t) {
+        const int st = t & 1;
+        mbar_wait(&v_empty[st], (((uint32_t)t >> 1) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], V_BYTES);
 #pragma unroll
-          for (int pl = 0; pl < NPL; ++pl)
-            tma_load_2d(sk + K_BYTES + pl * AT_V_TILE, &map_v, &kv_full[st], j * AT_BKEY,
-                        (int)(pl * p.v_plane_rows + ((int64_t)b * p.heads + h) * AT_D));
-        }
+        for (int pl = 0; pl < NPL; ++pl)
+          tma_load_2d(sV + st * V_BYTES + pl * AT_V_TILE, &map_v, &v_full[st], t * AT_BKEY,
+                      (int)(pl * p.v_plane_rows + ((int64_t)b * p.heads + h) * AT_D));
       }
     }
   } else if (warp == 1) {
@@ -124,28 +139,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       mbar_wait(q_full, 0);
       tc_fence_after();
-      auto issue_pv = [&](int t) {   // t-th PV of pass B, uses kv stage of job nc + t
-        const int i = nc + t, st = i & 1;
+      auto issue_pv = [&](int t) {   // t-th P.V of pass B
+        const int st = t & 1;
         mbar_wait(p_full, (uint32_t)t & 1);
+        mbar_wait(&v_full[st], ((uint32_t)t >> 1) & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sKV + st * STAGE_BYTES + K_BYTES);
+        const uint32_t v_addr = smem_u32(sV + st * V_BYTES);
         for (int term = 0; term < NT; ++term) {
           const uint64_t da = make_sw128_desc(p_addr + ta[term] * AT_P_TILE);
           const uint64_t db = make_sw128_desc(v_addr + tb[term] * AT_V_TILE);
 #pragma unroll
           for (int k = 0; k < AT_BKEY / 16; ++k) umma_bf16(tmem_o, da + 2 * k, db + 2 * k, idesc_o, (t | term | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&kv_empty[st]);
+        umma_commit(&v_empty[st]);
         umma_commit(p_empty);
       };
       for (int i = 0; i < njobs; ++i) {
         const int st = i & 1;
         const bool passB = i >= nc;
         const uint32_t ph = ((uint32_t)i >> 1) & 1;
-        mbar_wait(&kv_full[st], ph);
+        mbar_wait(&k_full[st], ph);
         mbar_wait(&s_empty[st], ph ^ 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sKV + st * STAGE_BYTES);
+        const uint32_t k_addr = smem_u32(sKV + st * K_BYTES);
         const uint32_t d_s = tmem_base + st * AT_BKEY;
         const int nterm = passB ? NT : 1;
         for (int term = 0; term < nterm; ++term) {
@@ -157,8 +173,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
         umma_commit(&s_full[st]);
-        if (!passB) umma_commit(&kv_empty[st]);
-        else if (i > nc) issue_pv(i - nc - 1);
+        umma_commit(&k_empty[st]);                         // K chunk is dead once its score MMAs retire
+        if (passB && i > nc) issue_pv(i - nc - 1);
       }
       issue_pv(nc - 1);
       umma_commit(o_full);

@@ -261,6 +261,7 @@ class ParaformerEngine(_EngineBase):
         fids_h, flens_h = fids.cpu(), flens.cpu()  # D2H of the result
         out["ids"] = [fids_h[b, : int(flens_h[b])].tolist() for b in range(fids_h.shape[0])]
         out["ids_padded"], out["ids_lens"] = fids_h, flens_h
+        out["ids_dev"], out["ids_lens_dev"] = fids, flens        # device copies (multi-GPU all-gather consumes these)
         if want_taps:
             out.update(argmax=ids, best_logp=best, logp=logp)
         return out
