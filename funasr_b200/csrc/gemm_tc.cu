@@ -121,22 +121,31 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
         const int64_t plane = (int64_t)(p.M / a.t_rows) * a.width * a.t_pad;
         const int bb0 = (int)(row0 / a.t_rows), tt0 = (int)(row0 - (int64_t)bb0 * a.t_rows);
         const bool fast = ((tt0 & 3) == 0) && ((a.t_rows & 3) == 0) && (row0 + 32 <= p.M);
+        if (fast) {
+          // 4 consecutive keys per store stay inside one utterance (t_rows % 4 == 0); one 64-bit address per lane, then
+          // +4 keys per group, hopping to the next utterance's plane row when the 32-row block crosses a boundary
+          __nv_bfloat16* base = a.vt_planes + ((int64_t)bb0 * a.width + cv) * a.t_pad;
+          const int64_t utt_stride = (int64_t)a.width * a.t_pad;
 #pragma unroll
-        for (int gi = 0; gi < 4; ++gi) {
-          const int g = gh * 4 + gi;
-          float x[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) x[i] = stage[(4 * g + i) * EPI_LD + cl] + bv;
-          int tt = tt0 + 4 * g, bb = bb0;
-          if (tt >= a.t_rows) { bb += tt / a.t_rows; tt %= a.t_rows; }
-          if (fast) {                                              // 4 keys stay inside one utterance (t_rows % 4 == 0)
-            store_planes4(a.vt_planes + ((int64_t)bb * a.width + cv) * a.t_pad + tt, plane, a.npl, x[0], x[1], x[2], x[3]);
-          } else {
+          for (int gi = 0; gi < 4; ++gi) {
+            const int g = gh * 4 + gi;
+            const float* sp4 = stage + (4 * g) * EPI_LD + cl;
+            const float x0 = sp4[0] + bv, x1 = sp4[EPI_LD] + bv, x2 = sp4[2 * EPI_LD] + bv, x3 = sp4[3 * EPI_LD] + bv;
+            int tt = tt0 + 4 * g;
+            __nv_bfloat16* dst = base;
+            if (tt >= a.t_rows) { tt -= a.t_rows; dst += utt_stride; }     // 32 rows span at most two utterances when t_rows >= 32
+            if (tt >= a.t_rows) { const int hop = tt / a.t_rows; tt -= hop * a.t_rows; dst += hop * utt_stride; }
+            store_planes4(dst + tt, plane, a.npl, x0, x1, x2, x3);
+          }
+        } else {
+#pragma unroll 1
+          for (int gi = 0; gi < 4; ++gi) {
+            const int g = gh * 4 + gi;
             for (int i = 0; i < 4; ++i) {
               const int64_t rw = row0 + 4 * g + i;
               if (rw >= p.M) break;
               const int b2 = (int)(rw / a.t_rows), t2 = (int)(rw - (int64_t)b2 * a.t_rows);
-              float xv = x[i];
+              float xv = stage[(4 * g + i) * EPI_LD + cl] + bv;
               for (int pl = 0; pl < a.npl; ++pl) {
                 const __nv_bfloat16 h0 = __float2bfloat16_rn(xv);
                 a.vt_planes[pl * plane + ((int64_t)b2 * a.width + cv) * a.t_pad + t2] = h0;
