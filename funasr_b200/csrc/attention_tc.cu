@@ -232,12 +232,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
+            // packed cvt.rn.bf16x2.f32 (ALU pipe) instead of two scalar F2F.BF16 (quarter-rate XU pipe, shared with EX2);
+            // bf16 -> fp32 is a 16-bit shift
             const float a = pr[cc * 8 + 2 * e], bb = pr[cc * 8 + 2 * e + 1];
-            const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(bb);
-            hi[e] = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
             if (NPL > 1) {
-              const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(bb - __bfloat162float(hb));
-              lo[e] = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+              const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hi[e] << 16), bb - __uint_as_float(hi[e] & 0xFFFF0000u));
+              lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
             }
           }
           const int pc = ((hf * 4 + cc) ^ (r & 7)) * 4;
@@ -290,12 +292,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           float x0 = o4.x, x1 = o4.y, x2 = o4.z, x3 = o4.w;
           const int64_t plane = (int64_t)p.batch * p.tq * p.ldp;
           for (int pl = 0; pl < p.out_nplanes; ++pl) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1), h2 = __float2bfloat16_rn(x2), h3 = __float2bfloat16_rn(x3);
+            const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
             uint2 pk;
-            pk.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            pk.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+            pk.x = *reinterpret_cast<const uint32_t*>(&p01);
+            pk.y = *reinterpret_cast<const uint32_t*>(&p23);
             *reinterpret_cast<uint2*>(p.ctx_planes + pl * plane + grow * p.ldp + col) = pk;
-            x0 -= __bfloat162float(h0); x1 -= __bfloat162float(h1); x2 -= __bfloat162float(h2); x3 -= __bfloat162float(h3);
+            x0 -= __uint_as_float(pk.x << 16); x1 -= __uint_as_float(pk.x & 0xFFFF0000u);
+            x2 -= __uint_as_float(pk.y << 16); x3 -= __uint_as_float(pk.y & 0xFFFF0000u);
           }
         }
       }
