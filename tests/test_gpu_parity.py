@@ -416,3 +416,49 @@ def test_config3_bucketed_ragged_vs_oracle():
     ref = run_bucketed(wavs, lambda b: O.paraformer_forward(b, p, cmvn, cfg.enc_layers, cfg.dec_layers)["ids"], max_batch=4, max_frames=4 * 100)
     assert got == ref
     assert len(bucket_by_length(lens, 4, 400)) >= 3
+
+
+# ------------------------------------------------------------------------------------------------- edge cases
+def test_long_utterance_60s_vs_oracle():
+    """Maximum practical size of one VAD segment (60 s -> T = 1000 LFR frames, 8 query tiles, 16 key chunks): both
+    precision paths against the oracle."""
+    from funasr_b200 import synth
+    cfg = synth.PARAFORMER_TINY
+    wavs = [synth.make_wav(960000, 81, "speechlike"), synth.make_wav(700001, 82, "speechlike")]
+    cmvn = synth.make_cmvn(cfg, 2)
+    p = state_dict_for(cfg, 12)
+    ref = O.paraformer_forward(wavs, p, cmvn, cfg.enc_layers, cfg.dec_layers)
+    for mode in ("fp32", "bf16x3"):
+        o = _run_model(cfg, 12, wavs, cmvn, mode)
+        assert o["feat_lens"].cpu().tolist() == [1000, 730]
+        assert o["token_num"].tolist() == ref["token_num"].tolist()
+        assert rel_err(o["logp"].cpu().numpy(), ref["logp"].numpy()) <= 1e-3
+        assert o["ids"] == ref["ids"]
+
+
+def test_silence_and_minimum_length():
+    """All-zero audio (log floor everywhere) and the shortest supported utterance (one 25 ms frame -> one LFR frame):
+    token counts and ids follow the oracle; a batch whose largest token count is 0 yields empty results like
+    Paraformer.inference (model.py:615-616)."""
+    import funasr_b200
+    from funasr_b200 import synth
+    from test_abi_host import _tiny_conf
+    cfg = synth.PARAFORMER_TINY
+    wavs = [torch.zeros(16000), synth.make_wav(400, 83, "noise"), synth.make_wav(24000, 84, "speechlike")]
+    cmvn = synth.make_cmvn(cfg, 2)
+    p = state_dict_for(cfg, 12)
+    ref = O.paraformer_forward(wavs, p, cmvn, cfg.enc_layers, cfg.dec_layers)
+    o = _run_model(cfg, 12, wavs, cmvn, "bf16x3")
+    assert o["token_num"].tolist() == ref["token_num"].tolist()
+    assert o["ids"] == ref["ids"]
+    # a predictor that never fires: bias -> very negative => alpha ~ 0, tail 0.45 < 1 => zero tokens everywhere
+    p2 = dict(p)
+    p2["predictor.cif_output.bias"] = torch.full((1,), -30.0)
+    m = funasr_b200.ParaformerB200(**_tiny_conf())
+    m.load_state_dict(p2, strict=True)
+    m.to(DEV).eval()
+    fe = funasr_b200.WavFrontendB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0, cmvn=cmvn)
+    res = m.inference([w.numpy() for w in wavs], key=["a", "b", "c"], tokenizer=None, frontend=fe, device=DEV)
+    assert res[0] == [] or res == ([], res[1])
+    ref2 = O.paraformer_forward(wavs, p2, cmvn, cfg.enc_layers, cfg.dec_layers)
+    assert int(ref2["token_num"].max()) == 0
