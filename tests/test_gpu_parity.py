@@ -462,3 +462,29 @@ def test_silence_and_minimum_length():
     assert res[0] == [] or res == ([], res[1])
     ref2 = O.paraformer_forward(wavs, p2, cmvn, cfg.enc_layers, cfg.dec_layers)
     assert int(ref2["token_num"].max()) == 0
+
+
+def test_abi_error_codes():
+    """The C ABI reports problems as negative status codes (no exceptions, no silent fallback): bad arguments (-1),
+    workspace too small (-3), unsupported shapes (-4); the Python layer turns them into FunasrB200Error."""
+    abi, lib = _lib()
+    from funasr_b200 import synth
+    cfg = synth.PARAFORMER_TINY
+    eng = _engine(cfg, 5, "bf16x3")
+    B, T = 2, 40
+    feats = torch.randn(B, T, 560, device=DEV)
+    lens = torch.tensor([40, 17], dtype=torch.int32, device=DEV)
+    out = torch.empty(B, T, 512, device=DEV)
+    need = lib.fa_sanm_encoder_workspace_bytes(B, T, eng.mode)
+    ws = torch.empty(need, dtype=torch.uint8, device=DEV)
+    ok = lib.fa_sanm_encoder_forward(C.byref(eng.enc), feats.data_ptr(), lens.data_ptr(), B, T, out.data_ptr(), eng.mode, ws.data_ptr(), need, _st())
+    assert ok == 0
+    assert lib.fa_sanm_encoder_forward(C.byref(eng.enc), feats.data_ptr(), lens.data_ptr(), B, T, out.data_ptr(), eng.mode, ws.data_ptr(), need // 4, _st()) == -3
+    assert lib.fa_sanm_encoder_forward(C.byref(eng.enc), None, lens.data_ptr(), B, T, out.data_ptr(), eng.mode, ws.data_ptr(), need, _st()) == -1
+    assert lib.fa_sanm_encoder_forward(C.byref(eng.enc), feats.data_ptr(), lens.data_ptr(), 0, T, out.data_ptr(), eng.mode, ws.data_ptr(), need, _st()) == -1
+    nm = abi.FaNorm(feats.data_ptr(), feats.data_ptr(), 4100, 1e-12)       # rows longer than the kernel supports
+    assert lib.fa_layernorm(feats.data_ptr(), 4, C.byref(nm), out.data_ptr(), None, 1.0, 1, _st()) == -4
+    assert lib.fa_fbank_lfr_cmvn(None, None, 1, 0, None, None, None, None, None, 1, _st()) == -1
+    with pytest.raises(abi.FunasrB200Error):
+        abi.check(-3, "demo")
+    torch.cuda.synchronize()
