@@ -49,7 +49,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   constexpr uint32_t K_HI_BYTES = 2 * AT_K_KBLK;          // pass A needs only the hi plane
   constexpr uint32_t P_BYTES = NPL * AT_P_TILE;
   constexpr int NT = NPL == 1 ? 1 : 3;
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align to 1024 B WITHOUT leaving the shared address space (a uintptr_t round trip makes every access a generic LD/ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sQ = smem;
   // K and V live in separate 2-deep rings: a K chunk is dead as soon as its score MMAs retire (long before P.V of the same
   // chunk), so the next K load is issued early and its latency hides behind softmax + P.V; V is only needed at P.V time.

@@ -181,6 +181,18 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
           const int64_t sc = 8 * p.ldc, s1 = 8 * p.ldr1, s2 = 8 * p.ldr2, so = 8 * p.ldo, sq = 8 * (int64_t)a.width;
           const int64_t plane_o = p.M * p.ldo, plane_q = p.M * (int64_t)a.width;
           const bool c_vec = (p.ldc & 3) == 0;
+          // residual rows are fetched for all four passes up front (memory-level parallelism: the out-projection and
+          // FFN-w_2 epilogues were latency bound on these loads), pointers advance by a fixed stride
+          float4 rv1[4], rv2[4];
+          if (EPI == EPI_F32) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              rv1[it] = (pr1 && it < rows_left) ? __ldg(reinterpret_cast<const float4*>(pr1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              rv2[it] = (pr2 && it < rows_left) ? __ldg(reinterpret_cast<const float4*>(pr2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (pr1) pr1 += s1;
+              if (pr2) pr2 += s2;
+            }
+          }
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             if (it < rows_left) {
@@ -188,16 +200,19 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
               float v0 = acc.x + bias4.x, v1 = acc.y + bias4.y, v2 = acc.z + bias4.z, v3 = acc.w + bias4.w;
               if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
               if (EPI == EPI_F32) {
-                if (pr1) { const float4 t = __ldg(reinterpret_cast<const float4*>(pr1 + it * s1)); v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w; }
-                if (pr2) { const float4 t = __ldg(reinterpret_cast<const float4*>(pr2 + it * s2)); v0 += t.x; v1 += t.y; v2 += t.z; v3 += t.w; }
+                v0 += rv1[it].x; v1 += rv1[it].y; v2 += rv1[it].z; v3 += rv1[it].w;
+                v0 += rv2[it].x; v1 += rv2[it].y; v2 += rv2[it].z; v3 += rv2[it].w;
               }
               if (EPI != EPI_PLANES && pc) {
-                if (c_vec) *reinterpret_cast<float4*>(pc + it * sc) = make_float4(v0, v1, v2, v3);
-                else { float* cr = pc + it * sc; cr[0] = v0; cr[1] = v1; cr[2] = v2; cr[3] = v3; }
+                if (c_vec) *reinterpret_cast<float4*>(pc) = make_float4(v0, v1, v2, v3);
+                else { pc[0] = v0; pc[1] = v1; pc[2] = v2; pc[3] = v3; }
               }
-              if (EPI == EPI_PLANES) store_planes4(po + it * so, plane_o, p.out_nplanes, v0, v1, v2, v3);
-              if (EPI == EPI_ATT && pq) store_planes4(pq + it * sq, plane_q, a.npl, __fmul_rn(v0, qs), __fmul_rn(v1, qs), __fmul_rn(v2, qs), __fmul_rn(v3, qs));
+              if (EPI == EPI_PLANES) store_planes4(po, plane_o, p.out_nplanes, v0, v1, v2, v3);
+              if (EPI == EPI_ATT && pq) store_planes4(pq, plane_q, a.npl, __fmul_rn(v0, qs), __fmul_rn(v1, qs), __fmul_rn(v2, qs), __fmul_rn(v3, qs));
             }
+            if (EPI != EPI_PLANES && pc) pc += sc;
+            if (EPI == EPI_PLANES) po += so;
+            if (EPI == EPI_ATT && pq) pq += sq;
           }
         } else {                                                   // ragged N tail (e.g. vocab 8404 / 25055): scalar, bounds checked
           for (int it = 0; it < 4 && it < rows_left; ++it) {
@@ -225,7 +240,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr uint32_t TILE_W_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = APL * TC_TILE_BYTES_A + WPL * TILE_W_BYTES;
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align to 1024 B WITHOUT leaving the shared address space (a uintptr_t round trip makes every access a generic LD/ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
@@ -342,7 +358,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   constexpr int BN = 256;
   constexpr uint32_t TILE_BYTES = 128 * TC_BK * 2;                 // 16 KB: 128 rows x 64 bf16
   constexpr uint32_t STAGE_BYTES = 2 * PL * TILE_BYTES;            // A planes + W-half planes of this CTA
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align to 1024 B WITHOUT leaving the shared address space (a uintptr_t round trip makes every access a generic LD/ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]

@@ -74,15 +74,16 @@ layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ 
       o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
       if (yr) yr[c4] = o;
       if (planes) {
-        float e[4] = {o.x, o.y, o.z, o.w};
+        float e0 = o.x, e1 = o.y, e2 = o.z, e3 = o.w;
         __nv_bfloat16* dst = planes + row * cols_pad + 4 * c4;
-        for (int pl = 0; pl < nplanes; ++pl) {
-          __nv_bfloat16 hh[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { hh[k] = __float2bfloat16_rn(e[k]); e[k] -= __bfloat162float(hh[k]); }
-          __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(dst + pl * plane_elems);
-          d2[0] = __halves2bfloat162(hh[0], hh[1]);
-          d2[1] = __halves2bfloat162(hh[2], hh[3]);
+        for (int pl = 0; pl < nplanes; ++pl) {       // packed cvt.rn.bf16x2 (ALU pipe), bf16 -> fp32 by shifts
+          const __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1), p23 = __floats2bfloat162_rn(e2, e3);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&p01);
+          pk.y = *reinterpret_cast<const uint32_t*>(&p23);
+          *reinterpret_cast<uint2*>(dst + pl * plane_elems) = pk;
+          e0 -= __uint_as_float(pk.x << 16); e1 -= __uint_as_float(pk.x & 0xFFFF0000u);
+          e2 -= __uint_as_float(pk.y << 16); e3 -= __uint_as_float(pk.y & 0xFFFF0000u);
         }
       }
     } else if (planes && 4 * c4 < cols_pad) {          // zero the K padding (e.g. 560 -> 576)
