@@ -196,8 +196,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + hf * 32, v);
         const int kbase = i * AT_BKEY + hf * 32;
+        if (kbase + 32 <= klen) {                       // whole half-chunk valid (warp-uniform): no per-element predicates
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) if (kbase + jj < klen) m = fmaxf(m, __uint_as_float(v[jj]));
+          for (int jj = 0; jj < 32; ++jj) m = fmaxf(m, __uint_as_float(v[jj]));
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) if (kbase + jj < klen) m = fmaxf(m, __uint_as_float(v[jj]));
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);
@@ -216,11 +221,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + hf * 32, v);
           const int kbase = t * AT_BKEY + hf * 32;
+          if (kbase + 32 <= klen) {                     // fully valid half-chunk: straight-line exp / accumulate
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const float pv = (kbase + jj < klen) ? __expf(__uint_as_float(v[jj]) - m) : 0.f;
-            pr[jj] = pv;
-            l += pv;
+            for (int jj = 0; jj < 32; ++jj) { const float pv = __expf(__uint_as_float(v[jj]) - m); pr[jj] = pv; l += pv; }
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              const float pv = (kbase + jj < klen) ? __expf(__uint_as_float(v[jj]) - m) : 0.f;
+              pr[jj] = pv;
+              l += pv;
+            }
           }
         }
         tc_fence_before();

@@ -101,60 +101,40 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
   const AttnSinks& a = p.att;
 #pragma unroll 1
   for (int c0 = half * EPI_CH; c0 < BN; c0 += 2 * EPI_CH) {
+    const int col0 = tile_col0 + c0;
     {
       uint32_t r[16];
       tmem_ld_32x16(tmem_acc + c0, r);
       float* srow = stage + lane * EPI_LD;
 #pragma unroll
       for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    }
-    __syncwarp();
-    const int col0 = tile_col0 + c0;
-    if (col0 < p.N && row0 < p.M) {
-      const bool full = col0 + EPI_CH <= p.N;
-      const bool v_sink = EPI == EPI_ATT && col0 >= a.v0 && col0 < a.v0 + a.width;
-      if (EPI == EPI_ATT && v_sink) {
-        // transposed per-head V planes: lane&15 = head dim, lane>>4 = which half of the eight 4-key groups
-        const int cl = lane & 15, gh = lane >> 4;
-        const int cv = col0 - a.v0 + cl;                           // h*128 + d
-        const float bv = p.bias ? __ldg(p.bias + col0 + cl) : 0.f;
+      if (EPI == EPI_ATT && col0 >= a.v0 && col0 < a.v0 + a.width && row0 + lane < p.M) {
+        // per-head transposed V planes straight from the row-per-lane registers: for a fixed head dim the 32 lanes hold 32
+        // consecutive keys -> every 2-byte store instruction covers one 64-byte run (2 sectors) instead of 32 scattered ones
+        const int64_t rw = row0 + lane;
+        const int b2 = (int)(rw / a.t_rows), t2 = (int)(rw - (int64_t)b2 * a.t_rows);
+        const int cv0 = col0 - a.v0;
+        __nv_bfloat16* dst = a.vt_planes + ((int64_t)b2 * a.width + cv0) * a.t_pad + t2;
         const int64_t plane = (int64_t)(p.M / a.t_rows) * a.width * a.t_pad;
-        const int bb0 = (int)(row0 / a.t_rows), tt0 = (int)(row0 - (int64_t)bb0 * a.t_rows);
-        const bool fast = ((tt0 & 3) == 0) && ((a.t_rows & 3) == 0) && (row0 + 32 <= p.M);
-        if (fast) {
-          // 4 consecutive keys per store stay inside one utterance (t_rows % 4 == 0); one 64-bit address per lane, then
-          // +4 keys per group, hopping to the next utterance's plane row when the 32-row block crosses a boundary
-          __nv_bfloat16* base = a.vt_planes + ((int64_t)bb0 * a.width + cv) * a.t_pad;
-          const int64_t utt_stride = (int64_t)a.width * a.t_pad;
 #pragma unroll
-          for (int gi = 0; gi < 4; ++gi) {
-            const int g = gh * 4 + gi;
-            const float* sp4 = stage + (4 * g) * EPI_LD + cl;
-            const float x0 = sp4[0] + bv, x1 = sp4[EPI_LD] + bv, x2 = sp4[2 * EPI_LD] + bv, x3 = sp4[3 * EPI_LD] + bv;
-            int tt = tt0 + 4 * g;
-            __nv_bfloat16* dst = base;
-            if (tt >= a.t_rows) { tt -= a.t_rows; dst += utt_stride; }     // 32 rows span at most two utterances when t_rows >= 32
-            if (tt >= a.t_rows) { const int hop = tt / a.t_rows; tt -= hop * a.t_rows; dst += hop * utt_stride; }
-            store_planes4(dst + tt, plane, a.npl, x0, x1, x2, x3);
-          }
-        } else {
-#pragma unroll 1
-          for (int gi = 0; gi < 4; ++gi) {
-            const int g = gh * 4 + gi;
-            for (int i = 0; i < 4; ++i) {
-              const int64_t rw = row0 + 4 * g + i;
-              if (rw >= p.M) break;
-              const int b2 = (int)(rw / a.t_rows), t2 = (int)(rw - (int64_t)b2 * a.t_rows);
-              float xv = stage[(4 * g + i) * EPI_LD + cl] + bv;
-              for (int pl = 0; pl < a.npl; ++pl) {
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(xv);
-                a.vt_planes[pl * plane + ((int64_t)b2 * a.width + cv) * a.t_pad + t2] = h0;
-                xv -= __bfloat162float(h0);
-              }
-            }
+        for (int j = 0; j < 16; j += 2) {
+          float x0 = __uint_as_float(r[j]), x1 = __uint_as_float(r[j + 1]);
+          if (p.bias) { x0 += __ldg(p.bias + col0 + j); x1 += __ldg(p.bias + col0 + j + 1); }
+          __nv_bfloat16* d0 = dst + (int64_t)j * a.t_pad;
+          for (int pl = 0; pl < a.npl; ++pl) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+            d0[pl * plane] = __ushort_as_bfloat16((unsigned short)(hb & 0xFFFFu));
+            d0[pl * plane + a.t_pad] = __ushort_as_bfloat16((unsigned short)(hb >> 16));
+            x0 -= __uint_as_float(hb << 16); x1 -= __uint_as_float(hb & 0xFFFF0000u);
           }
         }
       }
+    }
+    __syncwarp();
+    if (col0 < p.N && row0 < p.M) {
+      const bool full = col0 + EPI_CH <= p.N;
+      const bool v_sink = EPI == EPI_ATT && col0 >= a.v0 && col0 < a.v0 + a.width;
       // coalesced row-major phase: 8 rows x 4 float4 per pass.  All row/column address arithmetic is hoisted: one 64-bit
       // multiply per output stream per chunk, then constant strides (8 rows) across the four passes.
       const bool q_sink = EPI == EPI_ATT && col0 >= a.q0 && col0 < a.q0 + a.width;
