@@ -74,17 +74,42 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// x = hi + mid + lo split of 4 values, packed converts (cvt.rn.bf16x2.f32), bf16 -> f32 by bit shifts
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_stride, int npl, float x0, float x1, float x2, float x3) {
-  for (int pl = 0; pl < npl; ++pl) {
+// x = hi + mid + lo split of 4 values, packed converts (cvt.rn.bf16x2.f32), bf16 -> f32 by bit shifts.  NPL is a compile-
+// time constant: with a runtime plane count the loop compiled to a branchy 4x-unrolled body (ncu: 47 % of all executed
+// instructions of the FFN-w_1 GEMM sat in this function).
+template <int NPL>
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_stride, float x0, float x1, float x2, float x3) {
+#pragma unroll
+  for (int pl = 0; pl < NPL; ++pl) {
     const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
     uint2 pk;
     pk.x = *reinterpret_cast<const uint32_t*>(&p01);
     pk.y = *reinterpret_cast<const uint32_t*>(&p23);
-    *reinterpret_cast<uint2*>(dst + pl * plane_stride) = pk;
-    if (pl + 1 < npl) {
+    *reinterpret_cast<uint2*>(dst) = pk;
+    if (pl + 1 < NPL) {
+      dst += plane_stride;
       x0 -= __uint_as_float(pk.x << 16); x1 -= __uint_as_float(pk.x & 0xFFFF0000u);
       x2 -= __uint_as_float(pk.y << 16); x3 -= __uint_as_float(pk.y & 0xFFFF0000u);
+    }
+  }
+}
+
+// per-head transposed V planes straight from the row-per-lane registers: for a fixed head dim the 32 lanes hold 32
+// consecutive keys, so every 2-byte store instruction covers one 64-byte run
+template <int NPL>
+__device__ __forceinline__ void store_vt16(__nv_bfloat16* dst, int64_t t_pad, int64_t plane, const uint32_t (&r)[16], const float* bias) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    float x0 = __uint_as_float(r[j]), x1 = __uint_as_float(r[j + 1]);
+    if (bias) { x0 += __ldg(bias + j); x1 += __ldg(bias + j + 1); }
+    __nv_bfloat16* d0 = dst + (int64_t)j * t_pad;
+#pragma unroll
+    for (int pl = 0; pl < NPL; ++pl) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+      const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+      d0[0] = __ushort_as_bfloat16((unsigned short)(hb & 0xFFFFu));
+      d0[t_pad] = __ushort_as_bfloat16((unsigned short)(hb >> 16));
+      if (pl + 1 < NPL) { d0 += plane; x0 -= __uint_as_float(hb << 16); x1 -= __uint_as_float(hb & 0xFFFF0000u); }
     }
   }
 }
@@ -95,10 +120,118 @@ __device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_
 //   EPI_ATT    attention operands: scaled q planes / k planes / per-head transposed v planes (+ fp32 v for FSMN)
 constexpr int EPI_F32 = 0, EPI_PLANES = 1, EPI_ATT = 2;
 
-template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
+// Interior tiles (all 32 rows and all BN columns in range): straight-line code, no bounds predicates, every row base
+// computed once per tile and advanced by constant strides.
+template <int BN, int EPI, int NPL>
+__device__ __forceinline__ void epilogue_fast(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
                                               int half) {
   const AttnSinks& a = p.att;
+  constexpr int QPL = NPL < 2 ? NPL : 2;             // attention operands carry at most two planes
+  const int rr0 = lane >> 2, c4 = (lane & 3) * 4;
+  const int64_t rfirst = row0 + rr0;
+  float* srow = stage + lane * EPI_LD;
+  const float* sp = stage + rr0 * EPI_LD + c4;
+  float* c_row = (EPI != EPI_PLANES && p.C) ? p.C + rfirst * p.ldc + c4 : nullptr;
+  const float* r1_row = (EPI == EPI_F32 && p.r1) ? p.r1 + rfirst * p.ldr1 + c4 : nullptr;
+  const float* r2_row = (EPI == EPI_F32 && p.r2) ? p.r2 + rfirst * p.ldr2 + c4 : nullptr;
+  __nv_bfloat16* o_row = EPI == EPI_PLANES ? p.out_planes + rfirst * p.ldo + c4 : nullptr;
+  __nv_bfloat16* q_row = EPI == EPI_ATT ? a.q_planes + rfirst * a.width + c4 : nullptr;
+  __nv_bfloat16* k_row = EPI == EPI_ATT ? a.k_planes + rfirst * a.width + c4 : nullptr;
+  const int64_t sc = 8 * p.ldc, s1 = 8 * p.ldr1, s2 = 8 * p.ldr2, so = 8 * p.ldo, sq = 8 * (int64_t)a.width;
+  const int64_t plane_o = p.M * p.ldo, plane_q = p.M * (int64_t)a.width;
+  const bool c_vec = (p.ldc & 3) == 0;
+  __nv_bfloat16* vt_row = nullptr;
+  int64_t vt_plane = 0;
+  if (EPI == EPI_ATT) {
+    const int64_t rw = row0 + lane;
+    const int b2 = (int)(rw / a.t_rows), t2 = (int)(rw - (int64_t)b2 * a.t_rows);
+    vt_row = a.vt_planes + (int64_t)b2 * a.width * a.t_pad + t2;
+    vt_plane = (p.M / a.t_rows) * (int64_t)a.width * a.t_pad;
+  }
+#pragma unroll 1
+  for (int c0 = half * EPI_CH; c0 < BN; c0 += 2 * EPI_CH) {
+    const int col0 = tile_col0 + c0;
+    const bool v_sink = EPI == EPI_ATT && col0 >= a.v0 && col0 < a.v0 + a.width;
+    {
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_acc + c0, r);
+      if (EPI != EPI_ATT || !v_sink || p.C != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+      if (EPI == EPI_ATT && v_sink)
+        store_vt16<QPL>(vt_row + (int64_t)(col0 - a.v0) * a.t_pad, a.t_pad, vt_plane, r, p.bias ? p.bias + col0 : nullptr);
+    }
+    __syncwarp();
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c4));
+    if (EPI == EPI_F32) {
+      float* pc = c_row + col0;
+      const float* pr1 = r1_row ? r1_row + col0 : nullptr;
+      const float* pr2 = r2_row ? r2_row + col0 : nullptr;
+      // residual rows of all four passes are fetched up front (memory-level parallelism)
+      float4 rv1[4], rv2[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        rv1[it] = pr1 ? __ldg(reinterpret_cast<const float4*>(pr1 + it * s1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rv2[it] = pr2 ? __ldg(reinterpret_cast<const float4*>(pr2 + it * s2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
+        float v0 = acc.x + bias4.x, v1 = acc.y + bias4.y, v2 = acc.z + bias4.z, v3 = acc.w + bias4.w;
+        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+        v0 += rv1[it].x; v1 += rv1[it].y; v2 += rv1[it].z; v3 += rv1[it].w;
+        v0 += rv2[it].x; v1 += rv2[it].y; v2 += rv2[it].z; v3 += rv2[it].w;
+        if (c_vec) *reinterpret_cast<float4*>(pc) = make_float4(v0, v1, v2, v3);
+        else { pc[0] = v0; pc[1] = v1; pc[2] = v2; pc[3] = v3; }
+        pc += sc;
+      }
+    } else if (EPI == EPI_PLANES) {
+      __nv_bfloat16* po = o_row + col0;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
+        float v0 = acc.x + bias4.x, v1 = acc.y + bias4.y, v2 = acc.z + bias4.z, v3 = acc.w + bias4.w;
+        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+        store_planes4<NPL>(po, plane_o, v0, v1, v2, v3);
+        po += so;
+      }
+    } else {
+      const bool q_sink = col0 >= a.q0 && col0 < a.q0 + a.width;
+      const bool k_sink = col0 >= a.k0 && col0 < a.k0 + a.width;
+      if (q_sink || k_sink) {
+        __nv_bfloat16* pq = q_sink ? q_row + (col0 - a.q0) : k_row + (col0 - a.k0);
+        const float qs = q_sink ? a.qscale : 1.0f;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
+          store_planes4<QPL>(pq, plane_q, __fmul_rn(acc.x + bias4.x, qs), __fmul_rn(acc.y + bias4.y, qs), __fmul_rn(acc.z + bias4.z, qs),
+                             __fmul_rn(acc.w + bias4.w, qs));
+          pq += sq;
+        }
+      } else if (v_sink && c_row) {                    // fp32 V rows feed the FSMN memory block
+        float* pc = c_row + col0;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
+          const float4 o = make_float4(acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w);
+          if (c_vec) *reinterpret_cast<float4*>(pc) = o;
+          else { pc[0] = o.x; pc[1] = o.y; pc[2] = o.z; pc[3] = o.w; }
+          pc += sc;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Edge tiles (row tail of M, ragged N such as vocab 8404 / 25055): every access bounds checked.
+template <int BN, int EPI, int NPL>
+__device__ __noinline__ void epilogue_edge(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
+                                           int half) {
+  const AttnSinks& a = p.att;
+  constexpr int QPL = NPL < 2 ? NPL : 2;
 #pragma unroll 1
   for (int c0 = half * EPI_CH; c0 < BN; c0 += 2 * EPI_CH) {
     const int col0 = tile_col0 + c0;
@@ -109,34 +242,16 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
 #pragma unroll
       for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       if (EPI == EPI_ATT && col0 >= a.v0 && col0 < a.v0 + a.width && row0 + lane < p.M) {
-        // per-head transposed V planes straight from the row-per-lane registers: for a fixed head dim the 32 lanes hold 32
-        // consecutive keys -> every 2-byte store instruction covers one 64-byte run (2 sectors) instead of 32 scattered ones
         const int64_t rw = row0 + lane;
         const int b2 = (int)(rw / a.t_rows), t2 = (int)(rw - (int64_t)b2 * a.t_rows);
-        const int cv0 = col0 - a.v0;
-        __nv_bfloat16* dst = a.vt_planes + ((int64_t)b2 * a.width + cv0) * a.t_pad + t2;
-        const int64_t plane = (int64_t)(p.M / a.t_rows) * a.width * a.t_pad;
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          float x0 = __uint_as_float(r[j]), x1 = __uint_as_float(r[j + 1]);
-          if (p.bias) { x0 += __ldg(p.bias + col0 + j); x1 += __ldg(p.bias + col0 + j + 1); }
-          __nv_bfloat16* d0 = dst + (int64_t)j * a.t_pad;
-          for (int pl = 0; pl < a.npl; ++pl) {
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
-            d0[pl * plane] = __ushort_as_bfloat16((unsigned short)(hb & 0xFFFFu));
-            d0[pl * plane + a.t_pad] = __ushort_as_bfloat16((unsigned short)(hb >> 16));
-            x0 -= __uint_as_float(hb << 16); x1 -= __uint_as_float(hb & 0xFFFF0000u);
-          }
-        }
+        store_vt16<QPL>(a.vt_planes + ((int64_t)b2 * a.width + (col0 - a.v0)) * a.t_pad + t2, a.t_pad,
+                        (p.M / a.t_rows) * (int64_t)a.width * a.t_pad, r, p.bias ? p.bias + col0 : nullptr);
       }
     }
     __syncwarp();
     if (col0 < p.N && row0 < p.M) {
       const bool full = col0 + EPI_CH <= p.N;
       const bool v_sink = EPI == EPI_ATT && col0 >= a.v0 && col0 < a.v0 + a.width;
-      // coalesced row-major phase: 8 rows x 4 float4 per pass.  All row/column address arithmetic is hoisted: one 64-bit
-      // multiply per output stream per chunk, then constant strides (8 rows) across the four passes.
       const bool q_sink = EPI == EPI_ATT && col0 >= a.q0 && col0 < a.q0 + a.width;
       const bool k_sink = EPI == EPI_ATT && col0 >= a.k0 && col0 < a.k0 + a.width;
       const bool want_c = EPI == EPI_F32 ? true : (EPI == EPI_ATT ? (p.C != nullptr && v_sink) : false);
@@ -151,57 +266,32 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
           else { float* bp = reinterpret_cast<float*>(&bias4); for (int e = 0; e < 4; ++e) if (col + e < p.N) bp[e] = __ldg(p.bias + col + e); }
         }
         const float* sp = stage + rr0 * EPI_LD + c4;
-        if (EPI != EPI_F32 || full) {
-          float* pc = want_c ? p.C + rfirst * p.ldc + col : nullptr;
-          const float* pr1 = (EPI == EPI_F32 && p.r1) ? p.r1 + rfirst * p.ldr1 + col : nullptr;
-          const float* pr2 = (EPI == EPI_F32 && p.r2) ? p.r2 + rfirst * p.ldr2 + col : nullptr;
-          __nv_bfloat16* po = EPI == EPI_PLANES ? p.out_planes + rfirst * p.ldo + col : nullptr;
-          __nv_bfloat16* pq = q_sink ? a.q_planes + rfirst * a.width + (col - a.q0) : (k_sink ? a.k_planes + rfirst * a.width + (col - a.k0) : nullptr);
-          const float qs = q_sink ? a.qscale : 1.0f;
-          const int64_t sc = 8 * p.ldc, s1 = 8 * p.ldr1, s2 = 8 * p.ldr2, so = 8 * p.ldo, sq = 8 * (int64_t)a.width;
-          const int64_t plane_o = p.M * p.ldo, plane_q = p.M * (int64_t)a.width;
-          const bool c_vec = (p.ldc & 3) == 0;
-          // residual rows are fetched for all four passes up front (memory-level parallelism: the out-projection and
-          // FFN-w_2 epilogues were latency bound on these loads), pointers advance by a fixed stride
-          float4 rv1[4], rv2[4];
-          if (EPI == EPI_F32) {
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              rv1[it] = (pr1 && it < rows_left) ? __ldg(reinterpret_cast<const float4*>(pr1)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              rv2[it] = (pr2 && it < rows_left) ? __ldg(reinterpret_cast<const float4*>(pr2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              if (pr1) pr1 += s1;
-              if (pr2) pr2 += s2;
-            }
-          }
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            if (it < rows_left) {
-              const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
-              float v0 = acc.x + bias4.x, v1 = acc.y + bias4.y, v2 = acc.z + bias4.z, v3 = acc.w + bias4.w;
-              if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-              if (EPI == EPI_F32) {
-                v0 += rv1[it].x; v1 += rv1[it].y; v2 += rv1[it].z; v3 += rv1[it].w;
-                v0 += rv2[it].x; v1 += rv2[it].y; v2 += rv2[it].z; v3 += rv2[it].w;
+        const bool c_vec = (p.ldc & 3) == 0;
+        for (int it = 0; it < 4 && it < rows_left; ++it) {
+          const int64_t row = rfirst + 8 * it;
+          const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
+          float vv[4] = {acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w};
+          if (p.relu) { for (int e = 0; e < 4; ++e) vv[e] = fmaxf(vv[e], 0.f); }
+          if (full) {
+            if (EPI == EPI_F32) {
+              for (int e = 0; e < 4; ++e) {
+                if (p.r1) vv[e] += __ldg(p.r1 + row * p.ldr1 + col + e);
+                if (p.r2) vv[e] += __ldg(p.r2 + row * p.ldr2 + col + e);
               }
-              if (EPI != EPI_PLANES && pc) {
-                if (c_vec) *reinterpret_cast<float4*>(pc) = make_float4(v0, v1, v2, v3);
-                else { pc[0] = v0; pc[1] = v1; pc[2] = v2; pc[3] = v3; }
-              }
-              if (EPI == EPI_PLANES) store_planes4(po, plane_o, p.out_nplanes, v0, v1, v2, v3);
-              if (EPI == EPI_ATT && pq) store_planes4(pq, plane_q, a.npl, __fmul_rn(v0, qs), __fmul_rn(v1, qs), __fmul_rn(v2, qs), __fmul_rn(v3, qs));
             }
-            if (EPI != EPI_PLANES && pc) pc += sc;
-            if (EPI == EPI_PLANES) po += so;
-            if (EPI == EPI_ATT && pq) pq += sq;
-          }
-        } else {                                                   // ragged N tail (e.g. vocab 8404 / 25055): scalar, bounds checked
-          for (int it = 0; it < 4 && it < rows_left; ++it) {
-            const int64_t row = rfirst + 8 * it;
-            const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
-            const float vv[4] = {acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w};
+            if (want_c) {
+              float* pc = p.C + row * p.ldc + col;
+              if (c_vec) *reinterpret_cast<float4*>(pc) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+              else { pc[0] = vv[0]; pc[1] = vv[1]; pc[2] = vv[2]; pc[3] = vv[3]; }
+            }
+            if (EPI == EPI_PLANES) store_planes4<NPL>(p.out_planes + row * p.ldo + col, p.M * p.ldo, vv[0], vv[1], vv[2], vv[3]);
+            if (q_sink) store_planes4<QPL>(a.q_planes + row * a.width + (col - a.q0), p.M * (int64_t)a.width, __fmul_rn(vv[0], a.qscale),
+                                           __fmul_rn(vv[1], a.qscale), __fmul_rn(vv[2], a.qscale), __fmul_rn(vv[3], a.qscale));
+            if (k_sink) store_planes4<QPL>(a.k_planes + row * a.width + (col - a.k0), p.M * (int64_t)a.width, vv[0], vv[1], vv[2], vv[3]);
+          } else {                                                   // ragged N tail: scalar (fp32 output only)
             for (int e = 0; e < 4; ++e) {
               if (col + e >= p.N) break;
-              float x = p.relu ? fmaxf(vv[e], 0.f) : vv[e];
+              float x = vv[e];
               if (p.r1) x += __ldg(p.r1 + row * p.ldr1 + col + e);
               if (p.r2) x += __ldg(p.r2 + row * p.ldr2 + col + e);
               if (want_c) p.C[row * p.ldc + col + e] = x;
@@ -214,9 +304,16 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_a
   }
 }
 
+template <int BN, int EPI, int NPL>
+__device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
+                                              int half) {
+  if (row0 + 32 <= p.M && tile_col0 + BN <= p.N) epilogue_fast<BN, EPI, NPL>(p, tmem_acc, row0, tile_col0, stage, lane, half);
+  else epilogue_edge<BN, EPI, NPL>(p, tmem_acc, row0, tile_col0, stage, lane, half);
+}
+
 template <int BN, int STAGES, int APL, int WPL, int EPI>  // APL / WPL: A / W planes resident per stage
 __global__ void __launch_bounds__(384, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr uint32_t TILE_W_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = APL * TC_TILE_BYTES_A + WPL * TILE_W_BYTES;
@@ -309,7 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_warp<BN, EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32, tn * BN, epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half);
+      epilogue_warp<BN, EPI, APL>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32, tn * BN, epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);        // 4 arrivals (one per epilogue warp) free the accumulator
@@ -333,7 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // tcgen05.mma.cta_group::2 (M=256); each CTA drains its own 128 TMEM lanes in the epilogue.
 template <int STAGES, int PL, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int BN = 256;
   constexpr uint32_t TILE_BYTES = 128 * TC_BK * 2;                 // 16 KB: 128 rows x 64 bf16
@@ -424,7 +521,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_warp<BN, EPI>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * 256 + rank * 128 + q * 32, tn * BN, epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half);
+      epilogue_warp<BN, EPI, PL>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * 256 + rank * 128 + q * 32, tn * BN, epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
