@@ -38,7 +38,7 @@ struct AttTcParams {
 
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 softmax warps
 
-template <int NPL>
+template <int NPL, int OPL>   // NPL: operand planes (1 | 2); OPL: context planes written (0 = fp32 context only)
 __global__ void __launch_bounds__(384, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const AttTcParams p) {
@@ -46,27 +46,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   constexpr uint32_t Q_BYTES = NPL * 2 * AT_Q_KBLK;
   constexpr uint32_t K_BYTES = NPL * 2 * AT_K_KBLK;
   constexpr uint32_t V_BYTES = NPL * AT_V_TILE;
-  constexpr uint32_t K_HI_BYTES = 2 * AT_K_KBLK;          // pass A needs only the hi plane
   constexpr uint32_t P_BYTES = NPL * AT_P_TILE;
   constexpr int NT = NPL == 1 ? 1 : 3;
   // align to 1024 B WITHOUT leaving the shared address space (a uintptr_t round trip makes every access a generic LD/ST)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sQ = smem;
-  // K and V live in separate 2-deep rings: a K chunk is dead as soon as its score MMAs retire (long before P.V of the same
-  // chunk), so the next K load is issued early and its latency hides behind softmax + P.V; V is only needed at P.V time.
-  unsigned char* sKV = sQ + Q_BYTES;          // K ring [2][K_BYTES] followed by V ring [2][V_BYTES]
-  unsigned char* sV = sKV + 2 * K_BYTES;
-  unsigned char* sP = sV + 2 * V_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  // K and V chunks share ONE 3-slot ring, filled in exactly the order the MMA warp consumes them
+  //   pass A: Khi(0) .. Khi(nc-1)          pass B: K(0), K(1), V(0), K(2), V(1), ..., K(nc-1), V(nc-2), V(nc-1)
+  // (a K chunk is dead once its score MMAs retire, its V twin only at P.V time, and S(t+1) is issued before P.V(t)), which
+  // frees 32 KB against separate 2+2 rings — spent on double buffering P, so softmax(t+1) writes its probabilities while
+  // P.V(t) is still running instead of waiting for it (v2 was bound by that hand-off: tensor pipe 34 %).
+  constexpr uint32_t SLOT_BYTES = K_BYTES > V_BYTES ? K_BYTES : V_BYTES;
+  unsigned char* sRing = sQ + Q_BYTES;
+  unsigned char* sP = sRing + 3 * SLOT_BYTES;        // [2][P_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
   uint64_t* q_full = bars;            // [1]
-  uint64_t* k_full = bars + 1;        // [2]
-  uint64_t* k_empty = bars + 3;       // [2]
-  uint64_t* v_full = bars + 5;        // [2]
-  uint64_t* v_empty = bars + 7;       // [2]
-  uint64_t* s_full = bars + 9;        // [2]
-  uint64_t* s_empty = bars + 11;      // [2]
-  uint64_t* p_full = bars + 13;       // [1]
-  uint64_t* p_empty = bars + 14;      // [1]
+  uint64_t* r_full = bars + 1;        // [3]
+  uint64_t* r_empty = bars + 4;       // [3]
+  uint64_t* s_full = bars + 7;        // [2]
+  uint64_t* s_empty = bars + 9;       // [2]
+  uint64_t* p_full = bars + 11;       // [2]
+  uint64_t* p_empty = bars + 13;      // [2]
   uint64_t* o_full = bars + 15;       // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   float* s_red = reinterpret_cast<float*>(bars + 17);   // [2][128] row max / row sum exchange between column halves
@@ -75,16 +75,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
   const int klen = min(p.key_lens[b], p.tk);
   const int nc = (klen + AT_BKEY - 1) / AT_BKEY;     // key chunks with at least one valid key
-  const int njobs = 2 * nc;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
+    for (int s = 0; s < 3; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8);
+      mbar_init(&p_full[s], 8); mbar_init(&p_empty[s], 1);
     }
-    mbar_init(p_full, 8); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 256);
@@ -104,31 +104,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int kb = 0; kb < 2; ++kb)
           tma_load_2d(sQ + (pl * 2 + kb) * AT_Q_KBLK, &map_q, q_full, h * AT_D + kb * 64,
                       (int)(pl * p.q_plane_rows + (int64_t)b * p.tq + q0));
-      for (int i = 0; i < njobs; ++i) {                       // K ring: every job (pass A: hi plane only)
-        const int st = i & 1, j = i < nc ? i : i - nc;
-        const bool passB = i >= nc;
-        mbar_wait(&k_empty[st], (((uint32_t)i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&k_full[st], passB ? K_BYTES : K_HI_BYTES);
-        unsigned char* sk = sKV + st * K_BYTES;
-        const int npl_load = passB ? NPL : 1;
+      uint32_t n = 0;                                       // ring sequence number
+      auto load_k = [&](int j, int npl_load) {
+        const uint32_t slot = n % 3u;
+        mbar_wait(&r_empty[slot], ((n / 3u) & 1u) ^ 1u);
+        mbar_expect_tx(&r_full[slot], (uint32_t)npl_load * 2u * AT_K_KBLK);
+        unsigned char* dst = sRing + slot * SLOT_BYTES;
         for (int pl = 0; pl < npl_load; ++pl)
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb)
-            tma_load_2d(sk + (pl * 2 + kb) * AT_K_KBLK, &map_k, &k_full[st], h * AT_D + kb * 64,
+            tma_load_2d(dst + (pl * 2 + kb) * AT_K_KBLK, &map_k, &r_full[slot], h * AT_D + kb * 64,
                         (int)(pl * p.k_plane_rows + (int64_t)b * p.tk + j * AT_BKEY));
-      }
-    }
-  } else if (warp == 3) {
-    // ===================== V producer (pass B chunks) =====================
-    if (lane == 0 && nc > 0) {
-      for (int t = 0; t < nc; ++t) {
-        const int st = t & 1;
-        mbar_wait(&v_empty[st], (((uint32_t)t >> 1) & 1) ^ 1);
-        mbar_expect_tx(&v_full[st], V_BYTES);
+        ++n;
+      };
+      auto load_v = [&](int t) {
+        const uint32_t slot = n % 3u;
+        mbar_wait(&r_empty[slot], ((n / 3u) & 1u) ^ 1u);
+        mbar_expect_tx(&r_full[slot], V_BYTES);
+        unsigned char* dst = sRing + slot * SLOT_BYTES;
 #pragma unroll
         for (int pl = 0; pl < NPL; ++pl)
-          tma_load_2d(sV + st * V_BYTES + pl * AT_V_TILE, &map_v, &v_full[st], t * AT_BKEY,
+          tma_load_2d(dst + pl * AT_V_TILE, &map_v, &r_full[slot], t * AT_BKEY,
                       (int)(pl * p.v_plane_rows + ((int64_t)b * p.heads + h) * AT_D));
+        ++n;
+      };
+      for (int i = 0; i < nc; ++i) load_k(i, 1);            // pass A: hi plane only
+      load_k(0, NPL);
+      for (int t = 0; t < nc; ++t) {
+        if (t + 1 < nc) load_k(t + 1, NPL);
+        load_v(t);
       }
     }
   } else if (warp == 1) {
@@ -137,34 +141,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       constexpr uint32_t idesc_s = make_idesc_bf16(AT_BQ, AT_BKEY);
       constexpr uint32_t idesc_o = make_idesc_bf16(AT_BQ, AT_D);
       const int ta[3] = {0, 0, 1}, tb[3] = {0, 1, 0};
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      const uint32_t q_addr = smem_u32(sQ), p_addr0 = smem_u32(sP), ring_addr = smem_u32(sRing);
       mbar_wait(q_full, 0);
       tc_fence_after();
-      auto issue_pv = [&](int t) {   // t-th P.V of pass B
-        const int st = t & 1;
-        mbar_wait(p_full, (uint32_t)t & 1);
-        mbar_wait(&v_full[st], ((uint32_t)t >> 1) & 1);
+      uint32_t n = 0, sj = 0;                               // ring sequence number, score-tile job number
+      auto issue_qk = [&](int nterm) {
+        const uint32_t slot = n % 3u, st = sj & 1u;
+        mbar_wait(&r_full[slot], (n / 3u) & 1u);
+        mbar_wait(&s_empty[st], ((sj >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + st * V_BYTES);
-        for (int term = 0; term < NT; ++term) {
-          const uint64_t da = make_sw128_desc(p_addr + ta[term] * AT_P_TILE);
-          const uint64_t db = make_sw128_desc(v_addr + tb[term] * AT_V_TILE);
-#pragma unroll
-          for (int k = 0; k < AT_BKEY / 16; ++k) umma_bf16(tmem_o, da + 2 * k, db + 2 * k, idesc_o, (t | term | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&v_empty[st]);
-        umma_commit(p_empty);
-      };
-      for (int i = 0; i < njobs; ++i) {
-        const int st = i & 1;
-        const bool passB = i >= nc;
-        const uint32_t ph = ((uint32_t)i >> 1) & 1;
-        mbar_wait(&k_full[st], ph);
-        mbar_wait(&s_empty[st], ph ^ 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sKV + st * K_BYTES);
+        const uint32_t k_addr = ring_addr + slot * SLOT_BYTES;
         const uint32_t d_s = tmem_base + st * AT_BKEY;
-        const int nterm = passB ? NT : 1;
         for (int term = 0; term < nterm; ++term) {
 #pragma unroll
           for (int k = 0; k < AT_D / 16; ++k) {
@@ -174,10 +161,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
         umma_commit(&s_full[st]);
-        umma_commit(&k_empty[st]);                         // K chunk is dead once its score MMAs retire
-        if (passB && i > nc) issue_pv(i - nc - 1);
+        umma_commit(&r_empty[slot]);                        // K chunk is dead once its score MMAs retire
+        ++n; ++sj;
+      };
+      auto issue_pv = [&](int t) {
+        const uint32_t slot = n % 3u, pb = (uint32_t)t & 1u;
+        mbar_wait(&p_full[pb], ((uint32_t)t >> 1) & 1u);
+        mbar_wait(&r_full[slot], (n / 3u) & 1u);
+        tc_fence_after();
+        const uint32_t v_addr = ring_addr + slot * SLOT_BYTES, p_addr = p_addr0 + pb * P_BYTES;
+        for (int term = 0; term < NT; ++term) {
+          const uint64_t da = make_sw128_desc(p_addr + ta[term] * AT_P_TILE);
+          const uint64_t db = make_sw128_desc(v_addr + tb[term] * AT_V_TILE);
+#pragma unroll
+          for (int k = 0; k < AT_BKEY / 16; ++k) umma_bf16(tmem_o, da + 2 * k, db + 2 * k, idesc_o, (t | term | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&r_empty[slot]);
+        umma_commit(&p_empty[pb]);
+        ++n;
+      };
+      for (int i = 0; i < nc; ++i) issue_qk(1);
+      issue_qk(NT);
+      for (int t = 0; t < nc; ++t) {
+        if (t + 1 < nc) issue_qk(NT);
+        issue_pv(t);
       }
-      issue_pv(nc - 1);
       umma_commit(o_full);
     }
   } else if (warp >= 4) {
@@ -195,6 +203,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tc_fence_after();
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + hf * 32, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);           // values are in registers: release the score tile first
         const int kbase = i * AT_BKEY + hf * 32;
         if (kbase + 32 <= klen) {                       // whole half-chunk valid (warp-uniform): no per-element predicates
 #pragma unroll
@@ -203,23 +214,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) if (kbase + jj < klen) m = fmaxf(m, __uint_as_float(v[jj]));
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[st]);
       }
       s_red[hf * 128 + r] = m;
       softmax_bar();
       m = fmaxf(m, s_red[(hf ^ 1) * 128 + r]);     // finite: key 0 is always valid when nc > 0
       // ---- pass B: probabilities
-      uint32_t* prow = reinterpret_cast<uint32_t*>(sP + (size_t)r * 128);
       for (int t = 0; t < nc; ++t) {
-        const int i = nc + t, st = i & 1;
+        const int i = nc + t, st = i & 1, pb = t & 1;
         mbar_wait(&s_full[st], ((uint32_t)i >> 1) & 1);
         tc_fence_after();
         float pr[32];
         {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + hf * 32, v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[st]);
           const int kbase = t * AT_BKEY + hf * 32;
           if (kbase + 32 <= klen) {                     // fully valid half-chunk: straight-line exp / accumulate
 #pragma unroll
@@ -233,11 +243,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[st]);
         // P planes -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
-        mbar_wait(p_empty, ((uint32_t)t & 1) ^ 1);
+        uint32_t* prow = reinterpret_cast<uint32_t*>(sP + pb * P_BYTES + (size_t)r * 128);
+        mbar_wait(&p_empty[pb], (((uint32_t)t >> 1) & 1) ^ 1);
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           uint32_t hi[4], lo[4];
@@ -259,7 +267,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) mbar_arrive(&p_full[pb]);
       }
       softmax_bar();                   // everyone has read the exchanged maxima before the slots are reused
       s_red[hf * 128 + r] = l;
@@ -271,7 +279,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     // ---- epilogue: O / l for this warp's 32 rows x 64 head dims, staged through shared memory (the K/V ring is dead once
     //      o_full has fired) so that the context rows leave as coalesced 8-byte (bf16 planes) / 16-byte (fp32) stores
     const float inv = l > 0.f ? 1.0f / l : 0.f;
-    float* stage = reinterpret_cast<float*>(sKV) + (warp - 4) * (32 * 36);
+    float* stage = reinterpret_cast<float*>(sRing) + (warp - 4) * (32 * 36);
     const int64_t grow0 = (int64_t)b * p.tq + q0 + qw * 32;
 #pragma unroll 1
     for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
@@ -291,25 +299,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
       __syncwarp();
       const int rr0 = lane >> 3, c4 = (lane & 7) * 4;
+      const int col = h * AT_D + c0 + c4;
+      const int rows_ok = p.tq - (q0 + qw * 32);                      // valid rows of this warp's 32
+      float* pc = p.ctx ? p.ctx + (grow0 + rr0) * p.ldc + col : nullptr;
+      __nv_bfloat16* pp = OPL > 0 ? p.ctx_planes + (grow0 + rr0) * p.ldp + col : nullptr;
+      const int64_t plane = (int64_t)p.batch * p.tq * p.ldp;
+      const float* sp = stage + rr0 * 36 + c4;
 #pragma unroll 2
       for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + rr0;
-        if (q0 + qw * 32 + rr >= p.tq) break;
-        const float4 o4 = *reinterpret_cast<const float4*>(stage + rr * 36 + c4);
-        const int64_t grow = grow0 + rr;
-        const int col = h * AT_D + c0 + c4;
-        if (p.ctx) *reinterpret_cast<float4*>(p.ctx + grow * p.ldc + col) = o4;
-        if (p.ctx_planes) {
-          float x0 = o4.x, x1 = o4.y, x2 = o4.z, x3 = o4.w;
-          const int64_t plane = (int64_t)p.batch * p.tq * p.ldp;
-          for (int pl = 0; pl < p.out_nplanes; ++pl) {
-            const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&p01);
-            pk.y = *reinterpret_cast<const uint32_t*>(&p23);
-            *reinterpret_cast<uint2*>(p.ctx_planes + pl * plane + grow * p.ldp + col) = pk;
-            x0 -= __uint_as_float(pk.x << 16); x1 -= __uint_as_float(pk.x & 0xFFFF0000u);
-            x2 -= __uint_as_float(pk.y << 16); x3 -= __uint_as_float(pk.y & 0xFFFF0000u);
+        if (it * 4 + rr0 < rows_ok) {
+          const float4 o4 = *reinterpret_cast<const float4*>(sp + it * 4 * 36);
+          if (pc) *reinterpret_cast<float4*>(pc + (int64_t)it * 4 * p.ldc) = o4;
+          if (OPL > 0) {
+            float x0 = o4.x, x1 = o4.y, x2 = o4.z, x3 = o4.w;
+            __nv_bfloat16* dst = pp + (int64_t)it * 4 * p.ldp;
+#pragma unroll
+            for (int pl = 0; pl < OPL; ++pl) {
+              const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&p01);
+              pk.y = *reinterpret_cast<const uint32_t*>(&p23);
+              *reinterpret_cast<uint2*>(dst) = pk;
+              if (pl + 1 < OPL) {
+                dst += plane;
+                x0 -= __uint_as_float(pk.x << 16); x1 -= __uint_as_float(pk.x & 0xFFFF0000u);
+                x2 -= __uint_as_float(pk.y << 16); x3 -= __uint_as_float(pk.y & 0xFFFF0000u);
+              }
+            }
           }
         }
       }
@@ -409,6 +425,15 @@ int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk
   return attention_tc_planes_launch(qp, kp, vt, key_lens, batch, heads, tq, tk, ctx, ldc, ctx_planes, ldp, out_nplanes, mode, st);
 }
 
+template <int NPL, int OPL>
+static int launch_att(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttTcParams& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NPL * (2 * AT_Q_KBLK + 3 * AT_V_TILE + 2 * AT_P_TILE) + 1024 + 256 + 1024;
+  static bool done = false;
+  if (!done) { FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<NPL, OPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
+  attention_tc_kernel<NPL, OPL><<<grid, 384, smem, st>>>(mq, mk, mv, p);
+  return FA_OK;
+}
+
 // Operand planes already in place (written by the producing GEMMs' epilogues, gemm_tc.cu AttnSinks):
 // qp [npl][B*tq][H*128] (scaled), kp [npl][B*tk][H*128], vt [npl][B*H*128][round_up(tk,64)].
 int attention_tc_planes_launch(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfloat16* vt, const int32_t* key_lens,
@@ -429,16 +454,16 @@ int attention_tc_planes_launch(const __nv_bfloat16* qp, const __nv_bfloat16* kp,
   p.q_plane_rows = mq; p.k_plane_rows = mk; p.v_plane_rows = mv;
   p.ctx = ctx; p.ldc = ldc; p.ctx_planes = ctx_planes; p.ldp = ldp; p.out_nplanes = out_nplanes;
   dim3 grid((tq + AT_BQ - 1) / AT_BQ, heads, batch);
+  const int opl = ctx_planes ? out_nplanes : 0;
+  if (ctx_planes && (opl < 1 || opl > 3)) return FA_ERR_ARG;
   if (npl == 1) {
-    constexpr size_t smem = 2 * AT_Q_KBLK + 2 * (2 * AT_K_KBLK + AT_V_TILE) + AT_P_TILE + 1024 + 256 + 1024;
-    static bool done = false;
-    if (!done) { FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
-    attention_tc_kernel<1><<<grid, 384, smem, st>>>(mq_map, mk_map, mv_map, p);
+    if (opl > 1) return FA_ERR_UNSUPPORTED;
+    FA_RETURN_IF_ERR(opl == 0 ? (launch_att<1, 0>(grid, mq_map, mk_map, mv_map, p, st)) : (launch_att<1, 1>(grid, mq_map, mk_map, mv_map, p, st)));
   } else {
-    constexpr size_t smem = 2 * (2 * AT_Q_KBLK + 2 * (2 * AT_K_KBLK + AT_V_TILE) + AT_P_TILE) + 1024 + 256 + 1024;
-    static bool done = false;
-    if (!done) { FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
-    attention_tc_kernel<2><<<grid, 384, smem, st>>>(mq_map, mk_map, mv_map, p);
+    if (opl == 1) return FA_ERR_UNSUPPORTED;
+    FA_RETURN_IF_ERR(opl == 0 ? (launch_att<2, 0>(grid, mq_map, mk_map, mv_map, p, st))
+                     : opl == 2 ? (launch_att<2, 2>(grid, mq_map, mk_map, mv_map, p, st))
+                                : (launch_att<2, 3>(grid, mq_map, mk_map, mv_map, p, st)));
   }
   FA_CHECK_LAUNCH();
   return FA_OK;
