@@ -36,67 +36,79 @@ struct AttTcParams {
   __nv_bfloat16* ctx_planes; int64_t ldp; int out_nplanes;   // bf16 planes [npl][B*tq][ldp] (or null)
 };
 
+// Optional in-kernel timeline (tools/att_trace.py builds a separate library with -DFA_ATT_TRACE; the product build has none
+// of this): role 0 = TMA producer, 1 = MMA issuer, 2 = softmax warp 4 lane 0; (tag, clock64) pairs of one mid-grid CTA.
+#ifdef FA_ATT_TRACE
+__device__ long long g_att_trace[3][512];
+__device__ int g_att_cnt[3];
+#define TRACE_DECL() int tr_n = 0; const bool tr_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == gridDim.z / 2)
+#define TRACE(role, tag) do { if (tr_on && tr_n < 255) { g_att_trace[role][2 * tr_n] = (tag); g_att_trace[role][2 * tr_n + 1] = clock64(); ++tr_n; g_att_cnt[role] = tr_n; } } while (0)
+#else
+#define TRACE_DECL()
+#define TRACE(role, tag)
+#endif
+
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 softmax warps
 
-template <int NPL, int OPL>   // NPL: operand planes (1 | 2); OPL: context planes written (0 = fp32 context only)
+// NPL: operand planes (1 | 2); OPL: context planes written (0 = fp32 context only); CL: cluster size along the query-tile
+// axis (1 | 2 | 4) — the CL CTAs of a cluster work on different query tiles of the SAME (utterance, head) and share every
+// K / V chunk: each CTA fetches 1/CL of a chunk's 8 KB boxes and TMA-multicasts them into all CL shared memories.
+template <int NPL, int OPL, int CL>
 __global__ void __launch_bounds__(384, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const AttTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  constexpr uint32_t Q_BYTES = NPL * 2 * AT_Q_KBLK;
-  constexpr uint32_t K_BYTES = NPL * 2 * AT_K_KBLK;
-  constexpr uint32_t V_BYTES = NPL * AT_V_TILE;
-  constexpr uint32_t P_BYTES = NPL * AT_P_TILE;
+  constexpr uint32_t BOX = 8192;                          // every K / V box: 64 rows x 128 B
+  constexpr uint32_t Q_BYTES = NPL * 2 * AT_Q_KBLK;       // staging only: Q is moved to TMEM once
+  constexpr uint32_t SLOT_BYTES = NPL * 2 * BOX;          // one K chunk (NPL planes x 2 d-blocks) or one V chunk (NPL x 2 row halves)
+  constexpr int NSLOT = 5, NS = 3;                        // ring slots; S/P stages in TMEM
   constexpr int NT = NPL == 1 ? 1 : 3;
+  constexpr uint16_t MC_ALL = (uint16_t)((1u << CL) - 1u);
+  // TMEM columns: Q planes [0, NPL*64) | S/P stage st at 128 + 64*st (3 stages) | O at 320 .. 448
+  constexpr uint32_t TM_Q = 0, TM_S = 128, TM_O = 320;
   // align to 1024 B WITHOUT leaving the shared address space (a uintptr_t round trip makes every access a generic LD/ST)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* sQ = smem;
-  // K and V chunks share ONE 3-slot ring, filled in exactly the order the MMA warp consumes them
+  unsigned char* sQ = smem;                               // Q staging, later the epilogue's transpose buffer
+  // K and V chunks share ONE ring, filled in exactly the order the MMA warp consumes them
   //   pass A: Khi(0) .. Khi(nc-1)          pass B: K(0), K(1), V(0), K(2), V(1), ..., K(nc-1), V(nc-2), V(nc-1)
-  // (a K chunk is dead once its score MMAs retire, its V twin only at P.V time, and S(t+1) is issued before P.V(t)), which
-  // frees 32 KB against separate 2+2 rings — spent on double buffering P, so softmax(t+1) writes its probabilities while
-  // P.V(t) is still running instead of waiting for it (v2 was bound by that hand-off: tensor pipe 34 %).
-  constexpr uint32_t SLOT_BYTES = K_BYTES > V_BYTES ? K_BYTES : V_BYTES;
   unsigned char* sRing = sQ + Q_BYTES;
-  unsigned char* sP = sRing + 3 * SLOT_BYTES;        // [2][P_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
-  uint64_t* q_full = bars;            // [1]
-  uint64_t* r_full = bars + 1;        // [3]
-  uint64_t* r_empty = bars + 4;       // [3]
-  uint64_t* s_full = bars + 7;        // [2]
-  uint64_t* s_empty = bars + 9;       // [2]
-  uint64_t* p_full = bars + 11;       // [2]
-  uint64_t* p_empty = bars + 13;      // [2]
-  uint64_t* o_full = bars + 15;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  float* s_red = reinterpret_cast<float*>(bars + 17);   // [2][128] row max / row sum exchange between column halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + NSLOT * SLOT_BYTES);
+  uint64_t* q_full = bars;            // [1]  TMA -> softmax warps
+  uint64_t* q_ready = bars + 1;       // [1]  Q planes are in TMEM (8 arrivals)
+  uint64_t* r_full = bars + 2;        // [NSLOT]
+  uint64_t* r_empty = bars + 7;       // [NSLOT] CL arrivals: every CTA of the cluster has consumed its copy
+  uint64_t* s_full = bars + 12;       // [NS] score tile complete
+  uint64_t* sa_free = bars + 15;      // [NS] pass A: 8 softmax warps have read the tile
+  uint64_t* sb_free = bars + 18;      // [NS] pass B: the P.V that read the in-place probabilities has retired
+  uint64_t* p_full = bars + 21;       // [NS] probabilities written in place (8 arrivals)
+  uint64_t* o_full = bars + 24;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  float* s_red = reinterpret_cast<float*>(bars + 26);   // [2][128] row max / row sum exchange between column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   const int klen = min(p.key_lens[b], p.tk);
-  const int nc = (klen + AT_BKEY - 1) / AT_BKEY;     // key chunks with at least one valid key
+  const int nc = (klen + AT_BKEY - 1) / AT_BKEY;     // key chunks with at least one valid key (same for the whole cluster)
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 3; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8);
-      mbar_init(&p_full[s], 8); mbar_init(&p_empty[s], 1);
-    }
-    mbar_init(o_full, 1);
+    mbar_init(q_full, 1); mbar_init(q_ready, 8); mbar_init(o_full, 1);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], CL); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&sa_free[s], 8); mbar_init(&sb_free[s], 1); mbar_init(&p_full[s], 8); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                    // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t tmem_o = tmem_base + TM_O;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && nc > 0) {
+    if (nc > 0 && elect_one_sync()) {
       mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
       for (int pl = 0; pl < NPL; ++pl)
@@ -105,107 +117,150 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           tma_load_2d(sQ + (pl * 2 + kb) * AT_Q_KBLK, &map_q, q_full, h * AT_D + kb * 64,
                       (int)(pl * p.q_plane_rows + (int64_t)b * p.tq + q0));
       uint32_t n = 0;                                       // ring sequence number
-      auto load_k = [&](int j, int npl_load) {
-        const uint32_t slot = n % 3u;
-        mbar_wait(&r_empty[slot], ((n / 3u) & 1u) ^ 1u);
-        mbar_expect_tx(&r_full[slot], (uint32_t)npl_load * 2u * AT_K_KBLK);
+      TRACE_DECL();
+      TRACE(0, 0);
+      // one chunk = nb boxes of 8 KB; box bi is fetched by CTA (bi % CL) and multicast to the whole cluster
+      auto load_chunk = [&](bool is_v, int idx, int nb) {
+        const uint32_t slot = n % NSLOT;
+        mbar_wait(&r_empty[slot], ((n / NSLOT) & 1u) ^ 1u);
+        TRACE(0, 100 + (int)n);
+        mbar_expect_tx(&r_full[slot], (uint32_t)nb * BOX);
         unsigned char* dst = sRing + slot * SLOT_BYTES;
-        for (int pl = 0; pl < npl_load; ++pl)
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
-            tma_load_2d(dst + (pl * 2 + kb) * AT_K_KBLK, &map_k, &r_full[slot], h * AT_D + kb * 64,
-                        (int)(pl * p.k_plane_rows + (int64_t)b * p.tk + j * AT_BKEY));
+        for (int bi = 0; bi < nb; ++bi) {
+          if (CL > 1 && (uint32_t)(bi % CL) != crank) continue;
+          const int pl = bi >> 1, sub = bi & 1;
+          int c0, c1;
+          const CUtensorMap* mp;
+          if (is_v) { mp = &map_v; c0 = idx * AT_BKEY; c1 = (int)(pl * p.v_plane_rows + ((int64_t)b * p.heads + h) * AT_D + sub * 64); }
+          else { mp = &map_k; c0 = h * AT_D + sub * 64; c1 = (int)(pl * p.k_plane_rows + (int64_t)b * p.tk + idx * AT_BKEY); }
+          if (CL > 1) tma_load_2d_mc(dst + bi * BOX, mp, &r_full[slot], c0, c1, MC_ALL);
+          else tma_load_2d(dst + bi * BOX, mp, &r_full[slot], c0, c1);
+        }
         ++n;
       };
-      auto load_v = [&](int t) {
-        const uint32_t slot = n % 3u;
-        mbar_wait(&r_empty[slot], ((n / 3u) & 1u) ^ 1u);
-        mbar_expect_tx(&r_full[slot], V_BYTES);
-        unsigned char* dst = sRing + slot * SLOT_BYTES;
-#pragma unroll
-        for (int pl = 0; pl < NPL; ++pl)
-          tma_load_2d(dst + pl * AT_V_TILE, &map_v, &r_full[slot], t * AT_BKEY,
-                      (int)(pl * p.v_plane_rows + ((int64_t)b * p.heads + h) * AT_D));
-        ++n;
-      };
-      for (int i = 0; i < nc; ++i) load_k(i, 1);            // pass A: hi plane only
-      load_k(0, NPL);
+      for (int i = 0; i < nc; ++i) load_chunk(false, i, 2);            // pass A: hi plane only
+      load_chunk(false, 0, NPL * 2);
       for (int t = 0; t < nc; ++t) {
-        if (t + 1 < nc) load_k(t + 1, NPL);
-        load_v(t);
+        if (t + 1 < nc) load_chunk(false, t + 1, NPL * 2);
+        load_chunk(true, t, NPL * 2);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && nc > 0) {
+    if (nc > 0 && elect_one_sync()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(AT_BQ, AT_BKEY);
       constexpr uint32_t idesc_o = make_idesc_bf16(AT_BQ, AT_D);
       const int ta[3] = {0, 0, 1}, tb[3] = {0, 1, 0};
-      const uint32_t q_addr = smem_u32(sQ), p_addr0 = smem_u32(sP), ring_addr = smem_u32(sRing);
-      mbar_wait(q_full, 0);
+      const uint32_t ring_addr = smem_u32(sRing);
+      TRACE_DECL();
+      TRACE(1, 0);
+      mbar_wait(q_ready, 0);
       tc_fence_after();
-      uint32_t n = 0, sj = 0;                               // ring sequence number, score-tile job number
-      auto issue_qk = [&](int nterm) {
-        const uint32_t slot = n % 3u, st = sj & 1u;
-        mbar_wait(&r_full[slot], (n / 3u) & 1u);
-        mbar_wait(&s_empty[st], ((sj >> 1) & 1u) ^ 1u);
+      TRACE(1, 1);
+      uint32_t n = 0;                                       // ring sequence number
+      auto release_slot = [&](uint32_t slot) {
+        if (CL > 1) umma_commit_mc(&r_empty[slot], MC_ALL); else umma_commit(&r_empty[slot]);
+      };
+      // score tile of job j (pass A: j < nc, one term; pass B: j = nc + t, all terms) into stage j % NS
+      auto issue_qk = [&](int j) {
+        const uint32_t slot = n % NSLOT, st = (uint32_t)j % NS;
+        const int nterm = j < nc ? 1 : NT;
+        mbar_wait(&r_full[slot], (n / NSLOT) & 1u);
+        TRACE(1, 1000 + j);
+        const int jp = j - NS;                              // previous user of this stage
+        if (jp >= nc) mbar_wait(&sb_free[st], (uint32_t)((jp - nc) / NS) & 1u);        // its P.V has retired
+        else if (jp >= 0) mbar_wait(&sa_free[st], (uint32_t)(jp / NS) & 1u);           // pass A tile has been read
         tc_fence_after();
+        TRACE(1, 2000 + j);
         const uint32_t k_addr = ring_addr + slot * SLOT_BYTES;
-        const uint32_t d_s = tmem_base + st * AT_BKEY;
+        const uint32_t d_s = tmem_base + TM_S + st * AT_BKEY;
         for (int term = 0; term < nterm; ++term) {
 #pragma unroll
           for (int k = 0; k < AT_D / 16; ++k) {
-            const uint64_t da = make_sw128_desc(q_addr + (ta[term] * 2 + (k >> 2)) * AT_Q_KBLK) + 2 * (k & 3);
-            const uint64_t db = make_sw128_desc(k_addr + (tb[term] * 2 + (k >> 2)) * AT_K_KBLK) + 2 * (k & 3);
-            umma_bf16(d_s, da, db, idesc_s, (term | k) != 0 ? 1u : 0u);
+            const uint32_t a_t = tmem_base + TM_Q + ta[term] * 64 + k * 8;
+            const uint64_t db = make_sw128_desc(k_addr + (tb[term] * 2 + (k >> 2)) * BOX) + 2 * (k & 3);
+            umma_bf16_ts(d_s, a_t, db, idesc_s, (term | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&s_full[st]);
-        umma_commit(&r_empty[slot]);                        // K chunk is dead once its score MMAs retire
-        ++n; ++sj;
-      };
-      auto issue_pv = [&](int t) {
-        const uint32_t slot = n % 3u, pb = (uint32_t)t & 1u;
-        mbar_wait(&p_full[pb], ((uint32_t)t >> 1) & 1u);
-        mbar_wait(&r_full[slot], (n / 3u) & 1u);
-        tc_fence_after();
-        const uint32_t v_addr = ring_addr + slot * SLOT_BYTES, p_addr = p_addr0 + pb * P_BYTES;
-        for (int term = 0; term < NT; ++term) {
-          const uint64_t da = make_sw128_desc(p_addr + ta[term] * AT_P_TILE);
-          const uint64_t db = make_sw128_desc(v_addr + tb[term] * AT_V_TILE);
-#pragma unroll
-          for (int k = 0; k < AT_BKEY / 16; ++k) umma_bf16(tmem_o, da + 2 * k, db + 2 * k, idesc_o, (t | term | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&r_empty[slot]);
-        umma_commit(&p_empty[pb]);
+        release_slot(slot);                                 // K chunk is dead once its score MMAs retire
         ++n;
       };
-      for (int i = 0; i < nc; ++i) issue_qk(1);
-      issue_qk(NT);
+      auto issue_pv = [&](int t) {
+        const uint32_t slot = n % NSLOT, st = (uint32_t)(nc + t) % NS;
+        mbar_wait(&p_full[st], (uint32_t)(t / NS) & 1u);
+        TRACE(1, 3000 + t);
+        mbar_wait(&r_full[slot], (n / NSLOT) & 1u);
+        tc_fence_after();
+        TRACE(1, 4000 + t);
+        const uint32_t v_addr = ring_addr + slot * SLOT_BYTES;
+        const uint32_t p_t = tmem_base + TM_S + st * AT_BKEY;
+        for (int term = 0; term < NT; ++term) {
+          const uint64_t db = make_sw128_desc(v_addr + tb[term] * 2 * BOX);
+#pragma unroll
+          for (int k = 0; k < AT_BKEY / 16; ++k) {
+            // keys 16k..16k+15 of plane ta: half (k>>1) of the stage, 8 columns per step, lo plane 16 columns after hi
+            const uint32_t a_t = p_t + (k >> 1) * 32 + ta[term] * 16 + (k & 1) * 8;
+            umma_bf16_ts(tmem_o, a_t, db + 2 * k, idesc_o, (t | term | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&sb_free[st]);
+        release_slot(slot);
+        ++n;
+      };
+      for (int i = 0; i < nc; ++i) issue_qk(i);
+      issue_qk(nc);
       for (int t = 0; t < nc; ++t) {
-        if (t + 1 < nc) issue_qk(NT);
+        if (t + 1 < nc) issue_qk(nc + t + 1);
         issue_pv(t);
       }
       umma_commit(o_full);
+      TRACE(1, 9);
     }
   } else if (warp >= 4) {
     // ===================== softmax + epilogue: two threads per query row =====================
     const int qw = warp & 3;                   // TMEM lane quarter this warp may access
-    const int hf = (warp - 4) >> 2;            // column half of a 64-key chunk / of the 128 output dims
+    const int hf = (warp - 4) >> 2;            // column half of a 64-key chunk / of the 128 head dims
     const int r = qw * 32 + lane;              // row in tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(qw * 32) << 16;
     float m = -INFINITY, l = 0.f;
+#ifdef FA_ATT_TRACE
+    int tr_n = 0; const bool tr_on = (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == gridDim.z / 2) && warp == 4 && lane == 0;
+#endif
+    TRACE(2, 0);
     if (nc > 0) {
+      // ---- Q planes: shared memory (TMA, SWIZZLE_128B) -> TMEM, this thread's row, head dims [64 hf, 64 hf + 64)
+      mbar_wait(q_full, 0);
+#pragma unroll
+      for (int pl = 0; pl < NPL; ++pl) {
+        const unsigned char* qrow = sQ + (pl * 2 + hf) * AT_Q_KBLK + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t w[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 x = *reinterpret_cast<const uint4*>(qrow + (((half * 4 + c) ^ (r & 7)) << 4));
+            w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
+          }
+          tmem_st_32x16(tmem_base + lane_addr + TM_Q + pl * 64 + hf * 32 + half * 16, w);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_ready);
+      TRACE(2, 1);
       // ---- pass A: approximate row max over this thread's 32 columns of every chunk
       for (int i = 0; i < nc; ++i) {
-        const int st = i & 1;
-        mbar_wait(&s_full[st], ((uint32_t)i >> 1) & 1);
+        const int st = i % NS;
+        mbar_wait(&s_full[st], (uint32_t)(i / NS) & 1u);
         tc_fence_after();
+        TRACE(2, 1000 + i);
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + hf * 32, v);
+        tmem_ld_32x32(tmem_base + lane_addr + TM_S + st * AT_BKEY + hf * 32, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[st]);           // values are in registers: release the score tile first
+        if (lane == 0) mbar_arrive(&sa_free[st]);           // values are in registers: release the score tile first
         const int kbase = i * AT_BKEY + hf * 32;
         if (kbase + 32 <= klen) {                       // whole half-chunk valid (warp-uniform): no per-element predicates
 #pragma unroll
@@ -218,42 +273,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       s_red[hf * 128 + r] = m;
       softmax_bar();
       m = fmaxf(m, s_red[(hf ^ 1) * 128 + r]);     // finite: key 0 is always valid when nc > 0
-      // ---- pass B: probabilities
+      // ---- pass B: probabilities, written back IN PLACE over this thread's 32 score columns as bf16 planes
+      //      (columns [32 hf, +16) = hi plane of keys 32 hf .. 32 hf + 31, the next 16 columns = lo plane): the A operand of P.V
       for (int t = 0; t < nc; ++t) {
-        const int i = nc + t, st = i & 1, pb = t & 1;
-        mbar_wait(&s_full[st], ((uint32_t)i >> 1) & 1);
+        const int j = nc + t, st = j % NS;
+        mbar_wait(&s_full[st], (uint32_t)(j / NS) & 1u);
         tc_fence_after();
-        float pr[32];
+        TRACE(2, 2000 + t);
+        const uint32_t my_cols = tmem_base + lane_addr + TM_S + st * AT_BKEY + hf * 32;
+        uint32_t hi[16], lo[16];
         {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + lane_addr + st * AT_BKEY + hf * 32, v);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[st]);
+          tmem_ld_32x32(my_cols, v);
           const int kbase = t * AT_BKEY + hf * 32;
-          if (kbase + 32 <= klen) {                     // fully valid half-chunk: straight-line exp / accumulate
+          const bool whole = kbase + 32 <= klen;          // warp-uniform
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) { const float pv = __expf(__uint_as_float(v[jj]) - m); pr[jj] = pv; l += pv; }
-          } else {
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-              const float pv = (kbase + jj < klen) ? __expf(__uint_as_float(v[jj]) - m) : 0.f;
-              pr[jj] = pv;
-              l += pv;
-            }
-          }
-        }
-        // P planes -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
-        uint32_t* prow = reinterpret_cast<uint32_t*>(sP + pb * P_BYTES + (size_t)r * 128);
-        mbar_wait(&p_empty[pb], (((uint32_t)t >> 1) & 1) ^ 1);
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < 16; ++e) {
+            float a = __expf(__uint_as_float(v[2 * e]) - m), bb = __expf(__uint_as_float(v[2 * e + 1]) - m);
+            if (!whole) { a = (kbase + 2 * e < klen) ? a : 0.f; bb = (kbase + 2 * e + 1 < klen) ? bb : 0.f; }
+            l += a + bb;
             // packed cvt.rn.bf16x2.f32 (ALU pipe) instead of two scalar F2F.BF16 (quarter-rate XU pipe, shared with EX2);
             // bf16 -> fp32 is a 16-bit shift
-            const float a = pr[cc * 8 + 2 * e], bb = pr[cc * 8 + 2 * e + 1];
             const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
             hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
             if (NPL > 1) {
@@ -261,13 +301,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
               lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
             }
           }
-          const int pc = ((hf * 4 + cc) ^ (r & 7)) * 4;
-          *reinterpret_cast<uint4*>(prow + pc) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (NPL > 1) *reinterpret_cast<uint4*>(prow + AT_P_TILE / 4 + pc) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        TRACE(2, 3000 + t);
+        tmem_st_32x16(my_cols, hi);
+        if (NPL > 1) tmem_st_32x16(my_cols + 16, lo);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[pb]);
+        if (lane == 0) mbar_arrive(&p_full[st]);
+        TRACE(2, 5000 + t);
       }
       softmax_bar();                   // everyone has read the exchanged maxima before the slots are reused
       s_red[hf * 128 + r] = l;
@@ -275,11 +317,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       l += s_red[(hf ^ 1) * 128 + r];
       mbar_wait(o_full, 0);
       tc_fence_after();
+      TRACE(2, 8);
     }
     // ---- epilogue: O / l for this warp's 32 rows x 64 head dims, staged through shared memory (the K/V ring is dead once
     //      o_full has fired) so that the context rows leave as coalesced 8-byte (bf16 planes) / 16-byte (fp32) stores
     const float inv = l > 0.f ? 1.0f / l : 0.f;
-    float* stage = reinterpret_cast<float*>(sRing) + (warp - 4) * (32 * 36);
+    float* stage = reinterpret_cast<float*>(sQ) + (warp - 4) * (32 * 36);
     const int64_t grow0 = (int64_t)b * p.tq + q0 + qw * 32;
 #pragma unroll 1
     for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
@@ -331,10 +374,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
       __syncwarp();
     }
+    TRACE(2, 9);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (CL > 1) cluster_sync_all();      // no CTA exits while a peer may still multicast into it or arrive on its barriers
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // V [B, tk, ldv] (head h at column h*128) -> Vt planes [npl][B*H*128][tkp] (keys contiguous), via a 64x64 smem transpose.
@@ -425,13 +470,41 @@ int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk
   return attention_tc_planes_launch(qp, kp, vt, key_lens, batch, heads, tq, tk, ctx, ldc, ctx_planes, ldp, out_nplanes, mode, st);
 }
 
+template <int NPL, int OPL, int CL>
+static int launch_att_c(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttTcParams& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NPL * (2 * AT_Q_KBLK + 5 * 2 * 8192) + 1024 + 256 + 1024 + 256;
+  static bool done = false;
+  if (!done) {
+    FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<NPL, OPL, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
+  }
+  if (CL == 1) {
+    attention_tc_kernel<NPL, OPL, CL><<<grid, 384, smem, st>>>(mq, mk, mv, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(384, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FA_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_tc_kernel<NPL, OPL, CL>, mq, mk, mv, p));
+  }
+  return FA_OK;
+}
+
+// cluster size along the query-tile axis: the largest of {4, 2, 1} dividing the number of query tiles (FA_ATT_CLUSTER caps it)
+static int att_cluster_cap() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FA_ATT_CLUSTER"); v = e ? atoi(e) : 4; if (v != 1 && v != 2 && v != 4) v = 4; }
+  return v;
+}
+
 template <int NPL, int OPL>
 static int launch_att(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttTcParams& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NPL * (2 * AT_Q_KBLK + 3 * AT_V_TILE + 2 * AT_P_TILE) + 1024 + 256 + 1024;
-  static bool done = false;
-  if (!done) { FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<NPL, OPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
-  attention_tc_kernel<NPL, OPL><<<grid, 384, smem, st>>>(mq, mk, mv, p);
-  return FA_OK;
+  const int cap = att_cluster_cap();
+  if (cap >= 4 && grid.x % 4 == 0) return launch_att_c<NPL, OPL, 4>(grid, mq, mk, mv, p, st);
+  if (cap >= 2 && grid.x % 2 == 0) return launch_att_c<NPL, OPL, 2>(grid, mq, mk, mv, p, st);
+  return launch_att_c<NPL, OPL, 1>(grid, mq, mk, mv, p, st);
 }
 
 // Operand planes already in place (written by the producing GEMMs' epilogues, gemm_tc.cu AttnSinks):
@@ -448,7 +521,7 @@ int attention_tc_planes_launch(const __nv_bfloat16* qp, const __nv_bfloat16* kp,
   CUtensorMap mq_map, mk_map, mv_map;
   FA_RETURN_IF_ERR(make_bf16_map(&mq_map, qp, (uint64_t)mq * npl, (uint64_t)d, (uint64_t)d, AT_BQ));
   FA_RETURN_IF_ERR(make_bf16_map(&mk_map, kp, (uint64_t)mk * npl, (uint64_t)d, (uint64_t)d, AT_BKEY));
-  FA_RETURN_IF_ERR(make_bf16_map(&mv_map, vt, (uint64_t)mv * npl, (uint64_t)tk, (uint64_t)tkp, AT_D));
+  FA_RETURN_IF_ERR(make_bf16_map(&mv_map, vt, (uint64_t)mv * npl, (uint64_t)tk, (uint64_t)tkp, 64));   // 8 KB boxes: 64 d-rows x 64 keys
   AttTcParams p;
   p.tq = tq; p.tk = tk; p.heads = heads; p.batch = batch; p.key_lens = key_lens;
   p.q_plane_rows = mq; p.k_plane_rows = mk; p.v_plane_rows = mv;
@@ -470,6 +543,14 @@ int attention_tc_planes_launch(const __nv_bfloat16* qp, const __nv_bfloat16* kp,
 }
 
 }  // namespace fa
+
+#ifdef FA_ATT_TRACE
+extern "C" int fa_debug_att_trace(long long* host_out /* [3][512] */, int* counts /* [3] */) {
+  if (cudaMemcpyFromSymbol(host_out, fa::g_att_trace, sizeof(long long) * 3 * 512) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(counts, fa::g_att_cnt, sizeof(int) * 3) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 
 extern "C" size_t fa_attention_tc_workspace_bytes(int32_t batch, int32_t heads, int32_t tq, int32_t tk, int32_t gemm_mode) {
   return fa::attention_tc_scratch_bytes(batch, heads, tq, tk, gemm_mode);

@@ -347,7 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {          // single elected lane: no waterfall loops around the uniform-datapath TMA / MMA instructions
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
@@ -370,7 +370,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {          // single elected lane: no waterfall loops around the uniform-datapath TMA / MMA instructions
       constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -466,7 +466,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (elect_one_sync()) {          // single elected lane: no waterfall loops around the uniform-datapath TMA / MMA instructions
       int stage = 0; uint32_t phase = 0;
       for (int tile = pair; tile < n_tiles; tile += n_pairs) {
         const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
@@ -488,7 +488,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    if (leader && elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
