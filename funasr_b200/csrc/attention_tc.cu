@@ -291,7 +291,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           for (int e = 0; e < 16; ++e) {
             float a = __expf(__uint_as_float(v[2 * e]) - m), bb = __expf(__uint_as_float(v[2 * e + 1]) - m);
             if (!whole) { a = (kbase + 2 * e < klen) ? a : 0.f; bb = (kbase + 2 * e + 1 < klen) ? bb : 0.f; }
-            l += a + bb;
+            l += a;                                        // sequential order (matches the row-sum order of earlier builds)
+            l += bb;
             // packed cvt.rn.bf16x2.f32 (ALU pipe) instead of two scalar F2F.BF16 (quarter-rate XU pipe, shared with EX2);
             // bf16 -> fp32 is a 16-bit shift
             const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
@@ -492,10 +493,13 @@ static int launch_att_c(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk,
   return FA_OK;
 }
 
-// cluster size along the query-tile axis: the largest of {4, 2, 1} dividing the number of query tiles (FA_ATT_CLUSTER caps it)
+// cluster size along the query-tile axis: the largest of {4, 2, 1} that divides the number of query tiles and does not exceed
+// FA_ATT_CLUSTER.  Default 1: measured on B200 (B=64, H=4, T=500) the multicast variants are SLOWER (fa_attention_tc 207 us
+// at CL=1, 215 us at CL=2, 232 us at CL=4) — the kernel is not L2-bandwidth bound and clusters of 4 quantise badly on the
+// 18/20-SM GPCs; the path stays as an opt-in for shapes with many query tiles per (utterance, head).
 static int att_cluster_cap() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("FA_ATT_CLUSTER"); v = e ? atoi(e) : 4; if (v != 1 && v != 2 && v != 4) v = 4; }
+  if (v < 0) { const char* e = getenv("FA_ATT_CLUSTER"); v = e ? atoi(e) : 1; if (v != 1 && v != 2 && v != 4) v = 1; }
   return v;
 }
 

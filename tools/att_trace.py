@@ -39,6 +39,12 @@ for _ in range(3):
                              ws.data_ptr(), ws_bytes, st)
     assert rc == 0, rc
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    lib.fa_attention_tc(q.data_ptr(), D, k.data_ptr(), D, v.data_ptr(), D, lens.data_ptr(), B, H, T, T, ctx.data_ptr(), D, mode, ws.data_ptr(), ws_bytes, st)
+e1.record(); torch.cuda.synchronize()
+print(f"fa_attention_tc (split kernels + attention) avg {e0.elapsed_time(e1) / 20 * 1000:.1f} us per call")
 import numpy as np
 buf = np.zeros((3, 512), dtype=np.int64)
 cnt = np.zeros(3, dtype=np.int32)
