@@ -61,16 +61,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   constexpr uint32_t BOX = 8192;                          // every K / V box: 64 rows x 128 B
   constexpr uint32_t Q_BYTES = NPL * 2 * AT_Q_KBLK;       // staging only: Q is moved to TMEM once
   constexpr uint32_t SLOT_BYTES = NPL * 2 * BOX;          // one K chunk (NPL planes x 2 d-blocks) or one V chunk (NPL x 2 row halves)
-  constexpr int NSLOT = 5, NS = 3;                        // ring slots; S/P stages in TMEM
+  constexpr int NSLOT = 5, NS = 4;                        // ring slots; S/P stages in TMEM
   constexpr int NT = NPL == 1 ? 1 : 3;
   constexpr uint16_t MC_ALL = (uint16_t)((1u << CL) - 1u);
-  // TMEM columns: Q planes [0, NPL*64) | S/P stage st at 128 + 64*st (3 stages) | O at 320 .. 448
-  constexpr uint32_t TM_Q = 0, TM_S = 128, TM_O = 320;
+  // TMEM columns: Q planes [0, NPL*64) | S/P stage st at 128 + 64*st (4 stages) | O at 384 .. 512
+  constexpr uint32_t TM_Q = 0, TM_S = 128, TM_O = 384;
   // align to 1024 B WITHOUT leaving the shared address space (a uintptr_t round trip makes every access a generic LD/ST)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sQ = smem;                               // Q staging, later the epilogue's transpose buffer
   // K and V chunks share ONE ring, filled in exactly the order the MMA warp consumes them
-  //   pass A: Khi(0) .. Khi(nc-1)          pass B: K(0), K(1), V(0), K(2), V(1), ..., K(nc-1), V(nc-2), V(nc-1)
+  //   pass A: Khi(0) .. Khi(nc-1)          pass B: K(0), K(1), K(2), V(0), K(3), V(1), ..., K(nc-1), V(nc-3), V(nc-2), V(nc-1)
+  // (score tiles run TWO chunks ahead of P.V so the softmax of chunk t has two score-MMA durations to finish before the tensor
+  //  pipe needs its probabilities; with four S/P stages the stage S(t+2) overwrites was released by P.V(t-2) long before)
   unsigned char* sRing = sQ + Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + NSLOT * SLOT_BYTES);
   uint64_t* q_full = bars;            // [1]  TMA -> softmax warps
@@ -78,12 +80,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint64_t* r_full = bars + 2;        // [NSLOT]
   uint64_t* r_empty = bars + 7;       // [NSLOT] CL arrivals: every CTA of the cluster has consumed its copy
   uint64_t* s_full = bars + 12;       // [NS] score tile complete
-  uint64_t* sa_free = bars + 15;      // [NS] pass A: 8 softmax warps have read the tile
-  uint64_t* sb_free = bars + 18;      // [NS] pass B: the P.V that read the in-place probabilities has retired
-  uint64_t* p_full = bars + 21;       // [NS] probabilities written in place (8 arrivals)
-  uint64_t* o_full = bars + 24;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
-  float* s_red = reinterpret_cast<float*>(bars + 26);   // [2][128] row max / row sum exchange between column halves
+  uint64_t* sa_free = s_full + NS;    // [NS] pass A: 8 softmax warps have read the tile
+  uint64_t* sb_free = sa_free + NS;   // [NS] pass B: the P.V that read the in-place probabilities has retired
+  uint64_t* p_full = sb_free + NS;    // [NS] probabilities written in place (8 arrivals)
+  uint64_t* o_full = p_full + NS;     // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* s_red = reinterpret_cast<float*>(o_full + 2);   // [2][128] row max / row sum exchange between column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
@@ -140,8 +142,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       };
       for (int i = 0; i < nc; ++i) load_chunk(false, i, 2);            // pass A: hi plane only
       load_chunk(false, 0, NPL * 2);
+      if (nc > 1) load_chunk(false, 1, NPL * 2);
       for (int t = 0; t < nc; ++t) {
-        if (t + 1 < nc) load_chunk(false, t + 1, NPL * 2);
+        if (t + 2 < nc) load_chunk(false, t + 2, NPL * 2);
         load_chunk(true, t, NPL * 2);
       }
     }
@@ -210,8 +213,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       };
       for (int i = 0; i < nc; ++i) issue_qk(i);
       issue_qk(nc);
+      if (nc > 1) issue_qk(nc + 1);
       for (int t = 0; t < nc; ++t) {
-        if (t + 1 < nc) issue_qk(nc + t + 1);
+        if (t + 2 < nc) issue_qk(nc + t + 2);
         issue_pv(t);
       }
       umma_commit(o_full);

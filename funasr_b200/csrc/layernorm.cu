@@ -10,7 +10,7 @@
 
 namespace fa {
 
-template <int NV>  // float4 per lane (row length <= 128*NV)
+template <int NV, int NPL>  // NV: float4 per lane (row length <= 128*NV); NPL: bf16 planes written (0 = fp32 output only)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ g,
                  const float* __restrict__ bta, float eps, float* y,   // x may alias y (in-place)
@@ -73,21 +73,26 @@ layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ 
       o.z = (v[i].z - mean) * rstd * gg.z + bb.z;
       o.w = (v[i].w - mean) * rstd * gg.w + bb.w;
       if (yr) yr[c4] = o;
-      if (planes) {
+      if (NPL > 0) {
         float e0 = o.x, e1 = o.y, e2 = o.z, e3 = o.w;
         __nv_bfloat16* dst = planes + row * cols_pad + 4 * c4;
-        for (int pl = 0; pl < nplanes; ++pl) {       // packed cvt.rn.bf16x2 (ALU pipe), bf16 -> fp32 by shifts
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {           // packed cvt.rn.bf16x2 (ALU pipe), bf16 -> fp32 by shifts
           const __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1), p23 = __floats2bfloat162_rn(e2, e3);
           uint2 pk;
           pk.x = *reinterpret_cast<const uint32_t*>(&p01);
           pk.y = *reinterpret_cast<const uint32_t*>(&p23);
-          *reinterpret_cast<uint2*>(dst + pl * plane_elems) = pk;
-          e0 -= __uint_as_float(pk.x << 16); e1 -= __uint_as_float(pk.x & 0xFFFF0000u);
-          e2 -= __uint_as_float(pk.y << 16); e3 -= __uint_as_float(pk.y & 0xFFFF0000u);
+          *reinterpret_cast<uint2*>(dst) = pk;
+          if (pl + 1 < NPL) {
+            dst += plane_elems;
+            e0 -= __uint_as_float(pk.x << 16); e1 -= __uint_as_float(pk.x & 0xFFFF0000u);
+            e2 -= __uint_as_float(pk.y << 16); e3 -= __uint_as_float(pk.y & 0xFFFF0000u);
+          }
         }
       }
-    } else if (planes && 4 * c4 < cols_pad) {          // zero the K padding (e.g. 560 -> 576)
-      for (int pl = 0; pl < nplanes; ++pl) {
+    } else if (NPL > 0 && 4 * c4 < cols_pad) {         // zero the K padding (e.g. 560 -> 576)
+#pragma unroll
+      for (int pl = 0; pl < NPL; ++pl) {
         __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(planes + pl * plane_elems + row * cols_pad + 4 * c4);
         d2[0] = __halves2bfloat162(__float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f));
         d2[1] = d2[0];
@@ -105,14 +110,22 @@ int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, c
   if (planes && (cols_pad < n || (cols_pad & 3) || cols_pad > 2048)) return FA_ERR_UNSUPPORTED;
   const int need = ((planes ? cols_pad : n) / 4 + 31) / 32;
   const unsigned blocks = (unsigned)((rows + 7) / 8);
+  const int npl = planes ? nplanes : 0;
+  if (npl < 0 || npl > 3 || (planes && npl == 0)) return FA_ERR_ARG;
+#define FA_LN_LAUNCH(NV, NPL)                                                                                \
+  layernorm_kernel<NV, NPL><<<blocks, 256, 0, st>>>(x, rows, n, nm.g, nm.b, nm.eps, y, pe_inv, xscale,      \
+                                                    rows_per_batch > 0 ? rows_per_batch : 1, planes, nplanes, cols_pad)
 #define FA_LN_CASE(NV)                                                                                       \
-  layernorm_kernel<NV><<<blocks, 256, 0, st>>>(x, rows, n, nm.g, nm.b, nm.eps, y, pe_inv, xscale,           \
-                                               rows_per_batch > 0 ? rows_per_batch : 1, planes, nplanes, cols_pad)
+  do {                                                                                                       \
+    if (npl == 0) FA_LN_LAUNCH(NV, 0); else if (npl == 1) FA_LN_LAUNCH(NV, 1);                               \
+    else if (npl == 2) FA_LN_LAUNCH(NV, 2); else FA_LN_LAUNCH(NV, 3);                                        \
+  } while (0)
   if (need <= 4) FA_LN_CASE(4);
   else if (need <= 5) FA_LN_CASE(5);
   else if (need <= 8) FA_LN_CASE(8);
   else FA_LN_CASE(16);
 #undef FA_LN_CASE
+#undef FA_LN_LAUNCH
   FA_CHECK_LAUNCH();
   return FA_OK;
 }
