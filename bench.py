@@ -230,13 +230,14 @@ def main():
     sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.fa_launch_count()
+    r0 = getattr(eng, "replayed_launches", 0)       # kernels replayed from the decoder's CUDA graph are not seen by the C-side counter
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         out = step_device()
     e1.record()
     sync_all()
-    launches = int(lib.fa_launch_count() - l0)
+    launches = int(lib.fa_launch_count() - l0) + int(getattr(eng, "replayed_launches", 0) - r0)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -327,6 +327,7 @@ class ParaformerEngine(_EngineBase):
         ent["seen"] += 1
         if ent["graph"] is not None:
             ent["graph"].replay()
+            self.replayed_launches = getattr(self, "replayed_launches", 0) + ent["n_launch"]
         elif ent["seen"] < 2:
             run()                                                   # first sighting: plain launches (also the warm-up)
         else:
@@ -334,15 +335,17 @@ class ParaformerEngine(_EngineBase):
             side = self.__dict__.setdefault("_cap_stream", torch.cuda.Stream(device=self.device))
             side.wait_stream(cur)
             g = torch.cuda.CUDAGraph()
+            l0 = self.lib.fa_launch_count()
             with torch.cuda.graph(g, stream=side):
                 run()
+            ent["n_launch"] = int(self.lib.fa_launch_count() - l0)    # kernels recorded into the graph (counted once here)
             cur.wait_stream(side)
             if self._ws is not None and self._ws.data_ptr() != key[-1]:   # the workspace grew during capture: pointers are stale
                 run()
                 graphs.pop(key, None)
             else:
                 ent["graph"] = g
-                g.replay()
+                g.replay()                                          # the capture itself was counted by fa_launch_count
         return bufs[2], bufs[3]
 
 
