@@ -86,6 +86,15 @@ SIGNATURES = {
     "fa_paraformer_decoder_forward": (C.c_int, [C.POINTER(FaDecoder), _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
     "fa_greedy_filter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fa_split_bf16": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    # handle-style offline recogniser (funasrruntime.h:100-116 counterpart; offline.cu)
+    "fa_offline_init": (_vp, [C.c_char_p, _i32, _i32]),
+    "fa_offline_infer": (_vp, [_vp, C.POINTER(_vp), C.POINTER(_i64), _i32, _i32]),
+    "fa_offline_result_count": (_i32, [_vp]),
+    "fa_offline_result_ids": (C.POINTER(_i32), [_vp, _i32, C.POINTER(_i32)]),
+    "fa_offline_result_audio_seconds": (C.c_float, [_vp]),
+    "fa_offline_free_result": (None, [_vp]),
+    "fa_offline_uninit": (None, [_vp]),
+    "fa_offline_last_error": (C.c_char_p, []),
 }
 
 _lib = None

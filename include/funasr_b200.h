@@ -259,6 +259,28 @@ int fa_ctc_greedy_forward(const FaLinear* ctc_lo, const float* enc, const int32_
 int fa_split_bf16(const float* src, int64_t ld_src, int64_t rows, int32_t cols, int32_t cols_pad,
                   void* planes, fa_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Handle-style offline recogniser (no Python, no torch) — the counterpart of FunASR's C++ runtime surface
+ * runtime/onnxruntime/include/funasrruntime.h:100-116:
+ *   fa_offline_init          <-> FunOfflineInit(model_path, thread_num, use_gpu, batch_size)            :100
+ *   fa_offline_infer         <-> FunOfflineInferBuffer(handle, sz_buf, n_len, ...) ("pcm" = s16le)       :103-106
+ *   fa_offline_result_ids    <-> FunASRGetResult(result, n_index)   (token ids; the tokenizer stays with the caller) :69
+ *   fa_offline_result_audio_seconds <-> FunASRGetRetSnippetTime                                         :77
+ *   fa_offline_free_result / fa_offline_uninit <-> FunASRFreeResult :75 / FunOfflineUninit              :116
+ * model_file: flat tensor file written by funasr_b200/pack.py from a FunASR state_dict (same tensor names as model.pt) plus
+ * am.mvn and the kaldi mel/window tables.  pcm_format: 0 = float32 in [-1,1], 1 = int16 little endian (converted on the
+ * device, halves the H2D bytes).  bufs are HOST pointers, n_samples[i] >= 400.  Returns NULL on error
+ * (fa_offline_last_error() says why); there is no CPU fallback.
+ * ------------------------------------------------------------------------------------------- */
+void* fa_offline_init(const char* model_file, int32_t device, int32_t gemm_mode);
+void* fa_offline_infer(void* handle, const void* const* bufs, const int64_t* n_samples, int32_t batch, int32_t pcm_format);
+int32_t fa_offline_result_count(const void* result);
+const int32_t* fa_offline_result_ids(const void* result, int32_t index, int32_t* n_ids);
+float fa_offline_result_audio_seconds(const void* result);
+void fa_offline_free_result(void* result);
+void fa_offline_uninit(void* handle);
+const char* fa_offline_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

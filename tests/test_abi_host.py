@@ -193,3 +193,34 @@ def test_bucket_by_length_config3():
     fake = lambda batch: [[int(w.shape[-1]) % 97] for w in batch]
     wavs = [torch.zeros(k) for k in n[:50]]
     assert run_bucketed(wavs, fake, max_batch=8) == [[k % 97] for k in n[:50]]
+
+
+def test_model_file_roundtrip(tmp_path):
+    """pack.py writes exactly what csrc/offline.cu:load_file parses: FunASR state_dict names + derived tables."""
+    from funasr_b200 import pack, synth
+    cfg = synth.PARAFORMER_TINY
+    st = synth.make_state_dict(cfg, 3)
+    cmvn = synth.make_cmvn(cfg, 1)
+    path = str(tmp_path / "tiny.fab2")
+    n = pack.write_model_file(path, st, cfg, cmvn)
+    back = pack.read_model_file(path)
+    assert len(back) == n
+    assert back["__config__"].tolist()[:7] == [cfg.enc_layers, cfg.dec_layers, cfg.d_model, cfg.heads, cfg.kernel, cfg.vocab, cfg.feat_dim]
+    for k in ("encoder.encoders0.0.self_attn.linear_q_k_v.weight", "decoder.output_layer.weight", "predictor.cif_output.bias"):
+        assert np.array_equal(back[k], st[k].numpy())
+    cw = st["predictor.cif_conv1d.weight"]
+    assert np.array_equal(back["predictor.cif_conv1d.gemm_weight"][:, 512:1024], cw[:, :, 1].numpy())   # W[n, k*512+c] = w[n,c,k]
+    assert back["frontend.mel_banks"].shape == (80, 257) and back["frontend.cmvn"].shape == (2, 560)
+    with open(path, "rb") as f:
+        assert f.read(8) == b"FAB2MDL1"
+
+
+def test_offline_api_rejects_bad_arguments_without_a_gpu():
+    """The handle API fails loudly (NULL + message), never falls back: missing file / no CUDA device."""
+    from funasr_b200 import _abi
+    lib = _abi.load()
+    h = lib.fa_offline_init(b"/nonexistent/model.fab2", 0, 3)
+    assert not h
+    assert lib.fa_offline_last_error() != b""
+    assert not lib.fa_offline_init(None, 0, 3)
+    assert lib.fa_offline_result_count(None) == 0

@@ -488,3 +488,31 @@ def test_abi_error_codes():
     with pytest.raises(abi.FunasrB200Error):
         abi.check(-3, "demo")
     torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+def test_offline_handle_api_vs_reference_golden(tmp_path, mode):
+    """fa_offline_init / fa_offline_infer (the funasrruntime.h-style C handle API: no torch on the data path, weights from the
+    flat file written by pack.py) reproduces the unmodified reference's greedy ids on the ragged golden batch — float32 and
+    int16 PCM input."""
+    from funasr_b200 import pack
+    from funasr_b200.offline import OfflineRecognizer
+    cfg, wseed, wavs, cmvn, g = load_case("tiny_ragged3")
+    path = str(tmp_path / "m.fab2")
+    pack.write_model_file(path, state_dict_for(cfg, wseed), cfg, cmvn)
+    rec = OfflineRecognizer(path, 0, mode)
+    ids = rec.infer([w.numpy() for w in wavs])
+    assert [t for r in ids for t in r] == g["ids_flat"].tolist()
+    assert [len(r) for r in ids] == g["ids_len"].tolist()
+    assert abs(rec.last_audio_seconds - sum(w.numel() for w in wavs) / 16000.0) < 1e-3
+    # second call on the same handle (buffers are reused), different batch composition
+    ids2 = rec.infer([wavs[1].numpy()])
+    assert ids2[0] == ids[1]
+    # int16 PCM: identical to the float path on the dequantised waveform
+    pcm = [np.clip(np.round(w.numpy() * 32768.0), -32768, 32767).astype(np.int16) for w in wavs]
+    deq = [p.astype(np.float32) / 32768.0 for p in pcm]
+    assert rec.infer(pcm) == rec.infer(deq)
+    rec.close()
+    with pytest.raises(Exception):
+        OfflineRecognizer(str(tmp_path / "missing.fab2"), 0, mode)
