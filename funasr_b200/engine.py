@@ -283,7 +283,8 @@ class ParaformerEngine(_EngineBase):
         acoustic, tok, alphas, peaks = self.predict(enc, lens, persistent=fused)
         tok_host = tok.cpu()                       # D2H + sync: B int32
         n_max = int(tok_host.max()) if tok_host.numel() else 0
-        out = {"enc": enc, "alphas": alphas, "peaks": peaks, "token_num": tok_host, "acoustic": acoustic} if want_taps else {"token_num": tok_host}
+        out = {"enc": enc, "alphas": alphas, "peaks": peaks, "token_num": tok_host, "acoustic": acoustic} if want_taps else \
+            {"token_num": tok_host, "alphas": alphas, "peaks": peaks}      # CIF weights / fires stay on the device (timestamps read them)
         if n_max < 1:                              # paraformer/model.py:615-616
             out["ids"] = [[] for _ in range(feats.shape[0])]
             return out

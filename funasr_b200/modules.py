@@ -349,20 +349,37 @@ class ParaformerB200(nn.Module):
         if len(key) < b:
             key = key * b
         results = []
+        pred_timestamp = bool(kwargs.get("pred_timestamp", False))            # model.py:558
+        if pred_timestamp:
+            from .timestamps import paraformer_timestamps
+            alphas_h, peaks_h = out["alphas"].cpu().numpy(), out["peaks"].cpu().numpy()
         for i in range(b):
             token_int = ids[i]
             if tokenizer is not None:                         # CPU string work stays the reference's (model.py:668-687)
                 token = tokenizer.ids2tokens(token_int)
                 text = tokenizer.tokens2text(token)
+                stamp = None
+                if pred_timestamp:                            # model.py:673-680: CIF fires -> [start_ms, end_ms] per token
+                    _, stamp = paraformer_timestamps(peaks_h[i], alphas_h[i], list(token), kwargs.get("begin_time", 0))
                 if not hasattr(tokenizer, "bpemodel"):
                     try:
                         from funasr.utils import postprocess_utils
-                        text, _ = postprocess_utils.sentence_postprocess(token)
+                        if stamp is not None:
+                            text, stamp, _ = postprocess_utils.sentence_postprocess(token, stamp)
+                        else:
+                            text, _ = postprocess_utils.sentence_postprocess(token)
                     except ImportError:
                         pass
-                results.append({"key": key[i], "text": text})
+                res_i = {"key": key[i], "text": text}
+                if stamp is not None:
+                    res_i["timestamp"] = stamp
+                results.append(res_i)
             else:
-                results.append({"key": key[i], "token_int": token_int})
+                res_i = {"key": key[i], "token_int": token_int}
+                if pred_timestamp:                            # extension: the reference only time-stamps when it has a tokenizer
+                    res_i["timestamp"] = paraformer_timestamps(peaks_h[i], alphas_h[i], [str(t) for t in token_int],
+                                                               kwargs.get("begin_time", 0))[1]
+                results.append(res_i)
         return results, meta_data
 
 

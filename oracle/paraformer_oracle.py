@@ -314,7 +314,7 @@ def paraformer_forward(wavs: List[Tensor], p: Dict[str, Tensor], cmvn: Optional[
         enc, elens = encoder(feats, flens, p, enc_layers, heads, eps, taps)
         emb, token_num, alphas, peaks = predictor(enc, elens, p, tail_threshold)
         tok = token_num.round().long()
-        out = {"feats": feats, "feat_lens": flens, "enc": enc, "alphas": alphas, "token_num": tok.to(torch.int32),
+        out = {"feats": feats, "feat_lens": flens, "enc": enc, "alphas": alphas, "peaks": peaks, "token_num": tok.to(torch.int32),
                "acoustic": emb}
         if int(tok.max()) < 1:
             out.update(ids=[[] for _ in wavs], logp=None)

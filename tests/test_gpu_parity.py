@@ -317,6 +317,18 @@ def test_plugin_inference_contract():
     assert [r["key"] for r in res] == ["a", "b", "c"]
     assert [t for r in res for t in r["token_int"]] == g["ids_flat"].tolist()
     assert abs(meta["batch_data_time"] - float(g["batch_data_time"])) < 1e-6
+    # pred_timestamp (model.py:558,673-680): CIF fires -> [start_ms, end_ms] per token.  Expected values: the reference-pinned
+    # host routine (tests/test_timestamps.py) applied to the ORACLE's CIF weights / fires for the same batch.
+    from funasr_b200.timestamps import paraformer_timestamps
+    res_t, _ = m.inference([w.numpy() for w in wavs], key=["a", "b", "c"], tokenizer=None, frontend=fe, device=DEV, pred_timestamp=True)
+    ora = O.paraformer_forward(wavs, state_dict_for(cfg, wseed), cmvn, cfg.enc_layers, cfg.dec_layers)
+    for i, r in enumerate(res_t):
+        want = paraformer_timestamps(ora["peaks"][i].numpy(), ora["alphas"][i].numpy(), [str(t) for t in ora["ids"][i]])[1]
+        assert len(r["timestamp"]) == len(r["token_int"]) and len(want) == len(r["timestamp"])
+        assert all(a <= b for a, b in r["timestamp"])
+        # a CIF weight that differs in the last fp32 bits can move one fire by a frame: allow one 60 ms frame, require most exact
+        diffs = [max(abs(x[0] - y[0]), abs(x[1] - y[1])) for x, y in zip(r["timestamp"], want)]
+        assert max(diffs, default=0) <= 60 and sum(d == 0 for d in diffs) >= 0.9 * len(diffs)
 
 
 # ------------------------------------------------------------------------------------------------ SenseVoiceSmall

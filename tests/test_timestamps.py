@@ -1,0 +1,59 @@
+"""CIF timestamps (funasr_b200/timestamps.py) against golden vectors produced by the reference's own
+ts_prediction_lfr6_standard (oracle/make_timestamp_golden.py), and against the live reference when it is present."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+from funasr_b200 import timestamps as TS
+
+
+def _cases():
+    with open(os.path.join(GOLDEN, "timestamps.json")) as f:
+        return json.load(f)
+
+
+def test_timestamps_match_reference_golden():
+    cases = _cases()
+    assert len(cases) >= 100
+    n_nonempty = 0
+    for c in cases:
+        first, second = np.array(c["first"], np.float32), np.array(c["second"], np.float32)
+        txt, res = TS.ts_prediction_lfr6_standard(first, second, c["chars"], vad_offset=c["vad_offset"], upsample_rate=c["upsample_rate"])
+        assert res == c["res"]              # integer milliseconds: exact
+        assert txt == c["txt"]
+        n_nonempty += bool(res)
+    assert n_nonempty > len(cases) // 2
+
+
+def test_cif_wo_hidden_is_the_running_integral():
+    a = np.array([0.4, 0.7, 0.2, 0.9, 0.05], np.float32)
+    f = TS.cif_wo_hidden(a, 1.0)
+    assert np.allclose(f, [0.4, 1.1, 0.3, 1.2, 0.25], atol=1e-6)
+    assert TS.ts_prediction_lfr6_standard(a, a, []) == ("", [])
+
+
+def test_timestamps_against_live_reference_if_available():
+    try:
+        from oracle import ref_shim
+        ref_shim.import_reference()
+        import torch
+        from funasr.utils.timestamp_tools import ts_prediction_lfr6_standard as ref_fn
+    except Exception:
+        pytest.skip("reference not importable here (GPU box)")
+    rng = np.random.default_rng(7)
+    for trial in range(50):
+        T = int(rng.integers(6, 120))
+        a = (rng.random(T).astype(np.float32) ** 2 * 0.8).astype(np.float32)
+        peaks = TS.cif_wo_hidden(a, 1.0)
+        chars = ["c%d" % i for i in range(max(1, int((peaks >= 1 - 1e-4).sum()) - 1 + trial % 2))]
+        try:
+            want = ref_fn(torch.tensor(peaks.copy()), torch.tensor(a.copy()), copy.copy(chars), upsample_rate=1)
+        except IndexError:
+            want = ("", [])
+        got = TS.paraformer_timestamps(peaks, a, chars)
+        assert got[1] == want[1] and got[0] == want[0]
