@@ -90,8 +90,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-  const int klen = min(p.key_lens[b], p.tk);
-  const int nc = (klen + AT_BKEY - 1) / AT_BKEY;     // key chunks with at least one valid key (same for the whole cluster)
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
   if (warp == 1 && lane == 0) {
@@ -105,6 +103,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   __syncthreads();
   if (CL > 1) cluster_sync_all();                    // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
+  pdl_wait();                                        // everything above touched only shared / tensor memory
+  pdl_trigger();
+  const int klen = min(p.key_lens[b], p.tk);
+  const int nc = (klen + AT_BKEY - 1) / AT_BKEY;     // key chunks with at least one valid key (same for the whole cluster)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + TM_O;
 
@@ -483,17 +485,7 @@ static int launch_att_c(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk,
     FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<NPL, OPL, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done = true;
   }
-  if (CL == 1) {
-    attention_tc_kernel<NPL, OPL, CL><<<grid, 384, smem, st>>>(mq, mk, mv, p);
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(384, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    FA_CUDA_OK(cudaLaunchKernelEx(&cfg, attention_tc_kernel<NPL, OPL, CL>, mq, mk, mv, p));
-  }
+  FA_CUDA_OK(launch_pdl(attention_tc_kernel<NPL, OPL, CL>, grid, dim3(384), smem, st, CL, mq, mk, mv, p));
   return FA_OK;
 }
 

@@ -19,6 +19,8 @@ fsmn_kernel(const float* __restrict__ v, int64_t ldv, const int32_t* __restrict_
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int t0 = blockIdx.y * FSMN_TT;
   const int b = blockIdx.z;
+  pdl_wait();
+  pdl_trigger();
   if (c >= channels) return;
   constexpr int L = (K - 1) / 2;
   const int len = min(lens[b], t_max);
@@ -51,9 +53,9 @@ int fsmn_launch(const float* v, int64_t ldv, const int32_t* lens, int batch, int
   if (!v || !lens || !w || !out) return FA_ERR_ARG;
   dim3 grid((channels + 127) / 128, (t_max + FSMN_TT - 1) / FSMN_TT, batch);
   switch (ksize) {
-    case 11: fsmn_kernel<11><<<grid, 128, 0, st>>>(v, ldv, lens, t_max, channels, w, res, ldr, out, ldo); break;
-    case 21: fsmn_kernel<21><<<grid, 128, 0, st>>>(v, ldv, lens, t_max, channels, w, res, ldr, out, ldo); break;
-    case 31: fsmn_kernel<31><<<grid, 128, 0, st>>>(v, ldv, lens, t_max, channels, w, res, ldr, out, ldo); break;
+    case 11: FA_CUDA_OK(launch_pdl(fsmn_kernel<11>, grid, dim3(128), 0, st, 1, v, ldv, lens, t_max, channels, w, res, ldr, out, ldo)); break;
+    case 21: FA_CUDA_OK(launch_pdl(fsmn_kernel<21>, grid, dim3(128), 0, st, 1, v, ldv, lens, t_max, channels, w, res, ldr, out, ldo)); break;
+    case 31: FA_CUDA_OK(launch_pdl(fsmn_kernel<31>, grid, dim3(128), 0, st, 1, v, ldv, lens, t_max, channels, w, res, ldr, out, ldo)); break;
     default: return FA_ERR_UNSUPPORTED;
   }
   FA_CHECK_LAUNCH();

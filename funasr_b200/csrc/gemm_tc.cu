@@ -409,6 +409,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();                                          // prologue above is global-memory free; operands are read below
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -527,6 +529,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   cluster_sync_all();                                  // barriers of both CTAs are initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();                                          // prologue above is global-memory free; operands are read below
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -683,7 +687,7 @@ static int launch_cfg_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcPa
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < n_sm ? tiles : n_sm;
-  gemm_tc_kernel<BN, STAGES, APL, WPL, EPI><<<grid, 384, smem, st>>>(ma, mw, p);
+  FA_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, STAGES, APL, WPL, EPI>, dim3(grid), dim3(384), smem, st, 1, ma, mw, p));
   FA_CHECK_LAUNCH();
   return FA_OK;
 }
@@ -715,7 +719,7 @@ static int launch_cfg2_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcP
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int pairs = tiles < n_sm / 2 ? tiles : n_sm / 2;
-  gemm_tc2_kernel<STAGES, PL, EPI><<<2 * pairs, 384, smem, st>>>(ma, mw, p);
+  FA_CUDA_OK(launch_pdl(gemm_tc2_kernel<STAGES, PL, EPI>, dim3(2 * pairs), dim3(384), smem, st, 1, ma, mw, p));   // cluster dims are compile-time (__cluster_dims__)
   FA_CHECK_LAUNCH();
   return FA_OK;
 }

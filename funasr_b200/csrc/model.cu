@@ -1,6 +1,7 @@
 // Model-level C-ABI entry points: the kernel sequences of SANMEncoder.forward, CifPredictorV2.forward and
 // ParaformerSANMDecoder.forward (+ greedy arg-max), stream-ordered over a caller-provided workspace.
 #include "common.cuh"
+#include <stdlib.h>
 #include "kernels.h"
 #include <string.h>
 #include <math.h>
@@ -8,6 +9,12 @@
 namespace fa {
 
 std::atomic<unsigned long long> g_launch_count{0};
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FA_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 
 static int linear(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
                   const float* r2, int64_t ld2, float* y, int64_t ldy, int mode, Arena* scratch, cudaStream_t st) {
