@@ -40,7 +40,8 @@ class FaEncoder(C.Structure):
 
 class FaPredictor(C.Structure):
     _fields_ = [("conv", FaLinear), ("out_w", C.c_void_p), ("out_b", C.c_void_p), ("threshold", C.c_float),
-                ("tail_threshold", C.c_float), ("smooth_factor", C.c_float), ("noise_threshold", C.c_float)]
+                ("tail_threshold", C.c_float), ("smooth_factor", C.c_float), ("noise_threshold", C.c_float),
+                ("cif_variant", C.c_int32), ("_pad", C.c_int32)]
 
 
 class FaDecLayer(C.Structure):
@@ -84,6 +85,7 @@ SIGNATURES = {
     "fa_cif_predictor_forward": (C.c_int, [C.POINTER(FaPredictor), _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
     "fa_paraformer_decoder_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "fa_paraformer_decoder_forward": (C.c_int, [C.POINTER(FaDecoder), _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
+    "fa_cif_upsample_alphas": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _f, _vp, _vp, _vp]),
     "fa_greedy_filter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fa_split_bf16": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     # handle-style offline recogniser (funasrruntime.h:100-116 counterpart; offline.cu)

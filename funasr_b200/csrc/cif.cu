@@ -113,6 +113,98 @@ cif_fire_kernel(const float* __restrict__ enc, const float* __restrict__ alpha_r
   }
 }
 
+
+// BiCif flavour (CifPredictorV3.forward -> `cif`, funasr/models/bicif_paraformer/cif_predictor.py:37-84): the integrate-and-fire
+// recurrence runs sequentially in fp32 (no fp64 prefix sums), a fire subtracts exactly 1.0, and a frame is the running
+// fp32 sum  frame += cur * h  (multiply, then add) that restarts at  remainds * h  after every fire.  Same launch geometry
+// as cif_fire_kernel: thread 0 resolves the scalar recurrence into shared memory, then one thread per channel.
+__global__ void __launch_bounds__(512)
+cif_fire_loop_kernel(const float* __restrict__ enc, const float* __restrict__ alpha_rows, const int32_t* __restrict__ lens,
+                     int t_max, int d, float tail, float threshold, float* __restrict__ acoustic, int n_cap,
+                     int32_t* __restrict__ token_num, float* __restrict__ alphas_out, float* __restrict__ peaks_out) {
+  extern __shared__ float sm[];
+  float* s_cur = sm;                      // [T+1] weight of frame t inside the token being integrated
+  float* s_rem = sm + (t_max + 1);        // [T+1] weight carried into the next token when t fires
+  int* s_ord = reinterpret_cast<int*>(sm + 2 * (t_max + 1));  // [T+1] fire ordinal or -1
+  const int b = blockIdx.x;
+  const int T1 = t_max + 1;
+  const int len = min(lens[b], t_max);
+  for (int t = threadIdx.x; t < T1; t += blockDim.x) {
+    float a = t < t_max ? alpha_rows[(int64_t)b * t_max + t] : 0.f;
+    if (t == len) a = __fadd_rn(a, tail);           // tail_process_fn (:352-377): mask_2 - mask_1 is 1 exactly at index len
+    s_cur[t] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float integrate = 0.f;
+    double total = 0.0;
+    int ord = 0;
+    for (int t = 0; t < T1; ++t) {
+      const float alpha = s_cur[t];
+      total += (double)alpha;
+      const float completion = __fsub_rn(1.0f, integrate);      // :54
+      integrate = __fadd_rn(integrate, alpha);                   // :56
+      peaks_out[(int64_t)b * T1 + t] = integrate;                // list_fires (:57)
+      alphas_out[(int64_t)b * T1 + t] = alpha;
+      const bool fire = integrate >= threshold;                  // :59
+      if (fire) integrate = __fsub_rn(integrate, 1.0f);          // :60-62 (minus ones, not minus threshold)
+      const float cur = fire ? completion : alpha;               // :63
+      s_cur[t] = cur;
+      s_rem[t] = __fsub_rn(alpha, cur);                          // :64
+      s_ord[t] = fire ? ord++ : -1;
+    }
+    token_num[b] = (int32_t)floorf((float)total);                // tail_process_fn: floor(alphas.sum(-1)) (:374-375)
+  }
+  __syncthreads();
+  const float* hb = enc + (int64_t)b * t_max * d;
+  float* ob = acoustic + (int64_t)b * n_cap * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float frame = 0.f;
+    for (int t = 0; t < T1; ++t) {
+      const float h = t < t_max ? __ldg(hb + (int64_t)t * d + c) : 0.f;   // hidden gets one zero frame appended (:371-372)
+      frame = __fadd_rn(frame, __fmul_rn(s_cur[t], h));                   // :66
+      const int k = s_ord[t];
+      if (k >= 0) {
+        if (k < n_cap) ob[(int64_t)k * d + c] = frame;                    // :67, :78
+        frame = __fmul_rn(s_rem[t], h);                                   // :68-70
+      }
+    }
+  }
+}
+
+// Upsampled timestamp head of CifPredictorV3.get_upsample_timestamp (:300-352), after the BLSTM: per utterance
+//   alphas2 *= token_num / sum(alphas2);  us_peaks = cif_wo_hidden(alphas2, threshold - 1e-4)  (fp32, sequential).
+__global__ void cif_upsample_scan_kernel(float* __restrict__ alphas2, const int32_t* __restrict__ token_num, int t3, float thr,
+                                         float* __restrict__ us_peaks) {
+  const int b = blockIdx.x;
+  float* a = alphas2 + (int64_t)b * t3;
+  __shared__ double s_part[32];
+  double part = 0.0;
+  for (int t = threadIdx.x; t < t3; t += blockDim.x) part += (double)a[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  __shared__ float s_scale;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
+    s_scale = __fdiv_rn((float)token_num[b], (float)tot);       // (token_num / _token_num): fp32 division of the fp32 sum
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  for (int t = threadIdx.x; t < t3; t += blockDim.x) a[t] = __fmul_rn(a[t], scale);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float integrate = 0.f;
+    for (int t = 0; t < t3; ++t) {
+      integrate = __fadd_rn(integrate, a[t]);
+      us_peaks[(int64_t)b * t3 + t] = integrate;
+      if (integrate >= thr) integrate = __fsub_rn(integrate, thr);
+    }
+  }
+}
+
 int cif_im2col_launch(const float* enc, int64_t rows, int t_max, int d, float* xc, cudaStream_t st) {
   const int64_t total4 = rows * 3 * (d / 4);
   if (total4 <= 0) return FA_OK;
@@ -136,6 +228,24 @@ int cif_fire_launch(const float* enc, const float* alpha_rows, const int32_t* le
   if (smem > 200 * 1024) return FA_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) FA_CUDA_OK(cudaFuncSetAttribute(cif_fire_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cif_fire_kernel<<<batch, 512, smem, st>>>(enc, alpha_rows, lens, t_max, d, tail, acoustic, n_cap, token_num, alphas, peaks);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+int cif_fire_loop_launch(const float* enc, const float* alpha_rows, const int32_t* lens, int batch, int t_max, int d,
+                         float tail, float threshold, float* acoustic, int n_cap, int32_t* token_num, float* alphas, float* peaks,
+                         cudaStream_t st) {
+  const size_t smem = (size_t)3 * (t_max + 1) * sizeof(float);
+  if (smem > 200 * 1024) return FA_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) FA_CUDA_OK(cudaFuncSetAttribute(cif_fire_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cif_fire_loop_kernel<<<batch, 512, smem, st>>>(enc, alpha_rows, lens, t_max, d, tail, threshold, acoustic, n_cap, token_num, alphas,
+                                                 peaks);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+int cif_upsample_scan_launch(float* alphas2, const int32_t* token_num, int batch, int t3, float thr, float* us_peaks, cudaStream_t st) {
+  cif_upsample_scan_kernel<<<batch, 256, 0, st>>>(alphas2, token_num, t3, thr, us_peaks);
   FA_CHECK_LAUNCH();
   return FA_OK;
 }

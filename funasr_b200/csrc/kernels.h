@@ -49,6 +49,10 @@ int attention_f32_launch(const float* q, int64_t ldq, const float* k, int64_t ld
 int fsmn_launch(const float* v, int64_t ldv, const int32_t* lens, int batch, int t_max, int channels, const float* w,
                 int ksize, const float* res, int64_t ldr, float* out, int64_t ldo, cudaStream_t st);
 int cif_im2col_launch(const float* enc, int64_t rows, int t_max, int d, float* xc, cudaStream_t st);
+int cif_fire_loop_launch(const float* enc, const float* alpha_rows, const int32_t* lens, int batch, int t_max, int d,
+                         float tail, float threshold, float* acoustic, int n_cap, int32_t* token_num, float* alphas, float* peaks,
+                         cudaStream_t st);
+int cif_upsample_scan_launch(float* alphas2, const int32_t* token_num, int batch, int t3, float thr, float* us_peaks, cudaStream_t st);
 int cif_alpha_launch(const float* c, int d, const float* w, const float* b0, const int32_t* lens, int t_max,
                      int64_t rows, float smooth, float noise, float* alpha_rows, cudaStream_t st);
 int cif_fire_launch(const float* enc, const float* alpha_rows, const int32_t* lens, int batch, int t_max, int d,

@@ -208,8 +208,23 @@ extern "C" int fa_cif_predictor_forward(const FaPredictor* pred, const float* en
   FA_RETURN_IF_ERR(cif_alpha_launch(c, D, pred->out_w, pred->out_b, lens, t_max, M, pred->smooth_factor,
                                     pred->noise_threshold, alpha_rows, st));
   FA_CUDA_OK(cudaMemsetAsync(acoustic, 0, (size_t)batch * n_cap * D * sizeof(float), st));
+  if (pred->cif_variant == 1)     // CifPredictorV3 (BiCifParaformer): sequential fp32 `cif`
+    return cif_fire_loop_launch(enc, alpha_rows, lens, batch, t_max, D, pred->tail_threshold, pred->threshold, acoustic, n_cap,
+                                token_num, alphas, peaks, st);
+  if (pred->cif_variant != 0) return FA_ERR_ARG;
   return cif_fire_launch(enc, alpha_rows, lens, batch, t_max, D, pred->tail_threshold, acoustic, n_cap, token_num, alphas,
                          peaks, st);
+}
+
+// CifPredictorV3.get_upsample_timestamp after the BLSTM (bicif_paraformer/cif_predictor.py:331-352)
+extern "C" int fa_cif_upsample_alphas(const float* feat, int32_t dz, const float* w, const float* b, const int32_t* lens_up,
+                                      const int32_t* token_num, int32_t batch, int32_t t_up, float smooth2, float noise2,
+                                      float threshold, float* us_alphas, float* us_peaks, fa_stream_t stream) {
+  if (!feat || !w || !b || !lens_up || !token_num || !us_alphas || !us_peaks || batch <= 0 || t_up <= 0 || dz <= 0 || (dz & 3))
+    return FA_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  FA_RETURN_IF_ERR(cif_alpha_launch(feat, dz, w, b, lens_up, t_up, (int64_t)batch * t_up, smooth2, noise2, us_alphas, st));
+  return cif_upsample_scan_launch(us_alphas, token_num, batch, t_up, (float)((double)threshold - 1e-4), us_peaks, st);
 }
 
 // ------------------------------------------------------------------------------------------------ decoder

@@ -83,9 +83,9 @@ class _EngineBase:
     def _g(self, k):
         return self._dev(self._state[k])
 
-    def _lin(self, prefix, bias=True, weight=None) -> _abi.FaLinear:
+    def _lin(self, prefix, bias=True, weight=None, bias_tensor=None) -> _abi.FaLinear:
         w = self._dev(self._state[prefix + ".weight"]) if weight is None else weight
-        b = self._dev(self._state[prefix + ".bias"]) if bias else None
+        b = bias_tensor if bias_tensor is not None else (self._dev(self._state[prefix + ".bias"]) if bias else None)
         out_f, in_f = w.shape
         in_pad = (in_f + 63) // 64 * 64
         planes = None
@@ -151,10 +151,12 @@ class ParaformerEngine(_EngineBase):
     """Packed weights + workspace + the encoder/predictor/decoder ABI calls."""
 
     def __init__(self, state: Dict[str, torch.Tensor], cfg: ParaformerConfig, device, gemm_mode: str = "fp32",
-                 prefix_enc="encoder.", prefix_pred="predictor.", prefix_dec="decoder.", contextual: bool = False):
+                 prefix_enc="encoder.", prefix_pred="predictor.", prefix_dec="decoder.", contextual: bool = False, bicif: bool = False,
+                 smooth_factor2: float = 0.25, noise_threshold2: float = 0.01):
         self._init_base(state, device, gemm_mode, cfg.ln_eps)
         self.cfg = cfg
         self.contextual = contextual
+        self.bicif = bicif
         g, lin, norm = self._g, self._lin, self._norm
         D, K = cfg.d_model, cfg.kernel
         # ---- encoder
@@ -167,7 +169,18 @@ class ParaformerEngine(_EngineBase):
         conv = lin(prefix_pred + "cif_conv1d", weight=cw)
         self.pred = _abi.FaPredictor(conv, g(prefix_pred + "cif_output.weight").data_ptr(),
                                      g(prefix_pred + "cif_output.bias").data_ptr(), cfg.cif_threshold,
-                                     cfg.tail_threshold, 1.0, 0.0)
+                                     cfg.tail_threshold, 1.0, 0.0, 1 if bicif else 0, 0)
+        if bicif:   # CifPredictorV3 timestamp head (bicif_paraformer/cif_predictor.py:121-352, upsample_type "cnn_blstm", use_cif1_cnn False)
+            uw = state[prefix_pred + "upsample_cnn.weight"]                      # ConvTranspose1d weight [in, out, k], stride == k == 3
+            self.up_times = int(uw.shape[2])
+            # out[b, 3t+k, o] = sum_c x[b,t,c] w[c,o,k] + bias[o]  ==  one GEMM with W[(k,o), c], rows viewed as [B, 3T, 512]
+            self.up_lin = lin(prefix_pred + "upsample_cnn", weight=self._dev(uw.permute(2, 1, 0).reshape(-1, uw.shape[0])),
+                              bias_tensor=self._dev(state[prefix_pred + "upsample_cnn.bias"].repeat(self.up_times)))
+            self.blstm = torch.nn.LSTM(D, D, 1, bias=True, batch_first=True, dropout=0.0, bidirectional=True).to(self.device)
+            self.blstm.load_state_dict({k[len(prefix_pred + "blstm."):]: v for k, v in state.items() if k.startswith(prefix_pred + "blstm.")})
+            self.blstm.eval().requires_grad_(False)
+            self.out2_w, self.out2_b = g(prefix_pred + "cif_output2.weight"), g(prefix_pred + "cif_output2.bias")
+            self.smooth2, self.noise2 = float(smooth_factor2), float(noise_threshold2)
         # ---- decoder
         def dec_layer(L, p, full=True):
             L.norm1 = norm(p + ".norm1")
@@ -222,6 +235,31 @@ class ParaformerEngine(_EngineBase):
                                                      n_cap, tok.data_ptr(), alphas.data_ptr(), peaks.data_ptr(), self.mode,
                                                      ws.data_ptr(), ws.numel(), self._stream()), "fa_cif_predictor_forward")
         return acoustic, tok, alphas, peaks
+
+    def upsample_timestamp(self, enc: torch.Tensor, lens: torch.Tensor, token_num: torch.Tensor):
+        """CifPredictorV3.get_upsample_timestamp (bicif_paraformer/cif_predictor.py:300-352): enc [B,T,512], lens [B] i32,
+        token_num [B] i32 (rounded) -> (us_alphas [B,3T], us_peaks [B,3T]).  ConvTranspose1d upsampling = one GEMM of this library,
+        the BLSTM is cuDNN through torch.nn.LSTM (library call, TF32 off), the alpha head / rescale / fire scan is
+        fa_cif_upsample_alphas."""
+        if not self.bicif:
+            raise _abi.FunasrB200Error("engine was not built with bicif=True")
+        B, T, D = enc.shape
+        U = self.up_times
+        up = torch.empty((B, T * U, D), dtype=torch.float32, device=self.device)
+        ws = self._workspace(max(4 * B * T * U * D * 4, 1 << 20))
+        _abi.check(self.lib.fa_linear(enc.data_ptr(), D, B * T, C.byref(self.up_lin), 0, None, 0, None, 0, up.data_ptr(), U * D, self.mode,
+                                      ws.data_ptr(), ws.numel(), self._stream()), "fa_linear(upsample_cnn)")
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            feat, _ = self.blstm(up)
+        feat = feat.contiguous()
+        us_alphas = torch.empty((B, T * U), dtype=torch.float32, device=self.device)
+        us_peaks = torch.empty_like(us_alphas)
+        lens_up = (lens.to(torch.int32) * U).contiguous()
+        tok = token_num.to(self.device, torch.int32).contiguous()
+        _abi.check(self.lib.fa_cif_upsample_alphas(feat.data_ptr(), 2 * D, self.out2_w.data_ptr(), self.out2_b.data_ptr(), lens_up.data_ptr(),
+                                                   tok.data_ptr(), B, T * U, self.smooth2, self.noise2, self.cfg.cif_threshold,
+                                                   us_alphas.data_ptr(), us_peaks.data_ptr(), self._stream()), "fa_cif_upsample_alphas")
+        return us_alphas, us_peaks
 
     def set_hotwords(self, hw_embed: torch.Tensor):
         """Hotword memory [Nhw, 512] (LSTM last hidden states) for the contextual bias decoder."""
@@ -284,7 +322,7 @@ class ParaformerEngine(_EngineBase):
         tok_host = tok.cpu()                       # D2H + sync: B int32
         n_max = int(tok_host.max()) if tok_host.numel() else 0
         out = {"enc": enc, "alphas": alphas, "peaks": peaks, "token_num": tok_host, "acoustic": acoustic} if want_taps else \
-            {"token_num": tok_host, "alphas": alphas, "peaks": peaks}      # CIF weights / fires stay on the device (timestamps read them)
+            {"token_num": tok_host, "alphas": alphas, "peaks": peaks, "enc_dev": enc, "lens_dev": lens, "tok_dev": tok}   # device refs (timestamps)
         if n_max < 1:                              # paraformer/model.py:615-616
             out["ids"] = [[] for _ in range(feats.shape[0])]
             return out

@@ -178,6 +178,34 @@ class CifPredictorV2B200(_ParamHolder):
         return {"cif_conv1d.weight": (D, D, 3), "cif_conv1d.bias": (D,), "cif_output.weight": (1, D), "cif_output.bias": (1,)}
 
 
+@register("predictor_classes", "CifPredictorV3B200")
+class CifPredictorV3B200(_ParamHolder):
+    """Parameter container for CifPredictorV3 (funasr/models/bicif_paraformer/cif_predictor.py:121-352) in the configuration
+    BiCifParaformer ships with (template.yaml:52-63): upsample_type "cnn_blstm", use_cif1_cnn False, upsample_times 3."""
+
+    def __init__(self, idim, l_order, r_order, threshold=1.0, dropout=0.1, smooth_factor=1.0, noise_threshold=0, tail_threshold=0.0,
+                 smooth_factor2=1.0, noise_threshold2=0, upsample_times=5, upsample_type="cnn", use_cif1_cnn=True, tail_mask=True, **kwargs):
+        super().__init__()
+        if (idim, l_order, r_order, smooth_factor, noise_threshold, tail_mask) != (512, 1, 1, 1.0, 0, True) or tail_threshold <= 0:
+            raise _abi.FunasrB200Error("CifPredictorV3B200 supports idim=512, l_order=r_order=1, tail_threshold>0, tail_mask")
+        if upsample_type != "cnn_blstm" or use_cif1_cnn or upsample_times != 3:
+            raise _abi.FunasrB200Error("CifPredictorV3B200 supports upsample_type='cnn_blstm', use_cif1_cnn=False, upsample_times=3")
+        self.idim, self.threshold, self.tail_threshold = idim, threshold, tail_threshold
+        self.smooth_factor2, self.noise_threshold2, self.upsample_times = float(smooth_factor2), float(noise_threshold2), upsample_times
+        self._build()
+
+    def _specs(self):
+        D, U = self.idim, self.upsample_times
+        s = {"cif_conv1d.weight": (D, D, 3), "cif_conv1d.bias": (D,), "cif_output.weight": (1, D), "cif_output.bias": (1,),
+             "upsample_cnn.weight": (D, D, U), "upsample_cnn.bias": (D,), "cif_output2.weight": (1, 2 * D), "cif_output2.bias": (1,)}
+        for suf in ("", "_reverse"):
+            s["blstm.weight_ih_l0" + suf] = (4 * D, D)
+            s["blstm.weight_hh_l0" + suf] = (4 * D, D)
+            s["blstm.bias_ih_l0" + suf] = (4 * D,)
+            s["blstm.bias_hh_l0" + suf] = (4 * D,)
+        return s
+
+
 @register("decoder_classes", "ParaformerSANMDecoderB200")
 class ParaformerSANMDecoderB200(_ParamHolder):
     def __init__(self, vocab_size: int, encoder_output_size: int, attention_heads: int = 4, linear_units: int = 2048,
@@ -338,6 +366,8 @@ class ParaformerB200(nn.Module):
             meta_data["extract_feat"] = f"{time.perf_counter() - t2:0.3f}"
             meta_data["batch_data_time"] = sum(num_lfr_frames(n) for n in wl) * frontend.frame_shift * frontend.lfr_n / 1000
         out = eng.forward_feats(speech, lens, sos=self.sos, eos=self.eos, blank=self.blank_id)
+        if kwargs.get("_keep_taps"):
+            self._last_out = out                  # BiCifParaformerB200 reads enc / lens / token counts for its timestamp head
         ids = out["ids"]
         if max((int(t) for t in out["token_num"].tolist()), default=0) < 1:
             return [], meta_data                              # model.py:615-616
@@ -557,3 +587,57 @@ class ContextualParaformerB200(ParaformerB200):
             hw = [tokenizer.tokens2ids(h.split()) for h in kwargs["hotword"].split()] + [[self.sos]]
         self.engine(kwargs.get("device", "cuda")).set_hotwords(self.encode_hotwords(hw))
         return super().inference(data_in, data_lengths, key, tokenizer, frontend, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BiCifParaformer (timestamps)
+# ------------------------------------------------------------------------------------------------------------------
+@register("model_classes", "BiCifParaformerB200")
+class BiCifParaformerB200(ParaformerB200):
+    """Drop-in for BiCifParaformer's greedy inference (funasr/models/bicif_paraformer/model.py:271-428): the Paraformer path with
+    CifPredictorV3 (sequential fp32 `cif` on the token branch) plus the upsampled CIF timestamp head; results carry
+    "timestamp": [[start_ms, end_ms], ...] per token."""
+
+    def __init__(self, *args, **kwargs):
+        if not isinstance(kwargs.get("predictor"), type) and kwargs.get("predictor") != "CifPredictorV3B200":
+            kwargs["predictor"] = "CifPredictorV3B200"
+        super().__init__(*args, **kwargs)
+
+    def engine(self, device=None) -> ParaformerEngine:
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _abi.FunasrB200Error("BiCifParaformerB200 needs a CUDA device; there is no CPU path")
+        if self._engine is None or self._engine.device != dev:
+            self._engine = ParaformerEngine(self.state_dict(), self.cfg, dev, gemm_mode=self.gemm_mode, bicif=True,
+                                            smooth_factor2=self.predictor.smooth_factor2, noise_threshold2=self.predictor.noise_threshold2)
+        return self._engine
+
+    def calc_predictor_timestamp(self, encoder_out, encoder_out_lens, token_num):
+        """model.py:177-191 -> (ds_alphas=None, ds_cif_peak=None, us_alphas, us_peaks)."""
+        us_alphas, us_peaks = self.engine(encoder_out.device).upsample_timestamp(encoder_out, encoder_out_lens.to(torch.int32), token_num)
+        return None, None, us_alphas, us_peaks
+
+    def inference(self, data_in, data_lengths=None, key: list = None, tokenizer=None, frontend=None, **kwargs):
+        from .timestamps import ts_prediction_lfr6_standard
+        kwargs.pop("pred_timestamp", None)                      # BiCif always time-stamps, from its own head
+        results, meta_data = super().inference(data_in, data_lengths, key, tokenizer, frontend, _keep_taps=True, **kwargs)
+        out = getattr(self, "_last_out", None)
+        if not results or out is None:
+            return results, meta_data
+        eng = self.engine(kwargs.get("device", "cuda"))
+        us_alphas, us_peaks = eng.upsample_timestamp(out["enc_dev"], out["lens_dev"], out["tok_dev"])
+        ua, up, lens = us_alphas.cpu().numpy(), us_peaks.cpu().numpy(), out["lens_dev"].cpu().tolist()
+        for i, r in enumerate(results):
+            ids = out["ids"][i]
+            token = tokenizer.ids2tokens(ids) if tokenizer is not None else [str(t) for t in ids]
+            n = int(lens[i]) * eng.up_times
+            _, stamp = ts_prediction_lfr6_standard(ua[i][:n], up[i][:n], list(token), vad_offset=kwargs.get("begin_time", 0))   # model.py:402-407
+            if tokenizer is not None:
+                try:
+                    from funasr.utils import postprocess_utils
+                    r["text"], stamp, _ = postprocess_utils.sentence_postprocess(token, stamp)
+                except ImportError:
+                    pass
+            r["timestamp"] = stamp
+        self._last_out = None
+        return results, meta_data

@@ -65,6 +65,8 @@ DROP_IN_KEYS = {
     ("frontend_classes", "wav_frontend"): "WavFrontendB200",
     ("encoder_classes", "SANMEncoder"): "SANMEncoderB200",
     ("predictor_classes", "CifPredictorV2"): "CifPredictorV2B200",
+    ("predictor_classes", "CifPredictorV3"): "CifPredictorV3B200",
+    ("model_classes", "BiCifParaformer"): "BiCifParaformerB200",
     ("decoder_classes", "ParaformerSANMDecoder"): "ParaformerSANMDecoderB200",
 }
 

@@ -141,6 +141,25 @@ def make_contextual_state_dict(cfg: ParaformerConfig = PARAFORMER_LARGE, seed: i
     return sd
 
 
+def make_bicif_state_dict(cfg: ParaformerConfig = PARAFORMER_LARGE, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """BiCifParaformer (funasr/models/bicif_paraformer; predictor CifPredictorV3, upsample_type cnn_blstm, template.yaml:52-63):
+    the Paraformer dict plus the timestamp head `predictor.upsample_cnn` (ConvTranspose1d 512->512, k=s=3), `predictor.blstm`
+    (1-layer bidirectional LSTM 512->512) and `predictor.cif_output2` (Linear 1024->1)."""
+    sd = make_state_dict(cfg, seed)
+    g = torch.Generator().manual_seed(1000003 * seed + 77)
+    D = cfg.d_model
+    sd["predictor.upsample_cnn.weight"] = _randn(g, D, D, 3, std=1.0 / math.sqrt(D))
+    sd["predictor.upsample_cnn.bias"] = _randn(g, D, std=0.05)
+    for suf in ("", "_reverse"):
+        sd["predictor.blstm.weight_ih_l0" + suf] = _randn(g, 4 * D, D, std=1.5 / math.sqrt(D))
+        sd["predictor.blstm.weight_hh_l0" + suf] = _randn(g, 4 * D, D, std=1.0 / math.sqrt(D))
+        sd["predictor.blstm.bias_ih_l0" + suf] = _randn(g, 4 * D, std=0.05)
+        sd["predictor.blstm.bias_hh_l0" + suf] = _randn(g, 4 * D, std=0.05)
+    sd["predictor.cif_output2.weight"] = _randn(g, 1, 2 * D, std=3.0 / math.sqrt(2 * D))
+    sd["predictor.cif_output2.bias"] = torch.full((1,), -0.3)
+    return sd
+
+
 def make_hotwords(n: int, vocab: int, seed: int = 7, sos: int = 1):
     """n random hotword token-id sequences (len 2..6) + the trailing [sos] entry generate_hotwords_list appends
     (contextual_paraformer/model.py:606-607)."""

@@ -89,6 +89,9 @@ typedef struct {
   float tail_threshold; /* 0.45 */
   float smooth_factor;  /* 1.0 */
   float noise_threshold;/* 0.0 */
+  int32_t cif_variant;  /* 0: CifPredictorV2 `cif_v1` (fp64 prefix sums, paraformer/cif_predictor.py:818-908);
+                         * 1: CifPredictorV3 `cif` (sequential fp32, bicif_paraformer/cif_predictor.py:37-84) */
+  int32_t _pad;
 } FaPredictor;
 
 /* DecoderLayerSANM (funasr/models/paraformer/decoder.py:26-121) */
@@ -225,6 +228,15 @@ int fa_cif_predictor_forward(const FaPredictor* pred, const float* enc, const in
                              int32_t t_max, float* acoustic, int32_t n_cap, int32_t* token_num, float* alphas,
                              float* peaks, int32_t gemm_mode, void* workspace, size_t ws_bytes,
                              fa_stream_t stream);
+
+/* Timestamp head of CifPredictorV3.get_upsample_timestamp (bicif_paraformer/cif_predictor.py:331-352), after the
+ * ConvTranspose1d upsampling (a fa_linear with the [3*512, 512] repacked weight) and the BLSTM:
+ *   alphas2 = relu(sigmoid(feat . w + b) * smooth2 - noise2) * mask;  alphas2 *= token_num / sum(alphas2);
+ *   us_peaks = cif_wo_hidden(alphas2, threshold - 1e-4).
+ * feat [B, t_up, dz] (dz = 1024), lens_up[B] = 3 * encoder lengths, token_num[B]; us_alphas / us_peaks [B, t_up]. */
+int fa_cif_upsample_alphas(const float* feat, int32_t dz, const float* w, const float* b, const int32_t* lens_up,
+                           const int32_t* token_num, int32_t batch, int32_t t_up, float smooth2, float noise2,
+                           float threshold, float* us_alphas, float* us_peaks, fa_stream_t stream);
 
 /* ParaformerSANMDecoder.forward (decoder.py:397-449) + greedy argmax (paraformer/model.py:642-644).
  *   enc [B,T,512], enc_lens[B]; acoustic [B, ld_acoustic_rows, 512] of which the first n_max rows are used;

@@ -124,7 +124,7 @@ def main():
     write_cmvn_file(os.path.join(GOLD, "am_synth.mvn"), synth.make_cmvn(synth.PARAFORMER_LARGE, seed=1))
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("sensevoice", "contextual")):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("sensevoice", "contextual", "bicif")):
     main()
 
 
@@ -265,3 +265,79 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "contextual":
     with tempfile.TemporaryDirectory() as tmp:
         for name, (cfg, wseed, specs, n_hot) in CTX_CASES.items():
             run_ctx_case(name, cfg, wseed, specs, n_hot, tmp)
+
+
+# ------------------------------------------------------------------------------------------------ BiCifParaformer
+BICIF_CASES = {
+    "bicif_tiny_ragged3": (synth.PARAFORMER_TINY, 8, [(48000, 31, "speechlike"), (27200, 32, "noise"), (38437, 33, "speechlike")]),
+    "bicif_large_single": (synth.PARAFORMER_LARGE, 3, [(160000, 34, "speechlike")]),
+}
+
+
+def run_bicif_case(name, cfg, wseed, wav_specs, tmp):
+    import copy
+    from funasr import AutoModel
+    from funasr.utils.timestamp_tools import ts_prediction_lfr6_standard
+    cmvn_file = os.path.join(tmp, "am_%s.mvn" % name)
+    write_cmvn_file(cmvn_file, synth.make_cmvn(cfg, seed=1))
+    pt = os.path.join(tmp, "bicif_%s.pt" % name)
+    torch.save(synth.make_bicif_state_dict(cfg, wseed), pt)
+    tokens = ["<blank>", "<s>", "</s>"] + ["t%d" % i for i in range(cfg.vocab - 4)] + ["<unk>"]
+    am = AutoModel(
+        model="BiCifParaformer",
+        model_conf=dict(ctc_weight=0.0, lsm_weight=0.1, length_normalized_loss=True, predictor_weight=1.0, predictor_bias=1, sampling_ratio=0.75),
+        encoder="SANMEncoder",
+        encoder_conf=dict(output_size=cfg.d_model, attention_heads=cfg.heads, linear_units=cfg.ffn, num_blocks=cfg.enc_layers,
+                          dropout_rate=0.1, positional_dropout_rate=0.1, attention_dropout_rate=0.1, input_layer="pe",
+                          pos_enc_class="SinusoidalPositionEncoder", normalize_before=True, kernel_size=cfg.kernel, sanm_shfit=0,
+                          selfattention_layer_type="sanm"),
+        decoder="ParaformerSANMDecoder",
+        decoder_conf=dict(attention_heads=cfg.heads, linear_units=cfg.ffn, num_blocks=cfg.dec_layers, dropout_rate=0.1,
+                          positional_dropout_rate=0.1, self_attention_dropout_rate=0.1, src_attention_dropout_rate=0.1,
+                          att_layer_num=cfg.dec_layers, kernel_size=cfg.kernel, sanm_shfit=0),
+        predictor="CifPredictorV3",
+        predictor_conf=dict(idim=cfg.d_model, threshold=1.0, l_order=1, r_order=1, tail_threshold=cfg.tail_threshold, smooth_factor2=0.25,
+                            noise_threshold2=0.01, upsample_times=3, use_cif1_cnn=False, upsample_type="cnn_blstm"),
+        frontend="WavFrontend",
+        frontend_conf=dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0,
+                           cmvn_file=cmvn_file),
+        tokenizer="CharTokenizer", tokenizer_conf=dict(token_list=tokens, unk_symbol="<unk>", split_with_space=True),
+        device="cpu", ncpu=os.cpu_count(), disable_update=True, disable_pbar=True, init_param=pt,
+    )
+    model, frontend = am.model, am.kwargs["frontend"]
+    wavs = [synth.make_wav(n, s, k) for (n, s, k) in wav_specs]
+    with torch.no_grad():
+        from funasr.utils.load_utils import extract_fbank
+        feats, flens = extract_fbank([w for w in wavs], frontend=frontend)
+        enc, elens = model.encode(feats, flens)
+        emb, tok, alphas, peaks = model.calc_predictor(enc, elens)
+        tokl = tok.round().long()
+        logp, _ = model.cal_decoder_with_predictor(enc, elens, emb, tokl)
+        _, _, us_alphas, us_peaks = model.calc_predictor_timestamp(enc, elens, tokl)
+    ids, stamps = [], []
+    for i in range(len(wavs)):
+        ys = logp[i, : int(tokl[i])].argmax(-1).tolist()
+        ids.append([t for t in ys if t not in (0, 1, 2)])
+        n = int(elens[i]) * 3
+        _, st = ts_prediction_lfr6_standard(us_alphas[i][:n].clone(), us_peaks[i][:n].clone(), copy.copy([tokens[t] for t in ids[-1]]), vad_offset=0)
+        stamps.append(st)
+    N = logp.shape[1]
+    keep = sorted(set(list(range(min(4, N))) + [N // 2, N - 1]))
+    top2 = torch.topk(logp, 2, dim=-1).values
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), token_num=tokl.numpy().astype(np.int32), enc_lens=elens.numpy().astype(np.int32),
+                        alphas=alphas.numpy(), peaks=peaks.numpy(), acoustic=emb[:, :, ::5].numpy(),
+                        us_alphas=us_alphas.numpy(), us_peaks=us_peaks.numpy(),
+                        logp_rows=np.array(keep, dtype=np.int32), logp_sel=logp[:, keep, :].numpy(),
+                        ids_flat=np.array([t for r in ids for t in r], dtype=np.int32), ids_len=np.array([len(r) for r in ids], dtype=np.int32),
+                        stamps_flat=np.array([v for st in stamps for pair in st for v in pair], dtype=np.int32),
+                        stamps_len=np.array([len(st) for st in stamps], dtype=np.int32))
+    valid = torch.arange(N)[None, :] < tokl[:, None]
+    print("%s: B=%d tokens=%s stamps=%s min margin %.3e first stamps %s" % (name, len(wavs), tokl.tolist(), [len(s) for s in stamps],
+                                                                           float((top2[..., 0] - top2[..., 1])[valid].min()), stamps[0][:3]))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "bicif":
+    ref_shim.import_reference()
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (cfg, wseed, specs) in BICIF_CASES.items():
+            run_bicif_case(name, cfg, wseed, specs, tmp)

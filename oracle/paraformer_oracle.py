@@ -446,3 +446,98 @@ def contextual_forward(wavs, p, cmvn, enc_layers: int, dec_layers: int, hw_list,
         logits = contextual_decoder(enc, elens, emb, tok, hw, p, dec_layers, heads, eps)
         logp = torch.log_softmax(logits, dim=-1)
     return {"enc": enc, "token_num": tok.to(torch.int32), "acoustic": emb, "hw_embed": hw, "logp": logp, "ids": greedy_ids(logp, tok)}
+
+
+# --------------------------------------------------------------------------------------
+# BiCifParaformer: funasr/models/bicif_paraformer/{cif_predictor.py,model.py}
+# --------------------------------------------------------------------------------------
+def cif_loop(hidden: Tensor, alphas: Tensor, threshold: float = 1.0):
+    """`cif` bicif_paraformer/cif_predictor.py:37-84: sequential fp32 integrate-and-fire; returns (frames padded to the
+    largest fire count, fires)."""
+    B, T, D = hidden.shape
+    integrate = torch.zeros(B)
+    frame = torch.zeros(B, D)
+    fires, frames = [], []
+    for t in range(T):
+        alpha = alphas[:, t]
+        completion = torch.ones(B) - integrate
+        integrate = integrate + alpha
+        fires.append(integrate)
+        fire = integrate >= threshold
+        integrate = torch.where(fire, integrate - torch.ones(B), integrate)
+        cur = torch.where(fire, completion, alpha)
+        rem = alpha - cur
+        frame = frame + cur[:, None] * hidden[:, t, :]
+        frames.append(frame)
+        frame = torch.where(fire[:, None], rem[:, None] * hidden[:, t, :], frame)
+    fires = torch.stack(fires, 1)
+    frames = torch.stack(frames, 1)
+    rows = [frames[b][fires[b] >= threshold] for b in range(B)]
+    n = max(int(r.shape[0]) for r in rows)
+    out = torch.zeros(B, n, D)
+    for b, r in enumerate(rows):
+        out[b, : r.shape[0]] = r
+    return out, fires
+
+
+def predictor_v3(enc: Tensor, enc_lens: Tensor, p, tail_threshold=0.45, threshold=1.0):
+    """BiCifParaformer.calc_predictor model.py:162-175 -> CifPredictorV3.forward (inference branch, :219-298)."""
+    B, T, _ = enc.shape
+    mask = (torch.arange(T)[None, :] < enc_lens[:, None].long())[:, None, :]
+    al = cif_alphas(enc, mask, p)
+    hidden, al2, token_num = cif_tail(enc, al, mask.squeeze(1).float(), tail_threshold)
+    emb, fires = cif_loop(hidden, al2, threshold)
+    n_int = int(torch.max(token_num).type(torch.int32).item())
+    if emb.shape[1] < n_int:
+        emb = F.pad(emb, (0, 0, 0, n_int - emb.shape[1]))
+    return emb[:, :n_int, :], token_num, al2, fires
+
+
+def cif_wo_hidden_loop(alphas: Tensor, threshold: float) -> Tensor:
+    """`cif_wo_hidden` bicif_paraformer/cif_predictor.py:87-117."""
+    B, T = alphas.shape
+    integrate = torch.zeros(B)
+    fires = []
+    for t in range(T):
+        integrate = integrate + alphas[:, t]
+        fires.append(integrate)
+        integrate = torch.where(integrate >= threshold, integrate - torch.ones(B) * threshold, integrate)
+    return torch.stack(fires, 1)
+
+
+def upsample_timestamp(enc: Tensor, enc_lens: Tensor, token_num: Tensor, p, smooth2=0.25, noise2=0.01, threshold=1.0, times=3):
+    """CifPredictorV3.get_upsample_timestamp :300-352 with upsample_type "cnn_blstm", use_cif1_cnn False
+    -> (us_alphas [B, 3T], us_peaks [B, 3T])."""
+    B, T, D = enc.shape
+    up = F.conv_transpose1d(enc.transpose(1, 2), p["predictor.upsample_cnn.weight"], p["predictor.upsample_cnn.bias"], stride=times)
+    lstm = torch.nn.LSTM(D, D, 1, bias=True, batch_first=True, dropout=0.0, bidirectional=True)
+    lstm.load_state_dict({k[len("predictor.blstm."):]: v for k, v in p.items() if k.startswith("predictor.blstm.")})
+    with torch.no_grad():
+        o2, _ = lstm(up.transpose(1, 2))
+    a2 = torch.sigmoid(F.linear(o2, p["predictor.cif_output2.weight"], p["predictor.cif_output2.bias"]))
+    a2 = torch.relu(a2 * smooth2 - noise2)
+    mask = (torch.arange(T)[None, :] < enc_lens[:, None].long())[:, None, :]
+    mask2 = mask.repeat(1, times, 1).transpose(-1, -2).reshape(B, -1).unsqueeze(-1)
+    a2 = (a2 * mask2).squeeze(-1)
+    tot = a2.sum(-1)
+    a2 = a2 * (token_num / tot)[:, None].repeat(1, a2.size(1))
+    return a2, cif_wo_hidden_loop(a2, threshold - 1e-4)
+
+
+def bicif_forward(wavs: List[Tensor], p: Dict[str, Tensor], cmvn: Optional[Tensor], enc_layers: int, dec_layers: int, heads: int = 4,
+                  eps: float = 1e-12, tail_threshold: float = 0.45):
+    """BiCifParaformer.inference model.py:271-428 (greedy, tokenizer=None) plus the raw CIF timestamps it would attach."""
+    with torch.no_grad():
+        feats, flens = frontend(wavs, cmvn)
+        enc, elens = encoder(feats, flens, p, enc_layers, heads, eps, None)
+        emb, token_num, alphas, fires = predictor_v3(enc, elens, p, tail_threshold)
+        tok = token_num.round().long()
+        out = {"enc": enc, "enc_lens": elens, "alphas": alphas, "peaks": fires, "token_num": tok.to(torch.int32), "acoustic": emb}
+        if int(tok.max()) < 1:
+            out.update(ids=[[] for _ in wavs])
+            return out
+        logits = decoder(enc, elens, emb, tok, p, dec_layers, heads, eps, None)
+        logp = torch.log_softmax(logits, dim=-1)
+        us_alphas, us_peaks = upsample_timestamp(enc, elens, tok, p)
+        out.update(logp=logp, ids=greedy_ids(logp, tok), us_alphas=us_alphas, us_peaks=us_peaks)
+    return out

@@ -98,3 +98,31 @@ def load_ctx_case(name):
     cmvn = synth.make_cmvn(cfg, seed=1)
     cmvn = torch.tensor(np.array([[float("%.9g" % v) for v in row] for row in cmvn.tolist()], dtype=np.float32))
     return cfg, wseed, wavs, cmvn, synth.make_hotwords(n_hot, cfg.vocab, seed=7), gold
+
+
+# BiCifParaformer golden cases — must match oracle/make_golden.py:BICIF_CASES
+BICIF_CASES = {
+    "bicif_tiny_ragged3": ("tiny", 8, [(48000, 31, "speechlike"), (27200, 32, "noise"), (38437, 33, "speechlike")]),
+    "bicif_large_single": ("large", 3, [(160000, 34, "speechlike")]),
+}
+
+
+def load_bicif_case(name):
+    from funasr_b200 import synth
+    cfg_name, wseed, specs = BICIF_CASES[name]
+    cfg = synth.PARAFORMER_TINY if cfg_name == "tiny" else synth.PARAFORMER_LARGE
+    gold = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    wavs = [synth.make_wav(n, s, k) for (n, s, k) in specs]
+    cmvn = synth.make_cmvn(cfg, seed=1)
+    cmvn = torch.tensor(np.array([[float("%.9g" % v) for v in row] for row in cmvn.tolist()], dtype=np.float32))
+    return cfg, wseed, wavs, cmvn, gold
+
+
+def gold_stamps(g):
+    """[[[s, e], ...] per utterance] from the flat golden arrays."""
+    out, pos = [], 0
+    for n in g["stamps_len"].tolist():
+        flat = g["stamps_flat"][pos: pos + 2 * n].tolist()
+        out.append([[flat[2 * i], flat[2 * i + 1]] for i in range(n)])
+        pos += 2 * n
+    return out

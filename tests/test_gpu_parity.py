@@ -528,3 +528,72 @@ def test_offline_handle_api_vs_reference_golden(tmp_path, mode):
     rec.close()
     with pytest.raises(Exception):
         OfflineRecognizer(str(tmp_path / "missing.fab2"), 0, mode)
+
+
+# ------------------------------------------------------------------------------------------------ BiCifParaformer
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("name", ["bicif_tiny_ragged3", "bicif_large_single"])
+def test_bicif_vs_reference_golden(name, mode):
+    """BiCifParaformer against the unmodified reference: CifPredictorV3's sequential fp32 `cif` on the token
+    branch (fa_cif_predictor_forward, cif_variant 1), the upsampled timestamp head (ConvTranspose1d as a GEMM of this library,
+    cuDNN BLSTM, fa_cif_upsample_alphas) and the per-token [start_ms, end_ms] the reference derives from it."""
+    from conftest import gold_stamps, load_bicif_case
+    from funasr_b200 import synth
+    from funasr_b200.engine import FrontendEngine, ParaformerEngine
+    from funasr_b200.timestamps import ts_prediction_lfr6_standard
+    cfg, wseed, wavs, cmvn, g = load_bicif_case(name)
+    eng = ParaformerEngine(synth.make_bicif_state_dict(cfg, wseed), cfg, DEV, gemm_mode=mode, bicif=True)
+    fe = FrontendEngine(cmvn, DEV)
+    lens = [w.numel() for w in wavs]
+    pad = torch.nn.utils.rnn.pad_sequence(wavs, batch_first=True).to(DEV)
+    from funasr_b200.engine import num_lfr_frames
+    feats, fl = fe(pad, torch.tensor(lens, dtype=torch.int32, device=DEV), max(num_lfr_frames(n) for n in lens))
+    o = eng.forward_feats(feats, fl, want_taps=True)
+    assert o["token_num"].tolist() == g["token_num"].tolist()
+    assert np.abs(o["alphas"].cpu().numpy() - g["alphas"]).max() <= 1e-4
+    assert np.abs(o["peaks"].cpu().numpy() - g["peaks"]).max() <= 2e-3          # running fp32 integral of ~T alphas
+    n = int(g["token_num"].max())
+    assert rel_err(o["acoustic"][:, :n, ::5].cpu().numpy(), g["acoustic"]) <= 1e-3
+    assert rel_err(o["logp"][:, g["logp_rows"].tolist(), :].cpu().numpy(), g["logp_sel"]) <= 1e-3
+    assert [t for r in o["ids"] for t in r] == g["ids_flat"].tolist()           # greedy ids: bit-exact
+    tok = torch.tensor(g["token_num"], dtype=torch.int32, device=DEV)
+    us_alphas, us_peaks = eng.upsample_timestamp(o["enc"], fl, tok)
+    assert rel_err(us_alphas.cpu().numpy(), g["us_alphas"]) <= 1e-3
+    want = gold_stamps(g)
+    ua, up = us_alphas.cpu().numpy(), us_peaks.cpu().numpy()
+    exact = total = 0
+    for i, ids in enumerate(o["ids"]):
+        m = int(g["enc_lens"][i]) * 3
+        got = ts_prediction_lfr6_standard(ua[i][:m], up[i][:m], ["t%d" % (t - 3) for t in ids])[1]
+        assert len(got) == len(want[i])
+        for a, b in zip(got, want[i]):
+            total += 1
+            exact += a == b
+            assert abs(a[0] - b[0]) <= 20 and abs(a[1] - b[1]) <= 20            # at most one upsampled frame (20 ms)
+    assert exact >= 0.9 * total
+
+
+@pytest.mark.gpu
+def test_bicif_plugin_inference_timestamps():
+    """BiCifParaformerB200.inference keeps BiCifParaformer.inference's contract: token ids + "timestamp" per token."""
+    import funasr_b200
+    from conftest import gold_stamps, load_bicif_case
+    from funasr_b200 import synth
+    from test_abi_host import _tiny_conf
+    cfg, wseed, wavs, cmvn, g = load_bicif_case("bicif_tiny_ragged3")
+    conf = _tiny_conf()
+    conf["predictor"] = "CifPredictorV3B200"
+    conf["predictor_conf"] = dict(idim=512, threshold=1.0, l_order=1, r_order=1, tail_threshold=cfg.tail_threshold, smooth_factor2=0.25,
+                                  noise_threshold2=0.01, upsample_times=3, use_cif1_cnn=False, upsample_type="cnn_blstm")
+    m = funasr_b200.BiCifParaformerB200(**conf)
+    m.load_state_dict(synth.make_bicif_state_dict(cfg, wseed), strict=True)
+    m.to(DEV).eval()
+    fe = funasr_b200.WavFrontendB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6,
+                                     dither=0.0, cmvn=cmvn)
+    res, _ = m.inference([w.numpy() for w in wavs], key=["a", "b", "c"], tokenizer=None, frontend=fe, device=DEV)
+    assert [t for r in res for t in r["token_int"]] == g["ids_flat"].tolist()
+    want = gold_stamps(g)
+    for r, w in zip(res, want):
+        assert len(r["timestamp"]) == len(w)
+        assert all(abs(a[0] - b[0]) <= 20 and abs(a[1] - b[1]) <= 20 for a, b in zip(r["timestamp"], w))

@@ -1,10 +1,13 @@
 """CPU: the oracle restatement against the golden vectors produced by the UNMODIFIED reference
 (oracle/make_golden.py), and — when /root/reference is present — against the live reference itself."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from conftest import CTX_CASES, GOLDEN_CASES, SV_CASES, load_case, load_ctx_case, load_sv_case, rel_err, state_dict_for
+from conftest import (BICIF_CASES, CTX_CASES, GOLDEN_CASES, SV_CASES, gold_stamps, load_bicif_case, load_case, load_ctx_case, load_sv_case,
+                      rel_err, state_dict_for)
 
 import paraformer_oracle as O
 import ref_shim
@@ -121,3 +124,25 @@ def test_contextual_oracle_matches_reference_golden(name):
     assert rel_err(o["hw_embed"].numpy(), g["hw_embed"]) <= 1e-5
     assert rel_err(o["logp"][:, g["logp_rows"].tolist()].numpy(), g["logp_sel"]) <= 1e-4
     assert [t for r in o["ids"] for t in r] == g["ids_flat"].tolist() and [len(r) for r in o["ids"]] == g["ids_len"].tolist()
+
+
+@pytest.mark.parametrize("name", list(BICIF_CASES))
+def test_bicif_oracle_matches_reference_golden(name):
+    """BiCifParaformer: sequential fp32 `cif`, upsampled CIF timestamp head (ConvTranspose + BLSTM) and the
+    timestamps the reference's ts_prediction_lfr6_standard derives, vs the unmodified reference."""
+    from funasr_b200 import synth
+    from funasr_b200.timestamps import ts_prediction_lfr6_standard
+    cfg, wseed, wavs, cmvn, g = load_bicif_case(name)
+    o = O.bicif_forward(wavs, synth.make_bicif_state_dict(cfg, wseed), cmvn, cfg.enc_layers, cfg.dec_layers)
+    assert o["token_num"].tolist() == g["token_num"].tolist()
+    assert np.abs(o["alphas"].numpy() - g["alphas"]).max() <= 1e-5
+    assert np.abs(o["peaks"].numpy() - g["peaks"]).max() <= 1e-4
+    assert rel_err(o["acoustic"][:, :, ::5].numpy(), g["acoustic"]) <= 1e-5
+    assert rel_err(o["us_alphas"].numpy(), g["us_alphas"]) <= 1e-4
+    assert np.abs(o["us_peaks"].numpy() - g["us_peaks"]).max() <= 1e-3
+    assert [t for r in o["ids"] for t in r] == g["ids_flat"].tolist() and [len(r) for r in o["ids"]] == g["ids_len"].tolist()
+    want = gold_stamps(g)
+    for i, ids in enumerate(o["ids"]):
+        n = int(o["enc_lens"][i]) * 3
+        got = ts_prediction_lfr6_standard(o["us_alphas"][i][:n].numpy(), o["us_peaks"][i][:n].numpy(), ["t%d" % (t - 3) for t in ids])[1]
+        assert got == want[i]
