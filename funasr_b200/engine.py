@@ -178,7 +178,16 @@ class ParaformerEngine(_EngineBase):
                               bias_tensor=self._dev(state[prefix_pred + "upsample_cnn.bias"].repeat(self.up_times)))
             self.blstm = torch.nn.LSTM(D, D, 1, bias=True, batch_first=True, dropout=0.0, bidirectional=True).to(self.device)
             self.blstm.load_state_dict({k[len(prefix_pred + "blstm."):]: v for k, v in state.items() if k.startswith(prefix_pred + "blstm.")})
-            self.blstm.eval().requires_grad_(False)
+            self.blstm.eval().requires_grad_(False)               # cuDNN path, kept for A/B (FUNASR_B200_LSTM=cudnn)
+            # this library's BLSTM: input projections of both directions as ONE GEMM ([W_ih_fwd; W_ih_bwd], b_ih + b_hh), then the
+            # persistent weight-stationary recurrence fa_blstm_forward
+            bp = prefix_pred + "blstm."
+            w_ih = torch.cat([state[bp + "weight_ih_l0"], state[bp + "weight_ih_l0_reverse"]], 0)
+            b_all = torch.cat([state[bp + "bias_ih_l0"] + state[bp + "bias_hh_l0"],
+                               state[bp + "bias_ih_l0_reverse"] + state[bp + "bias_hh_l0_reverse"]], 0)
+            self.lstm_ih = lin(bp + "ih", weight=self._dev(w_ih), bias_tensor=self._dev(b_all))
+            self.lstm_hh_f, self.lstm_hh_b = g(bp + "weight_hh_l0"), g(bp + "weight_hh_l0_reverse")
+            self._lstm_sync = torch.zeros(2, dtype=torch.int32, device=self.device)
             self.out2_w, self.out2_b = g(prefix_pred + "cif_output2.weight"), g(prefix_pred + "cif_output2.bias")
             self.smooth2, self.noise2 = float(smooth_factor2), float(noise_threshold2)
         # ---- decoder
@@ -246,12 +255,20 @@ class ParaformerEngine(_EngineBase):
         B, T, D = enc.shape
         U = self.up_times
         up = torch.empty((B, T * U, D), dtype=torch.float32, device=self.device)
-        ws = self._workspace(max(4 * B * T * U * D * 4, 1 << 20))
+        ws = self._workspace(max(8 * B * T * U * D * 4, 1 << 20))
         _abi.check(self.lib.fa_linear(enc.data_ptr(), D, B * T, C.byref(self.up_lin), 0, None, 0, None, 0, up.data_ptr(), U * D, self.mode,
                                       ws.data_ptr(), ws.numel(), self._stream()), "fa_linear(upsample_cnn)")
-        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            feat, _ = self.blstm(up)
-        feat = feat.contiguous()
+        if os.environ.get("FUNASR_B200_LSTM", "native") == "cudnn" or B > 256:
+            with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                feat, _ = self.blstm(up)
+            feat = feat.contiguous()
+        else:
+            xproj = torch.empty((B * T * U, 8 * D), dtype=torch.float32, device=self.device)
+            _abi.check(self.lib.fa_linear(up.data_ptr(), D, B * T * U, C.byref(self.lstm_ih), 0, None, 0, None, 0, xproj.data_ptr(), 8 * D,
+                                          self.mode, ws.data_ptr(), ws.numel(), self._stream()), "fa_linear(blstm input projections)")
+            feat = torch.empty((B, T * U, 2 * D), dtype=torch.float32, device=self.device)
+            _abi.check(self.lib.fa_blstm_forward(xproj.data_ptr(), self.lstm_hh_f.data_ptr(), self.lstm_hh_b.data_ptr(), B, T * U, D,
+                                                 feat.data_ptr(), self._lstm_sync.data_ptr(), self._stream()), "fa_blstm_forward")
         us_alphas = torch.empty((B, T * U), dtype=torch.float32, device=self.device)
         us_peaks = torch.empty_like(us_alphas)
         lens_up = (lens.to(torch.int32) * U).contiguous()

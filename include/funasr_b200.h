@@ -238,6 +238,14 @@ int fa_cif_upsample_alphas(const float* feat, int32_t dz, const float* w, const 
                            const int32_t* token_num, int32_t batch, int32_t t_up, float smooth2, float noise2,
                            float threshold, float* us_alphas, float* us_peaks, fa_stream_t stream);
 
+/* One-layer bidirectional LSTM recurrence (torch.nn.LSTM(512, 512, 1, batch_first=True, bidirectional=True), the `blstm` of
+ * CifPredictorV3, bicif_paraformer/cif_predictor.py:187-190) as a persistent weight-stationary kernel.  The caller supplies
+ * the input projections of ALL steps (one fa_linear): xproj [B*T, 4096] = x [W_ih_fwd; W_ih_bwd]^T + (b_ih + b_hh), gate order
+ * i,f,g,o per direction.  w_hh_* [2048, 512].  out [B, T, 1024] (forward | reverse).  batch <= 256, hidden == 512.
+ * sync_scratch8: 8 bytes of device memory (zeroed by the call) for the per-direction step barrier. */
+int fa_blstm_forward(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, int32_t batch, int32_t t_len,
+                     int32_t hidden, float* out, void* sync_scratch8, fa_stream_t stream);
+
 /* ParaformerSANMDecoder.forward (decoder.py:397-449) + greedy argmax (paraformer/model.py:642-644).
  *   enc [B,T,512], enc_lens[B]; acoustic [B, ld_acoustic_rows, 512] of which the first n_max rows are used;
  *   tok_lens[B].  Outputs: argmax_ids [B, n_max] int32, argmax_logp [B, n_max] (log-softmax value of the
