@@ -52,11 +52,23 @@ blstm_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh_f, 
   for (int step = 0; step < T; ++step) {
     const int t = dir == 0 ? step : T - 1 - step;
     const int tp = dir == 0 ? t - 1 : t + 1;         // time index of h_{t-1} in processing order
+    // x projections (+ both biases) of this thread's 8 gate rows for every batch tile: independent of h, so they are fetched
+    // before the barrier wait and their latency hides behind it
+    float2 xin[4][4];
+#pragma unroll
+    for (int bt = 0; bt < 4; ++bt) {
+      const int b = bt * LS_BT + bl;
+      if (bt < n_tiles && b < batch) {
+        const float* xp = xproj + ((int64_t)b * T + t) * xp_ld + dir * 4 * LS_H + c * LS_UNITS + 2 * q;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xin[bt][g] = __ldg(reinterpret_cast<const float2*>(xp + g * LS_H));
+      }
+    }
     if (step > 0) {
       // every CTA of this direction has published its slice of h for the previous step
       if (tid == 0) {
         const unsigned int want = (unsigned int)step * LS_NC;
-        while (*reinterpret_cast<volatile unsigned int*>(counter) < want) { __nanosleep(40); }
+        while (*reinterpret_cast<volatile unsigned int*>(counter) < want) { }
         __threadfence();
       }
       __syncthreads();
@@ -67,24 +79,23 @@ blstm_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh_f, 
       const int b0 = bt * LS_BT;
       const int nb = min(LS_BT, batch - b0);
       if (step > 0) {
-        // gather h_{t-1} [nb, 512] of this direction (L2 -> smem); __ldcg: the lines were written by other SMs this launch
+        // gather h_{t-1} [nb, 512] of this direction, L2 -> shared memory with 16-byte async copies (cp.async.cg bypasses L1:
+        // the lines were written by other SMs during this launch); all 32 copies of a thread are in flight at once
+        const float* src0 = out + ((int64_t)b0 * T + tp) * out_ld + dir * LS_H;
         for (int idx = tid; idx < nb * (LS_H / 4); idx += blockDim.x) {
           const int b = idx / (LS_H / 4), k4 = idx % (LS_H / 4);
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(out + ((int64_t)(b0 + b) * T + tp) * out_ld + dir * LS_H) + k4);
-          *reinterpret_cast<float4*>(sH + b * LS_HLD + 4 * k4) = v;
+          const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sH + b * LS_HLD + 4 * k4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src0 + (int64_t)b * T * out_ld + 4 * k4) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
       __syncthreads();
       const int b = b0 + bl;
       if (bl < nb) {
-        // x projections (+ both biases) of this thread's 8 gate rows
-        const float* xp = xproj + ((int64_t)b * T + t) * xp_ld + dir * 4 * LS_H + c * LS_UNITS + 2 * q;
         float acc[4][2];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float2 x2 = __ldg(reinterpret_cast<const float2*>(xp + g * LS_H));
-          acc[g][0] = x2.x; acc[g][1] = x2.y;
-        }
+        for (int g = 0; g < 4; ++g) { acc[g][0] = xin[bt][g].x; acc[g][1] = xin[bt][g].y; }
         if (step > 0) {
           const float* hrow = sH + bl * LS_HLD;
           float dot[4][2];

@@ -39,6 +39,14 @@ U, D = 3, 512
 up = torch.empty((B, 500 * U, D), device=dev)
 with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
     t_lstm = timeit(lambda: eng.blstm(up))
+import ctypes as C
+from funasr_b200 import _abi
+xproj = torch.randn(B * 1500, 4096, device=dev) * 0.5
+feat = torch.empty(B, 1500, 1024, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+t_rec = timeit(lambda: _abi.check(eng.lib.fa_blstm_forward(xproj.data_ptr(), eng.lstm_hh_f.data_ptr(), eng.lstm_hh_b.data_ptr(), B, 1500, 512,
+                                                          feat.data_ptr(), eng._lstm_sync.data_ptr(), st), "blstm"))
+print(f"fa_blstm_forward alone (recurrence, B={B}, T=1500): {t_rec:.2f} ms = {t_rec / 1500 * 1000:.2f} us per step")
 os.environ["FUNASR_B200_LSTM"] = "cudnn"
 t_ts_cudnn = timeit(lambda: eng.upsample_timestamp(enc, lens, tok))
 os.environ["FUNASR_B200_LSTM"] = "native"
