@@ -246,6 +246,11 @@ int fa_cif_upsample_alphas(const float* feat, int32_t dz, const float* w, const 
 int fa_blstm_forward(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, int32_t batch, int32_t t_len,
                      int32_t hidden, float* out, void* sync_scratch8, fa_stream_t stream);
 
+/* Measurement aid for fa_blstm_forward: skip_mask bit 0 drops the recurrent dot products, bit 1 the h gather, bit 2 the step
+ * barrier (results are then meaningless); used by tools/bicif_probe.py to attribute the step time. */
+int fa_debug_blstm_variant(int32_t skip_mask, const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, int32_t batch,
+                           int32_t t_len, float* out, void* sync_scratch8, fa_stream_t stream);
+
 /* ParaformerSANMDecoder.forward (decoder.py:397-449) + greedy argmax (paraformer/model.py:642-644).
  *   enc [B,T,512], enc_lens[B]; acoustic [B, ld_acoustic_rows, 512] of which the first n_max rows are used;
  *   tok_lens[B].  Outputs: argmax_ids [B, n_max] int32, argmax_logp [B, n_max] (log-softmax value of the
