@@ -61,6 +61,16 @@ blstm_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh_f, 
   for (int step = 0; step < T; ++step) {
     const int t = dir == 0 ? step : T - 1 - step;
     const int tp = dir == 0 ? t - 1 : t + 1;         // time index of h_{t-1} in processing order
+    // x projections (+ both biases) of tile 0 are independent of h: fetched before the barrier wait, their DRAM latency hides
+    // behind it (the common case batch <= 64 has only this tile)
+    float x0[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = sg + 16 * i;
+      const float* xp = xproj + ((int64_t)min(b, batch - 1) * T + t) * xp_ld + dir * 4 * LS_H + c * LS_UNITS + u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) x0[i][g] = __ldg(xp + g * LS_H);
+    }
     if (step > 0 && !(SKIP & 4)) {
       // every CTA of this direction has published its slice of h for the previous step
       if (tid == 0) {
@@ -79,10 +89,15 @@ blstm_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh_f, 
       float acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int b = b0 + sg + 16 * i;
-        const float* xp = xproj + ((int64_t)min(b, batch - 1) * T + t) * xp_ld + dir * 4 * LS_H + c * LS_UNITS + u;
+        if (bt == 0) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) acc[i][g] = __ldg(xp + g * LS_H);
+          for (int g = 0; g < 4; ++g) acc[i][g] = x0[i][g];
+        } else {
+          const int b = b0 + sg + 16 * i;
+          const float* xp = xproj + ((int64_t)min(b, batch - 1) * T + t) * xp_ld + dir * 4 * LS_H + c * LS_UNITS + u;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) acc[i][g] = __ldg(xp + g * LS_H);
+        }
       }
       if (step > 0 && !(SKIP & 2)) {
         // gather h_{t-1} [nb, 512] of this direction, L2 -> shared memory with 16-byte async copies (cp.async.cg bypasses L1:
