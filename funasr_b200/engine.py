@@ -258,7 +258,8 @@ class ParaformerEngine(_EngineBase):
         ws = self._workspace(max(8 * B * T * U * D * 4, 1 << 20))
         _abi.check(self.lib.fa_linear(enc.data_ptr(), D, B * T, C.byref(self.up_lin), 0, None, 0, None, 0, up.data_ptr(), U * D, self.mode,
                                       ws.data_ptr(), ws.numel(), self._stream()), "fa_linear(upsample_cnn)")
-        if os.environ.get("FUNASR_B200_LSTM", "native") == "cudnn" or B > 256:
+        lstm_impl = os.environ.get("FUNASR_B200_LSTM", "tc")     # tc (default) | simt (exact fp32 FMAs) | cudnn (torch.nn.LSTM)
+        if lstm_impl == "cudnn" or B > 256:
             with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 feat, _ = self.blstm(up)
             feat = feat.contiguous()
@@ -267,8 +268,16 @@ class ParaformerEngine(_EngineBase):
             _abi.check(self.lib.fa_linear(up.data_ptr(), D, B * T * U, C.byref(self.lstm_ih), 0, None, 0, None, 0, xproj.data_ptr(), 8 * D,
                                           self.mode, ws.data_ptr(), ws.numel(), self._stream()), "fa_linear(blstm input projections)")
             feat = torch.empty((B, T * U, 2 * D), dtype=torch.float32, device=self.device)
-            _abi.check(self.lib.fa_blstm_forward(xproj.data_ptr(), self.lstm_hh_f.data_ptr(), self.lstm_hh_b.data_ptr(), B, T * U, D,
-                                                 feat.data_ptr(), self._lstm_sync.data_ptr(), self._stream()), "fa_blstm_forward")
+            if lstm_impl == "simt":
+                _abi.check(self.lib.fa_blstm_forward(xproj.data_ptr(), self.lstm_hh_f.data_ptr(), self.lstm_hh_b.data_ptr(), B, T * U, D,
+                                                     feat.data_ptr(), self._lstm_sync.data_ptr(), self._stream()), "fa_blstm_forward")
+            else:
+                nb = int(self.lib.fa_blstm_tc_scratch_bytes(B))
+                if getattr(self, "_lstm_scratch", None) is None or self._lstm_scratch.numel() < nb:
+                    self._lstm_scratch = torch.empty(nb, dtype=torch.uint8, device=self.device)
+                _abi.check(self.lib.fa_blstm_forward_tc(xproj.data_ptr(), self.lstm_hh_f.data_ptr(), self.lstm_hh_b.data_ptr(), B, T * U, D,
+                                                        feat.data_ptr(), self._lstm_scratch.data_ptr(), self._lstm_scratch.numel(),
+                                                        self._stream()), "fa_blstm_forward_tc")
         us_alphas = torch.empty((B, T * U), dtype=torch.float32, device=self.device)
         us_peaks = torch.empty_like(us_alphas)
         lens_up = (lens.to(torch.int32) * U).contiguous()

@@ -246,6 +246,13 @@ int fa_cif_upsample_alphas(const float* feat, int32_t dz, const float* w, const 
 int fa_blstm_forward(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, int32_t batch, int32_t t_len,
                      int32_t hidden, float* out, void* sync_scratch8, fa_stream_t stream);
 
+/* Tensor-core variant (default in the plugin): the per-step [B,512] x [512,2048] product on warp-level bf16 MMAs with the
+ * 3-product operand split (fp32 accumulate), h exchanged between CTAs as bf16 hi / lo planes.  Same contract as
+ * fa_blstm_forward; scratch >= fa_blstm_tc_scratch_bytes(batch) bytes of device memory (zeroed by the call). */
+size_t fa_blstm_tc_scratch_bytes(int32_t batch);
+int fa_blstm_forward_tc(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, int32_t batch, int32_t t_len,
+                        int32_t hidden, float* out, void* scratch, size_t scratch_bytes, fa_stream_t stream);
+
 /* Measurement aid for fa_blstm_forward: skip_mask bit 0 drops the recurrent dot products, bit 1 the h gather, bit 2 the step
  * barrier (results are then meaningless); used by tools/bicif_probe.py to attribute the step time. */
 int fa_debug_blstm_variant(int32_t skip_mask, const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, int32_t batch,

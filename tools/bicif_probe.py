@@ -46,14 +46,21 @@ feat = torch.empty(B, 1500, 1024, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 t_rec = timeit(lambda: _abi.check(eng.lib.fa_blstm_forward(xproj.data_ptr(), eng.lstm_hh_f.data_ptr(), eng.lstm_hh_b.data_ptr(), B, 1500, 512,
                                                           feat.data_ptr(), eng._lstm_sync.data_ptr(), st), "blstm"))
-print(f"fa_blstm_forward alone (recurrence, B={B}, T=1500): {t_rec:.2f} ms = {t_rec / 1500 * 1000:.2f} us per step")
+print(f"fa_blstm_forward (SIMT fp32) alone (recurrence, B={B}, T=1500): {t_rec:.2f} ms = {t_rec / 1500 * 1000:.2f} us per step")
+nbs = int(eng.lib.fa_blstm_tc_scratch_bytes(B))
+scr = torch.empty(nbs, dtype=torch.uint8, device=dev)
+feat_tc = torch.empty_like(feat)
+t_tc = timeit(lambda: _abi.check(eng.lib.fa_blstm_forward_tc(xproj.data_ptr(), eng.lstm_hh_f.data_ptr(), eng.lstm_hh_b.data_ptr(), B, 1500, 512,
+                                                            feat_tc.data_ptr(), scr.data_ptr(), nbs, st), "blstm tc"))
+torch.cuda.synchronize()
+print(f"fa_blstm_forward_tc (mma.sync bf16x3) alone: {t_tc:.2f} ms = {t_tc / 1500 * 1000:.2f} us per step; max |tc - simt| = {float((feat_tc - feat).abs().max()):.3e}")
 for mask, what in ((1, "no dot products"), (2, "no gather"), (4, "no barrier"), (3, "no dot, no gather"), (7, "x loads + gates + stores only")):
     tm = timeit(lambda: _abi.check(eng.lib.fa_debug_blstm_variant(mask, xproj.data_ptr(), eng.lstm_hh_f.data_ptr(), eng.lstm_hh_b.data_ptr(), B, 1500,
                                                                     feat.data_ptr(), eng._lstm_sync.data_ptr(), st), "blstm variant"), n=3)
     print(f"  variant {mask} ({what}): {tm:.2f} ms = {tm / 1.5:.2f} us per step")
 os.environ["FUNASR_B200_LSTM"] = "cudnn"
 t_ts_cudnn = timeit(lambda: eng.upsample_timestamp(enc, lens, tok))
-os.environ["FUNASR_B200_LSTM"] = "native"
+os.environ["FUNASR_B200_LSTM"] = "tc"
 a_n, p_n = eng.upsample_timestamp(enc, lens, tok)
 os.environ["FUNASR_B200_LSTM"] = "cudnn"
 a_c, p_c = eng.upsample_timestamp(enc, lens, tok)
