@@ -16,79 +16,83 @@ from typing import List, Sequence, Tuple
 
 import numpy as np
 
-START_END_THRESHOLD = 5
-MAX_TOKEN_DURATION = 12
+EDGE_SILENCE_FRAMES = 5        # leading / trailing gap (in CIF frames) above which a <sil> segment is emitted
+MAX_TOKEN_FRAMES = 12          # a token longer than this is cut and the remainder becomes <sil>
 
 
 def cif_wo_hidden(alphas: np.ndarray, threshold: float) -> np.ndarray:
-    """timestamp_tools.py:14-34 for one utterance: running fp32 integral, minus `threshold` after every fire; returns the
-    integral BEFORE the reset at every frame."""
-    a = np.asarray(alphas, dtype=np.float32)
-    fires = np.empty_like(a)
-    integrate = np.float32(0.0)
+    """Integrate-and-fire trace of one utterance (timestamp_tools.py:14-34): fp32 running sum of the weights, reduced by
+    `threshold` right after every frame where it reaches it; the returned trace holds the value BEFORE the reduction."""
+    w = np.asarray(alphas, dtype=np.float32)
+    trace = np.empty_like(w)
+    level = np.float32(0.0)
     thr = np.float32(threshold)
-    for t in range(a.shape[0]):
-        integrate = np.float32(integrate + a[t])
-        fires[t] = integrate
-        if integrate >= thr:
-            integrate = np.float32(integrate - np.float32(1.0) * thr)
-    return fires
+    for t, a in enumerate(w):
+        level = np.float32(level + a)
+        trace[t] = level
+        if level >= thr:
+            level = np.float32(level - np.float32(1.0) * thr)
+    return trace
+
+
+def _fire_positions(trace: np.ndarray, shift: float) -> np.ndarray:
+    return np.flatnonzero(trace >= np.float32(1.0 - 1e-4)).astype(np.float64) + shift
 
 
 def ts_prediction_lfr6_standard(us_alphas, us_peaks, char_list: Sequence[str], vad_offset: float = 0.0, force_time_shift: float = -1.5,
                                 sil_in_str: bool = True, upsample_rate: int = 3) -> Tuple[str, List[List[int]]]:
-    """Same contract as timestamp_tools.py:37-123 (one utterance).  Does not modify its inputs (the reference renormalises
-    its `us_alphas` argument in place, :68)."""
-    char_list = list(char_list)
-    if not len(char_list):
+    """Same contract as timestamp_tools.py:37-123 for one utterance: (formatted string, [[start_ms, end_ms] per token]).
+    Inputs are not modified (the reference renormalises its first argument in place, :68)."""
+    tokens = list(char_list)
+    if not tokens:
         return "", []
-    time_rate = 10.0 * 6 / 1000 / upsample_rate
-    alphas = np.array(us_alphas, dtype=np.float32).reshape(-1) if np.ndim(us_alphas) == 1 else np.array(us_alphas, dtype=np.float32)[0]
-    peaks = np.array(us_peaks, dtype=np.float32).reshape(-1) if np.ndim(us_peaks) == 1 else np.array(us_peaks, dtype=np.float32)[0]
-    if char_list[-1] == "</s>":
-        char_list = char_list[:-1]
-    thr = np.float32(1.0 - 1e-4)
-    fire_place = np.nonzero(peaks >= thr)[0].astype(np.float64) + force_time_shift
-    if len(fire_place) != len(char_list) + 1:
-        alphas = alphas / np.float32(alphas.sum(dtype=np.float32) / np.float32(len(char_list) + 1))
-        peaks = cif_wo_hidden(alphas, 1.0 - 1e-4)
-        fire_place = np.nonzero(peaks >= thr)[0].astype(np.float64) + force_time_shift
-    if len(fire_place) == 0:
+    if tokens[-1] == "</s>":
+        tokens.pop()
+    sec_per_frame = 10.0 * 6 / 1000 / upsample_rate
+    first = np.array(us_alphas, dtype=np.float32)
+    second = np.array(us_peaks, dtype=np.float32)
+    weights = first.reshape(-1) if first.ndim == 1 else first[0]
+    trace = second.reshape(-1) if second.ndim == 1 else second[0]
+    fires = _fire_positions(trace, force_time_shift)
+    if fires.size != len(tokens) + 1:
+        # the fire count disagrees with the token count: rescale the weights to sum to tokens + 1 and re-integrate (:67-72)
+        weights = weights / np.float32(weights.sum(dtype=np.float32) / np.float32(len(tokens) + 1))
+        trace = cif_wo_hidden(weights, 1.0 - 1e-4)
+        fires = _fire_positions(trace, force_time_shift)
+    if fires.size == 0:
         return "", []                      # the reference raises IndexError here (:83); nothing to time-stamp
-    num_frames = peaks.shape[0]
-    stamps: List[List[float]] = []
-    chars: List[str] = []
-    if fire_place[0] > START_END_THRESHOLD:
-        stamps.append([0.0, fire_place[0] * time_rate])
-        chars.append("<sil>")
-    for i in range(len(fire_place) - 1):
-        chars.append(char_list[i] if i < len(char_list) else "")
-        if MAX_TOKEN_DURATION < 0 or fire_place[i + 1] - fire_place[i] <= MAX_TOKEN_DURATION:
-            stamps.append([fire_place[i] * time_rate, fire_place[i + 1] * time_rate])
+    n_frames = trace.shape[0]
+    labels: List[str] = []
+    spans: List[List[float]] = []          # seconds
+
+    def emit(label, lo, hi):
+        labels.append(label)
+        spans.append([lo * sec_per_frame, hi * sec_per_frame])
+
+    if fires[0] > EDGE_SILENCE_FRAMES:
+        emit("<sil>", 0.0, fires[0])
+    for i, (lo, hi) in enumerate(zip(fires[:-1], fires[1:])):
+        label = tokens[i] if i < len(tokens) else ""
+        if MAX_TOKEN_FRAMES >= 0 and hi - lo > MAX_TOKEN_FRAMES:
+            cut = lo + MAX_TOKEN_FRAMES
+            emit(label, lo, cut)
+            emit("<sil>", cut, hi)
         else:
-            split = fire_place[i] + MAX_TOKEN_DURATION
-            stamps.append([fire_place[i] * time_rate, split * time_rate])
-            stamps.append([split * time_rate, fire_place[i + 1] * time_rate])
-            chars.append("<sil>")
-    if num_frames - fire_place[-1] > START_END_THRESHOLD:
-        end = (num_frames + fire_place[-1]) * 0.5
-        if stamps:
-            stamps[-1][1] = end * time_rate
-        stamps.append([end * time_rate, num_frames * time_rate])
-        chars.append("<sil>")
-    elif stamps:
-        stamps[-1][1] = num_frames * time_rate
+            emit(label, lo, hi)
+    if n_frames - fires[-1] > EDGE_SILENCE_FRAMES:
+        mid = (n_frames + fires[-1]) * 0.5
+        if spans:
+            spans[-1][1] = mid * sec_per_frame
+        emit("<sil>", mid, n_frames)
+    elif spans:
+        spans[-1][1] = n_frames * sec_per_frame
     if vad_offset:
-        for s in stamps:
-            s[0] += vad_offset / 1000.0
-            s[1] += vad_offset / 1000.0
-    txt = ""
-    for ch, s in zip(chars, stamps):
-        if not sil_in_str and ch == "<sil>":
-            continue
-        txt += "{} {} {};".format(ch, str(s[0] + 0.0005)[:5], str(s[1] + 0.0005)[:5])
-    res = [[int(s[0] * 1000), int(s[1] * 1000)] for ch, s in zip(chars, stamps) if ch != "<sil>"]
-    return txt, res
+        shift_s = vad_offset / 1000.0
+        spans = [[lo + shift_s, hi + shift_s] for lo, hi in spans]
+    text = "".join("{} {} {};".format(lab, str(lo + 0.0005)[:5], str(hi + 0.0005)[:5])
+                   for lab, (lo, hi) in zip(labels, spans) if sil_in_str or lab != "<sil>")
+    stamps = [[int(lo * 1000), int(hi * 1000)] for lab, (lo, hi) in zip(labels, spans) if lab != "<sil>"]
+    return text, stamps
 
 
 def paraformer_timestamps(peaks_row, alphas_row, tokens: Sequence[str], begin_time: float = 0.0) -> Tuple[str, List[List[int]]]:
