@@ -92,6 +92,7 @@ SIGNATURES = {
     "fa_debug_blstm_variant": (C.c_int, [_i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "fa_greedy_filter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fa_split_bf16": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "fa_resample": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _vp]),
     # handle-style offline recogniser (funasrruntime.h:100-116 counterpart; offline.cu)
     "fa_offline_init": (_vp, [C.c_char_p, _i32, _i32]),
     "fa_offline_infer": (_vp, [_vp, C.POINTER(_vp), C.POINTER(_i64), _i32, _i32]),

@@ -362,6 +362,15 @@ class ParaformerB200(nn.Module):
             for i, w in enumerate(wavs):
                 wav_dev[i, : wl[i]].copy_(w, non_blocking=True)
             wl_dev = torch.tensor(wl, dtype=torch.int32).to(device, non_blocking=True)
+            audio_fs = int(kwargs.get("fs", frontend.fs))          # rate of the given waveforms (load_utils.py:176-178 resamples)
+            if audio_fs != frontend.fs and all(isinstance(x, (np.ndarray, torch.Tensor)) for x in
+                                               (data_in if isinstance(data_in, (list, tuple)) else [data_in])):
+                from .resample import resample, sinc_resample_table
+                wav_dev, wl_dev = resample(wav_dev, wl_dev, audio_fs, frontend.fs)
+                _, o_r, n_r, _ = sinc_resample_table(audio_fs, frontend.fs)
+                wl = [-(-n_r * n // o_r) for n in wl]
+                if min(wl) < 400:
+                    raise _abi.FunasrB200Error("utterances shorter than one 25 ms frame (400 samples) are not supported")
             speech, lens = frontend.engine(device)(wav_dev, wl_dev, max(num_lfr_frames(n) for n in wl))
             meta_data["extract_feat"] = f"{time.perf_counter() - t2:0.3f}"
             meta_data["batch_data_time"] = sum(num_lfr_frames(n) for n in wl) * frontend.frame_shift * frontend.lfr_n / 1000

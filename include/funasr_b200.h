@@ -286,6 +286,13 @@ int fa_ctc_greedy_forward(const FaLinear* ctc_lo, const float* enc, const int32_
                           int32_t blank, int32_t* argmax_ids, int32_t* out_ids, int32_t* out_lens, float* logp,
                           int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream);
 
+/* Polyphase sinc resampler (torchaudio.functional.resample semantics, used by FunASR's loader when the input rate differs from
+ * the model's: funasr/utils/load_utils.py:176-178).  orig / nnew are the rates divided by their gcd, table [nnew, 2*width + orig]
+ * is torchaudio's _get_sinc_resample_kernel (funasr_b200/resample.py builds it).  x [B, x_stride] with lens[B] valid samples ->
+ * y [B, y_stride], first y_cap columns written (zero beyond each row's length), out_lens[b] = min(ceil(nnew*lens[b]/orig), y_cap). */
+int fa_resample(const float* x, const int32_t* lens, int32_t batch, int64_t x_stride, const float* table, int32_t orig,
+                int32_t nnew, int32_t width, float* y, int64_t y_stride, int32_t y_cap, int32_t* out_lens, fa_stream_t stream);
+
 /* Split fp32 [rows, cols] into three bf16 planes [3][rows][cols_pad] (hi, mid, lo; zero padded columns):
  * weight repack for the tcgen05 GEMM path (called once per weight after load_pretrained_model). */
 int fa_split_bf16(const float* src, int64_t ld_src, int64_t rows, int32_t cols, int32_t cols_pad,

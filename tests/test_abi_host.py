@@ -224,3 +224,15 @@ def test_offline_api_rejects_bad_arguments_without_a_gpu():
     assert lib.fa_offline_last_error() != b""
     assert not lib.fa_offline_init(None, 0, 3)
     assert lib.fa_offline_result_count(None) == 0
+
+
+def test_resample_table_matches_torchaudio():
+    """funasr_b200.resample restates torchaudio's _get_sinc_resample_kernel (the resampler behind load_utils.py:176-178)."""
+    import math
+    taf = pytest.importorskip("torchaudio.functional.functional")
+    from funasr_b200.resample import sinc_resample_table
+    for o, n in [(8000, 16000), (48000, 16000), (44100, 16000), (22050, 16000), (32000, 16000), (16000, 8000)]:
+        tab, orig, new, width = sinc_resample_table(o, n)
+        ref, w = taf._get_sinc_resample_kernel(o, n, math.gcd(o, n))
+        assert (orig, new, width) == (o // math.gcd(o, n), n // math.gcd(o, n), w)
+        assert np.array_equal(tab, ref[:, 0, :].numpy())

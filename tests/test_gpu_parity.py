@@ -597,3 +597,58 @@ def test_bicif_plugin_inference_timestamps():
     for r, w in zip(res, want):
         assert len(r["timestamp"]) == len(w)
         assert all(abs(a[0] - b[0]) <= 20 and abs(a[1] - b[1]) <= 20 for a, b in zip(r["timestamp"], w))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rates", [(8000, 16000), (48000, 16000), (44100, 16000)])
+def test_resample_matches_torchaudio_algorithm(rates):
+    """fa_resample against the torchaudio algorithm (pad (width, width + orig) zeros, conv1d with stride orig, truncate to
+    ceil(new * len / orig)) evaluated on the CPU with the same table — ragged batch, per-row lengths."""
+    from funasr_b200.resample import resample, sinc_resample_table
+    o, n = rates
+    tab, orig, new, width = sinc_resample_table(o, n)
+    g = torch.Generator().manual_seed(5)
+    lens = [o * 2 + 37, o + 1, 5000]
+    wav = torch.zeros(len(lens), max(lens))
+    for i, ln in enumerate(lens):
+        wav[i, :ln] = torch.randn(ln, generator=g) * 0.3
+    got, got_lens = resample(wav.to(DEV), torch.tensor(lens, dtype=torch.int32), o, n)
+    kern = torch.from_numpy(tab)[:, None, :]
+    for i, ln in enumerate(lens):
+        x = torch.nn.functional.pad(wav[i:i + 1, :ln], (width, width + orig))
+        ref = torch.nn.functional.conv1d(x[:, None], kern, stride=orig).transpose(1, 2).reshape(1, -1)
+        tl = -(-new * ln // orig)
+        assert int(got_lens[i]) == tl
+        assert torch.allclose(got[i, :tl].cpu(), ref[0, :tl], atol=2e-6, rtol=1e-5)
+        assert float(got[i, tl:].abs().max() if got.shape[1] > tl else 0.0) == 0.0
+    try:
+        import torchaudio
+        ta = torchaudio.functional.resample(wav[0:1, :lens[0]], o, n)
+        assert torch.allclose(got[0, :ta.shape[1]].cpu(), ta[0], atol=2e-6, rtol=1e-5)
+    except ImportError:
+        pass
+
+
+@pytest.mark.gpu
+def test_plugin_resamples_8k_input_like_the_reference_loader():
+    """inference(fs=8000): the waveform is resampled on the GPU (load_utils.py:176-178 semantics) before the frontend; ids equal
+    those obtained by resampling with the same algorithm on the CPU first."""
+    import funasr_b200
+    from funasr_b200.resample import sinc_resample_table
+    from test_abi_host import _tiny_conf
+    cfg, wseed, wavs, cmvn, g = load_case("tiny_ragged3")
+    m = funasr_b200.ParaformerB200(**_tiny_conf())
+    m.load_state_dict(state_dict_for(cfg, wseed), strict=True)
+    m.to(DEV).eval()
+    fe = funasr_b200.WavFrontendB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0, cmvn=cmvn)
+    w8 = [w[::2].contiguous() for w in wavs]                       # pretend 8 kHz recordings
+    res8, _ = m.inference([w.numpy() for w in w8], tokenizer=None, frontend=fe, device=DEV, fs=8000)
+    tab, orig, new, width = sinc_resample_table(8000, 16000)
+    kern = torch.from_numpy(tab)[:, None, :]
+    up = []
+    for w in w8:
+        x = torch.nn.functional.pad(w[None], (width, width + orig))
+        y = torch.nn.functional.conv1d(x[:, None], kern, stride=orig).transpose(1, 2).reshape(-1)
+        up.append(y[: -(-new * w.numel() // orig)].contiguous())
+    res16, _ = m.inference([w.numpy() for w in up], tokenizer=None, frontend=fe, device=DEV)
+    assert [r["token_int"] for r in res8] == [r["token_int"] for r in res16]
