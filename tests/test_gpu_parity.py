@@ -623,7 +623,9 @@ def test_resample_matches_torchaudio_algorithm(rates):
         assert float(got[i, tl:].abs().max() if got.shape[1] > tl else 0.0) == 0.0
     try:
         import torchaudio
-        ta = torchaudio.functional.resample(wav[0:1, :lens[0]], o, n)
+        # transforms.Resample precomputes the table in float64 like the reference's loader does (functional.resample on a float32
+        # waveform would build it in float32)
+        ta = torchaudio.transforms.Resample(o, n)(wav[0:1, :lens[0]])
         assert torch.allclose(got[0, :ta.shape[1]].cpu(), ta[0], atol=2e-6, rtol=1e-5)
     except ImportError:
         pass
