@@ -245,7 +245,7 @@ class ParaformerSANMDecoderB200(_ParamHolder):
         return s
 
 
-def _as_wave_list(data_in, fs: int, frontend=None, **kwargs) -> List[torch.Tensor]:
+def _as_wave_list(data_in, fs: int, frontend=None, audio_fs: int = 16000, **kwargs) -> List[torch.Tensor]:
     """ndarray / tensor / list thereof -> list of 1-D fp32 tensors.  Paths, bytes and urls are delegated to the
     reference's own loader (funasr.utils.load_utils.load_audio_text_image_video, model.py:578) when FunASR is
     installed; that part of the pipeline (audio decode / resample) is outside this backend's scope."""
@@ -259,7 +259,7 @@ def _as_wave_list(data_in, fs: int, frontend=None, **kwargs) -> List[torch.Tenso
                 from funasr.utils.load_utils import load_audio_text_image_video
             except Exception as e:  # pragma: no cover
                 raise _abi.FunasrB200Error("only ndarray / tensor waveforms are accepted without FunASR installed") from e
-            x = load_audio_text_image_video(x, fs=fs, audio_fs=kwargs.get("fs", 16000), data_type=kwargs.get("data_type", "sound"))
+            x = load_audio_text_image_video(x, fs=fs, audio_fs=audio_fs, data_type=kwargs.get("data_type", "sound"))
         x = x.to(torch.float32)
         if x.dim() > 1:
             x = x.mean(dim=0) if x.shape[0] > 1 else x[0]     # mono (load_utils.py:extract_fbank)
@@ -346,7 +346,9 @@ class ParaformerB200(nn.Module):
             lens = speech_lengths.to(device, torch.int32)
         else:
             t1 = time.perf_counter()
-            wavs = _as_wave_list(data_in, fs=getattr(frontend, "fs", 16000), **kwargs)
+            # kwargs["fs"] is the rate of the GIVEN audio (model.py:578 passes it to the loader as audio_fs)
+            wavs = _as_wave_list(data_in, fs=getattr(frontend, "fs", 16000), audio_fs=int(kwargs.get("fs", 16000)),
+                                 **{k: v for k, v in kwargs.items() if k not in ("fs", "audio_fs", "frontend")})
             t2 = time.perf_counter()
             meta_data["load_data"] = f"{t2 - t1:0.3f}"
             if not isinstance(frontend, WavFrontendB200):
@@ -503,7 +505,8 @@ class SenseVoiceSmallB200(nn.Module):
             raise _abi.FunasrB200Error("SenseVoiceSmallB200 needs frontend='WavFrontendB200'")
         eng = self.engine(device, frontend.cmvn)
         meta_data = {}
-        wavs = _as_wave_list(data_in, fs=frontend.fs, **kwargs)
+        wavs = _as_wave_list(data_in, fs=frontend.fs, audio_fs=int(kwargs.get("fs", 16000)),
+                             **{k: v for k, v in kwargs.items() if k not in ("fs", "audio_fs", "frontend")})
         wl = [int(w.numel()) for w in wavs]
         if min(wl) < 400:
             raise _abi.FunasrB200Error("utterances shorter than one 25 ms frame (400 samples) are not supported")
