@@ -56,7 +56,8 @@ def ts_prediction_lfr6_standard(us_alphas, us_peaks, char_list: Sequence[str], v
     fires = _fire_positions(trace, force_time_shift)
     if fires.size != len(tokens) + 1:
         # the fire count disagrees with the token count: rescale the weights to sum to tokens + 1 and re-integrate (:67-72)
-        weights = weights / np.float32(weights.sum(dtype=np.float32) / np.float32(len(tokens) + 1))
+        with np.errstate(invalid="ignore", divide="ignore"):          # all-zero weights: NaN like the reference, no fires below
+            weights = weights / np.float32(weights.sum(dtype=np.float32) / np.float32(len(tokens) + 1))
         trace = cif_wo_hidden(weights, 1.0 - 1e-4)
         fires = _fire_positions(trace, force_time_shift)
     if fires.size == 0:

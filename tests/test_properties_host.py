@@ -1,0 +1,62 @@
+"""Property tests (hypothesis) of the host-side logic around the hot path: utterance sharding, length bucketing, frame
+arithmetic and the CIF timestamp routine.  CPU only."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from funasr_b200.batching import bucket_by_length, padding_efficiency, run_bucketed
+from funasr_b200.engine import num_lfr_frames
+from funasr_b200.sharding import shard_utterances
+from funasr_b200 import timestamps as TS
+
+durs = st.lists(st.floats(min_value=0.03, max_value=120.0, allow_nan=False), min_size=0, max_size=200)
+
+
+@settings(max_examples=200, deadline=None)
+@given(durs, st.integers(min_value=1, max_value=8))
+def test_sharding_is_a_balanced_partition(d, world):
+    shards = shard_utterances(d, world)
+    flat = sorted(i for s in shards for i in s)
+    assert flat == list(range(len(d)))                               # every utterance exactly once
+    sizes = [len(s) for s in shards]
+    assert max(sizes) - min(sizes) <= 1                              # snake deal: sizes differ by at most one
+    if len(d) >= 2 * world:                                          # work is balanced to within the longest utterance
+        load = [sum(d[i] for i in s) for s in shards]
+        assert max(load) - min(load) <= max(d) + 1e-9
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.integers(min_value=400, max_value=16000 * 90), min_size=1, max_size=300),
+       st.integers(min_value=1, max_value=64), st.integers(min_value=1500, max_value=64 * 500))
+def test_bucketing_respects_caps_and_covers_everything(ns, max_batch, max_frames):
+    batches = bucket_by_length(ns, max_batch, max_frames)
+    assert sorted(i for b in batches for i in b) == list(range(len(ns)))
+    for b in batches:
+        assert 1 <= len(b) <= max_batch
+        t_max = max(num_lfr_frames(ns[i]) for i in b)
+        assert len(b) == 1 or len(b) * t_max <= max_frames           # a single over-long utterance still gets its own batch
+    assert 0.0 < padding_efficiency(ns, batches) <= 1.0
+    out = run_bucketed([np.zeros(n, np.float32) for n in ns], lambda ws: [[len(w)] for w in ws], max_batch, max_frames)
+    assert out == [[n] for n in ns]                                  # results come back in input order
+
+
+@given(st.integers(min_value=0, max_value=16000 * 600))
+def test_frame_arithmetic_matches_the_reference_formulas(n):
+    m = 1 + (n - 400) // 160 if n >= 400 else 0                      # kaldi.py _get_strided, snip_edges
+    t = int(np.ceil(m / 6))                                          # wav_frontend.py:73
+    assert num_lfr_frames(n) == t
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.floats(min_value=0.0, max_value=0.9375, allow_nan=False, width=32), min_size=8, max_size=300), st.integers(1, 40),
+       st.sampled_from([1, 3]), st.sampled_from([0.0, 250.0]))
+def test_timestamps_are_ordered_and_inside_the_utterance(alphas, n_tok, rate, offset):
+    a = np.array(alphas, dtype=np.float32)
+    peaks = TS.cif_wo_hidden(a, 1.0)
+    txt, res = TS.ts_prediction_lfr6_standard(a, peaks, ["t%d" % i for i in range(n_tok)], vad_offset=offset, upsample_rate=rate)
+    end_ms = (len(a) * 60.0 / rate) + offset
+    prev = -10**9
+    for s, e in res:
+        assert s <= e and s >= prev - 1                                # monotone up to the 1 ms integer truncation
+        assert e <= end_ms + 1
+        prev = s
+    assert len(res) <= max(n_tok, 1) + 1
