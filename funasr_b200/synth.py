@@ -160,6 +160,60 @@ def make_bicif_state_dict(cfg: ParaformerConfig = PARAFORMER_LARGE, seed: int = 
     return sd
 
 
+SEACO_FFN, SEACO_KERNEL, SEACO_LAYERS = 1024, 21, 6      # seaco_paraformer/template.yaml:57-69 (num_blocks 4 < att_layer_num 6 -> 6 layers)
+
+
+def seaco_no_bias_id(cfg: ParaformerConfig) -> int:
+    """The `NO_BIAS` token id (8377 of 8404 in the released model): the same distance from the end of the synthetic vocabulary."""
+    return cfg.vocab - 27
+
+
+def make_seaco_state_dict(cfg: ParaformerConfig = PARAFORMER_LARGE, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """SeacoParaformer (funasr/models/seaco_paraformer/model.py:50-120): the BiCif dict plus the 2-layer hotword LSTM
+    `bias_encoder`, the `seaco_decoder` (ParaformerSANMDecoder over the hotword memory: 6 attention layers, FFN 1024, FSMN k=21, no
+    input / output layer) and `hotword_output_layer`.  `decoder.embed` (the hotword embedding table here) gets unit variance."""
+    sd = make_bicif_state_dict(cfg, seed)
+    g = torch.Generator().manual_seed(1000003 * seed + 91)
+    D, V = cfg.d_model, cfg.vocab
+    sd["decoder.embed.0.weight"] = _randn(g, V, D, std=1.0)
+    for layer in (0, 1):
+        sd["bias_encoder.weight_ih_l%d" % layer] = _randn(g, 4 * D, D, std=1.0 / math.sqrt(D))
+        sd["bias_encoder.weight_hh_l%d" % layer] = _randn(g, 4 * D, D, std=1.0 / math.sqrt(D))
+        sd["bias_encoder.bias_ih_l%d" % layer] = _randn(g, 4 * D, std=0.05)
+        sd["bias_encoder.bias_hh_l%d" % layer] = _randn(g, 4 * D, std=0.05)
+
+    def linear(prefix, out_f, in_f, gain=1.0, bias=True):
+        sd[prefix + ".weight"] = _randn(g, out_f, in_f, std=gain / math.sqrt(in_f))
+        if bias:
+            sd[prefix + ".bias"] = _randn(g, out_f, std=0.02)
+
+    def norm(prefix, n):
+        sd[prefix + ".weight"] = 1.0 + _randn(g, n, std=0.1)
+        sd[prefix + ".bias"] = _randn(g, n, std=0.05)
+
+    def ffn(prefix, res):
+        linear(prefix + ".feed_forward.w_1", SEACO_FFN, D)
+        sd[prefix + ".feed_forward.w_2.weight"] = _randn(g, D, SEACO_FFN, std=res / math.sqrt(SEACO_FFN))
+        norm(prefix + ".feed_forward.norm", SEACO_FFN)
+
+    for i in range(SEACO_LAYERS):
+        p = "seaco_decoder.decoders.%d" % i
+        sd[p + ".self_attn.fsmn_block.weight"] = _randn(g, D, 1, SEACO_KERNEL, std=0.1)
+        linear(p + ".src_attn.linear_q", D, D, gain=1.5)
+        linear(p + ".src_attn.linear_k_v", 2 * D, D, gain=1.5)
+        linear(p + ".src_attn.linear_out", D, D, gain=0.5)
+        ffn(p, 0.3)
+        norm(p + ".norm1", D)
+        norm(p + ".norm2", D)
+        norm(p + ".norm3", D)
+    norm("seaco_decoder.after_norm", D)
+    ffn("seaco_decoder.decoders3.0", 0.7)
+    norm("seaco_decoder.decoders3.0.norm1", D)
+    linear("hotword_output_layer", V, D, gain=3.0)
+    sd["hotword_output_layer.bias"][seaco_no_bias_id(cfg)] = 3.0     # most positions vote NO_BIAS, some pick a hotword token
+    return sd
+
+
 def make_hotwords(n: int, vocab: int, seed: int = 7, sos: int = 1):
     """n random hotword token-id sequences (len 2..6) + the trailing [sos] entry generate_hotwords_list appends
     (contextual_paraformer/model.py:606-607)."""

@@ -124,7 +124,7 @@ def main():
     write_cmvn_file(os.path.join(GOLD, "am_synth.mvn"), synth.make_cmvn(synth.PARAFORMER_LARGE, seed=1))
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("sensevoice", "contextual", "bicif")):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("sensevoice", "contextual", "bicif", "seaco")):
     main()
 
 
@@ -341,3 +341,82 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "bicif":
     with tempfile.TemporaryDirectory() as tmp:
         for name, (cfg, wseed, specs) in BICIF_CASES.items():
             run_bicif_case(name, cfg, wseed, specs, tmp)
+
+
+# ------------------------------------------------------------------------------------------------ SeacoParaformer
+SEACO_CASES = {
+    # name: (cfg, weight seed, wavs, n hotwords, nfilter)  — the second case exercises attention-score filtering (nfilter < hotwords)
+    "seaco_tiny_ragged3": (synth.PARAFORMER_TINY, 10, [(48000, 41, "speechlike"), (27200, 42, "noise"), (38437, 43, "speechlike")], 6, 50),
+    "seaco_tiny_asf": (synth.PARAFORMER_TINY, 11, [(40000, 44, "speechlike"), (30000, 45, "speechlike")], 24, 8),
+}
+
+
+def run_seaco_case(name, cfg, wseed, wav_specs, n_hot, nfilter, tmp):
+    from funasr import AutoModel
+    cmvn_file = os.path.join(tmp, "am_%s.mvn" % name)
+    write_cmvn_file(cmvn_file, synth.make_cmvn(cfg, seed=1))
+    pt = os.path.join(tmp, "seaco_%s.pt" % name)
+    torch.save(synth.make_seaco_state_dict(cfg, wseed), pt)
+    tokens = ["<blank>", "<s>", "</s>"] + ["t%d" % i for i in range(cfg.vocab - 4)] + ["<unk>"]
+    no_bias = synth.seaco_no_bias_id(cfg)
+    am = AutoModel(
+        model="SeacoParaformer",
+        model_conf=dict(ctc_weight=0.0, lsm_weight=0.1, length_normalized_loss=True, predictor_weight=1.0, predictor_bias=1, sampling_ratio=0.75,
+                        inner_dim=512, bias_encoder_type="lstm", bias_encoder_bid=False, seaco_lsm_weight=0.1, seaco_length_normal=True,
+                        train_decoder=False, NO_BIAS=no_bias),
+        encoder="SANMEncoder",
+        encoder_conf=dict(output_size=cfg.d_model, attention_heads=cfg.heads, linear_units=cfg.ffn, num_blocks=cfg.enc_layers,
+                          dropout_rate=0.1, positional_dropout_rate=0.1, attention_dropout_rate=0.1, input_layer="pe",
+                          pos_enc_class="SinusoidalPositionEncoder", normalize_before=True, kernel_size=cfg.kernel, sanm_shfit=0,
+                          selfattention_layer_type="sanm"),
+        decoder="ParaformerSANMDecoder",
+        decoder_conf=dict(attention_heads=cfg.heads, linear_units=cfg.ffn, num_blocks=cfg.dec_layers, dropout_rate=0.1,
+                          positional_dropout_rate=0.1, self_attention_dropout_rate=0.1, src_attention_dropout_rate=0.1,
+                          att_layer_num=cfg.dec_layers, kernel_size=cfg.kernel, sanm_shfit=0),
+        seaco_decoder="ParaformerSANMDecoder",
+        seaco_decoder_conf=dict(attention_heads=4, linear_units=synth.SEACO_FFN, num_blocks=4, dropout_rate=0.1, positional_dropout_rate=0.1,
+                                self_attention_dropout_rate=0.1, src_attention_dropout_rate=0.1, kernel_size=synth.SEACO_KERNEL, sanm_shfit=0,
+                                use_output_layer=False, wo_input_layer=True),
+        predictor="CifPredictorV3",
+        predictor_conf=dict(idim=cfg.d_model, threshold=1.0, l_order=1, r_order=1, tail_threshold=cfg.tail_threshold, smooth_factor2=0.25,
+                            noise_threshold2=0.01, upsample_times=3, use_cif1_cnn=False, upsample_type="cnn_blstm"),
+        frontend="WavFrontend",
+        frontend_conf=dict(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0,
+                           cmvn_file=cmvn_file),
+        tokenizer="CharTokenizer", tokenizer_conf=dict(token_list=tokens, unk_symbol="<unk>", split_with_space=True),
+        device="cpu", ncpu=os.cpu_count(), disable_update=True, disable_pbar=True, init_param=pt,
+    )
+    model, frontend = am.model, am.kwargs["frontend"]
+    hw_list = synth.make_hotwords(n_hot, cfg.vocab, seed=9)
+    wavs = [synth.make_wav(n, s, k) for (n, s, k) in wav_specs]
+    with torch.no_grad():
+        from funasr.utils.load_utils import extract_fbank
+        feats, flens = extract_fbank([w for w in wavs], frontend=frontend)
+        enc, elens = model.encode(feats, flens)
+        emb, tok, alphas, peaks = model.calc_predictor(enc, elens)
+        tokl = tok.round().long()
+        merged = model._seaco_decode_with_ASF(enc, elens, emb, tokl, hw_list=hw_list, nfilter=nfilter)
+        sel = model._hotword_representation(torch.nn.utils.rnn.pad_sequence([torch.tensor(h) for h in hw_list], batch_first=True),
+                                            torch.tensor([len(h) for h in hw_list]).int())
+    ids = []
+    for i in range(len(wavs)):
+        ys = merged[i, : int(tokl[i])].argmax(-1).tolist()
+        ids.append([t for t in ys if t not in (0, 1, 2)])
+    N = merged.shape[1]
+    keep = sorted(set(list(range(min(4, N))) + [N // 2, N - 1]))
+    top2 = torch.topk(merged, 2, dim=-1).values
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), token_num=tokl.numpy().astype(np.int32), hw_selected=sel.numpy(),
+                        logp_rows=np.array(keep, dtype=np.int32), merged_sel=merged[:, keep, :].numpy(),
+                        argmax=merged.argmax(-1).numpy().astype(np.int32), margin=(top2[..., 0] - top2[..., 1]).numpy(),
+                        ids_flat=np.array([t for r in ids for t in r], dtype=np.int32), ids_len=np.array([len(r) for r in ids], dtype=np.int32))
+    valid = torch.arange(N)[None, :] < tokl[:, None]
+    n_bias = int(((merged.argmax(-1) != 0) & valid).sum())
+    print("%s: B=%d tokens=%s n_hot=%d nfilter=%d min margin %.3e ids[0][:6]=%s" % (name, len(wavs), tokl.tolist(), len(hw_list), nfilter,
+                                                                                 float((top2[..., 0] - top2[..., 1])[valid].min()), ids[0][:6]))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "seaco":
+    ref_shim.import_reference()
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, (cfg, wseed, specs, n_hot, nfilter) in SEACO_CASES.items():
+            run_seaco_case(name, cfg, wseed, specs, n_hot, nfilter, tmp)

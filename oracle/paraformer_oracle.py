@@ -541,3 +541,103 @@ def bicif_forward(wavs: List[Tensor], p: Dict[str, Tensor], cmvn: Optional[Tenso
         us_alphas, us_peaks = upsample_timestamp(enc, elens, tok, p)
         out.update(logp=logp, ids=greedy_ids(logp, tok), us_alphas=us_alphas, us_peaks=us_peaks)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# SeacoParaformer: funasr/models/seaco_paraformer/model.py (greedy inference with hotwords, ASF)
+# --------------------------------------------------------------------------------------
+def sanm_decoder_layers(x, x_lens, mem, mem_lens, p, prefix: str, layers, heads=4, eps=1e-12, attn_of: Optional[int] = None):
+    """DecoderLayerSANM.forward (paraformer/decoder.py:78-121) for `layers` of the decoder stored under `prefix`; with attn_of = i
+    the cross-attention matrix of layer i is returned instead (get_attn_mat :123-146) after running the layers before it."""
+    B, N, D = x.shape
+    T = mem.shape[1]
+    x_mask = (torch.arange(N)[None, :] < x_lens[:, None].long()).float()[:, :, None]
+    mem_mask = (torch.arange(T)[None, :] < mem_lens[:, None].long()).float()[:, None, :]
+    for i in layers:
+        pre = "%sdecoders.%d." % (prefix, i)
+        r = x
+        t = dec_ffn(layer_norm(x, p[pre + "norm1.weight"], p[pre + "norm1.bias"], eps), p, pre + "feed_forward.", eps)
+        t = layer_norm(t, p[pre + "norm2.weight"], p[pre + "norm2.bias"], eps)
+        x = r + fsmn(t, p[pre + "self_attn.fsmn_block.weight"], x_mask)
+        r = x
+        y = layer_norm(x, p[pre + "norm3.weight"], p[pre + "norm3.bias"], eps)
+        q = F.linear(y, p[pre + "src_attn.linear_q.weight"], p[pre + "src_attn.linear_q.bias"])
+        kv = F.linear(mem, p[pre + "src_attn.linear_k_v.weight"], p[pre + "src_attn.linear_k_v.bias"])
+        k, v = torch.split(kv, D, dim=-1)
+        if attn_of is not None and i == attn_of:
+            dk = D // heads
+            qh = q.view(B, N, heads, dk).transpose(1, 2) * dk ** (-0.5)
+            kh = k.view(B, T, heads, dk).transpose(1, 2)
+            sc = torch.matmul(qh, kh.transpose(-2, -1)).masked_fill(mem_mask[:, None].eq(0), -float("inf"))
+            return torch.softmax(sc, dim=-1).masked_fill(mem_mask[:, None].eq(0), 0.0)      # sanm/attention.py:781-793
+        x = r + F.linear(mh_attention(q, k, v, mem_mask, heads), p[pre + "src_attn.linear_out.weight"], p[pre + "src_attn.linear_out.bias"])
+    return x
+
+
+def sanm_decoder_hidden(x, x_lens, mem, mem_lens, p, prefix: str, n_layers: int, heads=4, eps=1e-12):
+    """ParaformerSANMDecoder.forward with return_hidden (decoder.py:397-449): decoders -> decoders3 -> after_norm."""
+    x = sanm_decoder_layers(x, x_lens, mem, mem_lens, p, prefix, range(n_layers), heads, eps)
+    pre = prefix + "decoders3.0."
+    x = dec_ffn(layer_norm(x, p[pre + "norm1.weight"], p[pre + "norm1.bias"], eps), p, pre + "feed_forward.", eps)
+    return layer_norm(x, p[prefix + "after_norm.weight"], p[prefix + "after_norm.bias"], eps)
+
+
+def seaco_hotword_representation(hw_list: List[List[int]], p: Dict[str, Tensor]) -> Tensor:
+    """_hotword_representation model.py:384-397: decoder.embed -> 2-layer LSTM over the PADDED batch (no packing) -> the output at
+    each hotword's last token."""
+    lens = [len(h) for h in hw_list]
+    pad = torch.zeros(len(hw_list), max(lens), dtype=torch.long)
+    for i, h in enumerate(hw_list):
+        pad[i, : len(h)] = torch.tensor(h)
+    lstm = torch.nn.LSTM(512, 512, 2, batch_first=True)
+    lstm.load_state_dict({k[len("bias_encoder."):]: v for k, v in p.items() if k.startswith("bias_encoder.")})
+    with torch.no_grad():
+        out, _ = lstm(F.embedding(pad, p["decoder.embed.0.weight"]))
+    return out[torch.arange(len(hw_list)), torch.tensor(lens) - 1]
+
+
+def seaco_decode_with_asf(enc, enc_lens, emb, tok, hw_list, p, dec_layers: int, no_bias: int, nfilter=50, seaco_weight=1.0, heads=4,
+                          eps=1e-12, seaco_layers=6):
+    """_seaco_decode_with_ASF model.py:271-382 -> merged log-probabilities [B, N, V] (plus the taps the tests compare)."""
+    hidden = sanm_decoder_hidden(emb, tok, enc, enc_lens, p, "decoder.", dec_layers, heads, eps)
+    dec_pred = torch.log_softmax(F.linear(hidden, p["decoder.output_layer.weight"], p["decoder.output_layer.bias"]), dim=-1)
+    B = enc.shape[0]
+    selected = seaco_hotword_representation(hw_list, p)
+    selected_all = selected
+    ctx = selected[None].repeat(B, 1, 1)
+    n_hw = ctx.shape[1]
+    picked = None
+    if 0 < nfilter < n_hw:                                             # ASF: keep the nfilter hotwords the FIRST utterance attends to most
+        attn = sanm_decoder_layers(hidden, tok, ctx, torch.full((B,), n_hw), p, "seaco_decoder.", range(seaco_layers), heads, eps,
+                                   attn_of=seaco_layers - 1)
+        scores = attn[0].sum(0).sum(0)
+        picked = torch.topk(scores, min(nfilter, n_hw - 1))[1].tolist() + [len(hw_list) - 1]
+        selected = selected[picked]
+        ctx = selected[None].repeat(B, 1, 1)
+        n_hw = ctx.shape[1]
+    hl = torch.full((B,), n_hw)
+    cif_att = sanm_decoder_hidden(emb, tok, ctx, hl, p, "seaco_decoder.", seaco_layers, heads, eps)
+    dec_att = sanm_decoder_hidden(hidden, tok, ctx, hl, p, "seaco_decoder.", seaco_layers, heads, eps)
+    dha_pred = torch.log_softmax(F.linear(cif_att + dec_att, p["hotword_output_layer.weight"], p["hotword_output_layer.bias"]), dim=-1)
+    lmbd = torch.full((B,), float(seaco_weight))
+    mask = (dha_pred.max(-1)[1] == no_bias).int().unsqueeze(-1)
+    a, b = ((1 - lmbd) / lmbd).reshape(-1, 1, 1), (1 / lmbd).reshape(-1, 1, 1)
+    mask = (mask + a) / b
+    return dec_pred * mask + dha_pred * (1 - mask), {"dec_hidden": hidden, "hw_selected": selected, "hw_selected_all": selected_all,
+                                                            "asf_picked": picked, "dha_pred": dha_pred}
+
+
+def seaco_forward(wavs: List[Tensor], p: Dict[str, Tensor], cmvn: Optional[Tensor], enc_layers: int, dec_layers: int, hw_list, no_bias: int,
+                  nfilter: int = 50, heads: int = 4, eps: float = 1e-12, tail_threshold: float = 0.45):
+    """SeacoParaformer.inference model.py:422-581 (greedy, tokenizer=None) with a hotword id list."""
+    with torch.no_grad():
+        feats, flens = frontend(wavs, cmvn)
+        enc, elens = encoder(feats, flens, p, enc_layers, heads, eps, None)
+        emb, token_num, alphas, fires = predictor_v3(enc, elens, p, tail_threshold)
+        tok = token_num.round().long()
+        merged, taps = seaco_decode_with_asf(enc, elens, emb, tok, hw_list, p, dec_layers, no_bias, nfilter, 1.0, heads, eps)
+        us_alphas, us_peaks = upsample_timestamp(enc, elens, tok, p)
+    out = {"enc_lens": elens, "token_num": tok.to(torch.int32), "merged": merged, "ids": greedy_ids(merged, tok), "us_alphas": us_alphas,
+           "us_peaks": us_peaks}
+    out.update(taps)
+    return out

@@ -130,3 +130,21 @@ def gold_stamps(g):
         out.append([[flat[2 * i], flat[2 * i + 1]] for i in range(n)])
         pos += 2 * n
     return out
+
+
+# SeacoParaformer golden cases — must match oracle/make_golden.py:SEACO_CASES (name: cfg, weight seed, wavs, n hotwords, nfilter)
+SEACO_CASES = {
+    "seaco_tiny_ragged3": ("tiny", 10, [(48000, 41, "speechlike"), (27200, 42, "noise"), (38437, 43, "speechlike")], 6, 50),
+    "seaco_tiny_asf": ("tiny", 11, [(40000, 44, "speechlike"), (30000, 45, "speechlike")], 24, 8),
+}
+
+
+def load_seaco_case(name):
+    from funasr_b200 import synth
+    cfg_name, wseed, specs, n_hot, nfilter = SEACO_CASES[name]
+    cfg = synth.PARAFORMER_TINY if cfg_name == "tiny" else synth.PARAFORMER_LARGE
+    gold = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    wavs = [synth.make_wav(n, s, k) for (n, s, k) in specs]
+    cmvn = synth.make_cmvn(cfg, seed=1)
+    cmvn = torch.tensor(np.array([[float("%.9g" % v) for v in row] for row in cmvn.tolist()], dtype=np.float32))
+    return cfg, wseed, wavs, cmvn, synth.make_hotwords(n_hot, cfg.vocab, seed=9), nfilter, gold

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import (BICIF_CASES, CTX_CASES, GOLDEN_CASES, SV_CASES, gold_stamps, load_bicif_case, load_case, load_ctx_case, load_sv_case,
+from conftest import (BICIF_CASES, CTX_CASES, GOLDEN_CASES, SEACO_CASES, SV_CASES, gold_stamps, load_bicif_case, load_case, load_ctx_case,
+                      load_seaco_case, load_sv_case,
                       rel_err, state_dict_for)
 
 import paraformer_oracle as O
@@ -146,3 +147,25 @@ def test_bicif_oracle_matches_reference_golden(name):
         n = int(o["enc_lens"][i]) * 3
         got = ts_prediction_lfr6_standard(o["us_alphas"][i][:n].numpy(), o["us_peaks"][i][:n].numpy(), ["t%d" % (t - 3) for t in ids])[1]
         assert got == want[i]
+
+
+@pytest.mark.parametrize("name", list(SEACO_CASES))
+def test_seaco_oracle_matches_reference_golden(name):
+    """SeacoParaformer (second half): 2-layer hotword LSTM, the seaco decoder over the hotword memory, attention-
+    score filtering (second case: 25 hotwords, nfilter 8) and the NO_BIAS merge, vs the unmodified reference's
+    `_seaco_decode_with_ASF`.  Oracle only — the CUDA path for this row is round-2 work."""
+    from funasr_b200 import synth
+    cfg, wseed, wavs, cmvn, hw, nfilter, g = load_seaco_case(name)
+    o = O.seaco_forward(wavs, synth.make_seaco_state_dict(cfg, wseed), cmvn, cfg.enc_layers, cfg.dec_layers, hw, synth.seaco_no_bias_id(cfg),
+                        nfilter=nfilter)
+    assert o["token_num"].tolist() == g["token_num"].tolist()
+    assert rel_err(seaco_sel(o, hw), g["hw_selected"]) <= 1e-5
+    assert rel_err(o["merged"][:, g["logp_rows"].tolist()].numpy(), g["merged_sel"]) <= 1e-4
+    assert [t for r in o["ids"] for t in r] == g["ids_flat"].tolist() and [len(r) for r in o["ids"]] == g["ids_len"].tolist()
+    if nfilter < len(hw):
+        assert o["asf_picked"] is not None and len(o["asf_picked"]) == nfilter + 1
+
+
+def seaco_sel(o, hw):
+    """the golden file stores the UNFILTERED hotword representations; recompute them when ASF filtered the oracle's copy"""
+    return o["hw_selected_all"].numpy()
