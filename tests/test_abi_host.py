@@ -236,3 +236,18 @@ def test_resample_table_matches_torchaudio():
         ref, w = taf._get_sinc_resample_kernel(o, n, math.gcd(o, n))
         assert (orig, new, width) == (o // math.gcd(o, n), n // math.gcd(o, n), w)
         assert np.array_equal(tab, ref[:, 0, :].numpy())
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/funasr_b200.h is a C header (not just C++): a C99 client compiles with -pedantic, links against the library and
+    runs; without a GPU / model file the handle API reports an error instead of falling back."""
+    exe = str(tmp_path / "offline_demo")
+    libdir = os.path.join(ROOT, "funasr_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "offline_demo.c"), "-L" + libdir, "-lfunasr_b200", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0 and "library: funasr_b200" in run.stdout
+    if not torch.cuda.is_available():
+        assert "init failed" in run.stdout
