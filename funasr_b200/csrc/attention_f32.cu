@@ -24,7 +24,7 @@ static_assert(sizeof(PsRow) * ATT_BQ <= sizeof(float) * ATT_D * (ATT_BK + 4), "P
 __global__ void __launch_bounds__(256)
 attention_f32_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
                      const float* __restrict__ v, int64_t ldv, const int32_t* __restrict__ key_lens, int tq, int tk,
-                     float* __restrict__ ctx, int64_t ldc, float qscale) {
+                     float* __restrict__ ctx, int64_t ldc, float qscale, int kv_shared) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttSmem& s = *reinterpret_cast<AttSmem*>(smem_raw);
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_BQ;
@@ -32,8 +32,9 @@ attention_f32_kernel(const float* __restrict__ q, int64_t ldq, const float* __re
   const int klen = min(key_lens[b], tk);
   PsRow* Ps = reinterpret_cast<PsRow*>(&s.Kt[0][0]);
   const float* qb = q + ((int64_t)b * tq) * ldq + h * ATT_D;
-  const float* kb = k + ((int64_t)b * tk) * ldk + h * ATT_D;
-  const float* vb = v + ((int64_t)b * tk) * ldv + h * ATT_D;
+  const int bkv = kv_shared ? 0 : b;                       // hotword memory: one k / v entry shared by every utterance
+  const float* kb = k + ((int64_t)bkv * tk) * ldk + h * ATT_D;
+  const float* vb = v + ((int64_t)bkv * tk) * ldv + h * ATT_D;
 
   // stage Q (scaled) transposed: 64 rows x 32 float4
   for (int idx = tid; idx < ATT_BQ * (ATT_D / 4); idx += 256) {
@@ -143,18 +144,15 @@ attention_f32_kernel(const float* __restrict__ q, int64_t ldq, const float* __re
 
 int attention_f32_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                          const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
-                         cudaStream_t st) {
+                         cudaStream_t st, int kv_shared) {
   if (batch <= 0 || tq <= 0) return FA_OK;
   if (!q || !k || !v || !key_lens || !ctx || tk <= 0) return FA_ERR_ARG;
   if ((ldq | ldk | ldv | ldc) & 3) return FA_ERR_UNSUPPORTED;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FA_CUDA_OK(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttSmem)));
-    attr_done = true;
-  }
+  static PerDeviceOnce once;
+  FA_RETURN_IF_ERR(ensure_dyn_smem(attention_f32_kernel, sizeof(AttSmem), once));
   dim3 grid((tq + ATT_BQ - 1) / ATT_BQ, heads, batch);
   const float qscale = (float)(1.0 / sqrt((double)ATT_D));  // float(d_k ** -0.5), attention.py:324
-  attention_f32_kernel<<<grid, 256, sizeof(AttSmem), st>>>(q, ldq, k, ldk, v, ldv, key_lens, tq, tk, ctx, ldc, qscale);
+  attention_f32_kernel<<<grid, 256, sizeof(AttSmem), st>>>(q, ldq, k, ldk, v, ldv, key_lens, tq, tk, ctx, ldc, qscale, kv_shared ? 1 : 0);
   FA_CHECK_LAUNCH();
   return FA_OK;
 }
@@ -165,5 +163,5 @@ extern "C" int fa_attention(const float* q, int64_t ldq, const float* k, int64_t
                             const int32_t* key_lens, int32_t batch, int32_t heads, int32_t tq, int32_t tk, float* ctx,
                             int64_t ld_ctx, fa_stream_t stream) {
   return fa::attention_f32_launch(q, ldq, k, ldk, v, ldv, key_lens, batch, heads, tq, tk, ctx, ld_ctx,
-                                  (cudaStream_t)stream);
+                                  (cudaStream_t)stream, 0);
 }

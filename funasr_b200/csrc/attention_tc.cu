@@ -30,6 +30,7 @@ constexpr uint32_t AT_P_TILE = AT_BQ * 128;      // 16 KB: 128 queries x 64 keys
 
 struct AttTcParams {
   int tq, tk, heads, batch;
+  int kv_shared;                                       // 1: every utterance attends over the SAME keys / values (hotword memory): K/V planes hold one batch entry
   const int32_t* key_lens;
   int64_t q_plane_rows, k_plane_rows, v_plane_rows;   // rows between planes in the respective 2D maps
   float* ctx; int64_t ldc;                             // fp32 output (or null)
@@ -106,6 +107,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   pdl_wait();                                        // everything above touched only shared / tensor memory
   pdl_trigger();
   const int klen = min(p.key_lens[b], p.tk);
+  const int bkv = p.kv_shared ? 0 : b;
   const int nc = (klen + AT_BKEY - 1) / AT_BKEY;     // key chunks with at least one valid key (same for the whole cluster)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base + TM_O;
@@ -135,8 +137,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           const int pl = bi >> 1, sub = bi & 1;
           int c0, c1;
           const CUtensorMap* mp;
-          if (is_v) { mp = &map_v; c0 = idx * AT_BKEY; c1 = (int)(pl * p.v_plane_rows + ((int64_t)b * p.heads + h) * AT_D + sub * 64); }
-          else { mp = &map_k; c0 = h * AT_D + sub * 64; c1 = (int)(pl * p.k_plane_rows + (int64_t)b * p.tk + idx * AT_BKEY); }
+          if (is_v) { mp = &map_v; c0 = idx * AT_BKEY; c1 = (int)(pl * p.v_plane_rows + ((int64_t)bkv * p.heads + h) * AT_D + sub * 64); }
+          else { mp = &map_k; c0 = h * AT_D + sub * 64; c1 = (int)(pl * p.k_plane_rows + (int64_t)bkv * p.tk + idx * AT_BKEY); }
           if (CL > 1) tma_load_2d_mc(dst + bi * BOX, mp, &r_full[slot], c0, c1, MC_ALL);
           else tma_load_2d(dst + bi * BOX, mp, &r_full[slot], c0, c1);
         }
@@ -449,14 +451,15 @@ size_t attention_tc_scratch_bytes(int batch, int heads, int tq, int tk, int mode
 
 int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                         const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
-                        __nv_bfloat16* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st) {
+                        __nv_bfloat16* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st, int kv_shared) {
   if (batch <= 0 || tq <= 0) return FA_OK;
   if (!q || !k || !v || !key_lens || tk <= 0 || !scratch) return FA_ERR_ARG;
   if ((ldq | ldk | ldv) & 3) return FA_ERR_UNSUPPORTED;
   const int npl = mode == FA_GEMM_BF16X1 ? 1 : 2;
   const int d = heads * AT_D;
   const int tkp = (tk + 63) / 64 * 64;
-  const int64_t mq = (int64_t)batch * tq, mk = (int64_t)batch * tk, mv = (int64_t)batch * d;
+  const int kvb = kv_shared ? 1 : batch;
+  const int64_t mq = (int64_t)batch * tq, mk = (int64_t)kvb * tk, mv = (int64_t)kvb * d;
   Arena local(scratch->base, scratch->cap);
   __nv_bfloat16* qp = local.take<__nv_bfloat16>((size_t)npl * mq * d);
   __nv_bfloat16* kp = local.take<__nv_bfloat16>((size_t)npl * mk * d);
@@ -470,21 +473,18 @@ int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk
     const int64_t totk = mk * (d / 4);
     scale_split_kernel<<<(unsigned)((totk + 255) / 256), 256, 0, st>>>(k, ldk, mk, d, 1.0f, npl, kp);
     FA_CHECK_LAUNCH();
-    dim3 g((tkp + 63) / 64, heads * 2, batch);
+    dim3 g((tkp + 63) / 64, heads * 2, kvb);
     vt_planes_kernel<<<g, 256, 0, st>>>(v, ldv, tk, tkp, heads, npl, mv * tkp, vt);
     FA_CHECK_LAUNCH();
   }
-  return attention_tc_planes_launch(qp, kp, vt, key_lens, batch, heads, tq, tk, ctx, ldc, ctx_planes, ldp, out_nplanes, mode, st);
+  return attention_tc_planes_launch(qp, kp, vt, key_lens, batch, heads, tq, tk, ctx, ldc, ctx_planes, ldp, out_nplanes, mode, st, kv_shared);
 }
 
 template <int NPL, int OPL, int CL>
 static int launch_att_c(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttTcParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)NPL * (2 * AT_Q_KBLK + 5 * 2 * 8192) + 1024 + 256 + 1024 + 256;
-  static bool done = false;
-  if (!done) {
-    FA_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<NPL, OPL, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done = true;
-  }
+  static PerDeviceOnce once;
+  FA_RETURN_IF_ERR(ensure_dyn_smem(attention_tc_kernel<NPL, OPL, CL>, smem, once));
   FA_CUDA_OK(launch_pdl(attention_tc_kernel<NPL, OPL, CL>, grid, dim3(384), smem, st, CL, mq, mk, mv, p));
   return FA_OK;
 }
@@ -511,19 +511,20 @@ static int launch_att(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, c
 // qp [npl][B*tq][H*128] (scaled), kp [npl][B*tk][H*128], vt [npl][B*H*128][round_up(tk,64)].
 int attention_tc_planes_launch(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfloat16* vt, const int32_t* key_lens,
                                int batch, int heads, int tq, int tk, float* ctx, int64_t ldc, __nv_bfloat16* ctx_planes,
-                               int64_t ldp, int out_nplanes, int mode, cudaStream_t st) {
+                               int64_t ldp, int out_nplanes, int mode, cudaStream_t st, int kv_shared) {
   if (batch <= 0 || tq <= 0) return FA_OK;
   if (!qp || !kp || !vt || !key_lens || tk <= 0) return FA_ERR_ARG;
   const int npl = mode == FA_GEMM_BF16X1 ? 1 : 2;
   const int d = heads * AT_D;
   const int tkp = (tk + 63) / 64 * 64;
-  const int64_t mq = (int64_t)batch * tq, mk = (int64_t)batch * tk, mv = (int64_t)batch * d;
+  const int kvb = kv_shared ? 1 : batch;
+  const int64_t mq = (int64_t)batch * tq, mk = (int64_t)kvb * tk, mv = (int64_t)kvb * d;
   CUtensorMap mq_map, mk_map, mv_map;
   FA_RETURN_IF_ERR(make_bf16_map(&mq_map, qp, (uint64_t)mq * npl, (uint64_t)d, (uint64_t)d, AT_BQ));
   FA_RETURN_IF_ERR(make_bf16_map(&mk_map, kp, (uint64_t)mk * npl, (uint64_t)d, (uint64_t)d, AT_BKEY));
   FA_RETURN_IF_ERR(make_bf16_map(&mv_map, vt, (uint64_t)mv * npl, (uint64_t)tk, (uint64_t)tkp, 64));   // 8 KB boxes: 64 d-rows x 64 keys
   AttTcParams p;
-  p.tq = tq; p.tk = tk; p.heads = heads; p.batch = batch; p.key_lens = key_lens;
+  p.tq = tq; p.tk = tk; p.heads = heads; p.batch = batch; p.key_lens = key_lens; p.kv_shared = kv_shared ? 1 : 0;
   p.q_plane_rows = mq; p.k_plane_rows = mk; p.v_plane_rows = mv;
   p.ctx = ctx; p.ldc = ldc; p.ctx_planes = ctx_planes; p.ldp = ldp; p.out_nplanes = out_nplanes;
   dim3 grid((tq + AT_BQ - 1) / AT_BQ, heads, batch);
@@ -563,5 +564,5 @@ extern "C" int fa_attention_tc(const float* q, int64_t ldq, const float* k, int6
   if (gemm_mode == FA_GEMM_F32_SIMT) return FA_ERR_ARG;
   fa::Arena scratch(workspace, ws_bytes);
   return fa::attention_tc_launch(q, ldq, k, ldk, v, ldv, key_lens, batch, heads, tq, tk, ctx, ld_ctx, nullptr, 0, 0, gemm_mode,
-                                 &scratch, (cudaStream_t)stream);
+                                 &scratch, (cudaStream_t)stream, 0);
 }

@@ -53,6 +53,50 @@ cif_alpha_kernel(const float* __restrict__ c, int d, const float* __restrict__ w
   }
 }
 
+// torch's CPU fp32 `x.sum(-1)` of one contiguous row, bit for bit (ATen/native/cpu/SumKernel.cpp: cascade_sum ->
+// vectorized_inner_sum -> row_sum -> multi_row_sum).  The x86 builds of torch 2.x run this kernel with 8 fp32 SIMD lanes
+// under every CPU capability (DEFAULT / AVX2 / AVX512 — verified against torch.sum for row lengths 1..9001 by
+// tests/test_oracle_golden.py::test_torch_row_sum_emulation), so the order is machine independent:
+//   the row is viewed as vectors of 8 lanes; vectors are dealt round-robin to 4 ILP accumulators (vector 4i+k -> accumulator k);
+//   each accumulator is a 4-level cascade that flushes level 0 into level 1 every 16 vectors (level 1 into 2 every 256, ...);
+//   then  p0 += leftover vectors;  p0 += p1; p0 += p2; p0 += p3;  result = (((tail scalars summed left to right) + lane0) + lane1) ...
+// The integer outcome floor(sum alpha) (cif_predictor.py:443-444) and the timestamp rescale token_num / sum(alpha2)
+// (bicif_paraformer/cif_predictor.py:343-345) follow the reference's rounding exactly.  Warp-collective (all 32 lanes of one
+// warp call it): thread (k = lane / 8, l = lane % 8) owns lane l of ILP accumulator k.  Every lane returns the sum.
+__device__ float torch_row_sum_f32(const float* __restrict__ x, int n) {
+  const int lane = threadIdx.x & 31, k = lane >> 3, l = lane & 7;
+  if (n < 8) {                                   // scalar_inner_sum: the same scheme with one lane
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int ilp = n >> 2;
+    for (int i = 0; i < ilp; ++i)
+      for (int kk = 0; kk < 4; ++kk) acc[kk] = __fadd_rn(acc[kk], x[4 * i + kk]);
+    for (int i = ilp * 4; i < n; ++i) acc[0] = __fadd_rn(acc[0], x[i]);
+    return __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), acc[2]), acc[3]);
+  }
+  const int vec_size = n >> 3, size_ilp = vec_size >> 2;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int i = 0;
+  while (i + 16 <= size_ilp) {                   // level_step = 16 (level_power = max(4, ceil_log2(size_ilp) / 4) = 4 up to 2^19 vectors)
+    for (int j = 0; j < 16; ++j, ++i) a0 = __fadd_rn(a0, x[((i << 2) + k) * 8 + l]);
+    a1 = __fadd_rn(a1, a0); a0 = 0.f;
+    if ((i & (15 << 4)) == 0) {
+      a2 = __fadd_rn(a2, a1); a1 = 0.f;
+      if ((i & (15 << 8)) == 0) { a3 = __fadd_rn(a3, a2); a2 = 0.f; }
+    }
+  }
+  for (; i < size_ilp; ++i) a0 = __fadd_rn(a0, x[((i << 2) + k) * 8 + l]);
+  a0 = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+  if (k == 0)
+    for (int v = size_ilp * 4; v < vec_size; ++v) a0 = __fadd_rn(a0, x[v * 8 + l]);
+  const float p1 = __shfl_sync(0xffffffffu, a0, 8 + l), p2 = __shfl_sync(0xffffffffu, a0, 16 + l), p3 = __shfl_sync(0xffffffffu, a0, 24 + l);
+  a0 = __fadd_rn(__fadd_rn(__fadd_rn(a0, p1), p2), p3);            // meaningful in lanes 0..7
+  float f = 0.f;
+  for (int t = vec_size * 8; t < n; ++t) f = __fadd_rn(f, x[t]);
+#pragma unroll
+  for (int ll = 0; ll < 8; ++ll) f = __fadd_rn(f, __shfl_sync(0xffffffffu, a0, ll));
+  return f;
+}
+
 // One CTA per utterance, one thread per channel.
 //   phase 1 (thread 0): alpha' = [alpha, 0], alpha'[len] += tail; token_num = floor(sum alpha'); fp64 prefix
 //                       sums -> fires / remainders / fire ordinals into shared memory.
@@ -74,6 +118,11 @@ cif_fire_kernel(const float* __restrict__ enc, const float* __restrict__ alpha_r
     s_alpha[t] = a;
   }
   __syncthreads();
+  __shared__ float s_total;
+  if ((threadIdx.x >> 5) == 1) {                    // warp 1, beside thread 0's scan: token_num = floor(alphas.sum(-1)) in torch's fp32 order
+    const float tot = torch_row_sum_f32(s_alpha, T1);
+    if ((threadIdx.x & 31) == 0) s_total = tot;
+  }
   if (threadIdx.x == 0) {
     double ps = 0.0;
     float prev_floor = 0.f;
@@ -90,11 +139,9 @@ cif_fire_kernel(const float* __restrict__ enc, const float* __restrict__ alpha_r
       peaks_out[(int64_t)b * T1 + t] = fires;
       alphas_out[(int64_t)b * T1 + t] = s_alpha[t];
     }
-    // token_num = floor(alphas.sum(-1)) in fp32 (:443-444).  torch's vectorised fp32 sum is reproduced to within
-    // an ulp by rounding the exact (fp64) sum once.
-    token_num[b] = (int32_t)floorf((float)ps);
   }
   __syncthreads();
+  if (threadIdx.x == 0) token_num[b] = (int32_t)floorf(s_total);     // floor(alphas.sum(-1)) (:443-444), torch's own summation order
   const float* hb = enc + (int64_t)b * t_max * d;
   float* ob = acoustic + (int64_t)b * n_cap * d;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -135,13 +182,16 @@ cif_fire_loop_kernel(const float* __restrict__ enc, const float* __restrict__ al
     s_cur[t] = a;
   }
   __syncthreads();
+  __shared__ float s_total;
+  float total_w1 = 0.f;
+  if ((threadIdx.x >> 5) == 1) total_w1 = torch_row_sum_f32(s_cur, T1);   // before thread 0 overwrites s_cur with the per-frame weights
+  __syncthreads();
+  if (threadIdx.x == 32) s_total = total_w1;
   if (threadIdx.x == 0) {
     float integrate = 0.f;
-    double total = 0.0;
     int ord = 0;
     for (int t = 0; t < T1; ++t) {
       const float alpha = s_cur[t];
-      total += (double)alpha;
       const float completion = __fsub_rn(1.0f, integrate);      // :54
       integrate = __fadd_rn(integrate, alpha);                   // :56
       peaks_out[(int64_t)b * T1 + t] = integrate;                // list_fires (:57)
@@ -153,9 +203,9 @@ cif_fire_loop_kernel(const float* __restrict__ enc, const float* __restrict__ al
       s_rem[t] = __fsub_rn(alpha, cur);                          // :64
       s_ord[t] = fire ? ord++ : -1;
     }
-    token_num[b] = (int32_t)floorf((float)total);                // tail_process_fn: floor(alphas.sum(-1)) (:374-375)
   }
   __syncthreads();
+  if (threadIdx.x == 0) token_num[b] = (int32_t)floorf(s_total);  // tail_process_fn: floor(alphas.sum(-1)) (:380-381), torch's summation order
   const float* hb = enc + (int64_t)b * t_max * d;
   float* ob = acoustic + (int64_t)b * n_cap * d;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -178,18 +228,10 @@ __global__ void cif_upsample_scan_kernel(float* __restrict__ alphas2, const int3
                                          float* __restrict__ us_peaks) {
   const int b = blockIdx.x;
   float* a = alphas2 + (int64_t)b * t3;
-  __shared__ double s_part[32];
-  double part = 0.0;
-  for (int t = threadIdx.x; t < t3; t += blockDim.x) part += (double)a[t];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
-  __syncthreads();
   __shared__ float s_scale;
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
-    s_scale = __fdiv_rn((float)token_num[b], (float)tot);       // (token_num / _token_num): fp32 division of the fp32 sum
+  if (threadIdx.x < 32) {
+    const float tot = torch_row_sum_f32(a, t3);                  // _token_num = alphas2.sum(-1) (:343), torch's fp32 summation order
+    if (threadIdx.x == 0) s_scale = __fdiv_rn((float)token_num[b], tot);       // (token_num / _token_num) :345
   }
   __syncthreads();
   const float scale = s_scale;
@@ -203,6 +245,12 @@ __global__ void cif_upsample_scan_kernel(float* __restrict__ alphas2, const int3
       if (integrate >= thr) integrate = __fsub_rn(integrate, thr);
     }
   }
+}
+
+// op-level entry for the parity tests: out[r] = torch-order fp32 sum of row r
+__global__ void row_sum_f32_kernel(const float* __restrict__ x, int64_t ld, int n, float* __restrict__ out) {
+  const float s = torch_row_sum_f32(x + (int64_t)blockIdx.x * ld, n);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
 int cif_im2col_launch(const float* enc, int64_t rows, int t_max, int d, float* xc, cudaStream_t st) {
@@ -251,3 +299,11 @@ int cif_upsample_scan_launch(float* alphas2, const int32_t* token_num, int batch
 }
 
 }  // namespace fa
+
+extern "C" int fa_row_sum_f32(const float* x, int64_t ld, int32_t rows, int32_t n, float* out, fa_stream_t stream) {
+  if (!x || !out || rows < 0 || n < 0 || n >= (8 << 19)) return FA_ERR_ARG;
+  if (rows == 0) return FA_OK;
+  fa::row_sum_f32_kernel<<<rows, 32, 0, (cudaStream_t)stream>>>(x, ld, n, out);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}

@@ -71,6 +71,33 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize and the SM count are PER-DEVICE: a process that drives two GPUs (two handles of
+// the offline API, a server with one worker thread per device) must set / query them once per (kernel instantiation, device).
+struct PerDeviceOnce { std::atomic<uint32_t> mask{0}; };
+template <typename K>
+inline int ensure_dyn_smem(K kern, size_t bytes, PerDeviceOnce& once) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return FA_ERR_CUDA;
+  const uint32_t bit = 1u << (dev & 31);
+  if (!(once.mask.load(std::memory_order_acquire) & bit)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return FA_ERR_CUDA;
+    once.mask.fetch_or(bit, std::memory_order_release);
+  }
+  return FA_OK;
+}
+// SM count of the current device (cached per device)
+inline int sm_count() {
+  static std::atomic<int> cache[32];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int n = cache[dev & 31].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev & 31].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Bump allocator over the caller's workspace.

@@ -190,11 +190,8 @@ extern "C" int fa_fbank_lfr_cmvn_strided(const float* wav, const int32_t* wav_le
       feats_batch_stride_rows < t_max)
     return FA_ERR_ARG;
   const size_t smem = sizeof(fa::FbankSmem);
-  static bool attr_done = false;
-  if (!attr_done) {
-    FA_CUDA_OK(cudaFuncSetAttribute(fa::fbank_lfr_cmvn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  static fa::PerDeviceOnce once;
+  FA_RETURN_IF_ERR(fa::ensure_dyn_smem(fa::fbank_lfr_cmvn_kernel, smem, once));
   dim3 grid((t_max + fa::kRows - 1) / fa::kRows, batch);
   fa::fbank_lfr_cmvn_kernel<<<grid, fa::kWarps * 32, smem, (cudaStream_t)stream>>>(
       wav, wav_lens, wav_stride, cmvn, mel_banks, window, feats, feat_lens, t_max, feats_batch_stride_rows);

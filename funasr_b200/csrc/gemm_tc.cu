@@ -21,6 +21,7 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <unordered_map>
 
 namespace fa {
 
@@ -649,8 +650,27 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2D bf16 tensor [rows, cols] (row pitch ld elements), box {64 cols, box_rows}, 128B swizzle
+// 2D bf16 tensor [rows, cols] (row pitch ld elements), box {64 cols, box_rows}, 128B swizzle.
+// A forward pass encodes ~570 maps over a few dozen distinct (pointer, shape) pairs — the workspace slices and the weight
+// planes are the same every layer and every step — so the encoded descriptors are kept in a small per-thread cache
+// (no locking; a descriptor depends only on the key).
+struct MapKey {
+  const void* base; uint64_t rows, cols, ld; uint32_t box;
+  bool operator==(const MapKey& o) const { return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.base * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols * 31 + k.ld * 131 + k.box + (h << 6) + (h >> 2));
+    return (size_t)h;
+  }
+};
 int make_bf16_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{base, rows, cols, ld, box_rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *m = it->second; return FA_OK; }
   PFN_encodeTiled enc = get_encode();
   if (!enc) return FA_ERR_CUDA;
   cuuint64_t dims[2] = {cols, rows};
@@ -660,7 +680,10 @@ int make_bf16_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? FA_OK : FA_ERR_CUDA;
+  if (r != CUDA_SUCCESS) return FA_ERR_CUDA;
+  if (cache.size() >= 4096) cache.clear();
+  cache.emplace(key, *m);
+  return FA_OK;
 }
 
 static int planes_for_mode(int mode) { return mode == FA_GEMM_BF16X1 ? 1 : (mode == FA_GEMM_BF16X3 ? 2 : 3); }
@@ -674,17 +697,9 @@ size_t gemm_tc_scratch_bytes(int64_t max_rows, int max_k, int mode) {
 template <int BN, int STAGES, int APL, int WPL, int EPI>
 static int launch_cfg_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (APL * TC_TILE_BYTES_A + WPL * BN * TC_BK * 2) + 1024 + 256 + EPI_WARPS * EPI_WARP_FLOATS * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, APL, WPL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    FA_CUDA_OK(cudaGetDevice(&dev));
-    FA_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static PerDeviceOnce once;
+  FA_RETURN_IF_ERR(ensure_dyn_smem(gemm_tc_kernel<BN, STAGES, APL, WPL, EPI>, smem, once));
+  const int n_sm = sm_count();
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < n_sm ? tiles : n_sm;
   FA_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, STAGES, APL, WPL, EPI>, dim3(grid), dim3(384), smem, st, 1, ma, mw, p));
@@ -706,17 +721,9 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcPara
 template <int STAGES, int PL, int EPI>
 static int launch_cfg2_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (2 * PL * 128 * TC_BK * 2) + 1024 + 256 + EPI_WARPS * EPI_WARP_FLOATS * 4;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FA_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, PL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    FA_CUDA_OK(cudaGetDevice(&dev));
-    FA_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static PerDeviceOnce once;
+  FA_RETURN_IF_ERR(ensure_dyn_smem(gemm_tc2_kernel<STAGES, PL, EPI>, smem, once));
+  const int n_sm = sm_count();
   const int tiles = p.tiles_m * p.tiles_n;
   const int pairs = tiles < n_sm / 2 ? tiles : n_sm / 2;
   FA_CUDA_OK(launch_pdl(gemm_tc2_kernel<STAGES, PL, EPI>, dim3(2 * pairs), dim3(384), smem, st, 1, ma, mw, p));   // cluster dims are compile-time (__cluster_dims__)

@@ -33,11 +33,12 @@ struct AttnSinks {
 // tcgen05 attention (attention_tc.cu); ctx fp32 and/or bf16 planes [npl][B*tq][ldp]
 int attention_tc_planes_launch(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfloat16* vt, const int32_t* key_lens,
                                int batch, int heads, int tq, int tk, float* ctx, int64_t ldc, __nv_bfloat16* ctx_planes,
-                               int64_t ldp, int out_nplanes, int mode, cudaStream_t st);
+                               int64_t ldp, int out_nplanes, int mode, cudaStream_t st, int kv_shared = 0);
 size_t attention_tc_scratch_bytes(int batch, int heads, int tq, int tk, int mode);
 int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                         const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
-                        __nv_bfloat16* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st);
+                        __nv_bfloat16* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st,
+                        int kv_shared = 0);   // kv_shared: k / v hold ONE batch entry that every utterance attends over
 int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
                           const float* r2, int64_t ld2, float* y, int64_t ldy, __nv_bfloat16* out_planes, int64_t ldo,
                           int mode, cudaStream_t st, const AttnSinks* att = nullptr);
@@ -45,7 +46,7 @@ int split_rows_launch(const float* x, int64_t ldx, int64_t rows, int cols, int c
                       cudaStream_t st);
 int attention_f32_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                          const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
-                         cudaStream_t st);
+                         cudaStream_t st, int kv_shared = 0);
 int fsmn_launch(const float* v, int64_t ldv, const int32_t* lens, int batch, int t_max, int channels, const float* w,
                 int ksize, const float* res, int64_t ldr, float* out, int64_t ldo, cudaStream_t st);
 int cif_im2col_launch(const float* enc, int64_t rows, int t_max, int d, float* xc, cudaStream_t st);

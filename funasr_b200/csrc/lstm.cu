@@ -167,11 +167,8 @@ static int blstm_launch_t(const float* xproj, const float* w_hh_f, const float* 
   if (!xproj || !w_hh_f || !w_hh_b || !out || !counters) return FA_ERR_ARG;
   if (hidden != LS_H || batch > 4 * LS_BT) return FA_ERR_UNSUPPORTED;
   const size_t smem = (size_t)(LS_ROWS * LS_WLD + LS_BT * LS_HLD) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    FA_CUDA_OK(cudaFuncSetAttribute(blstm_kernel<SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  static PerDeviceOnce once;
+  FA_RETURN_IF_ERR(ensure_dyn_smem(blstm_kernel<SKIP>, smem, once));
   FA_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), st));
   void* args[] = {(void*)&xproj, (void*)&w_hh_f, (void*)&w_hh_b, (void*)&batch, (void*)&T, (void*)&out, (void*)&counters};
   FA_CUDA_OK(cudaLaunchCooperativeKernel((const void*)blstm_kernel<SKIP>, dim3(2 * LS_NC), dim3(128), args, smem, st));
@@ -369,11 +366,8 @@ int blstm_tc_launch(const float* xproj, const float* w_hh_f, const float* w_hh_b
   const size_t need = 256 + (size_t)2 * 2 * 2 * batch_pad * LS_H * sizeof(__nv_bfloat16);
   if (scratch_bytes < need) return FA_ERR_WORKSPACE;
   const size_t smem = (size_t)2 * LS_ROWS * LT_PITCH + (size_t)2 * LS_BT * LT_PITCH;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FA_CUDA_OK(cudaFuncSetAttribute(blstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  static PerDeviceOnce once;
+  FA_RETURN_IF_ERR(ensure_dyn_smem(blstm_tc_kernel, smem, once));
   unsigned int* counters = static_cast<unsigned int*>(scratch);
   __nv_bfloat16* hx = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(scratch) + 256);
   FA_CUDA_OK(cudaMemsetAsync(scratch, 0, need, st));

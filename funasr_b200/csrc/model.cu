@@ -5,6 +5,9 @@
 #include "kernels.h"
 #include <string.h>
 #include <math.h>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace fa {
 
@@ -14,28 +17,35 @@ std::atomic<unsigned long long> g_launch_count{0};
 // bound with a tiny footprint, so it runs concurrently with the latency-bound attention kernel and joins before the
 // out-projection.  One lazily created (stream, fork event, join event) per device; FA_OVERLAP_FSMN=0 keeps everything on the
 // caller's stream.
-struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
-static SideStream* side_stream() {
-  static SideStream per_dev[16];
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("FA_OVERLAP_FSMN"); enabled = (e && e[0] == '0') ? 0 : 1; }
+// The (side stream, fork event, join event) triple belongs to ONE caller stream on one device: two host threads that run
+// encoders on different streams (two fa_offline handles, one worker thread per model) get different triples, so one thread's
+// fork record can never be consumed by the other's side stream.  Calls that share a caller stream are ordered by that stream.
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream* side_stream(cudaStream_t caller) {
+  static const bool enabled = [] { const char* e = getenv("FA_OVERLAP_FSMN"); return !(e && e[0] == '0'); }();
   if (!enabled) return nullptr;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  SideStream& s = per_dev[dev];
-  if (!s.ok) {
-    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    s.ok = true;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SideStream*> pool;
+  std::lock_guard<std::mutex> lock(mu);
+  SideStream*& slot = pool[std::make_pair(dev, caller)];
+  if (!slot) {
+    SideStream* s = new SideStream();
+    if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) {
+      delete s;
+      return nullptr;
+    }
+    slot = s;
   }
-  return &s;
+  return slot;
 }
 
 bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FA_PDL"); v = (e && e[0] == '1') ? 1 : 0; }   // opt-in: measured neutral (46.0 vs 46.1 ms)
-  return v == 1;
+  static const bool v = [] { const char* e = getenv("FA_PDL"); return e && e[0] == '1'; }();   // opt-in: measured neutral (46.0 vs 46.1 ms)
+  return v;
 }
 
 static int linear(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
@@ -120,7 +130,8 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
   for (int l = 0; l < enc->n_layers; ++l) {
     const FaEncLayer& L = enc->layers[l];
     const int in = L.norm1.n;
-    if (L.qkv.in_f != in || L.qkv.out_f != 3 * D || L.w1.in_f != D || L.w2.out_f != D) return FA_ERR_ARG;
+    if (L.qkv.in_f != in || L.qkv.out_f != 3 * D || L.w1.in_f != D || L.w2.out_f != D || L.w2.in_f != L.w1.out_f) return FA_ERR_ARG;
+    if (L.w1.out_f > 2048) return FA_ERR_UNSUPPORTED;      // the workspace plan sizes the FFN hidden slice for linear_units <= 2048
     // x = x*sqrt(D) + PE is folded into the first LayerNorm (encoder.py:409,428)
     // tensor-core path: LayerNorm writes the bf16 planes the QKV GEMM consumes (no fp32 round trip, no split pass)
     if (l > 0 && in != D) return FA_ERR_UNSUPPORTED;
@@ -137,7 +148,7 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
     } else {
       FA_RETURN_IF_ERR(linear(u, in, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, gemm_mode, &scratch, st));
     }
-    SideStream* side = tc ? side_stream() : nullptr;
+    SideStream* side = tc ? side_stream(st) : nullptr;
     if (side) {                                     // FSMN memory branch runs beside the attention kernel (both need only QKV)
       FA_CUDA_OK(cudaEventRecord(side->fork, st));
       FA_CUDA_OK(cudaStreamWaitEvent(side->st, side->fork, 0));
@@ -232,7 +243,16 @@ static size_t dec_scratch_bytes(int batch, int t_max, int n_max, int mode) {
   const int64_t Mq = (int64_t)batch * n_max, Mk = (int64_t)batch * t_max;
   return max_sz(gemm_tc_scratch_bytes(Mq > Mk ? Mq : Mk, 2048, mode), attention_tc_scratch_bytes(batch, 4, n_max, t_max, mode));
 }
-static size_t dec_plan(int batch, int t_max, int n_max, int vocab, int mode, size_t dec_scratch) {
+// hotword region of the contextual bias decoder: k|v rows of the (shared) hotword memory + GEMM / attention scratch
+static size_t hw_region_bytes(int batch, int n_max, int nh, int mode) {
+  if (nh <= 0) return 0;
+  const int64_t Mq = (int64_t)batch * n_max;
+  ArenaSizer s;
+  s.take((size_t)nh * 1024 * 4);
+  s.take(max_sz(gemm_tc_scratch_bytes(Mq > nh ? Mq : nh, 1024, mode), attention_tc_scratch_bytes(batch, 4, n_max, nh, mode)));
+  return s.off + 256;
+}
+static size_t dec_plan(int batch, int t_max, int n_max, int vocab, int mode, size_t dec_scratch, int n_hotwords) {
   const int64_t Mq = (int64_t)batch * n_max, Mk = (int64_t)batch * t_max;
   ArenaSizer s;
   s.take(Mq * 512ull * 4);   // ya
@@ -245,7 +265,7 @@ static size_t dec_plan(int batch, int t_max, int n_max, int vocab, int mode, siz
   s.take(Mk * 1024ull * 4);  // kv
   s.take(Mq * (size_t)vocab * 4);  // logits (used when the caller passes none)
   s.take(Mq * 1024ull * 4);        // [x_src_attn ; cx] of the contextual decoder
-  s.take(Mk * 1024ull * 4);        // hotword k|v replicated per utterance (n_hotwords <= t_max)
+  s.take(hw_region_bytes(batch, n_max, n_hotwords, mode));
   if (mode != FA_GEMM_F32_SIMT) {
     s.take(3ull * Mq * 512 * 2);   // ctx planes
     s.take(3ull * Mk * 512 * 2);   // enc planes (split once, reused by the 16 kv GEMMs)
@@ -261,12 +281,18 @@ static size_t dec_plan(int batch, int t_max, int n_max, int vocab, int mode, siz
 
 extern "C" size_t fa_paraformer_decoder_workspace_bytes(int32_t batch, int32_t t_max, int32_t n_max, int32_t vocab,
                                                         int32_t gemm_mode) {
-  return dec_plan(batch, t_max, n_max, vocab, gemm_mode, dec_scratch_bytes(batch, t_max, n_max, gemm_mode));
+  return dec_plan(batch, t_max, n_max, vocab, gemm_mode, dec_scratch_bytes(batch, t_max, n_max, gemm_mode), t_max);
+}
+extern "C" size_t fa_paraformer_decoder_workspace_bytes_hw(int32_t batch, int32_t t_max, int32_t n_max, int32_t vocab,
+                                                           int32_t gemm_mode, int32_t n_hotwords) {
+  return dec_plan(batch, t_max, n_max, vocab, gemm_mode, dec_scratch_bytes(batch, t_max, n_max, gemm_mode), n_hotwords);
 }
 
 static int dec_ffn(const FaDecLayer& L, const float* y, int64_t Mq, float* t1, float* hq, float* f, int mode,
                    Arena* scratch, cudaStream_t st, __nv_bfloat16* t1_planes, __nv_bfloat16* hq_planes) {
   // f = w_2( LN_2048( relu( w_1( LN1(y) ) ) ) )   decoder.py:97-100, sanm/positionwise_feed_forward.py:33
+  if (L.ffn_w1.in_f != 512 || L.ffn_w2.out_f != 512 || L.ffn_w2.in_f != L.ffn_w1.out_f || L.ffn_norm.n != L.ffn_w1.out_f) return FA_ERR_ARG;
+  if (L.ffn_w1.out_f > 2048) return FA_ERR_UNSUPPORTED;    // dec_plan sizes hq / hq_planes for linear_units <= 2048
   if (mode != FA_GEMM_F32_SIMT) {
     const int npl = npl_for(mode);
     if (L.ffn_w1.in_pad != 512 || L.ffn_w2.in_pad != L.ffn_w1.out_f) return FA_ERR_UNSUPPORTED;
@@ -305,7 +331,8 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
   float* kv = a.take<float>(Mk * 1024ull);
   float* lg = a.take<float>(Mq * (size_t)V);
   float* cat = a.take<float>(Mq * 1024ull);
-  float* kvb_rep = a.take<float>(Mk * 1024ull);
+  const size_t hwb = hw_region_bytes(batch, n_max, dec->has_bias ? dec->n_hotwords : 0, gemm_mode);
+  char* hw_region = a.take<char>(hwb);
   const bool tc = gemm_mode != FA_GEMM_F32_SIMT;
   const int npl = npl_for(gemm_mode);
   __nv_bfloat16* ctx_planes = tc ? a.take<__nv_bfloat16>(3ull * Mq * 512) : nullptr;
@@ -376,19 +403,26 @@ extern "C" int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* 
   if (dec->has_bias) {
     // ContextualParaformerDecoder.forward decoder.py:325-340
     const int nh = dec->n_hotwords;
-    if (!dec->hw_embed || !dec->hw_lens || nh <= 0 || nh > t_max || dec->clas_scale != 1.0f) return FA_ERR_UNSUPPORTED;
+    if (!dec->hw_embed || !dec->hw_lens || nh <= 0 || dec->clas_scale != 1.0f) return FA_ERR_UNSUPPORTED;
     float* x_self = nullptr;
     FA_RETURN_IF_ERR(attention_layer(dec->bias_last, y, &x_self, cat, 2 * D, nullptr));      // cat[:, :512] = x_src_attn
     // bias decoder: cross attention of LN3(x_self_attn) over the hotword memory (identical for every utterance)
     FA_RETURN_IF_ERR(layernorm_launch(x_self, Mq, dec->bias_norm3, t1, nullptr, 1.f, 1, st));
     FA_RETURN_IF_ERR(linear(t1, D, Mq, dec->bias_q, 0, nullptr, 0, nullptr, 0, qd, D, gemm_mode, &scratch, st));
-    FA_RETURN_IF_ERR(linear(dec->hw_embed, D, nh, dec->bias_kv, 0, nullptr, 0, nullptr, 0, kv, 2 * D, gemm_mode, &scratch, st));
-    FA_RETURN_IF_ERR(fa_broadcast_rows(kv, 1, nh * 2 * D, kvb_rep, 1, batch, stream));
+    // the hotword k | v rows [nh, 1024] are the same for every utterance: one copy, attended with kv_shared (no per-utterance
+    // replication, so the hotword count is independent of t_max)
+    Arena a2(hw_region, hwb);
+    float* kvh = a2.take<float>((size_t)nh * 1024);
+    const size_t sb2 = max_sz(gemm_tc_scratch_bytes(Mq > nh ? Mq : nh, 1024, gemm_mode), attention_tc_scratch_bytes(batch, 4, n_max, nh, gemm_mode));
+    char* sp2 = a2.take<char>(sb2);
+    if (!a2.ok()) return FA_ERR_WORKSPACE;
+    Arena scratch2(sp2, sb2);
+    FA_RETURN_IF_ERR(linear(dec->hw_embed, D, nh, dec->bias_kv, 0, nullptr, 0, nullptr, 0, kvh, 2 * D, gemm_mode, &scratch2, st));
     if (!tc) {
-      FA_RETURN_IF_ERR(attention_f32_launch(qd, D, kvb_rep, 2 * D, kvb_rep + D, 2 * D, dec->hw_lens, batch, dec->heads, n_max, nh, ctx, D, st));
+      FA_RETURN_IF_ERR(attention_f32_launch(qd, D, kvh, 2 * D, kvh + D, 2 * D, dec->hw_lens, batch, dec->heads, n_max, nh, ctx, D, st, 1));
     } else {
-      FA_RETURN_IF_ERR(attention_tc_launch(qd, D, kvb_rep, 2 * D, kvb_rep + D, 2 * D, dec->hw_lens, batch, dec->heads, n_max, nh, ctx, D,
-                                           nullptr, 0, 0, gemm_mode, &scratch, st));
+      FA_RETURN_IF_ERR(attention_tc_launch(qd, D, kvh, 2 * D, kvh + D, 2 * D, dec->hw_lens, batch, dec->heads, n_max, nh, ctx, D,
+                                           nullptr, 0, 0, gemm_mode, &scratch2, st, 1));
     }
     FA_RETURN_IF_ERR(linear(ctx, D, Mq, dec->bias_out, 0, nullptr, 0, nullptr, 0, cat + D, 2 * D, gemm_mode, &scratch, st));   // cat[:, 512:] = cx
     float* y2 = (x_self == ya) ? yb : ya;
@@ -458,6 +492,13 @@ extern "C" int fa_linear_planes(const void* a_planes, int64_t rows, const FaLine
   if (!a_planes || !lin || !y || gemm_mode == FA_GEMM_F32_SIMT) return FA_ERR_ARG;
   return gemm_tc_planes_launch(reinterpret_cast<const __nv_bfloat16*>(a_planes), rows, *lin, relu, res1, ld_res1, res2, ld_res2, y, ldy,
                                nullptr, 0, gemm_mode, (cudaStream_t)stream);
+}
+
+extern "C" int fa_linear_planes_to_planes(const void* a_planes, int64_t rows, const FaLinear* lin, int32_t relu, void* out_planes,
+                                          int64_t ld_out, int32_t gemm_mode, fa_stream_t stream) {
+  if (!a_planes || !lin || !out_planes || gemm_mode == FA_GEMM_F32_SIMT) return FA_ERR_ARG;
+  return gemm_tc_planes_launch(reinterpret_cast<const __nv_bfloat16*>(a_planes), rows, *lin, relu, nullptr, 0, nullptr, 0, nullptr, 0,
+                               reinterpret_cast<__nv_bfloat16*>(out_planes), ld_out, gemm_mode, (cudaStream_t)stream);
 }
 
 extern "C" const char* fa_version(void) { return "funasr_b200 0.1.0 (sm_100a)"; }

@@ -151,6 +151,12 @@ bool build(Model& m) {
   m.enc_layers = (int)c[0]; m.dec_layers = (int)c[1]; m.d_model = (int)c[2]; m.heads = (int)c[3]; m.kernel = (int)c[4];
   m.vocab = (int)c[5]; m.feat_dim = (int)c[6]; m.ln_eps = c[7]; m.cif_threshold = c[8]; m.tail_threshold = c[9];
   if (m.enc_layers < 1 || m.dec_layers < 1 || m.d_model != 512 || m.heads * 128 != m.d_model) { set_err("unsupported config"); return false; }
+  // the FSMN tap count is read from each stack's own weight [512, 1, K]: encoder and decoder kernel_size are independent
+  // constructor arguments in the reference (sanm/encoder.py:188, paraformer/decoder.py:234 — decoder default 21)
+  auto fsmn_taps = [&](const char* key) -> int {
+    const Tensor* t = b.get(key);
+    return (t && t->shape.size() == 3) ? (int)t->shape[2] : m.kernel;
+  };
   m.mel = b.ptr("frontend.mel_banks"); m.window = b.ptr("frontend.window");
   m.cmvn = m.t.count("frontend.cmvn") ? m.t["frontend.cmvn"].dev : nullptr;
   // encoder (engine.py:_enc_stack; SANMEncoder encoder.py:188-461)
@@ -163,7 +169,7 @@ bool build(Model& m) {
     L.fsmn_w = b.ptr(p + ".self_attn.fsmn_block.weight");
     L.w1 = b.lin(p + ".feed_forward.w_1"); L.w2 = b.lin(p + ".feed_forward.w_2");
   }
-  m.enc.layers = m.enc_l.data(); m.enc.n_layers = m.enc_layers; m.enc.heads = m.heads; m.enc.fsmn_k = m.kernel;
+  m.enc.layers = m.enc_l.data(); m.enc.n_layers = m.enc_layers; m.enc.heads = m.heads; m.enc.fsmn_k = fsmn_taps("encoder.encoders0.0.self_attn.fsmn_block.weight");
   m.enc.after_norm = b.norm("encoder.after_norm"); m.enc.pe_inv_timescales = b.ptr("encoder.pe_inv_timescales");
   // predictor (CifPredictorV2 cif_predictor.py:209-314); conv weight already repacked to [512, 3*512] by pack.py
   m.pred.conv = b.lin("predictor.cif_conv1d", true, "predictor.cif_conv1d.gemm_weight");
@@ -181,7 +187,7 @@ bool build(Model& m) {
   };
   m.dec_l.resize(m.dec_layers);
   for (int i = 0; i < m.dec_layers; ++i) dec_layer(m.dec_l[i], "decoder.decoders." + std::to_string(i), true);
-  m.dec.layers = m.dec_l.data(); m.dec.n_layers = m.dec_layers; m.dec.heads = m.heads; m.dec.fsmn_k = m.kernel; m.dec.vocab = m.vocab;
+  m.dec.layers = m.dec_l.data(); m.dec.n_layers = m.dec_layers; m.dec.heads = m.heads; m.dec.fsmn_k = fsmn_taps("decoder.decoders.0.self_attn.fsmn_block.weight"); m.dec.vocab = m.vocab;
   dec_layer(m.dec.last, "decoder.decoders3.0", false);
   m.dec.after_norm = b.norm("decoder.after_norm"); m.dec.output = b.lin("decoder.output_layer");
   m.dec.has_bias = 0;

@@ -109,6 +109,7 @@ class _EngineBase:
             L.fsmn_w = self._g(p + ".self_attn.fsmn_block.weight").data_ptr()     # [512,1,11] contiguous == [512,11]
             L.w1, L.w2 = self._lin(p + ".feed_forward.w_1"), self._lin(p + ".feed_forward.w_2")
         pe = self._dev(sinusoid_inv_timescales(pe_depth)) if pe_depth else None
+        fsmn_k = int(self._state[layer_prefixes[0] + ".self_attn.fsmn_block.weight"].shape[-1])    # taps come from the weights
         enc = _abi.FaEncoder(layers, len(layer_prefixes), heads, fsmn_k, 0, self._norm(after_norm_prefix), _ptr(pe))
         self._keep_structs = getattr(self, "_keep_structs", []) + [layers]
         return enc
@@ -122,7 +123,16 @@ class _EngineBase:
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = None
             self._ws = torch.empty((int(nbytes * 1.1) + 4096,), dtype=torch.uint8, device=self.device)
+            self._invalidate_graphs()           # every captured launch baked the old workspace address in
         return self._ws
+
+    def _invalidate_graphs(self):
+        """Captured CUDA graphs hold raw device addresses: whenever an engine-owned buffer or the workspace is replaced, every
+        graph is dropped (a stale graph would write into freed memory)."""
+        self.__dict__["_buf_gen"] = self.__dict__.get("_buf_gen", 0) + 1
+        g = self.__dict__.get("_dec_graphs")
+        if g:
+            g.clear()
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -135,6 +145,7 @@ class _EngineBase:
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
             t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
             bufs[name] = t
+            self._invalidate_graphs()
         return t
 
     def _encode(self, enc_struct, x: torch.Tensor, lens: torch.Tensor, d_model: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -158,7 +169,12 @@ class ParaformerEngine(_EngineBase):
         self.contextual = contextual
         self.bicif = bicif
         g, lin, norm = self._g, self._lin, self._norm
-        D, K = cfg.d_model, cfg.kernel
+        D = cfg.d_model
+        # FSMN tap counts come from each stack's own weights [512, 1, K]: encoder and decoder kernel_size are independent
+        # constructor arguments (decoder default 21, paraformer/decoder.py:234)
+        K = int(state[prefix_enc + "encoders0.0.self_attn.fsmn_block.weight"].shape[-1])
+        first_dec = prefix_dec + ("decoders.0" if (cfg.dec_layers > 1 or not contextual) else "last_decoder")
+        Kd = int(state[first_dec + ".self_attn.fsmn_block.weight"].shape[-1])
         # ---- encoder
         names = [prefix_enc + ("encoders0.0" if i == 0 else "encoders.%d" % (i - 1)) for i in range(cfg.enc_layers)]
         self.enc = self._enc_stack(names, prefix_enc + "after_norm", cfg.heads, K, cfg.feat_dim)
@@ -206,7 +222,7 @@ class ParaformerEngine(_EngineBase):
             dec_layer(self.dec_layers[i], prefix_dec + "decoders.%d" % i)
         self.dec = _abi.FaDecoder()
         self.dec.layers = self.dec_layers
-        self.dec.n_layers, self.dec.heads, self.dec.fsmn_k, self.dec.vocab = n_plain, cfg.heads, K, cfg.vocab
+        self.dec.n_layers, self.dec.heads, self.dec.fsmn_k, self.dec.vocab = n_plain, cfg.heads, Kd, cfg.vocab
         self.dec.has_bias = 0
         if contextual:   # ContextualParaformerDecoder (contextual_paraformer/decoder.py:133-352)
             dec_layer(self.dec.bias_last, prefix_dec + "last_decoder")
@@ -248,8 +264,9 @@ class ParaformerEngine(_EngineBase):
     def upsample_timestamp(self, enc: torch.Tensor, lens: torch.Tensor, token_num: torch.Tensor):
         """CifPredictorV3.get_upsample_timestamp (bicif_paraformer/cif_predictor.py:300-352): enc [B,T,512], lens [B] i32,
         token_num [B] i32 (rounded) -> (us_alphas [B,3T], us_peaks [B,3T]).  ConvTranspose1d upsampling = one GEMM of this library,
-        the BLSTM is cuDNN through torch.nn.LSTM (library call, TF32 off), the alpha head / rescale / fire scan is
-        fa_cif_upsample_alphas."""
+        the BLSTM = its input projections as one tcgen05 GEMM + this library's persistent weight-stationary recurrence
+        (fa_blstm_forward_tc: warp-level mma.sync bf16x3, not tcgen05 — the per-step product is only 64x32x512; or the exact fp32
+        fa_blstm_forward with FUNASR_B200_LSTM=simt), the alpha head / rescale / fire scan is fa_cif_upsample_alphas."""
         if not self.bicif:
             raise _abi.FunasrB200Error("engine was not built with bicif=True")
         B, T, D = enc.shape
@@ -258,8 +275,8 @@ class ParaformerEngine(_EngineBase):
         ws = self._workspace(max(8 * B * T * U * D * 4, 1 << 20))
         _abi.check(self.lib.fa_linear(enc.data_ptr(), D, B * T, C.byref(self.up_lin), 0, None, 0, None, 0, up.data_ptr(), U * D, self.mode,
                                       ws.data_ptr(), ws.numel(), self._stream()), "fa_linear(upsample_cnn)")
-        lstm_impl = os.environ.get("FUNASR_B200_LSTM", "tc")     # tc (default) | simt (exact fp32 FMAs) | cudnn (torch.nn.LSTM)
-        if lstm_impl == "cudnn" or B > 256:
+        lstm_impl = os.environ.get("FUNASR_B200_LSTM", "tc")     # tc (default) | simt (exact fp32 FMAs) | cudnn (torch.nn.LSTM, A/B only)
+        if lstm_impl == "cudnn":
             with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 feat, _ = self.blstm(up)
             feat = feat.contiguous()
@@ -268,16 +285,22 @@ class ParaformerEngine(_EngineBase):
             _abi.check(self.lib.fa_linear(up.data_ptr(), D, B * T * U, C.byref(self.lstm_ih), 0, None, 0, None, 0, xproj.data_ptr(), 8 * D,
                                           self.mode, ws.data_ptr(), ws.numel(), self._stream()), "fa_linear(blstm input projections)")
             feat = torch.empty((B, T * U, 2 * D), dtype=torch.float32, device=self.device)
-            if lstm_impl == "simt":
-                _abi.check(self.lib.fa_blstm_forward(xproj.data_ptr(), self.lstm_hh_f.data_ptr(), self.lstm_hh_b.data_ptr(), B, T * U, D,
-                                                     feat.data_ptr(), self._lstm_sync.data_ptr(), self._stream()), "fa_blstm_forward")
-            else:
-                nb = int(self.lib.fa_blstm_tc_scratch_bytes(B))
-                if getattr(self, "_lstm_scratch", None) is None or self._lstm_scratch.numel() < nb:
-                    self._lstm_scratch = torch.empty(nb, dtype=torch.uint8, device=self.device)
-                _abi.check(self.lib.fa_blstm_forward_tc(xproj.data_ptr(), self.lstm_hh_f.data_ptr(), self.lstm_hh_b.data_ptr(), B, T * U, D,
-                                                        feat.data_ptr(), self._lstm_scratch.data_ptr(), self._lstm_scratch.numel(),
-                                                        self._stream()), "fa_blstm_forward_tc")
+            # the recurrence kernel holds at most 256 sequences per launch: larger batches run as consecutive launches (sequences
+            # are independent) — never a library fallback
+            for b0 in range(0, B, 256):
+                bn = min(256, B - b0)
+                xp = xproj.data_ptr() + b0 * T * U * 8 * D * 4
+                fp = feat.data_ptr() + b0 * T * U * 2 * D * 4
+                if lstm_impl == "simt":
+                    _abi.check(self.lib.fa_blstm_forward(xp, self.lstm_hh_f.data_ptr(), self.lstm_hh_b.data_ptr(), bn, T * U, D,
+                                                         fp, self._lstm_sync.data_ptr(), self._stream()), "fa_blstm_forward")
+                else:
+                    nb = int(self.lib.fa_blstm_tc_scratch_bytes(bn))
+                    if getattr(self, "_lstm_scratch", None) is None or self._lstm_scratch.numel() < nb:
+                        self._lstm_scratch = torch.empty(nb, dtype=torch.uint8, device=self.device)
+                    _abi.check(self.lib.fa_blstm_forward_tc(xp, self.lstm_hh_f.data_ptr(), self.lstm_hh_b.data_ptr(), bn, T * U, D,
+                                                            fp, self._lstm_scratch.data_ptr(), self._lstm_scratch.numel(),
+                                                            self._stream()), "fa_blstm_forward_tc")
         us_alphas = torch.empty((B, T * U), dtype=torch.float32, device=self.device)
         us_peaks = torch.empty_like(us_alphas)
         lens_up = (lens.to(torch.int32) * U).contiguous()
@@ -311,7 +334,8 @@ class ParaformerEngine(_EngineBase):
             ids = torch.empty((B, n_max), dtype=torch.int32, device=self.device)
             best = torch.empty((B, n_max), dtype=torch.float32, device=self.device)
         logp = torch.empty((B, n_max, self.cfg.vocab), dtype=torch.float32, device=self.device) if want_logp else None
-        ws = self._workspace(self.lib.fa_paraformer_decoder_workspace_bytes(B, T, n_max, self.cfg.vocab, self.mode))
+        ws = self._workspace(self.lib.fa_paraformer_decoder_workspace_bytes_hw(B, T, n_max, self.cfg.vocab, self.mode,
+                                                                               self._hw.shape[0] if self.contextual else 0))
         _abi.check(self.lib.fa_paraformer_decoder_forward(
             C.byref(self.dec), enc.data_ptr(), enc_lens.data_ptr(), B, T, acoustic.data_ptr(), acoustic.shape[1],
             tok_lens.data_ptr(), n_max, ids.data_ptr(), best.data_ptr(), _ptr(logp), 1, self.mode, ws.data_ptr(), ws.numel(),
@@ -329,7 +353,7 @@ class ParaformerEngine(_EngineBase):
                                              out_lens.data_ptr(), self._stream()), "fa_greedy_filter")
         return out, out_lens
 
-    def forward_feats(self, feats: torch.Tensor, lens: torch.Tensor, want_taps: bool = False, sos=1, eos=2, blank=0):
+    def forward_feats(self, feats: torch.Tensor, lens: torch.Tensor, want_taps: bool = False, sos=1, eos=2, blank=0, host_lists: bool = True):
         """feats -> greedy ids.  One host synchronisation (the token counts), like the reference's `.item()`
         (cif_predictor.py:311) — every other reference sync is gone.
 
@@ -358,10 +382,11 @@ class ParaformerEngine(_EngineBase):
         else:
             ids, best, logp = self.decode(enc, lens, acoustic, tok, n_max, want_logp=want_taps)
             fids, flens = self.greedy_filter(ids, tok, sos, eos, blank)
-        fids_h, flens_h = fids.cpu(), flens.cpu()  # D2H of the result
-        out["ids"] = [fids_h[b, : int(flens_h[b])].tolist() for b in range(fids_h.shape[0])]
-        out["ids_padded"], out["ids_lens"] = fids_h, flens_h
         out["ids_dev"], out["ids_lens_dev"] = fids, flens        # device copies (multi-GPU all-gather consumes these)
+        if host_lists:
+            fids_h, flens_h = fids.cpu(), flens.cpu()  # D2H of the result
+            out["ids"] = [fids_h[b, : int(flens_h[b])].tolist() for b in range(fids_h.shape[0])]
+            out["ids_padded"], out["ids_lens"] = fids_h, flens_h
         if want_taps:
             out.update(argmax=ids, best_logp=best, logp=logp)
         return out
@@ -371,8 +396,13 @@ class ParaformerEngine(_EngineBase):
 
     def _decode_filter_fused(self, enc, lens, acoustic, tok, n_max, sos, eos, blank):
         B, T, _ = enc.shape
-        bufs = (self._persist("dec_ids_%d" % n_max, (B, n_max), torch.int32), self._persist("dec_best_%d" % n_max, (B, n_max)),
-                self._persist("dec_fids_%d" % n_max, (B, n_max), torch.int32), self._persist("dec_flens_%d" % n_max, (B,), torch.int32))
+        # four output buffers sized ONCE for the CIF bound (n_max <= T + 1) and viewed as [B, n_max]: their addresses do not depend
+        # on n_max, nothing grows with the number of distinct n_max values, and the graph key below covers every pointer a capture
+        # bakes in (all four buffers, the stage inputs, the workspace) plus the buffer generation
+        cap = B * (T + 1)
+        flat = (self._persist("dec_ids", (cap,), torch.int32), self._persist("dec_best", (cap,)),
+                self._persist("dec_fids", (cap,), torch.int32), self._persist("dec_flens", (B,), torch.int32))
+        bufs = (flat[0][: B * n_max].view(B, n_max), flat[1][: B * n_max].view(B, n_max), flat[2][: B * n_max].view(B, n_max), flat[3])
 
         def run():
             ids, _, _ = self.decode(enc, lens, acoustic, tok, n_max, out=(bufs[0], bufs[1]))
@@ -381,8 +411,11 @@ class ParaformerEngine(_EngineBase):
         if self.contextual or os.environ.get("FUNASR_B200_GRAPHS", "1") == "0":
             run()
             return bufs[2], bufs[3]
+        # size the workspace BEFORE the key is formed: a growth replaces it (and drops every graph)
+        self._workspace(self.lib.fa_paraformer_decoder_workspace_bytes_hw(B, T, n_max, self.cfg.vocab, self.mode, 0))
         key = (B, T, n_max, sos, eos, blank, enc.data_ptr(), lens.data_ptr(), acoustic.data_ptr(), tok.data_ptr(),
-               bufs[0].data_ptr(), bufs[2].data_ptr(), self._ws.data_ptr() if self._ws is not None else 0)
+               bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), self._ws.data_ptr(),
+               self.__dict__.get("_buf_gen", 0))
         graphs = self.__dict__.setdefault("_dec_graphs", {})
         ent = graphs.get(key)
         if ent is None:
@@ -405,7 +438,7 @@ class ParaformerEngine(_EngineBase):
                 run()
             ent["n_launch"] = int(self.lib.fa_launch_count() - l0)    # kernels recorded into the graph (counted once here)
             cur.wait_stream(side)
-            if self._ws is not None and self._ws.data_ptr() != key[-1]:   # the workspace grew during capture: pointers are stale
+            if self.__dict__.get("_buf_gen", 0) != key[-1]:              # a buffer / the workspace was replaced during capture: pointers are stale
                 run()
                 graphs.pop(key, None)
             else:
@@ -441,7 +474,7 @@ class SenseVoiceEngine(_EngineBase):
         return self._queries[key]
 
     def forward_wav(self, wav: torch.Tensor, wav_lens: torch.Tensor, host_lens: Sequence[int], language_id: int = 0,
-                    textnorm_id: int = 15, blank: int = 0, want_taps: bool = False):
+                    textnorm_id: int = 15, blank: int = 0, want_taps: bool = False, host_lists: bool = True):
         """wav [B, Nmax] fp32 on device -> CTC greedy ids.  No host synchronisation before the final D2H."""
         B = wav.shape[0]
         t_feat = max(num_lfr_frames(int(n)) for n in host_lens)
@@ -467,8 +500,10 @@ class SenseVoiceEngine(_EngineBase):
         _abi.check(self.lib.fa_ctc_greedy_forward(C.byref(self.ctc), enc.data_ptr(), lens.data_ptr(), B, T, blank, am.data_ptr(), ids.data_ptr(),
                                                   olens.data_ptr(), _ptr(logp), self.mode, ws.data_ptr(), ws.numel(), self._stream()),
                    "fa_ctc_greedy_forward")
-        ids_h, olens_h = ids.cpu(), olens.cpu()
-        out = {"ids": [ids_h[b, : int(olens_h[b])].tolist() for b in range(B)], "enc_lens": lens}
+        out = {"enc_lens": lens, "ids_dev": ids, "ids_lens_dev": olens}
+        if host_lists:
+            ids_h, olens_h = ids.cpu(), olens.cpu()
+            out["ids"] = [ids_h[b, : int(olens_h[b])].tolist() for b in range(B)]
         if want_taps:
             out.update(enc=enc, logp=logp, argmax=am)
         return out

@@ -332,13 +332,8 @@ class ParaformerB200(nn.Module):
         _, _, logp = eng.decode(encoder_out, encoder_out_lens.to(torch.int32), sematic_embeds.contiguous(), tok, n_max, want_logp=True)
         return logp, ys_pad_lens
 
-    def inference(self, data_in, data_lengths=None, key: list = None, tokenizer=None, frontend=None, **kwargs):
-        """Same contract as Paraformer.inference (model.py:534-697): returns (results, meta_data)."""
-        device = torch.device(kwargs.get("device", "cuda"))
-        if device.type != "cuda":
-            raise _abi.FunasrB200Error("ParaformerB200.inference needs device='cuda' (no CPU fallback)")
-        meta_data = {}
-        eng = self.engine(device)
+    def _features(self, data_in, data_lengths, frontend, device, kwargs, meta_data):
+        """model.py:572-600: load -> pad -> frontend, all on the device: (speech [B,T,560], lens [B] int32)."""
         if isinstance(data_in, torch.Tensor) and kwargs.get("data_type", "sound") == "fbank":
             speech = data_in if data_in.dim() == 3 else data_in[None]
             speech_lengths = data_lengths.reshape(-1) if data_lengths is not None else torch.tensor([speech.shape[1]])
@@ -376,6 +371,29 @@ class ParaformerB200(nn.Module):
             speech, lens = frontend.engine(device)(wav_dev, wl_dev, max(num_lfr_frames(n) for n in wl))
             meta_data["extract_feat"] = f"{time.perf_counter() - t2:0.3f}"
             meta_data["batch_data_time"] = sum(num_lfr_frames(n) for n in wl) * frontend.frame_shift * frontend.lfr_n / 1000
+        return speech, lens
+
+    def infer_ids_device(self, data_in, frontend=None, **kwargs):
+        """The hot path of inference() with the result left ON THE DEVICE: (ids [B, n] int32 padded with -1, lens [B] int32) —
+        what funasr_b200.sharding.ShardedRunner exchanges between GPUs (no per-utterance host lists on the way)."""
+        device = torch.device(kwargs.get("device", "cuda"))
+        if device.type != "cuda":
+            raise _abi.FunasrB200Error("%s needs device='cuda' (no CPU fallback)" % type(self).__name__)
+        speech, lens = self._features(data_in, None, frontend, device, kwargs, {})
+        out = self.engine(device).forward_feats(speech, lens, sos=self.sos, eos=self.eos, blank=self.blank_id, host_lists=False)
+        if "ids_dev" not in out:                                  # no utterance produced a token
+            b = speech.shape[0]
+            return torch.full((b, 1), -1, dtype=torch.int32, device=device), torch.zeros((b,), dtype=torch.int32, device=device)
+        return out["ids_dev"], out["ids_lens_dev"]
+
+    def inference(self, data_in, data_lengths=None, key: list = None, tokenizer=None, frontend=None, **kwargs):
+        """Same contract as Paraformer.inference (model.py:534-697): returns (results, meta_data)."""
+        device = torch.device(kwargs.get("device", "cuda"))
+        if device.type != "cuda":
+            raise _abi.FunasrB200Error("ParaformerB200.inference needs device='cuda' (no CPU fallback)")
+        meta_data = {}
+        eng = self.engine(device)
+        speech, lens = self._features(data_in, data_lengths, frontend, device, kwargs, meta_data)
         out = eng.forward_feats(speech, lens, sos=self.sos, eos=self.eos, blank=self.blank_id)
         if kwargs.get("_keep_taps"):
             self._last_out = out                  # BiCifParaformerB200 reads enc / lens / token counts for its timestamp head
@@ -499,12 +517,30 @@ class SenseVoiceSmallB200(nn.Module):
             self._engine = SenseVoiceEngine(self.state_dict(), self.cfg, dev, gemm_mode=self.gemm_mode, cmvn=cmvn)
         return self._engine
 
+    def infer_ids_device(self, data_in, frontend=None, **kwargs):
+        """CTC greedy ids left on the device: (ids [B, T] int32 padded with -1, lens [B] int32) for ShardedRunner."""
+        out = self._run(data_in, frontend, {}, host_lists=False, **kwargs)
+        return out["ids_dev"], out["ids_lens_dev"]
+
     def inference(self, data_in, data_lengths=None, key: list = ["wav_file_tmp_name"], tokenizer=None, frontend=None, **kwargs):
+        meta_data = {}
+        out = self._run(data_in, frontend, meta_data, **kwargs)
+        b = len(out["ids"])
+        if isinstance(key[0], (list, tuple)):
+            key = key[0]
+        if len(key) < b:
+            key = key * b
+        results = []
+        for i in range(b):
+            ids = out["ids"][i]
+            results.append({"key": key[i], "text": tokenizer.decode(ids)} if tokenizer is not None else {"key": key[i], "token_int": ids})
+        return results, meta_data
+
+    def _run(self, data_in, frontend, meta_data, host_lists=True, **kwargs):
         device = torch.device(kwargs.get("device", "cuda"))
         if not isinstance(frontend, WavFrontendB200):
             raise _abi.FunasrB200Error("SenseVoiceSmallB200 needs frontend='WavFrontendB200'")
         eng = self.engine(device, frontend.cmvn)
-        meta_data = {}
         wavs = _as_wave_list(data_in, fs=frontend.fs, audio_fs=int(kwargs.get("fs", 16000)),
                              **{k: v for k, v in kwargs.items() if k not in ("fs", "audio_fs", "frontend")})
         wl = [int(w.numel()) for w in wavs]
@@ -518,17 +554,8 @@ class SenseVoiceSmallB200(nn.Module):
         meta_data["batch_data_time"] = sum(num_lfr_frames(n) for n in wl) * frontend.frame_shift * frontend.lfr_n / 1000
         language = kwargs.get("language", "auto")
         textnorm = kwargs.get("text_norm", None) or ("withitn" if kwargs.get("use_itn", False) else "woitn")
-        out = eng.forward_wav(wav_dev, wl_dev, wl, self.lid_dict.get(language, 0), self.textnorm_dict[textnorm], self.blank_id)
-        b = len(wavs)
-        if isinstance(key[0], (list, tuple)):
-            key = key[0]
-        if len(key) < b:
-            key = key * b
-        results = []
-        for i in range(b):
-            ids = out["ids"][i]
-            results.append({"key": key[i], "text": tokenizer.decode(ids)} if tokenizer is not None else {"key": key[i], "token_int": ids})
-        return results, meta_data
+        return eng.forward_wav(wav_dev, wl_dev, wl, self.lid_dict.get(language, 0), self.textnorm_dict[textnorm], self.blank_id,
+                               host_lists=host_lists)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -592,6 +619,11 @@ class ContextualParaformerB200(ParaformerB200):
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # cuDNN RNNs default to TF32: keep fp32
             _, (h_n, _) = self.bias_encoder(packed)
         return h_n[0]
+
+    def infer_ids_device(self, data_in, frontend=None, **kwargs):
+        hw = kwargs.pop("hotword_ids", None)    # the reference re-encodes the hotword list on every call too (model.py:350-372)
+        self.engine(kwargs.get("device", "cuda")).set_hotwords(self.encode_hotwords(hw))
+        return super().infer_ids_device(data_in, frontend=frontend, **kwargs)
 
     def inference(self, data_in, data_lengths=None, key: list = None, tokenizer=None, frontend=None, **kwargs):
         hw = kwargs.get("hotword_ids")          # list of token-id lists (+ trailing [sos]); text hotwords need the tokenizer

@@ -184,6 +184,10 @@ int fa_split_rows(const float* x, int64_t ldx, int64_t rows, int32_t cols, int32
                   fa_stream_t stream);
 int fa_linear_planes(const void* a_planes, int64_t rows, const FaLinear* lin, int32_t relu, const float* res1, int64_t ld_res1,
                      const float* res2, int64_t ld_res2, float* y, int64_t ldy, int32_t gemm_mode, fa_stream_t stream);
+/* Same GEMM with the plane-emitting epilogue: out_planes [npl][rows][ld_out] bf16 (hi, lo, ...) of act(A W^T + b) — the launch the
+ * encoder makes for FFN w_1, whose ReLU output feeds w_2 without an fp32 round trip (bench.py times exactly this launch). */
+int fa_linear_planes_to_planes(const void* a_planes, int64_t rows, const FaLinear* lin, int32_t relu, void* out_planes,
+                               int64_t ld_out, int32_t gemm_mode, fa_stream_t stream);
 
 /* FSMN memory block: out = m * (v*m + dwconv_k(v*m)) (+ res); m[t] = t < lens[b]
  * (MultiHeadedAttentionSANM.forward_fsmn attention.py:216-239; decoder variant :583-631). */
@@ -229,6 +233,11 @@ int fa_cif_predictor_forward(const FaPredictor* pred, const float* enc, const in
                              float* peaks, int32_t gemm_mode, void* workspace, size_t ws_bytes,
                              fa_stream_t stream);
 
+/* out[r] = x[r, :n].sum() in fp32 with the summation order of torch's CPU kernel (ATen SumKernel.cpp: 8 SIMD lanes x 4 ILP
+ * accumulators, 4-level cascade): the CIF predictor's integer token count is floor(alphas.sum(-1)) (cif_predictor.py:443-444),
+ * so the order decides an integer outcome.  x [rows, ld] fp32 on the device, out [rows]. */
+int fa_row_sum_f32(const float* x, int64_t ld, int32_t rows, int32_t n, float* out, fa_stream_t stream);
+
 /* Timestamp head of CifPredictorV3.get_upsample_timestamp (bicif_paraformer/cif_predictor.py:331-352), after the
  * ConvTranspose1d upsampling (a fa_linear with the [3*512, 512] repacked weight) and the BLSTM:
  *   alphas2 = relu(sigmoid(feat . w + b) * smooth2 - noise2) * mask;  alphas2 *= token_num / sum(alphas2);
@@ -265,6 +274,10 @@ int fa_debug_blstm_variant(int32_t skip_mask, const float* xproj, const float* w
  *   If log_softmax != 0 the logits buffer is converted in place to log_softmax (model.py:345). */
 size_t fa_paraformer_decoder_workspace_bytes(int32_t batch, int32_t t_max, int32_t n_max, int32_t vocab,
                                              int32_t gemm_mode);
+/* Same, for a contextual decoder (FaDecoder.has_bias) with n_hotwords entries in its hotword memory; the plain query above
+ * assumes n_hotwords <= t_max. */
+size_t fa_paraformer_decoder_workspace_bytes_hw(int32_t batch, int32_t t_max, int32_t n_max, int32_t vocab,
+                                                int32_t gemm_mode, int32_t n_hotwords);
 int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* enc, const int32_t* enc_lens, int32_t batch,
                                   int32_t t_max, const float* acoustic, int64_t ld_acoustic_rows,
                                   const int32_t* tok_lens, int32_t n_max, int32_t* argmax_ids, float* argmax_logp,

@@ -543,6 +543,57 @@ def bicif_forward(wavs: List[Tensor], p: Dict[str, Tensor], cmvn: Optional[Tenso
     return out
 
 
+
+# --------------------------------------------------------------------------------------
+# torch's CPU fp32 row sum, restated step by step (ATen/native/cpu/SumKernel.cpp: cascade_sum -> vectorized_inner_sum ->
+# row_sum -> multi_row_sum).  The CIF token count is floor(alphas.sum(-1)) (cif_predictor.py:443-444), so the SUMMATION ORDER
+# decides an integer outcome; the CUDA kernel (csrc/cif.cu: torch_row_sum_f32) follows the same order and
+# tests/test_oracle_golden.py::test_torch_row_sum_emulation pins this restatement to torch.sum itself.
+# --------------------------------------------------------------------------------------
+def _multi_row_sum(R):
+    """R [size, 4, L] fp32 -> 4 accumulators [L]: 4-level cascade, level 0 flushed every 16 rows (level_power 4)."""
+    import numpy as np
+    size, L = R.shape[0], R.shape[2]
+    acc = np.zeros((4, 4, L), np.float32)
+    i = 0
+    while i + 16 <= size:
+        for _ in range(16):
+            acc[0] = acc[0] + R[i]
+            i += 1
+        for j in range(1, 4):
+            acc[j] = acc[j] + acc[j - 1]
+            acc[j - 1] = 0
+            if (i & (15 << (4 * j))) != 0:
+                break
+    while i < size:
+        acc[0] = acc[0] + R[i]
+        i += 1
+    for j in range(1, 4):
+        acc[0] = acc[0] + acc[j]
+    return [acc[0][k].copy() for k in range(4)]
+
+
+def torch_row_sum_f32(x, lanes: int = 8):
+    """x: 1-D fp32 array -> np.float32 equal to torch.from_numpy(x[None]).sum(-1) on x86 CPUs (8 lanes under every capability)."""
+    import numpy as np
+    x = np.asarray(x, dtype=np.float32)
+    n = x.shape[0]
+    L = lanes if n >= lanes else 1                       # rows shorter than a vector take scalar_inner_sum: same scheme, one lane
+    vec = n // L
+    V = x[: vec * L].reshape(vec, L)
+    ilp = vec // 4
+    ps = _multi_row_sum(V[: ilp * 4].reshape(ilp, 4, L))
+    for i in range(ilp * 4, vec):
+        ps[0] = ps[0] + V[i]
+    for k in range(1, 4):
+        ps[0] = ps[0] + ps[k]
+    f = np.float32(0)
+    for k in range(vec * L, n):
+        f = np.float32(f + x[k])
+    for k in range(L):
+        f = np.float32(f + ps[0][k])
+    return f
+
 # --------------------------------------------------------------------------------------
 # SeacoParaformer: funasr/models/seaco_paraformer/model.py (greedy inference with hotwords, ASF)
 # --------------------------------------------------------------------------------------

@@ -6,18 +6,37 @@ that are absent from this image but never *called* on the offline Paraformer pat
 modules make `import funasr` succeed so the reference's own classes can be run on
 CPU to (a) validate oracle/paraformer_oracle.py and (b) generate tests/golden/*.
 
-/root/reference does not exist on the GPU box: nothing under tests -m gpu,
-bench.py or __graft_entry__.smoke() may import this file.
+/root/reference does not exist on the GPU box.  What CAN travel there is the offline install of the unmodified
+reference under the git-ignored `baseline/_ref/` (`pip install --no-index --no-deps --target baseline/_ref /root/reference`,
+DESIGN.md §8): bench.py's `--impl reference` arm (oracle/ref_runner.py) and the one GPU test that drives
+`AutoModel.generate()` through this backend import it from there.  Nothing else under tests -m gpu, bench.py's own arm or
+__graft_entry__.smoke() touches the reference.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("FUNASR_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("FUNASR_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "funasr")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "funasr"))
+
+
+def reference_kind() -> str:
+    """'tree' = the read-only source tree (/root/reference), 'installed' = the pip --target copy under baseline/_ref."""
+    return "installed" if os.path.abspath(REFERENCE_ROOT).startswith(os.path.join(_REPO, "baseline")) else "tree"
 
 
 def install_stubs():

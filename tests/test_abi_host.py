@@ -121,6 +121,29 @@ mine = shards[dist.get_rank()]
 fake = lambda i: [100 * i + k for k in range(i % 5)]       # utterance i "decodes" to a known id list
 res = gather_token_ids([fake(i) for i in mine], mine, n, width=16)
 assert res == [fake(i) for i in range(n)], res
+assert gather_token_ids([fake(i) for i in mine], mine, n) == res            # width=None: sized by an all_reduce(MAX)
+try:
+    gather_token_ids([fake(i) for i in mine], mine, n, width=2)              # too narrow: raises, never truncates
+    raise SystemExit("expected ValueError")
+except ValueError:
+    pass
+# ShardedRunner: shard -> bucket -> infer -> (device-side rows) -> one all_gather, every rank gets every result in input order
+from funasr_b200.sharding import ShardedRunner
+lens = [400 + 160 * 6 * ((5 * i) % 9 + 1) for i in range(13)]                # 1..9 LFR frames... ragged
+wavs = [torch.full((k,), float(i)) for i, k in enumerate(lens)]
+def infer(batch):                                                            # "decodes" utterance i (read back from its samples) to [i, i+1, ...]
+    idx = [int(w[0]) for w in batch]
+    n = max(i % 4 for i in idx) or 1
+    ids = torch.full((len(batch), n), -1, dtype=torch.int32)
+    for r, i in enumerate(idx):
+        for k in range(i % 4):
+            ids[r, k] = i + k
+    return ids, torch.tensor([i % 4 for i in idx], dtype=torch.int32)
+run = ShardedRunner(infer, "cpu", max_batch=3, max_frames=3 * 10)
+got = run.run(wavs)
+assert got == [[i + k for k in range(i % 4)] for i in range(13)], got
+plan = run.plan(lens)
+assert sorted(i for b in plan["buckets"] for i in b) == sorted(plan["mine"]) and all(len(b) <= 3 for b in plan["buckets"])
 dist.barrier(); dist.destroy_process_group(); print("ok")
 '''
 

@@ -654,3 +654,23 @@ def test_plugin_resamples_8k_input_like_the_reference_loader():
         up.append(y[: -(-new * w.numel() // orig)].contiguous())
     res16, _ = m.inference([w.numpy() for w in up], tokenizer=None, frontend=fe, device=DEV)
     assert [r["token_int"] for r in res8] == [r["token_int"] for r in res16]
+
+
+def test_row_sum_matches_torch_cpu_order_bit_exact():
+    """fa_row_sum_f32 (the summation order the CIF kernels use for floor(alphas.sum(-1)), cif_predictor.py:443-444, and for the
+    timestamp rescale token_num / alphas2.sum(-1), bicif cif_predictor.py:343-345) equals torch's CPU fp32 sum bit for bit,
+    including rows whose sum is within an ulp of an integer (where floor() flips with the order)."""
+    abi, lib = _lib()
+    g = np.random.default_rng(3)
+    for n in [1, 5, 8, 33, 84, 101, 501, 502, 1001, 1500, 3001]:
+        rows = 64
+        x = (g.random((rows, n)) * 0.5).astype(np.float32)
+        if n >= 84:        # drive every row's exact sum onto an integer
+            s64 = x.astype(np.float64).sum(-1, keepdims=True)
+            x = (x.astype(np.float64) * (np.round(s64) / s64)).astype(np.float32)
+        want = torch.from_numpy(x).sum(-1)
+        xd = torch.from_numpy(x).to(DEV)
+        out = torch.empty(rows, device=DEV)
+        abi.check(lib.fa_row_sum_f32(xd.data_ptr(), n, rows, n, out.data_ptr(), _st()), "fa_row_sum_f32")
+        assert torch.equal(out.cpu(), want), n
+        assert torch.equal(torch.floor(out.cpu()), torch.floor(want))

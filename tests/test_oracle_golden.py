@@ -169,3 +169,27 @@ def test_seaco_oracle_matches_reference_golden(name):
 def seaco_sel(o, hw):
     """the golden file stores the UNFILTERED hotword representations; recompute them when ASF filtered the oracle's copy"""
     return o["hw_selected_all"].numpy()
+
+
+def test_torch_row_sum_emulation():
+    """The step-by-step restatement of torch's CPU fp32 row sum (oracle torch_row_sum_f32, mirrored by csrc/cif.cu) equals
+    torch.sum bit for bit — row lengths around every structural boundary (8-lane vectors, 4 ILP accumulators, 16-vector cascade
+    flushes), the CIF row lengths (T+1 = 84..1001, 3T = 1500) and rows whose sum sits within an ulp of an integer."""
+    g = np.random.default_rng(0)
+    for n in [1, 2, 3, 7, 8, 9, 15, 16, 31, 32, 33, 63, 64, 84, 101, 255, 256, 257, 500, 501, 502, 511, 512, 513, 1001, 1500, 3001, 9001]:
+        for trial in range(6):
+            x = (g.random(n) * (1.0 if trial % 2 else 0.4)).astype(np.float32)
+            want = torch.from_numpy(np.stack([x, x]))[1:].sum(-1).numpy()[0]
+            assert O.torch_row_sum_f32(x) == want, (n, trial)
+    # near-integer sums: scale a row so that its exact sum is an integer +- a few fp32 ulps; floor() then depends on the order
+    flips = 0
+    for trial in range(200):
+        n = 501
+        x = (g.random(n) * 0.5).astype(np.float32)
+        target = np.round(x.astype(np.float64).sum())
+        x = (x.astype(np.float64) * (target / x.astype(np.float64).sum())).astype(np.float32)
+        want = torch.from_numpy(x[None]).sum(-1).numpy()[0]
+        got = O.torch_row_sum_f32(x)
+        assert got == want
+        flips += int(np.floor(want) != np.floor(np.float32(x.astype(np.float64).sum())))
+    assert flips > 0      # the cases exist: an order-agnostic (fp64, rounded once) sum disagrees with torch on the integer part
