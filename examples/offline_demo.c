@@ -11,12 +11,12 @@
 int main(int argc, char** argv) {
   printf("library: %s\n", fa_version());
   if (argc < 3) {
-    void* h = fa_offline_init(argc > 1 ? argv[1] : "/nonexistent.fab2", 0, FA_GEMM_BF16X3);
+    void* h = fa_offline_init(argc > 1 ? argv[1] : "/nonexistent.fab2", 0, FA_GEMM_F16X3);
     if (!h) { printf("init failed (expected without a model / GPU): %s\n", fa_offline_last_error()); return 0; }
     fa_offline_uninit(h);
     return 0;
   }
-  void* h = fa_offline_init(argv[1], 0, FA_GEMM_BF16X3);
+  void* h = fa_offline_init(argv[1], 0, FA_GEMM_F16X3);
   if (!h) { fprintf(stderr, "init: %s\n", fa_offline_last_error()); return 1; }
   FILE* f = fopen(argv[2], "rb");
   if (!f) { fprintf(stderr, "cannot open %s\n", argv[2]); return 1; }

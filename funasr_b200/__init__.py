@@ -10,10 +10,11 @@ from .synth import PARAFORMER_LARGE, PARAFORMER_TINY, ParaformerConfig  # noqa: 
 from . import modules  # noqa: F401  (registers the classes)
 from .modules import (CifPredictorV2B200, ParaformerB200, ParaformerSANMDecoderB200, SANMEncoderB200,  # noqa: F401
                       SenseVoiceEncoderSmallB200, SenseVoiceSmallB200, WavFrontendB200, load_cmvn,
-                      ContextualParaformerB200, ContextualParaformerDecoderB200, BiCifParaformerB200, CifPredictorV3B200)
+                      ContextualParaformerB200, ContextualParaformerDecoderB200, BiCifParaformerB200, CifPredictorV3B200,
+                      SeacoParaformerB200)
 from .engine import FrontendEngine, ParaformerEngine, SenseVoiceEngine  # noqa: F401
 from .synth import SENSEVOICE_SMALL, SENSEVOICE_TINY, SenseVoiceConfig  # noqa: F401
-from .sharding import shard_utterances, gather_token_ids  # noqa: F401
+from .sharding import shard_utterances, gather_token_ids, ShardedRunner  # noqa: F401
 from .batching import bucket_by_length, padding_efficiency, run_bucketed  # noqa: F401
 
 __version__ = "0.1.0"

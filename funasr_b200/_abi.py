@@ -11,8 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfunasr_b200.so")
 
 FA_OK = 0
-GEMM_F32_SIMT, GEMM_BF16X1, GEMM_BF16X3, GEMM_BF16X6 = 0, 1, 3, 6
-GEMM_MODES = {"fp32": GEMM_F32_SIMT, "bf16": GEMM_BF16X1, "bf16x3": GEMM_BF16X3, "bf16x6": GEMM_BF16X6}
+GEMM_F32_SIMT, GEMM_F16X1, GEMM_F16X3, GEMM_F16X6 = 0, 1, 3, 6
+GEMM_MODES = {"fp32": GEMM_F32_SIMT, "fp16": GEMM_F16X1, "fp16x3": GEMM_F16X3, "fp16x6": GEMM_F16X6}
 
 c_f32p = C.POINTER(C.c_float)
 c_i32p = C.POINTER(C.c_int32)
@@ -88,13 +88,19 @@ SIGNATURES = {
     "fa_paraformer_decoder_workspace_bytes_hw": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "fa_paraformer_decoder_forward": (C.c_int, [C.POINTER(FaDecoder), _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
     "fa_row_sum_f32": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    "fa_paraformer_decoder_forward_hidden": (C.c_int, [C.POINTER(FaDecoder), _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _sz, _vp]),
+    "fa_sanm_decoder_stack_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "fa_sanm_decoder_stack_forward": (C.c_int, [C.POINTER(FaDecoder), _vp, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "fa_linear_argmax_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "fa_linear_argmax": (C.c_int, [C.POINTER(FaLinear), _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "fa_seaco_merge": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fa_cif_upsample_alphas": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _f, _vp, _vp, _vp]),
     "fa_blstm_forward": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fa_blstm_tc_scratch_bytes": (_sz, [_i32]),
     "fa_blstm_forward_tc": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fa_debug_blstm_variant": (C.c_int, [_i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "fa_greedy_filter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "fa_split_bf16": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "fa_split_planes": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "fa_resample": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _vp]),
     # handle-style offline recogniser (funasrruntime.h:100-116 counterpart; offline.cu)
     "fa_offline_init": (_vp, [C.c_char_p, _i32, _i32]),

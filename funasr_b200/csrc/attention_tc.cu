@@ -1,16 +1,16 @@
-// tcgen05 / TMEM / TMA fused multi-head attention with bf16 operand splitting (sm_100a).
+// tcgen05 / TMEM / TMA fused multi-head attention with fp16 operand splitting (sm_100a).
 //
 // Same contract as attention_f32.cu (sanm/attention.py:288-304 with scores from :324-325; cross-attention :760-794,
 // :811-812): ctx = softmax(mask(q d_k^-0.5 . k^T)) v per head, key-padding mask, heads merged.  Score and context
-// contractions run on the 5th-gen tensor cores with fp32 accumulation in TMEM; operands are bf16 planes (hi, lo) of the
+// contractions run on the 5th-gen tensor cores with fp32 accumulation in TMEM; operands are fp16 planes (hi, lo) of the
 // fp32 tensors so that S = Qh.Kh + Qh.Kl + Ql.Kh and O = Ph.Vh + Ph.Vl + Pl.Vh carry ~2^-17 relative error (x3 mode),
 // or one plane (x1 mode).  The [B,H,Tq,Tk] score tensor never leaves the SM.
 //
 // One CTA = 128 queries of one (utterance, head), keys in chunks of 64, two passes over the keys:
 //   pass A: S~ = Qh.Kh (one MMA term) -> per-row max m   (softmax is invariant to the choice of m; an approximate
-//           maximum only has to keep exp(s - m) in range, so one bf16 term suffices)
+//           maximum only has to keep exp(s - m) in range, so one fp16 term suffices)
 //   pass B: S (all terms) -> p = exp(s - m), l += sum p, P planes -> smem, O += P.V accumulated in TMEM with no
-//           rescaling traffic; finally O / l -> bf16 planes (A operand of the out-projection GEMM) and/or fp32.
+//           rescaling traffic; finally O / l -> fp16 planes (A operand of the out-projection GEMM) and/or fp32.
 // Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 softmax + epilogue:
 // TMEM lane == query row; two threads per row (warp w owns lane quarter w%4 and column half (w-4)/4) so that every SM
 // sub-partition has two softmax warps to interleave.  S is double buffered in TMEM so the MMAs of chunk j+1 overlap
@@ -23,8 +23,8 @@
 namespace fa {
 
 constexpr int AT_BQ = 128, AT_BKEY = 64, AT_D = 128;
-constexpr uint32_t AT_Q_KBLK = AT_BQ * 128;      // 16 KB: 128 rows x 64 bf16
-constexpr uint32_t AT_K_KBLK = AT_BKEY * 128;    // 8 KB : 64 keys x 64 bf16
+constexpr uint32_t AT_Q_KBLK = AT_BQ * 128;      // 16 KB: 128 rows x 64 fp16
+constexpr uint32_t AT_K_KBLK = AT_BKEY * 128;    // 8 KB : 64 keys x 64 fp16
 constexpr uint32_t AT_V_TILE = AT_D * 128;       // 16 KB: 128 d-rows x 64 keys
 constexpr uint32_t AT_P_TILE = AT_BQ * 128;      // 16 KB: 128 queries x 64 keys
 
@@ -34,7 +34,7 @@ struct AttTcParams {
   const int32_t* key_lens;
   int64_t q_plane_rows, k_plane_rows, v_plane_rows;   // rows between planes in the respective 2D maps
   float* ctx; int64_t ldc;                             // fp32 output (or null)
-  __nv_bfloat16* ctx_planes; int64_t ldp; int out_nplanes;   // bf16 planes [npl][B*tq][ldp] (or null)
+  plane_t* ctx_planes; int64_t ldp; int out_nplanes;   // fp16 planes [npl][B*tq][ldp] (or null)
 };
 
 // Optional in-kernel timeline (tools/att_trace.py builds a separate library with -DFA_ATT_TRACE; the product build has none
@@ -155,8 +155,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (nc > 0 && elect_one_sync()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(AT_BQ, AT_BKEY);
-      constexpr uint32_t idesc_o = make_idesc_bf16(AT_BQ, AT_D);
+      constexpr uint32_t idesc_s = make_idesc_f16(AT_BQ, AT_BKEY);
+      constexpr uint32_t idesc_o = make_idesc_f16(AT_BQ, AT_D);
       const int ta[3] = {0, 0, 1}, tb[3] = {0, 1, 0};
       const uint32_t ring_addr = smem_u32(sRing);
       TRACE_DECL();
@@ -186,7 +186,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           for (int k = 0; k < AT_D / 16; ++k) {
             const uint32_t a_t = tmem_base + TM_Q + ta[term] * 64 + k * 8;
             const uint64_t db = make_sw128_desc(k_addr + (tb[term] * 2 + (k >> 2)) * BOX) + 2 * (k & 3);
-            umma_bf16_ts(d_s, a_t, db, idesc_s, (term | k) != 0 ? 1u : 0u);
+            umma_f16_ts(d_s, a_t, db, idesc_s, (term | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&s_full[st]);
@@ -208,7 +208,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           for (int k = 0; k < AT_BKEY / 16; ++k) {
             // keys 16k..16k+15 of plane ta: half (k>>1) of the stage, 8 columns per step, lo plane 16 columns after hi
             const uint32_t a_t = p_t + (k >> 1) * 32 + ta[term] * 16 + (k & 1) * 8;
-            umma_bf16_ts(tmem_o, a_t, db + 2 * k, idesc_o, (t | term | k) != 0 ? 1u : 0u);
+            umma_f16_ts(tmem_o, a_t, db + 2 * k, idesc_o, (t | term | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&sb_free[st]);
@@ -281,7 +281,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       s_red[hf * 128 + r] = m;
       softmax_bar();
       m = fmaxf(m, s_red[(hf ^ 1) * 128 + r]);     // finite: key 0 is always valid when nc > 0
-      // ---- pass B: probabilities, written back IN PLACE over this thread's 32 score columns as bf16 planes
+      // probabilities are formed as p' = 2^10 exp(s - m): the common factor cancels in O / l, and it keeps probabilities down to
+      // 6e-8 inside the fp16 planes' NORMAL range (p' <= ~1100 with the approximate maximum of pass A; fp16 holds 65504)
+      const float mp = m - 6.931471805599453f;
+      // ---- pass B: probabilities, written back IN PLACE over this thread's 32 score columns as fp16 planes
       //      (columns [32 hf, +16) = hi plane of keys 32 hf .. 32 hf + 31, the next 16 columns = lo plane): the A operand of P.V
       for (int t = 0; t < nc; ++t) {
         const int j = nc + t, st = j % NS;
@@ -297,17 +300,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           const bool whole = kbase + 32 <= klen;          // warp-uniform
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            float a = __expf(__uint_as_float(v[2 * e]) - m), bb = __expf(__uint_as_float(v[2 * e + 1]) - m);
+            float a = __expf(__uint_as_float(v[2 * e]) - mp), bb = __expf(__uint_as_float(v[2 * e + 1]) - mp);
             if (!whole) { a = (kbase + 2 * e < klen) ? a : 0.f; bb = (kbase + 2 * e + 1 < klen) ? bb : 0.f; }
             l += a;                                        // sequential order (matches the row-sum order of earlier builds)
             l += bb;
-            // packed cvt.rn.bf16x2.f32 (ALU pipe) instead of two scalar F2F.BF16 (quarter-rate XU pipe, shared with EX2);
-            // bf16 -> fp32 is a 16-bit shift
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, bb);
-            hi[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            // packed conversions to the fp16 planes (tc_common.cuh)
+            hi[e] = pack_planes2(a, bb);
             if (NPL > 1) {
-              const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - __uint_as_float(hi[e] << 16), bb - __uint_as_float(hi[e] & 0xFFFF0000u));
-              lo[e] = *reinterpret_cast<const uint32_t*>(&l2);
+              const float2 hv = unpack_planes2(hi[e]);
+              lo[e] = pack_planes2(a - hv.x, bb - hv.y);
             }
           }
         }
@@ -329,7 +330,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       TRACE(2, 8);
     }
     // ---- epilogue: O / l for this warp's 32 rows x 64 head dims, staged through shared memory (the K/V ring is dead once
-    //      o_full has fired) so that the context rows leave as coalesced 8-byte (bf16 planes) / 16-byte (fp32) stores
+    //      o_full has fired) so that the context rows leave as coalesced 8-byte (fp16 planes) / 16-byte (fp32) stores
     const float inv = l > 0.f ? 1.0f / l : 0.f;
     float* stage = reinterpret_cast<float*>(sQ) + (warp - 4) * (32 * 36);
     const int64_t grow0 = (int64_t)b * p.tq + q0 + qw * 32;
@@ -354,7 +355,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const int col = h * AT_D + c0 + c4;
       const int rows_ok = p.tq - (q0 + qw * 32);                      // valid rows of this warp's 32
       float* pc = p.ctx ? p.ctx + (grow0 + rr0) * p.ldc + col : nullptr;
-      __nv_bfloat16* pp = OPL > 0 ? p.ctx_planes + (grow0 + rr0) * p.ldp + col : nullptr;
+      plane_t* pp = OPL > 0 ? p.ctx_planes + (grow0 + rr0) * p.ldp + col : nullptr;
       const int64_t plane = (int64_t)p.batch * p.tq * p.ldp;
       const float* sp = stage + rr0 * 36 + c4;
 #pragma unroll 2
@@ -364,18 +365,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           if (pc) *reinterpret_cast<float4*>(pc + (int64_t)it * 4 * p.ldc) = o4;
           if (OPL > 0) {
             float x0 = o4.x, x1 = o4.y, x2 = o4.z, x3 = o4.w;
-            __nv_bfloat16* dst = pp + (int64_t)it * 4 * p.ldp;
+            plane_t* dst = pp + (int64_t)it * 4 * p.ldp;
 #pragma unroll
             for (int pl = 0; pl < OPL; ++pl) {
-              const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
               uint2 pk;
-              pk.x = *reinterpret_cast<const uint32_t*>(&p01);
-              pk.y = *reinterpret_cast<const uint32_t*>(&p23);
+              pk.x = pack_planes2(x0, x1);
+              pk.y = pack_planes2(x2, x3);
               *reinterpret_cast<uint2*>(dst) = pk;
               if (pl + 1 < OPL) {
                 dst += plane;
-                x0 -= __uint_as_float(pk.x << 16); x1 -= __uint_as_float(pk.x & 0xFFFF0000u);
-                x2 -= __uint_as_float(pk.y << 16); x3 -= __uint_as_float(pk.y & 0xFFFF0000u);
+                const float2 ua = unpack_planes2(pk.x), ub = unpack_planes2(pk.y);
+                x0 -= ua.x; x1 -= ua.y; x2 -= ub.x; x3 -= ub.y;
               }
             }
           }
@@ -394,7 +394,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // V [B, tk, ldv] (head h at column h*128) -> Vt planes [npl][B*H*128][tkp] (keys contiguous), via a 64x64 smem transpose.
 __global__ void __launch_bounds__(256)
 vt_planes_kernel(const float* __restrict__ v, int64_t ldv, int tk, int tkp, int heads, int nplanes, int64_t plane_elems,
-                 __nv_bfloat16* __restrict__ vt) {
+                 plane_t* __restrict__ vt) {
   __shared__ float tile[64][65];
   const int t0 = blockIdx.x * 64, dblk = blockIdx.y, b = blockIdx.z;   // dblk over heads*2 (64-wide d blocks)
   const int tid = threadIdx.x;
@@ -410,19 +410,20 @@ vt_planes_kernel(const float* __restrict__ v, int64_t ldv, int tk, int tkp, int 
     const int d = idx >> 5, kp = (idx & 31) * 2;
     if (t0 + kp >= tkp) continue;
     float a = tile[kp][d], bb = tile[kp + 1][d];
-    __nv_bfloat16* dst = vt + ((int64_t)b * heads * AT_D + dblk * 64 + d) * tkp + t0 + kp;
+    plane_t* dst = vt + ((int64_t)b * heads * AT_D + dblk * 64 + d) * tkp + t0 + kp;
     for (int pl = 0; pl < nplanes; ++pl) {
-      const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(bb);
-      *reinterpret_cast<__nv_bfloat162*>(dst + pl * plane_elems) = __halves2bfloat162(ha, hb);
-      a -= __bfloat162float(ha); bb -= __bfloat162float(hb);
+      const uint32_t pk = pack_planes2(a, bb);
+      *reinterpret_cast<uint32_t*>(dst + pl * plane_elems) = pk;
+      const float2 u = unpack_planes2(pk);
+      a -= u.x; bb -= u.y;
     }
   }
 }
 
-// fp32 [rows, cols] (ld) * scale -> bf16 planes [nplanes][rows][cols]
+// fp32 [rows, cols] (ld) * scale -> fp16 planes [nplanes][rows][cols]
 __global__ void __launch_bounds__(256)
 scale_split_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, float scale, int nplanes,
-                   __nv_bfloat16* __restrict__ planes) {
+                   plane_t* __restrict__ planes) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int c4n = cols >> 2;
   if (i >= rows * c4n) return;
@@ -432,18 +433,18 @@ scale_split_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int 
   float v[4] = {__fmul_rn(x.x, scale), __fmul_rn(x.y, scale), __fmul_rn(x.z, scale), __fmul_rn(x.w, scale)};
   const int64_t plane = rows * cols;
   for (int pl = 0; pl < nplanes; ++pl) {
-    __nv_bfloat16 hh[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { hh[k] = __float2bfloat16_rn(v[k]); v[k] -= __bfloat162float(hh[k]); }
-    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(planes + pl * plane + r * cols + c);
-    dst[0] = __halves2bfloat162(hh[0], hh[1]);
-    dst[1] = __halves2bfloat162(hh[2], hh[3]);
+    uint2 pk;
+    pk.x = pack_planes2(v[0], v[1]);
+    pk.y = pack_planes2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(planes + pl * plane + r * cols + c) = pk;
+    const float2 ua = unpack_planes2(pk.x), ub = unpack_planes2(pk.y);
+    v[0] -= ua.x; v[1] -= ua.y; v[2] -= ub.x; v[3] -= ub.y;
   }
 }
 
 size_t attention_tc_scratch_bytes(int batch, int heads, int tq, int tk, int mode) {
   if (mode == FA_GEMM_F32_SIMT) return 0;
-  const int npl = mode == FA_GEMM_BF16X1 ? 1 : 2;
+  const int npl = mode == FA_GEMM_F16X1 ? 1 : 2;
   const int tkp = (tk + 63) / 64 * 64;
   const int d = heads * AT_D;
   return (size_t)npl * 2 * ((size_t)batch * tq * d + (size_t)batch * tk * d + (size_t)batch * d * tkp) + 4096;
@@ -451,19 +452,19 @@ size_t attention_tc_scratch_bytes(int batch, int heads, int tq, int tk, int mode
 
 int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                         const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
-                        __nv_bfloat16* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st, int kv_shared) {
+                        plane_t* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st, int kv_shared) {
   if (batch <= 0 || tq <= 0) return FA_OK;
   if (!q || !k || !v || !key_lens || tk <= 0 || !scratch) return FA_ERR_ARG;
   if ((ldq | ldk | ldv) & 3) return FA_ERR_UNSUPPORTED;
-  const int npl = mode == FA_GEMM_BF16X1 ? 1 : 2;
+  const int npl = mode == FA_GEMM_F16X1 ? 1 : 2;
   const int d = heads * AT_D;
   const int tkp = (tk + 63) / 64 * 64;
   const int kvb = kv_shared ? 1 : batch;
   const int64_t mq = (int64_t)batch * tq, mk = (int64_t)kvb * tk, mv = (int64_t)kvb * d;
   Arena local(scratch->base, scratch->cap);
-  __nv_bfloat16* qp = local.take<__nv_bfloat16>((size_t)npl * mq * d);
-  __nv_bfloat16* kp = local.take<__nv_bfloat16>((size_t)npl * mk * d);
-  __nv_bfloat16* vt = local.take<__nv_bfloat16>((size_t)npl * mv * tkp);
+  plane_t* qp = local.take<plane_t>((size_t)npl * mq * d);
+  plane_t* kp = local.take<plane_t>((size_t)npl * mk * d);
+  plane_t* vt = local.take<plane_t>((size_t)npl * mv * tkp);
   if (!local.ok()) return FA_ERR_WORKSPACE;
   const float qscale = (float)(1.0 / sqrt((double)AT_D));
   {
@@ -509,20 +510,20 @@ static int launch_att(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, c
 
 // Operand planes already in place (written by the producing GEMMs' epilogues, gemm_tc.cu AttnSinks):
 // qp [npl][B*tq][H*128] (scaled), kp [npl][B*tk][H*128], vt [npl][B*H*128][round_up(tk,64)].
-int attention_tc_planes_launch(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfloat16* vt, const int32_t* key_lens,
-                               int batch, int heads, int tq, int tk, float* ctx, int64_t ldc, __nv_bfloat16* ctx_planes,
+int attention_tc_planes_launch(const plane_t* qp, const plane_t* kp, const plane_t* vt, const int32_t* key_lens,
+                               int batch, int heads, int tq, int tk, float* ctx, int64_t ldc, plane_t* ctx_planes,
                                int64_t ldp, int out_nplanes, int mode, cudaStream_t st, int kv_shared) {
   if (batch <= 0 || tq <= 0) return FA_OK;
   if (!qp || !kp || !vt || !key_lens || tk <= 0) return FA_ERR_ARG;
-  const int npl = mode == FA_GEMM_BF16X1 ? 1 : 2;
+  const int npl = mode == FA_GEMM_F16X1 ? 1 : 2;
   const int d = heads * AT_D;
   const int tkp = (tk + 63) / 64 * 64;
   const int kvb = kv_shared ? 1 : batch;
   const int64_t mq = (int64_t)batch * tq, mk = (int64_t)kvb * tk, mv = (int64_t)kvb * d;
   CUtensorMap mq_map, mk_map, mv_map;
-  FA_RETURN_IF_ERR(make_bf16_map(&mq_map, qp, (uint64_t)mq * npl, (uint64_t)d, (uint64_t)d, AT_BQ));
-  FA_RETURN_IF_ERR(make_bf16_map(&mk_map, kp, (uint64_t)mk * npl, (uint64_t)d, (uint64_t)d, AT_BKEY));
-  FA_RETURN_IF_ERR(make_bf16_map(&mv_map, vt, (uint64_t)mv * npl, (uint64_t)tk, (uint64_t)tkp, 64));   // 8 KB boxes: 64 d-rows x 64 keys
+  FA_RETURN_IF_ERR(make_plane_map(&mq_map, qp, (uint64_t)mq * npl, (uint64_t)d, (uint64_t)d, AT_BQ));
+  FA_RETURN_IF_ERR(make_plane_map(&mk_map, kp, (uint64_t)mk * npl, (uint64_t)d, (uint64_t)d, AT_BKEY));
+  FA_RETURN_IF_ERR(make_plane_map(&mv_map, vt, (uint64_t)mv * npl, (uint64_t)tk, (uint64_t)tkp, 64));   // 8 KB boxes: 64 d-rows x 64 keys
   AttTcParams p;
   p.tq = tq; p.tk = tk; p.heads = heads; p.batch = batch; p.key_lens = key_lens; p.kv_shared = kv_shared ? 1 : 0;
   p.q_plane_rows = mq; p.k_plane_rows = mk; p.v_plane_rows = mv;

@@ -1,8 +1,8 @@
 // Output-side kernels of the greedy decode: row arg-max with log-sum-exp (log_softmax value of the arg-max,
 // paraformer/model.py:345,642-644), optional in-place log_softmax of the full logits for parity checks, the
-// {blank,sos,eos} filter (:655-666), and the fp32 -> bf16 plane split used by the tcgen05 GEMM weights.
+// {blank,sos,eos} filter (:655-666), and the fp32 -> fp16 plane split used by the tcgen05 GEMM weights.
 #include "common.cuh"
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 #include <math.h>
 
 namespace fa {
@@ -122,23 +122,23 @@ int ctc_filter_launch(const int32_t* ids, const int32_t* lens, int batch, int t_
   return FA_OK;
 }
 
-// x = hi + mid + lo with hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid); planes [3][rows][cols_pad].
+// x = hi + mid + lo with hi = f16(x), mid = f16(x - hi), lo = f16(x - hi - mid) (fp16 planes, tc_common.cuh); planes [3][rows][cols_pad].
 __global__ void __launch_bounds__(256)
-split_bf16_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, int cols_pad,
-                  __nv_bfloat16* __restrict__ planes) {
+split_planes_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, int cols_pad,
+                  plane_t* __restrict__ planes) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = rows * cols_pad;
   if (i >= total) return;
   const int64_t r = i / cols_pad;
   const int c = (int)(i - r * cols_pad);
   const float x = c < cols ? src[r * ld + c] : 0.f;
-  const __nv_bfloat16 h = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(h);
-  const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(m);
+  const plane_t h = to_plane(x);
+  const float r1 = x - plane_to_float(h);
+  const plane_t m = to_plane(r1);
+  const float r2 = r1 - plane_to_float(m);
   planes[i] = h;
   planes[total + i] = m;
-  planes[2 * total + i] = __float2bfloat16_rn(r2);
+  planes[2 * total + i] = to_plane(r2);
 }
 
 int argmax_lse_launch(float* logits, int64_t rows, int vocab, int64_t ld, int32_t* ids, float* best_logp,
@@ -169,12 +169,12 @@ extern "C" int fa_broadcast_rows(const float* rows, int32_t n_rows, int32_t cols
   return FA_OK;
 }
 
-extern "C" int fa_split_bf16(const float* src, int64_t ld_src, int64_t rows, int32_t cols, int32_t cols_pad,
+extern "C" int fa_split_planes(const float* src, int64_t ld_src, int64_t rows, int32_t cols, int32_t cols_pad,
                              void* planes, fa_stream_t stream) {
   if (!src || !planes || rows <= 0 || cols <= 0 || cols_pad < cols) return FA_ERR_ARG;
   const int64_t total = rows * cols_pad;
-  fa::split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      src, ld_src, rows, cols, cols_pad, reinterpret_cast<__nv_bfloat16*>(planes));
+  fa::split_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      src, ld_src, rows, cols, cols_pad, reinterpret_cast<fa::plane_t*>(planes));
   FA_CHECK_LAUNCH();
   return FA_OK;
 }

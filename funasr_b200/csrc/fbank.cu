@@ -7,8 +7,9 @@
 // HBM-bound by design: algorithmic bytes = 4 B/sample in + 4*560 B/LFR-row out (3.04 MB per 30 s).
 // One CTA owns kRows consecutive LFR rows of one utterance: it stages the (6*kRows+1) frames' worth of
 // samples into shared memory once (coalesced), each warp turns frames into log-mel rows with a
-// shared-memory 256-point complex Stockham FFT (real 512-point FFT by even/odd packing), and the CTA
-// then writes its LFR rows (7 stacked log-mel frames, CMVN applied) with fully coalesced stores.
+// register-resident 256-point complex FFT (radix 8 in registers x 32-point across the lanes on shuffles;
+// real 512-point FFT by even/odd packing), and the CTA then writes its LFR rows (7 stacked log-mel frames,
+// CMVN applied) with fully coalesced stores.
 // Adjacent CTAs recompute one overlapping frame (1/48 redundancy) instead of round-tripping log-mel
 // through HBM.
 #include "common.cuh"
@@ -96,52 +97,106 @@ fbank_lfr_cmvn_kernel(const float* __restrict__ wav, const int32_t* __restrict__
   }
   __syncthreads();
 
-  // ---- one warp per frame ----
-  float2* A = s.fft[warp][0];
-  float2* Bf = s.fft[warp][1];
+  // ---- one warp per frame: 512-point real FFT as a 256-point complex FFT held in REGISTERS ----
+  // z[n] = y[2n] + i y[2n+1]; lane L owns z[L + 32 r], r = 0..7.  256 = 8 x 32 (Cooley-Tukey):
+  //   (1) 8-point DFT over r in registers, (2) twiddle W_256^{L k1}, (3) 32-point DFT across the lanes for each k1 as five
+  //   decimation-in-frequency butterfly stages on warp shuffles (no shared-memory round trips; the round-1 kernel made eight
+  //   radix-2 Stockham passes through shared memory per frame and was bound by their latency: 1.12 ms for 64 x 30 s),
+  //   after which lane L holds Z[k1 + 8 rev5(L)].  The spectrum goes to shared memory ONCE for the real-FFT untangling
+  //   (needs Z[k] and Z[256 - k]), the power spectrum and the sparse mel filters.
+  // All twiddles depend only on the lane: hoisted out of the frame loop.
+  float2* Zs = s.fft[warp][0];                                    // [8][kZs] spectrum, row k1, column k2
+  float* P = reinterpret_cast<float*>(s.fft[warp][1]);            // [257] power spectrum
+  constexpr int kZs = 36;                                         // row pitch (float2): at most 2-way bank conflicts on the strided reads
+  auto twid = [&](int idx) -> float2 {                            // e^{-2 pi i idx / 512}, idx in [0, 512)
+    const float2 w = s.tw[idx & 255];
+    return idx < 256 ? w : make_float2(-w.x, -w.y);
+  };
+  float2 tw8[8], twl[5];
+#pragma unroll
+  for (int k1 = 1; k1 < 8; ++k1) tw8[k1] = twid(2 * lane * k1);   // W_256^{lane k1}
+#pragma unroll
+  for (int st = 0; st < 5; ++st) { const int mm = 16 >> st; twl[st] = twid((lane & (mm - 1)) * (256 / mm)); }   // W_{2m}^{lane mod m}
+  const int rev = (int)(__brev((unsigned)lane) >> 27);
+  const float kR = 0.70710678118654752f;
   for (int f = warp; f < nfr; f += kWarps) {
     const float* x = s.wav + f * kShift;
+    // samples 2(L + 32 r), +1 of the frame (zero beyond the 400-sample window) and their predecessors
+    float xe[8], xo[8], xp[8];
     float part = 0.f;
-    for (int j = lane; j < kWin; j += 32) part += x[j];
-    const float mean = warp_sum(part) / (float)kWin;                // remove_dc_offset kaldi.py:183-186
-    float* Af = reinterpret_cast<float*>(A);
-    for (int j = lane; j < kFft; j += 32) {
-      float y = 0.f;
-      if (j < kWin) {
-        const float cur = __fsub_rn(x[j], mean);
-        const float prev = __fsub_rn(x[j > 0 ? j - 1 : 0], mean);   // replicate pad, :193-198
-        y = __fmul_rn(__fsub_rn(cur, __fmul_rn(0.97f, prev)), s.win[j]);
-      }
-      Af[j] = y;                                                    // z[n] = y[2n] + i y[2n+1]
-    }
-    __syncwarp();
-    float2* in = A;
-    float2* outb = Bf;
-#pragma unroll 1
-    for (int p = 1; p < 256; p <<= 1) {                             // radix-2 Stockham, 8 passes
-      const int tws = 256 / p;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int i = lane + 32 * q;
-        const int k = i & (p - 1);
-        const int j = ((i - k) << 1) + k;
-        const float2 w = s.tw[k * tws];
-        const float2 u0 = in[i], v = in[i + 128];
-        const float2 u1 = make_float2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
-        outb[j] = make_float2(u0.x + u1.x, u0.y + u1.y);
-        outb[j + p] = make_float2(u0.x - u1.x, u0.y - u1.y);
-      }
-      __syncwarp();
-      float2* t = in; in = outb; outb = t;
+    for (int r = 0; r < 8; ++r) {
+      const int j0 = 2 * lane + 64 * r;
+      if (j0 < kWin) {
+        const float2 v = *reinterpret_cast<const float2*>(x + j0);
+        xe[r] = v.x; xo[r] = v.y;
+        xp[r] = x[j0 > 0 ? j0 - 1 : 0];                            // replicate pad, kaldi.py:193-198
+        part += v.x + v.y;
+      } else { xe[r] = xo[r] = xp[r] = 0.f; }
     }
-    // after 8 passes the spectrum of z sits in `in` (== A); power spectrum of the real signal -> P[0..256]
-    float* P = reinterpret_cast<float*>(outb);
+    const float mean = warp_sum(part) / (float)kWin;               // remove_dc_offset kaldi.py:183-186
+    float2 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int j0 = 2 * lane + 64 * r;
+      if (j0 < kWin) {
+        const float ce = __fsub_rn(xe[r], mean), co = __fsub_rn(xo[r], mean), cp = __fsub_rn(xp[r], mean);
+        const float2 w2 = *reinterpret_cast<const float2*>(s.win + j0);
+        v[r].x = __fmul_rn(__fsub_rn(ce, __fmul_rn(0.97f, cp)), w2.x);      // pre-emphasis then window (:193-204)
+        v[r].y = __fmul_rn(__fsub_rn(co, __fmul_rn(0.97f, ce)), w2.y);
+      } else { v[r] = make_float2(0.f, 0.f); }
+    }
+    // (1) 8-point DFT over r (two 4-point DFTs on the even / odd r, then the W_8 combine)
+    {
+      float2 e[4], o[4];
+      {
+        const float2 t0 = make_float2(v[0].x + v[4].x, v[0].y + v[4].y), t1 = make_float2(v[0].x - v[4].x, v[0].y - v[4].y);
+        const float2 t2 = make_float2(v[2].x + v[6].x, v[2].y + v[6].y), t3 = make_float2(v[2].x - v[6].x, v[2].y - v[6].y);
+        e[0] = make_float2(t0.x + t2.x, t0.y + t2.y); e[2] = make_float2(t0.x - t2.x, t0.y - t2.y);
+        e[1] = make_float2(t1.x + t3.y, t1.y - t3.x); e[3] = make_float2(t1.x - t3.y, t1.y + t3.x);    // t1 -/+ i t3
+      }
+      {
+        const float2 t0 = make_float2(v[1].x + v[5].x, v[1].y + v[5].y), t1 = make_float2(v[1].x - v[5].x, v[1].y - v[5].y);
+        const float2 t2 = make_float2(v[3].x + v[7].x, v[3].y + v[7].y), t3 = make_float2(v[3].x - v[7].x, v[3].y - v[7].y);
+        o[0] = make_float2(t0.x + t2.x, t0.y + t2.y); o[2] = make_float2(t0.x - t2.x, t0.y - t2.y);
+        o[1] = make_float2(t1.x + t3.y, t1.y - t3.x); o[3] = make_float2(t1.x - t3.y, t1.y + t3.x);
+      }
+      // W_8^1 = (1 - i)/sqrt2, W_8^2 = -i, W_8^3 = (-1 - i)/sqrt2
+      const float2 o1 = make_float2(kR * (o[1].x + o[1].y), kR * (o[1].y - o[1].x));
+      const float2 o2 = make_float2(o[2].y, -o[2].x);
+      const float2 o3 = make_float2(kR * (o[3].y - o[3].x), -kR * (o[3].x + o[3].y));
+      v[0] = make_float2(e[0].x + o[0].x, e[0].y + o[0].y); v[4] = make_float2(e[0].x - o[0].x, e[0].y - o[0].y);
+      v[1] = make_float2(e[1].x + o1.x, e[1].y + o1.y);     v[5] = make_float2(e[1].x - o1.x, e[1].y - o1.y);
+      v[2] = make_float2(e[2].x + o2.x, e[2].y + o2.y);     v[6] = make_float2(e[2].x - o2.x, e[2].y - o2.y);
+      v[3] = make_float2(e[3].x + o3.x, e[3].y + o3.y);     v[7] = make_float2(e[3].x - o3.x, e[3].y - o3.y);
+    }
+    // (2) twiddle W_256^{lane k1}
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1) v[k1] = make_float2(v[k1].x * tw8[k1].x - v[k1].y * tw8[k1].y, v[k1].x * tw8[k1].y + v[k1].y * tw8[k1].x);
+    // (3) 32-point DFT across the lanes (decimation in frequency: lane L ends with output index rev5(L))
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+      const int mm = 16 >> st;
+      const bool upper = (lane & mm) != 0;
+      const float2 w = twl[st];
+#pragma unroll
+      for (int k1 = 0; k1 < 8; ++k1) {
+        const float px = __shfl_xor_sync(0xffffffffu, v[k1].x, mm), py = __shfl_xor_sync(0xffffffffu, v[k1].y, mm);
+        const float dx = px - v[k1].x, dy = py - v[k1].y;                       // (lower - upper), used by the upper lane
+        v[k1] = upper ? make_float2(dx * w.x - dy * w.y, dx * w.y + dy * w.x) : make_float2(v[k1].x + px, v[k1].y + py);
+      }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) Zs[k1 * kZs + rev] = v[k1];                  // Z[k1 + 8 rev5(lane)]
+    __syncwarp();
+    // power spectrum of the real signal -> P[0..256]
+    auto Z = [&](int k) -> float2 { return Zs[(k & 7) * kZs + (k >> 3)]; };
     for (int k = lane; k < kBins; k += 32) {
       float re, im;
-      if (k == 0) { re = in[0].x + in[0].y; im = 0.f; }
-      else if (k == 256) { re = in[0].x - in[0].y; im = 0.f; }
+      if (k == 0) { const float2 z0 = Z(0); re = z0.x + z0.y; im = 0.f; }
+      else if (k == 256) { const float2 z0 = Z(0); re = z0.x - z0.y; im = 0.f; }
       else {
-        const float2 zk = in[k], zc = in[256 - k];
+        const float2 zk = Z(k), zc = Z(256 - k);
         const float er = 0.5f * (zk.x + zc.x), ei = 0.5f * (zk.y - zc.y);
         const float orr = 0.5f * (zk.y + zc.y), oi = -0.5f * (zk.x - zc.x);
         const float2 w = s.tw[k];

@@ -1,10 +1,10 @@
-// tcgen05 / TMEM / TMA GEMM with bf16 operand splitting and a fused nn.Linear epilogue (sm_100a only).
+// tcgen05 / TMEM / TMA GEMM with fp16 operand splitting and a fused nn.Linear epilogue (sm_100a only).
 //
 //   Y[M,N] = act( sum_{(p,q) in terms} A_p[M,K] * W_q[N,K]^T + b ) (+ res1) (+ res2)
 //
-// A_p / W_q are the bf16 planes of the fp32 operands (x = hi + mid + lo, made by split kernels), accumulation is
-// fp32 in TMEM.  Modes: BF16X1 = {(0,0)} (fast), BF16X3 = {(0,0),(0,1),(1,0)} (~2^-17 relative, the default
-// parity mode on tensor cores), BF16X6 = X3 + {(1,1),(0,2),(2,0)} (~fp32).  This replaces the torch.nn.Linear calls
+// A_p / W_q are the fp16 planes of the fp32 operands (x = hi + mid + lo, made by split kernels), accumulation is
+// fp32 in TMEM.  Modes: F16X1 = {(0,0)} (fast), F16X3 = {(0,0),(0,1),(1,0)} (~2^-17 relative, the default
+// parity mode on tensor cores), F16X6 = X3 + {(1,1),(0,2),(2,0)} (~fp32).  This replaces the torch.nn.Linear calls
 // of the hot path (sanm/attention.py:256,306, transformer/positionwise_feed_forward.py:34,
 // sanm/positionwise_feed_forward.py:33, paraformer/decoder.py:444, cif conv as GEMM).
 //
@@ -15,7 +15,7 @@
 //   warp 2 : TMEM allocator (2 accumulators x BN columns, double buffered so the epilogue of tile i overlaps
 //            the MMAs of tile i+1)
 //   warps 4-7 : epilogue   — tcgen05.ld (32 lanes x 32 columns per warp and step) -> bias/ReLU/residuals ->
-//            fp32 rows to HBM, or bf16 planes for a following GEMM.
+//            fp32 rows to HBM, or fp16 planes for a following GEMM.
 // Tensor-pipe bound when operand tiles are reused from L2; roofline notes in DESIGN.md.
 #include "common.cuh"
 #include "kernels.h"
@@ -26,7 +26,7 @@
 namespace fa {
 
 constexpr int TC_BM = 128;      // UMMA M (cta_group::1)
-constexpr int TC_BK = 64;       // one 128-byte swizzle span of bf16
+constexpr int TC_BK = 64;       // one 128-byte swizzle span of fp16
 constexpr int TC_UK = 16;       // UMMA K for 16-bit inputs
 constexpr uint32_t TC_TILE_BYTES_A = TC_BM * TC_BK * 2;   // 16 KB per plane tile
 
@@ -42,7 +42,7 @@ struct TcParams {
   const float* r1; int64_t ldr1;
   const float* r2; int64_t ldr2;
   float* C; int64_t ldc;                 // fp32 output (or null)
-  __nv_bfloat16* out_planes;             // bf16 plane output [3][M][ldo] (or null)
+  plane_t* out_planes;             // fp16 plane output [3][M][ldo] (or null)
   int64_t ldo; int out_nplanes;
   int tiles_m, tiles_n;
   AttnSinks att;                          // optional: route column ranges to attention operand planes
@@ -55,7 +55,7 @@ __constant__ int c_term_w[6] = {0, 1, 0, 1, 2, 0};
 // global latencies are hidden by the other): warp w drains TMEM lane quarter w%4 and every second 16-column chunk.
 //   phase 1  tcgen05.ld 32x32b.x16 (thread = row) -> raw fp32 accumulators into a padded shared-memory tile [32][20]
 //   phase 2  re-read with the warp laid out as 8 rows x 4 float4 columns, so bias / residual loads and every store are
-//            coalesced 16-byte (fp32) or 8-byte (bf16 plane) accesses; V columns of the attention sink take a
+//            coalesced 16-byte (fp32) or 8-byte (fp16 plane) accesses; V columns of the attention sink take a
 //            column-per-lane path that writes the per-head transposed planes as 4 consecutive keys (8 bytes) per store.
 // History (profiles/README.md): v1 stored straight from the row-per-thread layout (4-byte stores to 32 lines per
 // instruction); v2 staged through smem but kept 4 epilogue warps and measured SLOWER — ncu showed tensor pipe 17-25 %,
@@ -75,22 +75,21 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// x = hi + mid + lo split of 4 values, packed converts (cvt.rn.bf16x2.f32), bf16 -> f32 by bit shifts.  NPL is a compile-
+// x = hi + mid + lo split of 4 values into fp16 planes: packed converts (cvt.rn.satfinite.f16x2.f32), packed unpack.  NPL is a compile-
 // time constant: with a runtime plane count the loop compiled to a branchy 4x-unrolled body (ncu: 47 % of all executed
 // instructions of the FFN-w_1 GEMM sat in this function).
 template <int NPL>
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_stride, float x0, float x1, float x2, float x3) {
+__device__ __forceinline__ void store_planes4(plane_t* dst, int64_t plane_stride, float x0, float x1, float x2, float x3) {
 #pragma unroll
   for (int pl = 0; pl < NPL; ++pl) {
-    const __nv_bfloat162 p01 = __floats2bfloat162_rn(x0, x1), p23 = __floats2bfloat162_rn(x2, x3);
     uint2 pk;
-    pk.x = *reinterpret_cast<const uint32_t*>(&p01);
-    pk.y = *reinterpret_cast<const uint32_t*>(&p23);
+    pk.x = pack_planes2(x0, x1);
+    pk.y = pack_planes2(x2, x3);
     *reinterpret_cast<uint2*>(dst) = pk;
     if (pl + 1 < NPL) {
       dst += plane_stride;
-      x0 -= __uint_as_float(pk.x << 16); x1 -= __uint_as_float(pk.x & 0xFFFF0000u);
-      x2 -= __uint_as_float(pk.y << 16); x3 -= __uint_as_float(pk.y & 0xFFFF0000u);
+      const float2 a = unpack_planes2(pk.x), b = unpack_planes2(pk.y);
+      x0 -= a.x; x1 -= a.y; x2 -= b.x; x3 -= b.y;
     }
   }
 }
@@ -98,26 +97,25 @@ __device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_
 // per-head transposed V planes straight from the row-per-lane registers: for a fixed head dim the 32 lanes hold 32
 // consecutive keys, so every 2-byte store instruction covers one 64-byte run
 template <int NPL>
-__device__ __forceinline__ void store_vt16(__nv_bfloat16* dst, int64_t t_pad, int64_t plane, const uint32_t (&r)[16], const float* bias) {
+__device__ __forceinline__ void store_vt16(plane_t* dst, int64_t t_pad, int64_t plane, const uint32_t (&r)[16], const float* bias) {
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
     float x0 = __uint_as_float(r[j]), x1 = __uint_as_float(r[j + 1]);
     if (bias) { x0 += __ldg(bias + j); x1 += __ldg(bias + j + 1); }
-    __nv_bfloat16* d0 = dst + (int64_t)j * t_pad;
+    plane_t* d0 = dst + (int64_t)j * t_pad;
 #pragma unroll
     for (int pl = 0; pl < NPL; ++pl) {
-      const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
-      const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
-      d0[0] = __ushort_as_bfloat16((unsigned short)(hb & 0xFFFFu));
-      d0[t_pad] = __ushort_as_bfloat16((unsigned short)(hb >> 16));
-      if (pl + 1 < NPL) { d0 += plane; x0 -= __uint_as_float(hb << 16); x1 -= __uint_as_float(hb & 0xFFFF0000u); }
+      const uint32_t hb = pack_planes2(x0, x1);
+      d0[0] = __ushort_as_half((unsigned short)(hb & 0xFFFFu));
+      d0[t_pad] = __ushort_as_half((unsigned short)(hb >> 16));
+      if (pl + 1 < NPL) { d0 += plane; const float2 a = unpack_planes2(hb); x0 -= a.x; x1 -= a.y; }
     }
   }
 }
 
 // EPI selects the output kind at compile time so the inner loops carry no runtime branching on it:
 //   EPI_F32    fp32 rows (+ bias, ReLU, up to two residuals; ragged N tail supported)
-//   EPI_PLANES bf16 planes for a following GEMM (+ bias, ReLU)
+//   EPI_PLANES fp16 planes for a following GEMM (+ bias, ReLU)
 //   EPI_ATT    attention operands: scaled q planes / k planes / per-head transposed v planes (+ fp32 v for FSMN)
 constexpr int EPI_F32 = 0, EPI_PLANES = 1, EPI_ATT = 2;
 
@@ -193,13 +191,13 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, uint32_t tmem_a
   float* c_row = (EPI != EPI_PLANES && p.C) ? p.C + rfirst * p.ldc + c4 : nullptr;
   const float* r1_row = (EPI == EPI_F32 && p.r1) ? p.r1 + rfirst * p.ldr1 + c4 : nullptr;
   const float* r2_row = (EPI == EPI_F32 && p.r2) ? p.r2 + rfirst * p.ldr2 + c4 : nullptr;
-  __nv_bfloat16* o_row = EPI == EPI_PLANES ? p.out_planes + rfirst * p.ldo + c4 : nullptr;
-  __nv_bfloat16* q_row = EPI == EPI_ATT ? a.q_planes + rfirst * a.width + c4 : nullptr;
-  __nv_bfloat16* k_row = EPI == EPI_ATT ? a.k_planes + rfirst * a.width + c4 : nullptr;
+  plane_t* o_row = EPI == EPI_PLANES ? p.out_planes + rfirst * p.ldo + c4 : nullptr;
+  plane_t* q_row = EPI == EPI_ATT ? a.q_planes + rfirst * a.width + c4 : nullptr;
+  plane_t* k_row = EPI == EPI_ATT ? a.k_planes + rfirst * a.width + c4 : nullptr;
   const int64_t sc = 8 * p.ldc, s1 = 8 * p.ldr1, s2 = 8 * p.ldr2, so = 8 * p.ldo, sq = 8 * (int64_t)a.width;
   const int64_t plane_o = p.M * p.ldo, plane_q = p.M * (int64_t)a.width;
   const bool c_vec = (p.ldc & 3) == 0;
-  __nv_bfloat16* vt_row = nullptr;
+  plane_t* vt_row = nullptr;
   int64_t vt_plane = 0;
   if (EPI == EPI_ATT) {
     const int64_t rw = row0 + lane;
@@ -247,7 +245,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, uint32_t tmem_a
         pc += sc;
       }
     } else if (EPI == EPI_PLANES) {
-      __nv_bfloat16* po = o_row + col0;
+      plane_t* po = o_row + col0;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
@@ -260,7 +258,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, uint32_t tmem_a
       const bool q_sink = col0 >= a.q0 && col0 < a.q0 + a.width;
       const bool k_sink = col0 >= a.k0 && col0 < a.k0 + a.width;
       if (q_sink || k_sink) {
-        __nv_bfloat16* pq = q_sink ? q_row + (col0 - a.q0) : k_row + (col0 - a.k0);
+        plane_t* pq = q_sink ? q_row + (col0 - a.q0) : k_row + (col0 - a.k0);
         const float qs = q_sink ? a.qscale : 1.0f;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -439,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one_sync()) {          // single elected lane: no waterfall loops around the uniform-datapath TMA / MMA instructions
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+      constexpr uint32_t idesc = make_idesc_f16(TC_BM, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -455,8 +453,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t dw = make_sw128_desc(st + APL * TC_TILE_BYTES_A + c_term_w[t] * TILE_W_BYTES);
 #pragma unroll
             for (int k = 0; k < TC_BK / TC_UK; ++k) {
-              // advance 32 bytes (16 bf16) inside the 128-byte swizzle span: +2 in 16-byte units
-              umma_bf16(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | t | k) != 0 ? 1u : 0u);
+              // advance 32 bytes (16 fp16) inside the 128-byte swizzle span: +2 in 16-byte units
+              umma_f16(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | t | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[stage]);                  // ring slot free once these MMAs retire
@@ -500,7 +498,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int BN = 256;
-  constexpr uint32_t TILE_BYTES = 128 * TC_BK * 2;                 // 16 KB: 128 rows x 64 bf16
+  constexpr uint32_t TILE_BYTES = 128 * TC_BK * 2;                 // 16 KB: 128 rows x 64 fp16
   constexpr uint32_t STAGE_BYTES = 2 * PL * TILE_BYTES;            // A planes + W-half planes of this CTA
   // align to 1024 B WITHOUT leaving the shared address space (a uintptr_t round trip makes every access a generic LD/ST)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -558,7 +556,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN);
+      constexpr uint32_t idesc = make_idesc_f16(256, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = pair; tile < n_tiles; tile += n_pairs) {
@@ -573,7 +571,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint64_t da = make_sw128_desc(st + c_term_a[t] * TILE_BYTES);
             const uint64_t dw = make_sw128_desc(st + (PL + c_term_w[t]) * TILE_BYTES);
 #pragma unroll
-            for (int k = 0; k < TC_BK / TC_UK; ++k) umma_bf16_2sm(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | t | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TC_BK / TC_UK; ++k) umma_f16_2sm(d_tmem, da + 2 * k, dw + 2 * k, idesc, (kb | t | k) != 0 ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[stage]);              // frees the slot in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -606,10 +604,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
-// fp32 rows [rows, cols] (ld) -> bf16 planes [nplanes][rows][cols_pad]; 4 elements per thread.
+// fp32 rows [rows, cols] (ld) -> fp16 planes [nplanes][rows][cols_pad]; 4 elements per thread.
 __global__ void __launch_bounds__(256)
 split_rows_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, int cols_pad, int nplanes,
-                  __nv_bfloat16* __restrict__ planes) {
+                  plane_t* __restrict__ planes) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int c4n = cols_pad >> 2;
   const int64_t total = rows * c4n;
@@ -625,12 +623,12 @@ split_rows_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int c
   float v[4] = {x.x, x.y, x.z, x.w};
   const int64_t plane = rows * cols_pad;
   for (int pl = 0; pl < nplanes; ++pl) {
-    __nv_bfloat16 h[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { h[k] = __float2bfloat16_rn(v[k]); v[k] -= __bfloat162float(h[k]); }
-    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(planes + pl * plane + r * cols_pad + c);
-    dst[0] = __halves2bfloat162(h[0], h[1]);
-    dst[1] = __halves2bfloat162(h[2], h[3]);
+    uint2 pk;
+    pk.x = pack_planes2(v[0], v[1]);
+    pk.y = pack_planes2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(planes + pl * plane + r * cols_pad + c) = pk;
+    const float2 a = unpack_planes2(pk.x), b = unpack_planes2(pk.y);
+    v[0] -= a.x; v[1] -= a.y; v[2] -= b.x; v[3] -= b.y;
   }
 }
 
@@ -650,7 +648,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2D bf16 tensor [rows, cols] (row pitch ld elements), box {64 cols, box_rows}, 128B swizzle.
+// 2D fp16 tensor [rows, cols] (row pitch ld elements), box {64 cols, box_rows}, 128B swizzle.
 // A forward pass encodes ~570 maps over a few dozen distinct (pointer, shape) pairs — the workspace slices and the weight
 // planes are the same every layer and every step — so the encoded descriptors are kept in a small per-thread cache
 // (no locking; a descriptor depends only on the key).
@@ -666,7 +664,7 @@ struct MapKeyHash {
     return (size_t)h;
   }
 };
-int make_bf16_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int make_plane_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   const MapKey key{base, rows, cols, ld, box_rows};
   auto it = cache.find(key);
@@ -686,7 +684,7 @@ int make_bf16_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols
   return FA_OK;
 }
 
-static int planes_for_mode(int mode) { return mode == FA_GEMM_BF16X1 ? 1 : (mode == FA_GEMM_BF16X3 ? 2 : 3); }
+static int planes_for_mode(int mode) { return mode == FA_GEMM_F16X1 ? 1 : (mode == FA_GEMM_F16X3 ? 2 : 3); }
 
 size_t gemm_tc_scratch_bytes(int64_t max_rows, int max_k, int mode) {
   if (mode == FA_GEMM_F32_SIMT) return 0;
@@ -747,8 +745,8 @@ static bool use_2cta() {
 }
 
 // A planes already split: a_planes [npl][M][Kp]
-int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
-                          const float* r2, int64_t ld2, float* y, int64_t ldy, __nv_bfloat16* out_planes, int64_t ldo,
+int gemm_tc_planes_launch(const plane_t* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
+                          const float* r2, int64_t ld2, float* y, int64_t ldy, plane_t* out_planes, int64_t ldo,
                           int mode, cudaStream_t st, const AttnSinks* att) {
   if (M <= 0) return FA_OK;
   if (!lin.w_planes || !a_planes) return FA_ERR_ARG;
@@ -762,11 +760,11 @@ int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLine
   if (use_2cta() && npl <= 2 && N % 256 == 0 && M >= 256) {
     // cta_group::2: 256 x 256 pair tiles (see gemm_tc2_kernel)
     CUtensorMap ma2, mw2;
-    FA_RETURN_IF_ERR(make_bf16_map(&ma2, a_planes, (uint64_t)M * npl, (uint64_t)Kp, (uint64_t)Kp, 128));
-    FA_RETURN_IF_ERR(make_bf16_map(&mw2, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, 128));
+    FA_RETURN_IF_ERR(make_plane_map(&ma2, a_planes, (uint64_t)M * npl, (uint64_t)Kp, (uint64_t)Kp, 128));
+    FA_RETURN_IF_ERR(make_plane_map(&mw2, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, 128));
     TcParams p2;
     p2.M = M; p2.N = N; p2.Kp = Kp; p2.a_plane_rows = M; p2.w_plane_rows = N;
-    p2.n_terms = mode == FA_GEMM_BF16X1 ? 1 : 3;
+    p2.n_terms = mode == FA_GEMM_F16X1 ? 1 : 3;
     p2.relu = relu; p2.bias = lin.b; p2.r1 = r1; p2.ldr1 = ld1; p2.r2 = r2; p2.ldr2 = ld2; p2.C = y; p2.ldc = ldy;
     p2.out_planes = out_planes; p2.ldo = ldo; p2.out_nplanes = npl;
     p2.tiles_m = (int)((M + 255) / 256); p2.tiles_n = N / 256;
@@ -777,11 +775,11 @@ int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLine
   const bool wide = (npl <= 2) && (N % 256 == 0) && (N >= 1024);
   const int BN = wide ? 256 : 128;
   CUtensorMap ma, mw;
-  FA_RETURN_IF_ERR(make_bf16_map(&ma, a_planes, (uint64_t)M * npl, (uint64_t)Kp, (uint64_t)Kp, TC_BM));
-  FA_RETURN_IF_ERR(make_bf16_map(&mw, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, wide ? 128 : BN));
+  FA_RETURN_IF_ERR(make_plane_map(&ma, a_planes, (uint64_t)M * npl, (uint64_t)Kp, (uint64_t)Kp, TC_BM));
+  FA_RETURN_IF_ERR(make_plane_map(&mw, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, wide ? 128 : BN));
   TcParams p;
   p.M = M; p.N = N; p.Kp = Kp; p.a_plane_rows = M; p.w_plane_rows = N;
-  p.n_terms = mode == FA_GEMM_BF16X1 ? 1 : (mode == FA_GEMM_BF16X3 ? 3 : 6);
+  p.n_terms = mode == FA_GEMM_F16X1 ? 1 : (mode == FA_GEMM_F16X3 ? 3 : 6);
   p.relu = relu; p.bias = lin.b; p.r1 = r1; p.ldr1 = ld1; p.r2 = r2; p.ldr2 = ld2; p.C = y; p.ldc = ldy;
   p.out_planes = out_planes; p.ldo = ldo; p.out_nplanes = npl;
   p.tiles_m = (int)((M + TC_BM - 1) / TC_BM); p.tiles_n = (N + BN - 1) / BN;
@@ -796,7 +794,7 @@ int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLine
   }
 }
 
-int split_rows_launch(const float* x, int64_t ldx, int64_t rows, int cols, int cols_pad, int nplanes, __nv_bfloat16* planes,
+int split_rows_launch(const float* x, int64_t ldx, int64_t rows, int cols, int cols_pad, int nplanes, plane_t* planes,
                       cudaStream_t st) {
   if (rows <= 0) return FA_OK;
   if ((ldx & 3) || (((uintptr_t)x) & 15) || (cols_pad & 3)) return FA_ERR_UNSUPPORTED;
@@ -809,11 +807,11 @@ int split_rows_launch(const float* x, int64_t ldx, int64_t rows, int cols, int c
 int gemm_tc_launch(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
                    const float* r2, int64_t ld2, float* y, int64_t ldy, int mode, Arena* scratch, cudaStream_t st) {
   if (rows <= 0) return FA_OK;
-  if (mode != FA_GEMM_BF16X1 && mode != FA_GEMM_BF16X3 && mode != FA_GEMM_BF16X6) return FA_ERR_ARG;
+  if (mode != FA_GEMM_F16X1 && mode != FA_GEMM_F16X3 && mode != FA_GEMM_F16X6) return FA_ERR_ARG;
   if (!scratch) return FA_ERR_WORKSPACE;
   const int npl = planes_for_mode(mode);
   Arena local(scratch->base, scratch->cap);   // scratch is reused by every call (stream ordered)
-  __nv_bfloat16* planes = local.take<__nv_bfloat16>((size_t)npl * rows * lin.in_pad);
+  plane_t* planes = local.take<plane_t>((size_t)npl * rows * lin.in_pad);
   if (!local.ok()) return FA_ERR_WORKSPACE;
   FA_RETURN_IF_ERR(split_rows_launch(x, ldx, rows, lin.in_f, lin.in_pad, npl, planes, st));
   return gemm_tc_planes_launch(planes, rows, lin, relu, r1, ld1, r2, ld2, y, ldy, nullptr, 0, mode, st, nullptr);

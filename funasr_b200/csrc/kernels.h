@@ -2,16 +2,19 @@
 #pragma once
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace fa { typedef __half plane_t; }   // 16-bit operand plane element (tc_common.cuh)
 
 namespace fa {
 
-// y (fp32) and/or planes (bf16 [nplanes][rows][cols_pad], the A operand of a following tcgen05 GEMM)
+// y (fp32) and/or planes (fp16 [nplanes][rows][cols_pad], the A operand of a following tcgen05 GEMM)
 int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, const float* pe_inv, float xscale,
-                     int rows_per_batch, cudaStream_t st, __nv_bfloat16* planes = nullptr, int nplanes = 0, int cols_pad = 0);
+                     int rows_per_batch, cudaStream_t st, plane_t* planes = nullptr, int nplanes = 0, int cols_pad = 0);
 int gemm_f32_launch(const float* A, int64_t lda, int64_t M, const float* W, int N, int K, const float* bias, int relu,
                     const float* r1, int64_t ldr1, const float* r2, int64_t ldr2, float* C, int64_t ldc,
                     cudaStream_t st);
-// tcgen05 bf16-split GEMM (gemm_tc.cu)
+// tcgen05 fp16-split GEMM (gemm_tc.cu)
 size_t gemm_tc_scratch_bytes(int64_t max_rows, int max_k, int mode);
 int gemm_tc_launch(const float* x, int64_t ldx, int64_t rows, const FaLinear& lin, int relu, const float* r1,
                    int64_t ld1, const float* r2, int64_t ld2, float* y, int64_t ldy, int mode, Arena* scratch,
@@ -26,23 +29,23 @@ struct AttnSinks {
   int npl = 2;                 // planes written
   int t_rows = 1, t_pad = 64;  // rows per utterance (v rows = keys), padded key pitch of the transposed planes
   float qscale = 1.f;
-  __nv_bfloat16* q_planes = nullptr;   // [npl][M][width]
-  __nv_bfloat16* k_planes = nullptr;   // [npl][M][width]
-  __nv_bfloat16* vt_planes = nullptr;  // [npl][B*width][t_pad]
+  plane_t* q_planes = nullptr;   // [npl][M][width]
+  plane_t* k_planes = nullptr;   // [npl][M][width]
+  plane_t* vt_planes = nullptr;  // [npl][B*width][t_pad]
 };
-// tcgen05 attention (attention_tc.cu); ctx fp32 and/or bf16 planes [npl][B*tq][ldp]
-int attention_tc_planes_launch(const __nv_bfloat16* qp, const __nv_bfloat16* kp, const __nv_bfloat16* vt, const int32_t* key_lens,
-                               int batch, int heads, int tq, int tk, float* ctx, int64_t ldc, __nv_bfloat16* ctx_planes,
+// tcgen05 attention (attention_tc.cu); ctx fp32 and/or fp16 planes [npl][B*tq][ldp]
+int attention_tc_planes_launch(const plane_t* qp, const plane_t* kp, const plane_t* vt, const int32_t* key_lens,
+                               int batch, int heads, int tq, int tk, float* ctx, int64_t ldc, plane_t* ctx_planes,
                                int64_t ldp, int out_nplanes, int mode, cudaStream_t st, int kv_shared = 0);
 size_t attention_tc_scratch_bytes(int batch, int heads, int tq, int tk, int mode);
 int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                         const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
-                        __nv_bfloat16* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st,
+                        plane_t* ctx_planes, int64_t ldp, int out_nplanes, int mode, Arena* scratch, cudaStream_t st,
                         int kv_shared = 0);   // kv_shared: k / v hold ONE batch entry that every utterance attends over
-int gemm_tc_planes_launch(const __nv_bfloat16* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
-                          const float* r2, int64_t ld2, float* y, int64_t ldy, __nv_bfloat16* out_planes, int64_t ldo,
+int gemm_tc_planes_launch(const plane_t* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
+                          const float* r2, int64_t ld2, float* y, int64_t ldy, plane_t* out_planes, int64_t ldo,
                           int mode, cudaStream_t st, const AttnSinks* att = nullptr);
-int split_rows_launch(const float* x, int64_t ldx, int64_t rows, int cols, int cols_pad, int nplanes, __nv_bfloat16* planes,
+int split_rows_launch(const float* x, int64_t ldx, int64_t rows, int cols, int cols_pad, int nplanes, plane_t* planes,
                       cudaStream_t st);
 int attention_f32_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                          const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,

@@ -2,20 +2,20 @@
 // held in registers (two-pass mean / variance in fp32), float4 loads and stores.
 // Optional fused prologue for the first encoder layer: x*sqrt(d_model) + sinusoidal position encoding
 // (SANMEncoder.forward encoder.py:409,428; SinusoidalPositionEncoder embedding.py:396-432).
-// Optional fused epilogue for the tensor-core path: the normalised row is written as bf16 planes (hi, mid, lo) — the A
+// Optional fused epilogue for the tensor-core path: the normalised row is written as fp16 planes (hi, mid, lo) — the A
 // operand of the following tcgen05 GEMM — instead of / in addition to fp32.
 // HBM-bound: algorithmic bytes = 8 B per element (read + write).
 #include "common.cuh"
-#include <cuda_bf16.h>
+#include "tc_common.cuh"
 
 namespace fa {
 
-template <int NV, int NPL>  // NV: float4 per lane (row length <= 128*NV); NPL: bf16 planes written (0 = fp32 output only)
+template <int NV, int NPL>  // NV: float4 per lane (row length <= 128*NV); NPL: fp16 planes written (0 = fp32 output only)
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ g,
                  const float* __restrict__ bta, float eps, float* y,   // x may alias y (in-place)
                  const float* __restrict__ pe_inv, float xscale, int rows_per_batch,
-                 __nv_bfloat16* __restrict__ planes, int nplanes, int cols_pad) {
+                 plane_t* __restrict__ planes, int nplanes, int cols_pad) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   pdl_wait();
@@ -77,34 +77,31 @@ layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ 
       if (yr) yr[c4] = o;
       if (NPL > 0) {
         float e0 = o.x, e1 = o.y, e2 = o.z, e3 = o.w;
-        __nv_bfloat16* dst = planes + row * cols_pad + 4 * c4;
+        plane_t* dst = planes + row * cols_pad + 4 * c4;
 #pragma unroll
-        for (int pl = 0; pl < NPL; ++pl) {           // packed cvt.rn.bf16x2 (ALU pipe), bf16 -> fp32 by shifts
-          const __nv_bfloat162 p01 = __floats2bfloat162_rn(e0, e1), p23 = __floats2bfloat162_rn(e2, e3);
+        for (int pl = 0; pl < NPL; ++pl) {           // packed cvt.rn.satfinite.f16x2 per plane (tc_common.cuh: operand planes)
           uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&p01);
-          pk.y = *reinterpret_cast<const uint32_t*>(&p23);
+          pk.x = pack_planes2(e0, e1);
+          pk.y = pack_planes2(e2, e3);
           *reinterpret_cast<uint2*>(dst) = pk;
           if (pl + 1 < NPL) {
             dst += plane_elems;
-            e0 -= __uint_as_float(pk.x << 16); e1 -= __uint_as_float(pk.x & 0xFFFF0000u);
-            e2 -= __uint_as_float(pk.y << 16); e3 -= __uint_as_float(pk.y & 0xFFFF0000u);
+            const float2 a = unpack_planes2(pk.x), b = unpack_planes2(pk.y);
+            e0 -= a.x; e1 -= a.y; e2 -= b.x; e3 -= b.y;
           }
         }
       }
     } else if (NPL > 0 && 4 * c4 < cols_pad) {         // zero the K padding (e.g. 560 -> 576)
 #pragma unroll
       for (int pl = 0; pl < NPL; ++pl) {
-        __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(planes + pl * plane_elems + row * cols_pad + 4 * c4);
-        d2[0] = __halves2bfloat162(__float2bfloat16_rn(0.f), __float2bfloat16_rn(0.f));
-        d2[1] = d2[0];
+        *reinterpret_cast<uint2*>(planes + pl * plane_elems + row * cols_pad + 4 * c4) = make_uint2(0u, 0u);
       }
     }
   }
 }
 
 int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, const float* pe_inv, float xscale,
-                     int rows_per_batch, cudaStream_t st, __nv_bfloat16* planes, int nplanes, int cols_pad) {
+                     int rows_per_batch, cudaStream_t st, plane_t* planes, int nplanes, int cols_pad) {
   if (rows <= 0) return FA_OK;
   if (!x || (!y && !planes) || !nm.g || !nm.b) return FA_ERR_ARG;
   const int n = nm.n;

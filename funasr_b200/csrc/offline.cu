@@ -4,7 +4,7 @@
 // runtime/onnxruntime/src/paraformer.cpp).  No Python, no torch: weights come from one flat file written by
 // funasr_b200/pack.py (tensors under FunASR's own state_dict names), device memory from cudaMalloc.
 //
-//   fa_offline_init         model file -> handle (weights to HBM, bf16 planes for the tcgen05 GEMMs)
+//   fa_offline_init         model file -> handle (weights to HBM, fp16 planes for the tcgen05 GEMMs)
 //   fa_offline_infer        batch of host PCM buffers (f32 in [-1,1] or s16le) -> result (greedy token ids per utterance)
 //   fa_offline_result_*     accessors;  fa_offline_free_result / fa_offline_uninit
 // The tokenizer (ids -> text) stays with the caller, like every other entry point of this ABI.
@@ -135,7 +135,7 @@ struct Builder {
       void* planes = nullptr;
       if (cudaMalloc(&planes, (size_t)3 * L.out_f * L.in_pad * 2) != cudaSuccess) { ok = false; set_err("cudaMalloc planes"); return L; }
       m.owned.push_back(planes);
-      if (fa_split_bf16(L.w, L.in_f, L.out_f, L.in_f, L.in_pad, planes, m.st) != FA_OK) { ok = false; set_err("fa_split_bf16 failed"); }
+      if (fa_split_planes(L.w, L.in_f, L.out_f, L.in_f, L.in_pad, planes, m.st) != FA_OK) { ok = false; set_err("fa_split_planes failed"); }
       L.w_planes = planes;
     }
     return L;
@@ -207,7 +207,7 @@ extern "C" const char* fa_offline_last_error(void) { return g_err.c_str(); }
 extern "C" void* fa_offline_init(const char* model_file, int32_t device, int32_t gemm_mode) {
   g_err.clear();
   if (!model_file) { set_err("model_file is NULL"); return nullptr; }
-  if (gemm_mode != FA_GEMM_F32_SIMT && gemm_mode != FA_GEMM_BF16X1 && gemm_mode != FA_GEMM_BF16X3 && gemm_mode != FA_GEMM_BF16X6) {
+  if (gemm_mode != FA_GEMM_F32_SIMT && gemm_mode != FA_GEMM_F16X1 && gemm_mode != FA_GEMM_F16X3 && gemm_mode != FA_GEMM_F16X6) {
     set_err("bad gemm_mode"); return nullptr;
   }
   if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_err("no such CUDA device (this library has no CPU path)"); return nullptr; }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -63,8 +64,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -75,10 +76,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc]^T: the A operand (M=128 rows = TMEM lanes, K-major: 16 bf16 = 8 consecutive 32-bit
+// D[tmem] (+)= A[tmem] * B[smem desc]^T: the A operand (M=128 rows = TMEM lanes, K-major: 16 fp16 = 8 consecutive 32-bit
 // columns per K=16 step, element 2j in the low half of column j) is read from tensor memory, so only B costs shared-memory
 // bandwidth (attention: Q and P planes live in TMEM)
-__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -118,6 +119,23 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ operand planes
+// A 16-bit "plane" element of the split x = p0 + p1 (+ p2).  Planes are IEEE fp16 (11-bit significands): two planes carry ~22
+// bits of x, so the three products hi*hi + hi*lo + lo*hi of the x3 mode are good to ~2^-22 relative — 64x tighter than the same
+// three products on fp16 planes (8-bit significands, ~2^-16), at the same tcgen05 kind::f16 rate.  Round 1 used fp16 planes; the
+// B=64 full-depth parity run of round 2 showed their noise (log-prob error up to 9e-3 absolute) flipping ~1 greedy id per 1000
+// tokens at near-ties, while every GEMM operand of this path is LayerNorm-, ReLU- or softmax-bounded and sits far inside the fp16
+// range (conversions saturate at +-65504 instead of producing inf; values below 2^-14 go subnormal with 6e-8 absolute spacing).
+typedef __half plane_t;
+__device__ __forceinline__ uint32_t pack_planes2(float e0, float e1) {      // {e0 -> low half, e1 -> high half}, round to nearest, saturating
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_planes2(uint32_t p) { return __half22float2(*reinterpret_cast<const __half2*>(&p)); }
+__device__ __forceinline__ plane_t to_plane(float x) { return __ushort_as_half((unsigned short)(pack_planes2(x, 0.f) & 0xFFFFu)); }
+__device__ __forceinline__ float plane_to_float(plane_t h) { return __half2float(h); }
+
 // K-major, SWIZZLE_128B shared-memory operand descriptor (tile rows at 128-byte pitch, 8-row groups 1024 B apart).
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -128,9 +146,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                             // layout: SWIZZLE_128B               [61,64)
   return d;
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, shape M x N.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A / B format fp16 (bits 7-9 / 10-12 = 0; fp16 would be 1), both
+// K-major, shape M x N.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 
@@ -159,7 +178,7 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) 
 }
 // M=256 MMA across the CTA pair (issued by the leader only): A/B halves are read from both CTAs' shared memory at the
 // same offsets, D rows 0-127 land in the leader's TMEM, rows 128-255 in the peer's.
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -176,7 +195,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-// host: 2D bf16 tensor map [rows, cols] (row pitch ld elements), box {64 cols, box_rows}, SWIZZLE_128B (gemm_tc.cu)
-int make_bf16_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+// host: 2D fp16 tensor map [rows, cols] (row pitch ld elements), box {64 cols, box_rows}, SWIZZLE_128B (gemm_tc.cu)
+int make_plane_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 }  // namespace fa

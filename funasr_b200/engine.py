@@ -69,7 +69,7 @@ class FrontendEngine:
 
 
 class _EngineBase:
-    """Weight packing (device copies, bf16 planes, ctypes structs), workspace and the encoder call."""
+    """Weight packing (device copies, fp16 planes, ctypes structs), workspace and the encoder call."""
 
     def _init_base(self, state, device, gemm_mode, ln_eps):
         self.lib = _abi.load()
@@ -92,7 +92,7 @@ class _EngineBase:
         if self.mode != _abi.GEMM_F32_SIMT:
             planes = torch.empty((3, out_f, in_pad), dtype=torch.bfloat16, device=self.device)
             st = torch.cuda.current_stream(self.device).cuda_stream
-            _abi.check(self.lib.fa_split_bf16(w.data_ptr(), in_f, out_f, in_f, in_pad, planes.data_ptr(), st), "fa_split_bf16")
+            _abi.check(self.lib.fa_split_planes(w.data_ptr(), in_f, out_f, in_f, in_pad, planes.data_ptr(), st), "fa_split_planes")
             self._keep.append(planes)
         return _abi.FaLinear(w.data_ptr(), _ptr(b), _ptr(planes), out_f, in_f, in_pad, 0)
 
@@ -163,11 +163,14 @@ class ParaformerEngine(_EngineBase):
 
     def __init__(self, state: Dict[str, torch.Tensor], cfg: ParaformerConfig, device, gemm_mode: str = "fp32",
                  prefix_enc="encoder.", prefix_pred="predictor.", prefix_dec="decoder.", contextual: bool = False, bicif: bool = False,
-                 smooth_factor2: float = 0.25, noise_threshold2: float = 0.01):
+                 smooth_factor2: float = 0.25, noise_threshold2: float = 0.01, seaco: bool = False, no_bias: int = 8377):
         self._init_base(state, device, gemm_mode, cfg.ln_eps)
         self.cfg = cfg
         self.contextual = contextual
-        self.bicif = bicif
+        self.bicif = bicif or seaco          # SeacoParaformer derives from BiCifParaformer (CifPredictorV3 + timestamp head)
+        bicif = self.bicif
+        self.seaco = seaco
+        self.no_bias = int(no_bias)
         g, lin, norm = self._g, self._lin, self._norm
         D = cfg.d_model
         # FSMN tap counts come from each stack's own weights [512, 1, K]: encoder and decoder kernel_size are independent
@@ -237,6 +240,27 @@ class ParaformerEngine(_EngineBase):
         dec_layer(self.dec.last, prefix_dec + "decoders3.0", full=False)
         self.dec.after_norm = norm(prefix_dec + "after_norm")
         self.dec.output = lin(prefix_dec + "output_layer")
+        if seaco:   # SeacoParaformer (seaco_paraformer/model.py:50-120): hotword LSTM, SeACo decoder over the hotword memory, hotword_output_layer
+            sp = "seaco_decoder."
+            n_s = 0
+            while (sp + "decoders.%d.norm1.weight" % n_s) in state:
+                n_s += 1
+            self.seaco_layers = (_abi.FaDecLayer * n_s)()
+            for i in range(n_s):
+                dec_layer(self.seaco_layers[i], sp + "decoders.%d" % i)
+            self.seaco_dec = _abi.FaDecoder()
+            self.seaco_dec.layers, self.seaco_dec.n_layers, self.seaco_dec.heads = self.seaco_layers, n_s, cfg.heads
+            self.seaco_dec.fsmn_k = int(state[sp + "decoders.0.self_attn.fsmn_block.weight"].shape[-1])
+            self.seaco_dec.vocab, self.seaco_dec.has_bias = 0, 0
+            dec_layer(self.seaco_dec.last, sp + "decoders3.0", full=False)
+            self.seaco_dec.after_norm = norm(sp + "after_norm")
+            self.hw_out = lin("hotword_output_layer")
+            # the hotword encoder (Embedding + 2-layer LSTM over a handful of short token sequences) is O(#hotwords), independent of
+            # the audio: torch (cuDNN, TF32 off), as the scope contract allows for the hotword side
+            self.hw_embed_table = g(prefix_dec + "embed.0.weight")
+            self.hw_lstm = torch.nn.LSTM(D, D, 2, batch_first=True).to(self.device)
+            self.hw_lstm.load_state_dict({k[len("bias_encoder."):]: v for k, v in state.items() if k.startswith("bias_encoder.")})
+            self.hw_lstm.eval().requires_grad_(False)
         torch.cuda.current_stream(self.device).synchronize()
         self._state = None
 
@@ -265,7 +289,7 @@ class ParaformerEngine(_EngineBase):
         """CifPredictorV3.get_upsample_timestamp (bicif_paraformer/cif_predictor.py:300-352): enc [B,T,512], lens [B] i32,
         token_num [B] i32 (rounded) -> (us_alphas [B,3T], us_peaks [B,3T]).  ConvTranspose1d upsampling = one GEMM of this library,
         the BLSTM = its input projections as one tcgen05 GEMM + this library's persistent weight-stationary recurrence
-        (fa_blstm_forward_tc: warp-level mma.sync bf16x3, not tcgen05 — the per-step product is only 64x32x512; or the exact fp32
+        (fa_blstm_forward_tc: warp-level mma.sync on bf16 hi/lo planes, not tcgen05 — the per-step product is only 64x32x512; or the exact fp32
         fa_blstm_forward with FUNASR_B200_LSTM=simt), the alpha head / rescale / fire scan is fa_cif_upsample_alphas."""
         if not self.bicif:
             raise _abi.FunasrB200Error("engine was not built with bicif=True")
@@ -341,6 +365,98 @@ class ParaformerEngine(_EngineBase):
             tok_lens.data_ptr(), n_max, ids.data_ptr(), best.data_ptr(), _ptr(logp), 1, self.mode, ws.data_ptr(), ws.numel(),
             self._stream()), "fa_paraformer_decoder_forward")
         return ids, best, logp
+
+    # ------------------------------------------------------------------------------------------ SeacoParaformer
+    @torch.no_grad()
+    def seaco_hotword_representation(self, hw_list) -> torch.Tensor:
+        """_hotword_representation (seaco_paraformer/model.py:384-416): decoder.embed -> 2-layer LSTM over the packed padded
+        batch -> each hotword's output at its last token: [n_hw, 512]."""
+        lens = [len(h) for h in hw_list]
+        pad = torch.zeros((len(hw_list), max(lens)), dtype=torch.long, device=self.device)
+        for i, h in enumerate(hw_list):
+            pad[i, : len(h)] = torch.tensor(h, device=self.device)
+        emb = torch.nn.functional.embedding(pad, self.hw_embed_table)
+        packed = torch.nn.utils.rnn.pack_padded_sequence(emb, torch.tensor(lens, dtype=torch.int64), batch_first=True, enforce_sorted=False)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            out, _ = self.hw_lstm(packed)
+        out = torch.nn.utils.rnn.pad_packed_sequence(out, batch_first=True)[0]
+        return out[torch.arange(len(hw_list), device=self.device), torch.tensor(lens, device=self.device) - 1].contiguous()
+
+    def _seaco_stack(self, memory, x, ld_x_rows, tok, B, n_max, n_run, finish, hidden=None, attn=None):
+        n_hw = memory.shape[0]
+        mem_lens = torch.full((B,), n_hw, dtype=torch.int32, device=self.device)
+        ws = self._workspace(self.lib.fa_sanm_decoder_stack_workspace_bytes(B, n_hw, n_max, self.mode))
+        _abi.check(self.lib.fa_sanm_decoder_stack_forward(
+            C.byref(self.seaco_dec), memory.data_ptr(), mem_lens.data_ptr(), 1, B, n_hw, x.data_ptr(), ld_x_rows, tok.data_ptr(), n_max,
+            n_run, finish, _ptr(hidden), _ptr(attn), self.mode, ws.data_ptr(), ws.numel(), self._stream()), "fa_sanm_decoder_stack_forward")
+
+    def seaco_decode(self, enc, enc_lens, acoustic, tok, n_max, hw_list, nfilter: int = 50, want_logp: bool = False):
+        """_seaco_decode_with_ASF (seaco_paraformer/model.py:271-382) + arg-max: -> (ids [B,n_max] i32, best logp, taps)."""
+        if not self.seaco:
+            raise _abi.FunasrB200Error("engine was not built with seaco=True")
+        B, T, D = enc.shape
+        V = self.cfg.vocab
+        new = lambda *shape, dt=torch.float32: torch.empty(shape, dtype=dt, device=self.device)
+        dec_ids, dec_best, hidden = new(B, n_max, dt=torch.int32), new(B, n_max), new(B, n_max, D)
+        dec_logp = new(B, n_max, V) if want_logp else None
+        ws = self._workspace(self.lib.fa_paraformer_decoder_workspace_bytes_hw(B, T, n_max, V, self.mode, 0))
+        _abi.check(self.lib.fa_paraformer_decoder_forward_hidden(
+            C.byref(self.dec), enc.data_ptr(), enc_lens.data_ptr(), B, T, acoustic.data_ptr(), acoustic.shape[1], tok.data_ptr(), n_max,
+            dec_ids.data_ptr(), dec_best.data_ptr(), _ptr(dec_logp), 1, hidden.data_ptr(), self.mode, ws.data_ptr(), ws.numel(),
+            self._stream()), "fa_paraformer_decoder_forward_hidden")
+        taps = {"dec_hidden": hidden}
+        if hw_list is None:                                   # model.py:381-382: plain decoder distribution
+            return dec_ids, dec_best, dict(taps, merged=dec_logp)
+        selected = self.seaco_hotword_representation(hw_list)
+        taps["hw_selected_all"] = selected
+        n_hw = selected.shape[0]
+        if 0 < nfilter < n_hw:                                # ASF (model.py:320-343): keep the hotwords utterance 0 attends to most
+            probs = new(self.seaco_dec.heads, n_max, n_hw)
+            self._seaco_stack(selected, hidden, n_max, tok, 1, n_max, self.seaco_dec.n_layers, 0, attn=probs)
+            scores = probs.cpu().sum(0).sum(0)                # the reference's own reduction order, on the host (hotword_scores[0].sum(0).sum(0))
+            picked = torch.topk(scores, min(nfilter, n_hw - 1))[1].tolist() + [len(hw_list) - 1]
+            selected = selected[torch.tensor(picked, device=self.device)].contiguous()
+            taps["asf_picked"] = picked
+        taps["hw_selected"] = selected
+        cif_att, dec_att = new(B, n_max, D), new(B, n_max, D)
+        self._seaco_stack(selected, acoustic, acoustic.shape[1], tok, B, n_max, self.seaco_dec.n_layers, 1, hidden=cif_att)
+        self._seaco_stack(selected, hidden, n_max, tok, B, n_max, self.seaco_dec.n_layers, 1, hidden=dec_att)
+        dha_ids, dha_best = new(B, n_max, dt=torch.int32), new(B, n_max)
+        dha_logp = new(B, n_max, V) if want_logp else None
+        rows = B * n_max
+        ws = self._workspace(self.lib.fa_linear_argmax_workspace_bytes(rows, V, self.mode))
+        _abi.check(self.lib.fa_linear_argmax(C.byref(self.hw_out), cif_att.data_ptr(), dec_att.data_ptr(), rows, dha_ids.data_ptr(),
+                                             dha_best.data_ptr(), _ptr(dha_logp), self.mode, ws.data_ptr(), ws.numel(), self._stream()),
+                   "fa_linear_argmax")
+        ids, best = new(B, n_max, dt=torch.int32), new(B, n_max)
+        merged = new(B, n_max, V) if want_logp else None
+        _abi.check(self.lib.fa_seaco_merge(dec_ids.data_ptr(), dec_best.data_ptr(), dha_ids.data_ptr(), dha_best.data_ptr(), rows, self.no_bias,
+                                           ids.data_ptr(), best.data_ptr(), _ptr(dec_logp), _ptr(dha_logp), _ptr(merged), V, self._stream()),
+                   "fa_seaco_merge")
+        taps.update(merged=merged, dha_pred=dha_logp, dha_ids=dha_ids)
+        return ids, best, taps
+
+    def forward_feats_seaco(self, feats: torch.Tensor, lens: torch.Tensor, hw_list, nfilter: int = 50, want_taps: bool = False,
+                            sos=1, eos=2, blank=0):
+        """SeacoParaformer.inference (model.py:422-581) from features to greedy ids."""
+        enc = self._encode(self.enc, feats, lens, self.cfg.d_model)
+        acoustic, tok, alphas, peaks = self.predict(enc, lens)
+        tok_host = tok.cpu()
+        n_max = int(tok_host.max()) if tok_host.numel() else 0
+        out = {"token_num": tok_host, "alphas": alphas, "peaks": peaks, "enc_dev": enc, "lens_dev": lens, "tok_dev": tok}
+        if want_taps:
+            out.update(enc=enc, acoustic=acoustic)
+        if n_max < 1:
+            out["ids"] = [[] for _ in range(feats.shape[0])]
+            return out
+        ids, best, taps = self.seaco_decode(enc, lens, acoustic, tok, n_max, hw_list, nfilter, want_logp=want_taps)
+        fids, flens = self.greedy_filter(ids, tok, sos, eos, blank)
+        fids_h, flens_h = fids.cpu(), flens.cpu()
+        out["ids"] = [fids_h[b, : int(flens_h[b])].tolist() for b in range(fids_h.shape[0])]
+        out["ids_dev"], out["ids_lens_dev"] = fids, flens
+        if want_taps:
+            out.update(taps)
+        return out
 
     def greedy_filter(self, ids: torch.Tensor, tok_lens: torch.Tensor, sos=1, eos=2, blank=0, out: Optional[tuple] = None):
         B, n_max = ids.shape

@@ -373,6 +373,10 @@ class ParaformerB200(nn.Module):
             meta_data["batch_data_time"] = sum(num_lfr_frames(n) for n in wl) * frontend.frame_shift * frontend.lfr_n / 1000
         return speech, lens
 
+    def _forward(self, eng, speech, lens, kwargs):
+        """features -> greedy ids; subclasses with a different decode (SeACo) override this."""
+        return eng.forward_feats(speech, lens, sos=self.sos, eos=self.eos, blank=self.blank_id)
+
     def infer_ids_device(self, data_in, frontend=None, **kwargs):
         """The hot path of inference() with the result left ON THE DEVICE: (ids [B, n] int32 padded with -1, lens [B] int32) —
         what funasr_b200.sharding.ShardedRunner exchanges between GPUs (no per-utterance host lists on the way)."""
@@ -394,7 +398,7 @@ class ParaformerB200(nn.Module):
         meta_data = {}
         eng = self.engine(device)
         speech, lens = self._features(data_in, data_lengths, frontend, device, kwargs, meta_data)
-        out = eng.forward_feats(speech, lens, sos=self.sos, eos=self.eos, blank=self.blank_id)
+        out = self._forward(eng, speech, lens, kwargs)
         if kwargs.get("_keep_taps"):
             self._last_out = out                  # BiCifParaformerB200 reads enc / lens / token counts for its timestamp head
         ids = out["ids"]
@@ -685,3 +689,87 @@ class BiCifParaformerB200(ParaformerB200):
             r["timestamp"] = stamp
         self._last_out = None
         return results, meta_data
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SeacoParaformer (the `paraformer-zh` default alias)
+# ------------------------------------------------------------------------------------------------------------------
+class _SeacoDecoderHolder(_ParamHolder):
+    """Parameter container for the SeACo decoder: ParaformerSANMDecoder(use_output_layer=False, wo_input_layer=True)
+    (seaco_paraformer/model.py:100-110) — `decoders.{i}` (att_layer_num layers), `decoders3.0`, `after_norm`."""
+
+    def __init__(self, attention_heads: int = 4, linear_units: int = 1024, num_blocks: int = 4, att_layer_num: int = 6, kernel_size: int = 21,
+                 sanm_shfit: int = 0, **kwargs):
+        super().__init__()
+        if attention_heads != 4 or sanm_shfit != 0 or linear_units > 2048 or att_layer_num < 6:
+            raise _abi.FunasrB200Error("the SeACo decoder supports 4 heads, sanm_shfit=0, linear_units <= 2048, att_layer_num >= 6 "
+                                       "(forward_asf6 addresses decoders[0..5], paraformer/decoder.py:507-512)")
+        self.ffn, self.layers, self.kernel_size = linear_units, att_layer_num, kernel_size
+        self._build()
+
+    def _specs(self):
+        D, F, K = 512, self.ffn, self.kernel_size
+        s = {"after_norm.weight": (D,), "after_norm.bias": (D,)}
+
+        def ffn(p):
+            s[p + ".feed_forward.w_1.weight"] = (F, D)
+            s[p + ".feed_forward.w_1.bias"] = (F,)
+            s[p + ".feed_forward.w_2.weight"] = (D, F)
+            s[p + ".feed_forward.norm.weight"] = (F,)
+            s[p + ".feed_forward.norm.bias"] = (F,)
+
+        for i in range(self.layers):
+            p = "decoders.%d" % i
+            ffn(p)
+            s[p + ".self_attn.fsmn_block.weight"] = (D, 1, K)
+            for nme, shp in (("linear_q", (D, D)), ("linear_k_v", (2 * D, D)), ("linear_out", (D, D))):
+                s[p + ".src_attn.%s.weight" % nme] = shp
+                s[p + ".src_attn.%s.bias" % nme] = (shp[0],)
+            for n in ("norm1", "norm2", "norm3"):
+                s[p + ".%s.weight" % n] = (D,)
+                s[p + ".%s.bias" % n] = (D,)
+        ffn("decoders3.0")
+        s["decoders3.0.norm1.weight"] = (D,)
+        s["decoders3.0.norm1.bias"] = (D,)
+        return s
+
+
+@register("model_classes", "SeacoParaformerB200")
+class SeacoParaformerB200(BiCifParaformerB200):
+    """Drop-in for SeacoParaformer's greedy inference with hotwords (funasr/models/seaco_paraformer/model.py:50-581): the BiCif path
+    (CifPredictorV3 tokens + upsampled timestamps) with `_seaco_decode_with_ASF` in place of the plain decoder call — decoder
+    hidden states, the SeACo decoder over the hotword memory (twice), attention-score filtering when the hotword list is longer than
+    `nfilter`, hotword_output_layer, NO_BIAS merge.  The hotword encoder (Embedding + 2-layer LSTM, O(#hotwords)) runs in torch."""
+
+    def __init__(self, *args, inner_dim: int = 512, bias_encoder_type: str = "lstm", bias_encoder_bid: bool = False, seaco_decoder: str = None,
+                 seaco_decoder_conf: dict = None, NO_BIAS: int = 8377, **kwargs):
+        super().__init__(*args, **kwargs)
+        if inner_dim != 512 or bias_encoder_type != "lstm" or bias_encoder_bid:
+            raise _abi.FunasrB200Error("SeacoParaformerB200 supports inner_dim=512, bias_encoder_type='lstm', unidirectional")
+        conf = {k: v for k, v in (seaco_decoder_conf or {}).items() if k in ("attention_heads", "linear_units", "num_blocks", "att_layer_num",
+                                                                             "kernel_size", "sanm_shfit")}
+        self.seaco_decoder = _SeacoDecoderHolder(**conf)
+        self.bias_encoder = nn.LSTM(inner_dim, inner_dim, 2, batch_first=True)
+        self.hotword_output_layer = nn.Linear(inner_dim, self.vocab_size)
+        for p_ in list(self.bias_encoder.parameters()) + list(self.hotword_output_layer.parameters()):
+            p_.requires_grad_(False)
+        self.NO_BIAS = int(NO_BIAS)
+
+    def engine(self, device=None) -> ParaformerEngine:
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _abi.FunasrB200Error("SeacoParaformerB200 needs a CUDA device; there is no CPU path")
+        if self._engine is None or self._engine.device != dev:
+            self._engine = ParaformerEngine(self.state_dict(), self.cfg, dev, gemm_mode=self.gemm_mode, seaco=True, no_bias=self.NO_BIAS,
+                                            smooth_factor2=self.predictor.smooth_factor2, noise_threshold2=self.predictor.noise_threshold2)
+        return self._engine
+
+    def _forward(self, eng, speech, lens, kwargs):
+        hw = kwargs.get("hotword_ids")          # list of token-id lists incl. the trailing [sos] entry (generate_hotwords_list)
+        tok = kwargs.get("_tokenizer")
+        if hw is None and kwargs.get("hotword") and tok is not None:
+            hw = [tok.tokens2ids(h.split()) for h in kwargs["hotword"].split()] + [[self.sos]]
+        return eng.forward_feats_seaco(speech, lens, hw, nfilter=int(kwargs.get("nfilter", 50)), sos=self.sos, eos=self.eos, blank=self.blank_id)
+
+    def inference(self, data_in, data_lengths=None, key: list = None, tokenizer=None, frontend=None, **kwargs):
+        return super().inference(data_in, data_lengths, key, tokenizer, frontend, _tokenizer=tokenizer, **kwargs)

@@ -12,7 +12,7 @@ from . import _abi
 
 
 class OfflineRecognizer:
-    def __init__(self, model_file: str, device: int = 0, gemm_mode: str = "bf16x3"):
+    def __init__(self, model_file: str, device: int = 0, gemm_mode: str = "fp16x3"):
         self.lib = _abi.load()
         mode = _abi.GEMM_MODES[gemm_mode] if isinstance(gemm_mode, str) else int(gemm_mode)
         self.handle = self.lib.fa_offline_init(model_file.encode(), device, mode)

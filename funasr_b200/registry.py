@@ -67,6 +67,11 @@ DROP_IN_KEYS = {
     ("predictor_classes", "CifPredictorV2"): "CifPredictorV2B200",
     ("predictor_classes", "CifPredictorV3"): "CifPredictorV3B200",
     ("model_classes", "BiCifParaformer"): "BiCifParaformerB200",
+    ("model_classes", "SeacoParaformer"): "SeacoParaformerB200",
+    ("model_classes", "ContextualParaformer"): "ContextualParaformerB200",
+    ("decoder_classes", "ContextualParaformerDecoder"): "ContextualParaformerDecoderB200",
+    ("model_classes", "SenseVoiceSmall"): "SenseVoiceSmallB200",
+    ("encoder_classes", "SenseVoiceEncoderSmall"): "SenseVoiceEncoderSmallB200",
     ("decoder_classes", "ParaformerSANMDecoder"): "ParaformerSANMDecoderB200",
 }
 

@@ -95,8 +95,11 @@ class ShardedRunner:
     are not ordered behind it; ``finish`` waits and de-permutes."""
 
     def __init__(self, infer_batch: Callable[[List[torch.Tensor]], Tuple[torch.Tensor, torch.Tensor]], device, max_batch: int = 64,
-                 max_frames: int = 64 * 500, group=None):
+                 max_frames: int = 64 * 500, group=None, extra_ids: int = 1):
+        """extra_ids: id columns beyond the utterance's LFR frame count T a result row may need — 1 for the CIF models (tokens
+        <= T + 1, the tail token), 4 for SenseVoiceSmall (CTC ids over T + 4 frames: the four prepended query frames)."""
         self.infer_batch = infer_batch
+        self.extra_ids = int(extra_ids)
         self.device = torch.device(device)
         self.max_batch, self.max_frames, self.group = max_batch, max_frames, group
         self.world, self.rank = _world(group)
@@ -109,7 +112,7 @@ class ShardedRunner:
         local_lens = [int(n_samples[i]) for i in mine]
         buckets = [[mine[j] for j in b] for b in bucket_by_length(local_lens, self.max_batch, self.max_frames)]
         per = max(len(s) for s in shards)
-        width = max(num_lfr_frames(int(n)) for n in n_samples) + 1 if len(n_samples) else 1      # CIF bound: tokens <= T + 1
+        width = max(num_lfr_frames(int(n)) for n in n_samples) + self.extra_ids if len(n_samples) else 1   # bound on ids per utterance
         return {"shards": shards, "mine": mine, "buckets": buckets, "per": per, "width": width, "n_total": len(n_samples)}
 
     def _rows_buffer(self, per: int, width: int, slot: int) -> torch.Tensor:

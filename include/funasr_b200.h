@@ -37,13 +37,13 @@ typedef enum {
 /* GEMM arithmetic modes (FaLinear contractions). fp32 accumulate everywhere. */
 typedef enum {
   FA_GEMM_F32_SIMT = 0, /* fp32 FFMA tiles: the parity reference path */
-  FA_GEMM_BF16X1 = 1,   /* tcgen05 kind::f16, one bf16 pass (fast mode) */
-  FA_GEMM_BF16X3 = 3,   /* tcgen05, hi*hi + hi*lo + lo*hi (~2^-17 relative) */
-  FA_GEMM_BF16X6 = 6    /* tcgen05, three bf16 planes, six products (~fp32) */
+  FA_GEMM_F16X1 = 1,   /* tcgen05 kind::f16, one fp16 pass (fast mode) */
+  FA_GEMM_F16X3 = 3,   /* tcgen05, fp16 planes x = hi + lo: hi*hi + hi*lo + lo*hi (~2^-22 relative per product) */
+  FA_GEMM_F16X6 = 6    /* tcgen05, three fp16 planes, six products (~fp32) */
 } FaGemmMode;
 
-/* nn.Linear: y = x W^T + b.  w_planes (optional) holds the bf16 planes made by fa_split_bf16 for the
- * tcgen05 path: [3][out_f][in_pad] bf16 (hi, mid, lo), in_pad = in_f rounded up to 64. */
+/* nn.Linear: y = x W^T + b.  w_planes (optional) holds the fp16 planes made by fa_split_planes for the
+ * tcgen05 path: [3][out_f][in_pad] fp16 (hi, mid, lo), in_pad = in_f rounded up to 64. */
 typedef struct {
   const float* w;        /* [out_f, in_f] */
   const float* b;        /* [out_f] or NULL */
@@ -178,13 +178,13 @@ int fa_linear(const float* x, int64_t ldx, int64_t rows, const FaLinear* lin, in
               const float* res1, int64_t ld_res1, const float* res2, int64_t ld_res2,
               float* y, int64_t ldy, int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream);
 
-/* The tensor-core GEMM alone, A operand already split into bf16 planes [npl][rows][lin->in_pad] (npl = 1 / 2 / 3 for
- * BF16X1 / X3 / X6) by fa_split_rows: what the model-level calls launch between fused producers and consumers. */
+/* The tensor-core GEMM alone, A operand already split into fp16 planes [npl][rows][lin->in_pad] (npl = 1 / 2 / 3 for
+ * F16X1 / X3 / X6) by fa_split_rows: what the model-level calls launch between fused producers and consumers. */
 int fa_split_rows(const float* x, int64_t ldx, int64_t rows, int32_t cols, int32_t cols_pad, int32_t nplanes, void* planes,
                   fa_stream_t stream);
 int fa_linear_planes(const void* a_planes, int64_t rows, const FaLinear* lin, int32_t relu, const float* res1, int64_t ld_res1,
                      const float* res2, int64_t ld_res2, float* y, int64_t ldy, int32_t gemm_mode, fa_stream_t stream);
-/* Same GEMM with the plane-emitting epilogue: out_planes [npl][rows][ld_out] bf16 (hi, lo, ...) of act(A W^T + b) — the launch the
+/* Same GEMM with the plane-emitting epilogue: out_planes [npl][rows][ld_out] fp16 (hi, lo, ...) of act(A W^T + b) — the launch the
  * encoder makes for FFN w_1, whose ReLU output feeds w_2 without an fp32 round trip (bench.py times exactly this launch). */
 int fa_linear_planes_to_planes(const void* a_planes, int64_t rows, const FaLinear* lin, int32_t relu, void* out_planes,
                                int64_t ld_out, int32_t gemm_mode, fa_stream_t stream);
@@ -202,8 +202,8 @@ int fa_attention(const float* q, int64_t ldq, const float* k, int64_t ldk, const
                  const int32_t* key_lens, int32_t batch, int32_t heads, int32_t tq, int32_t tk,
                  float* ctx, int64_t ld_ctx, fa_stream_t stream);
 
-/* Same contract on the tcgen05 tensor cores (bf16 operand planes, fp32 accumulation in TMEM):
- * gemm_mode FA_GEMM_BF16X1 (one plane) or FA_GEMM_BF16X3/X6 (hi+lo planes, three MMA terms).  workspace holds the
+/* Same contract on the tcgen05 tensor cores (fp16 operand planes, fp32 accumulation in TMEM):
+ * gemm_mode FA_GEMM_F16X1 (one plane) or FA_GEMM_F16X3/X6 (hi+lo planes, three MMA terms).  workspace holds the
  * operand planes (size from fa_attention_tc_workspace_bytes). */
 size_t fa_attention_tc_workspace_bytes(int32_t batch, int32_t heads, int32_t tq, int32_t tk, int32_t gemm_mode);
 int fa_attention_tc(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
@@ -255,8 +255,8 @@ int fa_cif_upsample_alphas(const float* feat, int32_t dz, const float* w, const 
 int fa_blstm_forward(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, int32_t batch, int32_t t_len,
                      int32_t hidden, float* out, void* sync_scratch8, fa_stream_t stream);
 
-/* Tensor-core variant (default in the plugin): the per-step [B,512] x [512,2048] product on warp-level bf16 MMAs with the
- * 3-product operand split (fp32 accumulate), h exchanged between CTAs as bf16 hi / lo planes.  Same contract as
+/* Tensor-core variant (default in the plugin): the per-step [B,512] x [512,2048] product on warp-level fp16 MMAs with the
+ * 3-product operand split (fp32 accumulate), h exchanged between CTAs as fp16 hi / lo planes.  Same contract as
  * fa_blstm_forward; scratch >= fa_blstm_tc_scratch_bytes(batch) bytes of device memory (zeroed by the call). */
 size_t fa_blstm_tc_scratch_bytes(int32_t batch);
 int fa_blstm_forward_tc(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, int32_t batch, int32_t t_len,
@@ -284,6 +284,42 @@ int fa_paraformer_decoder_forward(const FaDecoder* dec, const float* enc, const 
                                   float* logits, int32_t log_softmax, int32_t gemm_mode, void* workspace,
                                   size_t ws_bytes, fa_stream_t stream);
 
+/* The same with return_hidden + return_both (decoder.py:441-449): additionally writes the after_norm output `hidden`
+ * [B, n_max, 512] — the `decoder_hidden` SeacoParaformer feeds to its hotword decoder (seaco_paraformer/model.py:290-297). */
+int fa_paraformer_decoder_forward_hidden(const FaDecoder* dec, const float* enc, const int32_t* enc_lens, int32_t batch,
+                                         int32_t t_max, const float* acoustic, int64_t ld_acoustic_rows,
+                                         const int32_t* tok_lens, int32_t n_max, int32_t* argmax_ids, float* argmax_logp,
+                                         float* logits, int32_t log_softmax, float* hidden, int32_t gemm_mode,
+                                         void* workspace, size_t ws_bytes, fa_stream_t stream);
+
+/* A SAN-M decoder stack WITHOUT input / output layer over an arbitrary memory: the SeACo decoder of SeacoParaformer
+ * (seaco_paraformer/model.py:100-110: ParaformerSANMDecoder(use_output_layer=False, wo_input_layer=True), FFN 1024, FSMN k=21,
+ * 6 attention layers) attending over the hotword embeddings.  Uses dec->layers / n_layers / heads / fsmn_k / last / after_norm.
+ *   memory [t_mem, 512] when mem_shared != 0 (the same hotword memory for every utterance, model.py:306-308), else
+ *   [B, t_mem, 512]; mem_lens[B]; x [B, ld_x_rows, 512] of which n_max rows are used; tok_lens[B].
+ *   n_run attention layers are run (<= dec->n_layers), then
+ *     finish != 0     : decoders3 + after_norm -> hidden [B, n_max, 512]  (ParaformerSANMDecoder.forward, decoder.py:397-449)
+ *     attn_probs != 0 : layer n_run-1 stops at its cross-attention and writes utterance 0's probability matrix
+ *                       [heads, n_max, t_mem] (forward_asf6 / get_attn_mat, decoder.py:485-513, :123-146); hidden untouched. */
+size_t fa_sanm_decoder_stack_workspace_bytes(int32_t batch, int32_t t_mem, int32_t n_max, int32_t gemm_mode);
+int fa_sanm_decoder_stack_forward(const FaDecoder* dec, const float* memory, const int32_t* mem_lens, int32_t mem_shared,
+                                  int32_t batch, int32_t t_mem, const float* x, int64_t ld_x_rows, const int32_t* tok_lens,
+                                  int32_t n_max, int32_t n_run, int32_t finish, float* hidden, float* attn_probs,
+                                  int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream);
+
+/* ids / best_logp [rows] = arg-max and its log-softmax value of (a (+ b)) W^T + bias — SeACo's hotword_output_layer over
+ * cif_attended + dec_attended (seaco_paraformer/model.py:351-355); logp != NULL receives the full log-softmax rows [rows, out_f]. */
+size_t fa_linear_argmax_workspace_bytes(int64_t rows, int32_t vocab, int32_t gemm_mode);
+int fa_linear_argmax(const FaLinear* lin, const float* a, const float* b_or_null, int64_t rows, int32_t* ids, float* best_logp,
+                     float* logp, int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream);
+
+/* SeACo merge with seaco_weight = 1 (seaco_paraformer/model.py:357-378): per token row, the decoder's arg-max where the hotword
+ * decoder's arg-max is NO_BIAS, else the hotword decoder's.  merged != NULL additionally receives the merged log-prob rows
+ * (dec_logp / dha_logp: full log-softmax rows [rows, vocab]). */
+int fa_seaco_merge(const int32_t* dec_ids, const float* dec_best, const int32_t* dha_ids, const float* dha_best, int64_t rows,
+                   int32_t no_bias, int32_t* out_ids, float* out_best, const float* dec_logp, const float* dha_logp,
+                   float* merged, int32_t vocab, fa_stream_t stream);
+
 /* Greedy post-filter (paraformer/model.py:655-666): keep argmax_ids[b, k] for k < tok_lens[b] that are not
  * in {blank=0, sos=1, eos=2}; out_ids [B, n_max] (padded with -1), out_lens [B]. */
 int fa_greedy_filter(const int32_t* argmax_ids, const int32_t* tok_lens, int32_t batch, int32_t n_max,
@@ -306,9 +342,9 @@ int fa_ctc_greedy_forward(const FaLinear* ctc_lo, const float* enc, const int32_
 int fa_resample(const float* x, const int32_t* lens, int32_t batch, int64_t x_stride, const float* table, int32_t orig,
                 int32_t nnew, int32_t width, float* y, int64_t y_stride, int32_t y_cap, int32_t* out_lens, fa_stream_t stream);
 
-/* Split fp32 [rows, cols] into three bf16 planes [3][rows][cols_pad] (hi, mid, lo; zero padded columns):
+/* Split fp32 [rows, cols] into three fp16 planes [3][rows][cols_pad] (hi, mid, lo; zero padded columns):
  * weight repack for the tcgen05 GEMM path (called once per weight after load_pretrained_model). */
-int fa_split_bf16(const float* src, int64_t ld_src, int64_t rows, int32_t cols, int32_t cols_pad,
+int fa_split_planes(const float* src, int64_t ld_src, int64_t rows, int32_t cols, int32_t cols_pad,
                   void* planes, fa_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@ from funasr_b200.engine import FrontendEngine, ParaformerEngine
 B = 64
 dev = "cuda:0"
 cfg = synth.ParaformerConfig()
-eng = ParaformerEngine(synth.make_bicif_state_dict(cfg, 0), cfg, dev, gemm_mode="bf16x3", bicif=True)
+eng = ParaformerEngine(synth.make_bicif_state_dict(cfg, 0), cfg, dev, gemm_mode="fp16x3", bicif=True)
 fe = FrontendEngine(synth.make_cmvn(cfg, 1), dev)
 base = [synth.make_wav(480000, 100 + i) for i in range(4)]
 wav = torch.stack([base[i % 4].roll(977 * i) for i in range(B)]).to(dev)
@@ -53,7 +53,7 @@ feat_tc = torch.empty_like(feat)
 t_tc = timeit(lambda: _abi.check(eng.lib.fa_blstm_forward_tc(xproj.data_ptr(), eng.lstm_hh_f.data_ptr(), eng.lstm_hh_b.data_ptr(), B, 1500, 512,
                                                             feat_tc.data_ptr(), scr.data_ptr(), nbs, st), "blstm tc"))
 torch.cuda.synchronize()
-print(f"fa_blstm_forward_tc (mma.sync bf16x3) alone: {t_tc:.2f} ms = {t_tc / 1500 * 1000:.2f} us per step; max |tc - simt| = {float((feat_tc - feat).abs().max()):.3e}")
+print(f"fa_blstm_forward_tc (mma.sync fp16x3) alone: {t_tc:.2f} ms = {t_tc / 1500 * 1000:.2f} us per step; max |tc - simt| = {float((feat_tc - feat).abs().max()):.3e}")
 for mask, what in ((1, "no dot products"), (2, "no gather"), (4, "no barrier"), (3, "no dot, no gather"), (7, "x loads + gates + stores only")):
     tm = timeit(lambda: _abi.check(eng.lib.fa_debug_blstm_variant(mask, xproj.data_ptr(), eng.lstm_hh_f.data_ptr(), eng.lstm_hh_b.data_ptr(), B, 1500,
                                                                     feat.data_ptr(), eng._lstm_sync.data_ptr(), st), "blstm variant"), n=3)

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from funasr_b200 import _abi
 lib = _abi.load()
-mode = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
+mode = sys.argv[1] if len(sys.argv) > 1 else "fp16x3"
 M, K, N = 32000, 512, 2048
 dev = "cuda:0"
 g = torch.Generator().manual_seed(0)
@@ -14,7 +14,7 @@ w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
 b = torch.randn(N, generator=g).to(dev)
 planes = torch.empty(3, N, K, dtype=torch.bfloat16, device=dev)
 st = torch.cuda.current_stream().cuda_stream
-_abi.check(lib.fa_split_bf16(w.data_ptr(), K, N, K, K, planes.data_ptr(), st), "split")
+_abi.check(lib.fa_split_planes(w.data_ptr(), K, N, K, K, planes.data_ptr(), st), "split")
 lin = _abi.FaLinear(w.data_ptr(), b.data_ptr(), planes.data_ptr(), N, K, K, 0)
 y = torch.empty(M, N, device=dev)
 ws = torch.empty(3 * M * K * 2 + 4096, dtype=torch.uint8, device=dev)

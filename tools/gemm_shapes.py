@@ -9,7 +9,7 @@ from funasr_b200 import _abi
 lib = _abi.load()
 dev = "cuda:0"
 st = torch.cuda.current_stream().cuda_stream
-gm = _abi.GEMM_MODES["bf16x3"]
+gm = _abi.GEMM_MODES["fp16x3"]
 M = 32000
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 peak = 1708.3e12
@@ -21,7 +21,7 @@ def run(name, N, K, n_res, relu=0, iters=8):
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
     b = torch.randn(N, generator=g).to(dev)
     wp = torch.empty(3, N, K, dtype=torch.bfloat16, device=dev)
-    _abi.check(lib.fa_split_bf16(w.data_ptr(), K, N, K, K, wp.data_ptr(), st), "split")
+    _abi.check(lib.fa_split_planes(w.data_ptr(), K, N, K, K, wp.data_ptr(), st), "split")
     lin = _abi.FaLinear(w.data_ptr(), b.data_ptr(), wp.data_ptr(), N, K, K, 0)
     xp = torch.empty(2, M, K, dtype=torch.bfloat16, device=dev)
     _abi.check(lib.fa_split_rows(x.data_ptr(), K, M, K, K, 2, xp.data_ptr(), st), "split_rows")

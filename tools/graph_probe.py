@@ -9,7 +9,7 @@ from funasr_b200.engine import FrontendEngine, ParaformerEngine
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 dev = "cuda:0"
 cfg = synth.ParaformerConfig()
-eng = ParaformerEngine(synth.make_state_dict(cfg, 0), cfg, dev, gemm_mode="bf16x3")
+eng = ParaformerEngine(synth.make_state_dict(cfg, 0), cfg, dev, gemm_mode="fp16x3")
 fe = FrontendEngine(synth.make_cmvn(cfg, 1), dev)
 base = [synth.make_wav(480000, 100 + i) for i in range(4)]
 wav = torch.stack([base[i % 4].roll(977 * i) for i in range(B)]).to(dev)

@@ -1,4 +1,4 @@
-"""Runs the hot path a few times (for ncu launch lists / captures). Usage: run_once.py --mode bf16x3 --B 16 --iters 2"""
+"""Runs the hot path a few times (for ncu launch lists / captures). Usage: run_once.py --mode fp16x3 --B 16 --iters 2"""
 import argparse, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -6,7 +6,7 @@ import torch
 from funasr_b200 import synth
 from funasr_b200.engine import FrontendEngine, ParaformerEngine
 ap = argparse.ArgumentParser()
-ap.add_argument("--mode", default="bf16x3"); ap.add_argument("--B", type=int, default=16); ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--mode", default="fp16x3"); ap.add_argument("--B", type=int, default=16); ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--layers", type=int, default=50)
 a = ap.parse_args()
 dev = "cuda:0"

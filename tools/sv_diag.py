@@ -7,7 +7,7 @@ DEV = torch.device('cuda:0')
 name = 'sv_large_single'
 cfg, wseed, wavs, cmvn, g = load_sv_case(name)
 res = {}
-for mode in ['fp32', 'bf16x3']:
+for mode in ['fp32', 'fp16x3']:
     eng = SenseVoiceEngine(synth.make_sensevoice_state_dict(cfg, wseed), cfg, DEV, gemm_mode=mode, cmvn=cmvn)
     lens = [w.numel() for w in wavs]
     pad = torch.nn.utils.rnn.pad_sequence(wavs, batch_first=True).to(DEV)
@@ -22,5 +22,5 @@ for mode in ['fp32', 'bf16x3']:
     for b_, t_ in bad[:10]:
         top = torch.topk(lp[t_], 3)
         print('  t', t_, 'ours', am[b_, t_], 'gold', ga[b_, t_], 'top3', top.indices.tolist(), [f'{x:.6f}' for x in top.values.tolist()], 'gold logp ours', float(lp[t_, ga[b_, t_]]))
-d = (res['fp32']['logp'] - res['bf16x3']['logp']).abs().max()
-print('max |logp fp32 - bf16x3|', float(d))
+d = (res['fp32']['logp'] - res['fp16x3']['logp']).abs().max()
+print('max |logp fp32 - fp16x3|', float(d))
