@@ -688,8 +688,8 @@ def dominant_gemm_roofline(lib, job, dev, mode, pk, pk_src):
     npl = {"fp16": 1, "fp16x3": 2, "fp16x6": 3}.get(mode, 0)
     if not npl:
         return {"bound": "fp32-simt", "kernel": "gemm_f32_kernel", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None}
-    planes = torch.empty(npl, M, K, dtype=torch.bfloat16, device=dev)
-    outp = torch.empty(npl, M, N, dtype=torch.bfloat16, device=dev)
+    planes = torch.empty(npl, M, K, dtype=torch.float16, device=dev)
+    outp = torch.empty(npl, M, N, dtype=torch.float16, device=dev)
     _abi.check(lib.fa_split_rows(x.data_ptr(), K, M, K, K, npl, planes.data_ptr(), st), "fa_split_rows")
     times = []
     for i in range(9):

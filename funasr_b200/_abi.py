@@ -59,6 +59,15 @@ class FaDecoder(C.Structure):
                 ("_pad2", C.c_int32)]
 
 
+class FaVadLayer(C.Structure):
+    _fields_ = [("lin", FaLinear), ("conv_w", C.c_void_p), ("affine", FaLinear)]
+
+
+class FaVadEncoder(C.Structure):
+    _fields_ = [("in1", FaLinear), ("in2", FaLinear), ("layers", C.POINTER(FaVadLayer)), ("n_layers", C.c_int32), ("lorder", C.c_int32),
+                ("out1", FaLinear), ("out2", FaLinear), ("sil_ids", C.c_int32 * 4), ("n_sil", C.c_int32), ("_pad", C.c_int32)]
+
+
 _vp, _i32, _i64, _sz, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float
 
 # name -> (restype, argtypes); every symbol include/funasr_b200.h declares
@@ -68,6 +77,9 @@ SIGNATURES = {
     "fa_status_string": (C.c_char_p, [C.c_int]),
     "fa_fbank_lfr_cmvn": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "fa_fbank_lfr_cmvn_strided": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp]),
+    "fa_fbank_tables_bytes": (_sz, []),
+    "fa_fbank_make_tables": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "fa_fbank_lfr_cmvn_tables": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
     "fa_broadcast_rows": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     "fa_ctc_greedy_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "fa_ctc_greedy_forward": (C.c_int, [C.POINTER(FaLinear), _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
@@ -99,6 +111,9 @@ SIGNATURES = {
     "fa_blstm_tc_scratch_bytes": (_sz, [_i32]),
     "fa_blstm_forward_tc": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "fa_debug_blstm_variant": (C.c_int, [_i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "fa_fsmn_vad_workspace_bytes": (_sz, [C.POINTER(FaVadEncoder), _i32]),
+    "fa_fsmn_vad_forward": (C.c_int, [C.POINTER(FaVadEncoder), _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "fa_frame_decibels": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "fa_greedy_filter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fa_split_planes": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "fa_resample": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _vp]),

@@ -17,28 +17,38 @@
 namespace fa {
 
 constexpr int kWin = 400, kShift = 160, kFft = 512, kBins = 257, kMel = 80;
-constexpr int kLfrM = 7, kLfrN = 6, kFeat = kMel * kLfrM;
-constexpr int kRows = 8;                               // LFR rows per CTA
-constexpr int kFrames = kLfrN * (kRows - 1) + kLfrM;   // 49 frames feed 8 rows
-constexpr int kSpan = (kFrames - 1) * kShift + kWin;   // 8080 samples
+constexpr int kFramesMax = 49;                         // frames one CTA turns into log-mel rows: 6*(8-1)+7 (ASR, LFR 7/6) or 1*(44-1)+5 (VAD, LFR 5/1)
+constexpr int kSpan = (kFramesMax - 1) * kShift + kWin;   // 8080 samples
 constexpr int kWarps = 8;
 constexpr int kMelPackMax = 1024;
+// Precomputed tables (fa_fbank_make_tables): constants of the configuration that every CTA would otherwise rebuild — the
+// sparse support of the 80 triangular mel filters, the FFT twiddles, the window.  Layout in floats:
+constexpr int kTabStart = 0, kTabLen = kMel, kTabOff = 2 * kMel, kTabW = 3 * kMel, kTabTw = kTabW + kMelPackMax,
+              kTabWin = kTabTw + 512, kTabFloats = kTabWin + kWin;
+constexpr int kZs = 36;                                // spectrum row pitch (float2): at most 2-way bank conflicts on the strided reads
 
 struct FbankSmem {
   float wav[kSpan + 8];
-  float logmel[kFrames * kMel];
-  float2 fft[kWarps][2][256];
+  float logmel[kFramesMax * kMel];
+  float2 zs[kWarps][8 * kZs];      // per warp: the 256-point spectrum as [k1 = 0..7][k2] rows of pitch kZs
+  float pw[kWarps][264];           // per warp: power spectrum P[0..256]
   float2 tw[256];
   float win[kWin];
   float melw[kMelPackMax];
   int mel_start[kMel], mel_len[kMel], mel_off[kMel];
 };
 
+// kLfrM / kLfrN: low-frame-rate stacking (7/6 for Paraformer & SenseVoice, 5/1 for the FSMN-VAD); kRows: LFR rows per CTA.
+// tables != nullptr: constants come precomputed from global memory (a 9 KB copy); nullptr: every CTA derives them from
+// mel_banks / window itself (the round-1 behaviour: a 20 k-load scan of the filter matrix per CTA, kept for the plain ABI).
+template <int kLfrM, int kLfrN, int kRows>
 __global__ void __launch_bounds__(kWarps * 32)
 fbank_lfr_cmvn_kernel(const float* __restrict__ wav, const int32_t* __restrict__ wav_lens, int64_t wav_stride,
                       const float* __restrict__ cmvn, const float* __restrict__ mel_banks,
-                      const float* __restrict__ window, float* __restrict__ feats, int32_t* __restrict__ feat_lens,
-                      int t_max, int64_t batch_stride_rows) {
+                      const float* __restrict__ window, const float* __restrict__ tables, float* __restrict__ feats,
+                      int32_t* __restrict__ feat_lens, int t_max, int64_t batch_stride_rows) {
+  constexpr int kFeat = kMel * kLfrM;
+  static_assert(kLfrN * (kRows - 1) + kLfrM <= kFramesMax, "too many frames per CTA");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FbankSmem& s = *reinterpret_cast<FbankSmem*>(smem_raw);
   const int b = blockIdx.y, i0 = blockIdx.x * kRows;
@@ -63,6 +73,17 @@ fbank_lfr_cmvn_kernel(const float* __restrict__ wav, const int32_t* __restrict__
     const float* src = wav + (int64_t)b * wav_stride + (int64_t)f_lo * kShift;
     const int span = (nfr - 1) * kShift + kWin;
     for (int j = tid; j < span; j += blockDim.x) s.wav[j] = __ldg(src + j) * 32768.0f;   // exact scaling
+  }
+  if (tables != nullptr) {
+    const int* ti = reinterpret_cast<const int*>(tables);
+    for (int j = tid; j < kMel; j += blockDim.x) {
+      s.mel_start[j] = __ldg(ti + kTabStart + j); s.mel_len[j] = __ldg(ti + kTabLen + j); s.mel_off[j] = __ldg(ti + kTabOff + j);
+    }
+    for (int j = tid; j < kMelPackMax; j += blockDim.x) s.melw[j] = __ldg(tables + kTabW + j);
+    for (int j = tid; j < 256; j += blockDim.x) s.tw[j] = make_float2(__ldg(tables + kTabTw + 2 * j), __ldg(tables + kTabTw + 2 * j + 1));
+    for (int j = tid; j < kWin; j += blockDim.x) s.win[j] = __ldg(tables + kTabWin + j);
+    __syncthreads();
+  } else {
     for (int j = tid; j < kWin; j += blockDim.x) s.win[j] = window[j];
     for (int k = tid; k < 256; k += blockDim.x) {
       float sn, cs;
@@ -83,19 +104,19 @@ fbank_lfr_cmvn_kernel(const float* __restrict__ wav, const int32_t* __restrict__
       }
       if (lane == 0) { s.mel_start[j] = en < 0 ? 0 : st; s.mel_len[j] = en < 0 ? 0 : en - st + 1; }
     }
+    __syncthreads();
+    if (tid == 0) {
+      int off = 0;
+      for (int j = 0; j < kMel; ++j) { s.mel_off[j] = off; off += s.mel_len[j]; if (off > kMelPackMax) { s.mel_len[j] = 0; off = s.mel_off[j]; } }
+    }
+    __syncthreads();
+    if (tid < kMel) {
+      const float* row = mel_banks + tid * kBins + s.mel_start[tid];
+      float* dst = s.melw + s.mel_off[tid];
+      for (int k = 0; k < s.mel_len[tid]; ++k) dst[k] = row[k];
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (tid == 0) {
-    int off = 0;
-    for (int j = 0; j < kMel; ++j) { s.mel_off[j] = off; off += s.mel_len[j]; if (off > kMelPackMax) { s.mel_len[j] = 0; off = s.mel_off[j]; } }
-  }
-  __syncthreads();
-  if (tid < kMel) {
-    const float* row = mel_banks + tid * kBins + s.mel_start[tid];
-    float* dst = s.melw + s.mel_off[tid];
-    for (int k = 0; k < s.mel_len[tid]; ++k) dst[k] = row[k];
-  }
-  __syncthreads();
 
   // ---- one warp per frame: 512-point real FFT as a 256-point complex FFT held in REGISTERS ----
   // z[n] = y[2n] + i y[2n+1]; lane L owns z[L + 32 r], r = 0..7.  256 = 8 x 32 (Cooley-Tukey):
@@ -105,9 +126,8 @@ fbank_lfr_cmvn_kernel(const float* __restrict__ wav, const int32_t* __restrict__
   //   after which lane L holds Z[k1 + 8 rev5(L)].  The spectrum goes to shared memory ONCE for the real-FFT untangling
   //   (needs Z[k] and Z[256 - k]), the power spectrum and the sparse mel filters.
   // All twiddles depend only on the lane: hoisted out of the frame loop.
-  float2* Zs = s.fft[warp][0];                                    // [8][kZs] spectrum, row k1, column k2
-  float* P = reinterpret_cast<float*>(s.fft[warp][1]);            // [257] power spectrum
-  constexpr int kZs = 36;                                         // row pitch (float2): at most 2-way bank conflicts on the strided reads
+  float2* Zs = s.zs[warp];                                        // [8][kZs] spectrum, row k1, column k2
+  float* P = s.pw[warp];                                          // [257] power spectrum
   auto twid = [&](int idx) -> float2 {                            // e^{-2 pi i idx / 512}, idx in [0, 512)
     const float2 w = s.tw[idx & 255];
     return idx < 256 ? w : make_float2(-w.x, -w.y);
@@ -235,7 +255,81 @@ fbank_lfr_cmvn_kernel(const float* __restrict__ wav, const int32_t* __restrict__
   }
 }
 
+// fa_fbank_make_tables: the per-configuration constants, computed once (same arithmetic as the in-kernel path)
+__global__ void fbank_tables_kernel(const float* __restrict__ mel_banks, const float* __restrict__ window, float* __restrict__ tables) {
+  __shared__ int s_start[kMel], s_len[kMel], s_off[kMel];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int* ti = reinterpret_cast<int*>(tables);
+  for (int j = warp; j < kMel; j += kWarps) {
+    const float* row = mel_banks + j * kBins;
+    int st = kBins, en = -1;
+    for (int k = lane; k < kBins; k += 32) {
+      if (row[k] != 0.f) { st = min(st, k); en = max(en, k); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      st = min(st, __shfl_xor_sync(0xffffffffu, st, o));
+      en = max(en, __shfl_xor_sync(0xffffffffu, en, o));
+    }
+    if (lane == 0) { s_start[j] = en < 0 ? 0 : st; s_len[j] = en < 0 ? 0 : en - st + 1; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int off = 0;
+    for (int j = 0; j < kMel; ++j) { s_off[j] = off; off += s_len[j]; if (off > kMelPackMax) { s_len[j] = 0; off = s_off[j]; } }
+  }
+  __syncthreads();
+  for (int j = tid; j < kMelPackMax; j += blockDim.x) tables[kTabW + j] = 0.f;
+  __syncthreads();
+  if (tid < kMel) {
+    ti[kTabStart + tid] = s_start[tid]; ti[kTabLen + tid] = s_len[tid]; ti[kTabOff + tid] = s_off[tid];
+    const float* row = mel_banks + tid * kBins + s_start[tid];
+    for (int k = 0; k < s_len[tid]; ++k) tables[kTabW + s_off[tid] + k] = row[k];
+  }
+  for (int k = tid; k < 256; k += blockDim.x) {
+    float sn, cs;
+    sincospif((float)k * (1.0f / 256.0f), &sn, &cs);        // e^{-2 pi i k / 512}
+    tables[kTabTw + 2 * k] = cs; tables[kTabTw + 2 * k + 1] = -sn;
+  }
+  for (int j = tid; j < kWin; j += blockDim.x) tables[kTabWin + j] = window[j];
+}
+
+template <int M, int N, int ROWS>
+static int fbank_launch(const float* wav, const int32_t* wav_lens, int batch, int64_t wav_stride, const float* cmvn, const float* mel_banks,
+                        const float* window, const float* tables, float* feats, int64_t stride_rows, int32_t* feat_lens, int t_max,
+                        cudaStream_t st) {
+  const size_t smem = sizeof(FbankSmem);
+  static PerDeviceOnce once;
+  FA_RETURN_IF_ERR(ensure_dyn_smem(fbank_lfr_cmvn_kernel<M, N, ROWS>, smem, once));
+  dim3 grid((t_max + ROWS - 1) / ROWS, batch);
+  fbank_lfr_cmvn_kernel<M, N, ROWS><<<grid, kWarps * 32, smem, st>>>(wav, wav_lens, wav_stride, cmvn, mel_banks, window, tables, feats,
+                                                                    feat_lens, t_max, stride_rows);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
 }  // namespace fa
+
+extern "C" size_t fa_fbank_tables_bytes(void) { return (size_t)fa::kTabFloats * sizeof(float); }
+
+extern "C" int fa_fbank_make_tables(const float* mel_banks, const float* window, float* tables, fa_stream_t stream) {
+  if (!mel_banks || !window || !tables) return FA_ERR_ARG;
+  fa::fbank_tables_kernel<<<1, fa::kWarps * 32, 0, (cudaStream_t)stream>>>(mel_banks, window, tables);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+extern "C" int fa_fbank_lfr_cmvn_tables(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride, const float* cmvn,
+                                        const float* tables, int32_t lfr_m, int32_t lfr_n, float* feats,
+                                        int64_t feats_batch_stride_rows, int32_t* feat_lens, int32_t t_max, fa_stream_t stream) {
+  if (!wav || !wav_lens || !tables || !feats || !feat_lens || batch <= 0 || t_max <= 0 || feats_batch_stride_rows < t_max) return FA_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (lfr_m == 7 && lfr_n == 6)
+    return fa::fbank_launch<7, 6, 8>(wav, wav_lens, batch, wav_stride, cmvn, nullptr, nullptr, tables, feats, feats_batch_stride_rows, feat_lens, t_max, st);
+  if (lfr_m == 5 && lfr_n == 1)
+    return fa::fbank_launch<5, 1, 44>(wav, wav_lens, batch, wav_stride, cmvn, nullptr, nullptr, tables, feats, feats_batch_stride_rows, feat_lens, t_max, st);
+  return FA_ERR_UNSUPPORTED;
+}
 
 extern "C" int fa_fbank_lfr_cmvn_strided(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride,
                                          const float* cmvn, const float* mel_banks, const float* window, float* feats,
@@ -244,14 +338,8 @@ extern "C" int fa_fbank_lfr_cmvn_strided(const float* wav, const int32_t* wav_le
   if (!wav || !wav_lens || !mel_banks || !window || !feats || !feat_lens || batch <= 0 || t_max <= 0 ||
       feats_batch_stride_rows < t_max)
     return FA_ERR_ARG;
-  const size_t smem = sizeof(fa::FbankSmem);
-  static fa::PerDeviceOnce once;
-  FA_RETURN_IF_ERR(fa::ensure_dyn_smem(fa::fbank_lfr_cmvn_kernel, smem, once));
-  dim3 grid((t_max + fa::kRows - 1) / fa::kRows, batch);
-  fa::fbank_lfr_cmvn_kernel<<<grid, fa::kWarps * 32, smem, (cudaStream_t)stream>>>(
-      wav, wav_lens, wav_stride, cmvn, mel_banks, window, feats, feat_lens, t_max, feats_batch_stride_rows);
-  FA_CHECK_LAUNCH();
-  return FA_OK;
+  return fa::fbank_launch<7, 6, 8>(wav, wav_lens, batch, wav_stride, cmvn, mel_banks, window, nullptr, feats, feats_batch_stride_rows, feat_lens,
+                                   t_max, (cudaStream_t)stream);
 }
 
 extern "C" int fa_fbank_lfr_cmvn(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride,

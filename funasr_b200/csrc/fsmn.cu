@@ -11,7 +11,9 @@ namespace fa {
 constexpr int FSMN_TT = 32;     // time steps per thread strip
 constexpr int FSMN_KMAX = 31;
 
-template <int K>
+// K taps, the window of output t covers inputs t - L .. t - L + K - 1: L = (K-1)/2 is the centred SAN-M memory block, L = K - 1
+// the causal memory of the FSMN-VAD encoder (FSMNBlock.conv_left over zero LEFT padding, fsmn_vad_streaming/encoder.py:136-160).
+template <int K, int L>
 __global__ void __launch_bounds__(128)
 fsmn_kernel(const float* __restrict__ v, int64_t ldv, const int32_t* __restrict__ lens, int t_max, int channels,
             const float* __restrict__ w, const float* __restrict__ res, int64_t ldr, float* __restrict__ out,
@@ -22,7 +24,6 @@ fsmn_kernel(const float* __restrict__ v, int64_t ldv, const int32_t* __restrict_
   pdl_wait();
   pdl_trigger();
   if (c >= channels) return;
-  constexpr int L = (K - 1) / 2;
   const int len = min(lens[b], t_max);
   float wk[K];
 #pragma unroll
@@ -48,14 +49,20 @@ fsmn_kernel(const float* __restrict__ v, int64_t ldv, const int32_t* __restrict_
 }
 
 int fsmn_launch(const float* v, int64_t ldv, const int32_t* lens, int batch, int t_max, int channels, const float* w,
-                int ksize, const float* res, int64_t ldr, float* out, int64_t ldo, cudaStream_t st) {
+                int ksize, const float* res, int64_t ldr, float* out, int64_t ldo, cudaStream_t st, int causal) {
   if (batch <= 0 || t_max <= 0) return FA_OK;
   if (!v || !lens || !w || !out) return FA_ERR_ARG;
   dim3 grid((channels + 127) / 128, (t_max + FSMN_TT - 1) / FSMN_TT, batch);
+  if (causal) {
+    if (ksize != 20) return FA_ERR_UNSUPPORTED;
+    FA_CUDA_OK(launch_pdl(fsmn_kernel<20, 19>, grid, dim3(128), 0, st, 1, v, ldv, lens, t_max, channels, w, res, ldr, out, ldo));
+    FA_CHECK_LAUNCH();
+    return FA_OK;
+  }
   switch (ksize) {
-    case 11: FA_CUDA_OK(launch_pdl(fsmn_kernel<11>, grid, dim3(128), 0, st, 1, v, ldv, lens, t_max, channels, w, res, ldr, out, ldo)); break;
-    case 21: FA_CUDA_OK(launch_pdl(fsmn_kernel<21>, grid, dim3(128), 0, st, 1, v, ldv, lens, t_max, channels, w, res, ldr, out, ldo)); break;
-    case 31: FA_CUDA_OK(launch_pdl(fsmn_kernel<31>, grid, dim3(128), 0, st, 1, v, ldv, lens, t_max, channels, w, res, ldr, out, ldo)); break;
+    case 11: FA_CUDA_OK(launch_pdl(fsmn_kernel<11, 5>, grid, dim3(128), 0, st, 1, v, ldv, lens, t_max, channels, w, res, ldr, out, ldo)); break;
+    case 21: FA_CUDA_OK(launch_pdl(fsmn_kernel<21, 10>, grid, dim3(128), 0, st, 1, v, ldv, lens, t_max, channels, w, res, ldr, out, ldo)); break;
+    case 31: FA_CUDA_OK(launch_pdl(fsmn_kernel<31, 15>, grid, dim3(128), 0, st, 1, v, ldv, lens, t_max, channels, w, res, ldr, out, ldo)); break;
     default: return FA_ERR_UNSUPPORTED;
   }
   FA_CHECK_LAUNCH();
@@ -67,5 +74,5 @@ int fsmn_launch(const float* v, int64_t ldv, const int32_t* lens, int batch, int
 extern "C" int fa_fsmn(const float* v, int64_t ldv, const int32_t* lens, int32_t batch, int32_t t_max, int32_t channels,
                        const float* w, int32_t ksize, const float* res, int64_t ld_res, float* out, int64_t ld_out,
                        fa_stream_t stream) {
-  return fa::fsmn_launch(v, ldv, lens, batch, t_max, channels, w, ksize, res, ld_res, out, ld_out, (cudaStream_t)stream);
+  return fa::fsmn_launch(v, ldv, lens, batch, t_max, channels, w, ksize, res, ld_res, out, ld_out, (cudaStream_t)stream, 0);
 }

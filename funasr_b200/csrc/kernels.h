@@ -51,7 +51,7 @@ int attention_f32_launch(const float* q, int64_t ldq, const float* k, int64_t ld
                          const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
                          cudaStream_t st, int kv_shared = 0);
 int fsmn_launch(const float* v, int64_t ldv, const int32_t* lens, int batch, int t_max, int channels, const float* w,
-                int ksize, const float* res, int64_t ldr, float* out, int64_t ldo, cudaStream_t st);
+                int ksize, const float* res, int64_t ldr, float* out, int64_t ldo, cudaStream_t st, int causal = 0);
 int cif_im2col_launch(const float* enc, int64_t rows, int t_max, int d, float* xc, cudaStream_t st);
 int cif_fire_loop_launch(const float* enc, const float* alpha_rows, const int32_t* lens, int batch, int t_max, int d,
                          float tail, float threshold, float* acoustic, int n_cap, int32_t* token_num, float* alphas, float* peaks,

@@ -53,6 +53,7 @@ struct Model {
   FaPredictor pred{};
   FaDecoder dec{};
   const float *mel = nullptr, *window = nullptr, *cmvn = nullptr;
+  float* fbank_tables = nullptr;                     // fa_fbank_make_tables output (owned)
   cudaStream_t st = nullptr;
   DevBuf wav, pcm16, lens, feats, flens, encb, acoustic, tok, alphas, peaks, ws, ids, best, fids, flens_out;
   ~Model() {
@@ -158,6 +159,13 @@ bool build(Model& m) {
     return (t && t->shape.size() == 3) ? (int)t->shape[2] : m.kernel;
   };
   m.mel = b.ptr("frontend.mel_banks"); m.window = b.ptr("frontend.window");
+  if (m.mel && m.window) {
+    void* tb = nullptr;
+    if (cudaMalloc(&tb, fa_fbank_tables_bytes()) != cudaSuccess) { set_err("cudaMalloc fbank tables"); return false; }
+    m.owned.push_back(tb);
+    m.fbank_tables = static_cast<float*>(tb);
+    if (fa_fbank_make_tables(m.mel, m.window, m.fbank_tables, m.st) != FA_OK) { set_err("fa_fbank_make_tables failed"); return false; }
+  }
   m.cmvn = m.t.count("frontend.cmvn") ? m.t["frontend.cmvn"].dev : nullptr;
   // encoder (engine.py:_enc_stack; SANMEncoder encoder.py:188-461)
   m.enc_l.resize(m.enc_layers);
@@ -262,8 +270,8 @@ extern "C" void* fa_offline_infer(void* handle, const void* const* bufs, const i
   const size_t ws2 = fa_cif_predictor_workspace_bytes(B, T, m.mode);
   ws = ws2 > ws ? ws2 : ws;
   FA_OFF(m.ws.reserve(ws), "device allocation failed (workspace)");
-  int rc = fa_fbank_lfr_cmvn(wav, static_cast<int32_t*>(m.lens.p), B, stride, m.cmvn, m.mel, m.window, static_cast<float*>(m.feats.p),
-                             static_cast<int32_t*>(m.flens.p), T, m.st);
+  int rc = fa_fbank_lfr_cmvn_tables(wav, static_cast<int32_t*>(m.lens.p), B, stride, m.cmvn, m.fbank_tables, 7, 6, static_cast<float*>(m.feats.p),
+                                    T, static_cast<int32_t*>(m.flens.p), T, m.st);
   FA_OFF(rc == FA_OK, std::string("fa_fbank_lfr_cmvn: ") + fa_status_string(rc));
   rc = fa_sanm_encoder_forward(&m.enc, static_cast<float*>(m.feats.p), static_cast<int32_t*>(m.flens.p), B, T, static_cast<float*>(m.encb.p),
                                m.mode, m.ws.p, m.ws.cap, m.st);

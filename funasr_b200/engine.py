@@ -46,25 +46,33 @@ def num_lfr_frames(n_samples: int, win=400, shift=160, lfr_n=6) -> int:
 
 
 class FrontendEngine:
-    """Fused Fbank+LFR+CMVN (fa_fbank_lfr_cmvn)."""
+    """Fused Fbank+LFR+CMVN (fa_fbank_lfr_cmvn_tables).  lfr_m / lfr_n: 7 / 6 (Paraformer, SenseVoice) or 5 / 1 (FSMN-VAD)."""
 
-    def __init__(self, cmvn: Optional[torch.Tensor], device):
+    def __init__(self, cmvn: Optional[torch.Tensor], device, lfr_m: int = 7, lfr_n: int = 6):
         self.lib = _abi.load()
         self.device = torch.device(device)
+        self.lfr_m, self.lfr_n = int(lfr_m), int(lfr_n)
+        self.feat_dim = 80 * self.lfr_m
         self.cmvn = None if cmvn is None else cmvn.to(self.device, torch.float32).contiguous()
+        if self.cmvn is not None and tuple(self.cmvn.shape) != (2, self.feat_dim):
+            raise _abi.FunasrB200Error("cmvn must be [2, %d] for lfr_m=%d" % (self.feat_dim, self.lfr_m))
         self.mel = kaldi_mel_banks().to(self.device)
         self.window = torch.hamming_window(400, periodic=False, alpha=0.54, beta=0.46, dtype=torch.float32).to(self.device)
+        # per-configuration constants (sparse mel support, twiddles, window), built once on the device
+        self.tables = torch.empty(int(self.lib.fa_fbank_tables_bytes()) // 4, dtype=torch.float32, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _abi.check(self.lib.fa_fbank_make_tables(self.mel.data_ptr(), self.window.data_ptr(), self.tables.data_ptr(), st), "fa_fbank_make_tables")
 
     def __call__(self, wav: torch.Tensor, wav_lens: torch.Tensor, t_max: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """wav [B, Nmax] fp32 on device, wav_lens [B] int32 on device -> feats [B, t_max, 560], feat_lens [B] int32."""
         assert wav.is_cuda and wav.dtype == torch.float32 and wav.stride(1) == 1
         B = wav.shape[0]
-        feats = torch.empty((B, t_max, 560), dtype=torch.float32, device=self.device)
+        feats = torch.empty((B, t_max, self.feat_dim), dtype=torch.float32, device=self.device)
         flens = torch.empty((B,), dtype=torch.int32, device=self.device)
         st = torch.cuda.current_stream(self.device).cuda_stream
-        _abi.check(self.lib.fa_fbank_lfr_cmvn(wav.data_ptr(), wav_lens.data_ptr(), B, wav.stride(0), _ptr(self.cmvn),
-                                              self.mel.data_ptr(), self.window.data_ptr(), feats.data_ptr(),
-                                              flens.data_ptr(), t_max, st), "fa_fbank_lfr_cmvn")
+        _abi.check(self.lib.fa_fbank_lfr_cmvn_tables(wav.data_ptr(), wav_lens.data_ptr(), B, wav.stride(0), _ptr(self.cmvn),
+                                                     self.tables.data_ptr(), self.lfr_m, self.lfr_n, feats.data_ptr(), t_max,
+                                                     flens.data_ptr(), t_max, st), "fa_fbank_lfr_cmvn_tables")
         return feats, flens
 
 
@@ -90,7 +98,7 @@ class _EngineBase:
         in_pad = (in_f + 63) // 64 * 64
         planes = None
         if self.mode != _abi.GEMM_F32_SIMT:
-            planes = torch.empty((3, out_f, in_pad), dtype=torch.bfloat16, device=self.device)
+            planes = torch.empty((3, out_f, in_pad), dtype=torch.float16, device=self.device)
             st = torch.cuda.current_stream(self.device).cuda_stream
             _abi.check(self.lib.fa_split_planes(w.data_ptr(), in_f, out_f, in_f, in_pad, planes.data_ptr(), st), "fa_split_planes")
             self._keep.append(planes)
@@ -598,9 +606,9 @@ class SenseVoiceEngine(_EngineBase):
         x = torch.empty((B, T, self.cfg.feat_dim), dtype=torch.float32, device=self.device)
         flens = torch.empty((B,), dtype=torch.int32, device=self.device)
         fe = self.frontend
-        _abi.check(self.lib.fa_fbank_lfr_cmvn_strided(wav.data_ptr(), wav_lens.data_ptr(), B, wav.stride(0), _ptr(fe.cmvn), fe.mel.data_ptr(),
-                                                      fe.window.data_ptr(), x.data_ptr() + 4 * self.cfg.feat_dim * 4, T, flens.data_ptr(),
-                                                      t_feat, self._stream()), "fa_fbank_lfr_cmvn_strided")
+        _abi.check(self.lib.fa_fbank_lfr_cmvn_tables(wav.data_ptr(), wav_lens.data_ptr(), B, wav.stride(0), _ptr(fe.cmvn), fe.tables.data_ptr(),
+                                                     7, 6, x.data_ptr() + 4 * self.cfg.feat_dim * 4, T, flens.data_ptr(),
+                                                     t_feat, self._stream()), "fa_fbank_lfr_cmvn_tables")
         q = self.query_rows(language_id, textnorm_id)
         _abi.check(self.lib.fa_broadcast_rows(q.data_ptr(), 4, self.cfg.feat_dim, x.data_ptr(), T, B, self._stream()), "fa_broadcast_rows")
         lens = torch.tensor([num_lfr_frames(int(n)) + 4 for n in host_lens], dtype=torch.int32).to(self.device, non_blocking=True)

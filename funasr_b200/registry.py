@@ -68,6 +68,9 @@ DROP_IN_KEYS = {
     ("predictor_classes", "CifPredictorV3"): "CifPredictorV3B200",
     ("model_classes", "BiCifParaformer"): "BiCifParaformerB200",
     ("model_classes", "SeacoParaformer"): "SeacoParaformerB200",
+    ("model_classes", "FsmnVADStreaming"): "FsmnVADStreamingB200",
+    ("encoder_classes", "FSMN"): "FSMNB200",
+    ("frontend_classes", "WavFrontendOnline"): "WavFrontendOnlineB200",
     ("model_classes", "ContextualParaformer"): "ContextualParaformerB200",
     ("decoder_classes", "ContextualParaformerDecoder"): "ContextualParaformerDecoderB200",
     ("model_classes", "SenseVoiceSmall"): "SenseVoiceSmallB200",

@@ -338,3 +338,105 @@ def sinusoid_inv_timescales(depth: int) -> torch.Tensor:
     """inv_timescales of SinusoidalPositionEncoder.encode (transformer/embedding.py:409-414), fp32 ops in the same order."""
     inc = torch.log(torch.tensor([10000], dtype=torch.float32)) / (depth / 2 - 1)
     return torch.exp(torch.arange(depth / 2).type(torch.float32) * (-inc))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FSMN-VAD (funasr/models/fsmn_vad_streaming: encoder FSMN, template.yaml:40-52)
+# ------------------------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class VadConfig:
+    input_dim: int = 400          # 80 mel x LFR 5 (lfr_n = 1)
+    input_affine_dim: int = 140
+    fsmn_layers: int = 4
+    linear_dim: int = 250
+    proj_dim: int = 128
+    lorder: int = 20
+    rorder: int = 0
+    output_affine_dim: int = 140
+    output_dim: int = 248
+    lfr_m: int = 5
+    lfr_n: int = 1
+    n_mels: int = 80
+
+
+VAD_DEFAULT = VadConfig()
+
+
+def make_vad_cmvn(seed: int = 0) -> torch.Tensor:
+    """[2, 400] (shift, scale) for the VAD frontend (80 mel x LFR 5)."""
+    g = torch.Generator().manual_seed(6007 * seed + 3)
+    mel = torch.arange(80, dtype=torch.float32) / 79
+    mean = (14.0 + 5.0 * mel).repeat(5)
+    shift = -(mean + _randn(g, 400, std=0.3))
+    scale = 0.8 + 0.4 * torch.rand(400, generator=g)
+    return torch.stack([shift, scale]).float()
+
+
+def make_vad_state_dict(cfg: VadConfig = VAD_DEFAULT, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Synthetic FSMN-VAD weights under the reference's names (encoder.in_linear1.linear.weight ...).  Random weights alone give a
+    silence posterior unrelated to the audio, so one hidden unit per layer carries a smoothed frame-energy signal from the
+    features to the silence logit (silence when the CMVN-normalised log-mel energy is low); every other weight is seeded noise at a
+    gain that perturbs but does not drown that signal.  The result segments bursty synthetic audio into several speech regions —
+    enough for the end-point logic, the 60 s chunking and the dynamic silence schedule to be exercised."""
+    g = torch.Generator().manual_seed(1000003 * seed + 131)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    A, L, P, O, V = cfg.input_affine_dim, cfg.linear_dim, cfg.proj_dim, cfg.output_affine_dim, cfg.output_dim
+
+    def lin(name, out_f, in_f, gain, bias=True):
+        sd[name + ".linear.weight"] = _randn(g, out_f, in_f, std=gain / math.sqrt(in_f))
+        if bias:
+            sd[name + ".linear.bias"] = _randn(g, out_f, std=0.05)
+
+    lin("encoder.in_linear1", A, cfg.input_dim, 0.5)
+    sd["encoder.in_linear1.linear.weight"][0] = 1.0 / cfg.input_dim                 # unit 0: mean normalised log-mel energy
+    sd["encoder.in_linear1.linear.bias"][0] = 0.0
+    lin("encoder.in_linear2", L, A, 0.5)
+    sd["encoder.in_linear2.linear.weight"][0] = 0.0
+    sd["encoder.in_linear2.linear.weight"][0, 0] = 1.0
+    sd["encoder.in_linear2.linear.bias"][0] = 4.0                                   # silence (~ -7) -> 0 after ReLU, speech (~ 0) -> ~4
+    for i in range(cfg.fsmn_layers):
+        p = "encoder.fsmn.%d" % i
+        lin(p + ".linear", P, L, 0.4, bias=False)
+        sd[p + ".linear.linear.weight"][0] = 0.0
+        sd[p + ".linear.linear.weight"][0, 0] = 1.0
+        sd[p + ".fsmn_block.conv_left.weight"] = _randn(g, P, 1, cfg.lorder, 1, std=0.03)
+        sd[p + ".fsmn_block.conv_left.weight"][0] = 0.025                           # energy channel: 20-frame smoothing
+        lin(p + ".affine", L, P, 0.5)
+        sd[p + ".affine.linear.weight"][0] = 0.0
+        sd[p + ".affine.linear.weight"][0, 0] = 0.66
+        sd[p + ".affine.linear.bias"][0] = 0.0
+    lin("encoder.out_linear1", O, L, 0.5)
+    sd["encoder.out_linear1.linear.weight"][0] = 0.0
+    sd["encoder.out_linear1.linear.weight"][0, 0] = 1.0
+    sd["encoder.out_linear1.linear.bias"][0] = 0.0
+    lin("encoder.out_linear2", V, O, 0.4)
+    sd["encoder.out_linear2.linear.weight"][:, 0] = 0.0
+    sd["encoder.out_linear2.linear.weight"][0, 0] = -1.4                            # silence logit falls with energy
+    sd["encoder.out_linear2.linear.bias"][0] = 8.0
+    return sd
+
+
+def make_vad_wav(seconds: float, seed: int = 0, pattern=None) -> torch.Tensor:
+    """Bursty 16 kHz test audio: speech-like stretches separated by near-silence.  pattern: [(speech_s, silence_s), ...] repeated
+    until `seconds`; default durations are drawn from the seed."""
+    n = int(seconds * 16000)
+    g = torch.Generator().manual_seed(7001 * seed + 19)
+    base = make_wav(min(n, 480000), 900 + seed, "speechlike")
+    reps = (n + base.numel() - 1) // base.numel()
+    x = base.repeat(reps)[:n].clone()
+    env = torch.zeros(n)
+    pos, k = int(0.3 * 16000 * float(torch.rand(1, generator=g))), 0
+    while pos < n:
+        if pattern:
+            sp, sl = pattern[k % len(pattern)]
+        else:
+            sp, sl = 0.6 + 5.0 * float(torch.rand(1, generator=g)), 0.15 + 2.8 * float(torch.rand(1, generator=g)) ** 2
+        a, b = pos, min(n, pos + int(sp * 16000))
+        env[a:b] = 1.0
+        pos = b + int(sl * 16000)
+        k += 1
+    ramp = 160
+    kern = torch.ones(1, 1, ramp) / ramp
+    env = torch.nn.functional.conv1d(torch.nn.functional.pad(env[None, None], (ramp // 2, ramp - ramp // 2 - 1)), kern)[0, 0]
+    noise = torch.randn(n, generator=g) * 0.0015
+    return (x * env + noise).clamp_(-1, 1).float().contiguous()

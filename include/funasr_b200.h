@@ -158,6 +158,16 @@ int fa_fbank_lfr_cmvn(const float* wav, const int32_t* wav_lens, int32_t batch, 
 int fa_fbank_lfr_cmvn_strided(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride,
                               const float* cmvn, const float* mel_banks, const float* window, float* feats,
                               int64_t feats_batch_stride_rows, int32_t* feat_lens, int32_t t_max, fa_stream_t stream);
+/* The same kernel fed with PRECOMPUTED constants (what the engines use): fa_fbank_make_tables derives, once per configuration,
+ * the sparse support of the 80 mel filters, the FFT twiddles and the window into `tables` (fa_fbank_tables_bytes() bytes of
+ * device memory), so that a CTA copies 9 KB instead of re-scanning the [80, 257] filter matrix.  lfr_m / lfr_n select the
+ * low-frame-rate stacking: 7 / 6 (Paraformer, SenseVoice: feats [B, t_max, 560]) or 5 / 1 (the FSMN-VAD frontend,
+ * fsmn_vad_streaming/template.yaml:54-62: feats [B, t_max, 400], one row per 10 ms frame); cmvn is [2, 80 * lfr_m] or NULL. */
+size_t fa_fbank_tables_bytes(void);
+int fa_fbank_make_tables(const float* mel_banks, const float* window, float* tables, fa_stream_t stream);
+int fa_fbank_lfr_cmvn_tables(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride, const float* cmvn,
+                             const float* tables, int32_t lfr_m, int32_t lfr_n, float* feats, int64_t feats_batch_stride_rows,
+                             int32_t* feat_lens, int32_t t_max, fa_stream_t stream);
 /* dst[b, r, :] = rows[r, :] for r < n_rows (dst rows of `cols` floats, utterances dst_batch_stride_rows apart):
  * the query-frame prepend `torch.cat((input_query, speech), dim=1)` of sense_voice/model.py:985-995. */
 int fa_broadcast_rows(const float* rows, int32_t n_rows, int32_t cols, float* dst, int64_t dst_batch_stride_rows,
@@ -319,6 +329,35 @@ int fa_linear_argmax(const FaLinear* lin, const float* a, const float* b_or_null
 int fa_seaco_merge(const int32_t* dec_ids, const float* dec_best, const int32_t* dha_ids, const float* dha_best, int64_t rows,
                    int32_t no_bias, int32_t* out_ids, float* out_best, const float* dec_logp, const float* dha_logp,
                    float* merged, int32_t vocab, fa_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FSMN-VAD (funasr/models/fsmn_vad_streaming): the encoder FSMN.forward (encoder.py:355-377) over the LFR-5/1 features of a whole
+ * waveform, reduced to the silence posterior per 10 ms frame that the end-point detector reads (model.py:789-792), and the frame
+ * energies of ComputeDecibel (model.py:458-529).  The detector itself is sequential threshold logic and stays on the host
+ * (funasr_b200/vad.py), as in the reference.
+ *   Weights are fp32 [out, in_padded] with the input dimension zero-padded to a multiple of 16 (FaLinear.in_f = padded width):
+ *   in1 400->140, in2 140(144)->250 + ReLU, per layer lin 250(256)->128 (no bias), conv_w [128, lorder] (causal depthwise taps,
+ *   tap lorder-1 = the current frame), affine 128->250 + ReLU, out1 250(256)->140, out2 140(144)->248.
+ *   feats [t, ld_feats] -> sil_prob [t]; scores != NULL additionally receives the full softmax [t, out2.out_f].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  FaLinear lin;
+  const float* conv_w;
+  FaLinear affine;
+} FaVadLayer;
+typedef struct {
+  FaLinear in1, in2;
+  const FaVadLayer* layers;
+  int32_t n_layers, lorder;
+  FaLinear out1, out2;
+  int32_t sil_ids[4];
+  int32_t n_sil, _pad;
+} FaVadEncoder;
+size_t fa_fsmn_vad_workspace_bytes(const FaVadEncoder* enc, int32_t t);
+int fa_fsmn_vad_forward(const FaVadEncoder* enc, const float* feats, int64_t ld_feats, int32_t t, float* sil_prob, float* scores,
+                        void* workspace, size_t ws_bytes, fa_stream_t stream);
+/* decibel[f] = 10 log10(sum_{j<400} wav[160 f + j]^2 + 1e-6), f < frames (ComputeDecibel, model.py:516-525). */
+int fa_frame_decibels(const float* wav, int64_t n_samples, int32_t frames, float* decibel, fa_stream_t stream);
 
 /* Greedy post-filter (paraformer/model.py:655-666): keep argmax_ids[b, k] for k < tok_lens[b] that are not
  * in {blank=0, sos=1, eos=2}; out_ids [B, n_max] (padded with -1), out_lens [B]. */

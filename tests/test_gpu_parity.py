@@ -137,7 +137,7 @@ def test_linear_tcgen05_vs_oracle(rows, out_f, in_f, mode, tol):
     r2 = torch.randn(rows, out_f, generator=g)
     xd, wd, bd, r1d, r2d = x.to(DEV), w.to(DEV), b.to(DEV), r1.to(DEV), r2.to(DEV)
     in_pad = (in_f + 63) // 64 * 64
-    planes = torch.empty(3, out_f, in_pad, dtype=torch.bfloat16, device=DEV)
+    planes = torch.empty(3, out_f, in_pad, dtype=torch.float16, device=DEV)
     abi.check(lib.fa_split_planes(wd.data_ptr(), in_f, out_f, in_f, in_pad, planes.data_ptr(), _st()), "split")
     torch.cuda.synchronize()
     assert rel_err((planes[0].float() + planes[1].float() + planes[2].float())[:, :in_f].cpu().numpy(), w.numpy()) <= 1e-7
@@ -883,3 +883,73 @@ def test_seaco_plugin_inference_with_timestamps():
     plain, _ = m.inference([w.numpy() for w in wavs], key=["a", "b"], tokenizer=None, frontend=fe, device=DEV)
     ref = O.bicif_forward(wavs, p, cmvn, cfg.enc_layers, cfg.dec_layers)
     assert [r["token_int"] for r in plain] == ref["ids"]
+
+
+# ------------------------------------------------------------------------------------------------ FSMN-VAD + long audio
+@pytest.mark.parametrize("name", ["vad_30s", "vad_130s", "vad_fixed800", "vad_random45", "vad_short", "vad_silence"])
+def test_fsmn_vad_vs_reference_golden(name):
+    """FSMN-VAD on the GPU against the UNMODIFIED reference (tests/golden/vad_*.npz from FsmnVADStreaming +
+    WavFrontendOnline through AutoModel.generate): fused Fbank + LFR 5/1 + CMVN, the FSMN encoder and the frame energies in one pass
+    over the whole waveform, the end-point detector on the host — silence posteriors within 1e-4, segment boundaries (integer
+    milliseconds) bit-exact, through the plugin class."""
+    import funasr_b200
+    from funasr_b200 import synth
+    from test_vad_host import VAD_CASES
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz")))
+    seconds, seed, pattern, kw = VAD_CASES[name]
+    wav = synth.make_vad_wav(seconds, seed, pattern)
+    c = synth.VAD_DEFAULT
+    m = funasr_b200.FsmnVADStreamingB200(encoder="FSMN", encoder_conf=dict(
+        input_dim=c.input_dim, input_affine_dim=c.input_affine_dim, fsmn_layers=c.fsmn_layers, linear_dim=c.linear_dim, proj_dim=c.proj_dim,
+        lorder=c.lorder, rorder=0, lstride=1, rstride=0, output_affine_dim=c.output_affine_dim, output_dim=c.output_dim))
+    m.load_state_dict(synth.make_vad_state_dict(c, 0), strict=True)
+    m.to(DEV).eval()
+    fe = funasr_b200.WavFrontendOnlineB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=5, lfr_n=1, dither=0.0,
+                                           cmvn=synth.make_vad_cmvn(0))
+    eng = m.engine(DEV, fe.cmvn)
+    sil, db, sc = eng.scores(wav.to(DEV), want_scores=True)
+    assert sil.numel() == g["sil_prob"].shape[0]
+    if sil.numel():
+        assert np.abs(sil.cpu().numpy() - g["sil_prob"]).max() <= 1e-4
+        assert np.abs(sc[g["score_rows"].tolist()].cpu().numpy() - g["score_sel"]).max() <= 1e-4
+        assert np.abs(db.cpu().numpy() - g["decibel"]).max() <= 1e-3
+    res, meta = m.inference(wav.numpy(), key=["k"], frontend=fe, device=DEV, **kw)
+    assert res[0]["key"] == "k" and res[0]["value"] == g["segments"].tolist()
+
+
+@pytest.mark.parametrize("name", ["longaudio_40s", "longaudio_25s_onebatch"])
+def test_long_audio_pipeline_vs_reference_golden(name):
+    """The whole long-audio path against the UNMODIFIED reference's AutoModel(model=Paraformer, vad_model=FsmnVADStreaming)
+    .generate() (inference_with_vad, auto_model.py:852-1035): VAD segments -> duration-sorted dynamic batches (batch_size_s) ->
+    padded-batch decoding -> results restored to time order and concatenated; greedy ids of the whole recording bit-exact."""
+    import funasr_b200
+    from funasr_b200 import synth
+    from test_abi_host import _tiny_conf
+    sys_path_cases = {"longaudio_40s": (40.0, 7, [(3.0, 2.5), (1.5, 2.2), (4.0, 3.0), (2.0, 2.2), (6.0, 2.4)], {"batch_size_s": 6}),
+                      "longaudio_25s_onebatch": (25.0, 8, [(2.0, 2.5), (3.0, 2.1)], {"batch_size_s": 300})}
+    seconds, seed, pattern, kw = sys_path_cases[name]
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz")))
+    wav = synth.make_vad_wav(seconds, seed, pattern)
+    assert wav.numel() == int(g["n_samples"])
+    cfg = synth.PARAFORMER_TINY
+    asr = funasr_b200.ParaformerB200(**_tiny_conf())
+    asr.load_state_dict(synth.make_state_dict(cfg, 3), strict=True)
+    asr.to(DEV).eval()
+    asr_fe = funasr_b200.WavFrontendB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0,
+                                         cmvn=synth.make_cmvn(cfg, 1))
+    c = synth.VAD_DEFAULT
+    vad = funasr_b200.FsmnVADStreamingB200(encoder="FSMN", encoder_conf=dict(
+        input_dim=c.input_dim, input_affine_dim=c.input_affine_dim, fsmn_layers=c.fsmn_layers, linear_dim=c.linear_dim, proj_dim=c.proj_dim,
+        lorder=c.lorder, rorder=0, lstride=1, rstride=0, output_affine_dim=c.output_affine_dim, output_dim=c.output_dim))
+    vad.load_state_dict(synth.make_vad_state_dict(c, 0), strict=True)
+    vad.to(DEV).eval()
+    vad_fe = funasr_b200.WavFrontendOnlineB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=5, lfr_n=1,
+                                               dither=0.0, cmvn=synth.make_vad_cmvn(0))
+    pipe = funasr_b200.LongAudioPipeline(asr, asr_fe, vad, vad_fe, device=DEV)
+    out = pipe.generate(wav.numpy(), key="rec", pred_timestamp=True, **kw)
+    assert len(out["vad_segments"]) >= 2
+    assert out["token_int"] == g["ids"].tolist()
+    # timestamps of every segment are shifted by its start and stay inside it (auto_model.py:1008-1022)
+    assert len(out["timestamp"]) == len(out["token_int"])
+    assert all(a <= b for a, b in out["timestamp"]) and out["timestamp"][0][0] >= out["vad_segments"][0][0]
+    assert out["timestamp"][-1][1] <= out["vad_segments"][-1][1] + 60

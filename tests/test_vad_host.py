@@ -1,0 +1,79 @@
+"""CPU: the FSMN-VAD host logic (funasr_b200/vad.py: end-point detector, the reference's chunked frame delivery, the dynamic
+end-silence schedule) and the oracle restatement of the VAD scores (oracle/vad_oracle.py) against golden vectors produced by the
+UNMODIFIED reference (oracle/make_vad_golden.py: FsmnVADStreaming + WavFrontendOnline through AutoModel.generate)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+import vad_oracle as VO
+from funasr_b200 import synth, vad
+
+# must match oracle/make_vad_golden.py:VAD_CASES
+VAD_CASES = {
+    "vad_30s": (30.0, 1, [(3.0, 2.5), (1.5, 0.4), (4.0, 3.0), (2.0, 2.2)], {}),
+    "vad_130s": (130.0, 2, [(70.0, 2.5), (5.0, 0.3), (20.0, 2.1), (10.0, 3.0)], {}),
+    "vad_fixed800": (30.0, 3, [(2.0, 1.0), (3.0, 0.5), (1.0, 1.5)], {"max_end_silence_time": 800}),
+    "vad_random45": (45.0, 4, None, {}),
+    "vad_short": (1.2, 5, [(5.0, 0.1)], {}),
+    "vad_silence": (3.0, 6, [(0.0, 9.0)], {}),
+}
+
+
+def _gold(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+@pytest.mark.parametrize("name", list(VAD_CASES))
+def test_detector_reproduces_reference_segments_from_reference_scores(name):
+    """Given the reference's OWN per-frame silence posteriors and frame energies, the restated detector returns the reference's
+    segments exactly (integer milliseconds) — incl. the 130 s case that crosses two 60 s chunk boundaries (frame delivery per
+    chunk, dynamic end-silence schedule, the 60 s maximum segment length) and the fixed-threshold case."""
+    g = _gold(name)
+    kw = VAD_CASES[name][3]
+    got = vad.detect_segments(g["sil_prob"].tolist(), g["decibel"].tolist(), int(g["n_samples"]), **kw)
+    assert got == g["segments"].tolist()
+    assert [c for c in vad.chunk_frame_counts(int(g["n_samples"])) if c > 0] == g["chunk_frames"].tolist()
+
+
+@pytest.mark.parametrize("name", ["vad_30s", "vad_130s", "vad_short"])
+def test_vad_oracle_scores_match_reference(name):
+    """The whole-waveform restatement of frontend + FSMN equals what the reference computed chunk by chunk through its stateful
+    online frontend and encoder caches."""
+    g = _gold(name)
+    seconds, seed, pattern, _ = VAD_CASES[name]
+    wav = synth.make_vad_wav(seconds, seed, pattern)
+    assert wav.numel() == int(g["n_samples"])
+    o = VO.vad_scores(wav, synth.make_vad_state_dict(synth.VAD_DEFAULT, 0), synth.make_vad_cmvn(0))
+    assert o["sil_prob"].numel() == g["sil_prob"].shape[0]
+    assert np.abs(o["sil_prob"].numpy() - g["sil_prob"]).max() <= 2e-5
+    assert np.abs(o["scores"][g["score_rows"].tolist()].numpy() - g["score_sel"]).max() <= 2e-5
+    assert np.abs(o["decibel"].numpy() - g["decibel"]).max() <= 1e-3
+    # and the end-to-end CPU chain oracle scores -> detector reproduces the reference's segments
+    got = vad.detect_segments(o["sil_prob"].tolist(), o["decibel"].tolist(), wav.numel(), **VAD_CASES[name][3])
+    assert got == g["segments"].tolist()
+
+
+def test_chunk_frame_counts_cover_every_frame():
+    for n in [399, 400, 559, 560, 1200, 16000, 959999, 960000, 960001, 960399, 960400, 1919999, 1920000, 2080000, 5000000]:
+        c = vad.chunk_frame_counts(n)
+        assert len(c) == n // 960000 + 1
+        total = vad.num_frames(n)
+        assert sum(c) == (total if total >= 3 else 0), (n, c, total)      # fewer than lfr_m - 2 frames: the online LFR never emits
+
+
+def test_merge_vad_matches_reference_function():
+    segs = [[0, 2450], [2990, 7940], [8970, 11440], [11990, 16920], [17970, 20440], [21030, 25940], [27000, 40000]]
+    assert vad.merge_vad(segs, 15000) == [[0, 11990], [11990, 25940], [25940, 40000]]
+    assert vad.merge_vad([[5, 9]], 15000) == [[5, 9]]
+    if os.path.isdir("/root/reference/funasr"):
+        import ref_shim
+        ref_shim.import_reference()
+        from funasr.utils.vad_utils import merge_vad as ref_merge
+        g = np.random.default_rng(0)
+        for _ in range(50):
+            t = np.sort(g.integers(0, 200000, size=2 * int(g.integers(1, 12)))).reshape(-1, 2).tolist()
+            assert vad.merge_vad([list(x) for x in t], 15000) == ref_merge([list(x) for x in t], 15000)

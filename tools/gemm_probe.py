@@ -12,7 +12,7 @@ g = torch.Generator().manual_seed(0)
 x = torch.randn(M, K, generator=g).to(dev)
 w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
 b = torch.randn(N, generator=g).to(dev)
-planes = torch.empty(3, N, K, dtype=torch.bfloat16, device=dev)
+planes = torch.empty(3, N, K, dtype=torch.float16, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 _abi.check(lib.fa_split_planes(w.data_ptr(), K, N, K, K, planes.data_ptr(), st), "split")
 lin = _abi.FaLinear(w.data_ptr(), b.data_ptr(), planes.data_ptr(), N, K, K, 0)

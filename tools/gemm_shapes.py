@@ -20,10 +20,10 @@ def run(name, N, K, n_res, relu=0, iters=8):
     x = torch.randn(M, K, generator=g).to(dev)
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
     b = torch.randn(N, generator=g).to(dev)
-    wp = torch.empty(3, N, K, dtype=torch.bfloat16, device=dev)
+    wp = torch.empty(3, N, K, dtype=torch.float16, device=dev)
     _abi.check(lib.fa_split_planes(w.data_ptr(), K, N, K, K, wp.data_ptr(), st), "split")
     lin = _abi.FaLinear(w.data_ptr(), b.data_ptr(), wp.data_ptr(), N, K, K, 0)
-    xp = torch.empty(2, M, K, dtype=torch.bfloat16, device=dev)
+    xp = torch.empty(2, M, K, dtype=torch.float16, device=dev)
     _abi.check(lib.fa_split_rows(x.data_ptr(), K, M, K, K, 2, xp.data_ptr(), st), "split_rows")
     y = torch.empty(M, N, device=dev)
     r1 = torch.randn(M, N, device=dev) if n_res >= 1 else None
