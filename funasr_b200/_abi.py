@@ -120,6 +120,9 @@ SIGNATURES = {
     # handle-style offline recogniser (funasrruntime.h:100-116 counterpart; offline.cu)
     "fa_offline_init": (_vp, [C.c_char_p, _i32, _i32]),
     "fa_offline_infer": (_vp, [_vp, C.POINTER(_vp), C.POINTER(_i64), _i32, _i32]),
+    "fa_offline_infer_hw": (_vp, [_vp, C.POINTER(_vp), C.POINTER(_i64), _i32, _i32, _vp, _i32]),
+    "fa_offline_is_contextual": (_i32, [_vp]),
+    "fa_offline_host_tensor": (_vp, [_vp, C.c_char_p, C.POINTER(_i64)]),
     "fa_offline_result_count": (_i32, [_vp]),
     "fa_offline_result_ids": (C.POINTER(_i32), [_vp, _i32, C.POINTER(_i32)]),
     "fa_offline_result_audio_seconds": (C.c_float, [_vp]),

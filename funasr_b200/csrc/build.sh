@@ -14,6 +14,12 @@ for f in fbank layernorm gemm_f32 gemm_tc attention_tc attention_f32 fsmn cif de
   fi
   objs="$objs ../_build/$f.o"
 done
+# host-only C++: the FunOffline* shim with the reference runtime's C++ signatures (include/funasrruntime_b200.h)
+if [ ! -f ../_build/runtime_shim.o ] || [ runtime_shim.cpp -nt ../_build/runtime_shim.o ] || [ ../../include/funasrruntime_b200.h -nt ../_build/runtime_shim.o ] || [ ../../include/funasr_b200.h -nt ../_build/runtime_shim.o ]; then
+  ( g++ -O2 -std=c++17 -fPIC -c runtime_shim.cpp -o ../_build/runtime_shim.o 2> ../_build/runtime_shim.log || { cat ../_build/runtime_shim.log; rm -f ../_build/runtime_shim.o; exit 1; } ) &
+  pids="$pids $!"
+fi
+objs="$objs ../_build/runtime_shim.o"
 for p in $pids; do wait $p || exit 1; done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libfunasr_b200.so $objs -lcudart
 echo "built $(cd ..; pwd)/libfunasr_b200.so"

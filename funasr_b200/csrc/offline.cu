@@ -55,7 +55,9 @@ struct Model {
   const float *mel = nullptr, *window = nullptr, *cmvn = nullptr;
   float* fbank_tables = nullptr;                     // fa_fbank_make_tables output (owned)
   cudaStream_t st = nullptr;
-  DevBuf wav, pcm16, lens, feats, flens, encb, acoustic, tok, alphas, peaks, ws, ids, best, fids, flens_out;
+  DevBuf wav, pcm16, lens, feats, flens, encb, acoustic, tok, alphas, peaks, ws, ids, best, fids, flens_out, hw, hw_lens;
+  bool contextual = false;                           // ContextualParaformer: decoder with a hotword bias branch
+  std::map<std::string, std::vector<float>> host_cache;   // fa_offline_host_tensor
   ~Model() {
     for (auto& kv : t) if (kv.second.dev) cudaFree(kv.second.dev);
     for (void* p : owned) cudaFree(p);
@@ -129,7 +131,8 @@ struct Builder {
   FaLinear lin(const std::string& p, bool bias = true, const char* weight_key = nullptr) {
     FaLinear L{};
     const Tensor* w = get(weight_key ? std::string(weight_key) : p + ".weight");
-    if (!w || w->shape.size() != 2) { if (ok) set_err("bad weight " + p); ok = false; return L; }
+    // [out, in] or a k = 1 Conv1d weight [out, in, 1] (bias_output, contextual_paraformer/decoder.py:287)
+    if (!w || !(w->shape.size() == 2 || (w->shape.size() == 3 && w->shape[2] == 1))) { if (ok) set_err("bad weight " + p); ok = false; return L; }
     L.w = w->dev; L.b = bias ? ptr(p + ".bias") : nullptr;
     L.out_f = (int32_t)w->shape[0]; L.in_f = (int32_t)w->shape[1]; L.in_pad = (L.in_f + 63) / 64 * 64;
     if (m.mode != FA_GEMM_F32_SIMT) {
@@ -193,12 +196,25 @@ bool build(Model& m) {
       L.q = b.lin(p + ".src_attn.linear_q"); L.kv = b.lin(p + ".src_attn.linear_k_v"); L.out = b.lin(p + ".src_attn.linear_out");
     }
   };
-  m.dec_l.resize(m.dec_layers);
-  for (int i = 0; i < m.dec_layers; ++i) dec_layer(m.dec_l[i], "decoder.decoders." + std::to_string(i), true);
-  m.dec.layers = m.dec_l.data(); m.dec.n_layers = m.dec_layers; m.dec.heads = m.heads; m.dec.fsmn_k = fsmn_taps("decoder.decoders.0.self_attn.fsmn_block.weight"); m.dec.vocab = m.vocab;
+  // ContextualParaformerDecoder (contextual_paraformer/decoder.py:133-352): the last attention layer is `last_decoder`, plus the
+  // hotword branch bias_decoder (norm3 + cross attention) and bias_output (Conv1d 1024 -> 512, k = 1)
+  m.contextual = m.t.count("decoder.bias_decoder.norm3.weight") > 0;
+  const int n_plain = m.contextual ? m.dec_layers - 1 : m.dec_layers;
+  m.dec_l.resize(n_plain > 0 ? n_plain : 1);
+  for (int i = 0; i < n_plain; ++i) dec_layer(m.dec_l[i], "decoder.decoders." + std::to_string(i), true);
+  m.dec.layers = m.dec_l.data(); m.dec.n_layers = n_plain; m.dec.heads = m.heads; m.dec.vocab = m.vocab;
+  m.dec.fsmn_k = fsmn_taps(n_plain > 0 ? "decoder.decoders.0.self_attn.fsmn_block.weight" : "decoder.last_decoder.self_attn.fsmn_block.weight");
   dec_layer(m.dec.last, "decoder.decoders3.0", false);
   m.dec.after_norm = b.norm("decoder.after_norm"); m.dec.output = b.lin("decoder.output_layer");
   m.dec.has_bias = 0;
+  if (m.contextual) {
+    dec_layer(m.dec.bias_last, "decoder.last_decoder", true);
+    m.dec.bias_norm3 = b.norm("decoder.bias_decoder.norm3");
+    m.dec.bias_q = b.lin("decoder.bias_decoder.src_attn.linear_q"); m.dec.bias_kv = b.lin("decoder.bias_decoder.src_attn.linear_k_v");
+    m.dec.bias_out = b.lin("decoder.bias_decoder.src_attn.linear_out");
+    m.dec.bias_output = b.lin("decoder.bias_output", false);
+    m.dec.clas_scale = 1.0f;
+  }
   if (!b.ok) return false;
   return cudaStreamSynchronize(m.st) == cudaSuccess;
 }
@@ -211,6 +227,8 @@ int num_lfr_frames(int64_t n) {       // wav_frontend.py:73 after kaldi.py snip_
 }  // namespace
 
 extern "C" const char* fa_offline_last_error(void) { return g_err.c_str(); }
+extern "C" void* fa_offline_infer_hw(void* handle, const void* const* bufs, const int64_t* n_samples, int32_t batch, int32_t pcm_format,
+                                     const float* hw_embed, int32_t n_hotwords);
 
 extern "C" void* fa_offline_init(const char* model_file, int32_t device, int32_t gemm_mode) {
   g_err.clear();
@@ -228,11 +246,35 @@ extern "C" void* fa_offline_init(const char* model_file, int32_t device, int32_t
 
 extern "C" void fa_offline_uninit(void* handle) { delete static_cast<Model*>(handle); }
 
+extern "C" int32_t fa_offline_is_contextual(const void* handle) { return handle && static_cast<const Model*>(handle)->contextual ? 1 : 0; }
+
+extern "C" const float* fa_offline_host_tensor(void* handle, const char* name, int64_t* numel) {
+  Model* m = static_cast<Model*>(handle);
+  if (numel) *numel = 0;
+  if (!m || !name) return nullptr;
+  auto it = m->t.find(name);
+  if (it == m->t.end()) return nullptr;
+  auto& hc = m->host_cache[name];
+  if (hc.empty() && it->second.numel() > 0) {
+    hc.resize((size_t)it->second.numel());
+    cudaSetDevice(m->device);
+    if (cudaMemcpy(hc.data(), it->second.dev, hc.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { hc.clear(); return nullptr; }
+  }
+  if (numel) *numel = (int64_t)hc.size();
+  return hc.data();
+}
+
 extern "C" void* fa_offline_infer(void* handle, const void* const* bufs, const int64_t* n_samples, int32_t batch, int32_t pcm_format) {
+  return fa_offline_infer_hw(handle, bufs, n_samples, batch, pcm_format, nullptr, 0);
+}
+
+extern "C" void* fa_offline_infer_hw(void* handle, const void* const* bufs, const int64_t* n_samples, int32_t batch, int32_t pcm_format,
+                                     const float* hw_embed, int32_t n_hotwords) {
   g_err.clear();
   Model* mp = static_cast<Model*>(handle);
   if (!mp || !bufs || !n_samples || batch <= 0 || (pcm_format != 0 && pcm_format != 1)) { set_err("bad argument"); return nullptr; }
   Model& m = *mp;
+  if (m.contextual && (!hw_embed || n_hotwords < 1)) { set_err("this model has a hotword bias decoder: pass hotword embeddings (at least the <s> entry)"); return nullptr; }
   cudaSetDevice(m.device);
   int64_t nmax = 0;
   double seconds = 0.0;
@@ -289,9 +331,19 @@ extern "C" void* fa_offline_infer(void* handle, const void* const* bufs, const i
   for (int i = 0; i < B; ++i) n_max = r->token_num[i] > n_max ? r->token_num[i] : n_max;
   r->ids.resize(B);
   if (n_max < 1) return r;                                   // paraformer/model.py:615-616
+  const int nh = m.contextual ? n_hotwords : 0;
   if (!(m.ids.reserve((size_t)B * n_max * 4) && m.best.reserve((size_t)B * n_max * 4) && m.fids.reserve((size_t)B * n_max * 4) &&
-        m.flens_out.reserve((size_t)B * 4) && m.ws.reserve(fa_paraformer_decoder_workspace_bytes(B, T, n_max, m.vocab, m.mode)))) {
+        m.flens_out.reserve((size_t)B * 4) && m.ws.reserve(fa_paraformer_decoder_workspace_bytes_hw(B, T, n_max, m.vocab, m.mode, nh)))) {
     set_err("device allocation failed (decoder)"); delete r; return nullptr;
+  }
+  if (m.contextual) {                                        // hotword memory [n_hw, 512] (contextual_paraformer/model.py:350-372) + per-utterance counts
+    if (!(m.hw.reserve((size_t)nh * D * 4) && m.hw_lens.reserve((size_t)B * 4))) { set_err("device allocation failed (hotwords)"); delete r; return nullptr; }
+    std::vector<int32_t> hl(B, nh);
+    cudaMemcpyAsync(m.hw.p, hw_embed, (size_t)nh * D * 4, cudaMemcpyHostToDevice, m.st);
+    cudaMemcpyAsync(m.hw_lens.p, hl.data(), (size_t)B * 4, cudaMemcpyHostToDevice, m.st);
+    cudaStreamSynchronize(m.st);                             // hl is a stack vector
+    m.dec.has_bias = 1; m.dec.n_hotwords = nh;
+    m.dec.hw_embed = static_cast<const float*>(m.hw.p); m.dec.hw_lens = static_cast<const int32_t*>(m.hw_lens.p);
   }
   rc = fa_paraformer_decoder_forward(&m.dec, static_cast<float*>(m.encb.p), static_cast<int32_t*>(m.flens.p), B, T, static_cast<float*>(m.acoustic.p),
                                      n_cap, static_cast<int32_t*>(m.tok.p), n_max, static_cast<int32_t*>(m.ids.p), static_cast<float*>(m.best.p),

@@ -36,7 +36,7 @@ def model_tensors(state: Dict[str, torch.Tensor], cfg: ParaformerConfig, cmvn: O
         out["frontend.cmvn"] = cmvn.detach().float().cpu().numpy()
     out["encoder.pe_inv_timescales"] = sinusoid_inv_timescales(cfg.feat_dim).float().numpy()
     for k, v in state.items():
-        if k.startswith(("encoder.", "predictor.", "decoder.")) and torch.is_floating_point(v):
+        if k.startswith(("encoder.", "predictor.", "decoder.", "bias_encoder.", "bias_embed.")) and torch.is_floating_point(v):
             out[k] = v.detach().float().cpu().contiguous().numpy()
     cw = state["predictor.cif_conv1d.weight"].detach().float().cpu()
     out["predictor.cif_conv1d.gemm_weight"] = cw.permute(0, 2, 1).reshape(cw.shape[0], -1).contiguous().numpy()

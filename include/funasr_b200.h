@@ -401,6 +401,15 @@ int fa_split_planes(const float* src, int64_t ld_src, int64_t rows, int32_t cols
  * ------------------------------------------------------------------------------------------- */
 void* fa_offline_init(const char* model_file, int32_t device, int32_t gemm_mode);
 void* fa_offline_infer(void* handle, const void* const* bufs, const int64_t* n_samples, int32_t batch, int32_t pcm_format);
+/* Same with a hotword memory for a ContextualParaformer model file (FunOfflineInferBuffer's `hw_emb`, funasrruntime.h:104): hw_embed
+ * is HOST memory [n_hotwords, 512], the rows CompileHotwordEmbedding produces (last entry = the <s> hotword).  Required when
+ * fa_offline_is_contextual(handle), ignored otherwise. */
+void* fa_offline_infer_hw(void* handle, const void* const* bufs, const int64_t* n_samples, int32_t batch, int32_t pcm_format,
+                          const float* hw_embed, int32_t n_hotwords);
+int32_t fa_offline_is_contextual(const void* handle);
+/* Host copy of a tensor of the model file by its FunASR state_dict name (e.g. "bias_embed.weight" for the hotword encoder that
+ * runs on the host); owned by the handle.  NULL if absent. */
+const float* fa_offline_host_tensor(void* handle, const char* name, int64_t* numel);
 int32_t fa_offline_result_count(const void* result);
 const int32_t* fa_offline_result_ids(const void* result, int32_t index, int32_t* n_ids);
 float fa_offline_result_audio_seconds(const void* result);

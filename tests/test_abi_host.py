@@ -274,3 +274,23 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert run.returncode == 0 and "library: funasr_b200" in run.stdout
     if not torch.cuda.is_available():
         assert "init failed" in run.stdout
+
+
+def test_funoffline_client_links_against_the_reference_header(tmp_path):
+    """Link compatibility of the C++ runtime surface: the client of examples/offline_runtime_client.cpp (the call sequence of
+    runtime/onnxruntime/bin/funasr-onnx-offline.cpp) compiled against the REFERENCE's own funasrruntime.h (when /root/reference is
+    present; this repo's copy of the declarations otherwise) links against libfunasr_b200.so — same names, same C++ argument types,
+    so the mangled symbols resolve — and fails cleanly (no CPU path, no model) when run without a GPU."""
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    ref_hdr = "/root/reference/runtime/onnxruntime/include/funasrruntime.h"
+    exe = str(tmp_path / "client")
+    for hdr, inc in ((('"funasrruntime.h"', os.path.dirname(ref_hdr)),) if os.path.exists(ref_hdr) else ()) + (('"funasrruntime_b200.h"', os.path.join(ROOT, "include")),):
+        cmd = ["g++", "-std=c++17", "-DFUNASR_RUNTIME_HEADER=" + hdr, "-I" + inc, "-I" + os.path.join(ROOT, "include"),
+               os.path.join(ROOT, "examples", "offline_runtime_client.cpp"), "-L" + os.path.join(ROOT, "funasr_b200"), "-lfunasr_b200",
+               "-Wl,-rpath," + os.path.join(ROOT, "funasr_b200"), "-o", exe]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-2000:]
+    r = subprocess.run([exe, str(tmp_path), str(tmp_path / "none.wav")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 1 and "init failed" in r.stdout

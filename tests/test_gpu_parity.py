@@ -953,3 +953,72 @@ def test_long_audio_pipeline_vs_reference_golden(name):
     assert len(out["timestamp"]) == len(out["token_int"])
     assert all(a <= b for a, b in out["timestamp"]) and out["timestamp"][0][0] >= out["vad_segments"][0][0]
     assert out["timestamp"][-1][1] <= out["vad_segments"][-1][1] + 60
+
+
+# ------------------------------------------------------------------------------------ FunOffline* (C++ runtime surface)
+def _cjk_tokens(vocab):
+    return ["<blank>", "<s>", "</s>"] + [chr(0x4E00 + i) for i in range(3, vocab)]
+
+
+def _write_wav16(path, wav):
+    import struct
+    pcm = np.clip(np.round(wav.numpy() * 32768.0), -32768, 32767).astype("<i2")
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + pcm.nbytes) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, 16000, 32000, 2, 16))
+        f.write(b"data" + struct.pack("<I", pcm.nbytes) + pcm.tobytes())
+    return pcm
+
+
+@pytest.mark.parametrize("contextual", [False, True])
+def test_funoffline_cpp_client_end_to_end(tmp_path, contextual):
+    """The C++ client (examples/offline_runtime_client.cpp: FunOfflineInit / CompileHotwordEmbedding / FunOfflineInfer /
+    FunOfflineInferBuffer / FunASRGetResult ... with the reference runtime's signatures) on a model directory written by pack.py:
+    the text it prints maps back to exactly the ids of the Python path on the same 16-bit audio — plain Paraformer, and
+    ContextualParaformer with multi-token hotwords compiled by the shim's host LSTM (hw_emb -> the CUDA bias decoder)."""
+    import subprocess
+    import funasr_b200
+    from funasr_b200 import pack, synth
+    from test_abi_host import _tiny_conf
+    cfg = synth.PARAFORMER_TINY
+    cmvn = synth.make_cmvn(cfg, 1)
+    wav = synth.make_wav(48000, 21 if contextual else 1, "speechlike")
+    state = synth.make_contextual_state_dict(cfg, 6) if contextual else synth.make_state_dict(cfg, 3)
+    mdir = tmp_path / "model"
+    mdir.mkdir()
+    pack.write_model_file(str(mdir / "model.fab2"), state, cfg, cmvn)
+    toks = _cjk_tokens(cfg.vocab)
+    (mdir / "tokens.txt").write_text("\n".join(toks) + "\n", encoding="utf-8")
+    pcm = _write_wav16(str(tmp_path / "a.wav"), wav)
+    deq = torch.from_numpy(pcm.astype(np.float32) / 32768.0)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "client")
+    r = subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "offline_runtime_client.cpp"),
+                        "-L" + os.path.join(root, "funasr_b200"), "-lfunasr_b200", "-Wl,-rpath," + os.path.join(root, "funasr_b200"), "-o", exe],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-1500:]
+    hw = synth.make_hotwords(5, cfg.vocab, seed=7)
+    hot_str = " ".join("".join(toks[t] for t in h) for h in hw[:-1]) if contextual else ""
+    r = subprocess.run([exe, str(mdir), str(tmp_path / "a.wav"), "fp16x3", hot_str], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-1500:]
+    out = dict(ln.split(" ", 1) for ln in r.stdout.strip().splitlines() if " " in ln)
+    ids_file = [toks.index(c) for c in out["file_result"].strip()]
+    ids_buf = [toks.index(c) for c in out["buffer_result"].strip()]
+    assert ids_file == ids_buf and len(ids_file) > 0
+    assert abs(float(out["audio_seconds"]) - 2 * 3.0) < 1e-3
+    # the Python path on the same dequantised audio
+    conf = _tiny_conf()
+    conf["gemm_mode"] = "fp16x3"
+    fe = funasr_b200.WavFrontendB200(fs=16000, window="hamming", n_mels=80, frame_length=25, frame_shift=10, lfr_m=7, lfr_n=6, dither=0.0, cmvn=cmvn)
+    if contextual:
+        conf["decoder"] = "ContextualParaformerDecoderB200"
+        m = funasr_b200.ContextualParaformerB200(**conf)
+        m.load_state_dict(state, strict=True)
+        m.to(DEV).eval()
+        res, _ = m.inference([deq.numpy()], key=["a"], tokenizer=None, frontend=fe, device=DEV, hotword_ids=hw)
+        assert int(out["hotword_rows"]) == len(hw)
+    else:
+        m = funasr_b200.ParaformerB200(**conf)
+        m.load_state_dict(state, strict=True)
+        m.to(DEV).eval()
+        res, _ = m.inference([deq.numpy()], key=["a"], tokenizer=None, frontend=fe, device=DEV)
+    assert ids_file == res[0]["token_int"]
