@@ -149,18 +149,22 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
       FA_RETURN_IF_ERR(linear(u, in, M, L.qkv, 0, nullptr, 0, nullptr, 0, qkv, 3 * D, gemm_mode, &scratch, st));
     }
     SideStream* side = tc ? side_stream(st) : nullptr;
-    if (side) {                                     // FSMN memory branch runs beside the attention kernel (both need only QKV)
-      FA_CUDA_OK(cudaEventRecord(side->fork, st));
-      FA_CUDA_OK(cudaStreamWaitEvent(side->st, side->fork, 0));
-      FA_RETURN_IF_ERR(fsmn_launch(qkv + 2 * D, 3 * D, lens, batch, t_max, D, L.fsmn_w, enc->fsmn_k, nullptr, 0, mem, D, side->st));
-      FA_CUDA_OK(cudaEventRecord(side->join, side->st));
-    } else {
-      FA_RETURN_IF_ERR(fsmn_launch(qkv + 2 * D, 3 * D, lens, batch, t_max, D, L.fsmn_w, enc->fsmn_k, nullptr, 0, mem, D, st));
-    }
     // x2 = (residual if in_size == size) + (linear_out(ctx) + fsmn_memory)     encoder.py:120-137, attention.py:327
     float* x2 = (x == xa) ? xb : xa;
     const float* res = (in == D && x != nullptr) ? x : nullptr;
     float* x3 = (x2 == xa) ? xb : xa;
+    // tensor-core path: the FSMN kernel (HBM bound, on the side stream beside the latency-bound attention kernel) also adds the
+    // layer's residual, so the out-projection epilogue reads ONE fp32 stream instead of two (it was bound by those reads:
+    // 198 MB in 69 us, tensor pipe 43 %).  fp32 path: the reference's own association ((att + mem) + residual) is kept.
+    const float* fsmn_res = tc ? res : nullptr;
+    if (side) {                                     // FSMN memory branch runs beside the attention kernel (both need only QKV)
+      FA_CUDA_OK(cudaEventRecord(side->fork, st));
+      FA_CUDA_OK(cudaStreamWaitEvent(side->st, side->fork, 0));
+      FA_RETURN_IF_ERR(fsmn_launch(qkv + 2 * D, 3 * D, lens, batch, t_max, D, L.fsmn_w, enc->fsmn_k, fsmn_res, D, mem, D, side->st));
+      FA_CUDA_OK(cudaEventRecord(side->join, side->st));
+    } else {
+      FA_RETURN_IF_ERR(fsmn_launch(qkv + 2 * D, 3 * D, lens, batch, t_max, D, L.fsmn_w, enc->fsmn_k, fsmn_res, D, mem, D, st));
+    }
     if (!tc) {
       FA_RETURN_IF_ERR(attention_f32_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, t_max,
                                             t_max, ctx, D, st));
@@ -174,7 +178,7 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
       FA_RETURN_IF_ERR(attention_tc_planes_launch(q_planes, k_planes, vt_planes, lens, batch, enc->heads, t_max, t_max, nullptr, 0,
                                                   ctx_planes, D, npl, gemm_mode, st));
       if (side) FA_CUDA_OK(cudaStreamWaitEvent(st, side->join, 0));          // join: linear_out adds the FSMN memory
-      FA_RETURN_IF_ERR(gemm_tc_planes_launch(ctx_planes, M, L.out, 0, mem, D, res, D, x2, D, nullptr, 0, gemm_mode, st));
+      FA_RETURN_IF_ERR(gemm_tc_planes_launch(ctx_planes, M, L.out, 0, mem, D, nullptr, 0, x2, D, nullptr, 0, gemm_mode, st));   // mem already holds residual + memory
       if (L.w1.out_f != L.w2.in_pad || L.w1.in_pad != D) return FA_ERR_UNSUPPORTED;
       FA_RETURN_IF_ERR(layernorm_launch(x2, M, L.norm2, nullptr, nullptr, 1.f, t_max, st, u_planes, npl, D));
       FA_RETURN_IF_ERR(gemm_tc_planes_launch(u_planes, M, L.w1, 1, nullptr, 0, nullptr, 0, nullptr, 0, h_planes, L.w1.out_f, gemm_mode, st));
