@@ -19,5 +19,7 @@ from .batching import bucket_by_length, padding_efficiency, run_bucketed  # noqa
 from .vad import VadOptions, detect_segments, merge_vad  # noqa: F401
 from .vad_model import FSMNB200, FsmnVADStreamingB200, VadEngine, WavFrontendOnlineB200  # noqa: F401
 from .long_audio import LongAudioPipeline, merge_results, pack_segments  # noqa: F401
+from .punc import CTTransformerB200, PuncEngine, split_to_mini_sentence, split_words  # noqa: F401
+from .audio import decode_pcm, load_audio, parse_wav_header  # noqa: F401
 
 __version__ = "0.1.0"

@@ -116,6 +116,8 @@ SIGNATURES = {
     "fa_frame_decibels": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "fa_greedy_filter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fa_split_planes": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "fa_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),
+    "fa_pcm_decode": (C.c_int, [_vp, _i32, _i32, _i64, _vp, _vp]),
     "fa_resample": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i32, _i32, _i32, _vp, _i64, _i32, _vp, _vp]),
     # handle-style offline recogniser (funasrruntime.h:100-116 counterpart; offline.cu)
     "fa_offline_init": (_vp, [C.c_char_p, _i32, _i32]),

@@ -142,6 +142,66 @@ attention_f32_kernel(const float* __restrict__ q, int64_t ldq, const float* __re
   }
 }
 
+// Generic head dimension (multiple of 32, <= 128) for the small SAN-M stacks around the hot path — CT-Transformer punctuation:
+// 8 heads x 32 (ct_transformer/template.yaml:31-45) over a few dozen tokens.  One warp per (utterance, head, query): scores of all
+// keys into shared memory, max, exp / sum, weighted sum of v.  Same mask semantics as the tiled kernel above.
+__global__ void __launch_bounds__(128)
+attention_small_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk, const float* __restrict__ v,
+                       int64_t ldv, const int32_t* __restrict__ key_lens, int heads, int hd, int tq, int tk, float* __restrict__ ctx,
+                       int64_t ldc, float qscale, int kv_shared, int64_t n_rows) {
+  extern __shared__ float s_sc[];                       // [4 warps][tk]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 4 + warp;   // ((b * heads) + h) * tq + n
+  if (row >= n_rows) return;
+  const int n = (int)(row % tq);
+  const int h = (int)((row / tq) % heads);
+  const int b = (int)(row / ((int64_t)tq * heads));
+  const int klen = min(key_lens[b], tk);
+  const int bkv = kv_shared ? 0 : b;
+  const int per = hd >> 5;                              // dims per lane (1..4)
+  float* sc = s_sc + warp * tk;
+  const float* qr = q + ((int64_t)b * tq + n) * ldq + h * hd;
+  float qv[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < per; ++j) qv[j] = __fmul_rn(qr[lane + 32 * j], qscale);
+  float mx = -INFINITY;
+  for (int t = 0; t < klen; ++t) {
+    const float* kr = k + ((int64_t)bkv * tk + t) * ldk + h * hd;
+    float acc = 0.f;
+    for (int j = 0; j < per; ++j) acc = fmaf(qv[j], kr[lane + 32 * j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) sc[t] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int t = lane; t < klen; t += 32) { const float e = expf(sc[t] - mx); sc[t] = e; sum += e; }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t = 0; t < klen; ++t) {
+    const float p = sc[t] / sum;
+    const float* vr = v + ((int64_t)bkv * tk + t) * ldv + h * hd;
+    for (int j = 0; j < per; ++j) o[j] = fmaf(p, vr[lane + 32 * j], o[j]);
+  }
+  float* dst = ctx + ((int64_t)b * tq + n) * ldc + h * hd;
+  for (int j = 0; j < per; ++j) dst[lane + 32 * j] = klen > 0 ? o[j] : 0.f;
+}
+
+int attention_small_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const int32_t* key_lens,
+                           int batch, int heads, int head_dim, int tq, int tk, float* ctx, int64_t ldc, cudaStream_t st, int kv_shared) {
+  if (batch <= 0 || tq <= 0) return FA_OK;
+  if (!q || !k || !v || !key_lens || !ctx || tk <= 0) return FA_ERR_ARG;
+  if (head_dim < 32 || head_dim > 128 || (head_dim & 31)) return FA_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)4 * tk * sizeof(float);
+  if (smem > 160 * 1024) return FA_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) FA_CUDA_OK(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t rows = (int64_t)batch * heads * tq;
+  attention_small_kernel<<<(unsigned)((rows + 3) / 4), 128, smem, st>>>(q, ldq, k, ldk, v, ldv, key_lens, heads, head_dim, tq, tk, ctx, ldc,
+                                                                       (float)(1.0 / sqrt((double)head_dim)), kv_shared ? 1 : 0, rows);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
 int attention_f32_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                          const int32_t* key_lens, int batch, int heads, int tq, int tk, float* ctx, int64_t ldc,
                          cudaStream_t st, int kv_shared) {

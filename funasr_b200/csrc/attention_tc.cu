@@ -30,6 +30,7 @@ constexpr uint32_t AT_P_TILE = AT_BQ * 128;      // 16 KB: 128 queries x 64 keys
 
 struct AttTcParams {
   int tq, tk, heads, batch;
+  float o_scale;                                       // round-toward-zero compensation of the P.V accumulation, per k-step (gemm_tc.cu: acc_scale)
   int kv_shared;                                       // 1: every utterance attends over the SAME keys / values (hotword memory): K/V planes hold one batch entry
   const int32_t* key_lens;
   int64_t q_plane_rows, k_plane_rows, v_plane_rows;   // rows between planes in the respective 2D maps
@@ -331,7 +332,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     }
     // ---- epilogue: O / l for this warp's 32 rows x 64 head dims, staged through shared memory (the K/V ring is dead once
     //      o_full has fired) so that the context rows leave as coalesced 8-byte (fp16 planes) / 16-byte (fp32) stores
-    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    const float inv = l > 0.f ? (1.0f + (float)(nc * (AT_BKEY / 16)) * p.o_scale) / l : 0.f;   // nc key chunks x 4 k-steps were accumulated into O
     float* stage = reinterpret_cast<float*>(sQ) + (warp - 4) * (32 * 36);
     const int64_t grow0 = (int64_t)b * p.tq + q0 + qw * 32;
 #pragma unroll 1
@@ -526,6 +527,10 @@ int attention_tc_planes_launch(const plane_t* qp, const plane_t* kp, const plane
   FA_RETURN_IF_ERR(make_plane_map(&mv_map, vt, (uint64_t)mv * npl, (uint64_t)tk, (uint64_t)tkp, 64));   // 8 KB boxes: 64 d-rows x 64 keys
   AttTcParams p;
   p.tq = tq; p.tk = tk; p.heads = heads; p.batch = batch; p.key_lens = key_lens; p.kv_shared = kv_shared ? 1 : 0;
+  {
+    static const bool rz_on = [] { const char* e = getenv("FA_RZ_COMP"); return !(e && e[0] == '0'); }();
+    p.o_scale = rz_on ? (npl > 1 ? 5.3e-8f : 3.4e-8f) : 0.f;                                   // relative shrink per 16-key k-step
+  }
   p.q_plane_rows = mq; p.k_plane_rows = mk; p.v_plane_rows = mv;
   p.ctx = ctx; p.ldc = ldc; p.ctx_planes = ctx_planes; p.ldp = ldp; p.out_nplanes = out_nplanes;
   dim3 grid((tq + AT_BQ - 1) / AT_BQ, heads, batch);

@@ -103,7 +103,13 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
   const int D = enc->after_norm.n;
   const int din = enc->layers[0].norm1.n;
   const bool embed = enc->pe_inv_timescales != nullptr;   // false: plain stack over an existing [B,T,512] stream
-  if (D != 512 || enc->heads * 128 != D || din > 560 || (!embed && din != D)) return FA_ERR_UNSUPPORTED;
+  const int hd = enc->heads > 0 ? D / enc->heads : 0;
+  // the tcgen05 kernels are built for the Paraformer / SenseVoice shape (d = 512, 4 x 128); the fp32 path also runs the small
+  // SAN-M stacks around the hot path (CT-Transformer punctuation: d = 256, 8 x 32)
+  if (D < 64 || D > 512 || (D & 15) || enc->heads < 1 || enc->heads * hd != D || hd < 32 || hd > 128 || (hd & 31) || din > 560 || (din & 15) ||
+      (!embed && din != D))
+    return FA_ERR_UNSUPPORTED;
+  if (gemm_mode != FA_GEMM_F32_SIMT && (D != 512 || hd != 128)) return FA_ERR_UNSUPPORTED;
   Arena a(workspace, ws_bytes);
   float* u = a.take<float>(M * (size_t)560);
   float* qkv = a.take<float>(M * 1536ull);
@@ -166,8 +172,12 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
       FA_RETURN_IF_ERR(fsmn_launch(qkv + 2 * D, 3 * D, lens, batch, t_max, D, L.fsmn_w, enc->fsmn_k, fsmn_res, D, mem, D, st));
     }
     if (!tc) {
-      FA_RETURN_IF_ERR(attention_f32_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, t_max,
-                                            t_max, ctx, D, st));
+      if (hd == 128) {
+        FA_RETURN_IF_ERR(attention_f32_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, t_max,
+                                              t_max, ctx, D, st));
+      } else {
+        FA_RETURN_IF_ERR(attention_small_launch(qkv, 3 * D, qkv + D, 3 * D, qkv + 2 * D, 3 * D, lens, batch, enc->heads, hd, t_max, t_max, ctx, D, st));
+      }
       FA_RETURN_IF_ERR(linear(ctx, D, M, L.out, 0, mem, D, res, D, x2, D, gemm_mode, &scratch, st));
       FA_RETURN_IF_ERR(layernorm_launch(x2, M, L.norm2, u, nullptr, 1.f, t_max, st));
       FA_RETURN_IF_ERR(linear(u, D, M, L.w1, 1, nullptr, 0, nullptr, 0, h, L.w1.out_f, gemm_mode, &scratch, st));
@@ -652,9 +662,9 @@ __global__ void add_rows_kernel(const float* __restrict__ a, const float* __rest
 
 extern "C" int fa_linear_argmax(const FaLinear* lin, const float* a, const float* b_or_null, int64_t rows, int32_t* ids, float* best_logp,
                                 float* logp, int32_t gemm_mode, void* workspace, size_t ws_bytes, fa_stream_t stream) {
-  if (!lin || !a || !ids || !best_logp || rows <= 0 || lin->in_f != 512) return FA_ERR_ARG;
+  if (!lin || !a || !ids || !best_logp || rows <= 0 || lin->in_f <= 0 || lin->in_f > 512 || (lin->in_f & 3)) return FA_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int V = lin->out_f;
+  const int V = lin->out_f, K = lin->in_f;
   Arena ar(workspace, ws_bytes);
   float* sum = ar.take<float>((size_t)rows * 512);
   float* lg = ar.take<float>((size_t)rows * V);
@@ -664,13 +674,13 @@ extern "C" int fa_linear_argmax(const FaLinear* lin, const float* a, const float
   Arena scratch(sp, sb);
   const float* x = a;
   if (b_or_null) {
-    const int64_t n4 = rows * 128;
+    const int64_t n4 = rows * (K / 4);
     add_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(a, b_or_null, sum, n4);
     FA_CHECK_LAUNCH();
     x = sum;
   }
   if (logp) lg = logp;
-  FA_RETURN_IF_ERR(linear(x, 512, rows, *lin, 0, nullptr, 0, nullptr, 0, lg, V, gemm_mode, &scratch, st));
+  FA_RETURN_IF_ERR(linear(x, K, rows, *lin, 0, nullptr, 0, nullptr, 0, lg, V, gemm_mode, &scratch, st));
   return argmax_lse_launch(lg, rows, V, V, ids, best_logp, logp ? 1 : 0, st);
 }
 
@@ -732,6 +742,20 @@ extern "C" int fa_linear_planes_to_planes(const void* a_planes, int64_t rows, co
   if (!a_planes || !lin || !out_planes || gemm_mode == FA_GEMM_F32_SIMT) return FA_ERR_ARG;
   return gemm_tc_planes_launch(reinterpret_cast<const plane_t*>(a_planes), rows, *lin, relu, nullptr, 0, nullptr, 0, nullptr, 0,
                                reinterpret_cast<plane_t*>(out_planes), ld_out, gemm_mode, (cudaStream_t)stream);
+}
+
+// rows of an embedding table: out[i, :] = table[ids[i], :] (torch.nn.Embedding forward, e.g. CTTransformer.embed ct_transformer/model.py:120)
+__global__ void embedding_kernel(const int32_t* __restrict__ ids, const float* __restrict__ table, int dim, int vocab, int64_t n, float* __restrict__ out) {
+  const int64_t i = blockIdx.x;
+  const int id = min(max(ids[i], 0), vocab - 1);
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) out[i * dim + c] = table[(int64_t)id * dim + c];
+}
+extern "C" int fa_embedding(const int32_t* ids, const float* table, int32_t dim, int32_t vocab, int64_t n, float* out, fa_stream_t stream) {
+  if (!ids || !table || !out || dim <= 0 || vocab <= 0 || n < 0) return FA_ERR_ARG;
+  if (n == 0) return FA_OK;
+  embedding_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(ids, table, dim, vocab, n, out);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
 }
 
 extern "C" const char* fa_version(void) { return "funasr_b200 0.1.0 (sm_100a)"; }

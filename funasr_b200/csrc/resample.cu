@@ -32,7 +32,44 @@ resample_kernel(const float* __restrict__ x, const int32_t* __restrict__ lens, i
   y[(int64_t)b * y_stride + n] = acc;                                         // rows are zero filled beyond out_len
 }
 
+// Interleaved PCM frames -> mono fp32 in [-1, 1): the sample decode of the loader (funasr/utils/load_utils.py:48-179 ->
+// torchaudio.load(normalize=True) semantics: u8 -> (x - 128) / 128, s16 -> x / 2^15, s24 (packed, little endian) -> x / 2^23,
+// s32 -> x / 2^31, f32 unchanged; load_utils.py:168-170 / extract_fbank average the channels).  One thread per frame.
+__global__ void __launch_bounds__(256)
+pcm_decode_kernel(const unsigned char* __restrict__ pcm, int fmt, int channels, int64_t frames, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= frames) return;
+  float acc = 0.f;
+  for (int c = 0; c < channels; ++c) {
+    const int64_t k = i * channels + c;
+    float v;
+    switch (fmt) {
+      case 0: v = reinterpret_cast<const float*>(pcm)[k]; break;
+      case 1: v = (float)reinterpret_cast<const int16_t*>(pcm)[k] * (1.0f / 32768.0f); break;
+      case 2: {
+        const unsigned char* p = pcm + 3 * k;
+        int32_t x = (int32_t)p[0] | ((int32_t)p[1] << 8) | ((int32_t)(signed char)p[2] << 16);
+        v = (float)x * (1.0f / 8388608.0f);
+        break;
+      }
+      case 3: v = (float)reinterpret_cast<const int32_t*>(pcm)[k] * (1.0f / 2147483648.0f); break;
+      default: v = ((float)pcm[k] - 128.0f) * (1.0f / 128.0f); break;
+    }
+    acc += v;
+  }
+  out[i] = channels > 1 ? acc / (float)channels : acc;
+}
+
 }  // namespace fa
+
+extern "C" int fa_pcm_decode(const void* pcm, int32_t sample_format, int32_t channels, int64_t frames, float* out, fa_stream_t stream) {
+  if (!pcm || !out || sample_format < 0 || sample_format > 4 || channels < 1 || channels > 64 || frames < 0) return FA_ERR_ARG;
+  if (frames == 0) return FA_OK;
+  fa::pcm_decode_kernel<<<(unsigned)((frames + 255) / 256), 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(pcm), sample_format, channels,
+                                                                                          frames, out);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
 
 extern "C" int fa_resample(const float* x, const int32_t* lens, int32_t batch, int64_t x_stride, const float* table, int32_t orig,
                            int32_t nnew, int32_t width, float* y, int64_t y_stride, int32_t y_cap, int32_t* out_lens, fa_stream_t stream) {

@@ -125,10 +125,13 @@ class SANMEncoderB200(_ParamHolder):
                  num_blocks: int = 6, kernel_size: int = 11, sanm_shfit: int = 0, input_layer: str = "pe",
                  normalize_before: bool = True, selfattention_layer_type: str = "sanm", **kwargs):
         super().__init__()
-        if (output_size, attention_heads, input_layer, normalize_before, selfattention_layer_type, sanm_shfit) != \
-                (512, 4, "pe", True, "sanm", 0) or input_size > 560:
-            raise _abi.FunasrB200Error("SANMEncoderB200 supports the Paraformer-large / SenseVoiceSmall encoder shape "
-                                       "(d=512, 4 heads, input_layer='pe', sanm, normalize_before)")
+        head_dim = output_size // attention_heads if attention_heads else 0
+        if (input_layer, normalize_before, selfattention_layer_type, sanm_shfit) != ("pe", True, "sanm", 0) or input_size > 560 or \
+                output_size % 16 or output_size > 512 or head_dim * attention_heads != output_size or head_dim not in (32, 64, 96, 128) or \
+                linear_units > 2048 or input_size % 16:
+            raise _abi.FunasrB200Error("SANMEncoderB200 supports input_layer='pe', sanm, normalize_before, d <= 512 (head dim 32..128), "
+                                       "linear_units <= 2048 — d=512 / 4 heads runs on the tensor cores (Paraformer, SenseVoice), other "
+                                       "shapes (CT-Transformer: d=256 / 8 heads) on the fp32 path")
         self.input_size, self._output_size = input_size, output_size
         self.heads, self.ffn, self.num_blocks, self.kernel_size = attention_heads, linear_units, num_blocks, kernel_size
         self._build()

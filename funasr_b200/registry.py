@@ -69,6 +69,7 @@ DROP_IN_KEYS = {
     ("model_classes", "BiCifParaformer"): "BiCifParaformerB200",
     ("model_classes", "SeacoParaformer"): "SeacoParaformerB200",
     ("model_classes", "FsmnVADStreaming"): "FsmnVADStreamingB200",
+    ("model_classes", "CTTransformer"): "CTTransformerB200",
     ("encoder_classes", "FSMN"): "FSMNB200",
     ("frontend_classes", "WavFrontendOnline"): "WavFrontendOnlineB200",
     ("model_classes", "ContextualParaformer"): "ContextualParaformerB200",

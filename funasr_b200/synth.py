@@ -440,3 +440,62 @@ def make_vad_wav(seconds: float, seed: int = 0, pattern=None) -> torch.Tensor:
     env = torch.nn.functional.conv1d(torch.nn.functional.pad(env[None, None], (ramp // 2, ramp - ramp // 2 - 1)), kern)[0, 0]
     noise = torch.randn(n, generator=g) * 0.0015
     return (x * env + noise).clamp_(-1, 1).float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CT-Transformer punctuation (funasr/models/ct_transformer: template.yaml:9-45)
+# ------------------------------------------------------------------------------------------------------------------
+PUNC_LIST = ["<unk>", "_", "，", "。", "？", "、"]
+PUNC_VOCAB, PUNC_DIM, PUNC_HEADS, PUNC_FFN, PUNC_LAYERS = 600, 256, 8, 1024, 4
+
+
+def punc_token_list():
+    """Synthetic vocabulary: CJK characters plus a few lower-case English words (the model sees both kinds)."""
+    words = ["the", "a", "of", "hello", "world", "speech", "model", "is", "fast", "gpu", "we", "test", "it", "now", "today", "and"]
+    return ["<blank>", "<s>", "</s>"] + [chr(0x4E00 + i) for i in range(PUNC_VOCAB - 4 - len(words))] + words + ["<unk>"]
+
+
+def make_punc_state_dict(seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """CTTransformer weights under the reference's names: embed.weight [V, 256], encoder.* (SANMEncoder d=256, 8 heads, FFN 1024, 4 blocks),
+    decoder.{weight [6, 256], bias}; decoder gain / bias chosen so that all punctuation classes occur."""
+    g = torch.Generator().manual_seed(1000003 * seed + 211)
+    D, F, K = PUNC_DIM, PUNC_FFN, 11
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    sd["embed.weight"] = _randn(g, PUNC_VOCAB, D, std=1.0)
+
+    def layer(p):
+        sd[p + ".self_attn.linear_q_k_v.weight"] = _randn(g, 3 * D, D, std=1.2 / math.sqrt(D))
+        sd[p + ".self_attn.linear_q_k_v.bias"] = _randn(g, 3 * D, std=0.02)
+        sd[p + ".self_attn.linear_out.weight"] = _randn(g, D, D, std=0.5 / math.sqrt(D))
+        sd[p + ".self_attn.linear_out.bias"] = _randn(g, D, std=0.02)
+        sd[p + ".self_attn.fsmn_block.weight"] = _randn(g, D, 1, K, std=0.1)
+        sd[p + ".feed_forward.w_1.weight"] = _randn(g, F, D, std=1.0 / math.sqrt(D))
+        sd[p + ".feed_forward.w_1.bias"] = _randn(g, F, std=0.02)
+        sd[p + ".feed_forward.w_2.weight"] = _randn(g, D, F, std=0.5 / math.sqrt(F))
+        sd[p + ".feed_forward.w_2.bias"] = _randn(g, D, std=0.02)
+        for n in ("norm1", "norm2"):
+            sd[p + ".%s.weight" % n] = 1.0 + _randn(g, D, std=0.1)
+            sd[p + ".%s.bias" % n] = _randn(g, D, std=0.05)
+
+    layer("encoder.encoders0.0")
+    for i in range(PUNC_LAYERS - 1):
+        layer("encoder.encoders.%d" % i)
+    sd["encoder.after_norm.weight"] = 1.0 + _randn(g, D, std=0.1)
+    sd["encoder.after_norm.bias"] = _randn(g, D, std=0.05)
+    sd["decoder.weight"] = _randn(g, len(PUNC_LIST), D, std=2.0 / math.sqrt(D))
+    sd["decoder.bias"] = torch.tensor([-6.0, 2.2, 0.6, 0.0, -0.6, -0.3])
+    return sd
+
+
+def make_punc_text(n_words: int, seed: int = 0) -> str:
+    """Unpunctuated mixed Chinese / English text: characters run together, English words separated by spaces."""
+    g = torch.Generator().manual_seed(31337 * seed + 7)
+    toks = punc_token_list()
+    out, prev_latin = [], False
+    for _ in range(n_words):
+        if float(torch.rand(1, generator=g)) < 0.2:
+            w = toks[PUNC_VOCAB - 1 - 16 + int(torch.randint(0, 16, (1,), generator=g))]
+            out.append((" " if out else "") + w + " ")
+        else:
+            out.append(toks[3 + int(torch.randint(0, PUNC_VOCAB - 4 - 16, (1,), generator=g))])
+    return "".join(out).replace("  ", " ").strip()

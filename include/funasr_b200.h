@@ -381,6 +381,14 @@ int fa_ctc_greedy_forward(const FaLinear* ctc_lo, const float* enc, const int32_
 int fa_resample(const float* x, const int32_t* lens, int32_t batch, int64_t x_stride, const float* table, int32_t orig,
                 int32_t nnew, int32_t width, float* y, int64_t y_stride, int32_t y_cap, int32_t* out_lens, fa_stream_t stream);
 
+/* out[i, :] = table[ids[i], :]  (torch.nn.Embedding forward; CTTransformer.embed, ct_transformer/model.py:120).  ids are clamped to the table. */
+int fa_embedding(const int32_t* ids, const float* table, int32_t dim, int32_t vocab, int64_t n, float* out, fa_stream_t stream);
+
+/* Sample decode of the audio loader on the device (funasr/utils/load_utils.py:48-179; torchaudio.load(normalize=True) scaling): interleaved
+ * PCM frames (device memory) -> mono fp32 [frames] in [-1, 1), channels averaged.  sample_format: 0 = f32, 1 = s16le, 2 = s24le packed,
+ * 3 = s32le, 4 = u8.  The container (RIFF WAV header) is parsed on the host (funasr_b200/audio.py). */
+int fa_pcm_decode(const void* pcm, int32_t sample_format, int32_t channels, int64_t frames, float* out, fa_stream_t stream);
+
 /* Split fp32 [rows, cols] into three fp16 planes [3][rows][cols_pad] (hi, mid, lo; zero padded columns):
  * weight repack for the tcgen05 GEMM path (called once per weight after load_pretrained_model). */
 int fa_split_planes(const float* src, int64_t ld_src, int64_t rows, int32_t cols, int32_t cols_pad,

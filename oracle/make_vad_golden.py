@@ -142,10 +142,38 @@ def run_long_case(name, seconds, seed, pattern, gen_kw, tmp):
     print("%s: %d ids, %d stamps, text[:60]=%r" % (name, len(ids), len(ts), text[:60]))
 
 
+# ---- CT-Transformer punctuation: AutoModel(model="CTTransformer").generate(input=text)
+PUNC_CASES = {"punc_short": (12, 1), "punc_long": (140, 2), "punc_english_tail": (33, 3)}
+
+
+def run_punc_cases(tmp):
+    from funasr import AutoModel
+    pt = os.path.join(tmp, "punc.pt")
+    torch.save(synth.make_punc_state_dict(0), pt)
+    toks = synth.punc_token_list()
+    am = AutoModel(model="CTTransformer",
+                   model_conf=dict(ignore_id=0, embed_unit=synth.PUNC_DIM, att_unit=synth.PUNC_DIM, dropout_rate=0.1, punc_list=synth.PUNC_LIST,
+                                   punc_weight=[1.0] * len(synth.PUNC_LIST), sentence_end_id=3),
+                   encoder="SANMEncoder",
+                   encoder_conf=dict(input_size=synth.PUNC_DIM, output_size=synth.PUNC_DIM, attention_heads=synth.PUNC_HEADS, linear_units=synth.PUNC_FFN,
+                                     num_blocks=synth.PUNC_LAYERS, dropout_rate=0.1, positional_dropout_rate=0.1, attention_dropout_rate=0.0,
+                                     input_layer="pe", pos_enc_class="SinusoidalPositionEncoder", normalize_before=True, kernel_size=11, sanm_shfit=0,
+                                     selfattention_layer_type="sanm", padding_idx=0),
+                   tokenizer="CharTokenizer", tokenizer_conf=dict(token_list=toks, unk_symbol="<unk>"),
+                   device="cpu", ncpu=os.cpu_count(), disable_update=True, disable_pbar=True, init_param=pt)
+    for name, (n_words, seed) in PUNC_CASES.items():
+        text = synth.make_punc_text(n_words, seed)
+        res = am.generate(input=text, disable_pbar=True)
+        r = res[0]
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), text_in=np.array(text), text_out=np.array(r["text"]),
+                            punc_array=np.asarray(r["punc_array"]).astype(np.int64))
+        print("%s: %d words -> %r  punc %s" % (name, n_words, r["text"][:70], np.bincount(np.asarray(r["punc_array"]).astype(np.int64), minlength=6).tolist()))
+
+
 def main():
     ref_shim.import_reference()
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["vad", "long"]
+    which = sys.argv[1:] or ["vad", "long", "punc"]
     with tempfile.TemporaryDirectory() as tmp:
         if "vad" in which:
             am = build_vad(tmp)
@@ -154,6 +182,8 @@ def main():
         if "long" in which:
             for name, (seconds, seed, pattern, kw) in LONG_CASES.items():
                 run_long_case(name, seconds, seed, pattern, kw, tmp)
+        if "punc" in which:
+            run_punc_cases(tmp)
 
 
 if __name__ == "__main__":

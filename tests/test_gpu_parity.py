@@ -1033,3 +1033,86 @@ def test_funoffline_cpp_client_end_to_end(tmp_path, contextual):
         m.to(DEV).eval()
         res, _ = m.inference([deq.numpy()], key=["a"], tokenizer=None, frontend=fe, device=DEV)
     assert ids_file == res[0]["token_int"]
+
+
+def test_audio_decode_matches_host_decoding(tmp_path):
+    """funasr_b200.audio: WAV containers (PCM 8 / 16 / 24 / 32 bit, float32, stereo) decoded, mixed down and
+    resampled on the GPU against the same decode done with numpy on the host (torchaudio.load(normalize=True) scaling, channel mean,
+    load_utils.py:168-178) — and against torchaudio.load itself when its backend can read the file."""
+    import struct
+    from funasr_b200 import audio
+    from funasr_b200.resample import sinc_resample_table
+    g = np.random.default_rng(7)
+    n = 8000
+    x = np.clip(g.standard_normal((n, 2)) * 0.3, -0.99, 0.99)
+
+    def wav_bytes(tag, bits, ch, rate, payload):
+        blk = ch * bits // 8
+        return (b"RIFF" + struct.pack("<I", 36 + len(payload)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, tag, ch, rate, rate * blk, blk, bits) +
+                b"data" + struct.pack("<I", len(payload)) + payload)
+
+    cases = []
+    s16 = np.round(x * 32767).astype("<i2")
+    cases.append(("s16 stereo", wav_bytes(1, 16, 2, 16000, s16.tobytes()), s16.astype(np.float32).mean(1) / 32768.0, 16000))
+    s32 = np.round(x[:, :1] * (2 ** 31 - 1)).astype("<i4")
+    cases.append(("s32 mono", wav_bytes(1, 32, 1, 16000, s32.tobytes()), (s32[:, 0].astype(np.float64) / 2 ** 31).astype(np.float32), 16000))
+    s24v = np.round(x[:, 0] * (2 ** 23 - 1)).astype(np.int32)
+    s24 = b"".join(struct.pack("<i", int(v))[:3] for v in s24v)
+    cases.append(("s24 mono", wav_bytes(1, 24, 1, 16000, s24), (s24v.astype(np.float64) / 2 ** 23).astype(np.float32), 16000))
+    u8 = np.round(x[:, 0] * 127 + 128).astype(np.uint8)
+    cases.append(("u8 mono", wav_bytes(1, 8, 1, 16000, u8.tobytes()), (u8.astype(np.float32) - 128.0) / 128.0, 16000))
+    f32 = x.astype("<f4")
+    cases.append(("f32 stereo 8k", wav_bytes(3, 32, 2, 8000, f32.tobytes()), f32.mean(1), 8000))
+    for name, data, want, rate in cases:
+        got = audio.load_audio(data, fs=16000, device=DEV)
+        if rate == 16000:
+            assert got.numel() == want.shape[0], name
+            assert np.abs(got.cpu().numpy() - want).max() <= 1e-6, name
+        else:                                                       # + resample (torchaudio's polyphase kernel, restated bit-exactly)
+            tab, orig, new, width = sinc_resample_table(rate, 16000)
+            xp = torch.nn.functional.pad(torch.from_numpy(want)[None], (width, width + orig))
+            ref = torch.nn.functional.conv1d(xp[:, None], torch.from_numpy(tab)[:, None, :], stride=orig).transpose(1, 2).reshape(-1)
+            tl = -(-new * want.shape[0] // orig)
+            assert got.numel() == tl and torch.allclose(got.cpu(), ref[:tl], atol=2e-6, rtol=1e-5), name
+    # a file path, and torchaudio as an independent decoder when available
+    p = tmp_path / "a.wav"
+    p.write_bytes(cases[0][1])
+    got = audio.load_audio(str(p), device=DEV)
+    try:
+        import torchaudio
+        ta, sr = torchaudio.load(str(p))
+        assert sr == 16000 and torch.allclose(got.cpu(), ta.mean(0), atol=1e-6)
+    except Exception:
+        pass
+    with pytest.raises(Exception):
+        audio.load_audio(b"RIFFxxxxWAVEjunk", device=DEV)
+
+
+# ------------------------------------------------------------------------------------------------ CT-Transformer punctuation
+
+@pytest.mark.parametrize("name", ["punc_short", "punc_long", "punc_english_tail"])
+def test_ct_transformer_vs_reference_golden(name):
+    """CTTransformerB200.inference on the GPU (fa_embedding -> SANM encoder with 32-wide heads -> fa_linear_argmax) against the
+    unmodified reference's AutoModel(model="CTTransformer").generate() for the same seeded weights and text: the punctuated text and
+    the punctuation id per token are equal (integer outputs, bit-exact bar)."""
+    import funasr_b200
+    from funasr_b200 import synth
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    toks = synth.punc_token_list()
+    t2i = {t: i for i, t in enumerate(toks)}
+
+    class Tok:
+        def encode(self, words):
+            return [t2i.get(w, t2i["<unk>"]) for w in words]
+
+    m = funasr_b200.CTTransformerB200(
+        encoder="SANMEncoder",
+        encoder_conf=dict(input_size=synth.PUNC_DIM, output_size=synth.PUNC_DIM, attention_heads=synth.PUNC_HEADS, linear_units=synth.PUNC_FFN,
+                          num_blocks=synth.PUNC_LAYERS, kernel_size=11, sanm_shfit=0, input_layer="pe", normalize_before=True),
+        vocab_size=len(toks), punc_list=synth.PUNC_LIST, punc_weight=[1.0] * len(synth.PUNC_LIST), embed_unit=synth.PUNC_DIM, att_unit=synth.PUNC_DIM,
+        sentence_end_id=3)
+    m.load_state_dict(synth.make_punc_state_dict(0), strict=True)
+    m.to(DEV).eval()
+    res, _ = m.inference([str(g["text_in"])], key=["k"], tokenizer=Tok(), device=DEV)
+    assert res[0]["text"] == str(g["text_out"])
+    assert res[0]["punc_array"].tolist() == g["punc_array"].tolist()
