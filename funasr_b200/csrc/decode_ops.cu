@@ -7,22 +7,43 @@
 
 namespace fa {
 
-// One CTA (256 threads) per row of logits [rows, vocab].  Ties resolve to the lowest index (torch.argmax).
-__global__ void __launch_bounds__(256)
+// One CTA per row of logits [rows, vocab].  Ties resolve to the lowest index (torch.argmax).
+// The row is read ONCE into registers (NV float4 per thread) and the three sweeps — maximum, sum of exponentials, lowest index whose
+// rounded log-prob equals the maximum's — run on the registers: the first version swept global memory three times with 4-byte
+// loads and took 300 us for 10^4 rows x 8404 (336 MB per sweep); one 16-byte sweep is ~60 us of HBM time.
+template <int THREADS, int NV>
+__global__ void __launch_bounds__(THREADS)
 argmax_lse_kernel(float* __restrict__ logits, int vocab, int64_t ld, int32_t* __restrict__ ids,
                   float* __restrict__ best_logp, int write_log_softmax) {
-  __shared__ float s_val[8];
-  __shared__ int s_idx[8];
-  __shared__ float s_sum[8];
+  constexpr int NW = THREADS / 32;
+  __shared__ float s_val[NW];
+  __shared__ int s_idx[NW];
+  __shared__ float s_sum[NW];
   const int64_t row = blockIdx.x;
   float* x = logits + row * ld;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  float v[NV][4];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i0 = 4 * (threadIdx.x + THREADS * k);
+    if (vec && i0 + 3 < vocab) {
+      const float4 t = *reinterpret_cast<const float4*>(x + i0);
+      v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[k][e] = i0 + e < vocab ? x[i0 + e] : -INFINITY;
+    }
+  }
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
-    const float v = x[i];
-    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
-  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = 4 * (threadIdx.x + THREADS * k) + e;          // increasing within a thread: strict > keeps the lowest index
+      if (v[k][e] > best) { best = v[k][e]; bi = i; }
+    }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -33,26 +54,41 @@ argmax_lse_kernel(float* __restrict__ logits, int vocab, int64_t ld, int32_t* __
   __syncthreads();
   best = s_val[0]; bi = s_idx[0];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) {
+  for (int w = 1; w < NW; ++w) {
     if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
   }
   float sum = 0.f;
-  for (int i = threadIdx.x; i < vocab; i += blockDim.x) sum += expf(x[i] - best);
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sum += expf(v[k][e] - best);       // padding holds -inf: exp = 0
   sum = warp_sum(sum);
   if (lane == 0) s_sum[warp] = sum;
   __syncthreads();
   sum = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) sum += s_sum[w];
+  for (int w = 0; w < NW; ++w) sum += s_sum[w];
   // torch log_softmax: (x - max) - log(sum exp(x - max)); arg-max is taken over those rounded values (model.py:642),
   // so an element whose log-prob rounds to the same float as the maximum's wins if its index is lower.
   const float lsum = logf(sum);
   const float best_lp = __fsub_rn(0.f, lsum);
   int tie = bi;
-  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
-    const float lp = __fsub_rn(__fsub_rn(x[i], best), lsum);
-    if (lp == best_lp && i < tie) tie = i;
-    if (write_log_softmax) x[i] = lp;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i0 = 4 * (threadIdx.x + THREADS * k);
+    float lp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      lp[e] = __fsub_rn(__fsub_rn(v[k][e], best), lsum);
+      if (lp[e] == best_lp && i0 + e < tie) tie = i0 + e;
+    }
+    if (write_log_softmax) {
+      if (vec && i0 + 3 < vocab) *reinterpret_cast<float4*>(x + i0) = make_float4(lp[0], lp[1], lp[2], lp[3]);
+      else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (i0 + e < vocab) x[i0 + e] = lp[e];
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tie = min(tie, __shfl_xor_sync(0xffffffffu, tie, o));
@@ -62,7 +98,7 @@ argmax_lse_kernel(float* __restrict__ logits, int vocab, int64_t ld, int32_t* __
   if (threadIdx.x == 0) {
     int t = s_idx[0];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) t = min(t, s_idx[w]);
+    for (int w = 1; w < NW; ++w) t = min(t, s_idx[w]);
     ids[row] = t;
     best_logp[row] = best_lp;
   }
@@ -144,7 +180,11 @@ split_planes_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int
 int argmax_lse_launch(float* logits, int64_t rows, int vocab, int64_t ld, int32_t* ids, float* best_logp,
                       int write_log_softmax, cudaStream_t st) {
   if (rows <= 0) return FA_OK;
-  argmax_lse_kernel<<<(unsigned)rows, 256, 0, st>>>(logits, vocab, ld, ids, best_logp, write_log_softmax);
+  // registers per thread hold the row: 256 x 36 = 9216 (Paraformer 8404), 1024 x 28 = 28672 (SenseVoice 25055), 512 x 120 = 61440
+  if (vocab <= 256 * 36) argmax_lse_kernel<256, 9><<<(unsigned)rows, 256, 0, st>>>(logits, vocab, ld, ids, best_logp, write_log_softmax);
+  else if (vocab <= 1024 * 28) argmax_lse_kernel<1024, 7><<<(unsigned)rows, 1024, 0, st>>>(logits, vocab, ld, ids, best_logp, write_log_softmax);
+  else if (vocab <= 512 * 120) argmax_lse_kernel<512, 30><<<(unsigned)rows, 512, 0, st>>>(logits, vocab, ld, ids, best_logp, write_log_softmax);
+  else return FA_ERR_UNSUPPORTED;
   FA_CHECK_LAUNCH();
   return FA_OK;
 }

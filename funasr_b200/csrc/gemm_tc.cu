@@ -45,6 +45,10 @@ struct TcParams {
   plane_t* out_planes;             // fp16 plane output [3][M][ldo] (or null)
   int64_t ldo; int out_nplanes;
   int tiles_m, tiles_n;
+  // cta_group::2 kernel only — schedule of the 256 x 256 pair tiles over the P CTA pairs: full_rounds rounds of P whole tiles, then
+  // the tail_tiles leftover tiles cut into tail_sub (1 | 2 | 4) column slices of 256 / tail_sub so that the last, partial wave
+  // costs ceil(tail_tiles * tail_sub / P) / tail_sub of a round instead of a whole one (gemm_tc2_kernel, pick_tail_sub)
+  int full_rounds, tail_tiles, tail_sub;
   AttnSinks att;                          // optional: route column ranges to attention operand planes
   // tcgen05 accumulates in fp32 with round-toward-zero: every 16-wide k-step shrinks the running sum by a fraction of an ulp, a
   // SYSTEMATIC relative error that grows linearly in K (tools/noise_probe.py, Gaussian data: -1.70e-6 at K = 512 and -6.35e-6 at
@@ -134,8 +138,7 @@ constexpr int EPI_F32 = 0, EPI_PLANES = 1, EPI_ATT = 2;
 // fp32-output interior tiles: the residual rows do not depend on the accumulator, so their loads are software pipelined one
 // chunk ahead and the first chunk's are issued BEFORE waiting for the accumulator (out-projection / FFN-w_2 epilogues were
 // bound by memory-level parallelism: 8 warps x 8 float4 loads in flight per SM sustain ~4 TB/s, measured 262 MB in 66 us).
-template <int BN>
-__device__ __forceinline__ void epilogue_fast_f32(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
+__device__ __forceinline__ void epilogue_fast_f32(const TcParams& p, const int BN, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
                                                   int half, uint64_t* full_bar, uint32_t full_phase) {
   const int rr0 = lane >> 2, c4 = (lane & 3) * 4;
   const int64_t rfirst = row0 + rr0;
@@ -189,10 +192,69 @@ __device__ __forceinline__ void epilogue_fast_f32(const TcParams& p, uint32_t tm
   }
 }
 
+// The same for at most ONE residual (every fp32-output GEMM of the model: out-projection + x, FFN w_2 + x): the registers the second
+// residual's pipeline would hold become a 3-deep ring of the first's, so each warp keeps three 16-column chunks (6 KB) of residual
+// rows in flight instead of one.  Measured before the change: out-projection (K = 512) 69 us for 250 tiles on 74 pairs = 17 us per
+// tile against 6-9 us of MMAs — the epilogue moved 256 KB per tile and CTA at 15 GB/s, exactly 16 KB in flight per SM over ~1.5 us
+// of loaded L2 / HBM latency (Little's law), i.e. bound by memory-level parallelism, not by bandwidth.
+__device__ __forceinline__ void epilogue_fast_f32_r1(const TcParams& p, const int BN, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage,
+                                                     int lane, int half, uint64_t* full_bar, uint32_t full_phase) {
+  const int rr0 = lane >> 2, c4 = (lane & 3) * 4;
+  const int64_t rfirst = row0 + rr0;
+  float* srow = stage + lane * EPI_LD;
+  const float* sp = stage + rr0 * EPI_LD + c4;
+  float* c_row = p.C + rfirst * p.ldc + c4 + tile_col0;
+  const float* r_row = p.r1 ? p.r1 + rfirst * p.ldr1 + c4 + tile_col0 : nullptr;
+  const int64_t sc = 8 * p.ldc, s1 = 8 * p.ldr1;
+  const bool c_vec = (p.ldc & 3) == 0;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int cb = half * EPI_CH;                       // this warp's chunk i covers columns [cb + 32 i, +16)
+  constexpr int RING = 3;
+  float4 ring[RING][4];
+  auto fetch = [&](float4 (&dst)[4], int c0) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) dst[it] = r_row ? __ldg(reinterpret_cast<const float4*>(r_row + c0 + it * s1)) : z4;
+  };
+#pragma unroll
+  for (int i = 0; i < RING; ++i)
+    if (cb + 32 * i < BN) fetch(ring[i], cb + 32 * i);              // issued BEFORE waiting for the accumulator
+  mbar_wait(full_bar, full_phase);
+  tc_fence_after();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {                                      // BN <= 256: at most 8 chunks per warp
+    const int c0 = cb + 32 * i;
+    if (c0 < BN) {
+      {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_acc + c0, r);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+      __syncwarp();
+      float4 bias4 = z4;
+      if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + tile_col0 + c0 + c4));
+      float* pc = c_row + c0;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const float4 acc = *reinterpret_cast<const float4*>(sp + it * 8 * EPI_LD);
+        const float4 rv = ring[i % RING][it];
+        float v0 = fmaf(acc.x, p.acc_scale, bias4.x), v1 = fmaf(acc.y, p.acc_scale, bias4.y), v2 = fmaf(acc.z, p.acc_scale, bias4.z), v3 = fmaf(acc.w, p.acc_scale, bias4.w);
+        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+        v0 += rv.x; v1 += rv.y; v2 += rv.z; v3 += rv.w;
+        if (c_vec) *reinterpret_cast<float4*>(pc) = make_float4(v0, v1, v2, v3);
+        else { pc[0] = v0; pc[1] = v1; pc[2] = v2; pc[3] = v3; }
+        pc += sc;
+      }
+      __syncwarp();
+      if (c0 + 32 * RING < BN) fetch(ring[i % RING], c0 + 32 * RING);
+    }
+  }
+}
+
 // Interior tiles (all 32 rows and all BN columns in range): straight-line code, no bounds predicates, every row base
 // computed once per tile and advanced by constant strides.
-template <int BN, int EPI, int NPL>
-__device__ __forceinline__ void epilogue_fast(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
+template <int EPI, int NPL>
+__device__ __forceinline__ void epilogue_fast(const TcParams& p, const int BN, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
                                               int half) {
   const AttnSinks& a = p.att;
   constexpr int QPL = NPL < 2 ? NPL : 2;             // attention operands carry at most two planes
@@ -297,8 +359,8 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, uint32_t tmem_a
 }
 
 // Edge tiles (row tail of M, ragged N such as vocab 8404 / 25055): every access bounds checked.
-template <int BN, int EPI, int NPL>
-__device__ __noinline__ void epilogue_edge(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
+template <int EPI, int NPL>
+__device__ __noinline__ void epilogue_edge(const TcParams& p, const int BN, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
                                            int half) {
   const AttnSinks& a = p.att;
   constexpr int QPL = NPL < 2 ? NPL : 2;
@@ -374,18 +436,20 @@ __device__ __noinline__ void epilogue_edge(const TcParams& p, uint32_t tmem_acc,
   }
 }
 
-template <int BN, int EPI, int NPL>
-__device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
+// BN: columns of this accumulator tile (a compile-time constant in the single-CTA kernel; 256 / 128 / 64 in the pair kernel)
+template <int EPI, int NPL>
+__device__ __forceinline__ void epilogue_warp(const TcParams& p, const int BN, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
                                               int half, uint64_t* full_bar, uint32_t full_phase) {
   const bool interior = row0 + 32 <= p.M && tile_col0 + BN <= p.N;
-  if (EPI == EPI_F32 && interior) {
-    epilogue_fast_f32<BN>(p, tmem_acc, row0, tile_col0, stage, lane, half, full_bar, full_phase);   // waits for the accumulator itself
+  if (EPI == EPI_F32 && interior) {                                                                  // both wait for the accumulator themselves
+    if (p.r2) epilogue_fast_f32(p, BN, tmem_acc, row0, tile_col0, stage, lane, half, full_bar, full_phase);
+    else epilogue_fast_f32_r1(p, BN, tmem_acc, row0, tile_col0, stage, lane, half, full_bar, full_phase);
     return;
   }
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
-  if (interior) epilogue_fast<BN, EPI, NPL>(p, tmem_acc, row0, tile_col0, stage, lane, half);
-  else epilogue_edge<BN, EPI, NPL>(p, tmem_acc, row0, tile_col0, stage, lane, half);
+  if (interior) epilogue_fast<EPI, NPL>(p, BN, tmem_acc, row0, tile_col0, stage, lane, half);
+  else epilogue_edge<EPI, NPL>(p, BN, tmem_acc, row0, tile_col0, stage, lane, half);
 }
 
 template <int BN, int STAGES, int APL, int WPL, int EPI>  // APL / WPL: A / W planes resident per stage
@@ -483,7 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-      epilogue_warp<BN, EPI, APL>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32, tn * BN,
+      epilogue_warp<EPI, APL>(p, BN, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * TC_BM + q * 32, tn * BN,
                                   epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half, &tmem_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
@@ -506,9 +570,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // (half of the N tile) per k-block, so operand bytes per MMA cycle are half those of the single-CTA 128x256 tile
 // (64 KB per k-block per SM for the three x3 terms) and three stages fit.  The leader issues
 // tcgen05.mma.cta_group::2 (M=256); each CTA drains its own 128 TMEM lanes in the epilogue.
+//
+// Schedule: pair q of P runs the whole tiles q, q + P, ... of the first full_rounds * P tiles, then the column slices q, q + P, ...
+// of the leftover tiles (item_of).  A 256 x 256 tile takes ~9 us (K = 512, x3) to ~35 us (K = 2048); with 250 tiles on 74 pairs
+// the last round kept 28 pairs busy for a whole tile time while 46 idled (16 % of the FFN-w_2 / out-projection launch).  Slices
+// of 128 / 64 columns (tcgen05.mma N = 128 / 64, the W box of each CTA 64 / 32 rows through a second tensor map) spread those 28
+// tiles over 56 / 112 items.  Narrow slices re-read the A rows from L2 more often, so only the tail uses them.
+struct TcItem { int tm, col0, bn; };
+__device__ __forceinline__ bool item_of(const TcParams& p, int pair, int n_pairs, int it, TcItem& o) {
+  int tile, part = 0;
+  o.bn = 256;
+  if (it < p.full_rounds) {
+    tile = pair + it * n_pairs;
+  } else {
+    const int j = pair + (it - p.full_rounds) * n_pairs;
+    if (j >= p.tail_tiles * p.tail_sub) return false;
+    tile = p.full_rounds * n_pairs + j / p.tail_sub;
+    part = j - (j / p.tail_sub) * p.tail_sub;
+    o.bn = 256 / p.tail_sub;
+  }
+  o.tm = tile / p.tiles_n;
+  o.col0 = (tile - o.tm * p.tiles_n) * 256 + part * o.bn;
+  return true;
+}
+
 template <int STAGES, int PL, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ TcParams p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w_tail,
+                const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int BN = 256;
   constexpr uint32_t TILE_BYTES = 128 * TC_BK * 2;                 // 16 KB: 128 rows x 64 fp16
@@ -525,11 +614,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int n_tiles = p.tiles_m * p.tiles_n;          // 256 x 256 pair tiles
   const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int k_blocks = p.Kp / TC_BK;
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_w_tail); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * EPI_WARPS); }
@@ -548,20 +636,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ===================== TMA producer (both CTAs) =====================
     if (elect_one_sync()) {          // single elected lane: no waterfall loops around the uniform-datapath TMA / MMA instructions
       int stage = 0; uint32_t phase = 0;
-      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      TcItem it;
+      for (int i = 0; item_of(p, pair, n_pairs, i, it); ++i) {
+        const CUtensorMap* mw = it.bn == BN ? &map_w : &map_w_tail;            // W box: bn / 2 rows per CTA
+        const uint32_t w_bytes = (uint32_t)(it.bn / 2) * (TC_BK * 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);       // bytes of BOTH CTAs land on the leader's barrier
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * PL * (TILE_BYTES + w_bytes));   // bytes of BOTH CTAs land on the leader's barrier
           unsigned char* st = smem + stage * STAGE_BYTES;
 #pragma unroll
           for (int pl = 0; pl < PL; ++pl)
             tma_load_2d_2sm(st + pl * TILE_BYTES, &map_a, &full_bar[stage], kb * TC_BK,
-                            (int)(pl * p.a_plane_rows + (int64_t)tm * 256 + rank * 128));
+                            (int)(pl * p.a_plane_rows + (int64_t)it.tm * 256 + rank * 128));
 #pragma unroll
           for (int pl = 0; pl < PL; ++pl)
-            tma_load_2d_2sm(st + (PL + pl) * TILE_BYTES, &map_w, &full_bar[stage], kb * TC_BK,
-                            pl * p.w_plane_rows + tn * BN + (int)rank * 128);
+            tma_load_2d_2sm(st + (PL + pl) * TILE_BYTES, mw, &full_bar[stage], kb * TC_BK,
+                            pl * p.w_plane_rows + it.col0 + (int)rank * (it.bn / 2));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -569,10 +659,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc_f16(256, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+      TcItem it;
+      for (int i = 0; item_of(p, pair, n_pairs, i, it); ++i) {
+        const uint32_t idesc = make_idesc_f16(256, it.bn);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);       // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -597,10 +688,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ===================== epilogue (each CTA: its 128 rows) =====================
     const int q = warp & 3, half = (warp - 4) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-      epilogue_warp<BN, EPI, PL>(p, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)tm * 256 + rank * 128 + q * 32, tn * BN,
-                                 epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half, &tmem_full[acc], acc_phase);
+    TcItem it;
+    for (int i = 0; item_of(p, pair, n_pairs, i, it); ++i) {
+      epilogue_warp<EPI, PL>(p, it.bn, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, (int64_t)it.tm * 256 + rank * 128 + q * 32, it.col0,
+                             epi_stage + (warp - 4) * EPI_WARP_FLOATS, lane, half, &tmem_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -730,25 +821,35 @@ static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcPara
 }
 
 template <int STAGES, int PL, int EPI>
-static int launch_cfg2_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+static int launch_cfg2_e(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mwt, const TcParams& p, int pairs, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (2 * PL * 128 * TC_BK * 2) + 1024 + 256 + EPI_WARPS * EPI_WARP_FLOATS * 4;
   static PerDeviceOnce once;
   FA_RETURN_IF_ERR(ensure_dyn_smem(gemm_tc2_kernel<STAGES, PL, EPI>, smem, once));
-  const int n_sm = sm_count();
-  const int tiles = p.tiles_m * p.tiles_n;
-  const int pairs = tiles < n_sm / 2 ? tiles : n_sm / 2;
-  FA_CUDA_OK(launch_pdl(gemm_tc2_kernel<STAGES, PL, EPI>, dim3(2 * pairs), dim3(384), smem, st, 1, ma, mw, p));   // cluster dims are compile-time (__cluster_dims__)
+  FA_CUDA_OK(launch_pdl(gemm_tc2_kernel<STAGES, PL, EPI>, dim3(2 * pairs), dim3(384), smem, st, 1, ma, mw, mwt, p));   // cluster dims are compile-time (__cluster_dims__)
   FA_CHECK_LAUNCH();
   return FA_OK;
 }
 
 template <int STAGES, int PL>
-static int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+static int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mwt, const TcParams& p, int pairs, cudaStream_t st) {
   switch (epi_kind(p)) {
-    case EPI_ATT: return launch_cfg2_e<STAGES, PL, EPI_ATT>(ma, mw, p, st);
-    case EPI_PLANES: return launch_cfg2_e<STAGES, PL, EPI_PLANES>(ma, mw, p, st);
-    default: return launch_cfg2_e<STAGES, PL, EPI_F32>(ma, mw, p, st);
+    case EPI_ATT: return launch_cfg2_e<STAGES, PL, EPI_ATT>(ma, mw, mwt, p, pairs, st);
+    case EPI_PLANES: return launch_cfg2_e<STAGES, PL, EPI_PLANES>(ma, mw, mwt, p, pairs, st);
+    default: return launch_cfg2_e<STAGES, PL, EPI_F32>(ma, mw, mwt, p, pairs, st);
   }
+}
+
+// Column slices per leftover tile (1 | 2 | 4): the one that minimises the tail's duration ceil(tail * sub / P) / sub, the coarser
+// one on ties (wider tiles move fewer operand bytes per flop).  FA_GEMM_TAIL=0 keeps whole tiles (A/B runs).
+static int pick_tail_sub(int tail_tiles, int pairs) {
+  static const bool on = [] { const char* e = getenv("FA_GEMM_TAIL"); return !(e && e[0] == '0'); }();
+  if (!on || tail_tiles == 0) return 1;
+  int best = 1, best_q = 4 * ((tail_tiles + pairs - 1) / pairs);           // duration in quarter rounds
+  for (int sub = 2; sub <= 4; sub *= 2) {
+    const int q = ((tail_tiles * sub + pairs - 1) / pairs) * (4 / sub);
+    if (q < best_q) { best_q = q; best = sub; }
+  }
+  return best;
 }
 
 static bool use_2cta() {
@@ -784,7 +885,14 @@ int gemm_tc_planes_launch(const plane_t* a_planes, int64_t M, const FaLinear& li
     p2.acc_scale = rz_comp_scale(Kp, p2.n_terms);
     if (att) { p2.att = *att; p2.att.enabled = 1; } else { p2.att = AttnSinks{}; }
     if (att && (att->width % 32 != 0 || att->t_rows <= 0 || M % att->t_rows != 0)) return FA_ERR_UNSUPPORTED;
-    return npl == 1 ? launch_cfg2<6, 1>(ma2, mw2, p2, st) : launch_cfg2<3, 2>(ma2, mw2, p2, st);
+    const int tiles = p2.tiles_m * p2.tiles_n, half_sms = sm_count() / 2;
+    p2.full_rounds = tiles / half_sms;
+    p2.tail_tiles = tiles - p2.full_rounds * half_sms;
+    p2.tail_sub = pick_tail_sub(p2.tail_tiles, half_sms);
+    const int pairs = p2.full_rounds > 0 ? half_sms : (p2.tail_tiles * p2.tail_sub < half_sms ? p2.tail_tiles * p2.tail_sub : half_sms);
+    CUtensorMap mwt = mw2;
+    if (p2.tail_sub > 1) FA_RETURN_IF_ERR(make_plane_map(&mwt, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, 128 / p2.tail_sub));
+    return npl == 1 ? launch_cfg2<6, 1>(ma2, mw2, mwt, p2, pairs, st) : launch_cfg2<3, 2>(ma2, mw2, mwt, p2, pairs, st);
   }
   const bool wide = (npl <= 2) && (N % 256 == 0) && (N >= 1024);
   const int BN = wide ? 256 : 128;
@@ -797,6 +905,7 @@ int gemm_tc_planes_launch(const plane_t* a_planes, int64_t M, const FaLinear& li
   p.relu = relu; p.bias = lin.b; p.r1 = r1; p.ldr1 = ld1; p.r2 = r2; p.ldr2 = ld2; p.C = y; p.ldc = ldy;
   p.out_planes = out_planes; p.ldo = ldo; p.out_nplanes = npl;
   p.tiles_m = (int)((M + TC_BM - 1) / TC_BM); p.tiles_n = (N + BN - 1) / BN;
+  p.full_rounds = 0; p.tail_tiles = 0; p.tail_sub = 1;
   p.acc_scale = rz_comp_scale(Kp, p.n_terms);
   if (att) { p.att = *att; p.att.enabled = 1; } else { p.att = AttnSinks{}; }
   if (att && (N % 32 != 0 || att->width % 32 != 0 || att->t_rows <= 0 || M % att->t_rows != 0)) return FA_ERR_UNSUPPORTED;

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import CTX_CASES, GOLDEN_CASES, SV_CASES, load_case, load_ctx_case, load_sv_case, rel_err, state_dict_for
+from conftest import CTX_CASES, GOLDEN, GOLDEN_CASES, SV_CASES, load_case, load_ctx_case, load_sv_case, rel_err, state_dict_for
 
 import paraformer_oracle as O
 

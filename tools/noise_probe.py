@@ -57,4 +57,4 @@ for mode in ("fp16x3", "fp16x6"):
     out["model"][mode] = {"enc_rel_err_vs_fp32": float(e), "logp_rel_err_vs_fp32": float(lp), "ids_equal": res[mode][2] == res["fp32"][2]}
     print(mode, out["model"][mode], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "noise_probe.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", os.environ.get("NOISE_PROBE_OUT", "noise_probe.json")), "w"), indent=1)
