@@ -91,6 +91,23 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// The same in two halves, so the load of chunk c+1 is in flight while chunk c is converted and stored: tmem_ld_issue() then, later,
+// tmem_ld_wait(r) — the registers are in/out operands of the wait so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
 // x = hi + mid + lo split of 4 values into fp16 planes: packed converts (cvt.rn.satfinite.f16x2.f32), packed unpack.  NPL is a compile-
 // time constant: with a runtime plane count the loop compiled to a branchy 4x-unrolled body (ncu: 47 % of all executed
 // instructions of the FFN-w_1 GEMM sat in this function).
@@ -129,11 +146,50 @@ __device__ __forceinline__ void store_vt16(plane_t* dst, int64_t t_pad, int64_t 
   }
 }
 
+// The same through shared memory, for key counts that are a multiple of 4 (rows of one utterance then start at a multiple of 4,
+// so groups of four consecutive keys stay inside one utterance and are 8-byte aligned in the transposed planes): the warp's
+// 32 x 16 chunk is staged at pitch 17 (conflict free for the row-per-lane writes AND for the column reads below), then lane
+// (g = lane & 7, c = lane >> 3) packs keys 4g..4g+3 of columns c, c+4, c+8, c+12 and stores 8 bytes per plane — 8 store
+// instructions per lane and chunk instead of 32 two-byte ones (ncu of the QKV GEMM, round 2: the V third of the tiles spent
+// ~180 instructions per chunk in store_vt16 and its tensor pipe sat at 74 % against 89 % for the plane-emitting FFN w_1).
+constexpr int VT_LD = 17;
+template <int NPL>
+__device__ __forceinline__ void store_vt_staged(plane_t* __restrict__ dst_g /* this lane's key group, column 0 of the chunk */, int64_t t_pad,
+                                                int64_t plane, const float (&x)[16], float* stage, int lane) {
+  float* srow = stage + lane * VT_LD;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) srow[j] = x[j];
+  __syncwarp();
+  const int g = lane & 7, c = lane >> 3;
+  const float* sp = stage + (4 * g) * VT_LD + c;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float k0 = sp[4 * i], k1 = sp[4 * i + VT_LD], k2 = sp[4 * i + 2 * VT_LD], k3 = sp[4 * i + 3 * VT_LD];
+    plane_t* d = dst_g + (int64_t)(c + 4 * i) * t_pad;
+#pragma unroll
+    for (int pl = 0; pl < NPL; ++pl) {
+      uint2 pk;
+      pk.x = pack_planes2(k0, k1);
+      pk.y = pack_planes2(k2, k3);
+      *reinterpret_cast<uint2*>(d) = pk;
+      if (pl + 1 < NPL) {
+        d += plane;
+        const float2 a = unpack_planes2(pk.x), b = unpack_planes2(pk.y);
+        k0 -= a.x; k1 -= a.y; k2 -= b.x; k3 -= b.y;
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // EPI selects the output kind at compile time so the inner loops carry no runtime branching on it:
 //   EPI_F32    fp32 rows (+ bias, ReLU, up to two residuals; ragged N tail supported)
 //   EPI_PLANES fp16 planes for a following GEMM (+ bias, ReLU)
 //   EPI_ATT    attention operands: scaled q planes / k planes / per-head transposed v planes (+ fp32 v for FSMN)
-constexpr int EPI_F32 = 0, EPI_PLANES = 1, EPI_ATT = 2;
+//   EPI_F32R2  EPI_F32 with TWO residuals (only reachable through the C ABI; its interior path keeps the one-chunk-ahead pipeline of
+//              both residual streams in a kernel instantiation of its own, so the common one-residual kernel can spend those
+//              registers on a deeper ring)
+constexpr int EPI_F32 = 0, EPI_PLANES = 1, EPI_ATT = 2, EPI_F32R2 = 3;
 
 // fp32-output interior tiles: the residual rows do not depend on the accumulator, so their loads are software pipelined one
 // chunk ahead and the first chunk's are issued BEFORE waiting for the accumulator (out-projection / FFN-w_2 epilogues were
@@ -193,7 +249,7 @@ __device__ __forceinline__ void epilogue_fast_f32(const TcParams& p, const int B
 }
 
 // The same for at most ONE residual (every fp32-output GEMM of the model: out-projection + x, FFN w_2 + x): the registers the second
-// residual's pipeline would hold become a 3-deep ring of the first's, so each warp keeps three 16-column chunks (6 KB) of residual
+// residual's pipeline would hold become a 5-deep ring of the first's, so each warp keeps five 16-column chunks (10 KB) of residual
 // rows in flight instead of one.  Measured before the change: out-projection (K = 512) 69 us for 250 tiles on 74 pairs = 17 us per
 // tile against 6-9 us of MMAs — the epilogue moved 256 KB per tile and CTA at 15 GB/s, exactly 16 KB in flight per SM over ~1.5 us
 // of loaded L2 / HBM latency (Little's law), i.e. bound by memory-level parallelism, not by bandwidth.
@@ -209,7 +265,7 @@ __device__ __forceinline__ void epilogue_fast_f32_r1(const TcParams& p, const in
   const bool c_vec = (p.ldc & 3) == 0;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int cb = half * EPI_CH;                       // this warp's chunk i covers columns [cb + 32 i, +16)
-  constexpr int RING = 3;
+  constexpr int RING = 5;
   float4 ring[RING][4];
   auto fetch = [&](float4 (&dst)[4], int c0) {
 #pragma unroll
@@ -220,13 +276,18 @@ __device__ __forceinline__ void epilogue_fast_f32_r1(const TcParams& p, const in
     if (cb + 32 * i < BN) fetch(ring[i], cb + 32 * i);              // issued BEFORE waiting for the accumulator
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
+  uint32_t rn[16];                                                    // next chunk's accumulators, in flight
+  tmem_ld_issue(tmem_acc + cb, rn);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {                                      // BN <= 256: at most 8 chunks per warp
     const int c0 = cb + 32 * i;
     if (c0 < BN) {
       {
         uint32_t r[16];
-        tmem_ld_32x16(tmem_acc + c0, r);
+        tmem_ld_wait(rn);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = rn[j];
+        if (c0 + 32 < BN) tmem_ld_issue(tmem_acc + c0 + 32, rn);
 #pragma unroll
         for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       }
@@ -272,25 +333,46 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const int BN, u
   const int64_t plane_o = p.M * p.ldo, plane_q = p.M * (int64_t)a.width;
   const bool c_vec = (p.ldc & 3) == 0;
   plane_t* vt_row = nullptr;
+  plane_t* vt_grp = nullptr;                          // staged path: this lane's group of four keys (rows row0 + 4 (lane & 7) ..)
   int64_t vt_plane = 0;
+  const bool vt_staged = EPI == EPI_ATT && (a.t_rows & 3) == 0 && (a.t_pad & 3) == 0 && (reinterpret_cast<uintptr_t>(a.vt_planes) & 7) == 0;
   if (EPI == EPI_ATT) {
     const int64_t rw = row0 + lane;
     const int b2 = (int)(rw / a.t_rows), t2 = (int)(rw - (int64_t)b2 * a.t_rows);
     vt_row = a.vt_planes + (int64_t)b2 * a.width * a.t_pad + t2;
     vt_plane = (p.M / a.t_rows) * (int64_t)a.width * a.t_pad;
+    const int64_t rg = row0 + 4 * (lane & 7);
+    const int bg = (int)(rg / a.t_rows), tg = (int)(rg - (int64_t)bg * a.t_rows);
+    vt_grp = a.vt_planes + (int64_t)bg * a.width * a.t_pad + tg;
   }
+  uint32_t rn[16];                                    // the NEXT chunk's accumulators, in flight while this one is processed
+  tmem_ld_issue(tmem_acc + half * EPI_CH, rn);
 #pragma unroll 1
   for (int c0 = half * EPI_CH; c0 < BN; c0 += 2 * EPI_CH) {
     const int col0 = tile_col0 + c0;
     const bool v_sink = EPI == EPI_ATT && col0 >= a.v0 && col0 < a.v0 + a.width;
     {
       uint32_t r[16];
-      tmem_ld_32x16(tmem_acc + c0, r);
+      tmem_ld_wait(rn);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = rn[j];
+      if (c0 + 2 * EPI_CH < BN) tmem_ld_issue(tmem_acc + c0 + 2 * EPI_CH, rn);
+      if (EPI == EPI_ATT && v_sink && vt_staged) {
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));      // same address in every lane: one broadcast
+          x[j] = fmaf(__uint_as_float(r[j]), p.acc_scale, b4.x); x[j + 1] = fmaf(__uint_as_float(r[j + 1]), p.acc_scale, b4.y);
+          x[j + 2] = fmaf(__uint_as_float(r[j + 2]), p.acc_scale, b4.z); x[j + 3] = fmaf(__uint_as_float(r[j + 3]), p.acc_scale, b4.w);
+        }
+        store_vt_staged<QPL>(vt_grp + (int64_t)(col0 - a.v0) * a.t_pad, a.t_pad, vt_plane, x, stage, lane);   // ends with __syncwarp: stage is free again
+      }
       if (EPI != EPI_ATT || !v_sink || p.C != nullptr) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       }
-      if (EPI == EPI_ATT && v_sink)
+      if (EPI == EPI_ATT && v_sink && !vt_staged)
         store_vt16<QPL>(vt_row + (int64_t)(col0 - a.v0) * a.t_pad, a.t_pad, vt_plane, r, p.bias ? p.bias + col0 : nullptr, p.acc_scale);
     }
     __syncwarp();
@@ -440,16 +522,20 @@ __device__ __noinline__ void epilogue_edge(const TcParams& p, const int BN, uint
 template <int EPI, int NPL>
 __device__ __forceinline__ void epilogue_warp(const TcParams& p, const int BN, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage, int lane,
                                               int half, uint64_t* full_bar, uint32_t full_phase) {
+  constexpr int EPIB = EPI == EPI_F32R2 ? EPI_F32 : EPI;
   const bool interior = row0 + 32 <= p.M && tile_col0 + BN <= p.N;
   if (EPI == EPI_F32 && interior) {                                                                  // both wait for the accumulator themselves
-    if (p.r2) epilogue_fast_f32(p, BN, tmem_acc, row0, tile_col0, stage, lane, half, full_bar, full_phase);
-    else epilogue_fast_f32_r1(p, BN, tmem_acc, row0, tile_col0, stage, lane, half, full_bar, full_phase);
+    epilogue_fast_f32_r1(p, BN, tmem_acc, row0, tile_col0, stage, lane, half, full_bar, full_phase);
+    return;
+  }
+  if (EPI == EPI_F32R2 && interior) {
+    epilogue_fast_f32(p, BN, tmem_acc, row0, tile_col0, stage, lane, half, full_bar, full_phase);
     return;
   }
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
-  if (interior) epilogue_fast<EPI, NPL>(p, BN, tmem_acc, row0, tile_col0, stage, lane, half);
-  else epilogue_edge<EPI, NPL>(p, BN, tmem_acc, row0, tile_col0, stage, lane, half);
+  if (interior) epilogue_fast<EPIB, NPL>(p, BN, tmem_acc, row0, tile_col0, stage, lane, half);
+  else epilogue_edge<EPIB, NPL>(p, BN, tmem_acc, row0, tile_col0, stage, lane, half);
 }
 
 template <int BN, int STAGES, int APL, int WPL, int EPI>  // APL / WPL: A / W planes resident per stage
@@ -809,13 +895,14 @@ static int launch_cfg_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcPa
   return FA_OK;
 }
 
-static inline int epi_kind(const TcParams& p) { return p.att.enabled ? EPI_ATT : (p.out_planes ? EPI_PLANES : EPI_F32); }
+static inline int epi_kind(const TcParams& p) { return p.att.enabled ? EPI_ATT : (p.out_planes ? EPI_PLANES : (p.r2 ? EPI_F32R2 : EPI_F32)); }
 
 template <int BN, int STAGES, int APL, int WPL>
 static int launch_cfg(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
   switch (epi_kind(p)) {
     case EPI_ATT: return launch_cfg_e<BN, STAGES, APL, WPL, EPI_ATT>(ma, mw, p, st);
     case EPI_PLANES: return launch_cfg_e<BN, STAGES, APL, WPL, EPI_PLANES>(ma, mw, p, st);
+    case EPI_F32R2: return launch_cfg_e<BN, STAGES, APL, WPL, EPI_F32R2>(ma, mw, p, st);
     default: return launch_cfg_e<BN, STAGES, APL, WPL, EPI_F32>(ma, mw, p, st);
   }
 }
@@ -835,6 +922,7 @@ static int launch_cfg2(const CUtensorMap& ma, const CUtensorMap& mw, const CUten
   switch (epi_kind(p)) {
     case EPI_ATT: return launch_cfg2_e<STAGES, PL, EPI_ATT>(ma, mw, mwt, p, pairs, st);
     case EPI_PLANES: return launch_cfg2_e<STAGES, PL, EPI_PLANES>(ma, mw, mwt, p, pairs, st);
+    case EPI_F32R2: return launch_cfg2_e<STAGES, PL, EPI_F32R2>(ma, mw, mwt, p, pairs, st);
     default: return launch_cfg2_e<STAGES, PL, EPI_F32>(ma, mw, mwt, p, pairs, st);
   }
 }

@@ -10,7 +10,8 @@ namespace fa {
 
 // y (fp32) and/or planes (fp16 [nplanes][rows][cols_pad], the A operand of a following tcgen05 GEMM)
 int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, const float* pe_inv, float xscale,
-                     int rows_per_batch, cudaStream_t st, plane_t* planes = nullptr, int nplanes = 0, int cols_pad = 0);
+                     int rows_per_batch, cudaStream_t st, plane_t* planes = nullptr, int nplanes = 0, int cols_pad = 0,
+                     float* emb_out = nullptr);   // emb_out: with pe_inv, also write the embedded (pre-norm) rows there
 int gemm_f32_launch(const float* A, int64_t lda, int64_t M, const float* W, int N, int K, const float* bias, int relu,
                     const float* r1, int64_t ldr1, const float* r2, int64_t ldr2, float* C, int64_t ldc,
                     cudaStream_t st);

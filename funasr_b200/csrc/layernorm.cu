@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ g,
                  const float* __restrict__ bta, float eps, float* y,   // x may alias y (in-place)
                  const float* __restrict__ pe_inv, float xscale, int rows_per_batch,
-                 plane_t* __restrict__ planes, int nplanes, int cols_pad) {
+                 plane_t* __restrict__ planes, int nplanes, int cols_pad, float* __restrict__ emb_out) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   pdl_wait();
@@ -43,6 +43,8 @@ layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ 
           const float pe = c < half ? sinf(__fmul_rn(pos, __ldg(pe_inv + c))) : cosf(__fmul_rn(pos, __ldg(pe_inv + c - half)));
           e[k] = __fadd_rn(__fmul_rn(e[k], xscale), pe);
         }
+        // the embedded row itself: the residual of a first layer whose in_size == size (encoder.py:120-126; CT-Transformer)
+        if (emb_out != nullptr) reinterpret_cast<float4*>(emb_out + row * n)[c4] = v[i];
       }
     }
   }
@@ -101,7 +103,7 @@ layernorm_kernel(const float* x, int64_t rows, int n, const float* __restrict__ 
 }
 
 int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, const float* pe_inv, float xscale,
-                     int rows_per_batch, cudaStream_t st, plane_t* planes, int nplanes, int cols_pad) {
+                     int rows_per_batch, cudaStream_t st, plane_t* planes, int nplanes, int cols_pad, float* emb_out) {
   if (rows <= 0) return FA_OK;
   if (!x || (!y && !planes) || !nm.g || !nm.b) return FA_ERR_ARG;
   const int n = nm.n;
@@ -113,7 +115,7 @@ int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, c
   if (npl < 0 || npl > 3 || (planes && npl == 0)) return FA_ERR_ARG;
 #define FA_LN_LAUNCH(NV, NPL)                                                                                \
   FA_CUDA_OK(launch_pdl(layernorm_kernel<NV, NPL>, dim3(blocks), dim3(256), 0, st, 1, x, rows, n, nm.g, nm.b, nm.eps, y, pe_inv,   \
-                        xscale, rows_per_batch > 0 ? rows_per_batch : 1, planes, nplanes, cols_pad))
+                        xscale, rows_per_batch > 0 ? rows_per_batch : 1, planes, nplanes, cols_pad, emb_out))
 #define FA_LN_CASE(NV)                                                                                       \
   do {                                                                                                       \
     if (npl == 0) FA_LN_LAUNCH(NV, 0); else if (npl == 1) FA_LN_LAUNCH(NV, 1);                               \
@@ -134,5 +136,5 @@ int layernorm_launch(const float* x, int64_t rows, const FaNorm& nm, float* y, c
 extern "C" int fa_layernorm(const float* x, int64_t rows, const FaNorm* norm, float* y, const float* pe_inv,
                             float xscale, int32_t rows_per_batch, fa_stream_t stream) {
   if (!norm) return FA_ERR_ARG;
-  return fa::layernorm_launch(x, rows, *norm, y, pe_inv, xscale, rows_per_batch, (cudaStream_t)stream, nullptr, 0, 0);
+  return fa::layernorm_launch(x, rows, *norm, y, pe_inv, xscale, rows_per_batch, (cudaStream_t)stream, nullptr, 0, 0, nullptr);
 }

@@ -142,8 +142,12 @@ extern "C" int fa_sanm_encoder_forward(const FaEncoder* enc, const float* feats,
     // tensor-core path: LayerNorm writes the fp16 planes the QKV GEMM consumes (no fp32 round trip, no split pass)
     if (l > 0 && in != D) return FA_ERR_UNSUPPORTED;
     const bool first = embed && l == 0;
+    // a first layer with in_size == size keeps its residual (encoder.py:120-126): the embedded rows x*sqrt(d) + PE are then needed
+    // beside their LayerNorm (CT-Transformer: 256 -> 256; Paraformer / SenseVoice: 560 -> 512, no residual)
+    float* emb = (first && in == D) ? xa : nullptr;
     FA_RETURN_IF_ERR(layernorm_launch(first ? feats : x, M, L.norm1, tc ? nullptr : u, first ? enc->pe_inv_timescales : nullptr,
-                                      first ? sqrtf((float)D) : 1.f, t_max, st, u_planes, npl, L.qkv.in_pad));
+                                      first ? sqrtf((float)D) : 1.f, t_max, st, u_planes, npl, L.qkv.in_pad, emb));
+    if (emb) x = emb;
     if (tc) {
       // QKV GEMM epilogue emits the attention operands directly: q (x d_k^-0.5) / k as fp16 planes, v transposed per head
       // as fp16 planes plus fp32 v (the only fp32 columns written) for the FSMN branch

@@ -20,6 +20,7 @@ from funasr_b200 import _abi  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--tag", default="")
 ap.add_argument("--mode", default="fp16x3")
+ap.add_argument("--only", default="", help="substring filter on the shape names")
 args = ap.parse_args()
 dev = "cuda:0"
 lib = _abi.load()
@@ -34,7 +35,10 @@ SHAPES = [("enc out-proj", 32000, 512, 512, "f32"), ("enc w_1", 32000, 2048, 512
           ("enc qkv-like", 32000, 1536, 512, "planes"),
           ("dec q/out", 9984, 512, 512, "f32"), ("dec w_1", 9984, 2048, 512, "planes"), ("dec w_2", 9984, 512, 2048, "f32"),
           ("dec kv", 32000, 1024, 512, "planes"), ("dec ragged rows", 10007, 512, 512, "f32"),
-          ("B=1 out-proj", 500, 512, 512, "f32"), ("B=1 w_1", 500, 2048, 512, "planes")]
+          ("B=1 out-proj", 500, 512, 512, "f32"), ("B=1 w_1", 500, 2048, 512, "planes"),
+          # diagnostics: the same out-projection without its residual stream / with plane output (what bounds the epilogue?)
+          ("diag out-proj no residual", 32000, 512, 512, "f32-nores"), ("diag out-proj planes", 32000, 512, 512, "planes")]
+SHAPES = [s_ for s_ in SHAPES if args.only in s_[0]]
 out = {"mode": args.mode, "tail": os.environ.get("FA_GEMM_TAIL", "1"), "shapes": []}
 for name, M, N, K, kind in SHAPES:
     x = torch.randn(M, K, generator=g).to(dev)
@@ -46,12 +50,13 @@ for name, M, N, K, kind in SHAPES:
     xp = torch.empty(npl, M, K, dtype=torch.float16, device=dev)
     _abi.check(lib.fa_split_rows(x.data_ptr(), K, M, K, K, npl, xp.data_ptr(), st), "split x")
     res = torch.randn(M, N, generator=g).to(dev) if kind == "f32" else None
-    y = torch.empty(M, N, device=dev) if kind == "f32" else None
+    y = torch.empty(M, N, device=dev) if kind.startswith("f32") else None
     yp = torch.empty(npl, M, N, dtype=torch.float16, device=dev) if kind == "planes" else None
 
     def launch():
-        if kind == "f32":
-            _abi.check(lib.fa_linear_planes(xp.data_ptr(), M, C.byref(lin), 0, res.data_ptr(), N, None, 0, y.data_ptr(), N, gm, st), "fa_linear_planes")
+        if kind.startswith("f32"):
+            _abi.check(lib.fa_linear_planes(xp.data_ptr(), M, C.byref(lin), 0, res.data_ptr() if res is not None else None, N, None, 0, y.data_ptr(), N, gm, st),
+                       "fa_linear_planes")
         else:
             _abi.check(lib.fa_linear_planes_to_planes(xp.data_ptr(), M, C.byref(lin), 1, yp.data_ptr(), N, gm, st), "fa_linear_planes_to_planes")
 
@@ -70,8 +75,8 @@ for name, M, N, K, kind in SHAPES:
     else:
         ref = xs[0] @ ws[0].t()
     ref = ref + b.double()
-    if kind == "f32":
-        got = y.double(); ref = ref + res.double()
+    if kind.startswith("f32"):
+        got = y.double(); ref = ref + (res.double() if res is not None else 0)
     else:
         got = yp.double().sum(0); ref = ref.clamp_min(0)
     err = ((got - ref).abs().max() / ref.abs().max()).item()
