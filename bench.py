@@ -215,8 +215,8 @@ class Job:
                 self.eng = ParaformerEngine(synth.make_state_dict(self.cfg, 0), self.cfg, dev, gemm_mode=mode)
             self.model.cfg = self.cfg
         self.model._engine = self.eng                                       # the plugin object drives the very same packed weights
-        self.runner_dev = ShardedRunner(self._infer_resident, dev, max_batch=64 if config != 4 else 128,
-                                        max_frames=(64 if config != 4 else 128) * 500, extra_ids=4 if config == 4 else 1)
+        mb, mf = BUCKET_LIMITS[config]
+        self.runner_dev = ShardedRunner(self._infer_resident, dev, max_batch=mb, max_frames=mf, extra_ids=4 if config == 4 else 1)
         self.runner_e2e = ShardedRunner(self._infer_plugin, dev, max_batch=self.runner_dev.max_batch, max_frames=self.runner_dev.max_frames,
                                         extra_ids=self.runner_dev.extra_ids)
         self.plan = self.runner_dev.plan(self.n_all)
@@ -294,14 +294,20 @@ class Job:
         return tot
 
 
+# (max utterances, max padded LFR frames) of one bucket: every config works on at most 32 000 padded frames (64 x 30 s) at a time
+# (128 x 30 s for the lighter SenseVoice encoder); the ragged config 3 lets short utterances fill that budget (up to 512 per bucket)
+# instead of stopping at 64, which keeps the GEMMs of the 5-10 s buckets as large as those of the 30 s ones
+BUCKET_LIMITS = {2: (64, 64 * 500), 3: (512, 64 * 500), 4: (128, 128 * 500), 5: (64, 64 * 500)}
+
+
 # ------------------------------------------------------------------------------------------------------------ CPU arm
 def parity_sample(config):
     """Global utterance indices whose ids / log-probs the CPU leg computes with the oracle, as ONE padded batch (the reference's
     padded-batch semantics matter for ragged lengths: the CIF conv reads the first padded frame)."""
     from funasr_b200.sharding import ShardedRunner
     if config == 3:
-        plan = ShardedRunner(None, "cpu").plan(_n_all_cfg3())
-        return list(plan["buckets"][-1])                                   # the shortest bucket: 64 utterances of ~5-8 s
+        plan = ShardedRunner(None, "cpu", max_batch=BUCKET_LIMITS[3][0], max_frames=BUCKET_LIMITS[3][1]).plan(_n_all_cfg3())
+        return list(plan["buckets"][-1])                                   # the last (shortest) bucket
     return [0, 1]
 
 

@@ -21,5 +21,6 @@ from .vad_model import FSMNB200, FsmnVADStreamingB200, VadEngine, WavFrontendOnl
 from .long_audio import LongAudioPipeline, merge_results, pack_segments  # noqa: F401
 from .punc import CTTransformerB200, PuncEngine, split_to_mini_sentence, split_words  # noqa: F401
 from .audio import decode_pcm, load_audio, parse_wav_header  # noqa: F401
+from .hotwords import generate_hotwords_list, load_seg_dict, seg_tokenize  # noqa: F401
 
 __version__ = "0.1.0"

@@ -120,15 +120,18 @@ __device__ __forceinline__ void frame_spectrum(const float* __restrict__ x, cons
   for (int k1 = 1; k1 < 8; ++k1) v[k1] = make_float2(v[k1].x * lt.tw8[k1].x - v[k1].y * lt.tw8[k1].y, v[k1].x * lt.tw8[k1].y + v[k1].y * lt.tw8[k1].x);
   // (3) 32-point DFT across the lanes (decimation in frequency: lane L ends with output index rev5(L))
 #pragma unroll
+  // One butterfly for both halves, no selects: r = partner + sgn * own (sgn = +1 in the lower lane: the sum; -1 in the upper lane:
+  // lower - upper), then r * w with w = the stage twiddle in the upper lane and exactly (1, 0) in the lower lane (lt.twl holds that).
+  // The last stage (pairs of adjacent lanes) has w = 1 everywhere.  Bit-identical to the select form: +-1 and (1, 0) are exact.
   for (int st = 0; st < 5; ++st) {
     const int mm = 16 >> st;
-    const bool upper = (lane & mm) != 0;
+    const float sgn = (lane & mm) ? -1.f : 1.f;
     const float2 w = lt.twl[st];
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) {
       const float px = __shfl_xor_sync(0xffffffffu, v[k1].x, mm), py = __shfl_xor_sync(0xffffffffu, v[k1].y, mm);
-      const float dx = px - v[k1].x, dy = py - v[k1].y;                       // (lower - upper), used by the upper lane
-      v[k1] = upper ? make_float2(dx * w.x - dy * w.y, dx * w.y + dy * w.x) : make_float2(v[k1].x + px, v[k1].y + py);
+      const float rx = fmaf(sgn, v[k1].x, px), ry = fmaf(sgn, v[k1].y, py);
+      v[k1] = st == 4 ? make_float2(rx, ry) : make_float2(rx * w.x - ry * w.y, rx * w.y + ry * w.x);
     }
   }
 #pragma unroll
@@ -235,7 +238,10 @@ fbank_lfr_cmvn_kernel(const float* __restrict__ wav, const int32_t* __restrict__
   for (int k1 = 1; k1 < 8; ++k1) lt.tw8[k1] = twid(2 * lane * k1);   // W_256^{lane k1}
   lt.tw8[0] = make_float2(1.f, 0.f);
 #pragma unroll
-  for (int st = 0; st < 5; ++st) { const int mm = 16 >> st; lt.twl[st] = twid((lane & (mm - 1)) * (256 / mm)); }   // W_{2m}^{lane mod m}
+  for (int st = 0; st < 5; ++st) {                                   // W_{2m}^{lane mod m} in the upper lane of a butterfly, 1 in the lower
+    const int mm = 16 >> st;
+    lt.twl[st] = (lane & mm) ? twid((lane & (mm - 1)) * (256 / mm)) : make_float2(1.f, 0.f);
+  }
   lt.rev = (int)(__brev((unsigned)lane) >> 27);
   for (int f = warp; f < nfr; f += kWarps) {
     frame_spectrum(s.wav + f * kShift, 1.0f, true, s.win, lt, lane, Zs);
@@ -339,7 +345,10 @@ fbank_tab_kernel(const float* __restrict__ wav, const int32_t* __restrict__ wav_
   for (int k1 = 1; k1 < 8; ++k1) lt.tw8[k1] = twid(2 * lane * k1);   // W_256^{lane k1}
   lt.tw8[0] = make_float2(1.f, 0.f);
 #pragma unroll
-  for (int st = 0; st < 5; ++st) { const int mm = 16 >> st; lt.twl[st] = twid((lane & (mm - 1)) * (256 / mm)); }   // W_{2m}^{lane mod m}
+  for (int st = 0; st < 5; ++st) {                                   // W_{2m}^{lane mod m} in the upper lane of a butterfly, 1 in the lower
+    const int mm = 16 >> st;
+    lt.twl[st] = (lane & mm) ? twid((lane & (mm - 1)) * (256 / mm)) : make_float2(1.f, 0.f);
+  }
   lt.rev = (int)(__brev((unsigned)lane) >> 27);
   const float* wb = wav + (int64_t)b * wav_stride;
   const bool vec2 = ((reinterpret_cast<uintptr_t>(wb) & 7) == 0);     // frames start at multiples of 160 samples
@@ -354,9 +363,10 @@ fbank_tab_kernel(const float* __restrict__ wav, const int32_t* __restrict__ wav_
       const float2 w = s.tw[k];
       const float a = w.x * orr - w.y * oi, c = w.x * oi + w.y * orr;            // W_512^k O_k
       const float re1 = er + a, im1 = ei + c, re2 = er - a, im2 = ei - c;          // X[k] = E + W O, X[256-k] = conj(E - W O)
-      const float mag1 = sqrtf(re1 * re1 + im1 * im1), mag2 = sqrtf(re2 * re2 + im2 * im2);   // rfft(..).abs().pow(2.0) :616-618
-      P[k] = mag1 * mag1;
-      P[256 - k] = mag2 * mag2;
+      // |X|^2 directly: the reference's abs().pow(2.0) (:616-618) rounds twice more; the difference (<= 1.5 ulp of P) is two orders
+      // below the rounding noise of the transform itself and saves two square-root sequences per pair
+      P[k] = re1 * re1 + im1 * im1;
+      P[256 - k] = re2 * re2 + im2 * im2;
     };
 #pragma unroll
     for (int i = 0; i < 4; ++i) pair(lane + 32 * i);             // k = 0..127 (k = 0 gives P[0] and P[256])
@@ -373,7 +383,8 @@ fbank_tab_kernel(const float* __restrict__ wav, const int32_t* __restrict__ wav_
       }
     }
     __syncwarp();
-    for (int j = lane; j < kMel; j += 32) s.logmel[f * kMel + j] = logf(fmaxf(macc[j], 1.1920929e-07f));    // :632-633
+    // __logf = lg2.approx * ln 2: <= 2 ulp outside [0.5, 2], 2^-21.4 absolute inside — far inside the 2e-5 log-mel tolerance
+    for (int j = lane; j < kMel; j += 32) s.logmel[f * kMel + j] = __logf(fmaxf(macc[j], 1.1920929e-07f));    // :632-633
     __syncwarp();
   }
   __syncthreads();

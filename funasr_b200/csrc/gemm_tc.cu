@@ -91,23 +91,6 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// The same in two halves, so the load of chunk c+1 is in flight while chunk c is converted and stored: tmem_ld_issue() then, later,
-// tmem_ld_wait(r) — the registers are in/out operands of the wait so that no use of them can be scheduled above it.
-__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :: "memory");
-}
-
 // x = hi + mid + lo split of 4 values into fp16 planes: packed converts (cvt.rn.satfinite.f16x2.f32), packed unpack.  NPL is a compile-
 // time constant: with a runtime plane count the loop compiled to a branchy 4x-unrolled body (ncu: 47 % of all executed
 // instructions of the FFN-w_1 GEMM sat in this function).
@@ -276,18 +259,13 @@ __device__ __forceinline__ void epilogue_fast_f32_r1(const TcParams& p, const in
     if (cb + 32 * i < BN) fetch(ring[i], cb + 32 * i);              // issued BEFORE waiting for the accumulator
   mbar_wait(full_bar, full_phase);
   tc_fence_after();
-  uint32_t rn[16];                                                    // next chunk's accumulators, in flight
-  tmem_ld_issue(tmem_acc + cb, rn);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {                                      // BN <= 256: at most 8 chunks per warp
     const int c0 = cb + 32 * i;
     if (c0 < BN) {
       {
         uint32_t r[16];
-        tmem_ld_wait(rn);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = rn[j];
-        if (c0 + 32 < BN) tmem_ld_issue(tmem_acc + c0 + 32, rn);
+        tmem_ld_32x16(tmem_acc + c0, r);
 #pragma unroll
         for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(srow + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       }
@@ -345,18 +323,13 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const int BN, u
     const int bg = (int)(rg / a.t_rows), tg = (int)(rg - (int64_t)bg * a.t_rows);
     vt_grp = a.vt_planes + (int64_t)bg * a.width * a.t_pad + tg;
   }
-  uint32_t rn[16];                                    // the NEXT chunk's accumulators, in flight while this one is processed
-  tmem_ld_issue(tmem_acc + half * EPI_CH, rn);
 #pragma unroll 1
   for (int c0 = half * EPI_CH; c0 < BN; c0 += 2 * EPI_CH) {
     const int col0 = tile_col0 + c0;
     const bool v_sink = EPI == EPI_ATT && col0 >= a.v0 && col0 < a.v0 + a.width;
     {
       uint32_t r[16];
-      tmem_ld_wait(rn);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) r[j] = rn[j];
-      if (c0 + 2 * EPI_CH < BN) tmem_ld_issue(tmem_acc + c0 + 2 * EPI_CH, rn);
+      tmem_ld_32x16(tmem_acc + c0, r);
       if (EPI == EPI_ATT && v_sink && vt_staged) {
         float x[16];
 #pragma unroll

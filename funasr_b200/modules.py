@@ -24,6 +24,7 @@ import torch.nn as nn
 
 from . import _abi
 from .engine import FrontendEngine, ParaformerEngine, SenseVoiceEngine, num_lfr_frames
+from .hotwords import generate_hotwords_list
 from .registry import get_tables, register
 from .synth import ParaformerConfig, SenseVoiceConfig
 
@@ -634,8 +635,8 @@ class ContextualParaformerB200(ParaformerB200):
 
     def inference(self, data_in, data_lengths=None, key: list = None, tokenizer=None, frontend=None, **kwargs):
         hw = kwargs.get("hotword_ids")          # list of token-id lists (+ trailing [sos]); text hotwords need the tokenizer
-        if hw is None and kwargs.get("hotword") and tokenizer is not None:
-            hw = [tokenizer.tokens2ids(h.split()) for h in kwargs["hotword"].split()] + [[self.sos]]
+        if hw is None and kwargs.get("hotword") and tokenizer is not None:      # .txt file or string; seg_dict aware (model.py:528-660)
+            hw = generate_hotwords_list(kwargs["hotword"], tokenizer, frontend, self.sos)
         self.engine(kwargs.get("device", "cuda")).set_hotwords(self.encode_hotwords(hw))
         return super().inference(data_in, data_lengths, key, tokenizer, frontend, **kwargs)
 
@@ -770,9 +771,9 @@ class SeacoParaformerB200(BiCifParaformerB200):
     def _forward(self, eng, speech, lens, kwargs):
         hw = kwargs.get("hotword_ids")          # list of token-id lists incl. the trailing [sos] entry (generate_hotwords_list)
         tok = kwargs.get("_tokenizer")
-        if hw is None and kwargs.get("hotword") and tok is not None:
-            hw = [tok.tokens2ids(h.split()) for h in kwargs["hotword"].split()] + [[self.sos]]
+        if hw is None and kwargs.get("hotword") and tok is not None:            # seaco_paraformer/model.py:583-690
+            hw = generate_hotwords_list(kwargs["hotword"], tok, kwargs.get("_frontend"), self.sos)
         return eng.forward_feats_seaco(speech, lens, hw, nfilter=int(kwargs.get("nfilter", 50)), sos=self.sos, eos=self.eos, blank=self.blank_id)
 
     def inference(self, data_in, data_lengths=None, key: list = None, tokenizer=None, frontend=None, **kwargs):
-        return super().inference(data_in, data_lengths, key, tokenizer, frontend, _tokenizer=tokenizer, **kwargs)
+        return super().inference(data_in, data_lengths, key, tokenizer, frontend, _tokenizer=tokenizer, _frontend=frontend, **kwargs)

@@ -1,6 +1,9 @@
 """Property tests (hypothesis) of the host-side logic around the hot path: utterance sharding, length bucketing, frame
 arithmetic and the CIF timestamp routine.  CPU only."""
+import os
+
 import numpy as np
+import pytest
 from hypothesis import given, settings, strategies as st
 
 from funasr_b200.batching import bucket_by_length, padding_efficiency, run_bucketed
@@ -60,3 +63,49 @@ def test_timestamps_are_ordered_and_inside_the_utterance(alphas, n_tok, rate, of
         assert e <= end_ms + 1
         prev = s
     assert len(res) <= max(n_tok, 1) + 1
+
+
+def test_hotword_list_follows_reference_seg_dict_rules(tmp_path):
+    """funasr_b200.hotwords.generate_hotwords_list against the reference's own function (contextual_paraformer/model.py:528-660)
+    when /root/reference is importable, and against hand-derived expectations otherwise: seg_dict lookup (lower-cased), per-character
+    fallback for CJK / digit words, <unk> for the rest, [sos] terminator; .txt files and plain strings."""
+    from funasr_b200.hotwords import generate_hotwords_list, seg_tokenize
+
+    class Tok:
+        vocab = {"<unk>": 9, "he@@": 3, "llo": 4, "你": 5, "好": 6, "7": 7, "gpu": 8}
+
+        def tokens2ids(self, toks):
+            return [self.vocab.get(t, self.vocab["<unk>"]) for t in toks]
+
+    class Fe:
+        cmvn_file = None
+
+    mvn = tmp_path / "am.mvn"
+    mvn.write_text("x")
+    (tmp_path / "seg_dict").write_text("hello he@@ llo\n你 你\n好 好\n7 7\ngpu gpu\n", encoding="utf8")
+    fe = Fe()
+    fe.cmvn_file = str(mvn)
+    sd = {"hello": "he@@ llo", "你": "你", "好": "好", "7": "7", "gpu": "gpu"}
+    assert seg_tokenize(["Hello", "你好7", "wörld", "你坏"], sd) == ["he@@", "llo", "你", "好", "7", "<unk>", "你", "<unk>"]
+    got = generate_hotwords_list("Hello 你好 GPU xyz", Tok(), fe, sos=1)
+    assert got == [[3, 4], [5, 6], [8], [9], [1]]
+    txt = tmp_path / "hw.txt"
+    txt.write_text("hello 你好\ngpu\n", encoding="utf8")
+    assert generate_hotwords_list(str(txt), Tok(), fe, sos=1) == [[3, 4, 5, 6], [8], [1]]
+    assert generate_hotwords_list(None, Tok(), fe, sos=1) is None
+    # without a seg_dict beside the cmvn file the words go to the tokenizer unchanged
+    assert generate_hotwords_list("gpu Hello", Tok(), Fe(), sos=1) == [[8], [9], [1]]
+    with pytest.raises(ValueError):
+        generate_hotwords_list("http://example.com/hw.txt", Tok(), fe, sos=1)
+    if os.path.isdir("/root/reference"):
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+        import ref_shim
+        ref_shim.import_reference()
+        from funasr.models.contextual_paraformer.model import ContextualParaformer
+
+        class Dummy:
+            sos = 1
+        for src in ["Hello 你好 GPU xyz", str(txt)]:
+            want = ContextualParaformer.generate_hotwords_list(Dummy(), src, tokenizer=Tok(), frontend=fe)
+            assert generate_hotwords_list(src, Tok(), fe, sos=1) == want
