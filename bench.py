@@ -397,7 +397,6 @@ def run_reference(args):
                 return oracle_on_sample(config, wavs)["ids"]
             return [oracle_on_sample(config, [w])["ids"][0] for w in wavs]
         if config == 2 or config == 3:
-            import ref_runner
             return ref_runner.generate_ids(am, wavs, batch_size=batch)
         tok = ref_runner.IdTokenizer() if config == 4 else None
         kw = dict(gen_kw)
