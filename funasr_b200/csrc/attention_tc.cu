@@ -2,8 +2,7 @@
 //
 // Same contract as attention_f32.cu (sanm/attention.py:288-304 with scores from :324-325; cross-attention :760-794,
 // :811-812): ctx = softmax(mask(q d_k^-0.5 . k^T)) v per head, key-padding mask, heads merged.  Score and context
-// contractions run on the 5th-gen tensor cores with fp32 accumulation in TMEM (scores: Q and K from shared memory; context: the
-// probabilities straight from TMEM, TS form, V from shared memory); operands are fp16 planes (hi, lo) of the
+// contractions run on the 5th-gen tensor cores with fp32 accumulation in TMEM; operands are fp16 planes (hi, lo) of the
 // fp32 tensors so that S = Qh.Kh + Qh.Kl + Ql.Kh and O = Ph.Vh + Ph.Vl + Pl.Vh carry ~2^-17 relative error (x3 mode),
 // or one plane (x1 mode).  The [B,H,Tq,Tk] score tensor never leaves the SM.
 //
@@ -62,25 +61,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     const __grid_constant__ CUtensorMap map_v, const AttTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr uint32_t BOX = 8192;                          // every K / V box: 64 rows x 128 B
-  constexpr uint32_t Q_BYTES = NPL * 2 * AT_Q_KBLK;       // Q planes: the A operand of every score MMA, read from shared memory
+  constexpr uint32_t Q_BYTES = NPL * 2 * AT_Q_KBLK;       // staging only: Q is moved to TMEM once
   constexpr uint32_t SLOT_BYTES = NPL * 2 * BOX;          // one K chunk (NPL planes x 2 d-blocks) or one V chunk (NPL x 2 row halves)
   constexpr int NSLOT = 5, NS = 4;                        // ring slots; S/P stages in TMEM
   constexpr int NT = NPL == 1 ? 1 : 3;
   constexpr uint16_t MC_ALL = (uint16_t)((1u << CL) - 1u);
-  // TMEM columns: S/P stage st at 128 + 64*st (4 stages) | O at 384 .. 512  (columns 0 .. 127 held the Q planes until round 2:
-  // moving Q smem -> registers -> TMEM cost ~3.9 k of a CTA's ~31 k cycles before the first MMA could issue; the score MMAs now take
-  // Q straight from the TMA tiles — 6 KB of shared-memory operand reads per 64-cycle MMA, well inside the 128 B/clk port)
-  constexpr uint32_t TM_S = 128, TM_O = 384;
+  // TMEM columns: Q planes [0, NPL*64) | S/P stage st at 128 + 64*st (4 stages) | O at 384 .. 512
+  // (Q in TMEM on purpose.  Round 2 tried the SS form — score MMAs reading Q from the TMA tiles in shared memory, no smem -> registers
+  //  -> TMEM move before the first MMA: every layer's launch got SLOWER, 105.7 -> 117.4 us at B = 64, T = 500; with Q, K and V all
+  //  coming through the shared-memory port the MMAs wait on operand reads.)
+  constexpr uint32_t TM_Q = 0, TM_S = 128, TM_O = 384;
   // align to 1024 B WITHOUT leaving the shared address space (a uintptr_t round trip makes every access a generic LD/ST)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* sQ = smem;                               // Q planes, later (all MMAs retired) the epilogue's transpose buffer
+  unsigned char* sQ = smem;                               // Q staging, later the epilogue's transpose buffer
   // K and V chunks share ONE ring, filled in exactly the order the MMA warp consumes them
   //   pass A: Khi(0) .. Khi(nc-1)          pass B: K(0), K(1), K(2), V(0), K(3), V(1), ..., K(nc-1), V(nc-3), V(nc-2), V(nc-1)
   // (score tiles run TWO chunks ahead of P.V so the softmax of chunk t has two score-MMA durations to finish before the tensor
   //  pipe needs its probabilities; with four S/P stages the stage S(t+2) overwrites was released by P.V(t-2) long before)
   unsigned char* sRing = sQ + Q_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + NSLOT * SLOT_BYTES);
-  uint64_t* q_full = bars;            // [1]  TMA -> MMA issuer (bars[1] unused)
+  uint64_t* q_full = bars;            // [1]  TMA -> softmax warps
+  uint64_t* q_ready = bars + 1;       // [1]  Q planes are in TMEM (8 arrivals)
   uint64_t* r_full = bars + 2;        // [NSLOT]
   uint64_t* r_empty = bars + 7;       // [NSLOT] CL arrivals: every CTA of the cluster has consumed its copy
   uint64_t* s_full = bars + 12;       // [NS] score tile complete
@@ -97,7 +98,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(o_full, 1);
+    mbar_init(q_full, 1); mbar_init(q_ready, 8); mbar_init(o_full, 1);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], CL); }
     for (int s = 0; s < NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&sa_free[s], 8); mbar_init(&sb_free[s], 1); mbar_init(&p_full[s], 8); }
     fence_barrier_init();
@@ -164,10 +165,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const uint32_t ring_addr = smem_u32(sRing);
       TRACE_DECL();
       TRACE(1, 0);
-      mbar_wait(q_full, 0);                                 // Q planes have landed in shared memory (TMA)
+      mbar_wait(q_ready, 0);
       tc_fence_after();
       TRACE(1, 1);
-      const uint32_t q_addr = smem_u32(sQ);
       uint32_t n = 0;                                       // ring sequence number
       auto release_slot = [&](uint32_t slot) {
         if (CL > 1) umma_commit_mc(&r_empty[slot], MC_ALL); else umma_commit(&r_empty[slot]);
@@ -188,10 +188,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int term = 0; term < nterm; ++term) {
 #pragma unroll
           for (int k = 0; k < AT_D / 16; ++k) {
-            // Q stays where TMA put it: plane ta, 64-wide head-dim block k >> 2 (a 128-row SWIZZLE_128B tile), 16-element step k & 3
-            const uint64_t da = make_sw128_desc(q_addr + (ta[term] * 2 + (k >> 2)) * AT_Q_KBLK) + 2 * (k & 3);
+            const uint32_t a_t = tmem_base + TM_Q + ta[term] * 64 + k * 8;
             const uint64_t db = make_sw128_desc(k_addr + (tb[term] * 2 + (k >> 2)) * BOX) + 2 * (k & 3);
-            umma_f16(d_s, da, db, idesc_s, (term | k) != 0 ? 1u : 0u);
+            umma_f16_ts(d_s, a_t, db, idesc_s, (term | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&s_full[st]);
@@ -242,6 +241,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #endif
     TRACE(2, 0);
     if (nc > 0) {
+      // ---- Q planes: shared memory (TMA, SWIZZLE_128B) -> TMEM, this thread's row, head dims [64 hf, 64 hf + 64)
+      mbar_wait(q_full, 0);
+#pragma unroll
+      for (int pl = 0; pl < NPL; ++pl) {
+        const unsigned char* qrow = sQ + (pl * 2 + hf) * AT_Q_KBLK + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t w[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 x = *reinterpret_cast<const uint4*>(qrow + (((half * 4 + c) ^ (r & 7)) << 4));
+            w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
+          }
+          tmem_st_32x16(tmem_base + lane_addr + TM_Q + pl * 64 + hf * 32 + half * 16, w);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_ready);
+      TRACE(2, 1);
       // ---- pass A: approximate row max over this thread's 32 columns of every chunk
       for (int i = 0; i < nc; ++i) {
         const int st = i % NS;
