@@ -932,7 +932,11 @@ int gemm_tc_planes_launch(const plane_t* a_planes, int64_t M, const FaLinear& li
   const int npl = planes_for_mode(mode);
   // 128x256 tiles halve the operand bytes per MMA cycle (the 128x128 tile is L2-bandwidth bound); used when N splits
   // evenly and there are enough tiles to fill the machine.  x6 keeps 128x128 (three planes per operand do not fit twice).
-  if (use_2cta() && npl <= 2 && N % 256 == 0 && M >= 256) {
+  // Ragged N (the vocabulary projections: 8404, 25055) also runs on pair tiles when the output is plain fp32 rows: the last column
+  // tile's W box reaches past row N of a plane — into the next plane's first rows or, for the last plane, out of the tensor map
+  // (zero fill) — so its surplus accumulator columns hold finite garbage that the bounds-checked edge epilogue never stores.
+  const bool ragged_ok = N >= 1024 && !out_planes && !att;
+  if (use_2cta() && npl <= 2 && (N % 256 == 0 || ragged_ok) && M >= 256) {
     // cta_group::2: 256 x 256 pair tiles (see gemm_tc2_kernel)
     CUtensorMap ma2, mw2;
     FA_RETURN_IF_ERR(make_plane_map(&ma2, a_planes, (uint64_t)M * npl, (uint64_t)Kp, (uint64_t)Kp, 128));
@@ -942,7 +946,7 @@ int gemm_tc_planes_launch(const plane_t* a_planes, int64_t M, const FaLinear& li
     p2.n_terms = mode == FA_GEMM_F16X1 ? 1 : 3;
     p2.relu = relu; p2.bias = lin.b; p2.r1 = r1; p2.ldr1 = ld1; p2.r2 = r2; p2.ldr2 = ld2; p2.C = y; p2.ldc = ldy;
     p2.out_planes = out_planes; p2.ldo = ldo; p2.out_nplanes = npl;
-    p2.tiles_m = (int)((M + 255) / 256); p2.tiles_n = N / 256;
+    p2.tiles_m = (int)((M + 255) / 256); p2.tiles_n = (N + 255) / 256;
     p2.acc_scale = rz_comp_scale(Kp, p2.n_terms);
     if (att) { p2.att = *att; p2.att.enabled = 1; } else { p2.att = AttnSinks{}; }
     if (att && (att->width % 32 != 0 || att->t_rows <= 0 || M % att->t_rows != 0)) return FA_ERR_UNSUPPORTED;

@@ -692,7 +692,7 @@ extern "C" int fa_linear_argmax(const FaLinear* lin, const float* a, const float
 extern "C" size_t fa_ctc_greedy_workspace_bytes(int32_t batch, int32_t t_max, int32_t vocab, int32_t gemm_mode) {
   const int64_t M = (int64_t)batch * t_max;
   ArenaSizer s;
-  s.take(M * (size_t)vocab * 4);
+  s.take(M * (size_t)((vocab + 3) & ~3) * 4);
   s.take(M * 4ull);
   s.take(gemm_tc_scratch_bytes(M, 512, gemm_mode));
   return s.off + 256;
@@ -706,15 +706,18 @@ extern "C" int fa_ctc_greedy_forward(const FaLinear* ctc_lo, const float* enc, c
   const int64_t M = (int64_t)batch * t_max;
   const int V = ctc_lo->out_f;
   Arena a(workspace, ws_bytes);
-  float* lg = a.take<float>(M * (size_t)V);
+  // internal logits rows are pitched to a multiple of 4 floats (25055 -> 25056) so the GEMM epilogue and the arg-max sweep use
+  // 16-byte accesses; a caller-provided log-prob tensor keeps the dense [M, V] layout
+  const int64_t ldv = logp ? V : ((V + 3) & ~3);
+  float* lg = a.take<float>(M * (size_t)((V + 3) & ~3));
   float* best = a.take<float>(M);
   const size_t sb = gemm_tc_scratch_bytes(M, 512, gemm_mode);
   char* sp = a.take<char>(sb);
   if (!a.ok()) return FA_ERR_WORKSPACE;
   Arena scratch(sp, sb);
   if (logp) lg = logp;
-  FA_RETURN_IF_ERR(linear(enc, ctc_lo->in_f, M, *ctc_lo, 0, nullptr, 0, nullptr, 0, lg, V, gemm_mode, &scratch, st));
-  FA_RETURN_IF_ERR(argmax_lse_launch(lg, M, V, V, argmax_ids, best, logp ? 1 : 0, st));
+  FA_RETURN_IF_ERR(linear(enc, ctc_lo->in_f, M, *ctc_lo, 0, nullptr, 0, nullptr, 0, lg, ldv, gemm_mode, &scratch, st));
+  FA_RETURN_IF_ERR(argmax_lse_launch(lg, M, V, ldv, argmax_ids, best, logp ? 1 : 0, st));
   return ctc_filter_launch(argmax_ids, lens, batch, t_max, blank, out_ids, out_lens, st);
 }
 

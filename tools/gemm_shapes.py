@@ -37,7 +37,9 @@ SHAPES = [("enc out-proj", 32000, 512, 512, "f32"), ("enc w_1", 32000, 2048, 512
           ("dec kv", 32000, 1024, 512, "planes"), ("dec ragged rows", 10007, 512, 512, "f32"),
           ("B=1 out-proj", 500, 512, 512, "f32"), ("B=1 w_1", 500, 2048, 512, "planes"),
           # diagnostics: the same out-projection without its residual stream / with plane output (what bounds the epilogue?)
-          ("diag out-proj no residual", 32000, 512, 512, "f32-nores"), ("diag out-proj planes", 32000, 512, 512, "planes")]
+          ("diag out-proj no residual", 32000, 512, 512, "f32-nores"), ("diag out-proj planes", 32000, 512, 512, "planes"),
+          # ragged N on pair tiles: the vocabulary projections (Paraformer 8404, SenseVoice 25055) and a ragged M x ragged N corner
+          ("vocab 8404", 9984, 8404, 512, "f32-nores"), ("vocab 25055", 8192, 25055, 512, "f32-nores"), ("ragged both", 1000, 1300, 512, "f32-nores")]
 SHAPES = [s_ for s_ in SHAPES if args.only in s_[0]]
 out = {"mode": args.mode, "tail": os.environ.get("FA_GEMM_TAIL", "1"), "shapes": []}
 for name, M, N, K, kind in SHAPES:
@@ -80,7 +82,7 @@ for name, M, N, K, kind in SHAPES:
     else:
         got = yp.double().sum(0); ref = ref.clamp_min(0)
     err = ((got - ref).abs().max() / ref.abs().max()).item()
-    tiles = -(-M // 256) * (N // 256)
+    tiles = -(-M // 256) * (-(-N // 256))
     row = {"name": name, "M": M, "N": N, "K": K, "kind": kind, "us": sum(times) / len(times), "us_min": min(times), "tiles": tiles, "rounds": tiles / 74.0,
            "tflops_issue": 2.0 * M * N * K * (3 if npl == 2 else 1) / (sum(times) / len(times)) / 1e6, "max_rel_err_vs_fp64": err}
     print(row, flush=True)
