@@ -19,6 +19,7 @@
 #include "kernels.h"
 #include "tc_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace fa {
 
@@ -395,6 +396,363 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// ------------------------------------------------------------------------------------------------ persistent variant
+// Same arithmetic, one CTA per SM looping over query tiles (tile = ((b * H + h) * n_qt + qt), round robin over the grid), so that
+// the fixed parts of a tile overlap the neighbouring tiles' tensor work instead of leaving the tensor pipe idle:
+//   * the Q tile of tile i+1 is fetched (TMA) while tile i computes, and moved to TMEM as soon as tile i's last score MMA has retired
+//     (barrier q_free) — i.e. under tile i's last P.V MMAs;
+//   * tile i's epilogue (O / l -> planes) runs while the tensor pipe already computes the pass-A score tiles of tile i+1 (O is handed
+//     back with o_free before the first P.V of tile i+1);
+//   * barrier initialisation, TMEM allocation and descriptor prefetch happen once per SM instead of once per tile.
+// In the one-tile-per-CTA kernel those parts (Q load + move 3.7 k, epilogue ~4 k, launch ~1.5 k of ~30 k cycles, in-kernel timeline
+// profiles/r1_attention_timeline_v15.txt) left the tensor pipe at 54 % (ncu).  Shared memory: Q 64 KB, K/V ring 4 x 32 KB, epilogue
+// transpose buffer 18 KB (16 rows per pass).  Every barrier keeps a running phase bit because its uses no longer start at zero.
+template <int NPL, int OPL>
+__global__ void __launch_bounds__(384, 1)
+attention_tcp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_v, const AttTcParams p, const int n_qt, const int n_tiles) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr uint32_t BOX = 8192;
+  constexpr uint32_t Q_BYTES = NPL * 2 * AT_Q_KBLK;
+  constexpr uint32_t SLOT_BYTES = NPL * 2 * BOX;
+  constexpr int NSLOT = 4, NS = 4;
+  constexpr int NT = NPL == 1 ? 1 : 3;
+  constexpr uint32_t EPI_BYTES = 8 * 16 * 36 * 4;              // 8 warps x [16 rows][36 floats]
+  constexpr uint32_t TM_Q = 0, TM_S = 128, TM_O = 384;
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sQ = smem;
+  unsigned char* sRing = sQ + Q_BYTES;
+  float* sEpi = reinterpret_cast<float*>(sRing + NSLOT * SLOT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(sEpi) + EPI_BYTES);
+  uint64_t* q_full = bars;            // TMA -> softmax warps: Q planes in shared memory
+  uint64_t* q_ready = bars + 1;       // softmax warps (8) -> MMA: Q planes in TMEM
+  uint64_t* sq_free = bars + 2;       // softmax warps (8) -> producer: sQ has been read
+  uint64_t* q_free = bars + 3;        // MMA -> softmax warps: every score MMA of the tile has retired (TMEM Q region reusable)
+  uint64_t* o_full = bars + 4;        // MMA -> softmax warps: O complete
+  uint64_t* o_free = bars + 5;        // softmax warps (8) -> MMA: O has been read
+  uint64_t* r_full = bars + 6;        // [NSLOT]
+  uint64_t* r_empty = r_full + NSLOT; // [NSLOT]
+  uint64_t* s_full = r_empty + NSLOT; // [NS]
+  uint64_t* sa_free = s_full + NS;    // [NS] pass A tile read (8)
+  uint64_t* sb_free = sa_free + NS;   // [NS] P.V retired (1)
+  uint64_t* p_full = sb_free + NS;    // [NS] probabilities written (8)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + NS);
+  float* s_red = reinterpret_cast<float*>(p_full + NS + 1);   // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1); mbar_init(q_ready, 8); mbar_init(sq_free, 8); mbar_init(q_free, 1); mbar_init(o_full, 1); mbar_init(o_free, 8);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 1); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&sa_free[s], 8); mbar_init(&sb_free[s], 1); mbar_init(&p_full[s], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  pdl_trigger();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + TM_O;
+
+  // tile -> (utterance, head, first query, valid keys, key chunks); identical in every role
+  auto decode = [&](int tile, int& b, int& h, int& q0, int& klen, int& nc) {
+    const int qt = tile % n_qt, bh = tile / n_qt;
+    h = bh % p.heads; b = bh / p.heads; q0 = qt * AT_BQ;
+    klen = min(p.key_lens[b], p.tk);
+    nc = (klen + AT_BKEY - 1) / AT_BKEY;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one_sync()) {
+      uint32_t n = 0, tc = 0;                                 // ring sequence number, tiles with keys so far
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int b, h, q0, klen, nc;
+        decode(tile, b, h, q0, klen, nc);
+        if (nc == 0) continue;
+        const int bkv = p.kv_shared ? 0 : b;
+        mbar_wait(sq_free, (tc & 1u) ^ 1u);                   // the previous tile's Q has left shared memory
+        mbar_expect_tx(q_full, Q_BYTES);
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl)
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+            tma_load_2d(sQ + (pl * 2 + kb) * AT_Q_KBLK, &map_q, q_full, h * AT_D + kb * 64, (int)(pl * p.q_plane_rows + (int64_t)b * p.tq + q0));
+        ++tc;
+        auto load_chunk = [&](bool is_v, int idx, int nb) {
+          const uint32_t slot = n % NSLOT;
+          mbar_wait(&r_empty[slot], ((n / NSLOT) & 1u) ^ 1u);
+          mbar_expect_tx(&r_full[slot], (uint32_t)nb * BOX);
+          unsigned char* dst = sRing + slot * SLOT_BYTES;
+          for (int bi = 0; bi < nb; ++bi) {
+            const int pl = bi >> 1, sub = bi & 1;
+            if (is_v) tma_load_2d(dst + bi * BOX, &map_v, &r_full[slot], idx * AT_BKEY, (int)(pl * p.v_plane_rows + ((int64_t)bkv * p.heads + h) * AT_D + sub * 64));
+            else tma_load_2d(dst + bi * BOX, &map_k, &r_full[slot], h * AT_D + sub * 64, (int)(pl * p.k_plane_rows + (int64_t)bkv * p.tk + idx * AT_BKEY));
+          }
+          ++n;
+        };
+        for (int i = 0; i < nc; ++i) load_chunk(false, i, 2);            // pass A: hi plane only
+        load_chunk(false, 0, NPL * 2);
+        if (nc > 1) load_chunk(false, 1, NPL * 2);
+        for (int t = 0; t < nc; ++t) {
+          if (t + 2 < nc) load_chunk(false, t + 2, NPL * 2);
+          load_chunk(true, t, NPL * 2);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc_s = make_idesc_f16(AT_BQ, AT_BKEY);
+      constexpr uint32_t idesc_o = make_idesc_f16(AT_BQ, AT_D);
+      const int ta[3] = {0, 0, 1}, tb[3] = {0, 1, 0};
+      const uint32_t ring_addr = smem_u32(sRing);
+      uint32_t n = 0, tc = 0, J = 0;                          // ring sequence, tiles with keys, score jobs so far (stage = J % NS)
+      uint32_t kinds = 0, phA = 0, phB = 0, phP = 0;          // per stage: previous user (2 bits: 1 pass A, 2 pass B), phase bits
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int b, h, q0, klen, nc;
+        decode(tile, b, h, q0, klen, nc);
+        if (nc == 0) continue;
+        mbar_wait(q_ready, tc & 1u);
+        tc_fence_after();
+        auto issue_qk = [&](int nterm, uint32_t kind) {
+          const uint32_t slot = n % NSLOT, st = J % NS;
+          mbar_wait(&r_full[slot], (n / NSLOT) & 1u);
+          const uint32_t prev = (kinds >> (2 * st)) & 3u;     // the stage's previous user must have released it
+          if (prev == 1u) { mbar_wait(&sa_free[st], (phA >> st) & 1u); phA ^= 1u << st; }
+          else if (prev == 2u) { mbar_wait(&sb_free[st], (phB >> st) & 1u); phB ^= 1u << st; }
+          kinds = (kinds & ~(3u << (2 * st))) | (kind << (2 * st));
+          tc_fence_after();
+          const uint32_t k_addr = ring_addr + slot * SLOT_BYTES;
+          const uint32_t d_s = tmem_base + TM_S + st * AT_BKEY;
+          for (int term = 0; term < nterm; ++term) {
+#pragma unroll
+            for (int k = 0; k < AT_D / 16; ++k) {
+              const uint32_t a_t = tmem_base + TM_Q + ta[term] * 64 + k * 8;
+              const uint64_t db = make_sw128_desc(k_addr + (tb[term] * 2 + (k >> 2)) * BOX) + 2 * (k & 3);
+              umma_f16_ts(d_s, a_t, db, idesc_s, (term | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&s_full[st]);
+          umma_commit(&r_empty[slot]);
+          ++n; ++J;
+        };
+        const uint32_t Jb = J + (uint32_t)nc;                 // job number of pass-B chunk 0
+        auto issue_pv = [&](int t) {
+          const uint32_t slot = n % NSLOT, st = (Jb + (uint32_t)t) % NS;
+          mbar_wait(&p_full[st], (phP >> st) & 1u); phP ^= 1u << st;
+          if (t == 0 && tc > 0) mbar_wait(o_free, (tc - 1u) & 1u);      // the previous tile's epilogue has read O
+          mbar_wait(&r_full[slot], (n / NSLOT) & 1u);
+          tc_fence_after();
+          const uint32_t v_addr = ring_addr + slot * SLOT_BYTES;
+          const uint32_t p_t = tmem_base + TM_S + st * AT_BKEY;
+          for (int term = 0; term < NT; ++term) {
+            const uint64_t db = make_sw128_desc(v_addr + tb[term] * 2 * BOX);
+#pragma unroll
+            for (int k = 0; k < AT_BKEY / 16; ++k) {
+              const uint32_t a_t = p_t + (k >> 1) * 32 + ta[term] * 16 + (k & 1) * 8;
+              umma_f16_ts(tmem_o, a_t, db + 2 * k, idesc_o, (t | term | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&sb_free[st]);
+          umma_commit(&r_empty[slot]);
+          ++n;
+        };
+        for (int i = 0; i < nc; ++i) issue_qk(1, 1u);
+        issue_qk(NT, 2u);
+        if (nc > 1) issue_qk(NT, 2u);
+        if (nc <= 2) umma_commit(q_free);                      // that was the tile's last score MMA
+        for (int t = 0; t < nc; ++t) {
+          if (t + 2 < nc) {
+            issue_qk(NT, 2u);
+            if (t + 3 == nc) umma_commit(q_free);
+          }
+          issue_pv(t);
+        }
+        umma_commit(o_full);
+        ++tc;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax + epilogue: two threads per query row =====================
+    const int qw = warp & 3, hf = (warp - 4) >> 2;
+    const int r = qw * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qw * 32) << 16;
+    float* stage = sEpi + (warp - 4) * (16 * 36);
+    uint32_t tc = 0, J = 0, phS = 0;                          // tiles with keys, score jobs, s_full phase bits
+    // epilogue of one tile: O / l for this warp's 32 rows x 64 head dims (nc == 0: zeros, no tensor memory involved)
+    auto epilogue = [&](int b, int h, int q0, int nc, float l, uint32_t o_parity) {
+      const float inv = l > 0.f ? (1.0f + (float)(nc * (AT_BKEY / 16)) * p.o_scale) / l : 0.f;
+      uint32_t v0[32], v1[32];
+      if (nc > 0) {
+        mbar_wait(o_full, o_parity);
+        tc_fence_after();
+        tmem_ld_32x32(tmem_o + lane_addr + hf * 64, v0);
+        tmem_ld_32x32(tmem_o + lane_addr + hf * 64 + 32, v1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);                    // O is in registers: the next tile's P.V may overwrite it
+      }
+      const int64_t grow0 = (int64_t)b * p.tq + q0 + qw * 32;
+      const int rows_ok = p.tq - (q0 + qw * 32);
+      const int64_t plane = (int64_t)p.batch * p.tq * p.ldp;
+#pragma unroll
+      for (int cg = 0; cg < 2; ++cg) {
+        const int c0 = hf * 64 + cg * 32;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {                 // 16 rows per pass through the transpose buffer
+          if ((lane >> 4) == half) {
+            float* srow = stage + (lane & 15) * 36;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4) {
+              float4 o4;
+              const uint32_t* vv = cg == 0 ? v0 : v1;
+              o4.x = nc > 0 ? __uint_as_float(vv[jj]) * inv : 0.f;
+              o4.y = nc > 0 ? __uint_as_float(vv[jj + 1]) * inv : 0.f;
+              o4.z = nc > 0 ? __uint_as_float(vv[jj + 2]) * inv : 0.f;
+              o4.w = nc > 0 ? __uint_as_float(vv[jj + 3]) * inv : 0.f;
+              *reinterpret_cast<float4*>(srow + jj) = o4;
+            }
+          }
+          __syncwarp();
+          const int rr0 = lane >> 3, c4 = (lane & 7) * 4;
+          const int col = h * AT_D + c0 + c4;
+          const float* sp = stage + rr0 * 36 + c4;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int row = half * 16 + it * 4 + rr0;
+            if (row < rows_ok) {
+              const float4 o4 = *reinterpret_cast<const float4*>(sp + it * 4 * 36);
+              if (p.ctx) *reinterpret_cast<float4*>(p.ctx + (grow0 + row) * p.ldc + col) = o4;
+              if (OPL > 0) {
+                float x0 = o4.x, x1 = o4.y, x2 = o4.z, x3 = o4.w;
+                plane_t* dst = p.ctx_planes + (grow0 + row) * p.ldp + col;
+#pragma unroll
+                for (int pl = 0; pl < OPL; ++pl) {
+                  uint2 pk;
+                  pk.x = pack_planes2(x0, x1);
+                  pk.y = pack_planes2(x2, x3);
+                  *reinterpret_cast<uint2*>(dst) = pk;
+                  if (pl + 1 < OPL) {
+                    dst += plane;
+                    const float2 ua = unpack_planes2(pk.x), ub = unpack_planes2(pk.y);
+                    x0 -= ua.x; x1 -= ua.y; x2 -= ub.x; x3 -= ub.y;
+                  }
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    };
+    bool pend = false;
+    int pb = 0, ph = 0, pq0 = 0, pnc = 0;
+    float pl_sum = 0.f;
+    uint32_t p_par = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int b, h, q0, klen, nc;
+      decode(tile, b, h, q0, klen, nc);
+      if (nc > 0) {
+        // ---- Q planes: shared memory -> TMEM (this thread's row, head dims [64 hf, +64)) once the previous tile's score MMAs are done
+        mbar_wait(q_full, tc & 1u);
+        if (tc > 0) { mbar_wait(q_free, (tc - 1u) & 1u); tc_fence_after(); }
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+          const unsigned char* qrow = sQ + (pl * 2 + hf) * AT_Q_KBLK + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t w[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 x = *reinterpret_cast<const uint4*>(qrow + (((half * 4 + c) ^ (r & 7)) << 4));
+              w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
+            }
+            tmem_st_32x16(tmem_base + lane_addr + TM_Q + pl * 64 + hf * 32 + half * 16, w);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(q_ready); mbar_arrive(sq_free); }
+      }
+      // ---- the previous tile's epilogue, while the tensor pipe starts on this tile's pass A
+      if (pend) { epilogue(pb, ph, pq0, pnc, pl_sum, p_par); pend = false; }
+      if (nc == 0) { epilogue(b, h, q0, 0, 0.f, 0u); continue; }
+      float m = -INFINITY, l = 0.f;
+      // ---- pass A: approximate row max
+      for (int i = 0; i < nc; ++i) {
+        const uint32_t st = J % NS;
+        mbar_wait(&s_full[st], (phS >> st) & 1u); phS ^= 1u << st;
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + lane_addr + TM_S + st * AT_BKEY + hf * 32, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sa_free[st]);
+        const int kbase = i * AT_BKEY + hf * 32;
+        if (kbase + 32 <= klen) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) m = fmaxf(m, __uint_as_float(v[jj]));
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) if (kbase + jj < klen) m = fmaxf(m, __uint_as_float(v[jj]));
+        }
+        ++J;
+      }
+      s_red[hf * 128 + r] = m;
+      softmax_bar();
+      m = fmaxf(m, s_red[(hf ^ 1) * 128 + r]);
+      const float mp = m - 6.931471805599453f;
+      // ---- pass B: probabilities in place (see attention_tc_kernel)
+      for (int t = 0; t < nc; ++t) {
+        const uint32_t st = J % NS;
+        mbar_wait(&s_full[st], (phS >> st) & 1u); phS ^= 1u << st;
+        tc_fence_after();
+        const uint32_t my_cols = tmem_base + lane_addr + TM_S + st * AT_BKEY + hf * 32;
+        uint32_t hi[16], lo[16];
+        {
+          uint32_t v[32];
+          tmem_ld_32x32(my_cols, v);
+          const int kbase = t * AT_BKEY + hf * 32;
+          const bool whole = kbase + 32 <= klen;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float a = __expf(__uint_as_float(v[2 * e]) - mp), bb = __expf(__uint_as_float(v[2 * e + 1]) - mp);
+            if (!whole) { a = (kbase + 2 * e < klen) ? a : 0.f; bb = (kbase + 2 * e + 1 < klen) ? bb : 0.f; }
+            l += a;
+            l += bb;
+            hi[e] = pack_planes2(a, bb);
+            if (NPL > 1) {
+              const float2 hv = unpack_planes2(hi[e]);
+              lo[e] = pack_planes2(a - hv.x, bb - hv.y);
+            }
+          }
+        }
+        tmem_st_32x16(my_cols, hi);
+        if (NPL > 1) tmem_st_32x16(my_cols + 16, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[st]);
+        ++J;
+      }
+      softmax_bar();                   // everyone has read the exchanged maxima before the slots are reused
+      s_red[hf * 128 + r] = l;
+      softmax_bar();
+      l += s_red[(hf ^ 1) * 128 + r];
+      pend = true; pb = b; ph = h; pq0 = q0; pnc = nc; pl_sum = l; p_par = tc & 1u;
+      ++tc;
+    }
+    if (pend) epilogue(pb, ph, pq0, pnc, pl_sum, p_par);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // V [B, tk, ldv] (head h at column h*128) -> Vt planes [npl][B*H*128][tkp] (keys contiguous), via a 64x64 smem transpose.
 __global__ void __launch_bounds__(256)
 vt_planes_kernel(const float* __restrict__ v, int64_t ldv, int tk, int tkp, int heads, int nplanes, int64_t plane_elems,
@@ -504,8 +862,27 @@ static int att_cluster_cap() {
   return v;
 }
 
+// The persistent kernel (one CTA per SM looping over query tiles) is the default: 98.4 us against 106.0 us per encoder layer at
+// B = 64, T = 500 (ncu launch lists of the same build, profiles/README.md).  FA_ATT_PERSIST=0: one CTA per query tile (A/B runs).
+static bool att_persistent() {
+  static const bool on = [] { const char* e = getenv("FA_ATT_PERSIST"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+template <int NPL, int OPL>
+static int launch_att_p(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttTcParams& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)NPL * (2 * AT_Q_KBLK + 4 * 2 * 8192) + 8 * 16 * 36 * 4 + 2048 + 1024;
+  static PerDeviceOnce once;
+  FA_RETURN_IF_ERR(ensure_dyn_smem(attention_tcp_kernel<NPL, OPL>, smem, once));
+  const int n_qt = (int)grid.x, n_tiles = (int)(grid.x * grid.y * grid.z);
+  const int ctas = n_tiles < sm_count() ? n_tiles : sm_count();
+  FA_CUDA_OK(launch_pdl(attention_tcp_kernel<NPL, OPL>, dim3(ctas), dim3(384), smem, st, 1, mq, mk, mv, p, n_qt, n_tiles));
+  return FA_OK;
+}
+
 template <int NPL, int OPL>
 static int launch_att(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttTcParams& p, cudaStream_t st) {
+  if (att_persistent()) return launch_att_p<NPL, OPL>(grid, mq, mk, mv, p, st);
   const int cap = att_cluster_cap();
   if (cap >= 4 && grid.x % 4 == 0) return launch_att_c<NPL, OPL, 4>(grid, mq, mk, mv, p, st);
   if (cap >= 2 && grid.x % 2 == 0) return launch_att_c<NPL, OPL, 2>(grid, mq, mk, mv, p, st);

@@ -8,6 +8,8 @@
 // fp64 then cast to fp32 (:835), fires = (fire + ps) - floor(ps) (:846-847), per-channel fp32 running sum of
 // alpha*h with separate multiply and add (:878), frame = ((PH[t_k] - PH[t_{k-1}]) + rem_{k-1} h_{k-1}) - rem_k h_k (:896).
 #include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
 #include <math.h>
 
 namespace fa {
@@ -28,15 +30,47 @@ cif_im2col_kernel(const float* __restrict__ enc, int t_max, int d, float* __rest
   reinterpret_cast<float4*>(xc)[i] = val;
 }
 
-// alpha[b,t] = relu(sigmoid(c . w + b0) * smooth - noise) * mask     (:280-285); one warp per row
+// The k = 3 conv as ONE GEMM without an im2col copy (tensor-core path): the encoder output goes to fp16 planes with one zero row in
+// front of and behind every utterance, P[b][0] = 0, P[b][1 + t] = enc[b, t], P[b][T + 1] = 0 (row pitch d).  The im2col row of
+// (b, t) — enc[b, t-1] | enc[b, t] | enc[b, t+1] — is then the 3 d CONTIGUOUS elements starting at P[b][t], i.e. the im2col matrix is
+// the overlapping 2-D view {rows b (T + 2) + t, 3 d columns, row pitch d}, which a TMA tensor map describes directly.  Rows
+// b (T + 2) + T and + T + 1 of that view mix two utterances: their outputs are computed and never read.
+__global__ void __launch_bounds__(256)
+cif_pad_planes_kernel(const float* __restrict__ enc, int t_max, int d, int nplanes, int64_t rows_alloc, int64_t rows_valid,
+                      plane_t* __restrict__ planes) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d4 = d >> 2;
+  if (i >= rows_alloc * d4) return;
+  const int64_t r = i / d4;
+  const int c = (int)(i - r * d4) * 4;
+  const int tp = t_max + 2;
+  const int64_t b = r / tp;
+  const int t = (int)(r - b * tp) - 1;
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < rows_valid && t >= 0 && t < t_max) x = __ldg(reinterpret_cast<const float4*>(enc + (b * t_max + t) * d + c));
+  float v[4] = {x.x, x.y, x.z, x.w};
+  const int64_t plane = rows_alloc * d;
+  for (int pl = 0; pl < nplanes; ++pl) {
+    uint2 pk;
+    pk.x = pack_planes2(v[0], v[1]);
+    pk.y = pack_planes2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(planes + pl * plane + r * d + c) = pk;
+    const float2 a = unpack_planes2(pk.x), bb = unpack_planes2(pk.y);
+    v[0] -= a.x; v[1] -= a.y; v[2] -= bb.x; v[3] -= bb.y;
+  }
+}
+
+// alpha[b,t] = relu(sigmoid(c . w + b0) * smooth - noise) * mask     (:280-285); one warp per row.  c_tb: rows of c per utterance
+// (t_max, or t_max + 2 when c comes from the padded-view GEMM above)
 __global__ void __launch_bounds__(256)
 cif_alpha_kernel(const float* __restrict__ c, int d, const float* __restrict__ w, const float* __restrict__ b0,
                  const int32_t* __restrict__ lens, int t_max, int64_t rows, float smooth, float noise,
-                 float* __restrict__ alpha_rows) {
+                 float* __restrict__ alpha_rows, int c_tb) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const float4* cr = reinterpret_cast<const float4*>(c + row * d);
+  const int64_t crow = (row / t_max) * c_tb + (row % t_max);
+  const float4* cr = reinterpret_cast<const float4*>(c + crow * d);
   const float4* w4 = reinterpret_cast<const float4*>(w);
   float acc = 0.f;
   for (int i = lane; i < (d >> 2); i += 32) {
@@ -262,9 +296,18 @@ int cif_im2col_launch(const float* enc, int64_t rows, int t_max, int d, float* x
 }
 
 int cif_alpha_launch(const float* c, int d, const float* w, const float* b0, const int32_t* lens, int t_max,
-                     int64_t rows, float smooth, float noise, float* alpha_rows, cudaStream_t st) {
+                     int64_t rows, float smooth, float noise, float* alpha_rows, cudaStream_t st, int c_rows_per_batch) {
   if (rows <= 0) return FA_OK;
-  cif_alpha_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(c, d, w, b0, lens, t_max, rows, smooth, noise, alpha_rows);
+  cif_alpha_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(c, d, w, b0, lens, t_max, rows, smooth, noise, alpha_rows,
+                                                               c_rows_per_batch > 0 ? c_rows_per_batch : t_max);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
+
+int cif_pad_planes_launch(const float* enc, int batch, int t_max, int d, int nplanes, int64_t rows_alloc, plane_t* planes, cudaStream_t st) {
+  if ((d & 3) || nplanes < 1 || nplanes > 3) return FA_ERR_UNSUPPORTED;
+  const int64_t total = rows_alloc * (d / 4);
+  cif_pad_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(enc, t_max, d, nplanes, rows_alloc, (int64_t)batch * (t_max + 2), planes);
   FA_CHECK_LAUNCH();
   return FA_OK;
 }

@@ -922,8 +922,11 @@ static bool use_2cta() {
 // A planes already split: a_planes [npl][M][Kp]
 int gemm_tc_planes_launch(const plane_t* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
                           const float* r2, int64_t ld2, float* y, int64_t ldy, plane_t* out_planes, int64_t ldo,
-                          int mode, cudaStream_t st, const AttnSinks* att) {
+                          int mode, cudaStream_t st, const AttnSinks* att, int64_t a_ld, int64_t a_plane_rows) {
   if (M <= 0) return FA_OK;
+  const uint64_t lda = a_ld > 0 ? (uint64_t)a_ld : (uint64_t)lin.in_pad;          // A row pitch (overlapping view: < K_pad)
+  const int64_t apr = a_plane_rows > 0 ? a_plane_rows : M;                         // rows between consecutive A planes
+  if (lda & 7) return FA_ERR_UNSUPPORTED;
   if (!lin.w_planes || !a_planes) return FA_ERR_ARG;
   const int N = lin.out_f, Kp = lin.in_pad;
   if (Kp % TC_BK != 0 || M * 3 > 0x7fffffffLL) return FA_ERR_UNSUPPORTED;
@@ -939,10 +942,12 @@ int gemm_tc_planes_launch(const plane_t* a_planes, int64_t M, const FaLinear& li
   if (use_2cta() && npl <= 2 && (N % 256 == 0 || ragged_ok) && M >= 256) {
     // cta_group::2: 256 x 256 pair tiles (see gemm_tc2_kernel)
     CUtensorMap ma2, mw2;
-    FA_RETURN_IF_ERR(make_plane_map(&ma2, a_planes, (uint64_t)M * npl, (uint64_t)Kp, (uint64_t)Kp, 128));
+    // rows of the map: every row of every plane whose K_pad elements lie inside the allocation (an overlapping view's last rows do not)
+    const uint64_t a_rows = (uint64_t)apr * npl - (lda < (uint64_t)Kp ? ((uint64_t)Kp - lda + lda - 1) / lda : 0);
+    FA_RETURN_IF_ERR(make_plane_map(&ma2, a_planes, a_rows, (uint64_t)Kp, lda, 128));
     FA_RETURN_IF_ERR(make_plane_map(&mw2, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, 128));
     TcParams p2;
-    p2.M = M; p2.N = N; p2.Kp = Kp; p2.a_plane_rows = M; p2.w_plane_rows = N;
+    p2.M = M; p2.N = N; p2.Kp = Kp; p2.a_plane_rows = apr; p2.w_plane_rows = N;
     p2.n_terms = mode == FA_GEMM_F16X1 ? 1 : 3;
     p2.relu = relu; p2.bias = lin.b; p2.r1 = r1; p2.ldr1 = ld1; p2.r2 = r2; p2.ldr2 = ld2; p2.C = y; p2.ldc = ldy;
     p2.out_planes = out_planes; p2.ldo = ldo; p2.out_nplanes = npl;
@@ -962,10 +967,11 @@ int gemm_tc_planes_launch(const plane_t* a_planes, int64_t M, const FaLinear& li
   const bool wide = (npl <= 2) && (N % 256 == 0) && (N >= 1024);
   const int BN = wide ? 256 : 128;
   CUtensorMap ma, mw;
-  FA_RETURN_IF_ERR(make_plane_map(&ma, a_planes, (uint64_t)M * npl, (uint64_t)Kp, (uint64_t)Kp, TC_BM));
+  const uint64_t a_rows1 = (uint64_t)apr * npl - (lda < (uint64_t)Kp ? ((uint64_t)Kp - lda + lda - 1) / lda : 0);
+  FA_RETURN_IF_ERR(make_plane_map(&ma, a_planes, a_rows1, (uint64_t)Kp, lda, TC_BM));
   FA_RETURN_IF_ERR(make_plane_map(&mw, lin.w_planes, (uint64_t)N * 3, (uint64_t)Kp, (uint64_t)Kp, wide ? 128 : BN));
   TcParams p;
-  p.M = M; p.N = N; p.Kp = Kp; p.a_plane_rows = M; p.w_plane_rows = N;
+  p.M = M; p.N = N; p.Kp = Kp; p.a_plane_rows = apr; p.w_plane_rows = N;
   p.n_terms = mode == FA_GEMM_F16X1 ? 1 : (mode == FA_GEMM_F16X3 ? 3 : 6);
   p.relu = relu; p.bias = lin.b; p.r1 = r1; p.ldr1 = ld1; p.r2 = r2; p.ldr2 = ld2; p.C = y; p.ldc = ldy;
   p.out_planes = out_planes; p.ldo = ldo; p.out_nplanes = npl;

@@ -45,7 +45,8 @@ int attention_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk
                         int kv_shared = 0);   // kv_shared: k / v hold ONE batch entry that every utterance attends over
 int gemm_tc_planes_launch(const plane_t* a_planes, int64_t M, const FaLinear& lin, int relu, const float* r1, int64_t ld1,
                           const float* r2, int64_t ld2, float* y, int64_t ldy, plane_t* out_planes, int64_t ldo,
-                          int mode, cudaStream_t st, const AttnSinks* att = nullptr);
+                          int mode, cudaStream_t st, const AttnSinks* att = nullptr, int64_t a_ld = 0, int64_t a_plane_rows = 0);
+// a_ld / a_plane_rows (0 = dense: K_pad / M): row pitch of the A planes and rows between planes when A is an overlapping view
 int split_rows_launch(const float* x, int64_t ldx, int64_t rows, int cols, int cols_pad, int nplanes, plane_t* planes,
                       cudaStream_t st);
 int attention_f32_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
@@ -61,7 +62,8 @@ int cif_fire_loop_launch(const float* enc, const float* alpha_rows, const int32_
                          cudaStream_t st);
 int cif_upsample_scan_launch(float* alphas2, const int32_t* token_num, int batch, int t3, float thr, float* us_peaks, cudaStream_t st);
 int cif_alpha_launch(const float* c, int d, const float* w, const float* b0, const int32_t* lens, int t_max,
-                     int64_t rows, float smooth, float noise, float* alpha_rows, cudaStream_t st);
+                     int64_t rows, float smooth, float noise, float* alpha_rows, cudaStream_t st, int c_rows_per_batch = 0);
+int cif_pad_planes_launch(const float* enc, int batch, int t_max, int d, int nplanes, int64_t rows_alloc, plane_t* planes, cudaStream_t st);
 int cif_fire_launch(const float* enc, const float* alpha_rows, const int32_t* lens, int batch, int t_max, int d,
                     float tail, float* acoustic, int n_cap, int32_t* token_num, float* alphas, float* peaks,
                     cudaStream_t st);

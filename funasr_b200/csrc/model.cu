@@ -232,10 +232,23 @@ extern "C" int fa_cif_predictor_forward(const FaPredictor* pred, const float* en
   char* sp = a.take<char>(sb);
   if (!a.ok()) return FA_ERR_WORKSPACE;
   Arena scratch(sp, sb);
-  FA_RETURN_IF_ERR(cif_im2col_launch(enc, M, t_max, D, xc, st));
-  FA_RETURN_IF_ERR(linear(xc, 3 * D, M, pred->conv, 1, nullptr, 0, nullptr, 0, c, D, gemm_mode, &scratch, st));
-  FA_RETURN_IF_ERR(cif_alpha_launch(c, D, pred->out_w, pred->out_b, lens, t_max, M, pred->smooth_factor,
-                                    pred->noise_threshold, alpha_rows, st));
+  if (gemm_mode != FA_GEMM_F32_SIMT && pred->conv.w_planes && pred->conv.in_pad == 3 * D) {
+    // tensor-core path: no im2col copy — the GEMM's A operand is the overlapping view of the zero-padded encoder planes (cif.cu)
+    const int npl = npl_for(gemm_mode);
+    const int64_t Mp = (int64_t)batch * (t_max + 2), rows_alloc = Mp + 2;
+    plane_t* pp = scratch.take<plane_t>((size_t)npl * rows_alloc * D);          // <= the im2col planes this scratch was sized for
+    if (!scratch.ok()) return FA_ERR_WORKSPACE;
+    float* cp = xc;                                                              // [Mp, D] fits the unused im2col buffer (3 D per row)
+    FA_RETURN_IF_ERR(cif_pad_planes_launch(enc, batch, t_max, D, npl, rows_alloc, pp, st));
+    FA_RETURN_IF_ERR(gemm_tc_planes_launch(pp, Mp, pred->conv, 1, nullptr, 0, nullptr, 0, cp, D, nullptr, 0, gemm_mode, st, nullptr, D, rows_alloc));
+    FA_RETURN_IF_ERR(cif_alpha_launch(cp, D, pred->out_w, pred->out_b, lens, t_max, M, pred->smooth_factor,
+                                      pred->noise_threshold, alpha_rows, st, t_max + 2));
+  } else {
+    FA_RETURN_IF_ERR(cif_im2col_launch(enc, M, t_max, D, xc, st));
+    FA_RETURN_IF_ERR(linear(xc, 3 * D, M, pred->conv, 1, nullptr, 0, nullptr, 0, c, D, gemm_mode, &scratch, st));
+    FA_RETURN_IF_ERR(cif_alpha_launch(c, D, pred->out_w, pred->out_b, lens, t_max, M, pred->smooth_factor,
+                                      pred->noise_threshold, alpha_rows, st));
+  }
   FA_CUDA_OK(cudaMemsetAsync(acoustic, 0, (size_t)batch * n_cap * D * sizeof(float), st));
   if (pred->cif_variant == 1)     // CifPredictorV3 (BiCifParaformer): sequential fp32 `cif`
     return cif_fire_loop_launch(enc, alpha_rows, lens, batch, t_max, D, pred->tail_threshold, pred->threshold, acoustic, n_cap,

@@ -126,7 +126,7 @@ def test_linear_fp32_vs_oracle(rows, out_f, in_f):
 
 @pytest.mark.parametrize("mode,tol", [("fp16x6", 1e-5), ("fp16x3", 3e-5), ("fp16", 2e-2)])
 @pytest.mark.parametrize("rows,out_f,in_f", [(1000, 1536, 560), (300, 512, 2048), (130, 8404, 512), (129, 1000, 512), (32000, 512, 512),
-                                             (1000, 8404, 512), (700, 25055, 512)])    # ragged N on pair tiles (vocabulary projections)
+                                             (1000, 8404, 512), (700, 25060, 512)])    # ragged N on pair tiles (vocabulary projections; residual rows need a pitch % 4 == 0)
 def test_linear_tcgen05_vs_oracle(rows, out_f, in_f, mode, tol):
     """tcgen05/TMEM/TMA GEMM with fp16 operand splitting against the CPU fp32 nn.Linear (ragged M/N/K tails)."""
     abi, lib = _lib()
