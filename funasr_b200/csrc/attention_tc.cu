@@ -401,14 +401,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // the fixed parts of a tile overlap the neighbouring tiles' tensor work instead of leaving the tensor pipe idle:
 //   * the Q tile of tile i+1 is fetched (TMA) while tile i computes, and moved to TMEM as soon as tile i's last score MMA has retired
 //     (barrier q_free) — i.e. under tile i's last P.V MMAs;
-//   * tile i's epilogue (O / l -> planes) runs while the tensor pipe already computes the pass-A score tiles of tile i+1 (O is handed
-//     back with o_free before the first P.V of tile i+1);
+//   * tile i's epilogue (O / l -> planes) is done by four warps of its own (one per TMEM lane quarter) while the softmax warps and
+//     the tensor pipe are already in tile i+1 (the row sums travel through shared memory, l_full / l_free; O is handed back with
+//     o_free before the first P.V of tile i+1);
 //   * barrier initialisation, TMEM allocation and descriptor prefetch happen once per SM instead of once per tile.
 // In the one-tile-per-CTA kernel those parts (Q load + move 3.7 k, epilogue ~4 k, launch ~1.5 k of ~30 k cycles, in-kernel timeline
 // profiles/r1_attention_timeline_v15.txt) left the tensor pipe at 54 % (ncu).  Shared memory: Q 64 KB, K/V ring 4 x 32 KB, epilogue
-// transpose buffer 18 KB (16 rows per pass).  Every barrier keeps a running phase bit because its uses no longer start at zero.
+// transpose buffer 9 KB (16 rows per pass).  Every barrier keeps a running phase bit because its uses no longer start at zero.
+// Warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-11 softmax (two threads per query row), 12-15 epilogue.
 template <int NPL, int OPL>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 attention_tcp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, const AttTcParams p, const int n_qt, const int n_tiles) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -417,7 +419,7 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   constexpr uint32_t SLOT_BYTES = NPL * 2 * BOX;
   constexpr int NSLOT = 4, NS = 4;
   constexpr int NT = NPL == 1 ? 1 : 3;
-  constexpr uint32_t EPI_BYTES = 8 * 16 * 36 * 4;              // 8 warps x [16 rows][36 floats]
+  constexpr uint32_t EPI_BYTES = 4 * 16 * 36 * 4;              // 4 epilogue warps x [16 rows][36 floats]
   constexpr uint32_t TM_Q = 0, TM_S = 128, TM_O = 384;
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sQ = smem;
@@ -429,20 +431,24 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* sq_free = bars + 2;       // softmax warps (8) -> producer: sQ has been read
   uint64_t* q_free = bars + 3;        // MMA -> softmax warps: every score MMA of the tile has retired (TMEM Q region reusable)
   uint64_t* o_full = bars + 4;        // MMA -> softmax warps: O complete
-  uint64_t* o_free = bars + 5;        // softmax warps (8) -> MMA: O has been read
+  uint64_t* o_free = bars + 5;        // epilogue warps (4) -> MMA: O has been read
   uint64_t* r_full = bars + 6;        // [NSLOT]
   uint64_t* r_empty = r_full + NSLOT; // [NSLOT]
   uint64_t* s_full = r_empty + NSLOT; // [NS]
   uint64_t* sa_free = s_full + NS;    // [NS] pass A tile read (8)
   uint64_t* sb_free = sa_free + NS;   // [NS] P.V retired (1)
   uint64_t* p_full = sb_free + NS;    // [NS] probabilities written (8)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + NS);
-  float* s_red = reinterpret_cast<float*>(p_full + NS + 1);   // [2][128]
+  uint64_t* l_full = p_full + NS;     // softmax warps of column half 0 (4) -> epilogue warps: row sums of the tile are in s_l
+  uint64_t* l_free = l_full + 1;      // epilogue warps (4) -> softmax warps: s_l has been read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(l_free + 1);
+  float* s_red = reinterpret_cast<float*>(l_free + 2);        // [2][128] row max / row sum exchange between the column halves
+  float* s_l = s_red + 256;                                   // [128] final row sums of the tile handed to the epilogue warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(q_ready, 8); mbar_init(sq_free, 8); mbar_init(q_free, 1); mbar_init(o_full, 1); mbar_init(o_free, 8);
+    mbar_init(q_full, 1); mbar_init(q_ready, 8); mbar_init(sq_free, 8); mbar_init(q_free, 1); mbar_init(o_full, 1); mbar_init(o_free, 4);
+    mbar_init(l_full, 4); mbar_init(l_free, 4);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 1); }
     for (int s = 0; s < NS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&sa_free[s], 8); mbar_init(&sb_free[s], 1); mbar_init(&p_full[s], 8); }
     fence_barrier_init();
@@ -575,32 +581,39 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         ++tc;
       }
     }
-  } else if (warp >= 4) {
-    // ===================== softmax + epilogue: two threads per query row =====================
-    const int qw = warp & 3, hf = (warp - 4) >> 2;
-    const int r = qw * 32 + lane;
+  } else if (warp >= 12) {
+    // ===================== epilogue: O / l -> fp16 planes and/or fp32, one warp per TMEM lane quarter =====================
+    const int qw = warp & 3;
     const uint32_t lane_addr = (uint32_t)(qw * 32) << 16;
-    float* stage = sEpi + (warp - 4) * (16 * 36);
-    uint32_t tc = 0, J = 0, phS = 0;                          // tiles with keys, score jobs, s_full phase bits
-    // epilogue of one tile: O / l for this warp's 32 rows x 64 head dims (nc == 0: zeros, no tensor memory involved)
-    auto epilogue = [&](int b, int h, int q0, int nc, float l, uint32_t o_parity) {
-      const float inv = l > 0.f ? (1.0f + (float)(nc * (AT_BKEY / 16)) * p.o_scale) / l : 0.f;
-      uint32_t v0[32], v1[32];
+    float* stage = sEpi + qw * (16 * 36);
+    uint32_t tc = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int b, h, q0, klen, nc;
+      decode(tile, b, h, q0, klen, nc);
+      float inv = 0.f;
       if (nc > 0) {
-        mbar_wait(o_full, o_parity);
-        tc_fence_after();
-        tmem_ld_32x32(tmem_o + lane_addr + hf * 64, v0);
-        tmem_ld_32x32(tmem_o + lane_addr + hf * 64 + 32, v1);
-        tc_fence_before();
+        mbar_wait(l_full, tc & 1u);
+        const float l = s_l[qw * 32 + lane];
         __syncwarp();
-        if (lane == 0) mbar_arrive(o_free);                    // O is in registers: the next tile's P.V may overwrite it
+        if (lane == 0) mbar_arrive(l_free);
+        inv = l > 0.f ? (1.0f + (float)(nc * (AT_BKEY / 16)) * p.o_scale) / l : 0.f;   // nc key chunks x 4 k-steps were accumulated into O
+        mbar_wait(o_full, tc & 1u);
+        tc_fence_after();
       }
       const int64_t grow0 = (int64_t)b * p.tq + q0 + qw * 32;
       const int rows_ok = p.tq - (q0 + qw * 32);
       const int64_t plane = (int64_t)p.batch * p.tq * p.ldp;
-#pragma unroll
-      for (int cg = 0; cg < 2; ++cg) {
-        const int c0 = hf * 64 + cg * 32;
+#pragma unroll 1
+      for (int cg = 0; cg < 4; ++cg) {
+        uint32_t v[32];
+        if (nc > 0) {
+          tmem_ld_32x32(tmem_o + lane_addr + cg * 32, v);
+          if (cg == 3) {                                       // O is in registers: the next tile's P.V may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_free);
+          }
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {                 // 16 rows per pass through the transpose buffer
           if ((lane >> 4) == half) {
@@ -608,17 +621,16 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
             for (int jj = 0; jj < 32; jj += 4) {
               float4 o4;
-              const uint32_t* vv = cg == 0 ? v0 : v1;
-              o4.x = nc > 0 ? __uint_as_float(vv[jj]) * inv : 0.f;
-              o4.y = nc > 0 ? __uint_as_float(vv[jj + 1]) * inv : 0.f;
-              o4.z = nc > 0 ? __uint_as_float(vv[jj + 2]) * inv : 0.f;
-              o4.w = nc > 0 ? __uint_as_float(vv[jj + 3]) * inv : 0.f;
+              o4.x = nc > 0 ? __uint_as_float(v[jj]) * inv : 0.f;
+              o4.y = nc > 0 ? __uint_as_float(v[jj + 1]) * inv : 0.f;
+              o4.z = nc > 0 ? __uint_as_float(v[jj + 2]) * inv : 0.f;
+              o4.w = nc > 0 ? __uint_as_float(v[jj + 3]) * inv : 0.f;
               *reinterpret_cast<float4*>(srow + jj) = o4;
             }
           }
           __syncwarp();
           const int rr0 = lane >> 3, c4 = (lane & 7) * 4;
-          const int col = h * AT_D + c0 + c4;
+          const int col = h * AT_D + cg * 32 + c4;
           const float* sp = stage + rr0 * 36 + c4;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
@@ -647,40 +659,39 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           __syncwarp();
         }
       }
-    };
-    bool pend = false;
-    int pb = 0, ph = 0, pq0 = 0, pnc = 0;
-    float pl_sum = 0.f;
-    uint32_t p_par = 0;
+      if (nc > 0) ++tc;
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax: two threads per query row =====================
+    const int qw = warp & 3, hf = (warp - 4) >> 2;
+    const int r = qw * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(qw * 32) << 16;
+    uint32_t tc = 0, J = 0, phS = 0;                          // tiles with keys, score jobs, s_full phase bits
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       int b, h, q0, klen, nc;
       decode(tile, b, h, q0, klen, nc);
-      if (nc > 0) {
-        // ---- Q planes: shared memory -> TMEM (this thread's row, head dims [64 hf, +64)) once the previous tile's score MMAs are done
-        mbar_wait(q_full, tc & 1u);
-        if (tc > 0) { mbar_wait(q_free, (tc - 1u) & 1u); tc_fence_after(); }
+      if (nc == 0) continue;                                   // the epilogue warps write the zero rows
+      // ---- Q planes: shared memory -> TMEM (this thread's row, head dims [64 hf, +64)) once the previous tile's score MMAs are done
+      mbar_wait(q_full, tc & 1u);
+      if (tc > 0) { mbar_wait(q_free, (tc - 1u) & 1u); tc_fence_after(); }
 #pragma unroll
-        for (int pl = 0; pl < NPL; ++pl) {
-          const unsigned char* qrow = sQ + (pl * 2 + hf) * AT_Q_KBLK + (r >> 3) * 1024 + (r & 7) * 128;
+      for (int pl = 0; pl < NPL; ++pl) {
+        const unsigned char* qrow = sQ + (pl * 2 + hf) * AT_Q_KBLK + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t w[16];
+        for (int half = 0; half < 2; ++half) {
+          uint32_t w[16];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 x = *reinterpret_cast<const uint4*>(qrow + (((half * 4 + c) ^ (r & 7)) << 4));
-              w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
-            }
-            tmem_st_32x16(tmem_base + lane_addr + TM_Q + pl * 64 + hf * 32 + half * 16, w);
+          for (int c = 0; c < 4; ++c) {
+            const uint4 x = *reinterpret_cast<const uint4*>(qrow + (((half * 4 + c) ^ (r & 7)) << 4));
+            w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
           }
+          tmem_st_32x16(tmem_base + lane_addr + TM_Q + pl * 64 + hf * 32 + half * 16, w);
         }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(q_ready); mbar_arrive(sq_free); }
       }
-      // ---- the previous tile's epilogue, while the tensor pipe starts on this tile's pass A
-      if (pend) { epilogue(pb, ph, pq0, pnc, pl_sum, p_par); pend = false; }
-      if (nc == 0) { epilogue(b, h, q0, 0, 0.f, 0u); continue; }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(q_ready); mbar_arrive(sq_free); }
       float m = -INFINITY, l = 0.f;
       // ---- pass A: approximate row max
       for (int i = 0; i < nc; ++i) {
@@ -742,11 +753,15 @@ attention_tcp_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       softmax_bar();                   // everyone has read the exchanged maxima before the slots are reused
       s_red[hf * 128 + r] = l;
       softmax_bar();
-      l += s_red[(hf ^ 1) * 128 + r];
-      pend = true; pb = b; ph = h; pq0 = q0; pnc = nc; pl_sum = l; p_par = tc & 1u;
+      if (hf == 0) {                   // row sums to the epilogue warps (which have consumed the previous tile's by now)
+        l += s_red[128 + r];
+        if (tc > 0) mbar_wait(l_free, (tc - 1u) & 1u);
+        s_l[r] = l;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(l_full);
+      }
       ++tc;
     }
-    if (pend) epilogue(pb, ph, pq0, pnc, pl_sum, p_par);
   }
   tc_fence_before();
   __syncthreads();
@@ -871,12 +886,12 @@ static bool att_persistent() {
 
 template <int NPL, int OPL>
 static int launch_att_p(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttTcParams& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)NPL * (2 * AT_Q_KBLK + 4 * 2 * 8192) + 8 * 16 * 36 * 4 + 2048 + 1024;
+  constexpr size_t smem = (size_t)NPL * (2 * AT_Q_KBLK + 4 * 2 * 8192) + 4 * 16 * 36 * 4 + 2048 + 1024;
   static PerDeviceOnce once;
   FA_RETURN_IF_ERR(ensure_dyn_smem(attention_tcp_kernel<NPL, OPL>, smem, once));
   const int n_qt = (int)grid.x, n_tiles = (int)(grid.x * grid.y * grid.z);
   const int ctas = n_tiles < sm_count() ? n_tiles : sm_count();
-  FA_CUDA_OK(launch_pdl(attention_tcp_kernel<NPL, OPL>, dim3(ctas), dim3(384), smem, st, 1, mq, mk, mv, p, n_qt, n_tiles));
+  FA_CUDA_OK(launch_pdl(attention_tcp_kernel<NPL, OPL>, dim3(ctas), dim3(512), smem, st, 1, mq, mk, mv, p, n_qt, n_tiles));
   return FA_OK;
 }
 
