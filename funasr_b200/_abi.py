@@ -80,6 +80,7 @@ SIGNATURES = {
     "fa_fbank_tables_bytes": (_sz, []),
     "fa_fbank_make_tables": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fa_fbank_lfr_cmvn_tables": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
+    "fa_fbank_short": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "fa_broadcast_rows": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     "fa_ctc_greedy_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "fa_ctc_greedy_forward": (C.c_int, [C.POINTER(FaLinear), _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),

@@ -510,7 +510,74 @@ static int fbank_launch(const float* wav, const int32_t* wav_lens, int batch, in
   return FA_OK;
 }
 
+// Utterances shorter than one 25 ms frame: the reference shrinks the window to the whole utterance (wav_frontend.py:174:
+// frame_length = min(25 ms, len / fs) => window = n samples, ONE frame, FFT size = next power of two of n; kaldi.py:514-647) and the
+// LFR stacking of a single frame is that frame repeated lfr_m times.  One CTA, a direct DFT in fp64 (<= 257 bins x 399 samples):
+// this is an edge case of a few microseconds, kept off the frame-per-warp kernel whose constants assume the 400 / 512 geometry.
+__global__ void __launch_bounds__(256)
+fbank_short_kernel(const float* __restrict__ wav, int n, const float* __restrict__ window, const float* __restrict__ mel, int pad,
+                   const float* __restrict__ cmvn, int lfr_m, float* __restrict__ out) {
+  __shared__ float xs[512], ys[512], pw[257], lm[kMel];
+  __shared__ double red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double part = 0.0;
+  for (int j = tid; j < pad; j += blockDim.x) {
+    const float v = j < n ? wav[j] * 32768.0f : 0.f;
+    xs[j] = v;
+    part += (double)v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  double tot = 0.0;
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float mean = (float)(tot / (double)n);                       // remove_dc_offset kaldi.py:183-186
+  for (int j = tid; j < pad; j += blockDim.x) {
+    float y = 0.f;
+    if (j < n) {
+      const float c = __fsub_rn(xs[j], mean), cp = __fsub_rn(xs[j > 0 ? j - 1 : 0], mean);
+      y = __fmul_rn(__fsub_rn(c, __fmul_rn(0.97f, cp)), window[j]);  // pre-emphasis (replicate pad) then window :193-204
+    }
+    ys[j] = y;
+  }
+  __syncthreads();
+  const int bins = pad / 2 + 1;
+  for (int k = tid; k < bins; k += blockDim.x) {
+    double re = 0.0, im = 0.0;
+    for (int j = 0; j < n; ++j) {
+      double sn, cs;
+      sincospi(2.0 * (double)((k * j) % pad) / (double)pad, &sn, &cs);
+      re += (double)ys[j] * cs;
+      im -= (double)ys[j] * sn;
+    }
+    pw[k] = (float)(re * re + im * im);
+  }
+  __syncthreads();
+  for (int j = tid; j < kMel; j += blockDim.x) {
+    const float* row = mel + (size_t)j * bins;
+    float acc = 0.f;
+    for (int k = 0; k < bins; ++k) acc = fmaf(pw[k], row[k], acc);
+    lm[j] = logf(fmaxf(acc, 1.1920929e-07f));
+  }
+  __syncthreads();
+  for (int idx = tid; idx < lfr_m * kMel; idx += blockDim.x) {
+    float v = lm[idx % kMel];
+    if (cmvn != nullptr) v = __fmul_rn(__fadd_rn(v, cmvn[idx]), cmvn[lfr_m * kMel + idx]);
+    out[idx] = v;
+  }
+}
+
 }  // namespace fa
+
+extern "C" int fa_fbank_short(const float* wav, int32_t n_samples, const float* window, const float* mel_banks, int32_t padded_fft,
+                              const float* cmvn, int32_t lfr_m, float* feats_row, fa_stream_t stream) {
+  if (!wav || !window || !mel_banks || !feats_row || n_samples < 2 || n_samples >= fa::kWin || lfr_m < 1 || lfr_m > 16) return FA_ERR_ARG;
+  if (padded_fft < n_samples || padded_fft > 512 || (padded_fft & (padded_fft - 1))) return FA_ERR_ARG;
+  fa::fbank_short_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(wav, n_samples, window, mel_banks, padded_fft, cmvn, lfr_m, feats_row);
+  FA_CHECK_LAUNCH();
+  return FA_OK;
+}
 
 extern "C" size_t fa_fbank_tables_bytes(void) { return (size_t)fa::kTabFloats * sizeof(float); }
 

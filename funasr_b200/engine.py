@@ -41,7 +41,9 @@ def kaldi_mel_banks(n_mels=80, n_fft=512, fs=16000.0, low=20.0, high=0.0) -> tor
 
 
 def num_lfr_frames(n_samples: int, win=400, shift=160, lfr_n=6) -> int:
-    m = 1 + (n_samples - win) // shift if n_samples >= win else 0
+    """LFR rows of an utterance.  Below one 25 ms window the reference shrinks the window to the utterance (wav_frontend.py:174):
+    one frame as long as kaldi.fbank accepts it (window >= 2 samples)."""
+    m = 1 + (n_samples - win) // shift if n_samples >= win else (1 if n_samples >= 2 else 0)
     return (m + lfr_n - 1) // lfr_n
 
 
@@ -59,12 +61,14 @@ class FrontendEngine:
         self.mel = kaldi_mel_banks().to(self.device)
         self.window = torch.hamming_window(400, periodic=False, alpha=0.54, beta=0.46, dtype=torch.float32).to(self.device)
         # per-configuration constants (sparse mel support, twiddles, window), built once on the device
+        self._short_mel = {}
         self.tables = torch.empty(int(self.lib.fa_fbank_tables_bytes()) // 4, dtype=torch.float32, device=self.device)
         st = torch.cuda.current_stream(self.device).cuda_stream
         _abi.check(self.lib.fa_fbank_make_tables(self.mel.data_ptr(), self.window.data_ptr(), self.tables.data_ptr(), st), "fa_fbank_make_tables")
 
-    def __call__(self, wav: torch.Tensor, wav_lens: torch.Tensor, t_max: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """wav [B, Nmax] fp32 on device, wav_lens [B] int32 on device -> feats [B, t_max, 560], feat_lens [B] int32."""
+    def __call__(self, wav: torch.Tensor, wav_lens: torch.Tensor, t_max: int, host_lens=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """wav [B, Nmax] fp32 on device, wav_lens [B] int32 on device -> feats [B, t_max, 560], feat_lens [B] int32.
+        host_lens: the same lengths on the host; needed only when some utterance is shorter than 400 samples."""
         assert wav.is_cuda and wav.dtype == torch.float32 and wav.stride(1) == 1
         B = wav.shape[0]
         feats = torch.empty((B, t_max, self.feat_dim), dtype=torch.float32, device=self.device)
@@ -73,7 +77,26 @@ class FrontendEngine:
         _abi.check(self.lib.fa_fbank_lfr_cmvn_tables(wav.data_ptr(), wav_lens.data_ptr(), B, wav.stride(0), _ptr(self.cmvn),
                                                      self.tables.data_ptr(), self.lfr_m, self.lfr_n, feats.data_ptr(), t_max,
                                                      flens.data_ptr(), t_max, st), "fa_fbank_lfr_cmvn_tables")
+        if host_lens is not None and min(host_lens) < 400:
+            self._short_rows(wav, host_lens, feats, flens, st)
         return feats, flens
+
+    def _short_rows(self, wav, host_lens, feats, flens, st):
+        """Utterances below one 25 ms frame (the batched kernel left their rows empty): one frame over the whole utterance each,
+        like kaldi.fbank(frame_length=len / fs) in wav_frontend.py:171-181."""
+        for b, n in enumerate(host_lens):
+            if n >= 400:
+                continue
+            if n < 2:
+                raise _abi.FunasrB200Error("an utterance needs at least 2 samples (kaldi.fbank asserts 2 <= window_size)")
+            pad = 1 << (n - 1).bit_length()
+            if pad not in self._short_mel:
+                self._short_mel[pad] = kaldi_mel_banks(n_fft=pad).to(self.device)
+            win = torch.hamming_window(n, periodic=False, alpha=0.54, beta=0.46, dtype=torch.float32).to(self.device)
+            _abi.check(self.lib.fa_fbank_short(wav[b].data_ptr(), n, win.data_ptr(), self._short_mel[pad].data_ptr(), pad, _ptr(self.cmvn),
+                                               self.lfr_m, feats[b, 0].data_ptr(), st), "fa_fbank_short")
+        idx = torch.tensor([b for b, n in enumerate(host_lens) if n < 400], dtype=torch.long).to(self.device)
+        flens.index_fill_(0, idx, 1)
 
 
 class _EngineBase:
@@ -609,6 +632,8 @@ class SenseVoiceEngine(_EngineBase):
         _abi.check(self.lib.fa_fbank_lfr_cmvn_tables(wav.data_ptr(), wav_lens.data_ptr(), B, wav.stride(0), _ptr(fe.cmvn), fe.tables.data_ptr(),
                                                      7, 6, x.data_ptr() + 4 * self.cfg.feat_dim * 4, T, flens.data_ptr(),
                                                      t_feat, self._stream()), "fa_fbank_lfr_cmvn_tables")
+        if min(int(n) for n in host_lens) < 400:
+            fe._short_rows(wav, [int(n) for n in host_lens], x[:, 4:], flens, self._stream())
         q = self.query_rows(language_id, textnorm_id)
         _abi.check(self.lib.fa_broadcast_rows(q.data_ptr(), 4, self.cfg.feat_dim, x.data_ptr(), T, B, self._stream()), "fa_broadcast_rows")
         lens = torch.tensor([num_lfr_frames(int(n)) + 4 for n in host_lens], dtype=torch.int32).to(self.device, non_blocking=True)

@@ -111,12 +111,12 @@ class WavFrontendB200(nn.Module):
     def forward(self, input: torch.Tensor, input_lengths, device=None, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
         eng = self.engine(device if device is not None else (input.device if input.is_cuda else None))
         lens = [int(x) for x in (input_lengths.tolist() if torch.is_tensor(input_lengths) else input_lengths)]
-        if min(lens) < 400:
-            raise _abi.FunasrB200Error("utterances shorter than one 25 ms frame (400 samples) are not supported")
+        if min(lens) < 2:
+            raise _abi.FunasrB200Error("an utterance needs at least 2 samples (kaldi.fbank asserts 2 <= window_size)")
         t_max = max(num_lfr_frames(n) for n in lens)
         wav = input.to(eng.device, torch.float32, non_blocking=True).contiguous()
         wl = torch.tensor(lens, dtype=torch.int32).to(eng.device, non_blocking=True)
-        feats, flens = eng(wav, wl, t_max)
+        feats, flens = eng(wav, wl, t_max, host_lens=lens)
         return feats, flens.to(torch.int64)
 
 
@@ -353,8 +353,8 @@ class ParaformerB200(nn.Module):
             if not isinstance(frontend, WavFrontendB200):
                 raise _abi.FunasrB200Error("ParaformerB200 needs frontend='WavFrontendB200' (the fused CUDA frontend)")
             wl = [int(w.numel()) for w in wavs]
-            if min(wl) < 400:
-                raise _abi.FunasrB200Error("utterances shorter than one 25 ms frame (400 samples) are not supported")
+            if min(wl) < 2:
+                raise _abi.FunasrB200Error("an utterance needs at least 2 samples (kaldi.fbank asserts 2 <= window_size)")
             nmax = max(wl)
             # pad_sequence (load_utils.py:412) done on the device: each utterance is copied host->device straight into its
             # row (truly asynchronous when the caller's buffers are pinned), no host-side staging copy
@@ -370,9 +370,9 @@ class ParaformerB200(nn.Module):
                 wav_dev, wl_dev = resample(wav_dev, wl_dev, audio_fs, frontend.fs)
                 _, o_r, n_r, _ = sinc_resample_table(audio_fs, frontend.fs)
                 wl = [-(-n_r * n // o_r) for n in wl]
-                if min(wl) < 400:
-                    raise _abi.FunasrB200Error("utterances shorter than one 25 ms frame (400 samples) are not supported")
-            speech, lens = frontend.engine(device)(wav_dev, wl_dev, max(num_lfr_frames(n) for n in wl))
+                if min(wl) < 2:
+                    raise _abi.FunasrB200Error("an utterance needs at least 2 samples (kaldi.fbank asserts 2 <= window_size)")
+            speech, lens = frontend.engine(device)(wav_dev, wl_dev, max(num_lfr_frames(n) for n in wl), host_lens=wl)
             meta_data["extract_feat"] = f"{time.perf_counter() - t2:0.3f}"
             meta_data["batch_data_time"] = sum(num_lfr_frames(n) for n in wl) * frontend.frame_shift * frontend.lfr_n / 1000
         return speech, lens
@@ -552,8 +552,8 @@ class SenseVoiceSmallB200(nn.Module):
         wavs = _as_wave_list(data_in, fs=frontend.fs, audio_fs=int(kwargs.get("fs", 16000)),
                              **{k: v for k, v in kwargs.items() if k not in ("fs", "audio_fs", "frontend")})
         wl = [int(w.numel()) for w in wavs]
-        if min(wl) < 400:
-            raise _abi.FunasrB200Error("utterances shorter than one 25 ms frame (400 samples) are not supported")
+        if min(wl) < 2:
+            raise _abi.FunasrB200Error("an utterance needs at least 2 samples (kaldi.fbank asserts 2 <= window_size)")
         nmax = max(wl)
         wav_dev = (torch.zeros if min(wl) != nmax else torch.empty)((len(wavs), nmax), dtype=torch.float32, device=device)
         for i, w in enumerate(wavs):

@@ -168,6 +168,13 @@ int fa_fbank_make_tables(const float* mel_banks, const float* window, float* tab
 int fa_fbank_lfr_cmvn_tables(const float* wav, const int32_t* wav_lens, int32_t batch, int64_t wav_stride, const float* cmvn,
                              const float* tables, int32_t lfr_m, int32_t lfr_n, float* feats, int64_t feats_batch_stride_rows,
                              int32_t* feat_lens, int32_t t_max, fa_stream_t stream);
+/* One utterance shorter than a 25 ms frame (2 <= n_samples < 400): WavFrontend.forward passes frame_length = min(25 ms, len / fs)
+ * (funasr/frontends/wav_frontend.py:174), so kaldi.fbank uses the whole utterance as ONE window of n_samples (hamming, `window`),
+ * zero-padded to padded_fft = the next power of two, with mel_banks [80, padded_fft / 2 + 1] built for that FFT size; the single
+ * log-mel frame is repeated lfr_m times and CMVN'd into feats_row [80 * lfr_m].  (The batched kernels above give such rows
+ * feat_lens = 0.) */
+int fa_fbank_short(const float* wav, int32_t n_samples, const float* window, const float* mel_banks, int32_t padded_fft,
+                   const float* cmvn, int32_t lfr_m, float* feats_row, fa_stream_t stream);
 /* dst[b, r, :] = rows[r, :] for r < n_rows (dst rows of `cols` floats, utterances dst_batch_stride_rows apart):
  * the query-frame prepend `torch.cat((input_query, speech), dim=1)` of sense_voice/model.py:985-995. */
 int fa_broadcast_rows(const float* rows, int32_t n_rows, int32_t cols, float* dst, int64_t dst_batch_stride_rows,

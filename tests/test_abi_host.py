@@ -91,10 +91,17 @@ def test_cmvn_file_parse():
 
 
 def test_frame_count_and_mel_banks():
-    assert num_lfr_frames(480000) == 500 and num_lfr_frames(80000) == 83 and num_lfr_frames(400) == 1 and num_lfr_frames(399) == 0
+    assert num_lfr_frames(480000) == 500 and num_lfr_frames(80000) == 83 and num_lfr_frames(400) == 1
+    # below one 25 ms window the reference shrinks the window to the utterance: still one frame, down to 2 samples (wav_frontend.py:174)
+    assert num_lfr_frames(399) == 1 and num_lfr_frames(2) == 1 and num_lfr_frames(1) == 0
     import paraformer_oracle as O
     banks = torch.nn.functional.pad(O.get_mel_banks(), (0, 1))
     assert torch.equal(kaldi_mel_banks(), banks.float())
+    for nfft in (256, 128, 32, 2):                                  # the FFT sizes of sub-frame utterances
+        assert torch.equal(kaldi_mel_banks(n_fft=nfft), torch.nn.functional.pad(O.get_mel_banks(80, nfft, 16000.0), (0, 1)).float())
+    for n in (399, 200, 17, 2):                                     # oracle frontend row count for such inputs
+        f_, l_ = O.frontend([synth.make_wav(n, 3)], None)
+        assert l_.tolist() == [1] and f_.shape == (1, 1, 560)
     assert torch.equal(synth.sinusoid_inv_timescales(560), torch.exp(torch.arange(280.0) * -(torch.log(torch.tensor([10000.0])) / 279)))
 
 

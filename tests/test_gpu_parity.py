@@ -1119,3 +1119,41 @@ def test_ct_transformer_vs_reference_golden(name):
     res, _ = m.inference([str(g["text_in"])], key=["k"], tokenizer=Tok(), device=DEV)
     assert res[0]["text"] == str(g["text_out"])
     assert res[0]["punc_array"].tolist() == g["punc_array"].tolist()
+
+
+def test_utterances_shorter_than_one_frame_follow_the_reference_window_rule():
+    """2 <= n < 400 samples: WavFrontend.forward passes frame_length = min(25 ms, len / fs) (wav_frontend.py:174), i.e. ONE window over
+    the whole utterance, FFT size = next power of two.  The GPU frontend (fa_fbank_short beside the batched kernel) against the oracle's
+    restatement of exactly that call — and against torchaudio's kaldi.fbank itself when it is importable — in a batch that mixes short
+    and ordinary utterances; feat_lens = 1 for the short ones."""
+    from funasr_b200 import synth
+    from funasr_b200.engine import FrontendEngine, num_lfr_frames
+    cfg = synth.PARAFORMER_TINY
+    cmvn = synth.make_cmvn(cfg, 1)
+    lens = [399, 3200, 256, 255, 100, 17, 2, 400]
+    wavs = [synth.make_wav(n, 10 + i) for i, n in enumerate(lens)]
+    ref_feats, ref_lens = O.frontend(wavs, cmvn)
+    assert ref_lens.tolist() == [num_lfr_frames(n) for n in lens] == [1, 3, 1, 1, 1, 1, 1, 1]
+    fe = FrontendEngine(cmvn, DEV)
+    pad = torch.nn.utils.rnn.pad_sequence(wavs, batch_first=True).to(DEV)
+    feats, fl = fe(pad, torch.tensor(lens, dtype=torch.int32, device=DEV), max(num_lfr_frames(n) for n in lens), host_lens=lens)
+    torch.cuda.synchronize()
+    assert fl.tolist() == ref_lens.tolist()
+    for b, n in enumerate(lens):
+        t = int(ref_lens[b])
+        got, want = feats[b, :t].cpu().numpy(), ref_feats[b, :t].numpy()
+        # log-mel of near-empty bins sits on the transform's rounding floor (DESIGN.md §2): absolute 2e-3 there, 3e-5 relative elsewhere
+        assert np.abs(got - want).max() <= 3e-5 * np.abs(want).max() + 2e-3, (n, np.abs(got - want).max())
+        assert (feats[b, t:] == 0).all()
+    try:
+        import torchaudio.compliance.kaldi as K
+    except Exception:
+        return
+    for b, n in enumerate(lens):
+        if n >= 400:
+            continue
+        m = K.fbank(wavs[b][None] * 32768.0, num_mel_bins=80, frame_length=min(25, torch.tensor(n) / 16000 * 1000), frame_shift=10, dither=0.0,
+                    energy_floor=0.0, window_type="hamming", sample_frequency=16000, snip_edges=True)
+        want = ((m.repeat(1, 7) + cmvn[0]) * cmvn[1]).numpy()
+        got = feats[b, :1].cpu().numpy()
+        assert np.abs(got - want).max() <= 3e-5 * np.abs(want).max() + 2e-3, (n, np.abs(got - want).max())

@@ -44,7 +44,8 @@ def test_bucketing_respects_caps_and_covers_everything(ns, max_batch, max_frames
 
 @given(st.integers(min_value=0, max_value=16000 * 600))
 def test_frame_arithmetic_matches_the_reference_formulas(n):
-    m = 1 + (n - 400) // 160 if n >= 400 else 0                      # kaldi.py _get_strided, snip_edges
+    win = min(400, n)                                                # wav_frontend.py:174: frame_length = min(25 ms, len / fs)
+    m = 1 + (n - win) // 160 if n >= 2 else 0                        # kaldi.py _get_strided, snip_edges (window_size >= 2 asserted)
     t = int(np.ceil(m / 6))                                          # wav_frontend.py:73
     assert num_lfr_frames(n) == t
 
