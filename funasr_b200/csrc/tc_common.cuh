@@ -122,10 +122,11 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 // ------------------------------------------------------------------------------------------------ operand planes
 // A 16-bit "plane" element of the split x = p0 + p1 (+ p2).  Planes are IEEE fp16 (11-bit significands): two planes carry ~22
 // bits of x, so the three products hi*hi + hi*lo + lo*hi of the x3 mode are good to ~2^-22 relative — 64x tighter than the same
-// three products on fp16 planes (8-bit significands, ~2^-16), at the same tcgen05 kind::f16 rate.  Round 1 used fp16 planes; the
-// B=64 full-depth parity run of round 2 showed their noise (log-prob error up to 9e-3 absolute) flipping ~1 greedy id per 1000
-// tokens at near-ties, while every GEMM operand of this path is LayerNorm-, ReLU- or softmax-bounded and sits far inside the fp16
-// range (conversions saturate at +-65504 instead of producing inf; values below 2^-14 go subnormal with 6e-8 absolute spacing).
+// three products on bf16 planes (8-bit significands, ~2^-16), at the same tcgen05 kind::f16 rate.  Round 1 used bf16 planes; the
+// B=64 full-depth parity run of round 2 showed log-prob errors up to 9e-3 absolute and ~1 flipped greedy id per 1000 tokens at
+// near-ties — which turned out to be the accumulator's round-toward-zero (gemm_tc.cu: acc_scale), not the operand precision; the
+// fp16 planes stay because they cost nothing: every GEMM operand of this path is LayerNorm-, ReLU- or softmax-bounded and sits far
+// inside the fp16 range (conversions saturate at +-65504 instead of producing inf; values below 2^-14 go subnormal, 6e-8 spacing).
 typedef __half plane_t;
 __device__ __forceinline__ uint32_t pack_planes2(float e0, float e1) {      // {e0 -> low half, e1 -> high half}, round to nearest, saturating
   uint32_t r;
@@ -146,7 +147,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                             // layout: SWIZZLE_128B               [61,64)
   return d;
 }
-// kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A / B format fp16 (bits 7-9 / 10-12 = 0; fp16 would be 1), both
+// kind::f16 instruction descriptor: D fp32 (bits 4-5 = 1), A / B format fp16 (bits 7-9 / 10-12 = 0; bf16 would be 1), both
 // K-major, shape M x N.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
