@@ -301,3 +301,24 @@ def test_funoffline_client_links_against_the_reference_header(tmp_path):
         assert r.returncode == 0, r.stdout[-2000:]
     r = subprocess.run([exe, str(tmp_path), str(tmp_path / "none.wav")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 1 and "init failed" in r.stdout
+
+
+def test_product_never_touches_the_oracle_or_the_reference_tree():
+    """The oracle is test infrastructure: nothing under funasr_b200/ (Python or native sources) or include/ may import, open, link or
+    name it, nor read /root/reference; missing the CUDA library must raise instead of falling back."""
+    bad = []
+    for base in (os.path.join(ROOT, "funasr_b200"), os.path.join(ROOT, "include"), os.path.join(ROOT, "examples")):
+        for dirpath, _, files in os.walk(base):
+            if "_build" in dirpath or "__pycache__" in dirpath:
+                continue
+            for fn in files:
+                if not fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".c", ".sh")):
+                    continue
+                text = open(os.path.join(dirpath, fn), errors="ignore").read()
+                for needle in ("paraformer_oracle", "vad_oracle", "punc_oracle", "ref_shim", "ref_runner", "import oracle", "from oracle",
+                               "/root/reference", "baseline/_ref", "oracle/"):
+                    if needle in text:
+                        bad.append((os.path.relpath(os.path.join(dirpath, fn), ROOT), needle))
+    assert not bad, bad
+    src = open(os.path.join(ROOT, "funasr_b200", "_abi.py")).read()
+    assert "FunasrB200Error" in src and "LIB_PATH" in src
