@@ -233,9 +233,10 @@ __device__ __forceinline__ void epilogue_fast_f32(const TcParams& p, const int B
 
 // The same for at most ONE residual (every fp32-output GEMM of the model: out-projection + x, FFN w_2 + x): the registers the second
 // residual's pipeline would hold become a 5-deep ring of the first's, so each warp keeps five 16-column chunks (10 KB) of residual
-// rows in flight instead of one.  Measured before the change: out-projection (K = 512) 69 us for 250 tiles on 74 pairs = 17 us per
-// tile against 6-9 us of MMAs — the epilogue moved 256 KB per tile and CTA at 15 GB/s, exactly 16 KB in flight per SM over ~1.5 us
-// of loaded L2 / HBM latency (Little's law), i.e. bound by memory-level parallelism, not by bandwidth.
+// rows in flight instead of one.  Measured: out-projection (K = 512, alone, L2 flushed) 63.9 us with one chunk in flight, 60.6 with
+// three, 57.3 with five, 46.1 WITHOUT its residual stream — so only part of the gap to the 26 us MMA floor was memory-level
+// parallelism; the rest is the L2 -> SM bandwidth the operand tiles (512 KB per tile and CTA for K = 512) and the fp32 rows
+// (256 KB in + out) share: 386 MB in 57 us = 6.8 TB/s (tools/gemm_shapes.py, profiles/r2_gemm_shapes_*.json).
 __device__ __forceinline__ void epilogue_fast_f32_r1(const TcParams& p, const int BN, uint32_t tmem_acc, int64_t row0, int tile_col0, float* stage,
                                                      int lane, int half, uint64_t* full_bar, uint32_t full_phase) {
   const int rr0 = lane >> 2, c4 = (lane & 3) * 4;
