@@ -20,6 +20,32 @@ GOLDEN_CASES = {
 }
 
 
+# (n_samples, wav seed, kind) of tests/golden/knf_fbank.npz — must match oracle/make_knf_golden.py:CASES
+KNF_CASES = [(16000, 31, "speechlike"), (8123, 32, "noise"), (400, 33, "noise"), (559, 34, "noise"), (48000, 35, "speechlike"), (27200, 36, "noise")]
+
+
+def knf_logmel_cases():
+    """-> [(wav fp32 tensor, golden log-mel [frames, 80] of the reference's compiled kaldi-native-fbank, live log-mel or None)].
+    The live column re-runs oracle/_ref/libknf_ref.so when it is present (built here from /root/reference; travels to the GPU box)."""
+    from funasr_b200 import synth
+    import knf_ref
+    g = np.load(os.path.join(GOLDEN, "knf_fbank.npz"))
+    assert g["cases"].tolist() == [[n, s, 0 if k == "speechlike" else 1] for n, s, k in KNF_CASES]
+    have = knf_ref.build()
+    out = []
+    for i, (n, s, k) in enumerate(KNF_CASES):
+        w = synth.make_wav(n, s, k)
+        out.append((w, g["logmel_%d" % i], knf_ref.fbank(w.numpy()) if have else None))
+    return out
+
+
+def knf_bound(ref_logmel, scale=1.0):
+    """|d log-mel| allowed against kaldi-native-fbank: both sides are fp32 FFTs at their rounding floor in near-empty mel bins
+    (its Ooura radix-4 FFT is ~4x noisier there than pocketfft): 4e-5 + 8e-6 * sqrt(E_frame_max / E_bin)."""
+    r = np.asarray(ref_logmel, dtype=np.float64)
+    return scale * (4e-5 + 8e-6 * np.exp(0.5 * (r.max(-1, keepdims=True) - r)))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     # a fresh checkout has no built library (it is git-ignored): build it once (nvcc cross-compiles sm_100a without a GPU)

@@ -315,7 +315,7 @@ def test_product_never_touches_the_oracle_or_the_reference_tree():
                 if not fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".c", ".sh")):
                     continue
                 text = open(os.path.join(dirpath, fn), errors="ignore").read()
-                for needle in ("paraformer_oracle", "vad_oracle", "punc_oracle", "ref_shim", "ref_runner", "import oracle", "from oracle",
+                for needle in ("paraformer_oracle", "vad_oracle", "punc_oracle", "ref_shim", "ref_runner", "knf_ref", "import oracle", "from oracle",
                                "/root/reference", "baseline/_ref", "oracle/"):
                     if needle in text:
                         bad.append((os.path.relpath(os.path.join(dirpath, fn), ROOT), needle))

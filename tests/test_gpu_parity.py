@@ -71,6 +71,23 @@ def test_fbank_lfr_cmvn_vs_oracle(lens, use_cmvn):
         assert float(got[b, n:].abs().max()) == 0.0 if n < got.shape[1] else True   # pad_sequence(0.0)
 
 
+def test_fbank_vs_the_reference_runtimes_compiled_kaldi_native_fbank():
+    """The CUDA frontend against the reference's OTHER Fbank: kaldi-native-fbank compiled from the reference tree
+    (oracle/_ref/libknf_ref.so when it travelled, else its committed outputs tests/golden/knf_fbank.npz), stacked 7/6 by the
+    oracle's LFR.  Frame counts exact; log-mel inside the rounding floor of two different fp32 FFTs (2 x conftest.knf_bound: the oracle alone uses 0.94 of it)."""
+    from conftest import knf_bound, knf_logmel_cases
+    cases = knf_logmel_cases()
+    got, got_len = _run_frontend([w for w, _, _ in cases], None)
+    for b, (w, gold, live) in enumerate(cases):
+        ref = O.apply_lfr(torch.from_numpy(live if live is not None else gold), 7, 6).double().numpy()
+        n = int(got_len[b])
+        assert n == ref.shape[0]
+        g, r = got[b, :n].double().numpy().reshape(n, 7, 80), ref.reshape(n, 7, 80)
+        d = np.abs(g - r)
+        assert (d <= knf_bound(r, 2.0)).all(), float((d / knf_bound(r, 2.0)).max())
+        assert d.mean() <= 2e-5
+
+
 def test_fbank_silence_and_clipping_edges():
     """All-zero audio hits the log floor (log eps); full-scale square wave exercises large magnitudes."""
     z = torch.zeros(3200)

@@ -51,6 +51,22 @@ def test_fbank_matches_pinned_torchaudio():
         assert torch.equal(ref, O.kaldi_fbank(w))
 
 
+def test_fbank_matches_the_reference_runtimes_compiled_kaldi_native_fbank():
+    """Second, independent pin of the Fbank arithmetic: the reference's vendored kaldi-native-fbank, compiled from the reference
+    tree (oracle/knf/Makefile) and driven like its C++ runtime (paraformer.cpp:24-31, :298-312).  Different FFT (Ooura), same
+    definition: frame counts equal, log-mel inside the two FFTs' rounding floor.  Checked against the committed fixture and,
+    when the compiled library is here, against a live run (which must also reproduce the fixture bit for bit)."""
+    from conftest import knf_bound, knf_logmel_cases
+    for w, gold, live in knf_logmel_cases():
+        mine = O.kaldi_fbank(w * (1 << 15)).double().numpy()
+        assert mine.shape == gold.shape                                   # integer: frame count exact
+        d = np.abs(mine - gold.astype(np.float64))
+        assert (d <= knf_bound(mine)).all(), float((d / knf_bound(mine)).max())
+        assert d.mean() <= 2e-5
+        if live is not None:
+            assert np.array_equal(live, gold)
+
+
 def test_lfr_equals_reference_formula():
     """apply_lfr restated as a clamped gather == the reference's pad+as_strided construction (wav_frontend.py:63-86)."""
     def ref_lfr(inputs, m, n):
