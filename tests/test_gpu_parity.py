@@ -192,6 +192,35 @@ def test_fsmn_vs_oracle():
     assert rel_err(out.cpu().numpy(), (res + ref).numpy()) <= 1e-6
 
 
+@pytest.mark.parametrize("B,T,Cn,ld,K,lens", [(3, 150, 512, 1536, 11, [150, 1, 77]), (5, 500, 512, 1536, 11, [500, 83, 0, 499, 321]),
+                                               (2, 64, 128, 128, 21, [64, 9]), (300, 70, 256, 256, 21, None)])
+def test_fsmn_tma_staged_variant_is_bit_identical(B, T, Cn, ld, K, lens):
+    """fa_fsmn_tma (persistent, warp-specialised, cp.async.bulk.tensor ring; utterance edges = the tensor map's zero fill) against the
+    SIMT kernel bit for bit and against the oracle — with and without the fused residual, a strided v view, partial last time tiles,
+    empty / one-frame utterances and more tiles than SMs."""
+    abi, lib = _lib()
+    g = torch.Generator().manual_seed(21)
+    lens = torch.tensor(lens if lens is not None else [int(x) for x in torch.randint(0, T + 1, (B,), generator=g)], dtype=torch.int32)
+    off = ld - Cn
+    src = torch.randn(B, T, ld, generator=g)
+    w = torch.randn(Cn, 1, K, generator=g) * 0.2
+    res = torch.randn(B, T, Cn, generator=g)
+    mask = (torch.arange(T)[None, :] < lens[:, None]).float()[:, :, None]
+    ref = O.fsmn(src[:, :, off:], w, mask)
+    sd, wd, ld_dev, rd = src.to(DEV), w.to(DEV), lens.to(DEV), res.to(DEV)
+    for r in (None, rd):
+        a, b = torch.full((B, T, Cn), 7.0, device=DEV), torch.full((B, T, Cn), -7.0, device=DEV)
+        args = (sd.data_ptr() + off * 4, ld, ld_dev.data_ptr(), B, T, Cn, wd.data_ptr(), K, None if r is None else r.data_ptr(), Cn)
+        abi.check(lib.fa_fsmn(*args, a.data_ptr(), Cn, _st()), "fa_fsmn")
+        abi.check(lib.fa_fsmn_tma(*args, b.data_ptr(), Cn, _st()), "fa_fsmn_tma")
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+        assert rel_err(b.cpu().numpy(), (ref if r is None else res + ref).numpy()) <= 1e-6
+    # unsupported shapes answer with a status code, never a wrong result
+    assert lib.fa_fsmn_tma(sd.data_ptr() + off * 4, ld, ld_dev.data_ptr(), B, T, Cn, wd.data_ptr(), 31, None, 0, a.data_ptr(), Cn, _st()) == -4
+    assert lib.fa_fsmn_tma(sd.data_ptr() + 4, ld, ld_dev.data_ptr(), B, T, Cn, wd.data_ptr(), K, None, 0, a.data_ptr(), Cn, _st()) == -4
+
+
 @pytest.mark.parametrize("tq,tk,lens", [(130, 130, [130, 1, 65]), (37, 211, [211, 64, 129])])
 def test_attention_vs_oracle(tq, tk, lens):
     abi, lib = _lib()
