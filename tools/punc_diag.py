@@ -1,4 +1,4 @@
-"""Stage-by-stage comparison of the CT-Transformer GPU path with the oracle (run by hand on a GPU box: python tests/diag_punc.py)."""
+"""Stage-by-stage comparison of the CT-Transformer GPU path with the oracle (run by hand on a GPU box: python tools/punc_diag.py)."""
 import ctypes as C
 import os
 import sys
