@@ -13,7 +13,8 @@
 //                       3-stage shared-memory ring with cp.async.bulk.tensor (3-D tensor map {channel, time, utterance}: the zero
 //                       padding of the convolution at the utterance edges IS the map's out-of-bounds fill), 8 consumer warps slide
 //                       their windows over shared memory (each v element crosses L2->SM once) and store the result rows coalesced.
-//                       Selected with FA_FSMN_TMA=1 (or called directly through fa_fsmn_tma); see DESIGN.md §6 for the A/B.
+//                       Default wherever its shape rules hold (k = 11 / 21, channels % 128 == 0, t_max >= 64, 16-byte aligned rows);
+//                       FA_FSMN_TMA=0 keeps the SIMT kernel everywhere.  A/B at the encoder shape: 48.1 -> 39.9 us.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cstdlib>
@@ -240,8 +241,12 @@ int fsmn_tma_launch(const float* v, int64_t ldv, const int32_t* lens, int batch,
   return fsmn_tma_launch_k<21>(v, ldv, lens, batch, t_max, channels, w, res, ldr, out, ldo, st);
 }
 
+// default on since the round-2 A/B (48.1 -> 39.9 us at the encoder shape, profiles/r2_fsmn_tma_ab.json); FA_FSMN_TMA=0 = SIMT strips only
+int fsmn_simt_launch(const float* v, int64_t ldv, const int32_t* lens, int batch, int t_max, int channels, const float* w,
+                     int ksize, const float* res, int64_t ldr, float* out, int64_t ldo, cudaStream_t st, int causal);
+
 static bool fsmn_tma_default() {
-  static const bool on = [] { const char* e = getenv("FA_FSMN_TMA"); return e && e[0] == '1'; }();
+  static const bool on = [] { const char* e = getenv("FA_FSMN_TMA"); return !(e && e[0] == '0'); }();
   return on;
 }
 
@@ -251,6 +256,13 @@ int fsmn_launch(const float* v, int64_t ldv, const int32_t* lens, int batch, int
   if (!v || !lens || !w || !out) return FA_ERR_ARG;
   if (!causal && fsmn_tma_default() && t_max >= FT_TT && fsmn_tma_supported(v, ldv, channels, ksize, res, ldr))
     return fsmn_tma_launch(v, ldv, lens, batch, t_max, channels, w, ksize, res, ldr, out, ldo, st);
+  return fsmn_simt_launch(v, ldv, lens, batch, t_max, channels, w, ksize, res, ldr, out, ldo, st, causal);
+}
+
+int fsmn_simt_launch(const float* v, int64_t ldv, const int32_t* lens, int batch, int t_max, int channels, const float* w,
+                     int ksize, const float* res, int64_t ldr, float* out, int64_t ldo, cudaStream_t st, int causal) {
+  if (batch <= 0 || t_max <= 0) return FA_OK;
+  if (!v || !lens || !w || !out) return FA_ERR_ARG;
   dim3 grid((channels + 127) / 128, (t_max + FSMN_TT - 1) / FSMN_TT, batch);
   if (causal) {
     if (ksize != 20) return FA_ERR_UNSUPPORTED;
@@ -274,6 +286,12 @@ extern "C" int fa_fsmn(const float* v, int64_t ldv, const int32_t* lens, int32_t
                        const float* w, int32_t ksize, const float* res, int64_t ld_res, float* out, int64_t ld_out,
                        fa_stream_t stream) {
   return fa::fsmn_launch(v, ldv, lens, batch, t_max, channels, w, ksize, res, ld_res, out, ld_out, (cudaStream_t)stream, 0);
+}
+
+extern "C" int fa_fsmn_simt(const float* v, int64_t ldv, const int32_t* lens, int32_t batch, int32_t t_max, int32_t channels,
+                            const float* w, int32_t ksize, const float* res, int64_t ld_res, float* out, int64_t ld_out,
+                            fa_stream_t stream) {
+  return fa::fsmn_simt_launch(v, ldv, lens, batch, t_max, channels, w, ksize, res, ld_res, out, ld_out, (cudaStream_t)stream, 0);
 }
 
 extern "C" int fa_fsmn_tma(const float* v, int64_t ldv, const int32_t* lens, int32_t batch, int32_t t_max, int32_t channels,

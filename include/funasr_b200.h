@@ -214,10 +214,14 @@ int fa_fsmn(const float* v, int64_t ldv, const int32_t* lens, int32_t batch, int
 /* The same memory block through the TMA-staged, warp-specialised kernel (persistent CTAs, cp.async.bulk.tensor ring of
  * [64 + k - 1] x 128-channel boxes, results bit-identical to fa_fsmn).  FA_ERR_UNSUPPORTED unless ksize is 11 or 21, channels is a
  * multiple of 128 and v / res are 16-byte aligned with pitches that are multiples of 4 floats.  fa_fsmn and the model-level calls
- * take this route when the environment has FA_FSMN_TMA=1. */
+ * take this route by default when the shape allows it and t_max >= 64 (FA_FSMN_TMA=0: SIMT kernel only). */
 int fa_fsmn_tma(const float* v, int64_t ldv, const int32_t* lens, int32_t batch, int32_t t_max, int32_t channels,
                 const float* w, int32_t ksize, const float* res, int64_t ld_res, float* out, int64_t ld_out,
                 fa_stream_t stream);
+/* The SIMT strip kernel for every shape (ksize 11 / 21 / 31, any channel count or alignment): the A/B partner of fa_fsmn_tma. */
+int fa_fsmn_simt(const float* v, int64_t ldv, const int32_t* lens, int32_t batch, int32_t t_max, int32_t channels,
+                 const float* w, int32_t ksize, const float* res, int64_t ld_res, float* out, int64_t ld_out,
+                 fa_stream_t stream);
 
 /* Multi-head scaled-dot attention with key-padding mask: masked_fill(-inf) -> softmax -> masked_fill(0)
  * -> @V, heads merged (attention.py:288-304 self, :760-794 cross).  head_dim is 128.

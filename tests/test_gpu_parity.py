@@ -211,10 +211,12 @@ def test_fsmn_tma_staged_variant_is_bit_identical(B, T, Cn, ld, K, lens):
     for r in (None, rd):
         a, b = torch.full((B, T, Cn), 7.0, device=DEV), torch.full((B, T, Cn), -7.0, device=DEV)
         args = (sd.data_ptr() + off * 4, ld, ld_dev.data_ptr(), B, T, Cn, wd.data_ptr(), K, None if r is None else r.data_ptr(), Cn)
-        abi.check(lib.fa_fsmn(*args, a.data_ptr(), Cn, _st()), "fa_fsmn")
+        d = torch.full((B, T, Cn), 3.0, device=DEV)
+        abi.check(lib.fa_fsmn_simt(*args, a.data_ptr(), Cn, _st()), "fa_fsmn_simt")
         abi.check(lib.fa_fsmn_tma(*args, b.data_ptr(), Cn, _st()), "fa_fsmn_tma")
+        abi.check(lib.fa_fsmn(*args, d.data_ptr(), Cn, _st()), "fa_fsmn")          # the default route (either kernel)
         torch.cuda.synchronize()
-        assert torch.equal(a, b)
+        assert torch.equal(a, b) and torch.equal(a, d)
         assert rel_err(b.cpu().numpy(), (ref if r is None else res + ref).numpy()) <= 1e-6
     # unsupported shapes answer with a status code, never a wrong result
     assert lib.fa_fsmn_tma(sd.data_ptr() + off * 4, ld, ld_dev.data_ptr(), B, T, Cn, wd.data_ptr(), 31, None, 0, a.data_ptr(), Cn, _st()) == -4

@@ -1,5 +1,5 @@
 """A/B of the two FSMN memory-block kernels at the benchmark's encoder shape (B = 64, T = 500, 512 channels, v = the fp32 V columns
-of the QKV buffer, fused residual): the SIMT strip kernel (fa_fsmn) against the TMA-staged warp-specialised one (fa_fsmn_tma).
+of the QKV buffer, fused residual): the SIMT strip kernel (fa_fsmn_simt) against the TMA-staged warp-specialised one (fa_fsmn_tma).
 CUDA events on the launching stream, L2 flushed before every launch (and, second column, back to back without a flush: the state
 the kernel sees in the step, where QKV / the residual stream were just written).  Prints one JSON line."""
 import json
@@ -20,7 +20,7 @@ w = (torch.randn(Cn, 1, K, generator=g) * 0.2).to(dev)
 res = torch.randn(B, T, Cn, generator=g).to(dev)
 lens = torch.full((B,), T, dtype=torch.int32, device=dev)
 out = {"simt": torch.empty(B, T, Cn, device=dev), "tma": torch.empty(B, T, Cn, device=dev)}
-fn = {"simt": lib.fa_fsmn, "tma": lib.fa_fsmn_tma}
+fn = {"simt": lib.fa_fsmn_simt, "tma": lib.fa_fsmn_tma}
 st = torch.cuda.current_stream().cuda_stream
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 algo_bytes = 3 * B * T * Cn * 4
