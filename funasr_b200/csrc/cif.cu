@@ -131,11 +131,18 @@ __device__ float torch_row_sum_f32(const float* __restrict__ x, int n) {
   return f;
 }
 
-// One CTA per utterance, one thread per channel.
+// One CTA per (utterance, group of CIF_CH channels), one thread per channel.
 //   phase 1 (thread 0): alpha' = [alpha, 0], alpha'[len] += tail; token_num = floor(sum alpha'); fp64 prefix
-//                       sums -> fires / remainders / fire ordinals into shared memory.
-//   phase 2 (all threads): channel-wise running sum of alpha'*h' over time, emitting one acoustic frame per fire.
-__global__ void __launch_bounds__(512)
+//                       sums -> fires / remainders / fire ordinals into shared memory (every channel group of an utterance
+//                       repeats this scalar scan — 500 steps, all groups run concurrently; group 0 writes the per-utterance outputs).
+//   phase 2 (all threads): channel-wise running sum of alpha'*h' over time, emitting one acoustic frame per fire.  The sum is a
+//                       sequential fp32 cumsum per channel (the reference's order), so the kernel is bound by the latency of its
+//                       loads, not by bytes: 64 channels per CTA put 8 CTAs on every utterance (512 CTAs at B = 64 instead of 64 —
+//                       round 2 launch list: 189 us for 65 MB with one 512-thread CTA per utterance), and the time loop fetches
+//                       CIF_UNROLL frames ahead of the dependent adds.
+constexpr int CIF_CH = 64;
+constexpr int CIF_UNROLL = 16;
+__global__ void __launch_bounds__(CIF_CH)
 cif_fire_kernel(const float* __restrict__ enc, const float* __restrict__ alpha_rows, const int32_t* __restrict__ lens,
                 int t_max, int d, float tail, float* __restrict__ acoustic, int n_cap, int32_t* __restrict__ token_num,
                 float* __restrict__ alphas_out, float* __restrict__ peaks_out) {
@@ -144,6 +151,7 @@ cif_fire_kernel(const float* __restrict__ enc, const float* __restrict__ alpha_r
   float* s_rem = sm + (t_max + 1);        // [T+1]
   int* s_ord = reinterpret_cast<int*>(sm + 2 * (t_max + 1));  // [T+1] fire ordinal or -1
   const int b = blockIdx.x;
+  const bool first_group = blockIdx.y == 0;
   const int T1 = t_max + 1;
   const int len = min(lens[b], t_max);
   for (int t = threadIdx.x; t < T1; t += blockDim.x) {
@@ -170,25 +178,40 @@ cif_fire_kernel(const float* __restrict__ enc, const float* __restrict__ alpha_r
       const float fires = __fsub_rn(__fadd_rn(fire ? 1.f : 0.f, psf), fl);   // :846-847
       s_rem[t] = __fsub_rn(fires, floorf(fires));   // :889
       s_ord[t] = fire ? ord++ : -1;
-      peaks_out[(int64_t)b * T1 + t] = fires;
-      alphas_out[(int64_t)b * T1 + t] = s_alpha[t];
+      if (first_group) {
+        peaks_out[(int64_t)b * T1 + t] = fires;
+        alphas_out[(int64_t)b * T1 + t] = s_alpha[t];
+      }
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) token_num[b] = (int32_t)floorf(s_total);     // floor(alphas.sum(-1)) (:443-444), torch's own summation order
+  if (threadIdx.x == 0 && first_group) token_num[b] = (int32_t)floorf(s_total);   // floor(alphas.sum(-1)) (:443-444), torch's own summation order
   const float* hb = enc + (int64_t)b * t_max * d;
   float* ob = acoustic + (int64_t)b * n_cap * d;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+  const int c = blockIdx.y * CIF_CH + threadIdx.x;
+  if (c < d) {
     float acc = 0.f, prev_acc = 0.f, prev_rh = 0.f;
-    for (int t = 0; t < T1; ++t) {
-      const float h = t < t_max ? __ldg(hb + (int64_t)t * d + c) : 0.f;   // hidden gets one zero frame appended (:441-442)
-      acc = __fadd_rn(acc, __fmul_rn(s_alpha[t], h));                     // cumsum(alphas * hidden) :878
-      const int k = s_ord[t];
-      if (k >= 0) {
-        const float rh = __fmul_rn(s_rem[t], h);
-        if (k < n_cap) ob[(int64_t)k * d + c] = __fsub_rn(__fadd_rn(__fsub_rn(acc, prev_acc), prev_rh), rh);   // :896
-        prev_acc = acc;
-        prev_rh = rh;
+    for (int t0 = 0; t0 < T1; t0 += CIF_UNROLL) {
+      float hh[CIF_UNROLL];
+#pragma unroll
+      for (int u = 0; u < CIF_UNROLL; ++u) {                              // the loads of CIF_UNROLL frames go out before the first dependent add
+        const int t = t0 + u;
+        hh[u] = t < t_max ? __ldg(hb + (int64_t)t * d + c) : 0.f;         // hidden gets one zero frame appended (:441-442)
+      }
+#pragma unroll
+      for (int u = 0; u < CIF_UNROLL; ++u) {
+        const int t = t0 + u;
+        if (t < T1) {
+          const float h = hh[u];
+          acc = __fadd_rn(acc, __fmul_rn(s_alpha[t], h));                 // cumsum(alphas * hidden) :878
+          const int k = s_ord[t];
+          if (k >= 0) {
+            const float rh = __fmul_rn(s_rem[t], h);
+            if (k < n_cap) ob[(int64_t)k * d + c] = __fsub_rn(__fadd_rn(__fsub_rn(acc, prev_acc), prev_rh), rh);   // :896
+            prev_acc = acc;
+            prev_rh = rh;
+          }
+        }
       }
     }
   }
@@ -318,7 +341,8 @@ int cif_fire_launch(const float* enc, const float* alpha_rows, const int32_t* le
   const size_t smem = (size_t)3 * (t_max + 1) * sizeof(float);
   if (smem > 200 * 1024) return FA_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) FA_CUDA_OK(cudaFuncSetAttribute(cif_fire_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cif_fire_kernel<<<batch, 512, smem, st>>>(enc, alpha_rows, lens, t_max, d, tail, acoustic, n_cap, token_num, alphas, peaks);
+  cif_fire_kernel<<<dim3(batch, (d + CIF_CH - 1) / CIF_CH), CIF_CH, smem, st>>>(enc, alpha_rows, lens, t_max, d, tail, acoustic, n_cap, token_num,
+                                                                                alphas, peaks);
   FA_CHECK_LAUNCH();
   return FA_OK;
 }
