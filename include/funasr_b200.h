@@ -207,7 +207,8 @@ int fa_linear_planes_to_planes(const void* a_planes, int64_t rows, const FaLinea
                                int64_t ld_out, int32_t gemm_mode, fa_stream_t stream);
 
 /* FSMN memory block: out = m * (v*m + dwconv_k(v*m)) (+ res); m[t] = t < lens[b]
- * (MultiHeadedAttentionSANM.forward_fsmn attention.py:216-239; decoder variant :583-631). */
+ * (MultiHeadedAttentionSANM.forward_fsmn attention.py:216-239; decoder variant :583-631).  out must not overlap v or res (the staged
+ * kernel reads whole tiles ahead of its stores). */
 int fa_fsmn(const float* v, int64_t ldv, const int32_t* lens, int32_t batch, int32_t t_max, int32_t channels,
             const float* w, int32_t ksize, const float* res, int64_t ld_res, float* out, int64_t ld_out,
             fa_stream_t stream);
