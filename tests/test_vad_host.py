@@ -77,3 +77,38 @@ def test_merge_vad_matches_reference_function():
         for _ in range(50):
             t = np.sort(g.integers(0, 200000, size=2 * int(g.integers(1, 12)))).reshape(-1, 2).tolist()
             assert vad.merge_vad([list(x) for x in t], 15000) == ref_merge([list(x) for x in t], 15000)
+
+
+def _flat_decibels(n_samples):
+    """Frame energies of make_vad_cpp_golden.flat_wave: every 400-sample frame holds 400 x 0.05^2."""
+    frames = vad.num_frames(n_samples)
+    return [10.0 * float(np.log10(np.float32(400 * np.float32(0.05) ** 2) + 1e-6))] * frames
+
+
+def test_detector_matches_the_reference_runtimes_compiled_cpp_detector():
+    """Second, independent pin of the end-point state machine: the reference's C++ runtime carries its own implementation
+    (runtime/onnxruntime/src/e2e-vad.h, header-only; compiled from the reference tree by oracle/knf/Makefile and called like
+    fsmn-vad.cpp:245-249).  It has no dynamic end-silence schedule, so funasr_b200/vad.py is run with a fixed max_end_silence_time.
+    Checked against the committed outputs of that detector (tests/golden/vad_cpp_detector.npz, oracle/make_vad_cpp_golden.py) and —
+    when the compiled library is present — live on fresh random posteriors (incl. recordings beyond the 60 s chunk / segment limit)
+    and on the Python reference's own scores of the fixed-schedule golden cases."""
+    import knf_ref
+    import make_vad_cpp_golden as mk
+    g = np.load(os.path.join(GOLDEN, "vad_cpp_detector.npz"))
+    for i, (n, mes, thr10) in enumerate(g["meta"].tolist()):
+        sp = (g["sil_prob_%d" % i].astype(np.float32) / 1024).tolist()
+        got = vad.detect_segments(sp, _flat_decibels(n), n, max_end_silence_time=mes, speech_noise_thres=thr10 / 10)
+        assert got == g["segments_%d" % i].tolist(), i
+    if not knf_ref.build():
+        return                                          # no reference tree and no prebuilt library: the fixture above is the check
+    rng = np.random.default_rng(7)
+    for it in range(60):
+        n, sp, wav, mes, thr = mk.random_case(rng, 40.0 if it < 50 else 150.0)
+        want = knf_ref.vad_segments(sp, wav, mes, 60000, thr)
+        db = VO.frame_decibels(torch.from_numpy(wav)).double().tolist()
+        assert vad.detect_segments(sp.tolist(), db, n, max_end_silence_time=mes, speech_noise_thres=thr) == want, it
+    for name in ("vad_fixed800", "vad_short", "vad_silence"):        # the Python reference's scores through the C++ detector
+        seconds, seed, pattern, _ = VAD_CASES[name]
+        gg = _gold(name)
+        wav = synth.make_vad_wav(seconds, seed, pattern).numpy()
+        assert knf_ref.vad_segments(gg["sil_prob"], wav, 800, 60000, 0.6) == gg["segments"].tolist()
