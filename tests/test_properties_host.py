@@ -110,3 +110,19 @@ def test_hotword_list_follows_reference_seg_dict_rules(tmp_path):
         for src in ["Hello 你好 GPU xyz", str(txt)]:
             want = ContextualParaformer.generate_hotwords_list(Dummy(), src, tokenizer=Tok(), frontend=fe)
             assert generate_hotwords_list(src, Tok(), fe, sos=1) == want
+
+
+def test_bench_flop_model_matches_the_survey_figures():
+    """bench.py's roofline numerators are SURVEY.md §8(d)'s algorithmic FLOPs: encoder 183.2 + predictor 0.787 + decoder
+    8.389 + 0.1132 N GFLOP per 30 s utterance (T = 500) = 206 GFLOP at N = 120; SenseVoiceSmall (T = 504) = 272 GFLOP."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert abs(bench.flops_paraformer(500, 0) / 1e9 - (183.2 + 0.787 + 8.389)) < 0.1
+    assert abs((bench.flops_paraformer(500, 1) - bench.flops_paraformer(500, 0)) / 1e9 - 0.1132) < 1e-3
+    assert abs(bench.flops_paraformer(500, 120) / 1e9 - 206.0) < 0.5
+    assert abs(bench.flops_sensevoice(504) / 1e9 - 272.0) < 1.0
+    # every bucket limit is a whole number of 30 s utterances of 500 frames
+    assert all(mf % 500 == 0 and mb >= mf // 500 for mb, mf in bench.BUCKET_LIMITS.values())
