@@ -16,7 +16,7 @@ from .engine import FrontendEngine, ParaformerEngine, SenseVoiceEngine  # noqa: 
 from .synth import SENSEVOICE_SMALL, SENSEVOICE_TINY, SenseVoiceConfig  # noqa: F401
 from .sharding import shard_utterances, gather_token_ids, ShardedRunner  # noqa: F401
 from .batching import bucket_by_length, padding_efficiency, run_bucketed  # noqa: F401
-from .vad import VadOptions, detect_segments, merge_vad  # noqa: F401
+from .vad import VadOptions, detect_segments, detect_segments_native, merge_vad  # noqa: F401
 from .vad_model import FSMNB200, FsmnVADStreamingB200, VadEngine, WavFrontendOnlineB200  # noqa: F401
 from .long_audio import LongAudioPipeline, merge_results, pack_segments  # noqa: F401
 from .punc import CTTransformerB200, PuncEngine, split_to_mini_sentence, split_words  # noqa: F401

@@ -68,6 +68,14 @@ class FaVadEncoder(C.Structure):
                 ("out1", FaLinear), ("out2", FaLinear), ("sil_ids", C.c_int32 * 4), ("n_sil", C.c_int32), ("_pad", C.c_int32)]
 
 
+class FaVadOptions(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("sample_rate", "detect_mode", "max_end_silence_time", "max_start_silence_time", "window_size_ms",
+                                         "sil_to_speech_time_thres", "speech_to_sil_time_thres", "do_extend", "lookback_time_start_point",
+                                         "lookahead_time_end_point", "max_single_segment_time", "noise_frame_num_used_for_snr", "frame_in_ms",
+                                         "frame_length_ms")] + \
+               [(n, C.c_double) for n in ("speech_2_noise_ratio", "snr_thres", "decibel_thres", "speech_noise_thres", "fe_prior_thres")]
+
+
 _vp, _i32, _i64, _sz, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float
 
 # name -> (restype, argtypes); every symbol include/funasr_b200.h declares
@@ -117,6 +125,7 @@ SIGNATURES = {
     "fa_fsmn_vad_workspace_bytes": (_sz, [C.POINTER(FaVadEncoder), _i32]),
     "fa_fsmn_vad_forward": (C.c_int, [C.POINTER(FaVadEncoder), _vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "fa_frame_decibels": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "fa_vad_detect_segments": (_i64, [_vp, _vp, _i64, _i64, C.POINTER(FaVadOptions), _i32, _i32, _vp, _i32, C.c_double, _vp, _i64]),
     "fa_greedy_filter": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fa_split_planes": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "fa_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, _vp]),

@@ -20,6 +20,12 @@ if [ ! -f ../_build/runtime_shim.o ] || [ runtime_shim.cpp -nt ../_build/runtime
   pids="$pids $!"
 fi
 objs="$objs ../_build/runtime_shim.o"
+# host-only C++: the FSMN-VAD end-point detector (fa_vad_detect_segments)
+if [ ! -f ../_build/vad_detector.o ] || [ vad_detector.cpp -nt ../_build/vad_detector.o ] || [ ../../include/funasr_b200.h -nt ../_build/vad_detector.o ]; then
+  ( g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c vad_detector.cpp -o ../_build/vad_detector.o 2> ../_build/vad_detector.log || { cat ../_build/vad_detector.log; rm -f ../_build/vad_detector.o; exit 1; } ) &
+  pids="$pids $!"
+fi
+objs="$objs ../_build/vad_detector.o"
 for p in $pids; do wait $p || exit 1; done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libfunasr_b200.so $objs -lcudart
 echo "built $(cd ..; pwd)/libfunasr_b200.so"

@@ -21,7 +21,7 @@ from . import _abi
 from .engine import FrontendEngine
 from .modules import WavFrontendB200, _ParamHolder, _as_wave_list, load_cmvn
 from .registry import register
-from .vad import VadOptions, detect_segments, num_frames
+from .vad import VadOptions, detect_segments_native, num_frames
 
 
 def _pad16(k: int) -> int:
@@ -102,7 +102,9 @@ class VadEngine:
     def segments(self, wav: torch.Tensor, opts: Optional[VadOptions] = None, **kw) -> List[List[int]]:
         sil, db, _ = self.scores(wav)
         both = torch.stack([sil, db]).cpu().numpy() if sil.numel() else np.zeros((2, 0), np.float32)       # one D2H: two floats per frame
-        return detect_segments(both[0].tolist(), both[1].tolist(), int(wav.numel()), opts, **kw)
+        # the sequential end-point walk runs in the library's host code (csrc/vad_detector.cpp); funasr_b200.vad.detect_segments is the
+        # same state machine in Python, kept as the specification (tests hold the two identical)
+        return detect_segments_native(both[0], both[1], int(wav.numel()), opts, **kw)
 
 
 @register("encoder_classes", "FSMNB200")

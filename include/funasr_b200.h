@@ -375,6 +375,22 @@ typedef struct {
 size_t fa_fsmn_vad_workspace_bytes(const FaVadEncoder* enc, int32_t t);
 int fa_fsmn_vad_forward(const FaVadEncoder* enc, const float* feats, int64_t ld_feats, int32_t t, float* sil_prob, float* scores,
                         void* workspace, size_t ws_bytes, fa_stream_t stream);
+/* Host-side end-point detector (no GPU work): the per-frame silence posteriors and frame energies of ONE whole recording ->
+ * [start_ms, end_ms] segments, as FsmnVADStreaming.inference produces them over its 60 s chunks (fsmn_vad_streaming/model.py:
+ * GetFrameState :761-823, WindowDetector :218-320, DetectOneFrame :1158-1302, dynamic end-silence schedule :1003-1067).  The fields
+ * are VADXOptions' (model.py:71-174).  schedule: n_schedule pairs {accumulated-speech limit in ms (< 0 = no limit), end silence in ms},
+ * used when dynamic_silence != 0 (the reference's default when no max_end_silence_time is given); speech_noise_thres: NaN = the
+ * options' value.  Returns the number of segments found (segments receives the first max_segments {start, end} pairs), or a negative
+ * status (FA_ERR_ARG also for posteriors outside (0, 1), where the reference's math.log raises). */
+typedef struct {
+  int32_t sample_rate, detect_mode, max_end_silence_time, max_start_silence_time, window_size_ms, sil_to_speech_time_thres,
+      speech_to_sil_time_thres, do_extend, lookback_time_start_point, lookahead_time_end_point, max_single_segment_time,
+      noise_frame_num_used_for_snr, frame_in_ms, frame_length_ms;
+  double speech_2_noise_ratio, snr_thres, decibel_thres, speech_noise_thres, fe_prior_thres;
+} FaVadOptions;
+int64_t fa_vad_detect_segments(const double* sil_prob, const double* decibel, int64_t frames, int64_t n_samples, const FaVadOptions* opts,
+                               int32_t chunk_ms, int32_t dynamic_silence, const double* schedule, int32_t n_schedule,
+                               double speech_noise_thres, int32_t* segments, int64_t max_segments);
 /* decibel[f] = 10 log10(sum_{j<400} wav[160 f + j]^2 + 1e-6), f < frames (ComputeDecibel, model.py:516-525). */
 int fa_frame_decibels(const float* wav, int64_t n_samples, int32_t frames, float* decibel, fa_stream_t stream);
 

@@ -112,3 +112,38 @@ def test_detector_matches_the_reference_runtimes_compiled_cpp_detector():
         gg = _gold(name)
         wav = synth.make_vad_wav(seconds, seed, pattern).numpy()
         assert knf_ref.vad_segments(gg["sil_prob"], wav, 800, 60000, 0.6) == gg["segments"].tolist()
+
+
+@pytest.mark.parametrize("name", list(VAD_CASES))
+def test_native_detector_reproduces_reference_segments(name):
+    """fa_vad_detect_segments (csrc/vad_detector.cpp, the state machine the product runs) on the reference's own scores: the
+    reference's segments, and the same as the Python restatement — fp64 and fp32 inputs (the GPU delivers fp32)."""
+    g = _gold(name)
+    kw = VAD_CASES[name][3]
+    n = int(g["n_samples"])
+    assert vad.detect_segments_native(g["sil_prob"], g["decibel"], n, **kw) == g["segments"].tolist()
+    both = np.stack([g["sil_prob"].astype(np.float32), g["decibel"].astype(np.float32)])
+    assert vad.detect_segments_native(both[0], both[1], n, **kw) == vad.detect_segments(both[0].tolist(), both[1].tolist(), n, **kw)
+
+
+def test_native_detector_equals_the_python_walk_on_random_recordings():
+    """Dynamic and fixed end-silence schedules, explicit thresholds, option changes, recordings past several 60 s chunks, empty input;
+    posteriors outside (0, 1) are an error in both (math.log raises in the reference)."""
+    import make_vad_cpp_golden as mk
+    rng = np.random.default_rng(11)
+    opts = [None, vad.VadOptions(do_extend=0), vad.VadOptions(detect_mode=0, max_start_silence_time=500), vad.VadOptions(max_single_segment_time=5000),
+            vad.VadOptions(window_size_ms=300, sil_to_speech_time_thres=200, speech_to_sil_time_thres=100), vad.VadOptions(decibel_thres=-1.0, snr_thres=-3.0)]
+    for it in range(120):
+        n, sp, wav, mes, thr = mk.random_case(rng, 200.0 if it % 10 == 0 else 30.0)
+        wav = (wav * rng.uniform(0.2, 2.0, size=wav.size).astype(np.float32)) if it % 3 == 0 else wav      # varying frame energies
+        db = VO.frame_decibels(torch.from_numpy(wav)).double().numpy()
+        o = opts[it % len(opts)]
+        for kw in ({}, {"max_end_silence_time": mes, "speech_noise_thres": thr}, {"dynamic_silence": True, "speech_noise_thres": thr},
+                   {"chunk_ms": 20000}):
+            assert vad.detect_segments_native(sp, db, n, o, **kw) == vad.detect_segments(sp.tolist(), db.tolist(), n, o, **kw), (it, kw)
+    assert vad.detect_segments_native(np.zeros(0), np.zeros(0), 300) == [] == vad.detect_segments([], [], 300)
+    from funasr_b200._abi import FunasrB200Error
+    with pytest.raises(FunasrB200Error):
+        vad.detect_segments_native(np.array([0.5, 0.0, 0.5]), np.zeros(3), 400 + 160 * 4)
+    with pytest.raises(ValueError):
+        vad.detect_segments([0.5, 0.0, 0.5], [0.0] * 3, 400 + 160 * 4)
