@@ -427,7 +427,7 @@ class ParaformerB200(nn.Module):
                 text = tokenizer.tokens2text(token)
                 stamp = None
                 if pred_timestamp:                            # model.py:673-680: CIF fires -> [start_ms, end_ms] per token
-                    _, stamp = paraformer_timestamps(peaks_h[i], alphas_h[i], list(token), kwargs.get("begin_time", 0))
+                    _, stamp = paraformer_timestamps(peaks_h[i], alphas_h[i], list(token), kwargs.get("begin_time", 0), want_text=False)
                 if not hasattr(tokenizer, "bpemodel"):
                     try:
                         from funasr.utils import postprocess_utils
@@ -445,7 +445,7 @@ class ParaformerB200(nn.Module):
                 res_i = {"key": key[i], "token_int": token_int}
                 if pred_timestamp:                            # extension: the reference only time-stamps when it has a tokenizer
                     res_i["timestamp"] = paraformer_timestamps(peaks_h[i], alphas_h[i], [str(t) for t in token_int],
-                                                               kwargs.get("begin_time", 0))[1]
+                                                               kwargs.get("begin_time", 0), want_text=False)[1]
                 results.append(res_i)
         return results, meta_data
 
@@ -683,7 +683,8 @@ class BiCifParaformerB200(ParaformerB200):
             ids = out["ids"][i]
             token = tokenizer.ids2tokens(ids) if tokenizer is not None else [str(t) for t in ids]
             n = int(lens[i]) * eng.up_times
-            _, stamp = ts_prediction_lfr6_standard(ua[i][:n], up[i][:n], list(token), vad_offset=kwargs.get("begin_time", 0))   # model.py:402-407
+            _, stamp = ts_prediction_lfr6_standard(ua[i][:n], up[i][:n], list(token), vad_offset=kwargs.get("begin_time", 0),
+                                                   want_text=False)                                                                 # model.py:402-407
             if tokenizer is not None:
                 try:
                     from funasr.utils import postprocess_utils

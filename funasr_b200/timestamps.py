@@ -40,9 +40,11 @@ def _fire_positions(trace: np.ndarray, shift: float) -> np.ndarray:
 
 
 def ts_prediction_lfr6_standard(us_alphas, us_peaks, char_list: Sequence[str], vad_offset: float = 0.0, force_time_shift: float = -1.5,
-                                sil_in_str: bool = True, upsample_rate: int = 3) -> Tuple[str, List[List[int]]]:
+                                sil_in_str: bool = True, upsample_rate: int = 3, want_text: bool = True) -> Tuple[str, List[List[int]]]:
     """Same contract as timestamp_tools.py:37-123 for one utterance: (formatted string, [[start_ms, end_ms] per token]).
-    Inputs are not modified (the reference renormalises its first argument in place, :68)."""
+    Inputs are not modified (the reference renormalises its first argument in place, :68).  want_text=False skips the formatted
+    string (the model classes drop it, model.py:402-407 / :674-680; formatting is half of this routine's host time at 64 utterances
+    per 40 ms GPU step) and returns "" in its place."""
     tokens = list(char_list)
     if not tokens:
         return "", []
@@ -90,13 +92,13 @@ def ts_prediction_lfr6_standard(us_alphas, us_peaks, char_list: Sequence[str], v
     if vad_offset:
         shift_s = vad_offset / 1000.0
         spans = [[lo + shift_s, hi + shift_s] for lo, hi in spans]
-    text = "".join("{} {} {};".format(lab, str(lo + 0.0005)[:5], str(hi + 0.0005)[:5])
-                   for lab, (lo, hi) in zip(labels, spans) if sil_in_str or lab != "<sil>")
+    text = "" if not want_text else "".join("{} {} {};".format(lab, str(lo + 0.0005)[:5], str(hi + 0.0005)[:5])
+                                            for lab, (lo, hi) in zip(labels, spans) if sil_in_str or lab != "<sil>")
     stamps = [[int(lo * 1000), int(hi * 1000)] for lab, (lo, hi) in zip(labels, spans) if lab != "<sil>"]
     return text, stamps
 
 
-def paraformer_timestamps(peaks_row, alphas_row, tokens: Sequence[str], begin_time: float = 0.0) -> Tuple[str, List[List[int]]]:
+def paraformer_timestamps(peaks_row, alphas_row, tokens: Sequence[str], begin_time: float = 0.0, want_text: bool = True) -> Tuple[str, List[List[int]]]:
     """The exact call of paraformer/model.py:674-680: (pre_peak_index[i], alphas[i], tokens, vad_offset=begin_time,
     upsample_rate=1)."""
-    return ts_prediction_lfr6_standard(peaks_row, alphas_row, list(tokens), vad_offset=begin_time, upsample_rate=1)
+    return ts_prediction_lfr6_standard(peaks_row, alphas_row, list(tokens), vad_offset=begin_time, upsample_rate=1, want_text=want_text)

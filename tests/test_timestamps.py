@@ -26,6 +26,9 @@ def test_timestamps_match_reference_golden():
         txt, res = TS.ts_prediction_lfr6_standard(first, second, c["chars"], vad_offset=c["vad_offset"], upsample_rate=c["upsample_rate"])
         assert res == c["res"]              # integer milliseconds: exact
         assert txt == c["txt"]
+        # the model classes ask for the stamps only (want_text=False): same stamps, no string
+        assert TS.ts_prediction_lfr6_standard(first, second, c["chars"], vad_offset=c["vad_offset"], upsample_rate=c["upsample_rate"],
+                                              want_text=False) == ("", c["res"])
         n_nonempty += bool(res)
     assert n_nonempty > len(cases) // 2
 
