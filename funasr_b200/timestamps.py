@@ -65,6 +65,8 @@ def ts_prediction_lfr6_standard(us_alphas, us_peaks, char_list: Sequence[str], v
     if fires.size == 0:
         return "", []                      # the reference raises IndexError here (:83); nothing to time-stamp
     n_frames = trace.shape[0]
+    if not want_text:
+        return "", _stamps_only(fires, n_frames, tokens, sec_per_frame, vad_offset)
     labels: List[str] = []
     spans: List[List[float]] = []          # seconds
 
@@ -96,6 +98,34 @@ def ts_prediction_lfr6_standard(us_alphas, us_peaks, char_list: Sequence[str], v
                                             for lab, (lo, hi) in zip(labels, spans) if sil_in_str or lab != "<sil>")
     stamps = [[int(lo * 1000), int(hi * 1000)] for lab, (lo, hi) in zip(labels, spans) if lab != "<sil>"]
     return text, stamps
+
+
+def _stamps_only(fires: np.ndarray, n_frames: int, tokens: Sequence[str], sec_per_frame: float, vad_offset: float) -> List[List[int]]:
+    """The [[start_ms, end_ms]] list of `ts_prediction_lfr6_standard` without building labels / the string: the same double
+    arithmetic element by element (start = lo * sec, end = (lo + 12 or hi) * sec, the trailing-edge rule on the LAST emitted span,
+    + vad_offset / 1000, int(x * 1000)), vectorised over the tokens.  A token cut at MAX_TOKEN_FRAMES is followed by a <sil> span,
+    which then is the last emitted span when it happens to the last token — the trailing-edge rule moves that <sil>, not the token.
+    Spans beyond the token list (label "") are stamps too, a vocabulary entry spelled "<sil>" is dropped like an inserted one."""
+    lo, hi = fires[:-1], fires[1:]
+    n_span = lo.shape[0]
+    if n_span == 0:
+        return []                                               # only edge <sil> spans exist
+    start = lo * sec_per_frame
+    cut = (hi - lo > MAX_TOKEN_FRAMES) if MAX_TOKEN_FRAMES >= 0 else np.zeros(n_span, dtype=bool)
+    end = np.where(cut, lo + MAX_TOKEN_FRAMES, hi) * sec_per_frame
+    if not cut[-1]:                                             # the last emitted span is the last token itself
+        if n_frames - fires[-1] > EDGE_SILENCE_FRAMES:
+            end[-1] = ((n_frames + fires[-1]) * 0.5) * sec_per_frame
+        else:
+            end[-1] = n_frames * sec_per_frame
+    if vad_offset:
+        shift_s = vad_offset / 1000.0
+        start, end = start + shift_s, end + shift_s
+    out = np.stack([start * 1000, end * 1000], axis=1).astype(np.int64)          # int(): truncation toward zero, like astype
+    if "<sil>" in tokens:
+        keep = np.array([not (i < len(tokens) and tokens[i] == "<sil>") for i in range(n_span)], dtype=bool)
+        out = out[keep]
+    return out.tolist()
 
 
 def paraformer_timestamps(peaks_row, alphas_row, tokens: Sequence[str], begin_time: float = 0.0, want_text: bool = True) -> Tuple[str, List[List[int]]]:

@@ -60,3 +60,37 @@ def test_timestamps_against_live_reference_if_available():
             want = ("", [])
         got = TS.paraformer_timestamps(peaks, a, chars)
         assert got[1] == want[1] and got[0] == want[0]
+
+
+def test_stamps_only_path_equals_the_labelled_walk():
+    """want_text=False takes a vectorised route; it must return the labelled walk's stamps in every regime: fire count equal to /
+    above / below the token count (re-integration), tokens cut at 12 frames (incl. the last one), leading / trailing silence or none,
+    a vocabulary entry spelled "<sil>", a VAD offset, upsampled (x3) and plain frames, a single fire, no fire at all."""
+    rng = np.random.default_rng(5)
+    n_checked = n_cut_last = 0
+    for trial in range(600):
+        T = int(rng.integers(4, 400))
+        dens = rng.choice([0.05, 0.15, 0.3, 0.6])
+        a = (rng.random(T).astype(np.float32) * np.float32(2 * dens)).astype(np.float32)
+        if trial % 7 == 0:
+            a[: T // 3] = 0                                      # long leading silence
+        if trial % 5 == 0:
+            a[-(T // 4):] = 0                                    # long trailing silence
+        if trial % 11 == 0:
+            a[T // 2: T // 2 + 20] = 0                           # a gap: the token before it is cut at 12 frames
+        peaks = TS.cif_wo_hidden(a, 1.0)
+        n_fire = int((peaks >= np.float32(1 - 1e-4)).sum())
+        n_tok = max(0, n_fire - 1 + int(rng.integers(-2, 3)))
+        chars = ["c%d" % i for i in range(n_tok)]
+        if chars and trial % 13 == 0:
+            chars[int(rng.integers(0, len(chars)))] = "<sil>"
+        for kw in ({"upsample_rate": 1}, {"upsample_rate": 3, "vad_offset": 12340}, {"upsample_rate": 1, "vad_offset": 250.5}):
+            for first, second in ((peaks, a), (a, peaks)):       # the Paraformer call order and the BiCif one
+                want = TS.ts_prediction_lfr6_standard(first, second, list(chars), **kw)
+                got = TS.ts_prediction_lfr6_standard(first, second, list(chars), want_text=False, **kw)
+                assert got == ("", want[1]), (trial, kw)
+                n_checked += 1
+        tr = peaks
+        fires = np.flatnonzero(tr >= np.float32(1 - 1e-4))
+        n_cut_last += int(fires.size >= 2 and fires[-1] - fires[-2] > 12)
+    assert n_checked == 3600 and n_cut_last > 5
