@@ -26,6 +26,11 @@ if [ ! -f ../_build/vad_detector.o ] || [ vad_detector.cpp -nt ../_build/vad_det
   pids="$pids $!"
 fi
 objs="$objs ../_build/vad_detector.o"
+if [ ! -f ../_build/host_ops.o ] || [ host_ops.cpp -nt ../_build/host_ops.o ] || [ ../../include/funasr_b200.h -nt ../_build/host_ops.o ]; then
+  ( g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c host_ops.cpp -o ../_build/host_ops.o 2> ../_build/host_ops.log || { cat ../_build/host_ops.log; rm -f ../_build/host_ops.o; exit 1; } ) &
+  pids="$pids $!"
+fi
+objs="$objs ../_build/host_ops.o"
 for p in $pids; do wait $p || exit 1; done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../libfunasr_b200.so $objs -lcudart
 echo "built $(cd ..; pwd)/libfunasr_b200.so"

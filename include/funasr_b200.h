@@ -391,6 +391,10 @@ typedef struct {
 int64_t fa_vad_detect_segments(const double* sil_prob, const double* decibel, int64_t frames, int64_t n_samples, const FaVadOptions* opts,
                                int32_t chunk_ms, int32_t dynamic_silence, const double* schedule, int32_t n_schedule,
                                double speech_noise_thres, int32_t* segments, int64_t max_segments);
+/* Host only: the integrate-and-fire trace of one utterance's weights, funasr/utils/timestamp_tools.py:14-34 (cif_wo_hidden: fp32 running
+ * sum, reduced by `threshold` after every frame that reaches it; trace[t] = the value before the reduction) — the re-integration step of
+ * ts_prediction_lfr6_standard (:67-72). */
+int fa_cif_wo_hidden_host(const float* alphas, int64_t n, float threshold, float* trace);
 /* decibel[f] = 10 log10(sum_{j<400} wav[160 f + j]^2 + 1e-6), f < frames (ComputeDecibel, model.py:516-525). */
 int fa_frame_decibels(const float* wav, int64_t n_samples, int32_t frames, float* decibel, fa_stream_t stream);
 

@@ -77,7 +77,10 @@ def test_state_dict_names_match_reference_layout():
 
 
 def test_registry_surface():
-    t = funasr_b200.get_tables()
+    # install() = the documented step after `import funasr` (another test of this session may have imported the live reference after
+    # funasr_b200, which switches get_tables() to the reference's own tables); without funasr it returns the local tables unchanged
+    t = funasr_b200.install()
+    assert t is funasr_b200.get_tables()
     for table, key in [("model_classes", "ParaformerB200"), ("frontend_classes", "WavFrontendB200"),
                        ("encoder_classes", "SANMEncoderB200"), ("predictor_classes", "CifPredictorV2B200"),
                        ("decoder_classes", "ParaformerSANMDecoderB200")]:

@@ -94,3 +94,16 @@ def test_stamps_only_path_equals_the_labelled_walk():
         fires = np.flatnonzero(tr >= np.float32(1 - 1e-4))
         n_cut_last += int(fires.size >= 2 and fires[-1] - fires[-2] > 12)
     assert n_checked == 3600 and n_cut_last > 5
+
+
+def test_native_cif_wo_hidden_equals_the_python_loop_bit_for_bit():
+    """fa_cif_wo_hidden_host (the library's host code) against the numpy-scalar loop it replaces: identical fp32 traces."""
+    rng = np.random.default_rng(9)
+    for trial in range(500):
+        n = int(rng.integers(0, 600))
+        a = (rng.random(n) ** int(rng.choice([1, 2, 3])) * float(rng.choice([0.3, 1.0, 2.5]))).astype(np.float32)
+        for thr in (1.0, 1.0 - 1e-4, 0.5):
+            assert np.array_equal(TS.cif_wo_hidden(a, thr), TS.cif_wo_hidden_py(a, thr))
+    assert TS.cif_wo_hidden(np.zeros(0, np.float32), 1.0).shape == (0,)
+    nan = TS.cif_wo_hidden(np.array([0.5, np.nan, 0.7], np.float32), 1.0)
+    assert nan[0] == np.float32(0.5) and np.isnan(nan[1:]).all()
