@@ -107,3 +107,19 @@ def test_native_cif_wo_hidden_equals_the_python_loop_bit_for_bit():
     assert TS.cif_wo_hidden(np.zeros(0, np.float32), 1.0).shape == (0,)
     nan = TS.cif_wo_hidden(np.array([0.5, np.nan, 0.7], np.float32), 1.0)
     assert nan[0] == np.float32(0.5) and np.isnan(nan[1:]).all()
+
+
+@pytest.mark.parametrize("name", ["bicif_large_single", "bicif_tiny_ragged3"])
+def test_model_class_route_reproduces_the_bicif_golden_timestamps(name):
+    """The route BiCifParaformerB200.inference takes on the host (stamps only, native re-integration) over the REFERENCE's own
+    upsampled weights / fires: the reference's timestamps (bicif_paraformer/model.py:402-407), integer milliseconds exact."""
+    from conftest import gold_stamps
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    want, pos = gold_stamps(d), 0
+    for b in range(d["us_alphas"].shape[0]):
+        k = int(d["ids_len"][b])
+        ids = d["ids_flat"][pos: pos + k]
+        pos += k
+        n = int(d["enc_lens"][b]) * 3
+        got = TS.ts_prediction_lfr6_standard(d["us_alphas"][b][:n], d["us_peaks"][b][:n], [str(t) for t in ids], want_text=False)
+        assert got == ("", want[b])
