@@ -15,8 +15,9 @@ overlaps the next job's kernels.  Prints ONE JSON line (rank 0).
 
 `value` times the job with the waveforms already resident in HBM; `e2e` times the same job through the plugin call
 (ParaformerB200.inference / infer_ids_device) with HOST (pinned) waveforms in and token ids on the host out, copies inside the
-timed region.  `parity` compares the ids of the TIMED job (and the log-probabilities of an untimed taps pass over the same
-utterances) with the CPU oracle's output for a bounded sample, computed by the CPU leg of the same run.
+timed region.  `parity` compares the ids of the TIMED job (and the log-probabilities and stage taps — features, encoder output, CIF
+weights, acoustic embeddings — of an untimed taps pass over the same utterances) with the CPU oracle's output for a bounded sample,
+computed by the CPU leg of the same run.
 `--impl reference` times the unmodified reference on the host cores (AutoModel(device="cpu").generate() from the offline
 install under baseline/_ref, kind "reference"; the CPU restatement oracle/, kind "port", when that cannot be imported).
 """
@@ -448,6 +449,9 @@ def run_reference(args):
             dump["valid_len"] = (o["token_num"] if "token_num" in o else o["enc_lens"]).numpy().astype(np.int64)
         if "token_num" in o:
             dump["token_num"] = o["token_num"].numpy()
+        for k, step in TAP_STRIDES.items():                 # stage taps: subsampled along time to keep the file small
+            if k in o and o[k] is not None:
+                dump["tap_" + k] = o[k][:, ::step].numpy() if step > 1 else o[k].numpy()
         if isinstance(ref_ids, list) and ref_ids and isinstance(ref_ids[0], list):
             dump["ref_equals_oracle"] = np.int64(int([list(map(int, r)) for r in ref_ids] == [list(map(int, r)) for r in o["ids"]]))
         np.savez(args.parity_out, **dump)
@@ -473,6 +477,37 @@ def cpu_baseline(config, parity_path, time_cap_s=420):
         return {"error": "reference leg printed no JSON (rc=%d)" % r.returncode}
     except subprocess.TimeoutExpired:
         return {"error": "CPU leg exceeded %d s" % time_cap_s}
+
+
+# stage taps compared in the parity block: oracle tensor -> stride along the time / token axis
+TAP_STRIDES = {"feats": 7, "enc": 7, "alphas": 1, "acoustic": 5}
+TAP_BARS = {"feats": ("mean_abs", 2e-5), "enc": ("rel", 1e-3), "alphas": ("max_abs", 1e-4), "acoustic": ("rel", 1e-3)}
+
+
+def compare_taps(dump, got):
+    """Stage taps of the GPU path (dict of tensors: feats [b,T,560], enc [b,T,512], alphas [b,T+1], acoustic [b,>=n,512]) against the
+    oracle's (`tap_*` arrays of the parity dump, subsampled by TAP_STRIDES) -> {name: {max_abs, mean_abs, rel, within}} with the bars the
+    GPU parity tests use (tests/test_gpu_parity.py: log-mel mean 2e-5, encoder / acoustic 1e-3 relative, alpha 1e-4 absolute)."""
+    out = {}
+    for k, step in TAP_STRIDES.items():
+        if "tap_" + k not in dump or k not in got or got[k] is None:
+            continue
+        ref = np.asarray(dump["tap_" + k], dtype=np.float64)
+        g = got[k].detach().float().cpu().numpy().astype(np.float64)
+        if k == "acoustic":
+            g = g[:, : int(np.asarray(dump["token_num"]).max())] if "token_num" in dump else g
+        g = g[:, ::step] if step > 1 else g
+        if g.shape != ref.shape:
+            out[k] = {"error": "shape %s vs oracle %s" % (list(g.shape), list(ref.shape))}
+            continue
+        d = np.abs(g - ref)
+        r = {"max_abs": float(d.max()) if d.size else 0.0, "mean_abs": float(d.mean()) if d.size else 0.0,
+             "rel": float(d.max() / max(float(np.abs(ref).max()), 1e-30)) if d.size else 0.0}
+        kind, bar = TAP_BARS[k]
+        r["bar"] = "%s <= %g" % (kind, bar)
+        r["within"] = bool(r[kind] <= bar)
+        out[k] = r
+    return out
 
 
 def parity_block(job, parity_path, last_ids):
@@ -506,6 +541,11 @@ def parity_block(job, parity_path, last_ids):
             lp = o["logp"][:, rows, :].cpu().numpy()
             if "token_num" in d:
                 out["token_num_equal"] = o["token_num"].tolist() == d["token_num"].tolist()
+        if job.config != 4:
+            try:
+                out["taps"] = compare_taps(d, {"feats": feats, "enc": o.get("enc"), "alphas": o.get("alphas"), "acoustic": o.get("acoustic")})
+            except Exception as e:  # pragma: no cover
+                out["taps"] = {"error": repr(e)[:200]}
         ref = d["logp_sel"]
         out["logp_rel_err"] = float(np.abs(lp.astype(np.float64) - ref).max() / max(float(np.abs(ref).max()), 1e-30))
         out["logp_tolerance"] = 1e-3

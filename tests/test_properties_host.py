@@ -126,3 +126,31 @@ def test_bench_flop_model_matches_the_survey_figures():
     assert abs(bench.flops_sensevoice(504) / 1e9 - 272.0) < 1.0
     # every bucket limit is a whole number of 30 s utterances of 500 frames
     assert all(mf % 500 == 0 and mb >= mf // 500 for mb, mf in bench.BUCKET_LIMITS.values())
+
+
+def test_bench_stage_tap_comparison():
+    """bench.py's parity block also compares the stage taps: the GPU tensors are subsampled like the oracle's dump,
+    the acoustic rows cut at the largest token count, bars as in the GPU parity tests; missing taps (config 5 has no feats / alphas in
+    its oracle output) are skipped, a shape disagreement is reported instead of raised."""
+    import importlib.util
+    import os
+    import torch
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    g = torch.Generator().manual_seed(0)
+    full = {"feats": torch.randn(2, 50, 560, generator=g), "enc": torch.randn(2, 50, 512, generator=g), "alphas": torch.rand(2, 51, generator=g),
+            "acoustic": torch.randn(2, 17, 512, generator=g)}
+    dump = {"tap_" + k: (v[:, ::bench.TAP_STRIDES[k]] if bench.TAP_STRIDES[k] > 1 else v).numpy() for k, v in full.items()}
+    dump["token_num"] = np.array([17, 9])
+    got = dict(full)
+    got["acoustic"] = torch.cat([full["acoustic"], torch.zeros(2, 34, 512)], 1)            # the device buffer is [B, T + 1, 512]
+    r = bench.compare_taps(dump, got)
+    assert set(r) == {"feats", "enc", "alphas", "acoustic"} and all(v["within"] and v["max_abs"] == 0.0 for v in r.values())
+    got["enc"] = full["enc"] * 1.01
+    got["alphas"] = full["alphas"] + 2e-4
+    r = bench.compare_taps(dump, got)
+    assert not r["enc"]["within"] and not r["alphas"]["within"] and r["feats"]["within"]
+    del dump["tap_feats"], dump["tap_alphas"]
+    assert set(bench.compare_taps(dump, dict(full, acoustic=got["acoustic"]))) == {"enc", "acoustic"}
+    assert "error" in bench.compare_taps(dump, dict(full, enc=full["enc"][:, :40], acoustic=got["acoustic"]))["enc"]
