@@ -36,7 +36,10 @@ bool is_ascii_word(const std::string& s) {
 }
 
 // tokens -> text: word pieces ending in "@@" are glued to the next token, consecutive ASCII words are separated by one space,
-// CJK tokens are concatenated (the behaviour of the runtime's Vocab::Vector2StringV2 for Paraformer's char/word vocabulary)
+// CJK tokens are concatenated.  A plain join in the spirit of the runtime's Vocab::Vector2StringV2 (runtime/onnxruntime/src/vocab.cpp:
+// 164-278) for Paraformer's char / word vocabulary — NOT a restatement of it: that function also drops <s> / </s> / <unk>, keeps
+// runs of single letters unspaced, repairs "xx@@" before a CJK token and has an en-bpe mode.  Text post-processing is CPU string
+// work outside the accelerated path; the ids this shim returns are the parity-checked output.
 std::string join_tokens(const OfflineStream& s, const int32_t* ids, int n) {
   std::string out;
   bool prev_ascii = false, glue = false;
