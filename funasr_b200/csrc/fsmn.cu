@@ -168,13 +168,13 @@ static int make_f32_map3(CUtensorMap* m, const void* base, uint64_t cols, uint64
                          uint32_t box_rows) {
   typedef CUresult (*PFN_enc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static PFN_enc enc = nullptr;
-  if (!enc) {
+  static const PFN_enc enc = []() -> PFN_enc {                     // thread-safe one-time lookup (two handles / two threads share this TU)
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return FA_ERR_CUDA;
-    enc = reinterpret_cast<PFN_enc>(p);
-  }
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<PFN_enc>(p);
+  }();
+  if (!enc) return FA_ERR_CUDA;
   struct Key {
     const void* base; uint64_t cols, rows, batch, ld; uint32_t bc, br;
     bool operator==(const Key& o) const { return base == o.base && cols == o.cols && rows == o.rows && batch == o.batch && ld == o.ld && bc == o.bc && br == o.br; }
