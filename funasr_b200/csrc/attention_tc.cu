@@ -872,8 +872,7 @@ static int launch_att_c(dim3 grid, const CUtensorMap& mq, const CUtensorMap& mk,
 // at CL=1, 215 us at CL=2, 232 us at CL=4) — the kernel is not L2-bandwidth bound and clusters of 4 quantise badly on the
 // 18/20-SM GPCs; the path stays as an opt-in for shapes with many query tiles per (utterance, head).
 static int att_cluster_cap() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FA_ATT_CLUSTER"); v = e ? atoi(e) : 1; if (v != 1 && v != 2 && v != 4) v = 1; }
+  static const int v = [] { const char* e = getenv("FA_ATT_CLUSTER"); const int c = e ? atoi(e) : 1; return (c == 2 || c == 4) ? c : 1; }();
   return v;
 }
 

@@ -915,9 +915,8 @@ static int pick_tail_sub(int tail_tiles, int pairs) {
 }
 
 static bool use_2cta() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FA_GEMM_2CTA"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
+  static const bool on = [] { const char* e = getenv("FA_GEMM_2CTA"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 // A planes already split: a_planes [npl][M][Kp]
