@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include <stdio.h>
 #include <string.h>
+#include <exception>
 #include <map>
 #include <string>
 #include <vector>
@@ -85,13 +86,16 @@ bool load_file(Model& m, const char* path) {
   if (!f) { set_err(std::string("cannot open ") + path); return false; }
   char magic[8];
   uint32_t n = 0;
-  bool ok = read_exact(f, magic, 8) && memcmp(magic, "FAB2MDL1", 8) == 0 && read_exact(f, &n, 4);
+  long fsize = 0;
+  if (fseek(f, 0, SEEK_END) == 0) fsize = ftell(f);
+  rewind(f);
+  bool ok = fsize > 0 && read_exact(f, magic, 8) && memcmp(magic, "FAB2MDL1", 8) == 0 && read_exact(f, &n, 4);
   std::vector<float> host;
   for (uint32_t i = 0; ok && i < n; ++i) {
     uint32_t nl = 0, nd = 0;
     uint64_t nbytes = 0;
     ok = read_exact(f, &nl, 4) && nl < 4096;
-    std::string name(nl, '\0');
+    std::string name(ok ? nl : 0, '\0');
     ok = ok && read_exact(f, &name[0], nl) && read_exact(f, &nd, 4) && nd <= 8;
     Tensor tt;
     tt.shape.resize(nd);
@@ -99,7 +103,8 @@ bool load_file(Model& m, const char* path) {
     if (!ok) break;
     const long pos = ftell(f);
     const long pad = (16 - pos % 16) % 16;
-    ok = fseek(f, pad, SEEK_CUR) == 0 && nbytes == (uint64_t)tt.numel() * 4;
+    ok = fseek(f, pad, SEEK_CUR) == 0 && nbytes == (uint64_t)tt.numel() * 4 &&
+         pos + pad <= fsize && nbytes <= (uint64_t)(fsize - (pos + pad));   // the payload lies inside the file: a corrupt size cannot drive an allocation
     if (!ok) break;
     host.resize(nbytes / 4);
     ok = read_exact(f, host.data(), nbytes);
@@ -240,7 +245,13 @@ extern "C" void* fa_offline_init(const char* model_file, int32_t device, int32_t
   Model* m = new Model();
   m->device = device; m->mode = gemm_mode;
   if (cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); delete m; return nullptr; }
-  if (!load_file(*m, model_file) || !build(*m)) { delete m; return nullptr; }
+  bool ok = false;
+  try {                                   // a malformed file can ask for an absurd allocation: no C++ exception may cross the C ABI
+    ok = load_file(*m, model_file) && build(*m);
+  } catch (const std::exception& e) {
+    set_err(std::string("model file rejected: ") + e.what());
+  }
+  if (!ok) { delete m; return nullptr; }
   return m;
 }
 
