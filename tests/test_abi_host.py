@@ -325,3 +325,53 @@ def test_product_never_touches_the_oracle_or_the_reference_tree():
     assert not bad, bad
     src = open(os.path.join(ROOT, "funasr_b200", "_abi.py")).read()
     assert "FunasrB200Error" in src and "LIB_PATH" in src
+
+
+def test_host_side_entry_points_from_plain_c(tmp_path):
+    """The two host-only routines of the ABI (no GPU needed) called from a C99 program: the integrate-and-fire trace and the VAD
+    end-point walk give the values the Python specifications give."""
+    src = tmp_path / "host_calls.c"
+    src.write_text(r'''
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include "funasr_b200.h"
+int main(void) {
+  const float a[5] = {0.4f, 0.7f, 0.2f, 0.9f, 0.05f};
+  float tr[5];
+  if (fa_cif_wo_hidden_host(a, 5, 1.0f, tr) != FA_OK) return 1;
+  printf("trace %.6f %.6f %.6f %.6f %.6f\n", tr[0], tr[1], tr[2], tr[3], tr[4]);
+  enum { F = 300 };
+  double sil[F], db[F];
+  for (int i = 0; i < F; ++i) { sil[i] = (i >= 60 && i < 200) ? 0.05 : 0.95; db[i] = 0.0; }
+  FaVadOptions o;
+  memset(&o, 0, sizeof o);
+  o.sample_rate = 16000; o.detect_mode = 1; o.max_end_silence_time = 800; o.max_start_silence_time = 3000; o.window_size_ms = 200;
+  o.sil_to_speech_time_thres = 150; o.speech_to_sil_time_thres = 150; o.do_extend = 1; o.lookback_time_start_point = 200;
+  o.lookahead_time_end_point = 100; o.max_single_segment_time = 60000; o.noise_frame_num_used_for_snr = 100; o.frame_in_ms = 10;
+  o.frame_length_ms = 25; o.speech_2_noise_ratio = 1.0; o.snr_thres = -100.0; o.decibel_thres = -100.0; o.speech_noise_thres = 0.6;
+  o.fe_prior_thres = 1e-4;
+  int32_t seg[16];
+  const int64_t n = fa_vad_detect_segments(sil, db, F, 400 + 160 * (F - 1), &o, 60000, 0, NULL, 0, NAN, seg, 8);
+  printf("segments %lld", (long long)n);
+  for (int i = 0; i < n && i < 8; ++i) printf(" [%d,%d]", seg[2 * i], seg[2 * i + 1]);
+  printf("\n");
+  printf("bad %lld\n", (long long)fa_vad_detect_segments(sil, db, F, 48000, NULL, 60000, 0, NULL, 0, NAN, seg, 8));
+  return 0;
+}
+''')
+    exe = str(tmp_path / "host_calls")
+    libdir = os.path.join(ROOT, "funasr_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src),
+                        "-L" + libdir, "-lfunasr_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    lines = run.stdout.strip().splitlines()
+    from funasr_b200 import timestamps as TS, vad
+    want_tr = TS.cif_wo_hidden_py(np.array([0.4, 0.7, 0.2, 0.9, 0.05], np.float32), 1.0)
+    assert lines[0] == "trace " + " ".join("%.6f" % v for v in want_tr)
+    sil = [0.05 if 60 <= i < 200 else 0.95 for i in range(300)]
+    want = vad.detect_segments(sil, [0.0] * 300, 400 + 160 * 299, max_end_silence_time=800)
+    assert want and lines[1] == "segments %d" % len(want) + "".join(" [%d,%d]" % (s, e) for s, e in want)
+    assert lines[2] == "bad -1"
